@@ -1,0 +1,299 @@
+// norm.cu — GroupNorm (+SiLU, +dropout) forward/backward over NHWC views.  HBM-bound: every kernel reads rows
+// of C contiguous floats (coalesced), each thread owns fixed channel(s) so per-channel scale/shift live in
+// registers, and all cross-block reductions go through fixed-order partial buffers (no atomics).
+#include "common.cuh"
+
+namespace {
+constexpr int NT = 256;
+constexpr int MAXCPT = 4;  // channels per thread when C > 256 (C <= 1024)
+
+struct Map {  // thread -> (channel slot, pixel lane)
+  int CT, PL, PPC, nchunks;
+};
+static inline Map make_map(int HW, int C) {
+  Map m;
+  if (C >= NT) { m.CT = NT; m.PL = 1; }
+  else { int ct = 32; while (ct < C) ct <<= 1; m.CT = ct; m.PL = NT / ct; }
+  int ppc = 8192 / C; if (ppc < m.PL) ppc = m.PL; if (ppc > HW) ppc = HW; if (ppc < 1) ppc = 1;
+  m.PPC = ppc; m.nchunks = (HW + ppc - 1) / ppc;
+  return m;
+}
+
+__device__ __forceinline__ float keep_scale(uint64_t seed, uint64_t idx, float p) {
+  // counter-based hash (splitmix64) -> uniform in [0,1); keep if u >= p, scaled by 1/(1-p)
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  float u = (float)(z >> 40) * (1.0f / 16777216.0f);
+  return u >= p ? 1.0f / (1.0f - p) : 0.0f;
+}
+
+__global__ void __launch_bounds__(NT) gn_stats_kernel(const dp_gn_args a, const Map mp, double* __restrict__ ws) {
+  extern __shared__ double sh[];  // [2][PL*CT or C]
+  const int n = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+  const int ct = tid % mp.CT, pl = tid / mp.CT;
+  const int p0 = chunk * mp.PPC, p1 = min(a.HW, p0 + mp.PPC);
+  double s[MAXCPT] = {0, 0, 0, 0}, q[MAXCPT] = {0, 0, 0, 0};
+  const float* xb = a.x + (long long)n * a.HW * a.ldx;
+  for (int pix = p0 + pl; pix < p1; pix += mp.PL) {
+    const float* row = xb + (long long)pix * a.ldx;
+#pragma unroll
+    for (int u = 0; u < MAXCPT; ++u) {
+      int c = ct + u * NT;
+      if (c < a.C) { float v = __ldg(row + c); s[u] += v; q[u] += (double)v * v; }
+    }
+  }
+  const int slots = (a.C > NT) ? a.C : mp.PL * mp.CT;
+  double* shs = sh; double* shq = sh + slots;
+  if (a.C > NT) {
+#pragma unroll
+    for (int u = 0; u < MAXCPT; ++u) { int c = ct + u * NT; if (c < a.C) { shs[c] = s[u]; shq[c] = q[u]; } }
+  } else { shs[pl * mp.CT + ct] = s[0]; shq[pl * mp.CT + ct] = q[0]; }
+  __syncthreads();
+  const int cpg = a.C / a.G;
+  for (int g = tid; g < a.G; g += NT) {
+    double ts = 0, tq = 0;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      if (a.C > NT) { ts += shs[c]; tq += shq[c]; }
+      else for (int l = 0; l < mp.PL; ++l) { ts += shs[l * mp.CT + c]; tq += shq[l * mp.CT + c]; }
+    }
+    double* o = ws + (((long long)n * mp.nchunks + chunk) * a.G + g) * 2;
+    o[0] = ts; o[1] = tq;
+  }
+}
+
+__global__ void gn_finalize_kernel(const dp_gn_args a, const Map mp, const double* __restrict__ ws) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;  // (n, g)
+  if (i >= a.N * a.G) return;
+  int n = i / a.G, g = i - n * a.G;
+  double ts = 0, tq = 0;
+  for (int ch = 0; ch < mp.nchunks; ++ch) {
+    const double* o = ws + (((long long)n * mp.nchunks + ch) * a.G + g) * 2;
+    ts += o[0]; tq += o[1];
+  }
+  double m = (double)a.HW * (a.C / a.G);
+  double mean = ts / m, var = tq / m - mean * mean;
+  if (var < 0) var = 0;
+  a.mean[i] = (float)mean;
+  a.rstd[i] = (float)(1.0 / sqrt(var + (double)a.eps));
+}
+
+__global__ void __launch_bounds__(NT) gn_apply_kernel(const dp_gn_args a, const Map mp) {
+  const int n = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+  const int ct = tid % mp.CT, pl = tid / mp.CT;
+  const int p0 = chunk * mp.PPC, p1 = min(a.HW, p0 + mp.PPC);
+  const int cpg = a.C / a.G;
+  float sc[MAXCPT], shf[MAXCPT];
+#pragma unroll
+  for (int u = 0; u < MAXCPT; ++u) {
+    int c = ct + u * NT;
+    if (c < a.C) {
+      int g = c / cpg;
+      float mu = a.mean[n * a.G + g], rs = a.rstd[n * a.G + g];
+      float ga = __ldg(a.gamma + c), be = __ldg(a.beta + c);
+      sc[u] = rs * ga; shf[u] = be - mu * rs * ga;
+    } else { sc[u] = 0.f; shf[u] = 0.f; }
+  }
+  const float* xb = a.x + (long long)n * a.HW * a.ldx;
+  float* yb = a.y + (long long)n * a.HW * a.ldy;
+  for (int pix = p0 + pl; pix < p1; pix += mp.PL) {
+    const float* row = xb + (long long)pix * a.ldx;
+    float* orow = yb + (long long)pix * a.ldy;
+#pragma unroll
+    for (int u = 0; u < MAXCPT; ++u) {
+      int c = ct + u * NT;
+      if (c < a.C) {
+        float y = fmaf(__ldg(row + c), sc[u], shf[u]);
+        if (a.silu) y = y * sigmoidf_acc(y);
+        if (a.dropout_p > 0.f) y *= keep_scale(a.dropout_seed + (a.dropout_seed_dev ? *a.dropout_seed_dev : 0ull), ((uint64_t)n * a.HW + pix) * a.C + c, a.dropout_p);
+        orow[c] = y;
+      }
+    }
+  }
+}
+
+// ---- backward ----
+__device__ __forceinline__ float gn_dy(const dp_gn_args& a, float dA, float y, uint64_t eidx) {
+  float g = dA;
+  if (a.dropout_p > 0.f) g *= keep_scale(a.dropout_seed + (a.dropout_seed_dev ? *a.dropout_seed_dev : 0ull), eidx, a.dropout_p);
+  if (a.silu) { float s = sigmoidf_acc(y); g *= s * (1.f + y * (1.f - s)); }
+  return g;
+}
+
+__global__ void __launch_bounds__(NT) gn_bwd_partial_kernel(const dp_gn_args a, const Map mp, float* __restrict__ part) {
+  extern __shared__ float shf32[];  // [2][PL*CT]   (only used when C <= NT)
+  const int n = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+  const int ct = tid % mp.CT, pl = tid / mp.CT;
+  const int p0 = chunk * mp.PPC, p1 = min(a.HW, p0 + mp.PPC);
+  const int cpg = a.C / a.G;
+  float mu[MAXCPT], rs[MAXCPT], ga[MAXCPT], be[MAXCPT], s1[MAXCPT], s2[MAXCPT];
+#pragma unroll
+  for (int u = 0; u < MAXCPT; ++u) {
+    int c = ct + u * NT; s1[u] = 0.f; s2[u] = 0.f;
+    if (c < a.C) { int g = c / cpg; mu[u] = a.mean[n * a.G + g]; rs[u] = a.rstd[n * a.G + g]; ga[u] = __ldg(a.gamma + c); be[u] = __ldg(a.beta + c); }
+    else { mu[u] = rs[u] = ga[u] = be[u] = 0.f; }
+  }
+  const float* xb = a.x + (long long)n * a.HW * a.ldx;
+  const float* db = a.dy + (long long)n * a.HW * a.lddy;
+  for (int pix = p0 + pl; pix < p1; pix += mp.PL) {
+#pragma unroll
+    for (int u = 0; u < MAXCPT; ++u) {
+      int c = ct + u * NT;
+      if (c < a.C) {
+        float xh = (__ldg(xb + (long long)pix * a.ldx + c) - mu[u]) * rs[u];
+        float y = fmaf(xh, ga[u], be[u]);
+        float g = gn_dy(a, __ldg(db + (long long)pix * a.lddy + c), y, ((uint64_t)n * a.HW + pix) * a.C + c);
+        s1[u] += g; s2[u] += g * xh;
+      }
+    }
+  }
+  float* o = part + ((long long)n * mp.nchunks + chunk) * 2 * a.C;
+  if (a.C > NT) {
+#pragma unroll
+    for (int u = 0; u < MAXCPT; ++u) { int c = ct + u * NT; if (c < a.C) { o[c] = s1[u]; o[a.C + c] = s2[u]; } }
+  } else {
+    float* sa = shf32; float* sb = shf32 + mp.PL * mp.CT;
+    sa[pl * mp.CT + ct] = s1[0]; sb[pl * mp.CT + ct] = s2[0];
+    __syncthreads();
+    if (pl == 0 && ct < a.C) {
+      float t1 = 0.f, t2 = 0.f;
+      for (int l = 0; l < mp.PL; ++l) { t1 += sa[l * mp.CT + ct]; t2 += sb[l * mp.CT + ct]; }
+      o[ct] = t1; o[a.C + ct] = t2;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NT) gn_bwd_finalize_kernel(const dp_gn_args a, const Map mp, const float* __restrict__ part,
+                                                             float* __restrict__ fin, float* __restrict__ coef) {
+  extern __shared__ float shc[];  // [2][C] gamma-weighted sums
+  const int n = blockIdx.x, tid = threadIdx.x;
+  for (int c = tid; c < a.C; c += NT) {
+    double t1 = 0, t2 = 0;
+    for (int ch = 0; ch < mp.nchunks; ++ch) {
+      const float* o = part + ((long long)n * mp.nchunks + ch) * 2 * a.C;
+      t1 += o[c]; t2 += o[a.C + c];
+    }
+    fin[((long long)n * 2) * a.C + c] = (float)t1;
+    fin[((long long)n * 2 + 1) * a.C + c] = (float)t2;
+    float ga = __ldg(a.gamma + c);
+    shc[c] = (float)t1 * ga; shc[a.C + c] = (float)t2 * ga;
+  }
+  __syncthreads();
+  const int cpg = a.C / a.G;
+  const double inv_m = 1.0 / ((double)a.HW * cpg);
+  for (int g = tid; g < a.G; g += NT) {
+    double u1 = 0, u2 = 0;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) { u1 += shc[c]; u2 += shc[a.C + c]; }
+    coef[((long long)n * a.G + g) * 2] = (float)(u1 * inv_m);
+    coef[((long long)n * a.G + g) * 2 + 1] = (float)(u2 * inv_m);
+  }
+}
+
+__global__ void gn_bwd_param_kernel(const dp_gn_args a, const float* __restrict__ fin) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.C) return;
+  double tb = 0, tg = 0;
+  for (int n = 0; n < a.N; ++n) { tb += fin[((long long)n * 2) * a.C + c]; tg += fin[((long long)n * 2 + 1) * a.C + c]; }
+  if (a.dbeta) a.dbeta[c] += (float)tb;
+  if (a.dgamma) a.dgamma[c] += (float)tg;
+}
+
+__global__ void __launch_bounds__(NT) gn_bwd_apply_kernel(const dp_gn_args a, const Map mp, const float* __restrict__ coef) {
+  const int n = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+  const int ct = tid % mp.CT, pl = tid / mp.CT;
+  const int p0 = chunk * mp.PPC, p1 = min(a.HW, p0 + mp.PPC);
+  const int cpg = a.C / a.G;
+  float mu[MAXCPT], rs[MAXCPT], ga[MAXCPT], be[MAXCPT], c1[MAXCPT], c2[MAXCPT];
+#pragma unroll
+  for (int u = 0; u < MAXCPT; ++u) {
+    int c = ct + u * NT;
+    if (c < a.C) {
+      int g = c / cpg; mu[u] = a.mean[n * a.G + g]; rs[u] = a.rstd[n * a.G + g]; ga[u] = __ldg(a.gamma + c); be[u] = __ldg(a.beta + c);
+      c1[u] = coef[((long long)n * a.G + g) * 2]; c2[u] = coef[((long long)n * a.G + g) * 2 + 1];
+    } else { mu[u] = rs[u] = ga[u] = be[u] = c1[u] = c2[u] = 0.f; }
+  }
+  const float* xb = a.x + (long long)n * a.HW * a.ldx;
+  const float* db = a.dy + (long long)n * a.HW * a.lddy;
+  float* ob = a.dx + (long long)n * a.HW * a.lddx;
+  const float* ab = a.dx_add ? a.dx_add + (long long)n * a.HW * a.ldadd : nullptr;
+  const float* ab2 = a.dx_add2 ? a.dx_add2 + (long long)n * a.HW * a.ldadd2 : nullptr;
+  for (int pix = p0 + pl; pix < p1; pix += mp.PL) {
+#pragma unroll
+    for (int u = 0; u < MAXCPT; ++u) {
+      int c = ct + u * NT;
+      if (c < a.C) {
+        float xh = (__ldg(xb + (long long)pix * a.ldx + c) - mu[u]) * rs[u];
+        float y = fmaf(xh, ga[u], be[u]);
+        float g = gn_dy(a, __ldg(db + (long long)pix * a.lddy + c), y, ((uint64_t)n * a.HW + pix) * a.C + c);
+        float d = rs[u] * (ga[u] * g - c1[u] - xh * c2[u]);
+        if (ab) d += ab[(long long)pix * a.ldadd + c];
+        if (ab2) d += ab2[(long long)pix * a.ldadd2 + c];
+        ob[(long long)pix * a.lddx + c] = d;
+      }
+    }
+  }
+}
+
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+}  // namespace
+
+extern "C" size_t dp_groupnorm_workspace_bytes(int32_t N, int32_t HW, int32_t C, int32_t G) {
+  if (N <= 0 || HW <= 0 || C <= 0 || G <= 0) return 0;
+  Map mp = make_map(HW, C);
+  size_t fwd = (size_t)N * mp.nchunks * G * 2 * sizeof(double);
+  size_t bwd = align256((size_t)N * mp.nchunks * 2 * C * sizeof(float)) + align256((size_t)N * 2 * C * sizeof(float)) +
+               align256((size_t)N * G * 2 * sizeof(float));
+  return align256(fwd > bwd ? fwd : bwd);
+}
+
+static int gn_validate(const dp_gn_args* a) {
+  DP_REQUIRE(a && a->x && a->gamma && a->beta && a->mean && a->rstd && a->workspace, DP_ERR_NULL);
+  DP_REQUIRE(a->N > 0 && a->HW > 0 && a->C > 0 && a->G > 0 && a->C % a->G == 0, DP_ERR_SHAPE);
+  DP_REQUIRE(a->C <= NT * MAXCPT && a->G <= 1024, DP_ERR_UNSUPPORTED);
+  DP_REQUIRE(a->N <= 65535, DP_ERR_SHAPE);
+  DP_REQUIRE(a->ldx >= a->C, DP_ERR_SHAPE);
+  DP_REQUIRE(a->dropout_p >= 0.f && a->dropout_p < 1.f, DP_ERR_SHAPE);
+  return DP_OK;
+}
+
+extern "C" int dp_groupnorm_fwd(const dp_gn_args* a, dp_stream_t stream) {
+  int rc = gn_validate(a);
+  if (rc) return rc;
+  DP_REQUIRE(a->y, DP_ERR_NULL);
+  DP_REQUIRE(a->ldy >= a->C, DP_ERR_SHAPE);
+  cudaStream_t st = (cudaStream_t)stream;
+  Map mp = make_map(a->HW, a->C);
+  dim3 grid(mp.nchunks, a->N);
+  int slots = (a->C > NT) ? a->C : mp.PL * mp.CT;
+  gn_stats_kernel<<<grid, NT, 2 * slots * sizeof(double), st>>>(*a, mp, (double*)a->workspace);
+  if ((rc = dp_check_launch())) return rc;
+  gn_finalize_kernel<<<(a->N * a->G + 127) / 128, 128, 0, st>>>(*a, mp, (const double*)a->workspace);
+  if ((rc = dp_check_launch())) return rc;
+  gn_apply_kernel<<<grid, NT, 0, st>>>(*a, mp);
+  return dp_check_launch();
+}
+
+extern "C" int dp_groupnorm_bwd(const dp_gn_args* a, dp_stream_t stream) {
+  int rc = gn_validate(a);
+  if (rc) return rc;
+  DP_REQUIRE(a->dy && a->dx, DP_ERR_NULL);
+  DP_REQUIRE(a->lddy >= a->C && a->lddx >= a->C, DP_ERR_SHAPE);
+  cudaStream_t st = (cudaStream_t)stream;
+  Map mp = make_map(a->HW, a->C);
+  char* ws = (char*)a->workspace;
+  float* part = (float*)ws;
+  float* fin = (float*)(ws + align256((size_t)a->N * mp.nchunks * 2 * a->C * sizeof(float)));
+  float* coef = (float*)((char*)fin + align256((size_t)a->N * 2 * a->C * sizeof(float)));
+  dim3 grid(mp.nchunks, a->N);
+  gn_bwd_partial_kernel<<<grid, NT, 2 * mp.PL * mp.CT * sizeof(float), st>>>(*a, mp, part);
+  if ((rc = dp_check_launch())) return rc;
+  gn_bwd_finalize_kernel<<<a->N, NT, 2 * a->C * sizeof(float), st>>>(*a, mp, part, fin, coef);
+  if ((rc = dp_check_launch())) return rc;
+  if (a->dgamma || a->dbeta) {
+    gn_bwd_param_kernel<<<(a->C + 127) / 128, 128, 0, st>>>(*a, fin);
+    if ((rc = dp_check_launch())) return rc;
+  }
+  gn_bwd_apply_kernel<<<grid, NT, 0, st>>>(*a, mp, coef);
+  return dp_check_launch();
+}

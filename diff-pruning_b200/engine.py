@@ -1,0 +1,708 @@
+"""Planned sm_100a executor for the UNet2DModel forward + backward (the Taylor-scoring / finetune hot path).
+
+Instead of dispatching ~1000 ATen ops per pass through autograd (ddpm_prune.py:100-102 ->
+unet_2d.py:219 -> autograd), the engine walks the module tree ONCE per (batch, resolution), lays every
+activation / gradient out in HBM as fp32 NHWC views, and records two static launch lists (forward, backward)
+of libdpb200 C-ABI calls with pre-built argument structs.  Static shapes + no allocation + no sync make the
+whole pass CUDA-graph capturable (scoring.py does that).
+
+HBM layout decisions:
+  * NHWC fp32 activations so an implicit-GEMM conv reads K-contiguous rows; weights packed K-major per tap.
+  * torch.cat([h, skip]) (unet_2d_blocks.py:1822,2035) never copies: the skip tensor and the up-path tensor
+    are written by their producers straight into the two channel ranges of one wider buffer (views with a
+    pixel stride), and so are their gradients.
+  * residual adds, bias adds and the per-image temb add are conv epilogues; GroupNorm backward takes the
+    residual-branch gradient as an addend; the 1x1 shortcut accumulates in place; dW accumulates into the
+    Parameter.grad arena across timesteps (ddpm_prune.py:102 has no zero_grad in the loop).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Callable, Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from .models import (Attention, Downsample2D, ResnetBlock2D, UNet2DModel, Upsample2D, sinusoidal_frequencies)
+
+_byref = C.byref
+Step = Callable[[int], None]
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class View:
+    """fp32 NHWC view: channels [off, off+C) of a contiguous (N, H, W, Ctot) buffer."""
+    __slots__ = ("t", "N", "H", "W", "C", "off", "ld", "g")
+
+    def __init__(self, t: torch.Tensor, off: int = 0, C_: Optional[int] = None):
+        assert t.dim() == 4 and t.is_contiguous() and t.dtype == torch.float32
+        self.t = t
+        self.N, self.H, self.W, self.ld = t.shape
+        self.off = off
+        self.C = self.ld - off if C_ is None else C_
+        self.g: Optional["View"] = None
+
+    @property
+    def ptr(self) -> int:
+        return self.t.data_ptr() + 4 * self.off
+
+    @property
+    def rows(self) -> int:
+        return self.N * self.H * self.W
+
+    def torch(self) -> torch.Tensor:
+        return self.t[..., self.off:self.off + self.C]
+
+
+class BItem:
+    """Backward work of one forward op: launches in execution order + the gradient views it writes."""
+    __slots__ = ("steps", "writes")
+
+    def __init__(self):
+        self.steps: List[Step] = []
+        self.writes: List[Tuple[View, Callable[[bool], None]]] = []
+
+
+def _copy_args(a):
+    b = type(a)()
+    C.memmove(C.byref(b), C.byref(a), C.sizeof(a))
+    return b
+
+
+class Plan:
+    """Static forward/backward launch lists for one (model, batch, H, W)."""
+
+    def __init__(self, model: UNet2DModel, batch: int, height: int, width: int, device, training: bool = False,
+                 need_grad: bool = True):
+        self.lib = L.load()
+        self.model = model
+        self.B, self.H, self.W = batch, height, width
+        self.dev = torch.device(device)
+        self.need_grad = need_grad
+        self.training = training
+        self.fwd: List[Step] = []
+        self.bwd: List[BItem] = []      # appended in forward order, executed reversed
+        self.pack: List[Step] = []      # weight packing launches (re-run when weights change)
+        self._keep: list = []           # tensors / structs that must stay alive
+        self._ginit: set = set()
+        self._gbuf: Dict[int, torch.Tensor] = {}
+        self._scratch: Dict[str, torch.Tensor] = {}
+        self._scratch_need: Dict[str, int] = {}
+        self._late: List[Callable[[], None]] = []   # pointer fix-ups once scratch buffers exist
+        self._packs: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
+        self.params = [p for p in model.parameters()]
+        self.dropout_seed_dev = torch.zeros(1, device=self.dev, dtype=torch.int64)
+        self._n_dropout = 0
+        self._build()
+
+    # ------------------------------------------------------------------ memory helpers
+    def new(self, N, H, W, C_) -> View:
+        t = torch.empty((N, H, W, C_), device=self.dev, dtype=torch.float32)
+        self._keep.append(t)
+        return View(t)
+
+    def gradof(self, v: View) -> View:
+        """Gradient view mirroring v (same buffer geometry, so concat views stay views)."""
+        if v.g is None:
+            gt = self._gbuf.get(v.t.data_ptr())
+            if gt is None:
+                gt = torch.empty_like(v.t)
+                self._gbuf[v.t.data_ptr()] = gt
+            v.g = View(gt, v.off, v.C)
+        return v.g
+
+    def g_is_init(self, v: View) -> bool:
+        g = self.gradof(v)
+        p = g.t.data_ptr()
+        return any(q == p and off <= g.off and g.off + g.C <= off + c for (q, off, c) in self._ginit)
+
+    def g_mark(self, v: View):
+        g = self.gradof(v)
+        self._ginit.add((g.t.data_ptr(), g.off, g.C))
+
+    def scratch(self, name: str, nfloats: int) -> str:
+        """Shared temporary (always consumed right after it is produced)."""
+        self._scratch_need[name] = max(self._scratch_need.get(name, 0), int(nfloats))
+        return name
+
+    def sptr(self, name: str) -> int:
+        return self._scratch[name].data_ptr()
+
+    # ------------------------------------------------------------------ parameter plumbing
+    def pgrad(self, p: nn.Parameter) -> int:
+        return self._grad_views[id(p)].data_ptr()
+
+    def _setup_param_grads(self):
+        total = sum(p.numel() for p in self.params)
+        self.grad_arena = torch.zeros(total, device=self.dev, dtype=torch.float32)
+        self._grad_views = {}
+        o = 0
+        for p in self.params:
+            self._grad_views[id(p)] = self.grad_arena[o:o + p.numel()].view_as(p)
+            o += p.numel()
+
+    def attach_grads(self):
+        """Make every Parameter.grad the plan's arena view (accumulating semantics are preserved)."""
+        for p in self.params:
+            gv = self._grad_views[id(p)]
+            if p.grad is None:
+                gv.zero_()
+                p.grad = gv
+            elif p.grad.data_ptr() != gv.data_ptr():
+                gv.copy_(p.grad)
+                p.grad = gv
+
+    def signature(self):
+        return tuple((p.data_ptr(), tuple(p.shape)) for p in self.params)
+
+    def weight_version(self):
+        return sum(p._version for p in self.params)
+
+    # ------------------------------------------------------------------ launch recording
+    def _rec(self, lst: List[Step], fn, args=None, what=""):
+        check = L.check
+        if args is not None:
+            self._keep.append(args)
+            ref = _byref(args)
+
+            def run(s, fn=fn, ref=ref, what=what):
+                rc = fn(ref, s)
+                if rc:
+                    check(rc, what)
+        else:
+            def run(s, fn=fn, what=what):
+                rc = fn(s)
+                if rc:
+                    check(rc, what)
+        lst.append(run)
+
+    def _bitem(self) -> BItem:
+        it = BItem()
+        self.bwd.append(it)
+        return it
+
+    # ------------------------------------------------------------------ op emitters
+    def _packed(self, w: nn.Parameter):
+        """(w_ck, w_kc): K-major packed copies of an OIHW / (out,in) weight; the packing launch is recorded once."""
+        got = self._packs.get(id(w))
+        if got is not None:
+            return got
+        K, Cin = w.shape[0], w.shape[1]
+        R = w.shape[2] if w.dim() == 4 else 1
+        S = w.shape[3] if w.dim() == 4 else 1
+        wck = torch.empty(w.numel(), device=self.dev, dtype=torch.float32)
+        wkc = torch.empty(w.numel(), device=self.dev, dtype=torch.float32)
+        lib = self.lib
+        self._rec(self.pack, lambda s, w=w, K=K, Cin=Cin, R=R, S=S, a=wck, b=wkc:
+                  lib.dp_pack_conv_weight(w.data_ptr(), K, Cin, R, S, a.data_ptr(), b.data_ptr(), s), what="pack")
+        self._packs[id(w)] = (wck, wkc)
+        return wck, wkc
+
+    def _colsum_tree(self, steps: List[Step], src_ptr: int, ld: int, rows: int, per_img: int, cols: int,
+                     seg_name: Optional[str]) -> str:
+        """Deterministic hierarchical column sums of a [rows][cols] view down to per-image sums (dense [N][cols]);
+        returns the scratch name holding them."""
+        lib = self.lib
+        get = (lambda p=src_ptr: p)
+        cur_ld, cur_rows, cur_per, level = ld, rows, per_img, 0
+        while True:
+            s_rows = 256 if (cur_per > 256 and cur_per % 256 == 0) else cur_per
+            nseg = cur_rows // s_rows
+            last = cur_per == s_rows
+            out_name = seg_name if (last and seg_name) else ("cs_a", "cs_b")[level & 1]
+            self.scratch(out_name, nseg * cols)
+            self._rec(steps, lambda s, g=get, ld_=cur_ld, r=cur_rows, sr=s_rows, o=out_name:
+                      lib.dp_colsum(g(), ld_, r, cols, sr, self.sptr(o), cols, 0, s), what="colsum")
+            get = (lambda o=out_name: self.sptr(o))
+            cur_ld, cur_rows, cur_per = cols, nseg, cur_per // s_rows
+            level += 1
+            if last:
+                return out_name
+
+    def conv(self, x: View, w: nn.Parameter, b: Optional[nn.Parameter], out: View, stride=1, pad=1,
+             rowadd: Optional[View] = None, residual: Optional[View] = None, accumulate_out=False, need_dx=True,
+             dx_scratch: Optional[str] = None, seg_out: Optional[str] = None, dy_dense: Optional[str] = None,
+             dx_into: Optional[View] = None):
+        """Records fprop (fwd) and bias-grad / wgrad / dgrad (bwd).
+        dgrad target: `dx_scratch` (shared dense scratch [rows][C]) or the gradient view of `dx_into` / `x`.
+        dy source: out.grad, or the dense scratch `dy_dense` ([rows][K]) when the consumer provides it."""
+        lib = self.lib
+        K, Cin = w.shape[0], w.shape[1]
+        R = w.shape[2] if w.dim() == 4 else 1
+        S = w.shape[3] if w.dim() == 4 else 1
+        assert x.C == Cin and out.C == K, (x.C, Cin, out.C, K)
+        wck, wkc = self._packed(w)
+        a = L.ConvArgs()
+        a.N, a.H, a.W, a.C = x.N, x.H, x.W, x.C
+        a.P, a.Q, a.K = out.H, out.W, K
+        a.R, a.S, a.stride, a.pad_t, a.pad_l = R, S, stride, pad, pad
+        a.flags = 1 if accumulate_out else 0
+        a.splits = 1
+        a.x, a.ldx, a.y, a.ldy = x.ptr, x.ld, out.ptr, out.ld
+        a.w = wck.data_ptr()
+        a.bias = b.data_ptr() if b is not None else None
+        if rowadd is not None:
+            a.rowadd, a.ld_rowadd = rowadd.ptr, rowadd.ld
+        if residual is not None:
+            a.residual, a.ld_res = residual.ptr, residual.ld
+        self._rec(self.fwd, lib.dp_conv2d_fprop, a, "conv fprop")
+        if not self.need_grad:
+            return
+        it = self._bitem()
+        steps = it.steps
+        if dy_dense is not None:
+            self.scratch(dy_dense, out.rows * K)
+            dy_get, dy_ld = (lambda n=dy_dense: self.sptr(n)), K
+        else:
+            dout = self.gradof(out)
+            dy_get, dy_ld = (lambda p=dout.ptr: p), dout.ld
+        # 1. bias gradient (and per-image sums for the caller when seg_out is set)
+        if b is not None or seg_out is not None:
+            if dy_dense is not None and out.H * out.W == 1:
+                seg = dy_dense  # already dense per-image rows
+            else:
+                seg = None
+            if seg is None:
+                # src pointer may be late-bound (dense scratch) -> wrap
+                if dy_dense is not None:
+                    raise NotImplementedError("dense dy with spatial extent")
+                seg = self._colsum_tree(steps, dout.ptr, dout.ld, out.rows, out.H * out.W, K, seg_out)
+            if b is not None:
+                self._rec(steps, lambda s, seg=seg, b=b, n=x.N: lib.dp_colsum(self.sptr(seg), K, n, K, n, self.pgrad(b), K, 1, s),
+                          what="bias grad")
+        # 2. wgrad -> split-K workspace -> fixed-order reduce into Parameter.grad
+        TC = R * S * Cin
+        tiles = ((K + 127) // 128) * ((TC + 127) // 128)
+        splits = max(1, min((592 + tiles - 1) // tiles, (out.rows + 511) // 512))
+        self.scratch("wgrad_ws", splits * K * TC)
+        wa = _copy_args(a)
+        wa.flags, wa.splits = 0, splits
+        wa.ldy = dy_ld
+        wa.rowadd, wa.residual, wa.bias = None, None, None
+        self._late.append(lambda wa=wa, g=dy_get: (setattr(wa, "y", g()), setattr(wa, "workspace", self.sptr("wgrad_ws"))))
+        self._rec(steps, lib.dp_conv2d_wgrad, wa, "conv wgrad")
+        ra = L.WgradReduceArgs()
+        ra.K, ra.C, ra.R, ra.S, ra.splits = K, Cin, R, S, splits
+        ra.dw = self.pgrad(w)
+        self._late.append(lambda ra=ra: setattr(ra, "workspace", self.sptr("wgrad_ws")))
+        self._rec(steps, lib.dp_conv2d_wgrad_reduce, ra, "wgrad reduce")
+        # 3. dgrad
+        if need_dx:
+            da = _copy_args(a)
+            da.ldy = dy_ld
+            da.w = wkc.data_ptr()
+            da.flags = 0
+            da.rowadd, da.residual, da.bias = None, None, None
+            self._late.append(lambda da=da, g=dy_get: setattr(da, "y", g()))
+            if dx_scratch is not None:
+                self.scratch(dx_scratch, x.rows * x.C)
+                da.ldx = x.C
+                self._late.append(lambda da=da, n=dx_scratch: setattr(da, "x", self.sptr(n)))
+            else:
+                tgt = dx_into if dx_into is not None else x
+                gx = self.gradof(tgt)
+                da.x, da.ldx = gx.ptr, gx.ld
+                it.writes.append((tgt, lambda init, da=da: setattr(da, "flags", 1 if init else 0)))
+            self._rec(steps, lib.dp_conv2d_dgrad, da, "conv dgrad")
+
+    def gn(self, x: View, norm: nn.GroupNorm, out: View, silu: bool, dropout_p: float = 0.0):
+        """fwd: out = dropout?(silu?(GN(x))).  Returns the fwd args (the backward reuses stats / dropout seed)."""
+        lib = self.lib
+        a = L.GnArgs()
+        a.N, a.HW, a.C, a.G = x.N, x.H * x.W, x.C, norm.num_groups
+        a.eps, a.silu = norm.eps, 1 if silu else 0
+        a.x, a.ldx, a.y, a.ldy = x.ptr, x.ld, out.ptr, out.ld
+        a.gamma, a.beta = norm.weight.data_ptr(), norm.bias.data_ptr()
+        stats = torch.empty(2 * x.N * norm.num_groups, device=self.dev, dtype=torch.float32)
+        self._keep.append(stats)
+        a.mean, a.rstd = stats.data_ptr(), stats.data_ptr() + 4 * x.N * norm.num_groups
+        if dropout_p > 0:
+            self._n_dropout += 1
+            a.dropout_p = dropout_p
+            a.dropout_seed = 0x9E3779B97F4A7C15 * self._n_dropout & 0xFFFFFFFFFFFFFFFF
+            a.dropout_seed_dev = self.dropout_seed_dev.data_ptr()
+        self.scratch("gn_ws", (lib.dp_groupnorm_workspace_bytes(a.N, a.HW, a.C, a.G) + 3) // 4)
+        self._late.append(lambda a=a: setattr(a, "workspace", self.sptr("gn_ws")))
+        self._rec(self.fwd, lib.dp_groupnorm_fwd, a, "gn fwd")
+        return a
+
+    def gn_bwd(self, a_fwd, x: View, norm: nn.GroupNorm, dy_get: Callable[[], int], lddy: int,
+               add2: Optional[View] = None):
+        """x.grad (=|+=) GN(+SiLU)(+dropout) backward (+ add2); dgamma/dbeta += ."""
+        lib = self.lib
+        b = _copy_args(a_fwd)
+        gx = self.gradof(x)
+        b.dx, b.lddx, b.lddy = gx.ptr, gx.ld, lddy
+        if add2 is not None:
+            b.dx_add2, b.ldadd2 = add2.ptr, add2.ld
+        b.dgamma, b.dbeta = self.pgrad(norm.weight), self.pgrad(norm.bias)
+        self._late.append(lambda b=b: (setattr(b, "dy", dy_get()), setattr(b, "workspace", self.sptr("gn_ws"))))
+        it = self._bitem()
+
+        def resolve(init, b=b, gx=gx):
+            if init:
+                b.dx_add, b.ldadd = gx.ptr, gx.ld
+        it.writes.append((x, resolve))
+        self._rec(it.steps, lib.dp_groupnorm_bwd, b, "gn bwd")
+
+    # ------------------------------------------------------------------ blocks
+    def resnet(self, m: ResnetBlock2D, x: View, out: View):
+        """ResnetBlock2D.forward — resnet.py:589-639."""
+        assert m.output_scale_factor == 1.0, "output_scale_factor != 1 is outside the DDPM configs"
+        Cout = m.conv1.out_channels
+        p_drop = float(m.dropout.p) if (self.training and m.dropout.p > 0) else 0.0
+        a1 = self.new(x.N, x.H, x.W, x.C)
+        h1 = self.new(x.N, x.H, x.W, Cout)
+        a2 = self.new(x.N, x.H, x.W, Cout)
+        tp = self.new(self.B, 1, 1, Cout)
+        has_sc = m.conv_shortcut is not None
+        da = lambda: self.sptr("da")
+        g1 = self.gn(x, m.norm1, a1, silu=True)
+        if self.need_grad:
+            self.gn_bwd(g1, x, m.norm1, da, x.C, add2=None if has_sc else self.gradof(out))
+        # time_emb_proj(silu(temb)) -> per-image row added in conv1's epilogue; its dY are conv1's per-image sums
+        self.conv(self.silu_temb, m.time_emb_proj.weight, m.time_emb_proj.bias, tp, pad=0, dy_dense="seg",
+                  dx_into=self.silu_temb)
+        self.conv(a1, m.conv1.weight, m.conv1.bias, h1, rowadd=tp, seg_out="seg", dx_scratch="da")
+        g2 = self.gn(h1, m.norm2, a2, silu=True, dropout_p=p_drop)
+        if self.need_grad:
+            self.gn_bwd(g2, h1, m.norm2, da, Cout)
+        if has_sc:
+            self.conv(a2, m.conv2.weight, m.conv2.bias, out, dx_scratch="da")
+            self.conv(x, m.conv_shortcut.weight, m.conv_shortcut.bias, out, pad=0, accumulate_out=True)
+        else:
+            self.conv(a2, m.conv2.weight, m.conv2.bias, out, residual=x, dx_scratch="da")
+
+    def attention(self, m: Attention, x: View, out: View):
+        """Attention + legacy AttnProcessor — attention_processor.py:415-470 (heads = 1, explicit stale scale)."""
+        lib = self.lib
+        if m.heads != 1:
+            raise NotImplementedError("multi-head attention blocks are outside the DDPM UNet2DModel configs (heads=1)")
+        assert m.rescale_output_factor == 1.0
+        N, H, W = x.N, x.H, x.W
+        T = H * W
+        inner = m.to_q.out_features
+        xn = self.new(N, H, W, x.C)
+        q, k, v, o = (self.new(N, H, W, inner) for _ in range(4))
+        P = torch.empty((N, T, T), device=self.dev, dtype=torch.float32)
+        self._keep.append(P)
+        g = self.gn(x, m.group_norm, xn, silu=False)
+        if self.need_grad:
+            self.gn_bwd(g, x, m.group_norm, lambda xn=xn: self.gradof(xn).ptr, x.C,
+                        add2=self.gradof(out) if m.residual_connection else None)
+        self.conv(xn, m.to_q.weight, m.to_q.bias, q, pad=0)
+        self.conv(xn, m.to_k.weight, m.to_k.bias, k, pad=0)
+        self.conv(xn, m.to_v.weight, m.to_v.bias, v, pad=0)
+
+        def gemm(M, Nn, Kd, A, a_rs, a_cs, a_bs, Bp, b_rs, b_cs, b_bs, Cp, ldc, c_bs, alpha):
+            ga = L.GemmArgs()
+            ga.M, ga.N, ga.Kd, ga.batch = M, Nn, Kd, N
+            ga.A, ga.a_rs, ga.a_cs, ga.a_bs = A, a_rs, a_cs, a_bs
+            ga.B, ga.b_rs, ga.b_cs, ga.b_bs = Bp, b_rs, b_cs, b_bs
+            ga.C, ga.ldc, ga.c_bs, ga.alpha, ga.accumulate = Cp, ldc, c_bs, alpha, 0
+            return ga
+        Pp, sc = P.data_ptr(), float(m.scale)
+        # S = scale * q k^T ; P = softmax(S) (in place) ; o = P v
+        self._rec(self.fwd, lib.dp_gemm_batched, gemm(T, T, inner, q.ptr, q.ld, 1, T * q.ld, k.ptr, 1, k.ld, T * k.ld,
+                                                      Pp, T, T * T, sc), "attn qk")
+        self._rec(self.fwd, lambda s: lib.dp_softmax_fwd(Pp, Pp, N * T, T, s), what="softmax")
+        self._rec(self.fwd, lib.dp_gemm_batched, gemm(T, inner, T, Pp, T, 1, T * T, v.ptr, v.ld, 1, T * v.ld,
+                                                      o.ptr, o.ld, T * o.ld, 1.0), "attn pv")
+        if self.need_grad:
+            dq, dk, dv, do = (self.gradof(t) for t in (q, k, v, o))
+            dP = torch.empty_like(P)
+            self._keep.append(dP)
+            dPp = dP.data_ptr()
+            it = self._bitem()
+            st = it.steps
+            # dV = P^T dO ; dP = dO V^T ; dS = P*(dP - rowsum(dP*P)) ; dQ = scale dS K ; dK = scale dS^T Q
+            self._rec(st, lib.dp_gemm_batched, gemm(T, inner, T, Pp, 1, T, T * T, do.ptr, do.ld, 1, T * do.ld,
+                                                    dv.ptr, dv.ld, T * dv.ld, 1.0), "attn dV")
+            self._rec(st, lib.dp_gemm_batched, gemm(T, T, inner, do.ptr, do.ld, 1, T * do.ld, v.ptr, 1, v.ld, T * v.ld,
+                                                    dPp, T, T * T, 1.0), "attn dP")
+            self._rec(st, lambda s: lib.dp_softmax_bwd(Pp, dPp, dPp, N * T, T, s), what="softmax bwd")
+            self._rec(st, lib.dp_gemm_batched, gemm(T, inner, T, dPp, T, 1, T * T, k.ptr, k.ld, 1, T * k.ld,
+                                                    dq.ptr, dq.ld, T * dq.ld, sc), "attn dQ")
+            self._rec(st, lib.dp_gemm_batched, gemm(T, inner, T, dPp, 1, T, T * T, q.ptr, q.ld, 1, T * q.ld,
+                                                    dk.ptr, dk.ld, T * dk.ld, sc), "attn dK")
+        self.conv(o, m.to_out[0].weight, m.to_out[0].bias, out, pad=0, residual=x if m.residual_connection else None)
+
+    # ------------------------------------------------------------------ whole network
+    def _build(self):
+        m, lib = self.model, self.lib
+        B, H, W = self.B, self.H, self.W
+        cfg = m.config
+        self._setup_param_grads()
+        # ---- inputs + timestep embedding chain (embeddings.py:22-62, 200-212)
+        self.t_dev = torch.zeros(B, device=self.dev, dtype=torch.int64)
+        self.x_in = self.new(B, H, W, cfg.in_channels)
+        half = cfg.block_out_channels[0] // 2
+        self.freqs = sinusoidal_frequencies(cfg.block_out_channels[0], cfg.freq_shift).to(self.dev)
+        te = m.time_embedding
+        temb0 = self.new(B, 1, 1, 2 * half)
+        l1, s1 = self.new(B, 1, 1, te.linear_1.out_features), self.new(B, 1, 1, te.linear_1.out_features)
+        emb = self.new(B, 1, 1, te.linear_2.out_features)
+        self.silu_temb = self.new(B, 1, 1, emb.C)
+        self._rec(self.fwd, lambda s: lib.dp_timestep_embedding(self.t_dev.data_ptr(), self.freqs.data_ptr(), temb0.ptr, B, half,
+                                                                1 if cfg.flip_sin_to_cos else 0, s), what="temb")
+        self.conv(temb0, te.linear_1.weight, te.linear_1.bias, l1, pad=0, need_dx=False)
+        n1, n2 = B * l1.C, B * emb.C
+        self._rec(self.fwd, lambda s: lib.dp_silu_fwd(l1.ptr, s1.ptr, n1, s), what="silu")
+        if self.need_grad:
+            self._rec(self._bitem().steps, lambda s: lib.dp_silu_bwd(l1.ptr, self.gradof(s1).ptr, self.gradof(l1).ptr, n1, 0, s),
+                      what="silu bwd")
+        self.conv(s1, te.linear_2.weight, te.linear_2.bias, emb, pad=0)
+        self._rec(self.fwd, lambda s: lib.dp_silu_fwd(emb.ptr, self.silu_temb.ptr, n2, s), what="silu")
+        if self.need_grad:
+            self._rec(self._bitem().steps,
+                      lambda s: lib.dp_silu_bwd(emb.ptr, self.gradof(self.silu_temb).ptr, self.gradof(emb).ptr, n2, 0, s),
+                      what="silu bwd")
+
+        # ---- skip/concat geometry: every skip lives in the upper channel range of its consumer's concat buffer
+        skip_shapes = []
+        ch, hh, ww = m.conv_in.out_channels, H, W
+        skip_shapes.append((hh, ww, ch))
+        for blk in m.down_blocks:
+            for r in blk.resnets:
+                ch = r.conv2.out_channels
+                skip_shapes.append((hh, ww, ch))
+            if blk.downsamplers is not None:
+                ch = blk.downsamplers[0].conv.out_channels
+                hh, ww = hh // 2, ww // 2
+                skip_shapes.append((hh, ww, ch))
+        consumers = [r for blk in m.up_blocks for r in blk.resnets]
+        assert len(consumers) == len(skip_shapes)
+        cat_total = [0] * len(skip_shapes)
+        for j, r in enumerate(consumers):
+            cat_total[len(skip_shapes) - 1 - j] = r.norm1.num_channels
+        counter = [0]
+
+        def new_skip() -> View:
+            i = counter[0]
+            counter[0] += 1
+            hh_, ww_, c = skip_shapes[i]
+            buf = self.new(B, hh_, ww_, cat_total[i])
+            assert cat_total[i] - c > 0
+            return View(buf.t, cat_total[i] - c, c)
+
+        def h_half(skip: View) -> View:   # channels [0, C_h) of the skip's concat buffer
+            return View(skip.t, 0, skip.off)
+
+        def cat_of(skip: View) -> View:
+            return View(skip.t, 0, skip.t.shape[-1])
+
+        x = new_skip()
+        self.conv(self.x_in, m.conv_in.weight, m.conv_in.bias, x, need_dx=False)
+        skips = [x]
+        for blk in m.down_blocks:
+            has_attn = getattr(blk, "has_attention", False)
+            for j, r in enumerate(blk.resnets):
+                if has_attn:
+                    mid = self.new(x.N, x.H, x.W, r.conv2.out_channels)
+                    self.resnet(r, x, mid)
+                    y = new_skip()
+                    self.attention(blk.attentions[j], mid, y)
+                else:
+                    y = new_skip()
+                    self.resnet(r, x, y)
+                x = y
+                skips.append(x)
+            if blk.downsamplers is not None:
+                d: Downsample2D = blk.downsamplers[0]
+                y = new_skip()
+                self.conv(x, d.conv.weight, d.conv.bias, y, stride=2, pad=d.padding)  # pad 0 => F.pad(0,1,0,1) folded
+                x = y
+                skips.append(x)
+
+        # ---- mid (its last op writes straight into the h-half of the first concat)
+        mb = m.mid_block
+        y = self.new(x.N, x.H, x.W, x.C)
+        self.resnet(mb.resnets[0], x, y)
+        x = y
+        if mb.attentions[0] is not None:
+            y = self.new(x.N, x.H, x.W, x.C)
+            self.attention(mb.attentions[0], x, y)
+            x = y
+        dest = h_half(skips[-1])
+        assert dest.C == x.C and dest.H == x.H, (dest.C, x.C)
+        self.resnet(mb.resnets[1], x, dest)
+
+        # ---- up
+        nblk = len(m.up_blocks)
+        for bi, blk in enumerate(m.up_blocks):
+            has_attn = getattr(blk, "has_attention", False)
+            nres = len(blk.resnets)
+            for j, r in enumerate(blk.resnets):
+                cat = cat_of(skips.pop())
+                if j < nres - 1:
+                    dest = h_half(skips[-1])
+                else:  # feeds the upsampler or the output head
+                    dest = self.new(cat.N, cat.H, cat.W, r.conv2.out_channels)
+                    assert blk.upsamplers is not None or bi == nblk - 1
+                if has_attn:
+                    mid = self.new(cat.N, cat.H, cat.W, r.conv2.out_channels)
+                    self.resnet(r, cat, mid)
+                    self.attention(blk.attentions[j], mid, dest)
+                else:
+                    self.resnet(r, cat, dest)
+                x = dest
+            if blk.upsamplers is not None:
+                u: Upsample2D = blk.upsamplers[0]
+                up = self.new(x.N, 2 * x.H, 2 * x.W, x.C)
+                xx = x
+                self._rec(self.fwd, lambda s, xx=xx, up=up: lib.dp_upsample2x_fwd(xx.ptr, xx.ld, up.ptr, up.ld, xx.N, xx.H, xx.W, xx.C, s),
+                          what="upsample")
+                if self.need_grad:
+                    it = self._bitem()
+                    accf = [0]
+                    it.writes.append((xx, lambda init, accf=accf: accf.__setitem__(0, 1 if init else 0)))
+                    self._rec(it.steps, lambda s, xx=xx, up=up, accf=accf: lib.dp_upsample2x_bwd(
+                        self.gradof(up).ptr, up.ld, self.gradof(xx).ptr, self.gradof(xx).ld, xx.N, xx.H, xx.W, xx.C, accf[0], s),
+                        what="upsample bwd")
+                dest = h_half(skips[-1])
+                self.conv(up, u.conv.weight, u.conv.bias, dest)
+                x = dest
+        assert not skips
+        # ---- out head (unet_2d.py:302-304)
+        a = self.new(x.N, x.H, x.W, x.C)
+        g = self.gn(x, m.conv_norm_out, a, silu=True)
+        if self.need_grad:
+            self.gn_bwd(g, x, m.conv_norm_out, lambda: self.sptr("da"), x.C)
+        self.y_out = self.new(B, H, W, cfg.out_channels)
+        self.conv(a, m.conv_out.weight, m.conv_out.bias, self.y_out, dx_scratch="da")
+
+        # ---- allocate shared scratch, bind late pointers, resolve (=|+=) of every gradient write in EXECUTION order
+        for name, n in self._scratch_need.items():
+            self._scratch[name] = torch.empty(max(n, 1), device=self.dev, dtype=torch.float32)
+        for fix in self._late:
+            fix()
+        self._late.clear()
+        if self.need_grad:
+            self.g_mark(self.silu_temb)   # zeroed at backward start; every resnet accumulates into it
+            self.g_mark(self.y_out)       # loaded from the loss gradient
+            for it in reversed(self.bwd):
+                for view, setter in it.writes:
+                    setter(self.g_is_init(view))
+                    self.g_mark(view)
+        self._packed_version = None
+        self.bwd_steps: List[Step] = [f for it in reversed(self.bwd) for f in it.steps]
+
+    # ------------------------------------------------------------------ execution
+    def run_pack(self, s: Optional[int] = None):
+        s = _stream() if s is None else s
+        for f in self.pack:
+            f(s)
+
+    def ensure_packed(self):
+        v = self.weight_version()
+        if v != self._packed_version:
+            self.run_pack()
+            self._packed_version = v
+
+    def run_forward(self, s: Optional[int] = None):
+        s = _stream() if s is None else s
+        for f in self.fwd:
+            f(s)
+
+    def run_backward(self, s: Optional[int] = None):
+        s = _stream() if s is None else s
+        self.gradof(self.silu_temb).t.zero_()
+        for f in self.bwd_steps:
+            f(s)
+
+    def load_input_nchw(self, sample: torch.Tensor, timesteps: torch.Tensor):
+        sample = sample.contiguous()
+        self.t_dev.copy_(timesteps.to(torch.int64), non_blocking=True)
+        L.check(self.lib.dp_nchw_to_nhwc(sample.data_ptr(), self.x_in.ptr, self.x_in.ld, self.B, self.x_in.C, self.H, self.W,
+                                         _stream()), "nchw->nhwc")
+
+    def output_nchw(self) -> torch.Tensor:
+        out = torch.empty((self.B, self.y_out.C, self.H, self.W), device=self.dev, dtype=torch.float32)
+        L.check(self.lib.dp_nhwc_to_nchw(self.y_out.ptr, self.y_out.ld, out.data_ptr(), self.B, self.y_out.C, self.H, self.W, 0,
+                                         _stream()), "nhwc->nchw")
+        return out
+
+    def load_grad_nchw(self, gout: torch.Tensor):
+        gout = gout.contiguous()
+        gy = self.gradof(self.y_out)
+        L.check(self.lib.dp_nchw_to_nhwc(gout.data_ptr(), gy.ptr, gy.ld, self.B, gy.C, self.H, self.W, _stream()),
+                "grad nchw->nhwc")
+
+    def bytes_allocated(self) -> int:
+        n = sum(t.numel() * t.element_size() for t in self._keep if isinstance(t, torch.Tensor))
+        n += sum(t.numel() * 4 for t in self._gbuf.values()) + sum(t.numel() * 4 for t in self._scratch.values())
+        n += sum(a.numel() * 8 for a, _ in self._packs.values()) + self.grad_arena.numel() * 4
+        return n
+
+
+# ----------------------------------------------------------------------------------------------------------
+# autograd boundary: the whole UNet is ONE node, parameters are listed as inputs so backward() fires, and the
+# engine writes Parameter.grad itself (accumulating), exactly what `loss.backward()` does at ddpm_prune.py:102.
+# ----------------------------------------------------------------------------------------------------------
+class _UNetFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sample, timesteps, plan, *params):
+        plan.ensure_packed()
+        plan.load_input_nchw(sample, timesteps)
+        plan.run_forward()
+        ctx.plan = plan
+        return plan.output_nchw()
+
+    @staticmethod
+    def backward(ctx, gout):
+        plan: Plan = ctx.plan
+        plan.attach_grads()
+        plan.load_grad_nchw(gout)
+        plan.run_backward()
+        return (None, None, None) + (None,) * len(plan.params)
+
+
+def get_plan(model: UNet2DModel, batch: int, H: int, W: int, device, need_grad: bool) -> Plan:
+    cache = model.__dict__.setdefault("_dpb200_plans", {})
+    training = bool(model.training)
+    key = (batch, H, W, str(device), need_grad, training)
+    plan = cache.get(key)
+    sig = tuple((p.data_ptr(), tuple(p.shape)) for p in model.parameters())
+    if plan is None or plan.signature() != sig:
+        if plan is not None or any(pl.signature() != sig for pl in cache.values()):
+            cache.clear()  # weights were replaced (e.g. pruned): every cached plan is stale
+        plan = Plan(model, batch, H, W, device, training=training, need_grad=need_grad)
+        cache[key] = plan
+    return plan
+
+
+def unet_apply(model: UNet2DModel, sample: torch.Tensor, timesteps: torch.Tensor) -> torch.Tensor:
+    """UNet2DModel.forward on CUDA (models.py).  unet_2d.py:219-316."""
+    if sample.dtype != torch.float32:
+        raise TypeError("diff_pruning_b200 engine computes in fp32; got %s" % sample.dtype)
+    B, Cc, H, W = sample.shape
+    need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in model.parameters())
+    plan = get_plan(model, B, H, W, sample.device, need_grad)
+    if need_grad:
+        return _UNetFunction.apply(sample, timesteps, plan, *plan.params)
+    plan.ensure_packed()
+    plan.load_input_nchw(sample, timesteps)
+    plan.run_forward()
+    return plan.output_nchw()
+
+
+def add_noise_cuda(sched, x0: torch.Tensor, noise: torch.Tensor, timesteps: torch.Tensor) -> torch.Tensor:
+    """DDPMScheduler.add_noise on CUDA — scheduling_ddpm.py:408-429."""
+    lib = L.load()
+    dev = x0.device
+    tab = sched._dev_tables.get(str(dev))
+    if tab is None:
+        tab = sched.alphas_cumprod.to(dev).contiguous()
+        sched._dev_tables[str(dev)] = tab
+    x0c, nz = x0.contiguous(), noise.contiguous()
+    t = timesteps.to(device=dev, dtype=torch.int64).contiguous()
+    out = torch.empty_like(x0c)
+    B, Cc, H, W = x0c.shape
+    L.check(lib.dp_add_noise(x0c.data_ptr(), nz.data_ptr(), t.data_ptr(), tab.data_ptr(), out.data_ptr(), B, Cc, H, W, 0, _stream()),
+            "add_noise")
+    return out

@@ -1,0 +1,342 @@
+"""The two hot loops of the reference as fused, CUDA-graph-replayed device programs.
+
+TaylorScorer   — ddpm_prune.py:94-106: for each timestep  add_noise -> UNet fwd -> mse -> bwd, gradients
+                 accumulating into Parameter.grad (no zero_grad between steps).  One graph replay per step.
+FinetuneStepper— ddpm_train.py:437-469: add_noise -> fwd -> loss -> bwd -> clip_grad_norm_(1.0) -> Adam -> EMA
+                 over flat parameter / gradient / moment / EMA arenas.
+taylor_layer_scores / TaylorImportance — torch_pruning TaylorImportance.__call__
+                 (ddpm_exp/torch_pruning/importance.py:375-434) on the device via dp_taylor_reduce.
+
+Multi-GPU: timesteps are sharded t = rank, rank+W, ... with ONE all-reduce(SUM) of the flat
+gradient arena at the end of scoring; finetune shards the minibatch and all-reduces the gradient arena each
+step (mean), both over NCCL.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from .engine import Plan, _stream, get_plan
+from .models import UNet2DModel, ddpm_alphas_cumprod
+
+
+def _dist_ready():
+    import torch.distributed as dist
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+class TaylorScorer:
+    """Accumulates sum_t dL_t/dW into Parameter.grad for fixed (clean_images, noise) — ddpm_prune.py:90-102."""
+
+    def __init__(self, model: UNet2DModel, clean_images: torch.Tensor, noise: torch.Tensor,
+                 num_train_timesteps: int = 1000, alphas_cumprod: Optional[torch.Tensor] = None, use_graph: bool = True):
+        assert clean_images.is_cuda and clean_images.shape == noise.shape and clean_images.dtype == torch.float32
+        self.lib = L.load()
+        self.model = model
+        self.dev = clean_images.device
+        B, C_, H, W = clean_images.shape
+        self.B, self.C, self.H, self.W = B, C_, H, W
+        self.clean = clean_images.contiguous().clone()
+        self.noise = noise.contiguous().clone()
+        self.acp = (alphas_cumprod if alphas_cumprod is not None else ddpm_alphas_cumprod(num_train_timesteps)).to(self.dev).contiguous()
+        was_training = model.training
+        model.eval()  # ddpm_prune.py:91
+        self.plan: Plan = get_plan(model, B, H, W, self.dev, need_grad=True)
+        if was_training:
+            model.train()
+        self.noise_nhwc = torch.empty((B, H, W, C_), device=self.dev, dtype=torch.float32)
+        n = B * C_ * H * W
+        self.n = n
+        self.partial = torch.empty(max(1, self.lib.dp_mse_partials(n)), device=self.dev, dtype=torch.float32)
+        self.loss = torch.zeros(1, device=self.dev, dtype=torch.float32)
+        self.use_graph = use_graph
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.loss_scale, self.grad_scale = 1.0 / n, 2.0 / n   # F.mse_loss mean reduction, ddpm_prune.py:101
+        self._refresh_noise()
+        self.plan.attach_grads()
+        self.plan.ensure_packed()
+
+    def _refresh_noise(self):
+        L.check(self.lib.dp_nchw_to_nhwc(self.noise.data_ptr(), self.noise_nhwc.data_ptr(), self.C, self.B, self.C, self.H, self.W,
+                                         _stream()), "noise nchw->nhwc")
+
+    def _body(self):
+        lib, p, s = self.lib, self.plan, _stream()
+        L.check(lib.dp_add_noise(self.clean.data_ptr(), self.noise.data_ptr(), p.t_dev.data_ptr(), self.acp.data_ptr(),
+                                 p.x_in.ptr, self.B, self.C, self.H, self.W, 1, s), "add_noise")
+        p.run_forward(s)
+        gy = p.gradof(p.y_out)
+        L.check(lib.dp_mse_loss_grad(p.y_out.ptr, self.noise_nhwc.data_ptr(), gy.ptr, self.n, self.loss_scale, self.grad_scale,
+                                     self.partial.data_ptr(), self.loss.data_ptr(), s), "mse")
+        p.run_backward(s)
+
+    def _capture(self):
+        torch.cuda.synchronize(self.dev)
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):   # warm-up outside capture (first-launch lazy module loading)
+            saved = self.plan.grad_arena.clone()
+            self._body()
+            self.plan.grad_arena.copy_(saved)
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._body()
+        self.graph = g
+
+    def step(self, t) -> torch.Tensor:
+        """One pass at timestep(s) t (int, or a (B,) tensor).  Returns the device loss scalar (no sync)."""
+        p = self.plan
+        p.attach_grads()
+        p.ensure_packed()
+        if torch.is_tensor(t):
+            p.t_dev.copy_(t.to(device=self.dev, dtype=torch.int64), non_blocking=True)
+        else:
+            p.t_dev.fill_(int(t))
+        if self.use_graph:
+            if self.graph is None:
+                tsave = p.t_dev.clone()
+                self._capture()
+                p.t_dev.copy_(tsave)
+            self.graph.replay()
+        else:
+            self._body()
+        return self.loss
+
+    def step_from_host(self, clean_pinned: torch.Tensor, noise_pinned: torch.Tensor, t: int) -> float:
+        """End-to-end step through host buffers: H2D of the batch, one pass, D2H of the loss."""
+        self.clean.copy_(clean_pinned, non_blocking=True)
+        self.noise.copy_(noise_pinned, non_blocking=True)
+        self._refresh_noise()
+        return float(self.step(t).item())
+
+    def run(self, timesteps: Iterable[int], shard: bool = True) -> torch.Tensor:
+        """The whole loop of ddpm_prune.py:97-102; with torch.distributed initialised, timesteps are sharded
+        (t_k for k = rank mod world) and the gradient arena is all-reduced (SUM) once at the end."""
+        ts = list(timesteps)
+        world, rank = 1, 0
+        if shard and _dist_ready():
+            import torch.distributed as dist
+            world, rank = dist.get_world_size(), dist.get_rank()
+        losses = torch.zeros(len(ts), device=self.dev, dtype=torch.float32)
+        for k, t in enumerate(ts):
+            if k % world != rank:
+                continue
+            losses[k:k + 1].copy_(self.step(t))
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.plan.grad_arena, op=dist.ReduceOp.SUM)
+            dist.all_reduce(losses, op=dist.ReduceOp.SUM)
+        return losses
+
+
+# --------------------------------------------------------------------------------------------------------
+# Taylor importance on device
+# --------------------------------------------------------------------------------------------------------
+def taylor_layer_scores(weight: torch.Tensor, grad: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """All six per-channel reductions of w*dw for one layer (out/in x signed/abs/sq) via dp_taylor_reduce.
+    weight: (O, I, R, S) conv, (O, I) linear, or (C,) GroupNorm gamma."""
+    lib = L.load()
+    assert weight.is_cuda and grad.is_cuda and weight.shape == grad.shape
+    w, g = weight.detach().contiguous().float(), grad.detach().contiguous().float()
+    a = L.TaylorArgs()
+    if w.dim() == 1:
+        O, I, RS = w.numel(), 1, 1
+    else:
+        O, I = w.shape[0], w.shape[1]
+        RS = w.numel() // (O * I)
+    a.O, a.I, a.RS = O, I, RS
+    a.w, a.dw = w.data_ptr(), g.data_ptr()
+    out = torch.empty((3, O), device=w.device, dtype=torch.float32)
+    a.out_signed, a.out_abs, a.out_sq = out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr()
+    res = {"out_signed": out[0], "out_abs": out[1], "out_sq": out[2]}
+    if w.dim() > 1:
+        inn = torch.empty((3, I), device=w.device, dtype=torch.float32)
+        a.in_signed, a.in_abs, a.in_sq = inn[0].data_ptr(), inn[1].data_ptr(), inn[2].data_ptr()
+        res.update({"in_signed": inn[0], "in_abs": inn[1], "in_sq": inn[2]})
+    L.check(lib.dp_taylor_reduce(a, _stream()), "taylor_reduce")
+    return res
+
+
+_VARIANT_KEY = {"vendored": "sq", "taylor": "signed", "diff": "abs"}
+
+
+def group_importance(items: Sequence[Tuple[str, str, Sequence[int]]], named_weights: Dict[str, torch.Tensor],
+                     named_grads: Dict[str, torch.Tensor], variant: str = "taylor",
+                     cache: Optional[dict] = None) -> Optional[torch.Tensor]:
+    """importance.py:375-434 for one group given as (layer_name, kind in {out,in,gn}, idxs) items.
+    variant: 'taylor' = |sum_k w dw| (multivariable=True, ddpm_prune.py:60), 'diff' = sum_k |w dw|
+    (multivariable=False, :66), 'vendored' = sum_k (w dw)^2 (vendored importance.py:393).  GroupNorm: |w dw| (:416)."""
+    cache = {} if cache is None else cache
+    imps = []
+    for name, kind, idxs in items:
+        sc = cache.get(name)
+        if sc is None:
+            sc = taylor_layer_scores(named_weights[name + ".weight"], named_grads[name + ".weight"])
+            cache[name] = sc
+        idx = torch.as_tensor(sorted(idxs), device=sc["out_abs"].device, dtype=torch.long)
+        if kind == "gn":
+            v = sc["out_abs"][idx]
+        else:
+            v = sc[f"{kind}_{_VARIANT_KEY[variant]}"][idx]
+            if variant == "taylor":
+                v = v.abs()
+        imps.append(v)
+    if not imps:
+        return None
+    size = len(imps[0])
+    return torch.stack([i for i in imps if len(i) == size], dim=0).sum(0)
+
+
+def select_pruning_idxs(imp: torch.Tensor, ch_groups: int, n_pruned: int) -> List[int]:
+    """metapruner.py:231-249 — host-side integer selection (argsort on CPU like the reference's CPU run)."""
+    imp = imp.detach().float().cpu()
+    if n_pruned <= 0:
+        return []
+    if ch_groups > 1:
+        size, per, out = len(imp) // ch_groups, n_pruned // ch_groups, []
+        for g in range(ch_groups):
+            out.append(torch.argsort(imp[g * size:(g + 1) * size])[:per] + g * size)
+        return torch.cat(out, 0).tolist()
+    return torch.argsort(imp)[: n_pruned // ch_groups].tolist()
+
+
+# --------------------------------------------------------------------------------------------------------
+# Finetune step
+# --------------------------------------------------------------------------------------------------------
+class FinetuneStepper:
+    """ddpm_train.py:437-469 on device.  Parameters are re-pointed into one flat arena (values preserved) so the
+    clip + Adam + EMA tail is a single pass over contiguous memory and DDP needs one all-reduce."""
+
+    def __init__(self, model: UNet2DModel, lr: float = 2e-4, betas=(0.9, 0.999), eps: float = 1e-8,
+                 ema_decay: float = 0.9999, max_grad_norm: float = 1.0, use_ema: bool = True,
+                 num_train_timesteps: int = 1000, use_graph: bool = True):
+        self.lib = L.load()
+        self.model = model
+        self.dev = next(model.parameters()).device
+        assert self.dev.type == "cuda"
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.ema_decay, self.max_grad_norm = ema_decay, max_grad_norm
+        self.params = list(model.parameters())
+        total = sum(p.numel() for p in self.params)
+        self.n = total
+        self.param_arena = torch.empty(total, device=self.dev, dtype=torch.float32)
+        o = 0
+        with torch.no_grad():
+            for p in self.params:
+                v = self.param_arena[o:o + p.numel()].view_as(p)
+                v.copy_(p.data)
+                p.data = v
+                o += p.numel()
+        self.m = torch.zeros(total, device=self.dev, dtype=torch.float32)
+        self.v = torch.zeros(total, device=self.dev, dtype=torch.float32)
+        self.ema = self.param_arena.clone() if use_ema else None
+        self.acp = ddpm_alphas_cumprod(num_train_timesteps).to(self.dev).contiguous()
+        self.step_scalars = torch.zeros(2, device=self.dev, dtype=torch.float32)
+        self.sumsq = torch.zeros(1, device=self.dev, dtype=torch.float32)
+        self.ss_partial = torch.empty(max(1, self.lib.dp_sumsq_partials(total)), device=self.dev, dtype=torch.float32)
+        self.loss = torch.zeros(1, device=self.dev, dtype=torch.float32)
+        self.steps_done = 0
+        self.use_graph = use_graph
+        self.plan: Optional[Plan] = None
+        self.g_main = self.g_tail = None
+        self.world = 1
+        if _dist_ready():
+            import torch.distributed as dist
+            self.world = dist.get_world_size()
+
+    def ema_state(self) -> Dict[str, torch.Tensor]:
+        out, o = {}, 0
+        for (name, p) in self.model.named_parameters():
+            out[name] = self.ema[o:o + p.numel()].view_as(p)
+            o += p.numel()
+        return out
+
+    def _setup(self, B, C_, H, W):
+        self.model.train()
+        self.plan = get_plan(self.model, B, H, W, self.dev, need_grad=True)
+        self.B, self.C, self.H, self.W = B, C_, H, W
+        self.clean = torch.empty((B, C_, H, W), device=self.dev, dtype=torch.float32)
+        self.noise = torch.empty_like(self.clean)
+        self.noise_nhwc = torch.empty((B, H, W, C_), device=self.dev, dtype=torch.float32)
+        self.nelem = B * C_ * H * W
+        self.partial = torch.empty(max(1, self.lib.dp_mse_partials(self.nelem)), device=self.dev, dtype=torch.float32)
+        self.plan.attach_grads()
+
+    def _main(self):
+        lib, p, s = self.lib, self.plan, _stream()
+        p.run_pack(s)
+        L.check(lib.dp_nchw_to_nhwc(self.noise.data_ptr(), self.noise_nhwc.data_ptr(), self.C, self.B, self.C, self.H, self.W, s), "noise")
+        L.check(lib.dp_add_noise(self.clean.data_ptr(), self.noise.data_ptr(), p.t_dev.data_ptr(), self.acp.data_ptr(),
+                                 p.x_in.ptr, self.B, self.C, self.H, self.W, 1, s), "add_noise")
+        p.run_forward(s)
+        gy = p.gradof(p.y_out)
+        # loss = (noise - out)^2 .sum(1,2,3).mean(0)  (ddpm_train.py:459)
+        L.check(lib.dp_mse_loss_grad(p.y_out.ptr, self.noise_nhwc.data_ptr(), gy.ptr, self.nelem, 1.0 / self.B, 2.0 / self.B,
+                                     self.partial.data_ptr(), self.loss.data_ptr(), s), "loss")
+        p.grad_arena.zero_()          # optimizer.zero_grad() (:456)
+        p.run_backward(s)
+
+    def _tail(self):
+        lib, p, s = self.lib, self.plan, _stream()
+        L.check(lib.dp_sumsq(p.grad_arena.data_ptr(), self.n, self.ss_partial.data_ptr(), self.sumsq.data_ptr(), s), "sumsq")
+        a = L.AdamArgs()
+        a.n = self.n
+        a.p, a.g, a.m, a.v = self.param_arena.data_ptr(), p.grad_arena.data_ptr(), self.m.data_ptr(), self.v.data_ptr()
+        a.ema = self.ema.data_ptr() if self.ema is not None else None
+        a.sumsq = self.sumsq.data_ptr() if self.max_grad_norm is not None else None
+        a.max_norm = float(self.max_grad_norm or 0.0)
+        a.lr, a.beta1, a.beta2, a.eps, a.ema_decay = self.lr, self.betas[0], self.betas[1], self.eps, self.ema_decay
+        a.step, a.grad_scale = 1, 1.0 / self.world
+        a.step_scalars = self.step_scalars.data_ptr()
+        self._adam_args = a
+        L.check(lib.dp_adam_clip_ema(a, s), "adam")
+
+    def _capture(self):
+        torch.cuda.synchronize(self.dev)
+        self.g_main = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_main):
+            self._main()
+        self.g_tail = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_tail):
+            self._tail()
+
+    def step(self, clean: torch.Tensor, noise: torch.Tensor, timesteps: torch.Tensor) -> torch.Tensor:
+        """One optimisation step; returns the device loss scalar (this rank's minibatch)."""
+        B, C_, H, W = clean.shape
+        if self.plan is None:
+            self._setup(B, C_, H, W)
+        p = self.plan
+        self.clean.copy_(clean, non_blocking=True)
+        self.noise.copy_(noise, non_blocking=True)
+        p.t_dev.copy_(timesteps.to(device=self.dev, dtype=torch.int64), non_blocking=True)
+        self.steps_done += 1
+        t = self.steps_done
+        bc = torch.tensor([1.0 - self.betas[0] ** t, math.sqrt(1.0 - self.betas[1] ** t)], dtype=torch.float32)
+        self.step_scalars.copy_(bc, non_blocking=True)
+        p.dropout_seed_dev.fill_(0x5DEECE66D * t & 0x7FFFFFFFFFFF)
+        if self.use_graph and self.g_main is None:
+            # warm-up once outside capture (lazy module loading), on a side stream as torch requires
+            side = torch.cuda.Stream(device=self.dev)
+            side.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(side):
+                self._main()
+            torch.cuda.current_stream(self.dev).wait_stream(side)
+            self._capture()
+        if self.use_graph:
+            self.g_main.replay()
+        else:
+            self._main()
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(p.grad_arena, op=dist.ReduceOp.SUM)   # mean applied through grad_scale = 1/world
+        if self.use_graph:
+            self.g_tail.replay()
+        else:
+            self._tail()
+        return self.loss

@@ -1,0 +1,45 @@
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with `-m gpu` on the B200 box)")
+    config.addinivalue_line("markers", "slow: long CPU oracle re-derivations (set DPB200_SLOW=1)")
+
+
+def pytest_collection_modifyitems(config, items):
+    has_cuda = torch.cuda.is_available()
+    for item in items:
+        if "gpu" in item.keywords and not has_cuda:
+            item.add_marker(pytest.mark.skip(reason="no CUDA device"))
+        if "slow" in item.keywords and not os.environ.get("DPB200_SLOW"):
+            item.add_marker(pytest.mark.skip(reason="set DPB200_SLOW=1"))
+
+
+def load_golden(name):
+    return torch.load(os.path.join(GOLDEN, name), map_location="cpu", weights_only=False)
+
+
+def expand(idxs):
+    if isinstance(idxs, tuple) and idxs and idxs[0] == "range":
+        return list(range(idxs[1], idxs[1] + idxs[2]))
+    return list(idxs)
+
+
+def rel_err(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def max_rel(a, b):
+    """max |a-b| / max|b| — the tolerance form used for eps_hat (<= 1e-4 relative fp32, BASELINE.json north_star)."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))

@@ -1,0 +1,169 @@
+"""End-to-end parity of the planned CUDA engine (through the C-ABI) against golden fixtures produced by the
+unmodified reference, and against the oracle on fresh seeds."""
+import copy
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import expand, load_golden, max_rel, rel_err
+import diff_pruning_b200 as dp
+from diff_pruning_b200.scoring import FinetuneStepper, TaylorScorer, group_importance, select_pruning_idxs
+from diff_pruning_b200 import pruning
+
+pytestmark = pytest.mark.gpu
+
+
+def inputs(b, hw):
+    g1, g2 = torch.Generator().manual_seed(1), torch.Generator().manual_seed(2)
+    return torch.randn(b, 3, hw, hw, generator=g1), torch.randn(b, 3, hw, hw, generator=g2)
+
+
+def build(cfg, seed=0):
+    torch.manual_seed(seed)
+    return dp.UNet2DModel(**cfg).eval().cuda()
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_tiny_two_accumulated_passes(use_graph):
+    """grads accumulate over passes (no zero_grad) — ddpm_prune.py:90,97-102."""
+    G = load_golden("tiny_unet.pt")
+    m = build(G["cfg"])
+    clean, noise = inputs(2, 16)
+    sc = TaylorScorer(m, clean.cuda(), noise.cuda(), use_graph=use_graph)
+    losses = [sc.step(7).item(), sc.step(400).item()]
+    assert losses == pytest.approx(G["losses"], rel=2e-6)
+    worst = max(rel_err(p.grad, G["grads"][k]) for k, p in m.named_parameters())
+    assert worst < 5e-5, worst
+
+
+def test_tiny_autograd_boundary_matches_scripts_loop():
+    """The unchanged script loop: scheduler.add_noise -> model(...).sample -> F.mse_loss -> loss.backward()."""
+    G = load_golden("tiny_unet.pt")
+    m = build(G["cfg"])
+    sched = dp.DDPMScheduler(num_train_timesteps=1000)
+    clean, noise = (t.cuda() for t in inputs(2, 16))
+    m.zero_grad()
+    losses = []
+    for tt in (7, 400):
+        t = (tt * torch.ones(2, device="cuda")).long()
+        out = m(sched.add_noise(clean, noise, t), t).sample
+        loss = F.mse_loss(out, noise)
+        loss.backward()
+        losses.append(loss.item())
+    assert losses == pytest.approx(G["losses"], rel=2e-6)
+    assert max_rel(out, G["out_last"]) < 1e-5
+    worst = max(rel_err(p.grad, G["grads"][k]) for k, p in m.named_parameters())
+    assert worst < 5e-5, worst
+    with torch.no_grad():   # per-sample timesteps, inference path
+        out2 = m(sched.add_noise(clean, noise, G["t2"].cuda()), G["t2"].cuda()).sample
+    assert max_rel(out2, G["out_t2"]) < 1e-5
+    # python-number timestep like the pipelines pass (pipeline_ddim.py:105)
+    with torch.no_grad():
+        o3 = m(clean, 5).sample
+        o4 = m(clean, torch.tensor(5, device="cuda")).sample
+    assert torch.equal(o3, o4)
+    # model survives pickling / deepcopy with live plans (ddpm_prune.py:135, op_counter.py:18)
+    m2 = copy.deepcopy(m)
+    assert "_dpb200_plans" not in m2.__dict__
+
+
+def test_cifar_eps_and_grads():
+    """C1 (CIFAR UNet) seed 0: eps_hat within 1e-4 relative of the reference CPU fp32 (north_star tolerance)."""
+    G = load_golden("cifar_fwd.pt")
+    m = build(dp.CIFAR10_DDPM_CONFIG)
+    sched = dp.DDPMScheduler()
+    clean16, noise16 = inputs(16, 32)
+    clean, noise = clean16[:2].cuda(), noise16[:2].cuda()
+    with torch.no_grad():
+        for tt, ref in G["eps_b2"].items():
+            t = (tt * torch.ones(2, device="cuda")).long()
+            assert max_rel(m(sched.add_noise(clean, noise, t), t).sample, ref) < 1e-4, tt
+    m.zero_grad()
+    sc = TaylorScorer(m, clean, noise, use_graph=False)
+    assert sc.step(500).item() == pytest.approx(G["loss_b2_t500"], rel=5e-6)
+    bad = []
+    for k, p in m.named_parameters():
+        s = G["grad_samples_b2_t500"][k]
+        g = p.grad.flatten()[:64].cpu()
+        if rel_err(g, s) > 2e-3 and float((g - s).abs().max()) > 1e-7:
+            bad.append((k, rel_err(g, s)))
+        f = G["grad_fp_b2_t500"][k]
+        assert float((p.grad.double() ** 2).sum()) == pytest.approx(f[2], rel=2e-3), k
+    assert not bad, bad[:5]
+
+
+def test_cfg1_scores_and_masks_bit_exact():
+    """BASELINE config 1 on the GPU: 100 timesteps B=16, ratio 0.3.  Losses, per-group importance vectors and the
+    pruned channel-index sets (all three importance variants) against the unmodified reference; then the pruned
+    network's eps_hat."""
+    G = load_golden("cifar_cfg1.pt")
+    m = build(dp.CIFAR10_DDPM_CONFIG)
+    clean, noise = inputs(G["B"], 32)
+    m.zero_grad()
+    sc = TaylorScorer(m, clean.cuda(), noise.cuda(), use_graph=True)
+    losses = sc.run(range(G["n_steps"])).cpu()
+    assert rel_err(losses, torch.tensor(G["losses"])) < 5e-6
+    for k, p in m.named_parameters():
+        assert float((p.grad.double() ** 2).sum()) == pytest.approx(G["grad_fp"][k][2], rel=5e-3), k
+    grads = {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+    sched = dp.DDPMScheduler()
+    for variant, V in G["variants"].items():
+        mv = copy.deepcopy(m)
+        for k, p in mv.named_parameters():
+            p.grad = grads[k].clone()
+        mods = dict(mv.named_modules())
+        worst_imp = 0.0
+        for g in V["groups"]:
+            items = [(n, k, expand(i)) for n, k, i in g["items"]]
+            named_w = {n + ".weight": mods[n].weight for n, _, _ in items}
+            named_g = {n + ".weight": mods[n].weight.grad for n, _, _ in items}
+            imp = group_importance(items, named_w, named_g, variant)
+            worst_imp = max(worst_imp, rel_err(imp, g["imp"]))
+            sel = select_pruning_idxs(imp, g["ch_groups"], g["n_pruned"])
+            assert sorted(sel) == sorted(g["idxs"]), (variant, g["root"], worst_imp)   # bit-exact mask
+            pruning.apply_group(mods, items, sel, g["channels"])
+        assert worst_imp < 2e-3, (variant, worst_imp)
+        pruning.fix_static_attributes(mv)
+        assert {k: list(v.shape) for k, v in mv.state_dict().items()} == V["pruned_shapes"]
+        assert sum(p.numel() for p in mv.parameters()) == V["pruned"][1] == 19851157
+        with torch.no_grad():
+            t = (10 * torch.ones(2, device="cuda")).long()
+            out = mv(sched.add_noise(clean[:2].cuda(), noise[:2].cuda(), t), t).sample
+        assert max_rel(out, V["pruned_eps_b2_t10"]) < 1e-4, variant
+
+
+def test_finetune_two_steps():
+    """ddpm_train.py:437-469 (dropout 0): loss, clipped Adam update and EMA after 2 steps vs the reference."""
+    G = load_golden("finetune_tiny.pt")
+    for use_graph in (False, True):
+        torch.manual_seed(0)
+        m = dp.UNet2DModel(**G["cfg"]).cuda().train()
+        st = FinetuneStepper(m, lr=2e-4, ema_decay=0.9999, max_grad_norm=1.0, use_graph=use_graph)
+        for s in G["steps"]:
+            loss = st.step(s["clean"].cuda(), s["noise"].cuda(), s["t"].cuda())
+            assert loss.item() == pytest.approx(s["loss"], rel=2e-5)
+            assert float(st.sumsq.sqrt()) == pytest.approx(s["grad_norm"], rel=2e-4)
+        ema = st.ema_state()
+        for k, p in m.named_parameters():
+            assert rel_err(p, G["params"][k]) < 2e-6, k
+            assert rel_err(ema[k], G["ema"][k]) < 2e-6, k
+
+
+def test_lsun_family_block_one_pass_vs_oracle():
+    """A narrow member of the LSUN-256 family (6 levels, attention at level 4, 64x64 input) vs the oracle."""
+    from oracle import unet_oracle as orc
+    cfg = dict(dp.LSUN256_DDPM_CONFIG, block_out_channels=(32, 32, 64, 64, 128, 128), sample_size=64)
+    torch.manual_seed(3)
+    m = dp.UNet2DModel(**cfg).eval()
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(9)
+    clean, noise = torch.randn(2, 3, 64, 64, generator=g), torch.randn(2, 3, 64, 64, generator=g)
+    t = torch.tensor([123, 877])
+    ref = orc.taylor_pass(sd, cfg, orc.alphas_cumprod(), clean, noise, t)
+    m = m.cuda()
+    m.zero_grad()
+    sc = TaylorScorer(m, clean.cuda(), noise.cuda(), use_graph=False)
+    assert sc.step(t).item() == pytest.approx(ref.item(), rel=5e-6)
+    worst = max(rel_err(p.grad, sd[k].grad) for k, p in m.named_parameters())
+    assert worst < 1e-4, worst

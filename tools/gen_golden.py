@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""Generate tests/golden/* by importing the UNMODIFIED reference (read-only /root/reference).
+
+Run in the build container only (the reference does not exist on the GPU box):
+    python tools/gen_golden.py [--skip-cfg1]
+Outputs (all small, committed):
+    tests/golden/tiny_unet.pt      TINY config: inputs, output, loss, all grads after 1 pass (B=2)
+    tests/golden/blocks.pt         one ResnetBlock2D (with shortcut) and one Attention: in/out/grads
+    tests/golden/cifar_fwd.pt      C1 seed-0: state-dict fingerprints, eps_hat for B=2 at t in {0,500,999},
+                                   KAT losses at B=16 t in {0,50,99}, grad fingerprints after one pass
+    tests/golden/cifar_cfg1.pt     BASELINE config 1 (B=16, t=0..99, ratio 0.3): per importance variant, the
+                                   interactive group sequence (structure, importance vector, pruned indices),
+                                   post-prune shapes / param+MAC counts / pruned-model eps
+    tests/golden/cifar_cfg1_s3.pt  same with 3 timesteps (fast CPU check of the oracle)
+    tests/golden/finetune_tiny.pt  2 finetune steps on TINY (Adam + clip + EMA), dropout 0
+"""
+import argparse
+import hashlib
+import json
+import os
+import sys
+import time
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+import ref_shim  # noqa: E402
+
+diffusers, tp = ref_shim.install()
+from diffusers import DDPMScheduler, UNet2DModel  # noqa: E402
+from diffusers.models.attention_processor import Attention, AttnProcessor  # noqa: E402
+from diffusers.models.resnet import Downsample2D, ResnetBlock2D, Upsample2D  # noqa: E402
+from torch_pruning.pruner import function as tpf  # noqa: E402
+
+import diff_pruning_b200 as dp  # noqa: E402  (configs only)
+
+OUT = os.path.join(ROOT, "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+
+
+def legacy_attn(model):
+    for m in model.modules():
+        if isinstance(m, Attention):
+            m.set_processor(AttnProcessor())
+
+
+def fp(t):
+    t = t.detach().double()
+    return [float(t.sum()), float(t.abs().sum()), float((t * t).sum())]
+
+
+def build(cfg, seed=0):
+    torch.manual_seed(seed)
+    m = UNet2DModel(**cfg).eval()
+    legacy_attn(m)  # identical math to 2_0 pre-pruning, and the only one that survives pruning
+    return m
+
+
+def inputs(b, hw, c=3):
+    g1, g2 = torch.Generator().manual_seed(1), torch.Generator().manual_seed(2)
+    return torch.randn(b, c, hw, hw, generator=g1), torch.randn(b, c, hw, hw, generator=g2)
+
+
+def gen_tiny():
+    cfg = dict(dp.TINY_TEST_CONFIG)
+    m = build(cfg)
+    sched = DDPMScheduler(num_train_timesteps=1000)
+    clean, noise = inputs(2, 16)
+    t = torch.tensor([7, 7]).long()
+    m.zero_grad()
+    losses = []
+    for tt in (7, 400):  # two accumulated passes (no zero_grad in between)
+        t = (tt * torch.ones(2)).long()
+        out = m(sched.add_noise(clean, noise, t), t).sample
+        loss = torch.nn.functional.mse_loss(out, noise)
+        loss.backward()
+        losses.append(loss.item())
+    with torch.no_grad():
+        t2 = torch.tensor([3, 950]).long()  # per-sample timesteps (finetune style)
+        out2 = m(sched.add_noise(clean, noise, t2), t2).sample
+    torch.save({"cfg": cfg, "seed": 0, "losses": losses, "out_last": out.detach(), "t2": t2, "out_t2": out2,
+                "grads": {k: p.grad.clone() for k, p in m.named_parameters()}},
+               os.path.join(OUT, "tiny_unet.pt"))
+    print("tiny", losses)
+
+
+def gen_blocks():
+    torch.manual_seed(3)
+    rb = ResnetBlock2D(in_channels=32, out_channels=64, temb_channels=128, groups=8, eps=1e-6)
+    x = torch.randn(2, 32, 8, 8, requires_grad=True)
+    temb = torch.randn(2, 128, requires_grad=True)
+    y = rb(x, temb)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    res = {"sd": {k: v.clone() for k, v in rb.state_dict().items()}, "x": x.detach(), "temb": temb.detach(),
+           "y": y.detach(), "gy": gy, "gx": x.grad.clone(), "gtemb": temb.grad.clone(),
+           "grads": {k: p.grad.clone() for k, p in rb.named_parameters()}}
+    torch.manual_seed(4)
+    at = Attention(64, heads=1, dim_head=64, rescale_output_factor=1.0, eps=1e-6, norm_num_groups=8,
+                   residual_connection=True, bias=True, upcast_softmax=True, _from_deprecated_attn_block=True)
+    at.set_processor(AttnProcessor())
+    xa = torch.randn(2, 64, 4, 4, requires_grad=True)
+    ya = at(xa)
+    gya = torch.randn_like(ya)
+    ya.backward(gya)
+    att = {"sd": {k: v.clone() for k, v in at.state_dict().items()}, "x": xa.detach(), "y": ya.detach(), "gy": gya,
+           "gx": xa.grad.clone(), "grads": {k: p.grad.clone() for k, p in at.named_parameters()}, "scale": at.scale}
+    torch.save({"resnet": res, "attn": att}, os.path.join(OUT, "blocks.pt"))
+    print("blocks ok")
+
+
+def cifar_cfg():
+    cfg = json.load(open(os.path.join(ref_shim.REF, "tools", "ddpm_cifar10_config.json")))
+    return {k: v for k, v in cfg.items() if not k.startswith("_")}
+
+
+def gen_cifar_fwd():
+    m = build(cifar_cfg())
+    sched = DDPMScheduler(num_train_timesteps=1000)
+    sd = m.state_dict()
+    res = {"sd_fp": {k: fp(v) for k, v in sd.items()},
+           "sd_sha": hashlib.sha256(b"".join(v.numpy().tobytes() for v in sd.values())).hexdigest(),
+           "n_params": sum(p.numel() for p in m.parameters())}
+    clean16, noise16 = inputs(16, 32)
+    kat = {}
+    with torch.no_grad():
+        for tt in (0, 50, 99):
+            t = (tt * torch.ones(16)).long()
+            out = m(sched.add_noise(clean16, noise16, t), t).sample
+            kat[tt] = torch.nn.functional.mse_loss(out, noise16).item()
+    res["kat_losses_b16"] = kat
+    clean, noise = clean16[:2].clone(), noise16[:2].clone()
+    eps = {}
+    with torch.no_grad():
+        for tt in (0, 500, 999):
+            t = (tt * torch.ones(2)).long()
+            eps[tt] = m(sched.add_noise(clean, noise, t), t).sample.clone()
+    res["eps_b2"] = eps
+    m.zero_grad()
+    t = (500 * torch.ones(2)).long()
+    out = m(sched.add_noise(clean, noise, t), t).sample
+    loss = torch.nn.functional.mse_loss(out, noise)
+    loss.backward()
+    res["loss_b2_t500"] = loss.item()
+    res["grad_fp_b2_t500"] = {k: fp(p.grad) for k, p in m.named_parameters()}
+    res["grad_samples_b2_t500"] = {k: p.grad.flatten()[:64].clone() for k, p in m.named_parameters()}
+    torch.save(res, os.path.join(OUT, "cifar_fwd.pt"))
+    print("cifar_fwd", kat, res["loss_b2_t500"])
+
+
+KIND = {tpf.prune_conv_out_channels: "out", tpf.prune_linear_out_channels: "out",
+        tpf.prune_conv_in_channels: "in", tpf.prune_linear_in_channels: "in",
+        tpf.prune_groupnorm_out_channels: "gn"}
+
+
+def describe_group(group, names):
+    items = []
+    for dep, idxs in group:
+        layer = dep.target.module
+        kind = KIND.get(dep.handler)
+        if layer not in names or kind is None:
+            continue  # non-parametric nodes (concat/split/elementwise) carry no score
+        if kind == "gn" and not layer.affine:
+            continue
+        items.append((names[layer], kind, [int(i) for i in idxs]))
+    return items
+
+
+def compress(idxs):
+    idxs = [int(i) for i in idxs]
+    if idxs and idxs == list(range(idxs[0], idxs[0] + len(idxs))):
+        return ("range", idxs[0], len(idxs))
+    return idxs
+
+
+def describe_group_c(group, names):
+    return [(n, k, compress(i)) for n, k, i in describe_group(group, names)]
+
+
+class VariantTaylor:
+    """reference importance.py:375-434 with :393/:407 switched per variant; :416 for GroupNorm."""
+
+    def __init__(self, variant):
+        self.variant = variant
+
+    @torch.no_grad()
+    def __call__(self, group, ch_groups=1):
+        imps = []
+        for dep, idxs in group:
+            idxs.sort()
+            layer, fn = dep.target.module, dep.handler
+            if fn in (tpf.prune_conv_out_channels, tpf.prune_linear_out_channels):
+                w, dw = layer.weight.data[idxs].flatten(1), layer.weight.grad.data[idxs].flatten(1)
+            elif fn in (tpf.prune_conv_in_channels, tpf.prune_linear_in_channels):
+                w = layer.weight.data.transpose(0, 1).flatten(1)[idxs]
+                dw = layer.weight.grad.data.transpose(0, 1).flatten(1)[idxs]
+            elif fn == tpf.prune_groupnorm_out_channels:
+                if layer.affine:
+                    imps.append((layer.weight.data[idxs] * layer.weight.grad.data[idxs]).abs())
+                continue
+            else:
+                continue
+            p = w * dw
+            imps.append({"vendored": p.abs().pow(2).sum(1), "taylor": p.sum(1).abs(), "diff": p.abs().sum(1)}[self.variant])
+        if not imps:
+            return None
+        size = len(imps[0])
+        return torch.stack([i for i in imps if len(i) == size], 0).sum(0)
+
+
+def gen_cfg1(n_steps=100, ratio=0.3, B=16, out_name="cifar_cfg1.pt"):
+    import copy
+    os.chdir("/tmp")  # prune_local writes ./run/pruning_logs
+    m0 = build(cifar_cfg())
+    sched = DDPMScheduler(num_train_timesteps=1000)
+    clean, noise = inputs(B, 32)
+    example = {"sample": torch.randn(1, 3, 32, 32), "timestep": torch.ones((1,)).long()}
+    m0.zero_grad()
+    m0.eval()
+    losses = []
+    t0 = time.time()
+    for k in range(n_steps):
+        t = (k * torch.ones(B)).long()
+        out = m0(sched.add_noise(clean, noise, t), t).sample
+        loss = torch.nn.functional.mse_loss(out, noise)
+        loss.backward()
+        losses.append(loss.item())
+        if k % 10 == 0:
+            print(f"  cfg1 pass {k} loss {losses[-1]:.7f} ({time.time() - t0:.0f}s)", flush=True)
+    grad_fp = {k: fp(p.grad) for k, p in m0.named_parameters()}
+    res = {"n_steps": n_steps, "ratio": ratio, "B": B, "losses": losses, "grad_fp": grad_fp, "variants": {}}
+    for variant in ("vendored", "taylor", "diff"):
+        m = copy.deepcopy(m0)
+        for (k, p), (_, q) in zip(m.named_parameters(), m0.named_parameters()):
+            p.grad = q.grad.clone()
+        legacy_attn(m)
+        names = {mod: n for n, mod in m.named_modules()}
+        # the pinned behaviour: the vendored TaylorImportance class for "vendored" (unmodified reference code),
+        # the same class body with the product/abs placement switched for the two pip forms.
+        imp = tp.importance.TaylorImportance() if variant == "vendored" else VariantTaylor(variant)
+        pruner = tp.pruner.MagnitudePruner(m, example, importance=imp, iterative_steps=1, channel_groups={},
+                                           ch_sparsity=ratio, ignored_layers=[m.conv_out])
+        base_macs, base_params = tp.utils.count_ops_and_params(m, example)
+        checker = VariantTaylor(variant)
+        groups = []
+        # Scores are evaluated INTERACTIVELY: later groups see layers already sliced by earlier groups
+        # (ddpm_prune.py:108-109 + metapruner.py:205-254), so record each group right before it is pruned.
+        for g in pruner.step(interactive=True):
+            module, fn = g[0][0].target.module, g[0][0].handler
+            cur = pruner.DG.get_out_channels(module)
+            full = pruner.DG.get_pruning_group(module, fn, list(range(cur)))
+            ch_groups = pruner.get_channel_groups(full)
+            sc = checker(full, ch_groups=ch_groups)
+            sc_ref = imp(full, ch_groups=ch_groups)
+            assert torch.equal(sc, sc_ref), names[module]
+            sel = [int(i) for i in g[0][1]]
+            full_items = describe_group(full, names)
+            pr_items = describe_group(g, names)
+            # index mapping is positional: pruned idxs of every item == its full idxs at the selected positions
+            # (same traversal => same item order; a layer may appear twice when both halves of a concat are in the group)
+            assert len(full_items) == len(pr_items)
+            for (n, k, i), (n2, k2, fi) in zip(pr_items, full_items):
+                # a layer fed by BOTH halves of a concat owned by this group appears once with the two index lists
+                # merged (len = parts * channels); such items are skipped by the importance (:422-426) but pruned.
+                parts = len(fi) // cur
+                assert (n, k) == (n2, k2) and len(fi) == parts * cur, (n, k)
+                assert sorted(i) == sorted(fi[q * cur + j] for q in range(parts) for j in sel), (n, k)
+            n_pruned = cur - int(pruner.layer_init_out_ch[module] * (1 - pruner.get_target_sparsity(module)))
+            groups.append({"root": names[module], "root_kind": KIND[fn], "ch_groups": int(ch_groups), "channels": int(cur),
+                           "n_pruned": int(n_pruned), "items": [(n, k, compress(i)) for n, k, i in full_items],
+                           "imp": sc.clone(), "idxs": sel})
+            g.prune()
+        for mod in m.modules():
+            if isinstance(mod, (Upsample2D, Downsample2D)):
+                mod.channels = mod.conv.in_channels
+        macs, params = tp.utils.count_ops_and_params(m, example)
+        shapes = {k: list(v.shape) for k, v in m.state_dict().items()}
+        with torch.no_grad():  # pruned-model forward (legacy attention, stale scale)
+            t = (10 * torch.ones(2)).long()
+            out = m(sched.add_noise(clean[:2], noise[:2], t), t).sample
+        res["variants"][variant] = {"groups": groups, "base": [base_macs, base_params], "pruned": [macs, params],
+                                    "pruned_shapes": shapes, "pruned_eps_b2_t10": out.clone()}
+        print("cfg1", variant, base_params, params, macs, len(groups), sum(len(g["idxs"]) for g in groups), flush=True)
+    torch.save(res, os.path.join(OUT, out_name))
+
+
+def gen_cfg1_s3():
+    gen_cfg1(n_steps=3, out_name="cifar_cfg1_s3.pt")
+
+
+def gen_finetune():
+    cfg = dict(dp.TINY_TEST_CONFIG)
+    m = build(cfg).train()
+    sched = DDPMScheduler(num_train_timesteps=1000)
+    opt = torch.optim.Adam(m.parameters(), lr=2e-4, betas=(0.9, 0.999), weight_decay=0.0, eps=1e-8)
+    from diffusers.training_utils import EMAModel
+    ema = EMAModel(m.parameters(), decay=0.9999, use_ema_warmup=True, inv_gamma=1.0, power=0.75,
+                   model_cls=UNet2DModel, model_config=m.config)
+    g = torch.Generator().manual_seed(5)
+    rec = {"cfg": cfg, "steps": []}
+    for step in range(2):
+        clean = torch.randn(4, 3, 16, 16, generator=g)
+        noise = torch.randn(4, 3, 16, 16, generator=g)
+        t = torch.randint(0, 1000, (4 // 2 + 1,), generator=g)
+        t = torch.cat([t, 1000 - t - 1], dim=0)[:4]
+        noisy = sched.add_noise(clean, noise, t)
+        opt.zero_grad()
+        out = m(noisy, t).sample
+        loss = (noise - out).square().sum(dim=(1, 2, 3)).mean(dim=0)
+        loss.backward()
+        gn = torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+        opt.step()
+        ema.step(m.parameters())
+        rec["steps"].append({"clean": clean, "noise": noise, "t": t, "loss": loss.item(), "grad_norm": gn.item()})
+    rec["params"] = {k: p.detach().clone() for k, p in m.named_parameters()}
+    rec["ema"] = {k: s.clone() for (k, _), s in zip(m.named_parameters(), ema.shadow_params)}
+    torch.save(rec, os.path.join(OUT, "finetune_tiny.pt"))
+    print("finetune", [s["loss"] for s in rec["steps"]], [s["grad_norm"] for s in rec["steps"]])
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--skip-cfg1", action="store_true")
+    ap.add_argument("--only", default=None)
+    a = ap.parse_args()
+    torch.set_num_threads(os.cpu_count())
+    jobs = {"tiny": gen_tiny, "blocks": gen_blocks, "finetune": gen_finetune, "cifar_fwd": gen_cifar_fwd,
+            "cfg1_s3": gen_cfg1_s3, "cfg1": gen_cfg1}
+    for name, fn in jobs.items():
+        if a.only and name != a.only:
+            continue
+        if name.startswith("cfg1") and a.skip_cfg1:
+            continue
+        fn()
