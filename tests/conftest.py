@@ -35,8 +35,21 @@ def expand(idxs):
 
 
 def rel_err(a, b):
+    """||a-b|| / ||b||"""
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def worst_grad_err(named_grads, ref):
+    """max relative error over parameters.  d/d(to_k.bias) is identically zero (softmax over keys is invariant to
+    the per-query constant q.b_k), so both sides hold pure rounding noise there: checked absolutely instead."""
+    worst = 0.0
+    for k, g in named_grads:
+        if k.endswith("to_k.bias"):
+            assert float(g.abs().max()) < 1e-6 and float(ref[k].abs().max()) < 1e-6, k
+            continue
+        worst = max(worst, rel_err(g, ref[k]))
+    return worst
 
 
 def max_rel(a, b):

@@ -33,7 +33,8 @@ def test_tiny_unet_two_accumulated_passes():
         losses.append(orc.taylor_pass(sd, cfg, ac, clean, noise, t).item())
     assert losses == pytest.approx(G["losses"], rel=1e-6)
     for k, g in G["grads"].items():
-        assert rel_err(sd[k].grad, g) < 2e-5, k
+        if not k.endswith("to_k.bias"):   # identically-zero gradient, see conftest.worst_grad_err
+            assert rel_err(sd[k].grad, g) < 2e-5, k
     with torch.no_grad():
         out2 = orc.unet_forward(sd, cfg, orc.add_noise(ac, clean, noise, G["t2"]), G["t2"])
     assert max_rel(out2, G["out_t2"]) < 1e-6
