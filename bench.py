@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py — Taylor-score UNet fwd+bwd passes/sec (BASELINE.json metric) on N B200s.
+
+A "step" = one pass of ddpm_prune.py:97-102 (add_noise -> UNet fwd -> mse -> full bwd, gradients accumulated) over
+one synthetic Gaussian batch.  Workload (config.workload): C1 = CIFAR-10 DDPM UNet (tools/ddpm_cifar10_config.json,
+seed-0 random init), batch 128 x 3x32x32 — BASELINE configs[1] ("DDPM CIFAR-10 32x32 ... 1xB200"; batch from
+scripts/prune_ddpm_cifar10.sh).  Multi-GPU: timesteps are sharded across ranks (weak scaling: every rank runs K
+steps on its own timesteps) and the flat gradient arena is all-reduced ONCE at the end, inside the timed region.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--no-graph]
+Under torchrun the usual RANK/LOCAL_RANK/WORLD_SIZE/MASTER_* env is used; rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "taylor_score_unet_fwd_bwd_passes_per_sec"
+UNIT = "passes/s"
+CONV_FLOP_PER_IMAGE_PASS = 34.27e9   # 6 x 5.712 G MACs-equivalents, conv layers only
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), d.get("bf16_tflops", 1590.0), "measured"
+    return 6650.0, 1400.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle sampling DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(",") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for nm, v in zip(names, r[2:6]):
+                if "Active" in v and "Not" not in v:
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth_batch(B, seed_off=0):
+    g1, g2 = torch.Generator().manual_seed(1 + seed_off), torch.Generator().manual_seed(2 + seed_off)
+    return torch.randn(B, 3, 32, 32, generator=g1), torch.randn(B, 3, 32, 32, generator=g2)
+
+
+def _cpu_setup(sample_B):
+    import diff_pruning_b200 as dp
+    from oracle import unet_oracle as orc
+    torch.manual_seed(0)
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in dp.UNet2DModel(**dp.CIFAR10_DDPM_CONFIG).state_dict().items()}
+    ac = orc.alphas_cumprod()
+    clean, noise = synth_batch(sample_B)
+    return (lambda k: orc.taylor_pass(sd, dp.CIFAR10_DDPM_CONFIG, ac, clean, noise, (k * torch.ones(sample_B)).long()))
+
+
+def best_cpu_threads(one_pass):
+    """Give the CPU arm its best thread count: torch's intra-op pool over-subscribes badly on 100+ core hosts for
+    these small convs (measured 79 s/pass at 128 threads vs ~1.5 s at 8-32), so try a few and keep the fastest."""
+    ncpu = os.cpu_count() or 1
+    cands = sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu})
+    best, best_t = cands[0], None
+    for c in cands:
+        torch.set_num_threads(c)
+        one_pass(0)                       # warm-up at this thread count (oneDNN primitive creation)
+        t0 = time.time(); one_pass(1); dt = time.time() - t0
+        if best_t is None or dt < best_t:
+            best, best_t = c, dt
+        if dt > 4 * best_t:               # clearly past the knee: stop trying larger pools
+            break
+    torch.set_num_threads(best)
+    return best
+
+
+def cpu_oracle_passes(batch_equiv, sample_B, min_seconds, max_passes, threads=None):
+    """Times the CPU restatement of the reference path (oracle port; torch CPU ATen ops, the reference's own backend)."""
+    one_pass = _cpu_setup(sample_B)
+    threads = threads or best_cpu_threads(one_pass)
+    torch.set_num_threads(threads)
+    one_pass(0)
+    times = []
+    t_all = time.time()
+    k = 1
+    while len(times) < max_passes and (time.time() - t_all < min_seconds or len(times) < 2):
+        t0 = time.time()
+        one_pass(k)
+        times.append(time.time() - t0)
+        k += 1
+    med = statistics.median(times)
+    return {"value": (sample_B / med) / batch_equiv, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{threads} of {os.cpu_count()} host threads (fastest of a short sweep); {len(times)} timed + 1 warm-up oracle passes at batch {sample_B} (median {med:.2f} s/pass, best "
+                      f"{min(times):.2f}), scaled by {sample_B}/{batch_equiv} to batch-{batch_equiv} passes; loadavg {os.getloadavg()[0]:.1f}"}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    B = args.batch
+    sample_B = 16   # the reference's own CPU-runnable case (BASELINE configs[0])
+    one_pass = _cpu_setup(sample_B)
+    threads = best_cpu_threads(one_pass)
+    for w in range(args.warmup):
+        one_pass(w)
+    t0 = time.time()
+    for k in range(args.steps):
+        one_pass(k)
+    dt = time.time() - t0
+    value = (sample_B * args.steps / dt) / B
+    sample = (f"each step = one oracle (torch CPU fp32) Taylor pass at batch {sample_B} on {threads} of {os.cpu_count()} host threads (fastest of a short sweep), "
+              f"scaled by {sample_B}/{B} to batch-{B} passes")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"C1 CIFAR-10 DDPM UNet2DModel Taylor pass, batch {B} 3x32x32 (CPU sample batch {sample_B})"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}), flush=True)
+
+
+def conv_flops(plan):
+    """Algorithmic FLOPs of the 4-D-weight convolutions in one pass (fprop + dgrad + wgrad), from the plan."""
+    return plan.B * CONV_FLOP_PER_IMAGE_PASS
+
+
+def _timed_pass(scorer, events):
+    """Runs one pass step by step with events around the steps tagged as conv launches."""
+    p = scorer.plan
+    s_int = torch.cuda.current_stream().cuda_stream
+    s = torch.cuda.current_stream()
+    lib = p.lib
+    from diff_pruning_b200 import _lib as L
+    p.t_dev.fill_(3)
+    L.check(lib.dp_add_noise(scorer.clean.data_ptr(), scorer.noise.data_ptr(), p.t_dev.data_ptr(), scorer.acp.data_ptr(),
+                             p.x_in.ptr, scorer.B, scorer.C, scorer.H, scorer.W, 1, s_int))
+    pairs = []
+
+    def run_list(steps, tags):
+        for f, tag in zip(steps, tags):
+            if tag:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(s); f(s_int); e1.record(s)
+                pairs.append((e0, e1))
+            else:
+                f(s_int)
+    is_conv = lambda f: getattr(f, "what", "").startswith("conv")
+    run_list(p.fwd, [is_conv(f) for f in p.fwd])
+    gy = p.gradof(p.y_out)
+    L.check(lib.dp_mse_loss_grad(p.y_out.ptr, scorer.noise_nhwc.data_ptr(), gy.ptr, scorer.n, scorer.loss_scale, scorer.grad_scale,
+                                 scorer.partial.data_ptr(), scorer.loss.data_ptr(), s_int))
+    saved = p.grad_arena.clone()
+    p.gradof(p.silu_temb).t.zero_()
+    run_list(p.bwd_steps, [is_conv(f) for f in p.bwd_steps])
+    torch.cuda.synchronize()
+    p.grad_arena.copy_(saved)
+    return sum(a.elapsed_time(b) for a, b in pairs) * 1e-3, len(pairs)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+    import diff_pruning_b200 as dp
+    from diff_pruning_b200 import _lib as L
+    from diff_pruning_b200.scoring import TaylorScorer
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    lib = L.load()
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    B = args.batch
+    torch.manual_seed(0)
+    model = dp.UNet2DModel(**dp.CIFAR10_DDPM_CONFIG).eval().to(dev)
+    clean, noise = synth_batch(B, seed_off=100 * rank)
+    clean_pin, noise_pin = clean.pin_memory(), noise.pin_memory()
+    model.zero_grad()
+    l0 = lib.dp_launch_count()
+    sc = TaylorScorer(model, clean.to(dev), noise.to(dev), use_graph=not (args.no_graph or args.profile_pass))
+    if args.profile_pass:   # for ncu: `--profile-from-start off`; exactly one eager pass inside the profiler range
+        for k in range(2):
+            sc.step(k)
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.start()
+        sc.step(5)
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.stop()
+        return
+    # timesteps: rank r takes t = r, r+W, r+2W, ...
+    ts = [(rank + k * world) % 1000 for k in range(args.warmup + args.steps)]
+    for k in range(args.warmup):
+        sc.step(ts[k])
+    torch.cuda.synchronize(dev)
+    launches_per_pass = None
+    if not args.no_graph:
+        # the graph replays exactly the launches recorded by one eager body
+        c0 = lib.dp_launch_count(); saved = sc.plan.grad_arena.clone(); sc._body(); sc.plan.grad_arena.copy_(saved)
+        launches_per_pass = lib.dp_launch_count() - c0
+        torch.cuda.synchronize(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---------------- device-resident timing
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    c_before = lib.dp_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        sc.step(ts[args.warmup + k])
+    if world > 1:
+        dist.all_reduce(sc.plan.grad_arena, op=dist.ReduceOp.SUM)   # the one collective of the scoring path
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    eager_launches = lib.dp_launch_count() - c_before
+    gpu_launches = eager_launches if args.no_graph else launches_per_pass * args.steps
+    # ---------------- end-to-end through host buffers (H2D batch each step, D2H loss each step)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for k in range(args.steps):
+        sc.step_from_host(clean_pin, noise_pin, ts[args.warmup + k])
+    if world > 1:
+        dist.all_reduce(sc.plan.grad_arena, op=dist.ReduceOp.SUM)
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        return
+    # ---------------- roofline of the dominant kernel (conv implicit GEMM), live CUDA events
+    conv_s, n_conv = _timed_pass(sc, None)
+    hbm, tf_sus, tf_burst, which = peaks()
+    flops = conv_flops(sc.plan)
+    achieved = flops / conv_s / 1e12
+    tc = bool(lib.dp_tc_available())
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": tf_sus, "unit": "TFLOP/s", "frac": achieved / tf_sus,
+                "traffic": None,
+                "kernel": "conv implicit GEMM (fprop+dgrad+wgrad launches of one pass: %d)" % n_conv,
+                "note": (f"algorithmic conv FLOPs/pass = {B} x 34.27 GFLOP (SURVEY.md §8d) / summed conv-launch device time "
+                         f"{conv_s * 1e3:.2f} ms of a {ms / args.steps:.2f} ms step; peak = bf16_tflops_sustained ({which}); "
+                         "fp32-exact tier: " + ("tcgen05 3xTF32" if tc else "CUDA-core FFMA (SIMT) — tensor path not active"))}
+    value = world * args.steps / (ms * 1e-3)
+    e2e = world * args.steps / (ms_e2e * 1e-3)
+    cpu = cpu_oracle_passes(B, 16, min_seconds=12.0, max_passes=8) if args.gpus == 1 and not args.no_cpu else None
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"C1 CIFAR-10 DDPM UNet2DModel (35.7M params, seed-0 init) Taylor pass, batch {B} x 3x32x32 per GPU, "
+                               f"timesteps sharded over {world} GPU(s), one grad all-reduce at the end",
+                   "l2": "per-pass working set (activations+grads, GBs) >> 126 MB L2: inputs larger than L2, no explicit flush",
+                   "cuda_graph": not args.no_graph, "imgs_per_s": value * B},
+        "clocks": clocks, "gpu_launches": int(gpu_launches),
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(2 * clean.numel() * 4 + 8 * B), "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "roofline": roofline,
+    }
+    if cpu is not None:
+        out["cpu_baseline"] = cpu
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=128)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--profile-pass", action="store_true", help="run one eager pass inside cudaProfilerStart/Stop (ncu)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    rank, world, local_rank = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    run_ours(args, rank, world, local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -179,6 +179,7 @@ class Plan:
                 rc = fn(s)
                 if rc:
                     check(rc, what)
+        run.what = what
         lst.append(run)
 
     def _bitem(self) -> BItem:
@@ -290,7 +291,7 @@ class Plan:
         ra.K, ra.C, ra.R, ra.S, ra.splits = K, Cin, R, S, splits
         ra.dw = self.pgrad(w)
         self._late.append(lambda ra=ra: setattr(ra, "workspace", self.sptr("wgrad_ws")))
-        self._rec(steps, lib.dp_conv2d_wgrad_reduce, ra, "wgrad reduce")
+        self._rec(steps, lib.dp_conv2d_wgrad_reduce, ra, "conv wgrad reduce")
         # 3. dgrad
         if need_dx:
             da = _copy_args(a)
