@@ -14,7 +14,7 @@ i32, i64, f32, u64, vp = C.c_int32, C.c_int64, C.c_float, C.c_uint64, C.c_void_p
 class ConvArgs(C.Structure):
     _fields_ = [(n, i32) for n in ("N", "H", "W", "C", "P", "Q", "K", "R", "S", "stride", "pad_t", "pad_l", "flags",
                                    "splits")] + [
-        ("x", vp), ("ldx", i64), ("y", vp), ("ldy", i64), ("w", vp), ("w_lo", vp), ("bias", vp), ("rowadd", vp),
+        ("x", vp), ("ldx", i64), ("y", vp), ("ldy", i64), ("w", vp), ("w_tc_hi", vp), ("w_tc_lo", vp), ("bias", vp), ("rowadd", vp),
         ("ld_rowadd", i64), ("residual", vp), ("ld_res", i64), ("workspace", vp)]
 
 
@@ -60,6 +60,7 @@ _SIGS = {
     "dp_conv2d_wgrad": (C.c_int, [C.POINTER(ConvArgs), vp]),
     "dp_conv2d_wgrad_reduce": (C.c_int, [C.POINTER(WgradReduceArgs), vp]),
     "dp_pack_conv_weight": (C.c_int, [vp, i32, i32, i32, i32, vp, vp, vp]),
+    "dp_pack_conv_weight_tc": (C.c_int, [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp]),
     "dp_gemm_batched": (C.c_int, [C.POINTER(GemmArgs), vp]),
     "dp_softmax_fwd": (C.c_int, [vp, vp, i64, i32, vp]),
     "dp_softmax_bwd": (C.c_int, [vp, vp, vp, i64, i32, vp]),

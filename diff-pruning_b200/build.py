@@ -43,7 +43,7 @@ def build(force=False, verbose=False):
             if verbose:
                 sys.stderr.write(r.stderr)
         objs.append(o)
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart", "-lcuda"]
+    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

@@ -1,0 +1,418 @@
+// conv_tc.cu — tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a (fprop, and stride-1 dgrad as a
+// tap-flipped fprop), fp32-grade via the 3xTF32 split:
+//     x*w ~= hi(x)*hi(w) + lo(x)*hi(w) + hi(x)*lo(w),   hi = cvt.rna.tf32(.), lo = . - hi  (exact in fp32)
+// with fp32 accumulation in TMEM.
+//
+// GEMM view: M = N*H*W output pixels (tile of 128 = one TMA box of the NHWC activation), N = output channels
+// (tile BN), K = taps x input channels, one pipeline stage = (one tap, 32 channels) = a 128-byte swizzle row.
+//
+// Warp roles (192 threads, 1 CTA / SM):
+//   warp 0      TMA producer: raw fp32 A box [128 px][32 ch] (im2col-free: the tap shift is a coordinate offset,
+//               image borders are TMA out-of-bounds zero fill) + pre-split B_hi / B_lo weight tiles
+//   warps 2..5  splitter: A (in place) -> hi, A_lo <- lo, smem->reg->smem, then fence.proxy.async + mbarrier
+//   warp 1      MMA issuer (one lane): 4 k-steps x 3 tcgen05.mma.kind::tf32 per stage, tcgen05.commit frees the stage
+//   warps 2..5  epilogue: tcgen05.ld accumulator rows, + bias / + per-image temb row / + residual / accumulate, store
+#include <cuda.h>
+#include <cstdlib>
+#include <mutex>
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BK = 32, STAGES = 3, NTHREADS = 192;
+constexpr int A_BYTES = BM * BK * 4;  // 16 KB
+
+struct TcParams {
+  int Nimg, H, W;
+  int Nout;            // GEMM N (valid output channels)
+  int R, S, pad, flip;
+  int kchunks;         // ceil(Kg / 32)
+  int bw, bh, bn, tiles_w, tiles_h;
+  float* y; long long ldy;
+  const float* bias;
+  const float* rowadd; long long ld_rowadd;
+  const float* residual; long long ld_res;
+  int accumulate;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// K-major, 128B-swizzled operand tile descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO(1)<<16 | SBO(1024B>>4)<<32
+// | version(1)<<46 | layout SWIZZLE_128B(2)<<61
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBh,
+               const __grid_constant__ CUtensorMap mapBl, const TcParams p) {
+  constexpr int B_BYTES = BN * BK * 4;
+  constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t pad_to = ((raw + 1023u) & ~1023u) - raw;
+  uint8_t* smem = smem_raw + pad_to;                 // 1024B aligned: required by SWIZZLE_128B (TMA and UMMA agree)
+  const uint32_t sbase = raw + pad_to;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  const uint32_t bar0 = sbase + STAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto conv_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
+  const uint32_t tmem_full_bar = bar0 + 8u * (3 * STAGES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(conv_bar(s), 128);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    // 2*BN columns: [0,BN) main accumulator (hi*hi), [BN,2BN) correction accumulator (lo*hi + hi*lo).  The tensor core
+    // adds into an fp32 accumulator with one (truncating) rounding per MMA; keeping the 2^-11-smaller correction terms
+    // out of the main accumulator cuts its rounding count 3x and keeps the small terms from being absorbed.
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  // ---- tile coordinates
+  const int tile_m = blockIdx.x, nblk = blockIdx.y;
+  const int tw = tile_m % p.tiles_w;
+  const int th = (tile_m / p.tiles_w) % p.tiles_h;
+  const int tn = tile_m / (p.tiles_w * p.tiles_h);
+  const int q0 = tw * p.bw, p0 = th * p.bh, n0 = tn * p.bn;
+  const int T = p.R * p.S;
+  const int num_iters = T * p.kchunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapBh)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapBl)) : "memory");
+      for (int it = 0; it < num_iters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        mbar_expect_tx(full_bar(s), A_BYTES + 2 * B_BYTES);
+        const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
+        const int r = tap / p.S, sx = tap - r * p.S;
+        const uint32_t st = sbase + s * STAGE_BYTES;
+        tma_load_4d(st, &mapA, full_bar(s), kc * BK, q0 + sx - p.pad, p0 + r - p.pad, n0);
+        const int tapb = p.flip ? (T - 1 - tap) : tap;
+        tma_load_3d(st + 2 * A_BYTES, &mapBh, full_bar(s), kc * BK, nblk * BN, tapb);
+        tma_load_3d(st + 2 * A_BYTES + B_BYTES, &mapBl, full_bar(s), kc * BK, nblk * BN, tapb);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 (1<<4) | A=TF32 (2<<7) | B=TF32 (2<<10) | K-major A,B |
+      // N>>3 at bit 17 | M>>4 at bit 24
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      for (int it = 0; it < num_iters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(conv_bar(s), ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t st = sbase + s * STAGE_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k) {
+          const uint64_t a_hi = umma_desc(st + k * 32), a_lo = umma_desc(st + A_BYTES + k * 32);
+          const uint64_t b_hi = umma_desc(st + 2 * A_BYTES + k * 32), b_lo = umma_desc(st + 2 * A_BYTES + B_BYTES + k * 32);
+          const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
+          umma_tf32(tmem_base + BN, a_lo, b_hi, idesc, first);
+          umma_tf32(tmem_base + BN, a_hi, b_lo, idesc, 1u);
+          umma_tf32(tmem_base, a_hi, b_hi, idesc, first);
+        }
+        umma_commit(empty_bar(s));   // stage free once these MMAs have consumed it
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    // ---- splitter: raw fp32 A tile -> (hi in place, lo)
+    const int ct = threadIdx.x - 64;
+    for (int it = 0; it < num_iters; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      mbar_wait(full_bar(s), ph);
+      float4* A = reinterpret_cast<float4*>(smem + s * STAGE_BYTES);
+      float4* Al = reinterpret_cast<float4*>(smem + s * STAGE_BYTES + A_BYTES);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int idx = ct + 128 * i;
+        float4 v = A[idx], h, l;
+        h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+        l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+        A[idx] = h;
+        Al[idx] = l;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+      mbar_arrive(conv_bar(s));
+    }
+    // ---- epilogue
+    mbar_wait(tmem_full_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int w_l = row % p.bw, h_l = (row / p.bw) % p.bh, n_l = row / (p.bw * p.bh);
+    const int img = n0 + n_l;
+    const bool row_ok = img < p.Nimg;
+    const long long m = ((long long)img * p.H + (p0 + h_l)) * p.W + (q0 + w_l);
+    float* yrow = p.y + m * p.ldy;
+    const float* rrow = p.residual ? p.residual + m * p.ld_res : nullptr;
+    const float* arow = p.rowadd ? p.rowadd + (long long)img * p.ld_rowadd : nullptr;
+#pragma unroll 1
+    for (int j = 0; j < BN / 32; ++j) {
+      uint32_t v[32], u[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 32);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+            "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
+            "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
+            "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+          : "r"(taddr + (uint32_t)BN));
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+            "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+            "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (row_ok) {
+        const int c0 = nblk * BN + j * 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int c = c0 + i;
+          if (c < p.Nout) {
+            float o = __uint_as_float(v[i]) + __uint_as_float(u[i]);
+            if (p.bias) o += __ldg(p.bias + c);
+            if (arow) o += __ldg(arow + c);
+            if (rrow) o += __ldg(rrow + c);
+            if (p.accumulate) o += yrow[c];
+            yrow[c] = o;
+          }
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+int g_tc_state = -1;  // -1 unknown, 0 unavailable, 1 ok
+std::mutex g_tc_mutex;
+
+int tc_init() {
+  std::lock_guard<std::mutex> lk(g_tc_mutex);
+  if (g_tc_state >= 0) return g_tc_state;
+  g_tc_state = 0;
+  if (getenv("DPB200_FORCE_SIMT")) return 0;
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess || major != 10) { (void)cudaGetLastError(); return 0; }
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+      qres != cudaDriverEntryPointSuccess) { (void)cudaGetLastError(); return 0; }
+  g_encode = (EncodeTiledFn)fn;
+  bool ok = cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 STAGES * (2 * A_BYTES + 2 * 128 * BK * 4) + 2048) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  STAGES * (2 * A_BYTES + 2 * 64 * BK * 4) + 2048) == cudaSuccess;
+  if (!ok) { (void)cudaGetLastError(); return 0; }
+  g_tc_state = 1;
+  return 1;
+}
+
+bool make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+              const cuuint32_t* box) {
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// 128-pixel box of an [N][H][W] grid
+bool pick_box(int N, int H, int W, int& bw, int& bh, int& bn) {
+  if (W >= BM) {
+    if (W % BM) return false;
+    bw = BM; bh = 1; bn = 1; return true;
+  }
+  if (BM % W) return false;
+  bw = W;
+  int rem = BM / W;
+  if (H >= rem) {
+    if (H % rem) return false;
+    bh = rem; bn = 1; return true;
+  }
+  if (rem % H) return false;
+  bh = H; bn = rem / H;
+  return true;
+}
+
+// Shared launcher.  act: [Nimg][H][W][Kg] view (ld_act) = A operand; w_hi/w_lo: [T][Nout][Kg]; out: [Nimg][H][W][Nout] view.
+int launch_tc(const float* act, long long ld_act, int Nimg, int H, int W, int Kg, const float* w_hi, const float* w_lo, int Nout,
+              int R, int S, int pad, int flip, float* out, long long ld_out, const float* bias, const float* rowadd,
+              long long ld_rowadd, const float* residual, long long ld_res, int accumulate, cudaStream_t st) {
+  if (!tc_init()) return DP_ERR_UNSUPPORTED;
+  if (!w_hi || !w_lo) return DP_ERR_UNSUPPORTED;
+  if (Kg % 4 || ld_act % 4 || ((uintptr_t)act & 15) || ((uintptr_t)w_hi & 15) || ((uintptr_t)w_lo & 15)) return DP_ERR_UNSUPPORTED;
+  if (Kg < 16 || Nout < 8) return DP_ERR_UNSUPPORTED;   // degenerate GEMMs stay on the SIMT path
+  int bw, bh, bn;
+  if (!pick_box(Nimg, H, W, bw, bh, bn)) return DP_ERR_UNSUPPORTED;
+  const int T = R * S;
+  CUtensorMap mA, mBh, mBl;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)Kg, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Nimg};
+    cuuint64_t str[3] = {(cuuint64_t)ld_act * 4, (cuuint64_t)W * ld_act * 4, (cuuint64_t)H * W * ld_act * 4};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+    if (!make_map(&mA, act, 4, dims, str, box)) return DP_ERR_UNSUPPORTED;
+  }
+  const int BN = (Nout <= 64) ? 64 : 128;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)Kg, (cuuint64_t)Nout, (cuuint64_t)T};
+    cuuint64_t str[2] = {(cuuint64_t)Kg * 4, (cuuint64_t)Nout * Kg * 4};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BN, 1};
+    if (!make_map(&mBh, w_hi, 3, dims, str, box) || !make_map(&mBl, w_lo, 3, dims, str, box)) return DP_ERR_UNSUPPORTED;
+  }
+  TcParams p{};
+  p.Nimg = Nimg; p.H = H; p.W = W; p.Nout = Nout; p.R = R; p.S = S; p.pad = pad; p.flip = flip;
+  p.kchunks = (Kg + BK - 1) / BK;
+  p.bw = bw; p.bh = bh; p.bn = bn; p.tiles_w = W / bw; p.tiles_h = H / bh;
+  p.y = out; p.ldy = ld_out; p.bias = bias; p.rowadd = rowadd; p.ld_rowadd = ld_rowadd; p.residual = residual; p.ld_res = ld_res;
+  p.accumulate = accumulate;
+  const int tiles_n = (Nimg + bn - 1) / bn;
+  dim3 grid((unsigned)(p.tiles_w * p.tiles_h * tiles_n), (unsigned)((Nout + BN - 1) / BN));
+  if (BN == 64) {
+    size_t smem = STAGES * (2 * A_BYTES + 2 * 64 * BK * 4) + 2048;
+    conv_tc_kernel<64><<<grid, NTHREADS, smem, st>>>(mA, mBh, mBl, p);
+  } else {
+    size_t smem = STAGES * (2 * A_BYTES + 2 * 128 * BK * 4) + 2048;
+    conv_tc_kernel<128><<<grid, NTHREADS, smem, st>>>(mA, mBh, mBl, p);
+  }
+  return dp_check_launch();
+}
+
+__global__ void pack_tc_kernel(const float* __restrict__ w, int K, int C, int RS, float* __restrict__ kc_hi, float* __restrict__ kc_lo,
+                               float* __restrict__ ck_hi, float* __restrict__ ck_lo) {
+  long long total = (long long)K * C * RS;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int tap = (int)(i % RS);
+    long long kc = i / RS;
+    int c = (int)(kc % C), k = (int)(kc / C);
+    float v = w[i], h = tf32_rna(v), l = v - h;
+    long long a = ((long long)tap * K + k) * C + c, b = ((long long)tap * C + c) * K + k;
+    if (kc_hi) kc_hi[a] = h;
+    if (kc_lo) kc_lo[a] = l;
+    if (ck_hi) ck_hi[b] = h;
+    if (ck_lo) ck_lo[b] = l;
+  }
+}
+}  // namespace
+
+int dp_tc_runtime_ok() { return tc_init(); }
+
+int dp_conv2d_fprop_tc(const dp_conv_args* a, dp_stream_t stream) {
+  if (!a || !a->x || !a->y) return DP_ERR_UNSUPPORTED;   // let the SIMT entry produce the precise error
+  if (a->stride != 1 || a->R != a->S || (a->R != 1 && a->R != 3) || a->pad_t != (a->R - 1) / 2 || a->pad_l != a->pad_t) return DP_ERR_UNSUPPORTED;
+  if (a->P != a->H || a->Q != a->W) return DP_ERR_UNSUPPORTED;
+  if (a->N <= 0 || a->H <= 0 || a->W <= 0 || a->C <= 0 || a->K <= 0 || a->ldx < a->C || a->ldy < a->K) return DP_ERR_UNSUPPORTED;
+  return launch_tc((const float*)a->x, a->ldx, a->N, a->H, a->W, a->C, a->w_tc_hi, a->w_tc_lo, a->K, a->R, a->S, a->pad_t, 0,
+                   (float*)a->y, a->ldy, a->bias, a->rowadd, a->ld_rowadd, a->residual, a->ld_res,
+                   (a->flags & DP_CONV_ACCUMULATE) ? 1 : 0, (cudaStream_t)stream);
+}
+
+// stride-1 dgrad == fprop of dy with the taps flipped and the (K,C) roles swapped: dx[n,h,w,c] = sum dy[n,h+1-r,w+1-s,k] W[k,c,r,s]
+int dp_conv2d_dgrad_tc(const dp_conv_args* a, dp_stream_t stream) {
+  if (!a || !a->x || !a->y) return DP_ERR_UNSUPPORTED;
+  if (a->stride != 1 || a->R != a->S || (a->R != 1 && a->R != 3) || a->pad_t != (a->R - 1) / 2 || a->pad_l != a->pad_t) return DP_ERR_UNSUPPORTED;
+  if (a->P != a->H || a->Q != a->W) return DP_ERR_UNSUPPORTED;
+  if (a->N <= 0 || a->H <= 0 || a->W <= 0 || a->C <= 0 || a->K <= 0 || a->ldx < a->C || a->ldy < a->K) return DP_ERR_UNSUPPORTED;
+  return launch_tc((const float*)a->y, a->ldy, a->N, a->H, a->W, a->K, a->w_tc_hi, a->w_tc_lo, a->C, a->R, a->S, a->pad_t, 1,
+                   (float*)a->x, a->ldx, nullptr, nullptr, 0, nullptr, 0, (a->flags & DP_CONV_ACCUMULATE) ? 1 : 0,
+                   (cudaStream_t)stream);
+}
+
+int dp_conv2d_wgrad_tc(const dp_conv_args*, dp_stream_t) { return DP_ERR_UNSUPPORTED; }
+
+extern "C" int dp_pack_conv_weight_tc(const float* w, int32_t K, int32_t C, int32_t R, int32_t S, float* kc_hi, float* kc_lo,
+                                      float* ck_hi, float* ck_lo, dp_stream_t stream) {
+  DP_REQUIRE(w, DP_ERR_NULL);
+  DP_REQUIRE(K > 0 && C > 0 && R > 0 && S > 0, DP_ERR_SHAPE);
+  long long total = (long long)K * C * R * S;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pack_tc_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, K, C, R * S, kc_hi, kc_lo, ck_hi, ck_lo);
+  return dp_check_launch();
+}

@@ -80,6 +80,7 @@ class Plan:
     def __init__(self, model: UNet2DModel, batch: int, height: int, width: int, device, training: bool = False,
                  need_grad: bool = True):
         self.lib = L.load()
+        self.tc = bool(self.lib.dp_tc_available()) if torch.device(device).type == "cuda" else False
         self.model = model
         self.B, self.H, self.W = batch, height, width
         self.dev = torch.device(device)
@@ -201,8 +202,14 @@ class Plan:
         lib = self.lib
         self._rec(self.pack, lambda s, w=w, K=K, Cin=Cin, R=R, S=S, a=wck, b=wkc:
                   lib.dp_pack_conv_weight(w.data_ptr(), K, Cin, R, S, a.data_ptr(), b.data_ptr(), s), what="pack")
-        self._packs[id(w)] = (wck, wkc)
-        return wck, wkc
+        tc = None
+        if self.tc and K * Cin >= 256:
+            tc = tuple(torch.empty(w.numel(), device=self.dev, dtype=torch.float32) for _ in range(4))  # kc_hi kc_lo ck_hi ck_lo
+            self._rec(self.pack, lambda s, w=w, K=K, Cin=Cin, R=R, S=S, t=tc:
+                      lib.dp_pack_conv_weight_tc(w.data_ptr(), K, Cin, R, S, t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(),
+                                                 t[3].data_ptr(), s), what="pack tc")
+        self._packs[id(w)] = (wck, wkc, tc)
+        return wck, wkc, tc
 
     def _colsum_tree(self, steps: List[Step], src_ptr: int, ld: int, rows: int, per_img: int, cols: int,
                      seg_name: Optional[str]) -> str:
@@ -237,8 +244,10 @@ class Plan:
         R = w.shape[2] if w.dim() == 4 else 1
         S = w.shape[3] if w.dim() == 4 else 1
         assert x.C == Cin and out.C == K, (x.C, Cin, out.C, K)
-        wck, wkc = self._packed(w)
+        wck, wkc, wtc = self._packed(w)
         a = L.ConvArgs()
+        if wtc is not None:
+            a.w_tc_hi, a.w_tc_lo = wtc[0].data_ptr(), wtc[1].data_ptr()
         a.N, a.H, a.W, a.C = x.N, x.H, x.W, x.C
         a.P, a.Q, a.K = out.H, out.W, K
         a.R, a.S, a.stride, a.pad_t, a.pad_l = R, S, stride, pad, pad
@@ -297,6 +306,8 @@ class Plan:
             da = _copy_args(a)
             da.ldy = dy_ld
             da.w = wkc.data_ptr()
+            if wtc is not None:
+                da.w_tc_hi, da.w_tc_lo = wtc[2].data_ptr(), wtc[3].data_ptr()
             da.flags = 0
             da.rowadd, da.residual, da.bias = None, None, None
             self._late.append(lambda da=da, g=dy_get: setattr(da, "y", g()))
@@ -637,7 +648,7 @@ class Plan:
     def bytes_allocated(self) -> int:
         n = sum(t.numel() * t.element_size() for t in self._keep if isinstance(t, torch.Tensor))
         n += sum(t.numel() * 4 for t in self._gbuf.values()) + sum(t.numel() * 4 for t in self._scratch.values())
-        n += sum(a.numel() * 8 for a, _ in self._packs.values()) + self.grad_arena.numel() * 4
+        n += sum(a.numel() * (8 + (16 if tc else 0)) for a, _, tc in self._packs.values()) + self.grad_arena.numel() * 4
         return n
 
 

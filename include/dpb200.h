@@ -65,7 +65,8 @@ typedef struct dp_conv_args {
   void* y;             /* fprop: out  | dgrad: in (dy)  | wgrad: in (dy) */
   int64_t ldy;
   const float* w;      /* fprop: packed [R*S][C][K] | dgrad: packed [R*S][K][C] (dp_pack_conv_weight) */
-  const float* w_lo;   /* reserved for the tensor-core path (residual term of the 3xTF32 split), may be NULL */
+  const float* w_tc_hi; /* optional tensor-core operand (dp_pack_conv_weight_tc): TF32-rounded part, GEMM-K contiguous: */
+  const float* w_tc_lo; /*   fprop [R*S][K][C] | dgrad [R*S][C][K]; w_tc_lo = w - w_tc_hi (3xTF32 split). NULL => SIMT path */
   const float* bias;   /* fprop epilogue: + bias[K]                                   (nullable) */
   const float* rowadd; /* fprop epilogue: + rowadd[n*ld_rowadd + k] per image n (temb, resnet.py:618-621) (nullable) */
   int64_t ld_rowadd;
@@ -97,6 +98,11 @@ int dp_conv2d_wgrad_reduce(const dp_wgrad_reduce_args* a, dp_stream_t stream);
 /* OIHW -> w_ck [R*S][C][K] (fprop operand) and w_kc [R*S][K][C] (dgrad operand); either output may be NULL */
 int dp_pack_conv_weight(const float* w_oihw, int32_t K, int32_t C, int32_t R, int32_t S, float* w_ck, float* w_kc,
                         dp_stream_t stream);
+
+/* 3xTF32 operands for the tcgen05 path: hi = cvt.rna.tf32(w), lo = w - hi (exact), each in both K-major forms:
+ *   kc_* [R*S][K][C] (fprop B operand, GEMM-K = C)   ck_* [R*S][C][K] (dgrad B operand, GEMM-K = K).  Any may be NULL. */
+int dp_pack_conv_weight_tc(const float* w_oihw, int32_t K, int32_t C, int32_t R, int32_t S, float* kc_hi, float* kc_lo,
+                           float* ck_hi, float* ck_lo, dp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Batched strided GEMM  C[b] (=|+=) alpha * A[b] x B[b]   (attention core: aten::baddbmm/bmm,

@@ -1,0 +1,125 @@
+"""tcgen05/TMA implicit-GEMM convolution (conv_tc.cu) vs plain torch fp32 CPU convolution.
+Tolerance: 3xTF32 split products carry ~2^-22 relative error each, fp32 accumulation in TMEM => 1.5e-5 on the tensor."""
+import ctypes as C
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as ge
+    ge.build()
+    from diff_pruning_b200 import _lib as L
+    lib = L.load()
+    if not lib.dp_tc_available():
+        pytest.fail("tensor-core path (tcgen05/TMA) not available on this device: conv_tc.cu must run on sm_100a")
+    return lib
+
+
+def S():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous().cuda()
+
+
+def nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous().cpu()
+
+
+CASES = [
+    # N, C, H, W, K, R, ld_extra_in, ld_extra_out
+    (2, 64, 16, 16, 128, 3, 0, 0),
+    (2, 32, 16, 16, 32, 3, 0, 0),       # BN=64 kernel, single k-chunk
+    (8, 256, 4, 4, 256, 3, 0, 0),       # 4x4 images: 8 images per 128-row box, two N tiles
+    (3, 96, 8, 8, 96, 3, 0, 0),         # pruned widths (96): partial N tile, 3 k-chunks; N not a multiple of the box
+    (1, 128, 32, 32, 128, 3, 64, 32),   # views inside wider (concat) buffers, 32x32 (box = 4 rows x 32)
+    (2, 256, 16, 16, 64, 1, 0, 0),      # 1x1 shortcut
+    (4, 40, 8, 8, 200, 1, 0, 0),        # ragged channel counts (K-chunk and N-tile tails)
+    (128, 512, 1, 1, 256, 1, 0, 0),     # time_emb_proj as a 1x1 conv over [B,1,1,512]
+]
+
+
+@pytest.mark.parametrize("N,Cin,H,W,K,R,ldx,ldy", CASES)
+def test_conv_tc_fprop_dgrad(lib, N, Cin, H, W, K, R, ldx, ldy):
+    from diff_pruning_b200 import _lib as L
+    g = torch.Generator().manual_seed(N + Cin + K)
+    pad = (R - 1) // 2
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(K, Cin, R, R, generator=g) / math.sqrt(Cin * R * R)
+    b = torch.randn(K, generator=g)
+    xr, wr = x.clone().requires_grad_(True), w.clone()
+    y_ref = F.conv2d(xr, wr, b, padding=pad)
+    rowadd, res = torch.randn(N, K, generator=g), torch.randn(N, K, H, W, generator=g)
+    gy = torch.randn(N, K, H, W, generator=g)
+    y_ref.backward(gy)
+    wd = w.contiguous().cuda()
+    packs = [torch.empty(w.numel(), device="cuda") for _ in range(4)]
+    assert lib.dp_pack_conv_weight_tc(wd.data_ptr(), K, Cin, R, R, *[p.data_ptr() for p in packs], S()) == 0
+    simt_ck, simt_kc = torch.empty(w.numel(), device="cuda"), torch.empty(w.numel(), device="cuda")
+    assert lib.dp_pack_conv_weight(wd.data_ptr(), K, Cin, R, R, simt_ck.data_ptr(), simt_kc.data_ptr(), S()) == 0
+    # hi + lo reproduces w exactly, hi has 13 zero low bits
+    assert torch.equal(packs[0] + packs[1], simt_kc) and torch.equal(packs[2] + packs[3], simt_ck)
+    assert int((packs[0].view(torch.int32) & 0x1FFF).abs().max()) == 0
+    xb = torch.randn(N, H, W, Cin + ldx, generator=g).cuda()
+    xb[..., ldx:] = nhwc(x)
+    yb = torch.full((N, H, W, K + ldy), 7.0, device="cuda")
+    a = L.ConvArgs()
+    a.N, a.H, a.W, a.C, a.P, a.Q, a.K = N, H, W, Cin, H, W, K
+    a.R = a.S = R
+    a.stride, a.pad_t, a.pad_l, a.splits = 1, pad, pad, 1
+    a.x, a.ldx, a.y, a.ldy = xb.data_ptr() + 4 * ldx, Cin + ldx, yb.data_ptr() + 4 * ldy, K + ldy
+    a.w, a.w_tc_hi, a.w_tc_lo = simt_ck.data_ptr(), packs[0].data_ptr(), packs[1].data_ptr()
+    bd, rd, resd = b.cuda(), rowadd.cuda().contiguous(), nhwc(res)
+    a.bias, a.rowadd, a.ld_rowadd, a.residual, a.ld_res = bd.data_ptr(), rd.data_ptr(), K, resd.data_ptr(), K
+    n0 = lib.dp_launch_count()
+    assert lib.dp_conv2d_fprop(C.byref(a), S()) == 0
+    torch.cuda.synchronize()
+    y_full = y_ref.detach() + rowadd[:, :, None, None] + res
+    assert rel_err(nchw(yb[..., ldy:]), y_full) < 1.5e-5
+    assert float((yb[..., :ldy] - 7.0).abs().sum()) == 0.0          # neighbours in the wider buffer untouched
+    # same call forced onto the SIMT path agrees (and is the exact-fp32 reference on device)
+    y2 = torch.zeros(N, H, W, K, device="cuda")
+    a2 = L.ConvArgs()
+    C.memmove(C.byref(a2), C.byref(a), C.sizeof(a))
+    a2.flags, a2.y, a2.ldy = 2, y2.data_ptr(), K
+    assert lib.dp_conv2d_fprop(C.byref(a2), S()) == 0
+    assert rel_err(yb[..., ldy:], y2) < 1.5e-5
+    # accumulate epilogue
+    a.flags, a.bias, a.rowadd, a.residual = 1, None, None, None
+    assert lib.dp_conv2d_fprop(C.byref(a), S()) == 0
+    assert rel_err(nchw(yb[..., ldy:]), y_full + (y_ref.detach() - b[None, :, None, None])) < 1.5e-5
+    # dgrad (tap-flipped fprop of dy) into a strided view, then accumulate
+    gyd = nhwc(gy)
+    gxb = torch.zeros(N, H, W, Cin + ldx, device="cuda")
+    d = L.ConvArgs()
+    C.memmove(C.byref(d), C.byref(a), C.sizeof(a))
+    d.flags = 0
+    d.x, d.ldx, d.y, d.ldy = gxb.data_ptr() + 4 * ldx, Cin + ldx, gyd.data_ptr(), K
+    d.w, d.w_tc_hi, d.w_tc_lo = simt_kc.data_ptr(), packs[2].data_ptr(), packs[3].data_ptr()
+    assert lib.dp_conv2d_dgrad(C.byref(d), S()) == 0
+    print("fprop err", rel_err(nchw(yb[..., ldy:]), y_full + (y_ref.detach() - b[None, :, None, None])), "dgrad err", rel_err(nchw(gxb[..., ldx:]), xr.grad))
+    assert rel_err(nchw(gxb[..., ldx:]), xr.grad) < 1.5e-5
+    assert float(gxb[..., :ldx].abs().sum()) == 0.0
+    d.flags = 1
+    assert lib.dp_conv2d_dgrad(C.byref(d), S()) == 0
+    assert rel_err(nchw(gxb[..., ldx:]), 2 * xr.grad) < 1.5e-5
+
+
+def test_single_pass_tf32_would_not_be_enough(lib):
+    """Documents why the split is needed: hi*hi alone (what plain TF32 computes) is ~1e-3 off."""
+    g = torch.Generator().manual_seed(0)
+    x, w = torch.randn(4096, 256, generator=g), torch.randn(256, 256, generator=g)
+    hi = lambda t: (t.view(torch.int32) + 0x1000 & ~0x1FFF).view(torch.float32)
+    exact = x.double() @ w.double().t()
+    one = (hi(x).double() @ hi(w).double().t())
+    three = one + ((x - hi(x)).double() @ hi(w).double().t()) + (hi(x).double() @ (w - hi(w)).double().t())
+    assert rel_err(one, exact) > 1e-4 and rel_err(three, exact) < 1e-6
