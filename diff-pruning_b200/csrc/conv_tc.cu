@@ -33,6 +33,7 @@ struct TcParams {
   const float* rowadd; long long ld_rowadd;
   const float* residual; long long ld_res;
   int accumulate;
+  int vec4;            // all epilogue pointers / strides are 16-byte aligned
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -241,16 +242,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       if (row_ok) {
         const int c0 = nblk * BN + j * 32;
+        if (p.vec4 && c0 + 32 <= p.Nout) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int c = c0 + i;
-          if (c < p.Nout) {
-            float o = __uint_as_float(v[i]) + __uint_as_float(u[i]);
-            if (p.bias) o += __ldg(p.bias + c);
-            if (arow) o += __ldg(arow + c);
-            if (rrow) o += __ldg(rrow + c);
-            if (p.accumulate) o += yrow[c];
-            yrow[c] = o;
+          for (int i = 0; i < 32; i += 4) {
+            float4 o = make_float4(__uint_as_float(v[i]) + __uint_as_float(u[i]), __uint_as_float(v[i + 1]) + __uint_as_float(u[i + 1]),
+                                   __uint_as_float(v[i + 2]) + __uint_as_float(u[i + 2]), __uint_as_float(v[i + 3]) + __uint_as_float(u[i + 3]));
+            if (p.bias) { float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + i)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+            if (arow) { float4 t = __ldg(reinterpret_cast<const float4*>(arow + c0 + i)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+            if (rrow) { float4 t = __ldg(reinterpret_cast<const float4*>(rrow + c0 + i)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+            float4* dst = reinterpret_cast<float4*>(yrow + c0 + i);
+            if (p.accumulate) { float4 t = *dst; o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+            *dst = o;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int c = c0 + i;
+            if (c < p.Nout) {
+              float o = __uint_as_float(v[i]) + __uint_as_float(u[i]);
+              if (p.bias) o += __ldg(p.bias + c);
+              if (arow) o += __ldg(arow + c);
+              if (rrow) o += __ldg(rrow + c);
+              if (p.accumulate) o += yrow[c];
+              yrow[c] = o;
+            }
           }
         }
       }
@@ -261,6 +276,186 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------ wgrad
+// dW[k][tap][c] = sum_pix dy[pix][k] * x[pix @ tap][c]  as GEMM  M = k (128), N = c (128), K = pixels.
+// Both operands are activations stored pixel-major / channel-contiguous, i.e. "MN-major" for the tensor core:
+// a stage = 32 pixels (one TMA box of the pixel grid) x 128 channels = 4 swizzle blocks [32 px][128 B] per operand
+// (MN-block stride LBO = 4 KB, 8-pixel K-group stride SBO = 1 KB).  Both tiles are split hi/lo in shared memory.
+// grid = (k tiles * c tiles * taps, splits): split z covers pixel chunks [z*cps, (z+1)*cps) and writes its partial
+// tile to workspace[z][k][tap*C + c]; dp_conv2d_wgrad_reduce sums splits in fixed order (deterministic).
+struct WgParams {
+  int Nimg, H, W, C, K;
+  int R, S, pad;
+  int bw, bh, bn, tiles_w, tiles_h;   // 32-pixel box
+  int total_chunks, chunks_per_split;
+  int c_tiles;
+  float* ws;
+};
+constexpr int WG_KPIX = 32, WG_T = 128 * WG_KPIX * 4;   // one operand tile = 16 KB
+
+// MN-major TF32 operands must use the SWIZZLE_128B_BASE32B layout (cute: Layout_MN_SW128_32B_Atom, "the only available
+// smem layout for mn-major tf32"): atoms of 4 K-rows x 128 B with the four 32-byte chunks of a row XOR-ed by (row & 3);
+// TMA writes it with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  LBO = 4096 B between 32-channel blocks, SBO = 512 B between
+// 4-pixel K-groups, layout_type = 1.
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (256ull << 16) | (32ull << 32) | (1ull << 46) | (1ull << 61);
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ CUtensorMap mapX, const WgParams p) {
+  constexpr int STAGE_BYTES = 4 * WG_T;   // dy(hi in place), dy_lo, x(hi in place), x_lo
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t pad_to = ((raw + 1023u) & ~1023u) - raw;
+  uint8_t* smem = smem_raw + pad_to;
+  const uint32_t sbase = raw + pad_to;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  const uint32_t bar0 = sbase + STAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto conv_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
+  const uint32_t tmem_full_bar = bar0 + 8u * (3 * STAGES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(conv_bar(s), 128); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int T = p.R * p.S;
+  int tile = blockIdx.x;
+  const int tap = tile % T; tile /= T;
+  const int ct = tile % p.c_tiles;
+  const int kt = tile / p.c_tiles;
+  const int r = tap / p.S, sx = tap - r * p.S;
+  const int chunk0 = blockIdx.y * p.chunks_per_split;
+  const int chunk1 = min(p.total_chunks, chunk0 + p.chunks_per_split);
+  const int num_iters = chunk1 - chunk0;   // >= 1 by construction
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapDy)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapX)) : "memory");
+      for (int it = 0; it < num_iters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        mbar_expect_tx(full_bar(s), 2 * WG_T);
+        const int chunk = chunk0 + it;
+        const int tw = chunk % p.tiles_w;
+        const int th = (chunk / p.tiles_w) % p.tiles_h;
+        const int tn = chunk / (p.tiles_w * p.tiles_h);
+        const int q0 = tw * p.bw, p0 = th * p.bh, n0 = tn * p.bn;
+        const uint32_t st = sbase + s * STAGE_BYTES;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {   // 4 blocks of 32 channels = 128 channels per operand
+          tma_load_4d(st + b * 4096, &mapDy, full_bar(s), kt * 128 + b * 32, q0, p0, n0);
+          tma_load_4d(st + 2 * WG_T + b * 4096, &mapX, full_bar(s), ct * 128 + b * 32, q0 + sx - p.pad, p0 + r - p.pad, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // A and B MN-major: bit 15 (a_major) and bit 16 (b_major) set
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      for (int it = 0; it < num_iters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(conv_bar(s), ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t st = sbase + s * STAGE_BYTES;
+#pragma unroll
+        for (int k = 0; k < WG_KPIX / 8; ++k) {
+          const uint64_t a_hi = umma_desc_mn(st + k * 1024), a_lo = umma_desc_mn(st + WG_T + k * 1024);
+          const uint64_t b_hi = umma_desc_mn(st + 2 * WG_T + k * 1024), b_lo = umma_desc_mn(st + 3 * WG_T + k * 1024);
+          const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
+          umma_tf32(tmem_base + 128, a_lo, b_hi, idesc, first);
+          umma_tf32(tmem_base + 128, a_hi, b_lo, idesc, 1u);
+          umma_tf32(tmem_base, a_hi, b_hi, idesc, first);
+        }
+        umma_commit(empty_bar(s));
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    const int tid = threadIdx.x - 64;
+    for (int it = 0; it < num_iters; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      mbar_wait(full_bar(s), ph);
+#pragma unroll
+      for (int op = 0; op < 2; ++op) {
+        float4* A = reinterpret_cast<float4*>(smem + s * STAGE_BYTES + op * 2 * WG_T);
+        float4* Al = reinterpret_cast<float4*>(smem + s * STAGE_BYTES + op * 2 * WG_T + WG_T);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int idx = tid + 128 * i;
+          float4 v = A[idx], h, l;
+          h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+          l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+          A[idx] = h;
+          Al[idx] = l;
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(conv_bar(s));
+    }
+    mbar_wait(tmem_full_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int q = warp & 3;
+    const int row = q * 32 + lane;            // k_out within the tile
+    const int kout = kt * 128 + row;
+    const long long TC_ = (long long)T * p.C;
+    float* wrow = p.ws + ((long long)blockIdx.y * p.K + kout) * TC_ + (long long)tap * p.C;
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+      uint32_t v[32], u[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 32);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+            "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+            "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr));
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+            "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
+            "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
+            "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+          : "r"(taddr + 128u));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (kout < p.K) {
+        const int c0 = ct * 128 + j * 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c0 + i < p.C) wrow[c0 + i] = __uint_as_float(v[i]) + __uint_as_float(u[i]);
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
   }
 }
 
@@ -289,16 +484,17 @@ int tc_init() {
                                  STAGES * (2 * A_BYTES + 2 * 128 * BK * 4) + 2048) == cudaSuccess;
   ok = ok && cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   STAGES * (2 * A_BYTES + 2 * 64 * BK * 4) + 2048) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGES * 4 * WG_T + 2048) == cudaSuccess;
   if (!ok) { (void)cudaGetLastError(); return 0; }
   g_tc_state = 1;
   return 1;
 }
 
 bool make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-              const cuuint32_t* box) {
+              const cuuint32_t* box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
@@ -352,6 +548,8 @@ int launch_tc(const float* act, long long ld_act, int Nimg, int H, int W, int Kg
   p.bw = bw; p.bh = bh; p.bn = bn; p.tiles_w = W / bw; p.tiles_h = H / bh;
   p.y = out; p.ldy = ld_out; p.bias = bias; p.rowadd = rowadd; p.ld_rowadd = ld_rowadd; p.residual = residual; p.ld_res = ld_res;
   p.accumulate = accumulate;
+  auto al16 = [](const void* q, long long ld) { return q == nullptr || ((((uintptr_t)q) & 15) == 0 && (ld % 4) == 0); };
+  p.vec4 = (al16(out, ld_out) && al16(bias, 0) && al16(rowadd, ld_rowadd) && al16(residual, ld_res)) ? 1 : 0;
   const int tiles_n = (Nimg + bn - 1) / bn;
   dim3 grid((unsigned)(p.tiles_w * p.tiles_h * tiles_n), (unsigned)((Nout + BN - 1) / BN));
   if (BN == 64) {
@@ -404,7 +602,54 @@ int dp_conv2d_dgrad_tc(const dp_conv_args* a, dp_stream_t stream) {
                    (cudaStream_t)stream);
 }
 
-int dp_conv2d_wgrad_tc(const dp_conv_args*, dp_stream_t) { return DP_ERR_UNSUPPORTED; }
+// 32-pixel K-chunk box of an [N][H][W] grid
+static bool pick_box32(int H, int W, int& bw, int& bh, int& bn) {
+  if (W >= WG_KPIX) { if (W % WG_KPIX) return false; bw = WG_KPIX; bh = 1; bn = 1; return true; }
+  if (WG_KPIX % W) return false;
+  bw = W;
+  int rem = WG_KPIX / W;
+  if (H >= rem) { if (H % rem) return false; bh = rem; bn = 1; return true; }
+  if (rem % H) return false;
+  bh = H; bn = rem / H;
+  return true;
+}
+
+int dp_conv2d_wgrad_tc(const dp_conv_args* a, dp_stream_t stream) {
+  if (!a || !a->x || !a->y || !a->workspace) return DP_ERR_UNSUPPORTED;
+  if (!tc_init()) return DP_ERR_UNSUPPORTED;
+  if (a->stride != 1 || a->R != a->S || (a->R != 1 && a->R != 3) || a->pad_t != (a->R - 1) / 2 || a->pad_l != a->pad_t) return DP_ERR_UNSUPPORTED;
+  if (a->P != a->H || a->Q != a->W || a->splits < 1) return DP_ERR_UNSUPPORTED;
+  if (a->C % 4 || a->K % 4 || a->ldx % 4 || a->ldy % 4 || ((uintptr_t)a->x & 15) || ((uintptr_t)a->y & 15)) return DP_ERR_UNSUPPORTED;
+  if (a->C < 16 || a->K < 16) return DP_ERR_UNSUPPORTED;
+  int bw, bh, bn;
+  if (!pick_box32(a->H, a->W, bw, bh, bn)) return DP_ERR_UNSUPPORTED;
+  if (a->N % bn) return DP_ERR_UNSUPPORTED;   // a partial image box would be fine (OOB zero) but keep chunks exact
+  CUtensorMap mDy, mX;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)a->K, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->N};
+    cuuint64_t str[3] = {(cuuint64_t)a->ldy * 4, (cuuint64_t)a->W * a->ldy * 4, (cuuint64_t)a->H * a->W * a->ldy * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+    if (!make_map(&mDy, a->y, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return DP_ERR_UNSUPPORTED;
+  }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)a->C, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->N};
+    cuuint64_t str[3] = {(cuuint64_t)a->ldx * 4, (cuuint64_t)a->W * a->ldx * 4, (cuuint64_t)a->H * a->W * a->ldx * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+    if (!make_map(&mX, a->x, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return DP_ERR_UNSUPPORTED;
+  }
+  WgParams p{};
+  p.Nimg = a->N; p.H = a->H; p.W = a->W; p.C = a->C; p.K = a->K; p.R = a->R; p.S = a->S; p.pad = a->pad_t;
+  p.bw = bw; p.bh = bh; p.bn = bn; p.tiles_w = a->W / bw; p.tiles_h = a->H / bh;
+  p.total_chunks = p.tiles_w * p.tiles_h * (a->N / bn);
+  p.chunks_per_split = (p.total_chunks + a->splits - 1) / a->splits;
+  if ((long long)p.chunks_per_split * (a->splits - 1) >= p.total_chunks) return DP_ERR_UNSUPPORTED;   // an empty split
+  p.c_tiles = (a->C + 127) / 128;
+  p.ws = a->workspace;
+  const int k_tiles = (a->K + 127) / 128;
+  dim3 grid((unsigned)(k_tiles * p.c_tiles * a->R * a->S), (unsigned)a->splits);
+  wgrad_tc_kernel<<<grid, NTHREADS, STAGES * 4 * WG_T + 2048, (cudaStream_t)stream>>>(mDy, mX, p);
+  return dp_check_launch();
+}
 
 extern "C" int dp_pack_conv_weight_tc(const float* w, int32_t K, int32_t C, int32_t R, int32_t S, float* kc_hi, float* kc_lo,
                                       float* ck_hi, float* ck_lo, dp_stream_t stream) {

@@ -56,7 +56,7 @@ def test_conv_tc_fprop_dgrad(lib, N, Cin, H, W, K, R, ldx, ldy):
     x = torch.randn(N, Cin, H, W, generator=g)
     w = torch.randn(K, Cin, R, R, generator=g) / math.sqrt(Cin * R * R)
     b = torch.randn(K, generator=g)
-    xr, wr = x.clone().requires_grad_(True), w.clone()
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
     y_ref = F.conv2d(xr, wr, b, padding=pad)
     rowadd, res = torch.randn(N, K, generator=g), torch.randn(N, K, H, W, generator=g)
     gy = torch.randn(N, K, H, W, generator=g)
@@ -112,6 +112,25 @@ def test_conv_tc_fprop_dgrad(lib, N, Cin, H, W, K, R, ldx, ldy):
     d.flags = 1
     assert lib.dp_conv2d_dgrad(C.byref(d), S()) == 0
     assert rel_err(nchw(gxb[..., ldx:]), 2 * xr.grad) < 1.5e-5
+    # wgrad (MN-major operands, both split in-kernel), deterministic split-K + reduce into dW (+=)
+    pix_chunks = N * H * W // 32
+    for splits in sorted({1, min(3, pix_chunks)}):
+        ws = torch.full((splits * K * R * R * Cin,), float("nan"), device="cuda")
+        wg = L.ConvArgs()
+        C.memmove(C.byref(wg), C.byref(a), C.sizeof(a))
+        wg.flags, wg.splits, wg.y, wg.ldy, wg.workspace = 0, splits, gyd.data_ptr(), K, ws.data_ptr()
+        assert lib.dp_conv2d_wgrad(C.byref(wg), S()) == 0
+        dw = torch.ones(K, Cin, R, R, device="cuda")
+        r = L.WgradReduceArgs()
+        r.K, r.C, r.R, r.S, r.splits = K, Cin, R, R, splits
+        r.workspace, r.dw = ws.data_ptr(), dw.data_ptr()
+        assert lib.dp_conv2d_wgrad_reduce(C.byref(r), S()) == 0
+        assert rel_err(dw.cpu() - 1, wr.grad) < 1.5e-5, splits
+        # and the SIMT path on the same problem agrees
+        ws2 = torch.empty_like(ws)
+        wg.flags, wg.workspace = 2, ws2.data_ptr()
+        assert lib.dp_conv2d_wgrad(C.byref(wg), S()) == 0
+        assert rel_err(ws.view(splits, -1).sum(0), ws2.view(splits, -1).sum(0)) < 1.5e-5
 
 
 def test_single_pass_tf32_would_not_be_enough(lib):
