@@ -145,9 +145,11 @@ def test_finetune_two_steps():
             assert loss.item() == pytest.approx(s["loss"], rel=2e-5)
             assert float(st.sumsq.sqrt()) == pytest.approx(s["grad_norm"], rel=2e-4)
         ema = st.ema_state()
+        # Adam normalises the step (m/sqrt(v)): a zero-initialised bias moves by ~lr per step, so its relative
+        # error after 2 steps equals the gradient's relative rounding error (~1e-5), not 1e-7.
         for k, p in m.named_parameters():
-            assert rel_err(p, G["params"][k]) < 2e-6, k
-            assert rel_err(ema[k], G["ema"][k]) < 2e-6, k
+            assert rel_err(p, G["params"][k]) < 5e-5, k
+            assert rel_err(ema[k], G["ema"][k]) < 5e-5, k
 
 
 def test_lsun_family_block_one_pass_vs_oracle():
