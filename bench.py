@@ -173,7 +173,7 @@ def _timed_pass(scorer, events):
     from diff_pruning_b200 import _lib as L
     p.t_dev.fill_(3)
     L.check(lib.dp_add_noise(scorer.clean.data_ptr(), scorer.noise.data_ptr(), p.t_dev.data_ptr(), scorer.acp.data_ptr(),
-                             p.x_in.ptr, scorer.B, scorer.C, scorer.H, scorer.W, 1, s_int))
+                             p.x_in.ptr, scorer.B, scorer.C, scorer.H, scorer.W, 1, p.x_in.ld, s_int))
     pairs = []
 
     def run_list(steps, tags):

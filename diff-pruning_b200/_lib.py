@@ -45,7 +45,8 @@ class TaylorArgs(C.Structure):
 
 class AdamArgs(C.Structure):
     _fields_ = [("n", i64), ("p", vp), ("g", vp), ("m", vp), ("v", vp), ("ema", vp), ("sumsq", vp),
-                ("max_norm", f32), ("lr", f32), ("beta1", f32), ("beta2", f32), ("eps", f32), ("ema_decay", f32),
+                ("max_norm", C.c_double), ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double),
+                ("eps", C.c_double), ("ema_decay", C.c_double),
                 ("step", i32), ("grad_scale", f32), ("step_scalars", vp)]
 
 
@@ -70,7 +71,7 @@ _SIGS = {
     "dp_silu_fwd": (C.c_int, [vp, vp, i64, vp]),
     "dp_silu_bwd": (C.c_int, [vp, vp, vp, i64, i32, vp]),
     "dp_timestep_embedding": (C.c_int, [vp, vp, vp, i32, i32, i32, vp]),
-    "dp_add_noise": (C.c_int, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    "dp_add_noise": (C.c_int, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i64, vp]),
     "dp_nchw_to_nhwc": (C.c_int, [vp, vp, i64, i32, i32, i32, i32, vp]),
     "dp_nhwc_to_nchw": (C.c_int, [vp, i64, vp, i32, i32, i32, i32, i32, vp]),
     "dp_mse_partials": (i64, [i64]),

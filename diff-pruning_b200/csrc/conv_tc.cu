@@ -280,6 +280,217 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 }
 
 
+
+// ------------------------------------------------------------------------------------------------ TS variant
+// Same GEMM, but the split A operand goes registers -> TENSOR MEMORY (tcgen05.st) and the MMA reads A from TMEM
+// (tcgen05.mma [d], [a_tmem], b_desc): the shared-memory pipe only carries the TMA writes, one read of the raw A tile and
+// the B operand reads (112 KB per 768-cycle stage instead of 192 KB), which is what bounds the SS kernel above.
+// TMEM map (512 columns): [0,BN) main accumulator | [BN,2BN) correction accumulator | 2BN + 64*s: A_hi(32) A_lo(32) of stage s.
+constexpr int STAGES_TS = 4;
+
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]),
+        "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]),
+        "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv_tc_ts_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBh,
+                  const __grid_constant__ CUtensorMap mapBl, const TcParams p) {
+  constexpr int B_BYTES = BN * BK * 4;
+  constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;
+  constexpr uint32_t A_COL0 = 2 * BN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t pad_to = ((raw + 1023u) & ~1023u) - raw;
+  uint8_t* smem = smem_raw + pad_to;
+  const uint32_t sbase = raw + pad_to;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES_TS * STAGE_BYTES);
+  const uint32_t bar0 = sbase + STAGES_TS * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto conv_bar = [&](int s) { return bar0 + 8u * (STAGES_TS + s); };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES_TS + s); };
+  const uint32_t tmem_full_bar = bar0 + 8u * (3 * STAGES_TS);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES_TS + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES_TS; ++s) { mbar_init(full_bar(s), 1); mbar_init(conv_bar(s), 128); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tile_m = blockIdx.x, nblk = blockIdx.y;
+  const int tw = tile_m % p.tiles_w;
+  const int th = (tile_m / p.tiles_w) % p.tiles_h;
+  const int tn = tile_m / (p.tiles_w * p.tiles_h);
+  const int q0 = tw * p.bw, p0 = th * p.bh, n0 = tn * p.bn;
+  const int T = p.R * p.S;
+  const int num_iters = T * p.kchunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapBh)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapBl)) : "memory");
+      for (int it = 0; it < num_iters; ++it) {
+        const int s = it % STAGES_TS;
+        const uint32_t ph = (uint32_t)(it / STAGES_TS) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        mbar_expect_tx(full_bar(s), A_BYTES + 2 * B_BYTES);
+        const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
+        const int r = tap / p.S, sx = tap - r * p.S;
+        const uint32_t st = sbase + s * STAGE_BYTES;
+        tma_load_4d(st, &mapA, full_bar(s), kc * BK, q0 + sx - p.pad, p0 + r - p.pad, n0);
+        const int tapb = p.flip ? (T - 1 - tap) : tap;
+        tma_load_3d(st + A_BYTES, &mapBh, full_bar(s), kc * BK, nblk * BN, tapb);
+        tma_load_3d(st + A_BYTES + B_BYTES, &mapBl, full_bar(s), kc * BK, nblk * BN, tapb);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      for (int it = 0; it < num_iters; ++it) {
+        const int s = it % STAGES_TS;
+        const uint32_t ph = (uint32_t)(it / STAGES_TS) & 1u;
+        mbar_wait(conv_bar(s), ph);     // A hi/lo of this stage are in TMEM (and, transitively, B has landed in smem)
+        mbar_wait(full_bar(s), ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t st = sbase + s * STAGE_BYTES;
+        const uint32_t a_t = tmem_base + A_COL0 + 64u * s;
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k) {
+          const uint64_t b_hi = umma_desc(st + A_BYTES + k * 32), b_lo = umma_desc(st + A_BYTES + B_BYTES + k * 32);
+          const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
+          umma_tf32_ts(tmem_base + BN, a_t + 32 + k * 8, b_hi, idesc, first);   // lo * hi
+          umma_tf32_ts(tmem_base + BN, a_t + k * 8, b_lo, idesc, 1u);           // hi * lo
+          umma_tf32_ts(tmem_base, a_t + k * 8, b_hi, idesc, first);             // hi * hi
+        }
+        umma_commit(empty_bar(s));
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    // ---- splitter: thread <-> tile row (TMEM lane).  Row r of the 128B-swizzled tile: 16-byte chunk j sits at (j ^ (r & 7)).
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    for (int it = 0; it < num_iters; ++it) {
+      const int s = it % STAGES_TS;
+      const uint32_t ph = (uint32_t)(it / STAGES_TS) & 1u;
+      mbar_wait(full_bar(s), ph);
+      const uint8_t* arow = smem + s * STAGE_BYTES + row * 128;
+      uint32_t hi[32], lo[32];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 v = *reinterpret_cast<const float4*>(arow + ((j ^ (row & 7)) << 4));
+        const float h0 = tf32_rna(v.x), h1 = tf32_rna(v.y), h2 = tf32_rna(v.z), h3 = tf32_rna(v.w);
+        hi[4 * j + 0] = __float_as_uint(h0); hi[4 * j + 1] = __float_as_uint(h1);
+        hi[4 * j + 2] = __float_as_uint(h2); hi[4 * j + 3] = __float_as_uint(h3);
+        lo[4 * j + 0] = __float_as_uint(v.x - h0); lo[4 * j + 1] = __float_as_uint(v.y - h1);
+        lo[4 * j + 2] = __float_as_uint(v.z - h2); lo[4 * j + 3] = __float_as_uint(v.w - h3);
+      }
+      const uint32_t a_t = tmem_base + lane_addr + A_COL0 + 64u * s;
+      tmem_st32(a_t, hi);
+      tmem_st32(a_t + 32, lo);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(conv_bar(s));
+    }
+    // ---- epilogue (identical to the SS kernel)
+    mbar_wait(tmem_full_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int w_l = row % p.bw, h_l = (row / p.bw) % p.bh, n_l = row / (p.bw * p.bh);
+    const int img = n0 + n_l;
+    const bool row_ok = img < p.Nimg;
+    const long long m = ((long long)img * p.H + (p0 + h_l)) * p.W + (q0 + w_l);
+    float* yrow = p.y + m * p.ldy;
+    const float* rrow = p.residual ? p.residual + m * p.ld_res : nullptr;
+    const float* arow2 = p.rowadd ? p.rowadd + (long long)img * p.ld_rowadd : nullptr;
+#pragma unroll 1
+    for (int j = 0; j < BN / 32; ++j) {
+      uint32_t v[32], u[32];
+      const uint32_t taddr = tmem_base + lane_addr + (uint32_t)(j * 32);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+            "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+            "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr));
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+            "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
+            "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
+            "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+          : "r"(taddr + (uint32_t)BN));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (row_ok) {
+        const int c0 = nblk * BN + j * 32;
+        if (p.vec4 && c0 + 32 <= p.Nout) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            float4 o = make_float4(__uint_as_float(v[i]) + __uint_as_float(u[i]), __uint_as_float(v[i + 1]) + __uint_as_float(u[i + 1]),
+                                   __uint_as_float(v[i + 2]) + __uint_as_float(u[i + 2]), __uint_as_float(v[i + 3]) + __uint_as_float(u[i + 3]));
+            if (p.bias) { float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + i)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+            if (arow2) { float4 t = __ldg(reinterpret_cast<const float4*>(arow2 + c0 + i)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+            if (rrow) { float4 t = __ldg(reinterpret_cast<const float4*>(rrow + c0 + i)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+            float4* dst = reinterpret_cast<float4*>(yrow + c0 + i);
+            if (p.accumulate) { float4 t = *dst; o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+            *dst = o;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int c = c0 + i;
+            if (c < p.Nout) {
+              float o = __uint_as_float(v[i]) + __uint_as_float(u[i]);
+              if (p.bias) o += __ldg(p.bias + c);
+              if (arow2) o += __ldg(arow2 + c);
+              if (rrow) o += __ldg(rrow + c);
+              if (p.accumulate) o += yrow[c];
+              yrow[c] = o;
+            }
+          }
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ wgrad
 // dW[k][tap][c] = sum_pix dy[pix][k] * x[pix @ tap][c]  as GEMM  M = k (128), N = c (128), K = pixels.
 // Both operands are activations stored pixel-major / channel-contiguous, i.e. "MN-major" for the tensor core:
@@ -465,6 +676,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
 int g_tc_state = -1;  // -1 unknown, 0 unavailable, 1 ok
+bool g_use_ss = false; // DPB200_TC_SS=1: keep the A operand in shared memory (SS-mode kernel) instead of TMEM (TS-mode)
 std::mutex g_tc_mutex;
 
 int tc_init() {
@@ -484,6 +696,11 @@ int tc_init() {
                                  STAGES * (2 * A_BYTES + 2 * 128 * BK * 4) + 2048) == cudaSuccess;
   ok = ok && cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   STAGES * (2 * A_BYTES + 2 * 64 * BK * 4) + 2048) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(conv_tc_ts_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  STAGES_TS * (A_BYTES + 2 * 128 * BK * 4) + 2048) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(conv_tc_ts_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  STAGES_TS * (A_BYTES + 2 * 64 * BK * 4) + 2048) == cudaSuccess;
+  g_use_ss = getenv("DPB200_TC_SS") != nullptr;
   ok = ok && cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGES * 4 * WG_T + 2048) == cudaSuccess;
   if (!ok) { (void)cudaGetLastError(); return 0; }
   g_tc_state = 1;
@@ -523,8 +740,8 @@ int launch_tc(const float* act, long long ld_act, int Nimg, int H, int W, int Kg
               long long ld_rowadd, const float* residual, long long ld_res, int accumulate, cudaStream_t st) {
   if (!tc_init()) return DP_ERR_UNSUPPORTED;
   if (!w_hi || !w_lo) return DP_ERR_UNSUPPORTED;
-  if (Kg % 4 || ld_act % 4 || ((uintptr_t)act & 15) || ((uintptr_t)w_hi & 15) || ((uintptr_t)w_lo & 15)) return DP_ERR_UNSUPPORTED;
-  if (Kg < 16 || Nout < 8) return DP_ERR_UNSUPPORTED;   // degenerate GEMMs stay on the SIMT path
+  if (ld_act % 4 || ((uintptr_t)act & 15) || ((uintptr_t)w_hi & 15) || ((uintptr_t)w_lo & 15)) return DP_ERR_UNSUPPORTED;
+  if (Kg % 4) return DP_ERR_UNSUPPORTED;                 // packed weight rows [Nout][Kg] must be 16-byte multiples for TMA
   int bw, bh, bn;
   if (!pick_box(Nimg, H, W, bw, bh, bn)) return DP_ERR_UNSUPPORTED;
   const int T = R * S;
@@ -552,12 +769,12 @@ int launch_tc(const float* act, long long ld_act, int Nimg, int H, int W, int Kg
   p.vec4 = (al16(out, ld_out) && al16(bias, 0) && al16(rowadd, ld_rowadd) && al16(residual, ld_res)) ? 1 : 0;
   const int tiles_n = (Nimg + bn - 1) / bn;
   dim3 grid((unsigned)(p.tiles_w * p.tiles_h * tiles_n), (unsigned)((Nout + BN - 1) / BN));
-  if (BN == 64) {
-    size_t smem = STAGES * (2 * A_BYTES + 2 * 64 * BK * 4) + 2048;
-    conv_tc_kernel<64><<<grid, NTHREADS, smem, st>>>(mA, mBh, mBl, p);
+  if (g_use_ss) {
+    if (BN == 64) conv_tc_kernel<64><<<grid, NTHREADS, STAGES * (2 * A_BYTES + 2 * 64 * BK * 4) + 2048, st>>>(mA, mBh, mBl, p);
+    else conv_tc_kernel<128><<<grid, NTHREADS, STAGES * (2 * A_BYTES + 2 * 128 * BK * 4) + 2048, st>>>(mA, mBh, mBl, p);
   } else {
-    size_t smem = STAGES * (2 * A_BYTES + 2 * 128 * BK * 4) + 2048;
-    conv_tc_kernel<128><<<grid, NTHREADS, smem, st>>>(mA, mBh, mBl, p);
+    if (BN == 64) conv_tc_ts_kernel<64><<<grid, NTHREADS, STAGES_TS * (A_BYTES + 2 * 64 * BK * 4) + 2048, st>>>(mA, mBh, mBl, p);
+    else conv_tc_ts_kernel<128><<<grid, NTHREADS, STAGES_TS * (A_BYTES + 2 * 128 * BK * 4) + 2048, st>>>(mA, mBh, mBl, p);
   }
   return dp_check_launch();
 }
@@ -619,8 +836,7 @@ int dp_conv2d_wgrad_tc(const dp_conv_args* a, dp_stream_t stream) {
   if (!tc_init()) return DP_ERR_UNSUPPORTED;
   if (a->stride != 1 || a->R != a->S || (a->R != 1 && a->R != 3) || a->pad_t != (a->R - 1) / 2 || a->pad_l != a->pad_t) return DP_ERR_UNSUPPORTED;
   if (a->P != a->H || a->Q != a->W || a->splits < 1) return DP_ERR_UNSUPPORTED;
-  if (a->C % 4 || a->K % 4 || a->ldx % 4 || a->ldy % 4 || ((uintptr_t)a->x & 15) || ((uintptr_t)a->y & 15)) return DP_ERR_UNSUPPORTED;
-  if (a->C < 16 || a->K < 16) return DP_ERR_UNSUPPORTED;
+  if (a->ldx % 4 || a->ldy % 4 || ((uintptr_t)a->x & 15) || ((uintptr_t)a->y & 15)) return DP_ERR_UNSUPPORTED;
   int bw, bh, bn;
   if (!pick_box32(a->H, a->W, bw, bh, bn)) return DP_ERR_UNSUPPORTED;
   if (a->N % bn) return DP_ERR_UNSUPPORTED;   // a partial image box would be fine (OOB zero) but keep chunks exact

@@ -363,35 +363,43 @@ extern "C" int dp_gemm_batched(const dp_gemm_args* a, dp_stream_t stream) {
 // ---------------------------------------------------------------------------------------------
 // split-K reduce + scatter into the OIHW gradient (+ optional signed Taylor accumulation)
 namespace {
-__global__ void wgrad_reduce_kernel(const dp_wgrad_reduce_args a) {
-  // one block per output channel k; threads stride over (tap,c)
-  const int k = blockIdx.x;
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const dp_wgrad_reduce_args a) {
+  // block (x = chunk of 256 (tap,c) entries, y = output channel k): coalesced reads of every split, 4 splits in flight
+  const int k = blockIdx.y;
   const int RS = a.R * a.S, TC = RS * a.C;
   const long long split_stride = (long long)a.K * TC;
-  const float* ws = a.workspace + (long long)k * TC;
-  float so = 0.f;
-  for (int i = threadIdx.x; i < TC; i += blockDim.x) {
-    float s = 0.f;
-    for (int z = 0; z < a.splits; ++z) s += ws[z * split_stride + i];
-    int tap = i / a.C, c = i - tap * a.C;
-    long long gi = ((long long)k * a.C + c) * RS + tap;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i < TC) {
+    const float* ws = a.workspace + (long long)k * TC + i;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int z = 0;
+    for (; z + 4 <= a.splits; z += 4) {
+      s0 += ws[(z + 0) * split_stride]; s1 += ws[(z + 1) * split_stride];
+      s2 += ws[(z + 2) * split_stride]; s3 += ws[(z + 3) * split_stride];
+    }
+    for (; z < a.splits; ++z) s0 += ws[z * split_stride];
+    const float s = (s0 + s1) + (s2 + s3);
+    const int tap = i / a.C, c = i - tap * a.C;
+    const long long gi = ((long long)k * a.C + c) * RS + tap;
     a.dw[gi] += s;
-    if (a.w && (a.score_out || a.score_in)) {
-      float t = a.w[gi] * s;
-      so += t;
-      if (a.score_in) const_cast<float*>(a.workspace)[(long long)k * TC + i] = t;  // split 0 slot reused: W*dW_t
-    }
+    // signed first-order Taylor term of this pass, parked in the (already consumed) split-0 slot for the score kernels
+    if (a.w && (a.score_out || a.score_in)) const_cast<float*>(a.workspace)[(long long)k * TC + i] = a.w[gi] * s;
   }
-  if (a.w && a.score_out) {
-    __shared__ float red[32];
-    so = warp_sum(so);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = so;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
-      v = warp_sum(v);
-      if (threadIdx.x == 0) a.score_out[k] += v;
-    }
+}
+__global__ void wgrad_score_out_kernel(const dp_wgrad_reduce_args a) {
+  // one block per output channel k: fixed-order sum over (tap, c) of W*dW_t
+  const int k = blockIdx.x;
+  const int TC = a.R * a.S * a.C;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < TC; i += blockDim.x) s += a.workspace[(long long)k * TC + i];
+  __shared__ float red[32];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) a.score_out[k] += v;
   }
 }
 __global__ void wgrad_score_in_kernel(const dp_wgrad_reduce_args a) {
@@ -432,9 +440,16 @@ extern "C" int dp_conv2d_wgrad_reduce(const dp_wgrad_reduce_args* a, dp_stream_t
   DP_REQUIRE(a && a->workspace && a->dw, DP_ERR_NULL);
   DP_REQUIRE(a->K > 0 && a->C > 0 && a->R > 0 && a->S > 0 && a->splits >= 1, DP_ERR_SHAPE);
   cudaStream_t st = (cudaStream_t)stream;
-  wgrad_reduce_kernel<<<a->K, 256, 0, st>>>(*a);
+  const int TC = a->R * a->S * a->C;
+  const int nblk = (TC + 255) / 256;
+  DP_REQUIRE(a->K <= 65535, DP_ERR_SHAPE);
+  wgrad_reduce_kernel<<<dim3(nblk, a->K), 256, 0, st>>>(*a);
   int rc = dp_check_launch();
   if (rc) return rc;
+  if (a->w && a->score_out) {
+    wgrad_score_out_kernel<<<a->K, 256, 0, st>>>(*a);
+    if ((rc = dp_check_launch())) return rc;
+  }
   if (a->w && a->score_in) {
     wgrad_score_in_kernel<<<a->C, 256, 0, st>>>(*a);
     rc = dp_check_launch();

@@ -235,12 +235,164 @@ __global__ void __launch_bounds__(NT) gn_bwd_apply_kernel(const dp_gn_args a, co
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// float4 variants (C % 4 == 0, 16-byte aligned views): each thread owns 4 consecutive channels, 8 pixel lanes for
+// C = 128.  Same partial-buffer layouts as the scalar kernels, so finalize/param kernels are shared.
+static inline Map make_map4(int HW, int C) {
+  Map m;
+  int c4 = C / 4, ct = 8;
+  while (ct < c4) ct <<= 1;
+  m.CT = ct; m.PL = NT / ct;
+  int ppc = 16384 / C; if (ppc < m.PL) ppc = m.PL; if (ppc > HW) ppc = HW; if (ppc < 1) ppc = 1;
+  m.PPC = ppc; m.nchunks = (HW + ppc - 1) / ppc;
+  return m;
+}
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+__global__ void __launch_bounds__(NT) gn_stats4_kernel(const dp_gn_args a, const Map mp, double* __restrict__ ws) {
+  extern __shared__ double sh[];  // [2][PL][CT*4]
+  const int n = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+  const int ct = tid % mp.CT, pl = tid / mp.CT, c0 = ct * 4;
+  const int p0 = chunk * mp.PPC, p1 = min(a.HW, p0 + mp.PPC);
+  double s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+  const float* xb = a.x + (long long)n * a.HW * a.ldx + c0;
+  if (c0 < a.C) {
+#pragma unroll 4
+    for (int pix = p0 + pl; pix < p1; pix += mp.PL) {
+      float4 v = ld4(xb + (long long)pix * a.ldx);
+      s[0] += v.x; q[0] += (double)v.x * v.x; s[1] += v.y; q[1] += (double)v.y * v.y;
+      s[2] += v.z; q[2] += (double)v.z * v.z; s[3] += v.w; q[3] += (double)v.w * v.w;
+    }
+  }
+  const int W4 = mp.CT * 4;
+  double* shs = sh; double* shq = sh + mp.PL * W4;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { shs[pl * W4 + c0 + e] = s[e]; shq[pl * W4 + c0 + e] = q[e]; }
+  __syncthreads();
+  const int cpg = a.C / a.G;
+  for (int g = tid; g < a.G; g += NT) {
+    double ts = 0, tq = 0;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c)
+      for (int l = 0; l < mp.PL; ++l) { ts += shs[l * W4 + c]; tq += shq[l * W4 + c]; }
+    double* o = ws + (((long long)n * mp.nchunks + chunk) * a.G + g) * 2;
+    o[0] = ts; o[1] = tq;
+  }
+}
+
+__global__ void __launch_bounds__(NT) gn_apply4_kernel(const dp_gn_args a, const Map mp) {
+  const int n = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+  const int ct = tid % mp.CT, pl = tid / mp.CT, c0 = ct * 4;
+  if (c0 >= a.C) return;
+  const int p0 = chunk * mp.PPC, p1 = min(a.HW, p0 + mp.PPC);
+  const int cpg = a.C / a.G;
+  float sc[4], shf[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    int c = c0 + e, g = c / cpg;
+    float mu = a.mean[n * a.G + g], rs = a.rstd[n * a.G + g], ga = __ldg(a.gamma + c), be = __ldg(a.beta + c);
+    sc[e] = rs * ga; shf[e] = be - mu * rs * ga;
+  }
+  const float* xb = a.x + (long long)n * a.HW * a.ldx + c0;
+  float* yb = a.y + (long long)n * a.HW * a.ldy + c0;
+  const uint64_t seed = a.dropout_seed + (a.dropout_seed_dev ? *a.dropout_seed_dev : 0ull);
+#pragma unroll 4
+  for (int pix = p0 + pl; pix < p1; pix += mp.PL) {
+    float4 v = ld4(xb + (long long)pix * a.ldx);
+    float y[4] = {fmaf(v.x, sc[0], shf[0]), fmaf(v.y, sc[1], shf[1]), fmaf(v.z, sc[2], shf[2]), fmaf(v.w, sc[3], shf[3])};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (a.silu) y[e] = y[e] * sigmoidf_acc(y[e]);
+      if (a.dropout_p > 0.f) y[e] *= keep_scale(seed, ((uint64_t)n * a.HW + pix) * a.C + c0 + e, a.dropout_p);
+    }
+    *reinterpret_cast<float4*>(yb + (long long)pix * a.ldy) = make_float4(y[0], y[1], y[2], y[3]);
+  }
+}
+
+__global__ void __launch_bounds__(NT) gn_bwd_partial4_kernel(const dp_gn_args a, const Map mp, float* __restrict__ part) {
+  extern __shared__ float shf32[];  // [2][PL][CT*4]
+  const int n = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+  const int ct = tid % mp.CT, pl = tid / mp.CT, c0 = ct * 4;
+  const int p0 = chunk * mp.PPC, p1 = min(a.HW, p0 + mp.PPC);
+  const int cpg = a.C / a.G;
+  float mu[4], rs[4], ga[4], be[4], s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+  const bool act = c0 < a.C;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    int c = act ? c0 + e : 0, g = c / cpg;
+    mu[e] = a.mean[n * a.G + g]; rs[e] = a.rstd[n * a.G + g]; ga[e] = __ldg(a.gamma + c); be[e] = __ldg(a.beta + c);
+  }
+  if (act) {
+    const float* xb = a.x + (long long)n * a.HW * a.ldx + c0;
+    const float* db = a.dy + (long long)n * a.HW * a.lddy + c0;
+#pragma unroll 2
+    for (int pix = p0 + pl; pix < p1; pix += mp.PL) {
+      float4 xv = ld4(xb + (long long)pix * a.ldx), dv = ld4(db + (long long)pix * a.lddy);
+      float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ds[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float xh = (xs[e] - mu[e]) * rs[e];
+        float g = gn_dy(a, ds[e], fmaf(xh, ga[e], be[e]), ((uint64_t)n * a.HW + pix) * a.C + c0 + e);
+        s1[e] += g; s2[e] += g * xh;
+      }
+    }
+  }
+  const int W4 = mp.CT * 4;
+  float* sa = shf32; float* sb = shf32 + mp.PL * W4;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { sa[pl * W4 + c0 + e] = s1[e]; sb[pl * W4 + c0 + e] = s2[e]; }
+  __syncthreads();
+  float* o = part + ((long long)n * mp.nchunks + chunk) * 2 * a.C;
+  for (int c = tid; c < a.C; c += NT) {
+    float t1 = 0.f, t2 = 0.f;
+    for (int l = 0; l < mp.PL; ++l) { t1 += sa[l * W4 + c]; t2 += sb[l * W4 + c]; }
+    o[c] = t1; o[a.C + c] = t2;
+  }
+}
+
+__global__ void __launch_bounds__(NT) gn_bwd_apply4_kernel(const dp_gn_args a, const Map mp, const float* __restrict__ coef) {
+  const int n = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+  const int ct = tid % mp.CT, pl = tid / mp.CT, c0 = ct * 4;
+  if (c0 >= a.C) return;
+  const int p0 = chunk * mp.PPC, p1 = min(a.HW, p0 + mp.PPC);
+  const int cpg = a.C / a.G;
+  float mu[4], rs[4], ga[4], be[4], k1[4], k2[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    int c = c0 + e, g = c / cpg;
+    mu[e] = a.mean[n * a.G + g]; rs[e] = a.rstd[n * a.G + g]; ga[e] = __ldg(a.gamma + c); be[e] = __ldg(a.beta + c);
+    k1[e] = coef[((long long)n * a.G + g) * 2]; k2[e] = coef[((long long)n * a.G + g) * 2 + 1];
+  }
+  const float* xb = a.x + (long long)n * a.HW * a.ldx + c0;
+  const float* db = a.dy + (long long)n * a.HW * a.lddy + c0;
+  float* ob = a.dx + (long long)n * a.HW * a.lddx + c0;
+  const float* ab = a.dx_add ? a.dx_add + (long long)n * a.HW * a.ldadd + c0 : nullptr;
+  const float* ab2 = a.dx_add2 ? a.dx_add2 + (long long)n * a.HW * a.ldadd2 + c0 : nullptr;
+#pragma unroll 2
+  for (int pix = p0 + pl; pix < p1; pix += mp.PL) {
+    float4 xv = ld4(xb + (long long)pix * a.ldx), dv = ld4(db + (long long)pix * a.lddy);
+    float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ds[4] = {dv.x, dv.y, dv.z, dv.w}, d[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float xh = (xs[e] - mu[e]) * rs[e];
+      float g = gn_dy(a, ds[e], fmaf(xh, ga[e], be[e]), ((uint64_t)n * a.HW + pix) * a.C + c0 + e);
+      d[e] = rs[e] * (ga[e] * g - k1[e] - xh * k2[e]);
+    }
+    if (ab) { float4 t = *reinterpret_cast<const float4*>(ab + (long long)pix * a.ldadd); d[0] += t.x; d[1] += t.y; d[2] += t.z; d[3] += t.w; }
+    if (ab2) { float4 t = ld4(ab2 + (long long)pix * a.ldadd2); d[0] += t.x; d[1] += t.y; d[2] += t.z; d[3] += t.w; }
+    *reinterpret_cast<float4*>(ob + (long long)pix * a.lddx) = make_float4(d[0], d[1], d[2], d[3]);
+  }
+}
+
+static inline bool al16(const void* p, long long ld) { return p == nullptr || ((((uintptr_t)p) & 15) == 0 && (ld % 4) == 0); }
+
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 }  // namespace
 
 extern "C" size_t dp_groupnorm_workspace_bytes(int32_t N, int32_t HW, int32_t C, int32_t G) {
   if (N <= 0 || HW <= 0 || C <= 0 || G <= 0) return 0;
   Map mp = make_map(HW, C);
+  if (C % 4 == 0) { Map m4 = make_map4(HW, C); if (m4.nchunks > mp.nchunks) mp.nchunks = m4.nchunks; }
   size_t fwd = (size_t)N * mp.nchunks * G * 2 * sizeof(double);
   size_t bwd = align256((size_t)N * mp.nchunks * 2 * C * sizeof(float)) + align256((size_t)N * 2 * C * sizeof(float)) +
                align256((size_t)N * G * 2 * sizeof(float));
@@ -263,14 +415,20 @@ extern "C" int dp_groupnorm_fwd(const dp_gn_args* a, dp_stream_t stream) {
   DP_REQUIRE(a->y, DP_ERR_NULL);
   DP_REQUIRE(a->ldy >= a->C, DP_ERR_SHAPE);
   cudaStream_t st = (cudaStream_t)stream;
-  Map mp = make_map(a->HW, a->C);
+  const bool v4 = (a->C % 4 == 0) && al16(a->x, a->ldx) && al16(a->y, a->ldy);
+  Map mp = v4 ? make_map4(a->HW, a->C) : make_map(a->HW, a->C);
   dim3 grid(mp.nchunks, a->N);
-  int slots = (a->C > NT) ? a->C : mp.PL * mp.CT;
-  gn_stats_kernel<<<grid, NT, 2 * slots * sizeof(double), st>>>(*a, mp, (double*)a->workspace);
+  if (v4) {
+    gn_stats4_kernel<<<grid, NT, 2 * mp.PL * mp.CT * 4 * sizeof(double), st>>>(*a, mp, (double*)a->workspace);
+  } else {
+    int slots = (a->C > NT) ? a->C : mp.PL * mp.CT;
+    gn_stats_kernel<<<grid, NT, 2 * slots * sizeof(double), st>>>(*a, mp, (double*)a->workspace);
+  }
   if ((rc = dp_check_launch())) return rc;
   gn_finalize_kernel<<<(a->N * a->G + 127) / 128, 128, 0, st>>>(*a, mp, (const double*)a->workspace);
   if ((rc = dp_check_launch())) return rc;
-  gn_apply_kernel<<<grid, NT, 0, st>>>(*a, mp);
+  if (v4) gn_apply4_kernel<<<grid, NT, 0, st>>>(*a, mp);
+  else gn_apply_kernel<<<grid, NT, 0, st>>>(*a, mp);
   return dp_check_launch();
 }
 
@@ -280,13 +438,16 @@ extern "C" int dp_groupnorm_bwd(const dp_gn_args* a, dp_stream_t stream) {
   DP_REQUIRE(a->dy && a->dx, DP_ERR_NULL);
   DP_REQUIRE(a->lddy >= a->C && a->lddx >= a->C, DP_ERR_SHAPE);
   cudaStream_t st = (cudaStream_t)stream;
-  Map mp = make_map(a->HW, a->C);
+  const bool v4 = (a->C % 4 == 0) && al16(a->x, a->ldx) && al16(a->dy, a->lddy) && al16(a->dx, a->lddx) &&
+                  al16(a->dx_add, a->ldadd) && al16(a->dx_add2, a->ldadd2);
+  Map mp = v4 ? make_map4(a->HW, a->C) : make_map(a->HW, a->C);
   char* ws = (char*)a->workspace;
   float* part = (float*)ws;
   float* fin = (float*)(ws + align256((size_t)a->N * mp.nchunks * 2 * a->C * sizeof(float)));
   float* coef = (float*)((char*)fin + align256((size_t)a->N * 2 * a->C * sizeof(float)));
   dim3 grid(mp.nchunks, a->N);
-  gn_bwd_partial_kernel<<<grid, NT, 2 * mp.PL * mp.CT * sizeof(float), st>>>(*a, mp, part);
+  if (v4) gn_bwd_partial4_kernel<<<grid, NT, 2 * mp.PL * mp.CT * 4 * sizeof(float), st>>>(*a, mp, part);
+  else gn_bwd_partial_kernel<<<grid, NT, 2 * mp.PL * mp.CT * sizeof(float), st>>>(*a, mp, part);
   if ((rc = dp_check_launch())) return rc;
   gn_bwd_finalize_kernel<<<a->N, NT, 2 * a->C * sizeof(float), st>>>(*a, mp, part, fin, coef);
   if ((rc = dp_check_launch())) return rc;
@@ -294,6 +455,7 @@ extern "C" int dp_groupnorm_bwd(const dp_gn_args* a, dp_stream_t stream) {
     gn_bwd_param_kernel<<<(a->C + 127) / 128, 128, 0, st>>>(*a, fin);
     if ((rc = dp_check_launch())) return rc;
   }
-  gn_bwd_apply_kernel<<<grid, NT, 0, st>>>(*a, mp, coef);
+  if (v4) gn_bwd_apply4_kernel<<<grid, NT, 0, st>>>(*a, mp, coef);
+  else gn_bwd_apply_kernel<<<grid, NT, 0, st>>>(*a, mp, coef);
   return dp_check_launch();
 }

@@ -58,28 +58,27 @@ __global__ void sumsq_stage2_kernel(const float* __restrict__ partial, long long
   for (int o = NT / 2; o > 0; o >>= 1) { if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
   if (threadIdx.x == 0) out[0] = (float)red[0];
 }
-__global__ void adam_kernel(const dp_adam_args a, float bc1, float bc2_sqrt) {
+struct AdamConsts { float step_size, bc2_sqrt, w1, w2, beta2, eps, max_norm, ema_d, ema_1md; };
+__global__ void adam_kernel(const dp_adam_args a, AdamConsts k) {
   // torch.optim.Adam (single-tensor path) op order:
   //   exp_avg.lerp_(g, 1-b1); exp_avg_sq.mul_(b2).addcmul_(g, g, value=1-b2)
   //   denom = exp_avg_sq.sqrt() / sqrt(bc2) + eps ; p.addcdiv_(exp_avg, denom, value=-lr/bc1)
   float clip = 1.0f;
   if (a.sumsq) {
     float total = sqrtf(*a.sumsq) * a.grad_scale;            // norm of the (scaled) gradient
-    float coef = a.max_norm / (total + 1e-6f);               // torch.nn.utils.clip_grad_norm_
+    float coef = k.max_norm / (total + 1e-6f);               // torch.nn.utils.clip_grad_norm_
     clip = coef < 1.0f ? coef : 1.0f;
   }
-  if (a.step_scalars) { bc1 = a.step_scalars[0]; bc2_sqrt = a.step_scalars[1]; }
+  if (a.step_scalars) { k.step_size = a.step_scalars[0]; k.bc2_sqrt = a.step_scalars[1]; }
   const float gs = a.grad_scale * clip;
-  const float step_size = a.lr / bc1;
-  const float w1 = 1.0f - a.beta1, w2 = 1.0f - a.beta2;
   for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < a.n; i += (long long)gridDim.x * NT) {
     float g = a.g[i] * gs;
-    float m = a.m[i]; m = m + w1 * (g - m);
-    float v = a.v[i] * a.beta2 + w2 * g * g;
-    float denom = sqrtf(v) / bc2_sqrt + a.eps;
-    float p = a.p[i] - step_size * (m / denom);
+    float m = a.m[i]; m = m + k.w1 * (g - m);
+    float v = a.v[i] * k.beta2 + k.w2 * g * g;
+    float denom = sqrtf(v) / k.bc2_sqrt + k.eps;
+    float p = a.p[i] - k.step_size * (m / denom);
     a.m[i] = m; a.v[i] = v; a.p[i] = p;
-    if (a.ema) a.ema[i] = (1.0f - a.ema_decay) * p + a.ema_decay * a.ema[i];
+    if (a.ema) a.ema[i] = k.ema_1md * p + k.ema_d * a.ema[i];   // training_utils.py:216
   }
 }
 }  // namespace
@@ -107,9 +106,13 @@ extern "C" int dp_sumsq(const float* x, int64_t n, float* partial, float* out, d
 extern "C" int dp_adam_clip_ema(const dp_adam_args* a, dp_stream_t stream) {
   DP_REQUIRE(a && a->p && a->g && a->m && a->v, DP_ERR_NULL);
   DP_REQUIRE(a->n > 0 && a->step >= 1, DP_ERR_SHAPE);
-  double bc1 = 1.0 - pow((double)a->beta1, a->step), bc2 = 1.0 - pow((double)a->beta2, a->step);
+  const double bc1 = 1.0 - pow(a->beta1, a->step), bc2 = 1.0 - pow(a->beta2, a->step);
+  AdamConsts k;
+  k.step_size = (float)(a->lr / bc1); k.bc2_sqrt = (float)sqrt(bc2);
+  k.w1 = (float)(1.0 - a->beta1); k.w2 = (float)(1.0 - a->beta2); k.beta2 = (float)a->beta2; k.eps = (float)a->eps;
+  k.max_norm = (float)a->max_norm; k.ema_d = (float)a->ema_decay; k.ema_1md = (float)(1.0 - a->ema_decay);
   long long nb = (a->n + NT * 4 - 1) / (NT * 4);
   if (nb > 148 * 16) nb = 148 * 16;
-  adam_kernel<<<(unsigned)nb, NT, 0, (cudaStream_t)stream>>>(*a, (float)bc1, (float)sqrt(bc2));
+  adam_kernel<<<(unsigned)nb, NT, 0, (cudaStream_t)stream>>>(*a, k);
   return dp_check_launch();
 }

@@ -36,7 +36,7 @@ __global__ void temb_kernel(const int64_t* __restrict__ t, const float* __restri
   if (flip) { o[k] = c; o[half + k] = s; } else { o[k] = s; o[half + k] = c; }
 }
 __global__ void add_noise_kernel(const float* __restrict__ x0, const float* __restrict__ nz, const int64_t* __restrict__ t,
-                                 const float* __restrict__ acp, float* __restrict__ out, int B, int C, int HW, int nhwc) {
+                                 const float* __restrict__ acp, float* __restrict__ out, int B, int C, int HW, int nhwc, long long ld) {
   long long total = (long long)B * C * HW;
   for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
     int hw = (int)(i % HW);
@@ -44,7 +44,7 @@ __global__ void add_noise_kernel(const float* __restrict__ x0, const float* __re
     int c = (int)(bc % C), b = (int)(bc / C);
     float ac = acp[t[b]];
     float v = sqrtf(ac) * x0[i] + sqrtf(1.0f - ac) * nz[i];
-    if (nhwc) out[((long long)b * HW + hw) * C + c] = v; else out[i] = v;
+    if (nhwc) out[((long long)b * HW + hw) * ld + c] = v; else out[i] = v;
   }
 }
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, long long ld, int N, int C, int HW) {
@@ -189,9 +189,11 @@ extern "C" int dp_timestep_embedding(const int64_t* t, const float* freqs, float
   return dp_check_launch();
 }
 extern "C" int dp_add_noise(const float* x0, const float* noise, const int64_t* t, const float* acp, float* out, int32_t B,
-                            int32_t C, int32_t H, int32_t W, int32_t out_nhwc, dp_stream_t st) {
+                            int32_t C, int32_t H, int32_t W, int32_t out_nhwc, int64_t ld_out, dp_stream_t st) {
   DP_REQUIRE(x0 && noise && t && acp && out, DP_ERR_NULL); DP_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, DP_ERR_SHAPE);
-  add_noise_kernel<<<nblocks((long long)B * C * H * W, NT), NT, 0, (cudaStream_t)st>>>(x0, noise, t, acp, out, B, C, H * W, out_nhwc);
+  DP_REQUIRE(ld_out == 0 || ld_out >= C, DP_ERR_SHAPE);
+  add_noise_kernel<<<nblocks((long long)B * C * H * W, NT), NT, 0, (cudaStream_t)st>>>(x0, noise, t, acp, out, B, C, H * W, out_nhwc,
+                                                                                    ld_out ? ld_out : C);
   return dp_check_launch();
 }
 extern "C" int dp_nchw_to_nhwc(const float* in, float* out, int64_t ld, int32_t N, int32_t C, int32_t H, int32_t W, dp_stream_t st) {

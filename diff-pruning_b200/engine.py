@@ -452,7 +452,13 @@ class Plan:
         self._setup_param_grads()
         # ---- inputs + timestep embedding chain (embeddings.py:22-62, 200-212)
         self.t_dev = torch.zeros(B, device=self.dev, dtype=torch.int64)
-        self.x_in = self.new(B, H, W, cfg.in_channels)
+        # network input / output live in buffers padded to a multiple of 4 channels (zero pad) so their pixel stride is
+        # 16-byte aligned: TMA can then read them and conv_in / conv_out run on the tensor-core path too
+        def padded(c):
+            t = torch.zeros((B, H, W, (c + 3) // 4 * 4), device=self.dev, dtype=torch.float32)
+            self._keep.append(t)
+            return View(t, 0, c)
+        self.x_in = padded(cfg.in_channels)
         half = cfg.block_out_channels[0] // 2
         self.freqs = sinusoidal_frequencies(cfg.block_out_channels[0], cfg.freq_shift).to(self.dev)
         te = m.time_embedding
@@ -585,7 +591,8 @@ class Plan:
         g = self.gn(x, m.conv_norm_out, a, silu=True)
         if self.need_grad:
             self.gn_bwd(g, x, m.conv_norm_out, lambda: self.sptr("da"), x.C)
-        self.y_out = self.new(B, H, W, cfg.out_channels)
+        self.y_out = padded(cfg.out_channels)
+        self.gradof(self.y_out).t.zero_()
         self.conv(a, m.conv_out.weight, m.conv_out.bias, self.y_out, dx_scratch="da")
 
         # ---- allocate shared scratch, bind late pointers, resolve (=|+=) of every gradient write in EXECUTION order
@@ -715,6 +722,6 @@ def add_noise_cuda(sched, x0: torch.Tensor, noise: torch.Tensor, timesteps: torc
     t = timesteps.to(device=dev, dtype=torch.int64).contiguous()
     out = torch.empty_like(x0c)
     B, Cc, H, W = x0c.shape
-    L.check(lib.dp_add_noise(x0c.data_ptr(), nz.data_ptr(), t.data_ptr(), tab.data_ptr(), out.data_ptr(), B, Cc, H, W, 0, _stream()),
+    L.check(lib.dp_add_noise(x0c.data_ptr(), nz.data_ptr(), t.data_ptr(), tab.data_ptr(), out.data_ptr(), B, Cc, H, W, 0, 0, _stream()),
             "add_noise")
     return out

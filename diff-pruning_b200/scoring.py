@@ -48,10 +48,11 @@ class TaylorScorer:
         self.plan: Plan = get_plan(model, B, H, W, self.dev, need_grad=True)
         if was_training:
             model.train()
-        self.noise_nhwc = torch.empty((B, H, W, C_), device=self.dev, dtype=torch.float32)
+        ldo = self.plan.y_out.ld                      # y_out is a C-channel view of a zero-padded ld-channel buffer
+        self.noise_nhwc = torch.zeros((B, H, W, ldo), device=self.dev, dtype=torch.float32)
         n = B * C_ * H * W
-        self.n = n
-        self.partial = torch.empty(max(1, self.lib.dp_mse_partials(n)), device=self.dev, dtype=torch.float32)
+        self.n = B * H * W * ldo                      # flat extent handed to the loss kernel (pads contribute 0)
+        self.partial = torch.empty(max(1, self.lib.dp_mse_partials(self.n)), device=self.dev, dtype=torch.float32)
         self.loss = torch.zeros(1, device=self.dev, dtype=torch.float32)
         self.use_graph = use_graph
         self.graph: Optional[torch.cuda.CUDAGraph] = None
@@ -61,13 +62,13 @@ class TaylorScorer:
         self.plan.ensure_packed()
 
     def _refresh_noise(self):
-        L.check(self.lib.dp_nchw_to_nhwc(self.noise.data_ptr(), self.noise_nhwc.data_ptr(), self.C, self.B, self.C, self.H, self.W,
-                                         _stream()), "noise nchw->nhwc")
+        L.check(self.lib.dp_nchw_to_nhwc(self.noise.data_ptr(), self.noise_nhwc.data_ptr(), self.noise_nhwc.shape[-1], self.B, self.C,
+                                         self.H, self.W, _stream()), "noise nchw->nhwc")
 
     def _body(self):
         lib, p, s = self.lib, self.plan, _stream()
         L.check(lib.dp_add_noise(self.clean.data_ptr(), self.noise.data_ptr(), p.t_dev.data_ptr(), self.acp.data_ptr(),
-                                 p.x_in.ptr, self.B, self.C, self.H, self.W, 1, s), "add_noise")
+                                 p.x_in.ptr, self.B, self.C, self.H, self.W, 1, p.x_in.ld, s), "add_noise")
         p.run_forward(s)
         gy = p.gradof(p.y_out)
         L.check(lib.dp_mse_loss_grad(p.y_out.ptr, self.noise_nhwc.data_ptr(), gy.ptr, self.n, self.loss_scale, self.grad_scale,
@@ -263,17 +264,18 @@ class FinetuneStepper:
         self.B, self.C, self.H, self.W = B, C_, H, W
         self.clean = torch.empty((B, C_, H, W), device=self.dev, dtype=torch.float32)
         self.noise = torch.empty_like(self.clean)
-        self.noise_nhwc = torch.empty((B, H, W, C_), device=self.dev, dtype=torch.float32)
-        self.nelem = B * C_ * H * W
+        self.noise_nhwc = torch.zeros((B, H, W, self.plan.y_out.ld), device=self.dev, dtype=torch.float32)
+        self.nelem = B * H * W * self.plan.y_out.ld   # flat extent incl. zero pads (contribute 0 to the loss)
         self.partial = torch.empty(max(1, self.lib.dp_mse_partials(self.nelem)), device=self.dev, dtype=torch.float32)
         self.plan.attach_grads()
 
     def _main(self):
         lib, p, s = self.lib, self.plan, _stream()
         p.run_pack(s)
-        L.check(lib.dp_nchw_to_nhwc(self.noise.data_ptr(), self.noise_nhwc.data_ptr(), self.C, self.B, self.C, self.H, self.W, s), "noise")
+        L.check(lib.dp_nchw_to_nhwc(self.noise.data_ptr(), self.noise_nhwc.data_ptr(), self.noise_nhwc.shape[-1], self.B, self.C, self.H,
+                                    self.W, s), "noise")
         L.check(lib.dp_add_noise(self.clean.data_ptr(), self.noise.data_ptr(), p.t_dev.data_ptr(), self.acp.data_ptr(),
-                                 p.x_in.ptr, self.B, self.C, self.H, self.W, 1, s), "add_noise")
+                                 p.x_in.ptr, self.B, self.C, self.H, self.W, 1, p.x_in.ld, s), "add_noise")
         p.run_forward(s)
         gy = p.gradof(p.y_out)
         # loss = (noise - out)^2 .sum(1,2,3).mean(0)  (ddpm_train.py:459)
@@ -317,7 +319,7 @@ class FinetuneStepper:
         p.t_dev.copy_(timesteps.to(device=self.dev, dtype=torch.int64), non_blocking=True)
         self.steps_done += 1
         t = self.steps_done
-        bc = torch.tensor([1.0 - self.betas[0] ** t, math.sqrt(1.0 - self.betas[1] ** t)], dtype=torch.float32)
+        bc = torch.tensor([self.lr / (1.0 - self.betas[0] ** t), math.sqrt(1.0 - self.betas[1] ** t)], dtype=torch.float32)
         self.step_scalars.copy_(bc, non_blocking=True)
         p.dropout_seed_dev.fill_(0x5DEECE66D * t & 0x7FFFFFFFFFFF)
         if self.use_graph and self.g_main is None:

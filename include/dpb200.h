@@ -167,7 +167,8 @@ int dp_timestep_embedding(const int64_t* t, const float* freqs, float* out, int3
 /* x_t = sqrt(acp[t_b])*x0 + sqrt(1-acp[t_b])*eps — scheduling_ddpm.py:415-428.  x0/noise NCHW; out NHWC if
  * out_nhwc else NCHW.  acp: alphas_cumprod table [T]. */
 int dp_add_noise(const float* x0, const float* noise, const int64_t* t, const float* acp, float* out, int32_t B,
-                 int32_t C, int32_t H, int32_t W, int32_t out_nhwc, dp_stream_t stream);
+                 int32_t C, int32_t H, int32_t W, int32_t out_nhwc, int64_t ld_out /* NHWC pixel stride, 0 = C */,
+                 dp_stream_t stream);
 
 int dp_nchw_to_nhwc(const float* in, float* out, int64_t ld_out, int32_t N, int32_t C, int32_t H, int32_t W,
                     dp_stream_t stream);
@@ -222,10 +223,12 @@ typedef struct dp_adam_args {
   int64_t n;
   float* p; const float* g; float* m; float* v; float* ema; /* ema nullable */
   const float* sumsq;   /* device scalar: total grad sum of squares; NULL = no clipping */
-  float max_norm, lr, beta1, beta2, eps, ema_decay;
+  /* hyper-parameters as doubles: the derived constants (1-beta1, 1-beta2, lr/(1-beta1^t), 1-ema_decay ...) are formed
+   * in double on the host and rounded once to fp32, exactly like the Python scalars torch feeds its kernels */
+  double max_norm, lr, beta1, beta2, eps, ema_decay;
   int32_t step;         /* 1-based; used for the bias corrections when step_scalars == NULL */
   float grad_scale;     /* multiplies g before everything (1/world for DDP mean) */
-  const float* step_scalars; /* optional DEVICE [2] = {1-beta1^t, sqrt(1-beta2^t)} so a captured CUDA graph can be
+  const float* step_scalars; /* optional DEVICE [2] = {lr/(1-beta1^t), sqrt(1-beta2^t)} so a captured CUDA graph can be
                                 replayed for every step (host-computed kernel arguments would be frozen) */
 } dp_adam_args;
 int dp_adam_clip_ema(const dp_adam_args* a, dp_stream_t stream);

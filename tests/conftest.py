@@ -41,12 +41,17 @@ def rel_err(a, b):
 
 
 def worst_grad_err(named_grads, ref):
-    """max relative error over parameters.  d/d(to_k.bias) is identically zero (softmax over keys is invariant to
-    the per-query constant q.b_k), so both sides hold pure rounding noise there: checked absolutely instead."""
+    """max relative error over parameter gradients.  Some gradients are IDENTICALLY zero in exact arithmetic
+    (d/d to_k.bias: softmax over keys is invariant to the per-query constant q.b_k; d/d conv1.bias and time_emb_proj.* when
+    the following GroupNorm has one channel per group: a per-channel shift is normalised away), so both sides hold pure
+    cancellation noise there.  Those tensors (reference RMS < 1e-5 of the largest gradient RMS) are checked absolutely."""
+    named_grads = list(named_grads)
+    rms = {k: float(ref[k].detach().double().norm()) / ref[k].numel() ** 0.5 for k, _ in named_grads}
+    top = max(rms.values())
     worst = 0.0
     for k, g in named_grads:
-        if k.endswith("to_k.bias"):
-            assert float(g.abs().max()) < 1e-6 and float(ref[k].abs().max()) < 1e-6, k
+        if rms[k] < 1e-5 * top:
+            assert float(g.detach().abs().max()) < 1e-4 * top, k
             continue
         worst = max(worst, rel_err(g, ref[k]))
     return worst

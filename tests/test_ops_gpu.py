@@ -184,7 +184,8 @@ def test_softmax_fwd_bwd(lib, rows, cols):
 
 
 GN_CASES = [(2, 8, 8, 32, 8, 1, 0), (3, 4, 4, 96, 32, 1, 16), (2, 16, 16, 128, 32, 0, 0), (2, 4, 4, 512, 32, 1, 0),
-            (2, 2, 2, 768, 32, 1, 0), (1, 32, 32, 192, 32, 1, 64), (4, 3, 5, 24, 3, 0, 0)]
+            (2, 2, 2, 768, 32, 1, 0), (1, 32, 32, 192, 32, 1, 64), (4, 3, 5, 24, 3, 0, 0),
+            (2, 8, 8, 30, 3, 1, 0), (2, 8, 8, 64, 8, 1, 2), (2, 4, 4, 358, 2, 1, 0)]   # scalar path: C%4!=0 / misaligned view
 
 
 @pytest.mark.parametrize("N,H,W,Cc,G,silu,ldx", GN_CASES)
@@ -289,7 +290,7 @@ def test_pointwise_ops(lib):
     for nh in (0, 1):
         out = torch.empty(5 * 3 * 64, device="cuda")
         assert lib.dp_add_noise(x0.cuda().data_ptr(), nz.cuda().data_ptr(), t.cuda().data_ptr(), ac.cuda().data_ptr(),
-                                out.data_ptr(), 5, 3, 8, 8, nh, S()) == 0
+                                out.data_ptr(), 5, 3, 8, 8, nh, 0, S()) == 0
         got = out.view(5, 8, 8, 3).permute(0, 3, 1, 2).cpu() if nh else out.view(5, 3, 8, 8).cpu()
         assert float((got - ref).abs().max()) < 1e-6
     # layout round trip into a wider buffer
@@ -379,7 +380,7 @@ def test_adam_clip_ema_matches_torch(lib):
         a.n, a.p, a.g, a.m, a.v, a.ema, a.sumsq = n, pd.data_ptr(), gd.data_ptr(), md.data_ptr(), vd.data_ptr(), ed.data_ptr(), ss.data_ptr()
         a.max_norm, a.lr, a.beta1, a.beta2, a.eps, a.ema_decay, a.step, a.grad_scale = 1.0, 2e-4, 0.9, 0.999, 1e-8, 0.9999, step, 1.0
         if step == 2:   # device-scalar bias corrections (graph-replay form)
-            scal.copy_(torch.tensor([1 - 0.9 ** step, math.sqrt(1 - 0.999 ** step)]))
+            scal.copy_(torch.tensor([2e-4 / (1 - 0.9 ** step), math.sqrt(1 - 0.999 ** step)]))
             a.step_scalars, a.step = scal.data_ptr(), 1
         assert lib.dp_adam_clip_ema(C.byref(a), S()) == 0
         assert rel_err(pd.cpu(), pt.detach()) < 1e-6 and rel_err(ed.cpu(), ema_ref) < 1e-6

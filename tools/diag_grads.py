@@ -6,8 +6,9 @@ import diff_pruning_b200 as dp
 from diff_pruning_b200.scoring import TaylorScorer
 
 cfgname = sys.argv[1] if len(sys.argv) > 1 else "tiny"
-cfg = {"tiny": dp.TINY_TEST_CONFIG, "cifar": dp.CIFAR10_DDPM_CONFIG}[cfgname]
-B, hw = (2, 16) if cfgname == "tiny" else (2, 32)
+cfg = {"tiny": dp.TINY_TEST_CONFIG, "cifar": dp.CIFAR10_DDPM_CONFIG,
+       "lsun_small": dict(dp.LSUN256_DDPM_CONFIG, block_out_channels=(32, 32, 64, 64, 128, 128), sample_size=64)}[cfgname]
+B, hw = {"tiny": (2, 16), "cifar": (2, 32), "lsun_small": (2, 64)}[cfgname]
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
 torch.manual_seed(0)
