@@ -34,6 +34,10 @@ struct TcParams {
   const float* residual; long long ld_res;
   int accumulate;
   int vec4;            // all epilogue pointers / strides are 16-byte aligned
+  // generalised tap table (stride-2 dgrad runs as 4 parity classes with 1/2/2/4 taps each) and output pixel mapping
+  int ntaps;
+  signed char dh[9], dw[9], wt[9];
+  int os, oa, ob, Ho, Wo;   // output pixel = (p*os + oa, q*os + ob) on an [Ho][Wo] grid
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -138,8 +142,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const int th = (tile_m / p.tiles_w) % p.tiles_h;
   const int tn = tile_m / (p.tiles_w * p.tiles_h);
   const int q0 = tw * p.bw, p0 = th * p.bh, n0 = tn * p.bn;
-  const int T = p.R * p.S;
-  const int num_iters = T * p.kchunks;
+  const int num_iters = p.ntaps * p.kchunks;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -152,10 +155,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         mbar_wait(empty_bar(s), ph ^ 1u);
         mbar_expect_tx(full_bar(s), A_BYTES + 2 * B_BYTES);
         const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
-        const int r = tap / p.S, sx = tap - r * p.S;
         const uint32_t st = sbase + s * STAGE_BYTES;
-        tma_load_4d(st, &mapA, full_bar(s), kc * BK, q0 + sx - p.pad, p0 + r - p.pad, n0);
-        const int tapb = p.flip ? (T - 1 - tap) : tap;
+        tma_load_4d(st, &mapA, full_bar(s), kc * BK, q0 + p.dw[tap], p0 + p.dh[tap], n0);
+        const int tapb = p.wt[tap];
         tma_load_3d(st + 2 * A_BYTES, &mapBh, full_bar(s), kc * BK, nblk * BN, tapb);
         tma_load_3d(st + 2 * A_BYTES + B_BYTES, &mapBl, full_bar(s), kc * BK, nblk * BN, tapb);
       }
@@ -213,7 +215,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int w_l = row % p.bw, h_l = (row / p.bw) % p.bh, n_l = row / (p.bw * p.bh);
     const int img = n0 + n_l;
     const bool row_ok = img < p.Nimg;
-    const long long m = ((long long)img * p.H + (p0 + h_l)) * p.W + (q0 + w_l);
+    const long long m = ((long long)img * p.Ho + ((p0 + h_l) * p.os + p.oa)) * p.Wo + ((q0 + w_l) * p.os + p.ob);
     float* yrow = p.y + m * p.ldy;
     const float* rrow = p.residual ? p.residual + m * p.ld_res : nullptr;
     const float* arow = p.rowadd ? p.rowadd + (long long)img * p.ld_rowadd : nullptr;
@@ -347,8 +349,7 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   const int th = (tile_m / p.tiles_w) % p.tiles_h;
   const int tn = tile_m / (p.tiles_w * p.tiles_h);
   const int q0 = tw * p.bw, p0 = th * p.bh, n0 = tn * p.bn;
-  const int T = p.R * p.S;
-  const int num_iters = T * p.kchunks;
+  const int num_iters = p.ntaps * p.kchunks;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -361,10 +362,9 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         mbar_wait(empty_bar(s), ph ^ 1u);
         mbar_expect_tx(full_bar(s), A_BYTES + 2 * B_BYTES);
         const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
-        const int r = tap / p.S, sx = tap - r * p.S;
         const uint32_t st = sbase + s * STAGE_BYTES;
-        tma_load_4d(st, &mapA, full_bar(s), kc * BK, q0 + sx - p.pad, p0 + r - p.pad, n0);
-        const int tapb = p.flip ? (T - 1 - tap) : tap;
+        tma_load_4d(st, &mapA, full_bar(s), kc * BK, q0 + p.dw[tap], p0 + p.dh[tap], n0);
+        const int tapb = p.wt[tap];
         tma_load_3d(st + A_BYTES, &mapBh, full_bar(s), kc * BK, nblk * BN, tapb);
         tma_load_3d(st + A_BYTES + B_BYTES, &mapBl, full_bar(s), kc * BK, nblk * BN, tapb);
       }
@@ -425,7 +425,7 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     const int w_l = row % p.bw, h_l = (row / p.bw) % p.bh, n_l = row / (p.bw * p.bh);
     const int img = n0 + n_l;
     const bool row_ok = img < p.Nimg;
-    const long long m = ((long long)img * p.H + (p0 + h_l)) * p.W + (q0 + w_l);
+    const long long m = ((long long)img * p.Ho + ((p0 + h_l) * p.os + p.oa)) * p.Wo + ((q0 + w_l) * p.os + p.ob);
     float* yrow = p.y + m * p.ldy;
     const float* rrow = p.residual ? p.residual + m * p.ld_res : nullptr;
     const float* arow2 = p.rowadd ? p.rowadd + (long long)img * p.ld_rowadd : nullptr;
@@ -518,27 +518,33 @@ __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr) {
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ CUtensorMap mapX, const WgParams p) {
-  constexpr int STAGE_BYTES = 4 * WG_T;   // dy(hi in place), dy_lo, x(hi in place), x_lo
+  // stage smem: dy raw (16 KB, read once by the splitter) | x (hi in place, 16 KB) | x_lo (16 KB)
+  // The A operand (dY^T: lane = out-channel, column = pixel) is built in TENSOR MEMORY: thread <-> out-channel reads its
+  // channel across the 32 pixel rows of the (32B-atom swizzled) tile — one conflict-free 128 B row per warp instruction —
+  // splits hi/lo and writes 2 x 32 columns with tcgen05.st; the MMA then runs in TS mode (A from TMEM, B = x MN-major smem).
+  // TMEM: [0,128) main acc | [128,256) correction acc | 256 + 64*s: A_hi(32) A_lo(32) of stage s (4 stages -> 512 columns).
+  constexpr int WSTAGES = 4;
+  constexpr int STAGE_BYTES = 3 * WG_T;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t pad_to = ((raw + 1023u) & ~1023u) - raw;
   uint8_t* smem = smem_raw + pad_to;
   const uint32_t sbase = raw + pad_to;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  const uint32_t bar0 = sbase + STAGES * STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WSTAGES * STAGE_BYTES);
+  const uint32_t bar0 = sbase + WSTAGES * STAGE_BYTES;
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
-  auto conv_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
-  const uint32_t tmem_full_bar = bar0 + 8u * (3 * STAGES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+  auto conv_bar = [&](int s) { return bar0 + 8u * (WSTAGES + s); };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (2 * WSTAGES + s); };
+  const uint32_t tmem_full_bar = bar0 + 8u * (3 * WSTAGES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * WSTAGES + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(conv_bar(s), 128); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < WSTAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(conv_bar(s), 128); mbar_init(empty_bar(s), 1); }
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -561,8 +567,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapDy)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapX)) : "memory");
       for (int it = 0; it < num_iters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        const int s = it % WSTAGES;
+        const uint32_t ph = (uint32_t)(it / WSTAGES) & 1u;
         mbar_wait(empty_bar(s), ph ^ 1u);
         mbar_expect_tx(full_bar(s), 2 * WG_T);
         const int chunk = chunk0 + it;
@@ -574,28 +580,29 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant
 #pragma unroll
         for (int b = 0; b < 4; ++b) {   // 4 blocks of 32 channels = 128 channels per operand
           tma_load_4d(st + b * 4096, &mapDy, full_bar(s), kt * 128 + b * 32, q0, p0, n0);
-          tma_load_4d(st + 2 * WG_T + b * 4096, &mapX, full_bar(s), ct * 128 + b * 32, q0 + sx - p.pad, p0 + r - p.pad, n0);
+          tma_load_4d(st + WG_T + b * 4096, &mapX, full_bar(s), ct * 128 + b * 32, q0 + sx - p.pad, p0 + r - p.pad, n0);
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // A and B MN-major: bit 15 (a_major) and bit 16 (b_major) set
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      // B MN-major (bit 16); A comes from TMEM
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       for (int it = 0; it < num_iters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        const int s = it % WSTAGES;
+        const uint32_t ph = (uint32_t)(it / WSTAGES) & 1u;
         mbar_wait(conv_bar(s), ph);
+        mbar_wait(full_bar(s), ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t st = sbase + s * STAGE_BYTES;
+        const uint32_t a_t = tmem_base + 256u + 64u * s;
 #pragma unroll
         for (int k = 0; k < WG_KPIX / 8; ++k) {
-          const uint64_t a_hi = umma_desc_mn(st + k * 1024), a_lo = umma_desc_mn(st + WG_T + k * 1024);
-          const uint64_t b_hi = umma_desc_mn(st + 2 * WG_T + k * 1024), b_lo = umma_desc_mn(st + 3 * WG_T + k * 1024);
+          const uint64_t b_hi = umma_desc_mn(st + WG_T + k * 1024), b_lo = umma_desc_mn(st + 2 * WG_T + k * 1024);
           const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
-          umma_tf32(tmem_base + 128, a_lo, b_hi, idesc, first);
-          umma_tf32(tmem_base + 128, a_hi, b_lo, idesc, 1u);
-          umma_tf32(tmem_base, a_hi, b_hi, idesc, first);
+          umma_tf32_ts(tmem_base + 128, a_t + 32 + k * 8, b_hi, idesc, first);
+          umma_tf32_ts(tmem_base + 128, a_t + k * 8, b_lo, idesc, 1u);
+          umma_tf32_ts(tmem_base, a_t + k * 8, b_hi, idesc, first);
         }
         umma_commit(empty_bar(s));
       }
@@ -603,14 +610,33 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant
     }
   } else {
     const int tid = threadIdx.x - 64;
+    const int q = warp & 3;                   // TMEM lane quarter == 32-channel block of dy
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     for (int it = 0; it < num_iters; ++it) {
-      const int s = it % STAGES;
-      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      const int s = it % WSTAGES;
+      const uint32_t ph = (uint32_t)(it / WSTAGES) & 1u;
       mbar_wait(full_bar(s), ph);
+      // (1) dy^T -> TMEM.  Block q holds channels 32q..32q+31 as rows [pix][32 ch]; SWIZZLE_128B_ATOM_32B: the 32-byte
+      //     chunk j of row `pix` sits at chunk position j ^ (pix & 3).
+      {
+        const uint8_t* blk = smem + s * STAGE_BYTES + q * 4096;
+        uint32_t hi[32], lo[32];
 #pragma unroll
-      for (int op = 0; op < 2; ++op) {
-        float4* A = reinterpret_cast<float4*>(smem + s * STAGE_BYTES + op * 2 * WG_T);
-        float4* Al = reinterpret_cast<float4*>(smem + s * STAGE_BYTES + op * 2 * WG_T + WG_T);
+        for (int pix = 0; pix < 32; ++pix) {
+          const int chunk = (lane >> 3) ^ (pix & 3);
+          const float v = *reinterpret_cast<const float*>(blk + pix * 128 + chunk * 32 + (lane & 7) * 4);
+          const float h = tf32_rna(v);
+          hi[pix] = __float_as_uint(h);
+          lo[pix] = __float_as_uint(v - h);
+        }
+        const uint32_t a_t = tmem_base + lane_addr + 256u + 64u * s;
+        tmem_st32(a_t, hi);
+        tmem_st32(a_t + 32, lo);
+      }
+      // (2) x tile: hi in place, lo to the side (elementwise, layout agnostic)
+      {
+        float4* A = reinterpret_cast<float4*>(smem + s * STAGE_BYTES + WG_T);
+        float4* Al = reinterpret_cast<float4*>(smem + s * STAGE_BYTES + 2 * WG_T);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int idx = tid + 128 * i;
@@ -621,12 +647,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant
           Al[idx] = l;
         }
       }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(conv_bar(s));
     }
     mbar_wait(tmem_full_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int q = warp & 3;
     const int row = q * 32 + lane;            // k_out within the tile
     const int kout = kt * 128 + row;
     const long long TC_ = (long long)T * p.C;
@@ -634,7 +661,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant
 #pragma unroll 1
     for (int j = 0; j < 4; ++j) {
       uint32_t v[32], u[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 32);
+      const uint32_t taddr = tmem_base + lane_addr + (uint32_t)(j * 32);
       asm volatile(
           "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
           "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -666,7 +693,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -701,7 +728,7 @@ int tc_init() {
   ok = ok && cudaFuncSetAttribute(conv_tc_ts_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   STAGES_TS * (A_BYTES + 2 * 64 * BK * 4) + 2048) == cudaSuccess;
   g_use_ss = getenv("DPB200_TC_SS") != nullptr;
-  ok = ok && cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGES * 4 * WG_T + 2048) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 3 * WG_T + 2048) == cudaSuccess;
   if (!ok) { (void)cudaGetLastError(); return 0; }
   g_tc_state = 1;
   return 1;
@@ -734,17 +761,18 @@ bool pick_box(int N, int H, int W, int& bw, int& bh, int& bn) {
   return true;
 }
 
-// Shared launcher.  act: [Nimg][H][W][Kg] view (ld_act) = A operand; w_hi/w_lo: [T][Nout][Kg]; out: [Nimg][H][W][Nout] view.
+struct TapTable { int n; signed char dh[9], dw[9], wt[9]; };
+// Shared launcher.  act: [Nimg][H][W][Kg] view (ld_act) = A operand on whose pixel grid the M tiles live; w_hi/w_lo: [T][Nout][Kg];
+// out: [Nimg][Ho][Wo][Nout] view, output pixel = (p*os+oa, q*os+ob).
 int launch_tc(const float* act, long long ld_act, int Nimg, int H, int W, int Kg, const float* w_hi, const float* w_lo, int Nout,
-              int R, int S, int pad, int flip, float* out, long long ld_out, const float* bias, const float* rowadd,
-              long long ld_rowadd, const float* residual, long long ld_res, int accumulate, cudaStream_t st) {
+              int T, const TapTable& taps, int os, int oa, int ob, int Ho, int Wo, float* out, long long ld_out, const float* bias,
+              const float* rowadd, long long ld_rowadd, const float* residual, long long ld_res, int accumulate, cudaStream_t st) {
   if (!tc_init()) return DP_ERR_UNSUPPORTED;
   if (!w_hi || !w_lo) return DP_ERR_UNSUPPORTED;
   if (ld_act % 4 || ((uintptr_t)act & 15) || ((uintptr_t)w_hi & 15) || ((uintptr_t)w_lo & 15)) return DP_ERR_UNSUPPORTED;
   if (Kg % 4) return DP_ERR_UNSUPPORTED;                 // packed weight rows [Nout][Kg] must be 16-byte multiples for TMA
   int bw, bh, bn;
   if (!pick_box(Nimg, H, W, bw, bh, bn)) return DP_ERR_UNSUPPORTED;
-  const int T = R * S;
   CUtensorMap mA, mBh, mBl;
   {
     cuuint64_t dims[4] = {(cuuint64_t)Kg, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Nimg};
@@ -760,7 +788,10 @@ int launch_tc(const float* act, long long ld_act, int Nimg, int H, int W, int Kg
     if (!make_map(&mBh, w_hi, 3, dims, str, box) || !make_map(&mBl, w_lo, 3, dims, str, box)) return DP_ERR_UNSUPPORTED;
   }
   TcParams p{};
-  p.Nimg = Nimg; p.H = H; p.W = W; p.Nout = Nout; p.R = R; p.S = S; p.pad = pad; p.flip = flip;
+  p.Nimg = Nimg; p.H = H; p.W = W; p.Nout = Nout; p.R = 0; p.S = 0; p.pad = 0; p.flip = 0;
+  p.ntaps = taps.n;
+  for (int i = 0; i < 9; ++i) { p.dh[i] = taps.dh[i]; p.dw[i] = taps.dw[i]; p.wt[i] = taps.wt[i]; }
+  p.os = os; p.oa = oa; p.ob = ob; p.Ho = Ho; p.Wo = Wo;
   p.kchunks = (Kg + BK - 1) / BK;
   p.bw = bw; p.bh = bh; p.bn = bn; p.tiles_w = W / bw; p.tiles_h = H / bh;
   p.y = out; p.ldy = ld_out; p.bias = bias; p.rowadd = rowadd; p.ld_rowadd = ld_rowadd; p.residual = residual; p.ld_res = ld_res;
@@ -798,25 +829,64 @@ __global__ void pack_tc_kernel(const float* __restrict__ w, int K, int C, int RS
 
 int dp_tc_runtime_ok() { return tc_init(); }
 
+static TapTable dense_taps(int R, int S, int pad, bool flip) {
+  TapTable t{};
+  t.n = R * S;
+  for (int r = 0; r < R; ++r)
+    for (int s = 0; s < S; ++s) {
+      int i = r * S + s;
+      t.dh[i] = (signed char)(r - pad); t.dw[i] = (signed char)(s - pad);
+      t.wt[i] = (signed char)(flip ? (R * S - 1 - i) : i);
+    }
+  return t;
+}
+
 int dp_conv2d_fprop_tc(const dp_conv_args* a, dp_stream_t stream) {
   if (!a || !a->x || !a->y) return DP_ERR_UNSUPPORTED;   // let the SIMT entry produce the precise error
   if (a->stride != 1 || a->R != a->S || (a->R != 1 && a->R != 3) || a->pad_t != (a->R - 1) / 2 || a->pad_l != a->pad_t) return DP_ERR_UNSUPPORTED;
   if (a->P != a->H || a->Q != a->W) return DP_ERR_UNSUPPORTED;
   if (a->N <= 0 || a->H <= 0 || a->W <= 0 || a->C <= 0 || a->K <= 0 || a->ldx < a->C || a->ldy < a->K) return DP_ERR_UNSUPPORTED;
-  return launch_tc((const float*)a->x, a->ldx, a->N, a->H, a->W, a->C, a->w_tc_hi, a->w_tc_lo, a->K, a->R, a->S, a->pad_t, 0,
-                   (float*)a->y, a->ldy, a->bias, a->rowadd, a->ld_rowadd, a->residual, a->ld_res,
-                   (a->flags & DP_CONV_ACCUMULATE) ? 1 : 0, (cudaStream_t)stream);
+  return launch_tc((const float*)a->x, a->ldx, a->N, a->H, a->W, a->C, a->w_tc_hi, a->w_tc_lo, a->K, a->R * a->S,
+                   dense_taps(a->R, a->S, a->pad_t, false), 1, 0, 0, a->H, a->W, (float*)a->y, a->ldy, a->bias, a->rowadd,
+                   a->ld_rowadd, a->residual, a->ld_res, (a->flags & DP_CONV_ACCUMULATE) ? 1 : 0, (cudaStream_t)stream);
 }
 
-// stride-1 dgrad == fprop of dy with the taps flipped and the (K,C) roles swapped: dx[n,h,w,c] = sum dy[n,h+1-r,w+1-s,k] W[k,c,r,s]
+// stride-1 dgrad == fprop of dy with the taps flipped and the (K,C) roles swapped: dx[n,h,w,c] = sum dy[n,h+1-r,w+1-s,k] W[k,c,r,s].
+// stride-2 dgrad: dx[2i+a, 2j+b] only sees taps with (a+pad-r), (b+pad-s) even -> 4 parity classes, each a dense GEMM over the
+// dy grid with 1/2/2/4 taps and a strided output mapping (no MACs wasted on structural zeros).
 int dp_conv2d_dgrad_tc(const dp_conv_args* a, dp_stream_t stream) {
   if (!a || !a->x || !a->y) return DP_ERR_UNSUPPORTED;
-  if (a->stride != 1 || a->R != a->S || (a->R != 1 && a->R != 3) || a->pad_t != (a->R - 1) / 2 || a->pad_l != a->pad_t) return DP_ERR_UNSUPPORTED;
-  if (a->P != a->H || a->Q != a->W) return DP_ERR_UNSUPPORTED;
   if (a->N <= 0 || a->H <= 0 || a->W <= 0 || a->C <= 0 || a->K <= 0 || a->ldx < a->C || a->ldy < a->K) return DP_ERR_UNSUPPORTED;
-  return launch_tc((const float*)a->y, a->ldy, a->N, a->H, a->W, a->K, a->w_tc_hi, a->w_tc_lo, a->C, a->R, a->S, a->pad_t, 1,
-                   (float*)a->x, a->ldx, nullptr, nullptr, 0, nullptr, 0, (a->flags & DP_CONV_ACCUMULATE) ? 1 : 0,
-                   (cudaStream_t)stream);
+  if (a->R != a->S || (a->R != 1 && a->R != 3)) return DP_ERR_UNSUPPORTED;
+  const int acc = (a->flags & DP_CONV_ACCUMULATE) ? 1 : 0;
+  if (a->stride == 1) {
+    if (a->pad_t != (a->R - 1) / 2 || a->pad_l != a->pad_t || a->P != a->H || a->Q != a->W) return DP_ERR_UNSUPPORTED;
+    return launch_tc((const float*)a->y, a->ldy, a->N, a->H, a->W, a->K, a->w_tc_hi, a->w_tc_lo, a->C, a->R * a->S,
+                     dense_taps(a->R, a->S, a->pad_t, true), 1, 0, 0, a->H, a->W, (float*)a->x, a->ldx, nullptr, nullptr, 0, nullptr, 0,
+                     acc, (cudaStream_t)stream);
+  }
+  if (a->stride != 2 || a->R != 3 || a->H != 2 * a->P || a->W != 2 * a->Q) return DP_ERR_UNSUPPORTED;
+  TapTable cls[4];
+  for (int ca = 0; ca < 2; ++ca)
+    for (int cb = 0; cb < 2; ++cb) {
+      TapTable& t = cls[ca * 2 + cb];
+      t = TapTable{};
+      for (int r = 0; r < 3; ++r)
+        for (int s = 0; s < 3; ++s) {
+          int nh = ca + a->pad_t - r, nw = cb + a->pad_l - s;
+          if ((nh & 1) || (nw & 1)) continue;
+          t.dh[t.n] = (signed char)(nh / 2); t.dw[t.n] = (signed char)(nw / 2); t.wt[t.n] = (signed char)(r * 3 + s);
+          ++t.n;
+        }
+      if (t.n == 0) return DP_ERR_UNSUPPORTED;
+    }
+  for (int ca = 0; ca < 2; ++ca)
+    for (int cb = 0; cb < 2; ++cb) {
+      int rc = launch_tc((const float*)a->y, a->ldy, a->N, a->P, a->Q, a->K, a->w_tc_hi, a->w_tc_lo, a->C, 9, cls[ca * 2 + cb], 2, ca, cb,
+                         a->H, a->W, (float*)a->x, a->ldx, nullptr, nullptr, 0, nullptr, 0, acc, (cudaStream_t)stream);
+      if (rc != DP_OK) return (ca == 0 && cb == 0) ? rc : (rc == DP_ERR_UNSUPPORTED ? DP_ERR_SHAPE : rc);
+    }
+  return DP_OK;
 }
 
 // 32-pixel K-chunk box of an [N][H][W] grid
@@ -863,7 +933,7 @@ int dp_conv2d_wgrad_tc(const dp_conv_args* a, dp_stream_t stream) {
   p.ws = a->workspace;
   const int k_tiles = (a->K + 127) / 128;
   dim3 grid((unsigned)(k_tiles * p.c_tiles * a->R * a->S), (unsigned)a->splits);
-  wgrad_tc_kernel<<<grid, NTHREADS, STAGES * 4 * WG_T + 2048, (cudaStream_t)stream>>>(mDy, mX, p);
+  wgrad_tc_kernel<<<grid, NTHREADS, 4 * 3 * WG_T + 2048, (cudaStream_t)stream>>>(mDy, mX, p);
   return dp_check_launch();
 }
 

@@ -142,3 +142,36 @@ def test_single_pass_tf32_would_not_be_enough(lib):
     one = (hi(x).double() @ hi(w).double().t())
     three = one + ((x - hi(x)).double() @ hi(w).double().t()) + (hi(x).double() @ (w - hi(w)).double().t())
     assert rel_err(one, exact) > 1e-4 and rel_err(three, exact) < 1e-6
+
+
+@pytest.mark.parametrize("N,Cin,H,K", [(2, 64, 16, 64), (4, 128, 8, 96), (1, 32, 32, 160)])
+def test_stride2_dgrad_parity_classes(lib, N, Cin, H, K):
+    """Downsample2D backward (stride 2, F.pad(0,1,0,1) folded, resnet.py:213-218) as 4 tensor-core parity-class GEMMs."""
+    from diff_pruning_b200 import _lib as L
+    g = torch.Generator().manual_seed(N + Cin)
+    x = torch.randn(N, Cin, H, H, generator=g).requires_grad_(True)
+    w = torch.randn(K, Cin, 3, 3, generator=g) / math.sqrt(Cin * 9)
+    y = F.conv2d(F.pad(x, (0, 1, 0, 1)), w, None, stride=2)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    P = H // 2
+    wd = w.contiguous().cuda()
+    packs = [torch.empty(w.numel(), device="cuda") for _ in range(4)]
+    assert lib.dp_pack_conv_weight_tc(wd.data_ptr(), K, Cin, 3, 3, *[p.data_ptr() for p in packs], S()) == 0
+    ck, kc = torch.empty(w.numel(), device="cuda"), torch.empty(w.numel(), device="cuda")
+    assert lib.dp_pack_conv_weight(wd.data_ptr(), K, Cin, 3, 3, ck.data_ptr(), kc.data_ptr(), S()) == 0
+    gyd = nhwc(gy)
+    gx = torch.full((N, H, H, Cin), float("nan"), device="cuda")
+    d = L.ConvArgs()
+    d.N, d.H, d.W, d.C, d.P, d.Q, d.K = N, H, H, Cin, P, P, K
+    d.R = d.S = 3
+    d.stride, d.pad_t, d.pad_l, d.splits = 2, 0, 0, 1
+    d.x, d.ldx, d.y, d.ldy = gx.data_ptr(), Cin, gyd.data_ptr(), K
+    d.w, d.w_tc_hi, d.w_tc_lo = kc.data_ptr(), packs[2].data_ptr(), packs[3].data_ptr()
+    n0 = lib.dp_launch_count()
+    assert lib.dp_conv2d_dgrad(C.byref(d), S()) == 0
+    assert lib.dp_launch_count() - n0 == 4          # four parity-class launches, i.e. the tensor-core path was taken
+    assert rel_err(nchw(gx), x.grad) < 1.5e-5
+    d.flags = 1
+    assert lib.dp_conv2d_dgrad(C.byref(d), S()) == 0
+    assert rel_err(nchw(gx), 2 * x.grad) < 1.5e-5
