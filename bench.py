@@ -159,6 +159,64 @@ def run_reference(args, rank, world):
         "gpu_launches": 0}), flush=True)
 
 
+def pruned_c1_model(dev):
+    """C1 pruned at ratio 0.3 to the reference's 19.85 M-parameter architecture (tests/golden/cifar_cfg1.pt records which
+    channel positions the reference removed in BASELINE config 1); weights are the seed-0 random init, sliced."""
+    import diff_pruning_b200 as dp
+    from diff_pruning_b200 import pruning
+    path = os.path.join(ROOT, "tests", "golden", "cifar_cfg1.pt")
+    if not os.path.exists(path):
+        return None
+    G = torch.load(path, map_location="cpu", weights_only=False)
+    torch.manual_seed(0)
+    m = dp.UNet2DModel(**dp.CIFAR10_DDPM_CONFIG)
+    mods = dict(m.named_modules())
+    expand = lambda i: list(range(i[1], i[1] + i[2])) if isinstance(i, tuple) and i and i[0] == "range" else list(i)
+    for g in G["variants"]["taylor"]["groups"]:
+        pruning.apply_group(mods, [(n, k, expand(i)) for n, k, i in g["items"]], g["idxs"], g["channels"])
+    pruning.fix_static_attributes(m)
+    return m.to(dev)
+
+
+def finetune_bench(args, rank, world, dev, barrier):
+    """Secondary metric of BASELINE.json: finetune imgs/sec on the pruned C1 network — ddpm_train.py:437-469
+    (antithetic timesteps, add_noise, fwd, loss, bwd, clip 1.0, Adam 2e-4, EMA 0.9999, dropout 0.1), batch 128 per GPU,
+    gradient all-reduce (mean) per step when N > 1."""
+    import torch.distributed as dist
+    from diff_pruning_b200.scoring import FinetuneStepper
+    m = pruned_c1_model(dev)
+    if m is None:
+        return None
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.1                      # scripts/finetune_ddpm_cifar10.sh --dropout 0.1 (utils.set_dropout)
+    m.train()
+    B = args.batch
+    st = FinetuneStepper(m, lr=2e-4, ema_decay=0.9999, max_grad_norm=1.0, use_graph=not args.no_graph)
+    g = torch.Generator().manual_seed(7 + rank)
+    clean, noise = torch.randn(B, 3, 32, 32, generator=g).to(dev), torch.randn(B, 3, 32, 32, generator=g).to(dev)
+    t = torch.randint(0, 1000, (B // 2 + 1,), generator=g)
+    t = torch.cat([t, 1000 - t - 1])[:B].to(dev)
+    K = max(3, min(args.steps, 10))
+    for _ in range(3):
+        st.step(clean, noise, t)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        st.step(clean, noise, t)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms[0])
+    nparams = sum(p.numel() for p in m.parameters())
+    return {"metric": "finetune_imgs_per_sec", "value": world * B * K / (ms * 1e-3), "unit": "imgs/s", "ms_per_step": ms / K, "steps": K,
+            "config": f"pruned C1 ({nparams / 1e6:.3f} M params, ratio 0.3 architecture), batch {B}/GPU, dropout 0.1, Adam+clip+EMA, "
+                      f"{world} GPU(s)", "loss": float(st.loss.item())}
+
+
 def conv_flops(plan):
     """Algorithmic FLOPs of the 4-D-weight convolutions in one pass (fprop + dgrad + wgrad), from the plan."""
     return plan.B * CONV_FLOP_PER_IMAGE_PASS
@@ -277,12 +335,18 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
+    # ---------------- roofline of the dominant kernel (conv implicit GEMM), live CUDA events
+    conv_s, n_conv = _timed_pass(sc, None) if rank == 0 else (1.0, 0)
+    plan_B = sc.plan.B
+    del sc
+    if hasattr(model, "_dpb200_plans"):
+        model._dpb200_plans.clear()
+    torch.cuda.empty_cache()
+    finetune_leg = finetune_bench(args, rank, world, dev, barrier) if not args.no_finetune else None
     if rank != 0:
         return
-    # ---------------- roofline of the dominant kernel (conv implicit GEMM), live CUDA events
-    conv_s, n_conv = _timed_pass(sc, None)
     hbm, tf_sus, tf_burst, which = peaks()
-    flops = conv_flops(sc.plan)
+    flops = plan_B * CONV_FLOP_PER_IMAGE_PASS
     achieved = flops / conv_s / 1e12
     tc = bool(lib.dp_tc_available())
     roofline = {"bound": "tensor", "achieved": achieved, "peak": tf_sus, "unit": "TFLOP/s", "frac": achieved / tf_sus,
@@ -294,6 +358,7 @@ def run_ours(args, rank, world, local_rank):
     value = world * args.steps / (ms * 1e-3)
     e2e = world * args.steps / (ms_e2e * 1e-3)
     cpu = cpu_oracle_passes(B, 16, min_seconds=12.0, max_passes=8) if args.gpus == 1 and not args.no_cpu else None
+    fin = finetune_leg
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -309,6 +374,8 @@ def run_ours(args, rank, world, local_rank):
     }
     if cpu is not None:
         out["cpu_baseline"] = cpu
+    if fin is not None:
+        out["finetune"] = fin
     print(json.dumps(out), flush=True)
 
 
@@ -322,6 +389,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--profile-pass", action="store_true", help="run one eager pass inside cudaProfilerStart/Stop (ncu)")
+    ap.add_argument("--no-finetune", action="store_true", help="skip the secondary finetune imgs/s leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     rank, world, local_rank = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))

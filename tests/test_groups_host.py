@@ -1,0 +1,42 @@
+"""The structural group derivation (pruning.build_groups) against the groups torch_pruning's DependencyGraph produced in
+the reference run (tests/golden/cifar_cfg1.pt), through the whole interactive prune sequence.  CPU only, no compute."""
+import torch
+
+from conftest import expand, load_golden
+import diff_pruning_b200 as dp
+from diff_pruning_b200 import pruning
+
+
+def norm(items):
+    return sorted((n, k, tuple(sorted(i))) for n, k, i in items)
+
+
+def test_groups_match_reference_through_the_prune_sequence():
+    G = load_golden("cifar_cfg1.pt")["variants"]["taylor"]
+    torch.manual_seed(0)
+    m = dp.UNet2DModel(**dp.CIFAR10_DDPM_CONFIG)
+    morder = pruning.traced_module_order(m)
+    first = pruning.build_groups(m, ignored_layers=[m.conv_out], module_order=morder)
+    assert [g["root"] for g in first] == [g["root"] for g in G["groups"]]          # same 50 groups, same order
+    mods = dict(m.named_modules())
+    for ref in G["groups"]:
+        mine = next(g for g in pruning.build_groups(m, ignored_layers=[m.conv_out], module_order=morder) if g["root"] == ref["root"])
+        assert mine["channels"] == ref["channels"] and mine["ch_groups"] == ref["ch_groups"], ref["root"]
+        assert norm(mine["items"]) == norm((n, k, expand(i)) for n, k, i in ref["items"]), ref["root"]
+        pruning.apply_group(mods, mine["items"], ref["idxs"], mine["channels"])     # the reference's selection
+    pruning.fix_static_attributes(m)
+    assert {k: list(v.shape) for k, v in m.state_dict().items()} == G["pruned_shapes"]
+    assert sum(p.numel() for p in m.parameters()) == 19851157
+    # the pruned module tree still builds a plan-able / traceable network
+    with torch.no_grad(), dp.trace_mode():
+        out = m(torch.randn(1, 3, 32, 32), torch.ones(1).long()).sample
+    assert out.shape == (1, 3, 32, 32)
+
+
+def test_groups_lsun_family_counts():
+    torch.manual_seed(0)
+    m = dp.UNet2DModel(**dict(dp.LSUN256_DDPM_CONFIG, block_out_channels=(32, 32, 64, 64, 128, 128)))
+    gs = pruning.build_groups(m, ignored_layers=[m.conv_out])
+    prod = {n for g in gs for n, k, _ in g["items"] if k == "out"}
+    layers = {n for n, mod in m.named_modules() if isinstance(mod, (torch.nn.Conv2d, torch.nn.Linear))}
+    assert prod == layers - {"conv_out"}          # every conv / linear output is in exactly one group

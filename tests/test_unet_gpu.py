@@ -112,25 +112,40 @@ def test_cfg1_scores_and_masks_bit_exact():
         mv = copy.deepcopy(m)
         for k, p in mv.named_parameters():
             p.grad = grads[k].clone()
-        mods = dict(mv.named_modules())
+        # the whole product pipeline: structural groups in the reference's order -> device-side scores -> selection -> slicing
+        rec = pruning.taylor_prune(mv, G["ratio"], variant, ignored_layers=[mv.conv_out])
+        assert [r["root"] for r in rec] == [g["root"] for g in V["groups"]]
         worst_imp = 0.0
-        for g in V["groups"]:
-            items = [(n, k, expand(i)) for n, k, i in g["items"]]
-            named_w = {n + ".weight": mods[n].weight for n, _, _ in items}
-            named_g = {n + ".weight": mods[n].weight.grad for n, _, _ in items}
-            imp = group_importance(items, named_w, named_g, variant)
-            worst_imp = max(worst_imp, rel_err(imp, g["imp"]))
-            sel = select_pruning_idxs(imp, g["ch_groups"], g["n_pruned"])
-            assert sorted(sel) == sorted(g["idxs"]), (variant, g["root"], worst_imp)   # bit-exact mask
-            pruning.apply_group(mods, items, sel, g["channels"])
+        for r, g in zip(rec, V["groups"]):
+            worst_imp = max(worst_imp, rel_err(r["imp"], g["imp"]))
+            assert sorted(r["idxs"]) == sorted(g["idxs"]), (variant, g["root"], worst_imp)   # bit-exact mask
         assert worst_imp < 2e-3, (variant, worst_imp)
-        pruning.fix_static_attributes(mv)
         assert {k: list(v.shape) for k, v in mv.state_dict().items()} == V["pruned_shapes"]
         assert sum(p.numel() for p in mv.parameters()) == V["pruned"][1] == 19851157
         with torch.no_grad():
             t = (10 * torch.ones(2, device="cuda")).long()
             out = mv(sched.add_noise(clean[:2].cuda(), noise[:2].cuda(), t), t).sample
         assert max_rel(out, V["pruned_eps_b2_t10"]) < 1e-4, variant
+    # the same through the reference's own call sequence (ddpm_prune.py:60,79-87,108-116) on the compat names
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "diff-pruning_b200", "compat"))
+    import torch_pruning as tp
+    from diffusers.models.resnet import Downsample2D, Upsample2D
+    mv = copy.deepcopy(m)
+    for k, p in mv.named_parameters():
+        p.grad = grads[k].clone()
+    ex = {"sample": torch.randn(1, 3, 32, 32).cuda(), "timestep": torch.ones((1,)).long().cuda()}
+    pr = tp.pruner.MagnitudePruner(mv, ex, importance=tp.importance.TaylorImportance(multivariable=True), iterative_steps=1,
+                                   channel_groups={}, ch_sparsity=G["ratio"], ignored_layers=[mv.conv_out])
+    got = []
+    for g in pr.step(interactive=True):
+        got.append(sorted(g.idxs))
+        g.prune()
+    for mod in mv.modules():
+        if isinstance(mod, (Upsample2D, Downsample2D)):
+            mod.channels = mod.conv.in_channels
+    assert got == [sorted(g["idxs"]) for g in G["variants"]["taylor"]["groups"]]
+    assert tp.utils.count_ops_and_params(mv, ex) == (G["variants"]["taylor"]["pruned"][0], 19851157.0)
 
 
 def test_finetune_two_steps():
