@@ -560,7 +560,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant
   const int r = tap / p.S, sx = tap - r * p.S;
   const int chunk0 = blockIdx.y * p.chunks_per_split;
   const int chunk1 = min(p.total_chunks, chunk0 + p.chunks_per_split);
-  const int num_iters = chunk1 - chunk0;   // >= 1 by construction
+  const int num_iters = max(0, chunk1 - chunk0);   // 0 for a trailing empty split: its workspace tile is zero-filled
 
   if (warp == 0) {
     if (lane == 0) {
@@ -658,6 +658,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant
     const int kout = kt * 128 + row;
     const long long TC_ = (long long)T * p.C;
     float* wrow = p.ws + ((long long)blockIdx.y * p.K + kout) * TC_ + (long long)tap * p.C;
+    if (num_iters == 0) {                     // nothing was accumulated (TMEM holds garbage): this split contributes zeros
+      if (kout < p.K)
+        for (int c = ct * 128; c < min(p.C, ct * 128 + 128); ++c) wrow[c] = 0.f;
+    } else
 #pragma unroll 1
     for (int j = 0; j < 4; ++j) {
       uint32_t v[32], u[32];
@@ -770,7 +774,6 @@ int launch_tc(const float* act, long long ld_act, int Nimg, int H, int W, int Kg
   if (!tc_init()) return DP_ERR_UNSUPPORTED;
   if (!w_hi || !w_lo) return DP_ERR_UNSUPPORTED;
   if (ld_act % 4 || ((uintptr_t)act & 15) || ((uintptr_t)w_hi & 15) || ((uintptr_t)w_lo & 15)) return DP_ERR_UNSUPPORTED;
-  if (Kg % 4) return DP_ERR_UNSUPPORTED;                 // packed weight rows [Nout][Kg] must be 16-byte multiples for TMA
   int bw, bh, bn;
   if (!pick_box(Nimg, H, W, bw, bh, bn)) return DP_ERR_UNSUPPORTED;
   CUtensorMap mA, mBh, mBl;
@@ -782,8 +785,9 @@ int launch_tc(const float* act, long long ld_act, int Nimg, int H, int W, int Kg
   }
   const int BN = (Nout <= 64) ? 64 : 128;
   {
-    cuuint64_t dims[3] = {(cuuint64_t)Kg, (cuuint64_t)Nout, (cuuint64_t)T};
-    cuuint64_t str[2] = {(cuuint64_t)Kg * 4, (cuuint64_t)Nout * Kg * 4};
+    const cuuint64_t Kg4 = (cuuint64_t)((Kg + 3) & ~3);   // dp_pack_conv_weight_tc pads rows to 16 B
+    cuuint64_t dims[3] = {Kg4, (cuuint64_t)Nout, (cuuint64_t)T};
+    cuuint64_t str[2] = {Kg4 * 4, (cuuint64_t)Nout * Kg4 * 4};
     cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BN, 1};
     if (!make_map(&mBh, w_hi, 3, dims, str, box) || !make_map(&mBl, w_lo, 3, dims, str, box)) return DP_ERR_UNSUPPORTED;
   }
@@ -812,17 +816,23 @@ int launch_tc(const float* act, long long ld_act, int Nimg, int H, int W, int Kg
 
 __global__ void pack_tc_kernel(const float* __restrict__ w, int K, int C, int RS, float* __restrict__ kc_hi, float* __restrict__ kc_lo,
                                float* __restrict__ ck_hi, float* __restrict__ ck_lo) {
-  long long total = (long long)K * C * RS;
+  // rows are padded to a multiple of 4 floats (16 B, a TMA stride requirement) with zeros: kc [RS][K][C4], ck [RS][C][K4]
+  const int C4 = (C + 3) & ~3, K4 = (K + 3) & ~3;
+  const long long na = (long long)RS * K * C4, nb = (long long)RS * C * K4;
+  const long long total = na > nb ? na : nb;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int tap = (int)(i % RS);
-    long long kc = i / RS;
-    int c = (int)(kc % C), k = (int)(kc / C);
-    float v = w[i], h = tf32_rna(v), l = v - h;
-    long long a = ((long long)tap * K + k) * C + c, b = ((long long)tap * C + c) * K + k;
-    if (kc_hi) kc_hi[a] = h;
-    if (kc_lo) kc_lo[a] = l;
-    if (ck_hi) ck_hi[b] = h;
-    if (ck_lo) ck_lo[b] = l;
+    if (i < na && (kc_hi || kc_lo)) {
+      int c = (int)(i % C4); long long t = i / C4; int k = (int)(t % K), tap = (int)(t / K);
+      float v = c < C ? w[((long long)k * C + c) * RS + tap] : 0.f, h = tf32_rna(v);
+      if (kc_hi) kc_hi[i] = h;
+      if (kc_lo) kc_lo[i] = v - h;
+    }
+    if (i < nb && (ck_hi || ck_lo)) {
+      int k = (int)(i % K4); long long t = i / K4; int c = (int)(t % C), tap = (int)(t / C);
+      float v = k < K ? w[((long long)k * C + c) * RS + tap] : 0.f, h = tf32_rna(v);
+      if (ck_hi) ck_hi[i] = h;
+      if (ck_lo) ck_lo[i] = v - h;
+    }
   }
 }
 }  // namespace
@@ -928,7 +938,6 @@ int dp_conv2d_wgrad_tc(const dp_conv_args* a, dp_stream_t stream) {
   p.bw = bw; p.bh = bh; p.bn = bn; p.tiles_w = a->W / bw; p.tiles_h = a->H / bh;
   p.total_chunks = p.tiles_w * p.tiles_h * (a->N / bn);
   p.chunks_per_split = (p.total_chunks + a->splits - 1) / a->splits;
-  if ((long long)p.chunks_per_split * (a->splits - 1) >= p.total_chunks) return DP_ERR_UNSUPPORTED;   // an empty split
   p.c_tiles = (a->C + 127) / 128;
   p.ws = a->workspace;
   const int k_tiles = (a->K + 127) / 128;
@@ -941,7 +950,7 @@ extern "C" int dp_pack_conv_weight_tc(const float* w, int32_t K, int32_t C, int3
                                       float* ck_hi, float* ck_lo, dp_stream_t stream) {
   DP_REQUIRE(w, DP_ERR_NULL);
   DP_REQUIRE(K > 0 && C > 0 && R > 0 && S > 0, DP_ERR_SHAPE);
-  long long total = (long long)K * C * R * S;
+  long long total = (long long)R * S * ((long long)K * ((C + 3) & ~3) > (long long)C * ((K + 3) & ~3) ? (long long)K * ((C + 3) & ~3) : (long long)C * ((K + 3) & ~3));
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   pack_tc_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, K, C, R * S, kc_hi, kc_lo, ck_hi, ck_lo);

@@ -103,9 +103,11 @@ class Plan:
 
     # ------------------------------------------------------------------ memory helpers
     def new(self, N, H, W, C_) -> View:
-        t = torch.empty((N, H, W, C_), device=self.dev, dtype=torch.float32)
+        """Activation buffer; the pixel stride is rounded up to 4 floats so every view is TMA-addressable (16-byte pitch)
+        even for pruned widths such as 179 or 358."""
+        t = torch.empty((N, H, W, (C_ + 3) // 4 * 4), device=self.dev, dtype=torch.float32)
         self._keep.append(t)
-        return View(t)
+        return View(t, 0, C_)
 
     def gradof(self, v: View) -> View:
         """Gradient view mirroring v (same buffer geometry, so concat views stay views)."""
@@ -204,7 +206,9 @@ class Plan:
                   lib.dp_pack_conv_weight(w.data_ptr(), K, Cin, R, S, a.data_ptr(), b.data_ptr(), s), what="pack")
         tc = None
         if self.tc and K * Cin >= 256:
-            tc = tuple(torch.empty(w.numel(), device=self.dev, dtype=torch.float32) for _ in range(4))  # kc_hi kc_lo ck_hi ck_lo
+            RS = R * S
+            na, nb = RS * K * ((Cin + 3) // 4 * 4), RS * Cin * ((K + 3) // 4 * 4)
+            tc = tuple(torch.empty(n, device=self.dev, dtype=torch.float32) for n in (na, na, nb, nb))  # kc_hi kc_lo ck_hi ck_lo
             self._rec(self.pack, lambda s, w=w, K=K, Cin=Cin, R=R, S=S, t=tc:
                       lib.dp_pack_conv_weight_tc(w.data_ptr(), K, Cin, R, S, t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(),
                                                  t[3].data_ptr(), s), what="pack tc")
@@ -289,6 +293,8 @@ class Plan:
         TC = R * S * Cin
         tiles = ((K + 127) // 128) * ((TC + 127) // 128)
         splits = max(1, min((592 + tiles - 1) // tiles, (out.rows + 511) // 512))
+        chunks = max(1, out.rows // 32)              # tensor-core wgrad walks 32-pixel chunks: avoid empty trailing splits
+        splits = -(-chunks // -(-chunks // splits)) if splits <= chunks else splits
         self.scratch("wgrad_ws", splits * K * TC)
         wa = _copy_args(a)
         wa.flags, wa.splits = 0, splits
@@ -469,7 +475,7 @@ class Plan:
         self._rec(self.fwd, lambda s: lib.dp_timestep_embedding(self.t_dev.data_ptr(), self.freqs.data_ptr(), temb0.ptr, B, half,
                                                                 1 if cfg.flip_sin_to_cos else 0, s), what="temb")
         self.conv(temb0, te.linear_1.weight, te.linear_1.bias, l1, pad=0, need_dx=False)
-        n1, n2 = B * l1.C, B * emb.C
+        n1, n2 = B * l1.ld, B * emb.ld   # flat extents incl. pitch padding (pads are never read as channels)
         self._rec(self.fwd, lambda s: lib.dp_silu_fwd(l1.ptr, s1.ptr, n1, s), what="silu")
         if self.need_grad:
             self._rec(self._bitem().steps, lambda s: lib.dp_silu_bwd(l1.ptr, self.gradof(s1).ptr, self.gradof(l1).ptr, n1, 0, s),
@@ -512,7 +518,7 @@ class Plan:
             return View(skip.t, 0, skip.off)
 
         def cat_of(skip: View) -> View:
-            return View(skip.t, 0, skip.t.shape[-1])
+            return View(skip.t, 0, skip.off + skip.C)
 
         x = new_skip()
         self.conv(self.x_in, m.conv_in.weight, m.conv_in.bias, x, need_dx=False)

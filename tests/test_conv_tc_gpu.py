@@ -45,6 +45,9 @@ CASES = [
     (2, 256, 16, 16, 64, 1, 0, 0),      # 1x1 shortcut
     (4, 40, 8, 8, 200, 1, 0, 0),        # ragged channel counts (K-chunk and N-tile tails)
     (128, 512, 1, 1, 256, 1, 0, 0),     # time_emb_proj as a 1x1 conv over [B,1,1,512]
+    (2, 192, 16, 16, 179, 1, 0, 1),     # pruned attention to_q: 192 -> 179 (odd N, output view with a 180-float pitch)
+    (2, 179, 16, 16, 192, 1, 1, 0),     # pruned attention to_out: 179 -> 192 (odd GEMM-K: padded weight rows, 180-float pitch)
+    (64, 358, 1, 1, 96, 1, 2, 0),       # pruned time_emb_proj: 358 -> 96
 ]
 
 
@@ -62,12 +65,14 @@ def test_conv_tc_fprop_dgrad(lib, N, Cin, H, W, K, R, ldx, ldy):
     gy = torch.randn(N, K, H, W, generator=g)
     y_ref.backward(gy)
     wd = w.contiguous().cuda()
-    packs = [torch.empty(w.numel(), device="cuda") for _ in range(4)]
+    C4, K4 = (Cin + 3) // 4 * 4, (K + 3) // 4 * 4
+    packs = [torch.empty(n, device="cuda") for n in (R * R * K * C4, R * R * K * C4, R * R * Cin * K4, R * R * Cin * K4)]
     assert lib.dp_pack_conv_weight_tc(wd.data_ptr(), K, Cin, R, R, *[p.data_ptr() for p in packs], S()) == 0
     simt_ck, simt_kc = torch.empty(w.numel(), device="cuda"), torch.empty(w.numel(), device="cuda")
     assert lib.dp_pack_conv_weight(wd.data_ptr(), K, Cin, R, R, simt_ck.data_ptr(), simt_kc.data_ptr(), S()) == 0
-    # hi + lo reproduces w exactly, hi has 13 zero low bits
-    assert torch.equal(packs[0] + packs[1], simt_kc) and torch.equal(packs[2] + packs[3], simt_ck)
+    # hi + lo reproduces w exactly (rows zero-padded to 16 B), hi has 13 zero low bits
+    assert torch.equal((packs[0] + packs[1]).view(R * R, K, C4)[..., :Cin].reshape(-1), simt_kc)
+    assert torch.equal((packs[2] + packs[3]).view(R * R, Cin, K4)[..., :K].reshape(-1), simt_ck)
     assert int((packs[0].view(torch.int32) & 0x1FFF).abs().max()) == 0
     xb = torch.randn(N, H, W, Cin + ldx, generator=g).cuda()
     xb[..., ldx:] = nhwc(x)
@@ -114,7 +119,7 @@ def test_conv_tc_fprop_dgrad(lib, N, Cin, H, W, K, R, ldx, ldy):
     assert rel_err(nchw(gxb[..., ldx:]), 2 * xr.grad) < 1.5e-5
     # wgrad (MN-major operands, both split in-kernel), deterministic split-K + reduce into dW (+=)
     pix_chunks = N * H * W // 32
-    for splits in sorted({1, min(3, pix_chunks)}):
+    for splits in sorted({1, min(3, pix_chunks), min(7, pix_chunks)}):   # 7 leaves a trailing EMPTY split for 16 chunks
         ws = torch.full((splits * K * R * R * Cin,), float("nan"), device="cuda")
         wg = L.ConvArgs()
         C.memmove(C.byref(wg), C.byref(a), C.sizeof(a))
@@ -156,7 +161,7 @@ def test_stride2_dgrad_parity_classes(lib, N, Cin, H, K):
     y.backward(gy)
     P = H // 2
     wd = w.contiguous().cuda()
-    packs = [torch.empty(w.numel(), device="cuda") for _ in range(4)]
+    packs = [torch.empty(w.numel(), device="cuda") for _ in range(4)]    # Cin, K multiples of 4 here: no row padding
     assert lib.dp_pack_conv_weight_tc(wd.data_ptr(), K, Cin, 3, 3, *[p.data_ptr() for p in packs], S()) == 0
     ck, kc = torch.empty(w.numel(), device="cuda"), torch.empty(w.numel(), device="cuda")
     assert lib.dp_pack_conv_weight(wd.data_ptr(), K, Cin, 3, 3, ck.data_ptr(), kc.data_ptr(), S()) == 0
