@@ -289,6 +289,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 // the B operand reads (112 KB per 768-cycle stage instead of 192 KB), which is what bounds the SS kernel above.
 // TMEM map (512 columns): [0,BN) main accumulator | [BN,2BN) correction accumulator | 2BN + 64*s: A_hi(32) A_lo(32) of stage s.
 constexpr int STAGES_TS = 4;
+constexpr int PF_DIST = 8;   // L2 prefetch distance (stages) for the activation boxes
 
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
@@ -309,13 +310,34 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
       : "memory");
 }
 
-template <int BN>
+__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// CL = thread-block-cluster size along the M tiles (1, 2 or 4).  The CL CTAs of a cluster work on different pixel tiles but the
+// SAME weight tile: each CTA fetches 1/CL of B_hi / B_lo and TMA-multicasts it into all of them, so the L2->SM traffic per MMA
+// stage drops from 48 KB to 16 + 32/CL KB — the L2->SM path (~42 B/clk/SM), not the tensor pipe, is what bounds this kernel.
+template <int BN, int CL>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_ts_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBh,
                   const __grid_constant__ CUtensorMap mapBl, const TcParams p) {
   constexpr int B_BYTES = BN * BK * 4;
   constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;
   constexpr uint32_t A_COL0 = 2 * BN;
+  constexpr int SLICE_ROWS = BN / CL, SLICE_BYTES = B_BYTES / CL;
+  constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1);
+  uint32_t cta_rank = 0;
+  if (CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t pad_to = ((raw + 1023u) & ~1023u) - raw;
@@ -331,7 +353,7 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES_TS; ++s) { mbar_init(full_bar(s), 1); mbar_init(conv_bar(s), 128); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < STAGES_TS; ++s) { mbar_init(full_bar(s), 1); mbar_init(conv_bar(s), 128); mbar_init(empty_bar(s), CL); }
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -341,6 +363,7 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast / remote commit can reach them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
@@ -364,14 +387,28 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
         const uint32_t st = sbase + s * STAGE_BYTES;
         tma_load_4d(st, &mapA, full_bar(s), kc * BK, q0 + p.dw[tap], p0 + p.dh[tap], n0);
+        if (it + PF_DIST < num_iters) {   // pull the A box of a later stage into L2 while this one is in flight
+          const int it2 = it + PF_DIST, tap2 = it2 / p.kchunks, kc2 = it2 - tap2 * p.kchunks;
+          asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+                       ::"l"(reinterpret_cast<uint64_t>(&mapA)), "r"(kc2 * BK), "r"(q0 + p.dw[tap2]), "r"(p0 + p.dh[tap2]), "r"(n0) : "memory");
+        }
         const int tapb = p.wt[tap];
-        tma_load_3d(st + A_BYTES, &mapBh, full_bar(s), kc * BK, nblk * BN, tapb);
-        tma_load_3d(st + A_BYTES + B_BYTES, &mapBl, full_bar(s), kc * BK, nblk * BN, tapb);
+        if (CL == 1) {
+          tma_load_3d(st + A_BYTES, &mapBh, full_bar(s), kc * BK, nblk * BN, tapb);
+          tma_load_3d(st + A_BYTES + B_BYTES, &mapBl, full_bar(s), kc * BK, nblk * BN, tapb);
+        } else {   // my 1/CL row-slice of both weight tiles, multicast to every CTA of the cluster (same smem offsets)
+          const int row0 = nblk * BN + (int)cta_rank * SLICE_ROWS;
+          tma_load_3d_mc(st + A_BYTES + cta_rank * SLICE_BYTES, &mapBh, full_bar(s), kc * BK, row0, tapb, MC_MASK);
+          tma_load_3d_mc(st + A_BYTES + B_BYTES + cta_rank * SLICE_BYTES, &mapBl, full_bar(s), kc * BK, row0, tapb, MC_MASK);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      // UMMA N = valid channels of this N tile rounded up to 16 (pruned widths 96 / 192 / 179 do not pay for 128)
+      const int n_valid = min(BN, p.Nout - nblk * BN);
+      const uint32_t n_instr = (uint32_t)((n_valid + 15) & ~15);
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((n_instr >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       for (int it = 0; it < num_iters; ++it) {
         const int s = it % STAGES_TS;
         const uint32_t ph = (uint32_t)(it / STAGES_TS) & 1u;
@@ -388,7 +425,7 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           umma_tf32_ts(tmem_base + BN, a_t + k * 8, b_lo, idesc, 1u);           // hi * lo
           umma_tf32_ts(tmem_base, a_t + k * 8, b_hi, idesc, first);             // hi * hi
         }
-        umma_commit(empty_bar(s));
+        if (CL == 1) umma_commit(empty_bar(s)); else umma_commit_mc(empty_bar(s), MC_MASK);   // release the stage in EVERY CTA that multicasts into it
       }
       umma_commit(tmem_full_bar);
     }
@@ -485,6 +522,7 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // nobody leaves while a peer may still signal its barriers
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
@@ -707,7 +745,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
 int g_tc_state = -1;  // -1 unknown, 0 unavailable, 1 ok
-bool g_use_ss = false; // DPB200_TC_SS=1: keep the A operand in shared memory (SS-mode kernel) instead of TMEM (TS-mode)
+bool g_use_ss = false;
+int g_cluster = 1;     // DPB200_TC_CLUSTER=2|4: CTAs per cluster sharing (TMA-multicasting) one weight tile.  Measured on B200
+                       // (profiles/r01_experiments.md): 46.7 / 47.5 / 48.3 ms per pass for 1 / 2 / 4 -> off by default. // DPB200_TC_SS=1: keep the A operand in shared memory (SS-mode kernel) instead of TMEM (TS-mode)
 std::mutex g_tc_mutex;
 
 int tc_init() {
@@ -727,10 +767,12 @@ int tc_init() {
                                  STAGES * (2 * A_BYTES + 2 * 128 * BK * 4) + 2048) == cudaSuccess;
   ok = ok && cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   STAGES * (2 * A_BYTES + 2 * 64 * BK * 4) + 2048) == cudaSuccess;
-  ok = ok && cudaFuncSetAttribute(conv_tc_ts_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  STAGES_TS * (A_BYTES + 2 * 128 * BK * 4) + 2048) == cudaSuccess;
-  ok = ok && cudaFuncSetAttribute(conv_tc_ts_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  STAGES_TS * (A_BYTES + 2 * 64 * BK * 4) + 2048) == cudaSuccess;
+  const int smem128 = STAGES_TS * (A_BYTES + 2 * 128 * BK * 4) + 2048, smem64 = STAGES_TS * (A_BYTES + 2 * 64 * BK * 4) + 2048;
+  ok = ok && cudaFuncSetAttribute(conv_tc_ts_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem128) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(conv_tc_ts_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem128) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(conv_tc_ts_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem128) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(conv_tc_ts_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem64) == cudaSuccess;
+  if (const char* e = getenv("DPB200_TC_CLUSTER")) g_cluster = atoi(e);
   g_use_ss = getenv("DPB200_TC_SS") != nullptr;
   ok = ok && cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 3 * WG_T + 2048) == cudaSuccess;
   if (!ok) { (void)cudaGetLastError(); return 0; }
@@ -807,9 +849,32 @@ int launch_tc(const float* act, long long ld_act, int Nimg, int H, int W, int Kg
   if (g_use_ss) {
     if (BN == 64) conv_tc_kernel<64><<<grid, NTHREADS, STAGES * (2 * A_BYTES + 2 * 64 * BK * 4) + 2048, st>>>(mA, mBh, mBl, p);
     else conv_tc_kernel<128><<<grid, NTHREADS, STAGES * (2 * A_BYTES + 2 * 128 * BK * 4) + 2048, st>>>(mA, mBh, mBl, p);
+  } else if (BN == 64) {
+    conv_tc_ts_kernel<64, 1><<<grid, NTHREADS, STAGES_TS * (A_BYTES + 2 * 64 * BK * 4) + 2048, st>>>(mA, mBh, mBl, p);
   } else {
-    if (BN == 64) conv_tc_ts_kernel<64><<<grid, NTHREADS, STAGES_TS * (A_BYTES + 2 * 64 * BK * 4) + 2048, st>>>(mA, mBh, mBl, p);
-    else conv_tc_ts_kernel<128><<<grid, NTHREADS, STAGES_TS * (A_BYTES + 2 * 128 * BK * 4) + 2048, st>>>(mA, mBh, mBl, p);
+    int cl = g_cluster;
+    while (cl > 1 && (grid.x % cl)) cl >>= 1;
+    const size_t smem = STAGES_TS * (A_BYTES + 2 * 128 * BK * 4) + 2048;
+    if (cl <= 1) {
+      conv_tc_ts_kernel<128, 1><<<grid, NTHREADS, smem, st>>>(mA, mBh, mBl, p);
+    } else {
+      // weight-tile slices of 128/cl rows per CTA need their own (smaller-box) tensor maps
+      CUtensorMap sBh, sBl;
+      const cuuint64_t Kg4 = (cuuint64_t)((Kg + 3) & ~3);
+      cuuint64_t dims[3] = {Kg4, (cuuint64_t)Nout, (cuuint64_t)T};
+      cuuint64_t str[2] = {Kg4 * 4, (cuuint64_t)Nout * Kg4 * 4};
+      cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)(128 / cl), 1};
+      if (!make_map(&sBh, w_hi, 3, dims, str, box) || !make_map(&sBl, w_lo, 3, dims, str, box)) return DP_ERR_UNSUPPORTED;
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = grid; cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = (unsigned)cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      cudaError_t e = (cl == 2) ? cudaLaunchKernelEx(&cfg, conv_tc_ts_kernel<128, 2>, mA, sBh, sBl, p)
+                                : cudaLaunchKernelEx(&cfg, conv_tc_ts_kernel<128, 4>, mA, sBh, sBl, p);
+      if (e != cudaSuccess) { g_dp_last_cuda_error = (int)e; (void)cudaGetLastError(); return DP_ERR_CUDA; }
+    }
   }
   return dp_check_launch();
 }
