@@ -349,12 +349,20 @@ def run_ours(args, rank, world, local_rank):
     flops = plan_B * CONV_FLOP_PER_IMAGE_PASS
     achieved = flops / conv_s / 1e12
     tc = bool(lib.dp_tc_available())
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
+    if os.path.exists(tp) and B == 128:   # dram__bytes_read+write summed over the conv launches of one pass (committed ncu capture)
+        tj = json.load(open(tp))
+        traffic = tj["dram_read_bytes"] + tj["dram_write_bytes"]
     roofline = {"bound": "tensor", "achieved": achieved, "peak": tf_sus, "unit": "TFLOP/s", "frac": achieved / tf_sus,
-                "traffic": None,
+                "traffic": traffic,
                 "kernel": "conv implicit GEMM (fprop+dgrad+wgrad launches of one pass: %d)" % n_conv,
                 "note": (f"algorithmic conv FLOPs/pass = {B} x 34.27 GFLOP (SURVEY.md §8d) / summed conv-launch device time "
                          f"{conv_s * 1e3:.2f} ms of a {ms / args.steps:.2f} ms step; peak = bf16_tflops_sustained ({which}); "
-                         "fp32-exact tier: " + ("tcgen05 3xTF32" if tc else "CUDA-core FFMA (SIMT) — tensor path not active"))}
+                         "fp32-exact tier: " + ("tcgen05 3xTF32 (3 tensor instructions per product: attainable ceiling = 1/6 of this bf16 peak)" if tc
+                                                 else "CUDA-core FFMA (SIMT) — tensor path not active") +
+                         "; traffic = DRAM bytes of all conv launches of one pass (profiles/r01_conv_traffic.json), algorithmic conv "
+                         "I/O of the pass is ~8.6 GB")}
     value = world * args.steps / (ms * 1e-3)
     e2e = world * args.steps / (ms_e2e * 1e-3)
     cpu = cpu_oracle_passes(B, 16, min_seconds=12.0, max_passes=8) if args.gpus == 1 and not args.no_cpu else None

@@ -529,6 +529,225 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ persistent variant
+// One CTA per SM loops over output tiles (static stride), 10 warps: TMA producer | MMA issuer | 4 splitter warps |
+// 4 epilogue warps.  Two accumulator sets in TMEM (2 x [main 128 | correction 128] = 512 columns) let the epilogue of tile
+// i (TMEM -> registers -> global, ~20-50 % of a short-K tile) overlap the main loop of tile i+1; barrier init, TMEM
+// allocation and descriptor prefetch are paid once per SM instead of once per tile.  A operand hi/lo in shared memory
+// (SS mode; the TS variant needs the TMEM columns the second accumulator set occupies).
+constexpr int PS_THREADS = 320, PS_STAGES = 3;
+
+__global__ void __launch_bounds__(PS_THREADS, 1)
+conv_tc_ps_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBh,
+                  const __grid_constant__ CUtensorMap mapBl, const TcParams p, const int tiles_m, const int total_tiles) {
+  constexpr int BN = 128;
+  constexpr int B_BYTES = BN * BK * 4;
+  constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t pad_to = ((raw + 1023u) & ~1023u) - raw;
+  uint8_t* smem = smem_raw + pad_to;
+  const uint32_t sbase = raw + pad_to;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PS_STAGES * STAGE_BYTES);
+  const uint32_t bar0 = sbase + PS_STAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto conv_bar = [&](int s) { return bar0 + 8u * (PS_STAGES + s); };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (2 * PS_STAGES + s); };
+  auto tfull_bar = [&](int b) { return bar0 + 8u * (3 * PS_STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar0 + 8u * (3 * PS_STAGES + 2 + b); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * PS_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < PS_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(conv_bar(s), 128); mbar_init(empty_bar(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  const int iters_per_tile = p.ntaps * p.kchunks;
+
+  auto tile_coords = [&](int tile, int& q0, int& p0, int& n0, int& nblk) {
+    nblk = tile / tiles_m;
+    const int tile_m = tile - nblk * tiles_m;
+    const int tw = tile_m % p.tiles_w;
+    const int th = (tile_m / p.tiles_w) % p.tiles_h;
+    const int tn = tile_m / (p.tiles_w * p.tiles_h);
+    q0 = tw * p.bw; p0 = th * p.bh; n0 = tn * p.bn;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapBh)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapBl)) : "memory");
+      uint32_t g = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int q0, p0, n0, nblk;
+        tile_coords(tile, q0, p0, n0, nblk);
+        for (int it = 0; it < iters_per_tile; ++it, ++g) {
+          const int s = g % PS_STAGES;
+          const uint32_t ph = (g / PS_STAGES) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          mbar_expect_tx(full_bar(s), A_BYTES + 2 * B_BYTES);
+          const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
+          const uint32_t st = sbase + s * STAGE_BYTES;
+          tma_load_4d(st, &mapA, full_bar(s), kc * BK, q0 + p.dw[tap], p0 + p.dh[tap], n0);
+          const int tapb = p.wt[tap];
+          tma_load_3d(st + 2 * A_BYTES, &mapBh, full_bar(s), kc * BK, nblk * BN, tapb);
+          tma_load_3d(st + 2 * A_BYTES + B_BYTES, &mapBl, full_bar(s), kc * BK, nblk * BN, tapb);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t g = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+        const int nblk = tile / tiles_m;
+        const int n_valid = min(BN, p.Nout - nblk * BN);
+        const uint32_t n_instr = (uint32_t)((n_valid + 15) & ~15);
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((n_instr >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        const uint32_t b = tl & 1u, use = tl >> 1;
+        mbar_wait(tempty_bar(b), (use & 1u) ^ 1u);          // epilogue has drained this accumulator set
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t acc = tmem_base + b * 256u;
+        for (int it = 0; it < iters_per_tile; ++it, ++g) {
+          const int s = g % PS_STAGES;
+          const uint32_t ph = (g / PS_STAGES) & 1u;
+          mbar_wait(conv_bar(s), ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t st = sbase + s * STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            const uint64_t a_hi = umma_desc(st + k * 32), a_lo = umma_desc(st + A_BYTES + k * 32);
+            const uint64_t b_hi = umma_desc(st + 2 * A_BYTES + k * 32), b_lo = umma_desc(st + 2 * A_BYTES + B_BYTES + k * 32);
+            const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
+            umma_tf32(acc + 128, a_lo, b_hi, idesc, first);
+            umma_tf32(acc + 128, a_hi, b_lo, idesc, 1u);
+            umma_tf32(acc, a_hi, b_hi, idesc, first);
+          }
+          umma_commit(empty_bar(s));
+        }
+        umma_commit(tfull_bar(b));
+      }
+    }
+  } else if (warp < 6) {
+    // ---- splitter warps 2..5
+    const int ct = threadIdx.x - 64;
+    uint32_t g = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int it = 0; it < iters_per_tile; ++it, ++g) {
+        const int s = g % PS_STAGES;
+        const uint32_t ph = (g / PS_STAGES) & 1u;
+        mbar_wait(full_bar(s), ph);
+        float4* A = reinterpret_cast<float4*>(smem + s * STAGE_BYTES);
+        float4* Al = reinterpret_cast<float4*>(smem + s * STAGE_BYTES + A_BYTES);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int idx = ct + 128 * i;
+          float4 v = A[idx], h, l;
+          h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+          l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+          A[idx] = h;
+          Al[idx] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(conv_bar(s));
+      }
+    }
+  } else {
+    // ---- epilogue warps 6..9 (TMEM lane quarter = warp & 3)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const int w_l = row % p.bw, h_l = (row / p.bw) % p.bh, n_l = row / (p.bw * p.bh);
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+      int q0, p0, n0, nblk;
+      tile_coords(tile, q0, p0, n0, nblk);
+      const uint32_t b = tl & 1u, use = tl >> 1;
+      mbar_wait(tfull_bar(b), use & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int img = n0 + n_l;
+      const bool row_ok = img < p.Nimg;
+      const long long m = ((long long)img * p.Ho + ((p0 + h_l) * p.os + p.oa)) * p.Wo + ((q0 + w_l) * p.os + p.ob);
+      float* yrow = p.y + m * p.ldy;
+      const float* rrow = p.residual ? p.residual + m * p.ld_res : nullptr;
+      const float* arow2 = p.rowadd ? p.rowadd + (long long)img * p.ld_rowadd : nullptr;
+#pragma unroll 1
+      for (int j = 0; j < BN / 32; ++j) {
+        uint32_t v[32], u[32];
+        const uint32_t taddr = tmem_base + lane_addr + b * 256u + (uint32_t)(j * 32);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr));
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+              "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
+              "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
+              "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+            : "r"(taddr + 128u));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (j == BN / 32 - 1) {   // accumulators are in registers: hand the TMEM set back to the MMA warp
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          mbar_arrive(tempty_bar(b));
+        }
+        if (row_ok) {
+          const int c0 = nblk * BN + j * 32;
+          if (p.vec4 && c0 + 32 <= p.Nout) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              float4 o = make_float4(__uint_as_float(v[i]) + __uint_as_float(u[i]), __uint_as_float(v[i + 1]) + __uint_as_float(u[i + 1]),
+                                     __uint_as_float(v[i + 2]) + __uint_as_float(u[i + 2]), __uint_as_float(v[i + 3]) + __uint_as_float(u[i + 3]));
+              if (p.bias) { float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + i)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+              if (arow2) { float4 t = __ldg(reinterpret_cast<const float4*>(arow2 + c0 + i)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+              if (rrow) { float4 t = __ldg(reinterpret_cast<const float4*>(rrow + c0 + i)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+              float4* dst = reinterpret_cast<float4*>(yrow + c0 + i);
+              if (p.accumulate) { float4 t = *dst; o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+              *dst = o;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int c = c0 + i;
+              if (c < p.Nout) {
+                float o = __uint_as_float(v[i]) + __uint_as_float(u[i]);
+                if (p.bias) o += __ldg(p.bias + c);
+                if (arow2) o += __ldg(arow2 + c);
+                if (rrow) o += __ldg(rrow + c);
+                if (p.accumulate) o += yrow[c];
+                yrow[c] = o;
+              }
+            }
+          }
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ wgrad
 // dW[k][tap][c] = sum_pix dy[pix][k] * x[pix @ tap][c]  as GEMM  M = k (128), N = c (128), K = pixels.
 // Both operands are activations stored pixel-major / channel-contiguous, i.e. "MN-major" for the tensor core:
@@ -746,6 +965,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn g_encode = nullptr;
 int g_tc_state = -1;  // -1 unknown, 0 unavailable, 1 ok
 bool g_use_ss = false;
+int g_persistent = 1;  // DPB200_TC_PERSISTENT=0: one tile per CTA (TS kernel) instead of the persistent kernel
+int g_num_sms = 148;
 int g_cluster = 1;     // DPB200_TC_CLUSTER=2|4: CTAs per cluster sharing (TMA-multicasting) one weight tile.  Measured on B200
                        // (profiles/r01_experiments.md): 46.7 / 47.5 / 48.3 ms per pass for 1 / 2 / 4 -> off by default. // DPB200_TC_SS=1: keep the A operand in shared memory (SS-mode kernel) instead of TMEM (TS-mode)
 std::mutex g_tc_mutex;
@@ -773,6 +994,9 @@ int tc_init() {
   ok = ok && cudaFuncSetAttribute(conv_tc_ts_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem128) == cudaSuccess;
   ok = ok && cudaFuncSetAttribute(conv_tc_ts_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem64) == cudaSuccess;
   if (const char* e = getenv("DPB200_TC_CLUSTER")) g_cluster = atoi(e);
+  ok = ok && cudaFuncSetAttribute(conv_tc_ps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PS_STAGES * (2 * A_BYTES + 2 * 128 * BK * 4) + 2048) == cudaSuccess;
+  if (const char* e = getenv("DPB200_TC_PERSISTENT")) g_persistent = atoi(e);
+  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev); }
   g_use_ss = getenv("DPB200_TC_SS") != nullptr;
   ok = ok && cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 3 * WG_T + 2048) == cudaSuccess;
   if (!ok) { (void)cudaGetLastError(); return 0; }
@@ -849,6 +1073,10 @@ int launch_tc(const float* act, long long ld_act, int Nimg, int H, int W, int Kg
   if (g_use_ss) {
     if (BN == 64) conv_tc_kernel<64><<<grid, NTHREADS, STAGES * (2 * A_BYTES + 2 * 64 * BK * 4) + 2048, st>>>(mA, mBh, mBl, p);
     else conv_tc_kernel<128><<<grid, NTHREADS, STAGES * (2 * A_BYTES + 2 * 128 * BK * 4) + 2048, st>>>(mA, mBh, mBl, p);
+  } else if (BN == 128 && g_persistent) {
+    const int tiles_m = (int)grid.x, total = (int)(grid.x * grid.y);
+    const int ctas = total < g_num_sms ? total : g_num_sms;
+    conv_tc_ps_kernel<<<ctas, PS_THREADS, PS_STAGES * (2 * A_BYTES + 2 * 128 * BK * 4) + 2048, st>>>(mA, mBh, mBl, p, tiles_m, total);
   } else if (BN == 64) {
     conv_tc_ts_kernel<64, 1><<<grid, NTHREADS, STAGES_TS * (A_BYTES + 2 * 64 * BK * 4) + 2048, st>>>(mA, mBh, mBl, p);
   } else {
