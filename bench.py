@@ -362,7 +362,7 @@ def run_ours(args, rank, world, local_rank):
                          "fp32-exact tier: " + ("tcgen05 3xTF32 (3 tensor instructions per product: attainable ceiling = 1/6 of this bf16 peak)" if tc
                                                  else "CUDA-core FFMA (SIMT) — tensor path not active") +
                          "; traffic = DRAM bytes of all conv launches of one pass (profiles/r01_conv_traffic.json), algorithmic conv "
-                         "I/O of the pass is ~8.6 GB")}
+                         "I/O of the pass is ~13 GB (3 x 128 x 8.49 M fp32 conv in+out elements, SURVEY.md §8d)")}
     value = world * args.steps / (ms * 1e-3)
     e2e = world * args.steps / (ms_e2e * 1e-3)
     cpu = cpu_oracle_passes(B, 16, min_seconds=12.0, max_passes=8) if args.gpus == 1 and not args.no_cpu else None
