@@ -78,7 +78,7 @@ class Plan:
     """Static forward/backward launch lists for one (model, batch, H, W)."""
 
     def __init__(self, model: UNet2DModel, batch: int, height: int, width: int, device, training: bool = False,
-                 need_grad: bool = True):
+                 need_grad: bool = True, fused_scores: bool = False):
         self.lib = L.load()
         self.tc = bool(self.lib.dp_tc_available()) if torch.device(device).type == "cuda" else False
         self.model = model
@@ -99,6 +99,12 @@ class Plan:
         self.params = [p for p in model.parameters()]
         self.dropout_seed_dev = torch.zeros(1, device=self.dev, dtype=torch.int64)
         self._n_dropout = 0
+        self.fused_scores = fused_scores and need_grad
+        self.scores: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
+        if self.fused_scores:   # one flat vector: [out-channel | in-channel] signed scores of every conv / linear weight
+            n = sum(p.shape[0] + p.shape[1] for p in self.params if p.dim() >= 2)
+            self.score_arena = torch.zeros(n, device=self.dev, dtype=torch.float32)
+            self._score_off = 0
         self._build()
 
     # ------------------------------------------------------------------ memory helpers
@@ -165,6 +171,15 @@ class Plan:
 
     def weight_version(self):
         return sum(p._version for p in self.params)
+
+    def _score_views(self, w: nn.Parameter, K: int, Cin: int):
+        got = self.scores.get(id(w))
+        if got is None:
+            o = self._score_off
+            got = (self.score_arena[o:o + K], self.score_arena[o + K:o + K + Cin])
+            self._score_off = o + K + Cin
+            self.scores[id(w)] = got
+        return got
 
     # ------------------------------------------------------------------ launch recording
     def _rec(self, lst: List[Step], fn, args=None, what=""):
@@ -305,6 +320,9 @@ class Plan:
         ra = L.WgradReduceArgs()
         ra.K, ra.C, ra.R, ra.S, ra.splits = K, Cin, R, S, splits
         ra.dw = self.pgrad(w)
+        if self.fused_scores:   # signed first-order Taylor terms sum_k W*dW_t fall out of the split-K reduce (ddpm_prune.py:60)
+            so, si = self._score_views(w, K, Cin)
+            ra.w, ra.score_out, ra.score_in = w.data_ptr(), so.data_ptr(), si.data_ptr()
         self._late.append(lambda ra=ra: setattr(ra, "workspace", self.sptr("wgrad_ws")))
         self._rec(steps, lib.dp_conv2d_wgrad_reduce, ra, "conv wgrad reduce")
         # 3. dgrad
@@ -687,16 +705,16 @@ class _UNetFunction(torch.autograd.Function):
         return (None, None, None) + (None,) * len(plan.params)
 
 
-def get_plan(model: UNet2DModel, batch: int, H: int, W: int, device, need_grad: bool) -> Plan:
+def get_plan(model: UNet2DModel, batch: int, H: int, W: int, device, need_grad: bool, fused_scores: bool = False) -> Plan:
     cache = model.__dict__.setdefault("_dpb200_plans", {})
     training = bool(model.training)
-    key = (batch, H, W, str(device), need_grad, training)
+    key = (batch, H, W, str(device), need_grad, training, fused_scores)
     plan = cache.get(key)
     sig = tuple((p.data_ptr(), tuple(p.shape)) for p in model.parameters())
     if plan is None or plan.signature() != sig:
         if plan is not None or any(pl.signature() != sig for pl in cache.values()):
             cache.clear()  # weights were replaced (e.g. pruned): every cached plan is stale
-        plan = Plan(model, batch, H, W, device, training=training, need_grad=need_grad)
+        plan = Plan(model, batch, H, W, device, training=training, need_grad=need_grad, fused_scores=fused_scores)
         cache[key] = plan
     return plan
 

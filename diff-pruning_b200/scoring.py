@@ -33,7 +33,8 @@ class TaylorScorer:
     """Accumulates sum_t dL_t/dW into Parameter.grad for fixed (clean_images, noise) — ddpm_prune.py:90-102."""
 
     def __init__(self, model: UNet2DModel, clean_images: torch.Tensor, noise: torch.Tensor,
-                 num_train_timesteps: int = 1000, alphas_cumprod: Optional[torch.Tensor] = None, use_graph: bool = True):
+                 num_train_timesteps: int = 1000, alphas_cumprod: Optional[torch.Tensor] = None, use_graph: bool = True,
+                 fused_scores: bool = False):
         assert clean_images.is_cuda and clean_images.shape == noise.shape and clean_images.dtype == torch.float32
         self.lib = L.load()
         self.model = model
@@ -45,7 +46,10 @@ class TaylorScorer:
         self.acp = (alphas_cumprod if alphas_cumprod is not None else ddpm_alphas_cumprod(num_train_timesteps)).to(self.dev).contiguous()
         was_training = model.training
         model.eval()  # ddpm_prune.py:91
-        self.plan: Plan = get_plan(model, B, H, W, self.dev, need_grad=True)
+        # fused_scores: the split-K wgrad reduce also accumulates sum_t sum_k W*dW_t per out/in channel of every conv/linear
+        # (plan.score_arena, ~78 k floats for C1): the `multivariable=True` importance is |that| — no extra pass over dW,
+        # and the multi-GPU exchange can be this small vector instead of the 143 MB gradient arena.
+        self.plan: Plan = get_plan(model, B, H, W, self.dev, need_grad=True, fused_scores=fused_scores)
         if was_training:
             model.train()
         ldo = self.plan.y_out.ld                      # y_out is a C-channel view of a zero-padded ld-channel buffer
@@ -81,14 +85,22 @@ class TaylorScorer:
         side.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(side):   # warm-up outside capture (first-launch lazy module loading)
             saved = self.plan.grad_arena.clone()
+            saved_sc = self.plan.score_arena.clone() if self.plan.fused_scores else None
             self._body()
             self.plan.grad_arena.copy_(saved)
+            if saved_sc is not None:
+                self.plan.score_arena.copy_(saved_sc)
         torch.cuda.current_stream(self.dev).wait_stream(side)
         torch.cuda.synchronize(self.dev)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self._body()
         self.graph = g
+
+    def signed_scores(self) -> Dict[str, Tuple[torch.Tensor, torch.Tensor]]:
+        """{weight name: (out-channel, in-channel) sum_t sum_k W*dW_t} accumulated by the fused reduce (fused_scores=True)."""
+        names = {id(p): n for n, p in self.model.named_parameters()}
+        return {names[k]: v for k, v in self.plan.scores.items()}
 
     def step(self, t) -> torch.Tensor:
         """One pass at timestep(s) t (int, or a (B,) tensor).  Returns the device loss scalar (no sync)."""
@@ -133,6 +145,8 @@ class TaylorScorer:
             import torch.distributed as dist
             dist.all_reduce(self.plan.grad_arena, op=dist.ReduceOp.SUM)
             dist.all_reduce(losses, op=dist.ReduceOp.SUM)
+            if self.plan.fused_scores:
+                dist.all_reduce(self.plan.score_arena, op=dist.ReduceOp.SUM)
         return losses
 
 

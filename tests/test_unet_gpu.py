@@ -184,3 +184,46 @@ def test_lsun_family_block_one_pass_vs_oracle():
     assert sc.step(t).item() == pytest.approx(ref.item(), rel=5e-6)
     worst = worst_grad_err(((k, p.grad) for k, p in m.named_parameters()), {k: v.grad for k, v in sd.items()})
     assert worst < 1e-4, worst
+
+
+def test_fused_signed_scores_fall_out_of_backward():
+    """North-star item: the wgrad reduce accumulates sum_t sum_k W*dW_t per channel while it adds dW_t into .grad; the
+    `multivariable=True` Taylor score |.| computed from that equals the one computed from the accumulated gradient
+    (scores are linear in dW: sum_t and sum_k commute)."""
+    from diff_pruning_b200.scoring import taylor_layer_scores
+    m = build(dp.TINY_TEST_CONFIG)
+    clean, noise = inputs(2, 16)
+    sc = TaylorScorer(m, clean.cuda(), noise.cuda(), use_graph=True, fused_scores=True)
+    for t in (3, 250, 600, 990):
+        sc.step(t)
+    fused = sc.signed_scores()
+    params = dict(m.named_parameters())
+    assert len(fused) == sum(1 for p in params.values() if p.dim() >= 2)
+    worst = 0.0
+    for name, (so, si) in fused.items():
+        ref = taylor_layer_scores(params[name], params[name].grad)
+        scale = float(ref["out_abs"].max())          # sum |w dw|: the magnitude of the summands (signed sums can cancel)
+        worst = max(worst, float((so - ref["out_signed"]).abs().max()) / scale, float((si - ref["in_signed"]).abs().max()) / scale)
+    assert worst < 2e-5, worst
+
+
+def test_lsun256_architecture_one_pass_vs_oracle():
+    """BASELINE config 3 architecture (google/ddpm-ema-bedroom-256: 113.7 M params, 3x256x256), batch 1, one Taylor pass on
+    the GPU vs the CPU oracle: loss and every parameter gradient."""
+    from oracle import unet_oracle as orc
+    cfg = dp.LSUN256_DDPM_CONFIG
+    torch.manual_seed(0)
+    m = dp.UNet2DModel(**cfg).eval()
+    assert round(sum(p.numel() for p in m.parameters()) / 1e6, 3) == 113.673
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(4)
+    clean, noise = torch.randn(1, 3, 256, 256, generator=g), torch.randn(1, 3, 256, 256, generator=g)
+    t = torch.tensor([321])
+    torch.set_num_threads(min(32, torch.get_num_threads()))
+    ref = orc.taylor_pass(sd, cfg, orc.alphas_cumprod(), clean, noise, t)
+    m = m.cuda()
+    m.zero_grad()
+    sc = TaylorScorer(m, clean.cuda(), noise.cuda(), use_graph=False)
+    assert sc.step(t).item() == pytest.approx(ref.item(), rel=1e-5)
+    worst = worst_grad_err(((k, p.grad) for k, p in m.named_parameters()), {k: v.grad for k, v in sd.items()})
+    assert worst < 2e-4, worst
