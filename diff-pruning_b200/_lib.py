@@ -30,6 +30,11 @@ class GemmArgs(C.Structure):
                 ("C", vp), ("ldc", i64), ("c_bs", i64), ("alpha", f32), ("accumulate", i32)]
 
 
+class GemmNtArgs(C.Structure):
+    _fields_ = [("batch", i32), ("H", i32), ("W", i32), ("Kg", i32), ("N", i32), ("A", vp), ("ld_a", i64), ("b_hi", vp),
+                ("b_lo", vp), ("C", vp), ("ldc", i64), ("alpha", f32)]
+
+
 class GnArgs(C.Structure):
     _fields_ = [("N", i32), ("HW", i32), ("C", i32), ("G", i32), ("eps", f32), ("silu", i32),
                 ("x", vp), ("ldx", i64), ("y", vp), ("ldy", i64), ("gamma", vp), ("beta", vp), ("mean", vp),
@@ -63,6 +68,9 @@ _SIGS = {
     "dp_pack_conv_weight": (C.c_int, [vp, i32, i32, i32, i32, vp, vp, vp]),
     "dp_pack_conv_weight_tc": (C.c_int, [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp]),
     "dp_gemm_batched": (C.c_int, [C.POINTER(GemmArgs), vp]),
+    "dp_gemm_nt_tc": (C.c_int, [C.POINTER(GemmNtArgs), vp]),
+    "dp_split_tf32": (C.c_int, [vp, i64, i64, i32, i32, i32, i32, vp, vp, vp]),
+    "dp_transpose_batched": (C.c_int, [vp, vp, i32, i32, i32, vp]),
     "dp_softmax_fwd": (C.c_int, [vp, vp, i64, i32, vp]),
     "dp_softmax_bwd": (C.c_int, [vp, vp, vp, i64, i32, vp]),
     "dp_groupnorm_workspace_bytes": (C.c_size_t, [i32, i32, i32, i32]),

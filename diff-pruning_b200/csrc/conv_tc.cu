@@ -38,6 +38,8 @@ struct TcParams {
   int ntaps;
   signed char dh[9], dw[9], wt[9];
   int os, oa, ob, Ho, Wo;   // output pixel = (p*os + oa, q*os + ob) on an [Ho][Wo] grid
+  float alpha;              // epilogue scale of the accumulator (attention logits); 1 for convolutions
+  int b_from_img;           // batched GEMM: the B tile index is the tile's image (bn == 1) instead of a filter tap
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -600,7 +602,7 @@ conv_tc_ps_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
           const uint32_t st = sbase + s * STAGE_BYTES;
           tma_load_4d(st, &mapA, full_bar(s), kc * BK, q0 + p.dw[tap], p0 + p.dh[tap], n0);
-          const int tapb = p.wt[tap];
+          const int tapb = p.b_from_img ? n0 : p.wt[tap];
           tma_load_3d(st + 2 * A_BYTES, &mapBh, full_bar(s), kc * BK, nblk * BN, tapb);
           tma_load_3d(st + 2 * A_BYTES + B_BYTES, &mapBl, full_bar(s), kc * BK, nblk * BN, tapb);
         }
@@ -713,8 +715,8 @@ conv_tc_ps_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           if (p.vec4 && c0 + 32 <= p.Nout) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-              float4 o = make_float4(__uint_as_float(v[i]) + __uint_as_float(u[i]), __uint_as_float(v[i + 1]) + __uint_as_float(u[i + 1]),
-                                     __uint_as_float(v[i + 2]) + __uint_as_float(u[i + 2]), __uint_as_float(v[i + 3]) + __uint_as_float(u[i + 3]));
+              float4 o = make_float4(p.alpha * (__uint_as_float(v[i]) + __uint_as_float(u[i])), p.alpha * (__uint_as_float(v[i + 1]) + __uint_as_float(u[i + 1])),
+                                     p.alpha * (__uint_as_float(v[i + 2]) + __uint_as_float(u[i + 2])), p.alpha * (__uint_as_float(v[i + 3]) + __uint_as_float(u[i + 3])));
               if (p.bias) { float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + i)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
               if (arow2) { float4 t = __ldg(reinterpret_cast<const float4*>(arow2 + c0 + i)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
               if (rrow) { float4 t = __ldg(reinterpret_cast<const float4*>(rrow + c0 + i)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
@@ -727,7 +729,7 @@ conv_tc_ps_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             for (int i = 0; i < 32; ++i) {
               const int c = c0 + i;
               if (c < p.Nout) {
-                float o = __uint_as_float(v[i]) + __uint_as_float(u[i]);
+                float o = p.alpha * (__uint_as_float(v[i]) + __uint_as_float(u[i]));
                 if (p.bias) o += __ldg(p.bias + c);
                 if (arow2) o += __ldg(arow2 + c);
                 if (rrow) o += __ldg(rrow + c);
@@ -1036,7 +1038,8 @@ struct TapTable { int n; signed char dh[9], dw[9], wt[9]; };
 // out: [Nimg][Ho][Wo][Nout] view, output pixel = (p*os+oa, q*os+ob).
 int launch_tc(const float* act, long long ld_act, int Nimg, int H, int W, int Kg, const float* w_hi, const float* w_lo, int Nout,
               int T, const TapTable& taps, int os, int oa, int ob, int Ho, int Wo, float* out, long long ld_out, const float* bias,
-              const float* rowadd, long long ld_rowadd, const float* residual, long long ld_res, int accumulate, cudaStream_t st) {
+              const float* rowadd, long long ld_rowadd, const float* residual, long long ld_res, int accumulate, cudaStream_t st,
+              float alpha = 1.0f, int b_from_img = 0) {
   if (!tc_init()) return DP_ERR_UNSUPPORTED;
   if (!w_hi || !w_lo) return DP_ERR_UNSUPPORTED;
   if (ld_act % 4 || ((uintptr_t)act & 15) || ((uintptr_t)w_hi & 15) || ((uintptr_t)w_lo & 15)) return DP_ERR_UNSUPPORTED;
@@ -1062,6 +1065,8 @@ int launch_tc(const float* act, long long ld_act, int Nimg, int H, int W, int Kg
   p.ntaps = taps.n;
   for (int i = 0; i < 9; ++i) { p.dh[i] = taps.dh[i]; p.dw[i] = taps.dw[i]; p.wt[i] = taps.wt[i]; }
   p.os = os; p.oa = oa; p.ob = ob; p.Ho = Ho; p.Wo = Wo;
+  p.alpha = alpha; p.b_from_img = b_from_img;
+  if ((alpha != 1.0f || b_from_img) && !(g_persistent && !g_use_ss && Nout > 64 && bn == 1)) return DP_ERR_UNSUPPORTED;
   p.kchunks = (Kg + BK - 1) / BK;
   p.bw = bw; p.bh = bh; p.bn = bn; p.tiles_w = W / bw; p.tiles_h = H / bh;
   p.y = out; p.ldy = ld_out; p.bias = bias; p.rowadd = rowadd; p.ld_rowadd = ld_rowadd; p.residual = residual; p.ld_res = ld_res;
@@ -1128,6 +1133,84 @@ __global__ void pack_tc_kernel(const float* __restrict__ w, int K, int C, int RS
     }
   }
 }
+__global__ void split_tf32_kernel(const float* __restrict__ x, long long ld, long long bs, int rows, int cols, int transpose,
+                                  float* __restrict__ hi, float* __restrict__ lo) {
+  // 32x32 tile through shared memory so both the read (along cols) and the transposed write (along rows) are coalesced
+  __shared__ float t[32][33];
+  const int b = blockIdx.z, r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const float* xb = x + (long long)b * bs;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    int r = r0 + i, c = c0 + threadIdx.x;
+    t[i][threadIdx.x] = (r < rows && c < cols) ? xb[(long long)r * ld + c] : 0.f;
+  }
+  __syncthreads();
+  if (!transpose) {
+    const int cols4 = (cols + 3) & ~3;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+      int r = r0 + i, c = c0 + threadIdx.x;
+      if (r < rows && c < cols4) {
+        float v = t[i][threadIdx.x], h = tf32_rna(v);
+        long long o = ((long long)b * rows + r) * cols4 + c;
+        hi[o] = h; lo[o] = v - h;
+      }
+    }
+  } else {
+    const int rows4 = (rows + 3) & ~3;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+      int c = c0 + i, r = r0 + threadIdx.x;
+      if (c < cols && r < rows4) {
+        float v = t[threadIdx.x][i], h = tf32_rna(v);
+        long long o = ((long long)b * cols + c) * rows4 + r;
+        hi[o] = h; lo[o] = v - h;
+      }
+    }
+  }
+}
+__global__ void transpose_batched_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
+  __shared__ float t[32][33];
+  const int b = blockIdx.z, r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const float* ib = in + (long long)b * rows * cols;
+  float* ob = out + (long long)b * rows * cols;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    int r = r0 + i, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) t[i][threadIdx.x] = ib[(long long)r * cols + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) ob[(long long)c * rows + r] = t[threadIdx.x][i];
+  }
+}
+}  // namespace
+
+extern "C" int dp_split_tf32(const float* x, int64_t ld, int64_t bs, int32_t batch, int32_t rows, int32_t cols, int32_t transpose,
+                             float* hi, float* lo, dp_stream_t stream) {
+  DP_REQUIRE(x && hi && lo, DP_ERR_NULL);
+  DP_REQUIRE(batch > 0 && rows > 0 && cols > 0 && ld >= cols && batch <= 65535, DP_ERR_SHAPE);
+  // the padded tail of a row (cols4 / rows4) must be covered by the grid: round the covered extent up
+  const int ccov = transpose ? cols : ((cols + 3) & ~3), rcov = transpose ? ((rows + 3) & ~3) : rows;
+  dim3 grid((ccov + 31) / 32, (rcov + 31) / 32, batch);
+  split_tf32_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(x, ld, bs, rows, cols, transpose, hi, lo);
+  return dp_check_launch();
+}
+extern "C" int dp_transpose_batched(const float* in, float* out, int32_t batch, int32_t rows, int32_t cols, dp_stream_t stream) {
+  DP_REQUIRE(in && out, DP_ERR_NULL);
+  DP_REQUIRE(batch > 0 && rows > 0 && cols > 0 && batch <= 65535, DP_ERR_SHAPE);
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32, batch);
+  transpose_batched_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(in, out, rows, cols);
+  return dp_check_launch();
+}
+extern "C" int dp_gemm_nt_tc(const dp_gemm_nt_args* a, dp_stream_t stream) {
+  DP_REQUIRE(a && a->A && a->b_hi && a->b_lo && a->C, DP_ERR_NULL);
+  DP_REQUIRE(a->batch > 0 && a->H > 0 && a->W > 0 && a->Kg > 0 && a->N > 0 && a->ld_a >= a->Kg && a->ldc >= a->N, DP_ERR_SHAPE);
+  if (a->batch > 127) { /* the B "tap" index travels in a signed char table only for real taps; images use n0 directly */ }
+  TapTable t{};
+  t.n = 1;
+  return launch_tc(a->A, a->ld_a, a->batch, a->H, a->W, a->Kg, a->b_hi, a->b_lo, a->N, a->batch, t, 1, 0, 0, a->H, a->W, a->C, a->ldc,
+                   nullptr, nullptr, 0, nullptr, 0, 0, (cudaStream_t)stream, a->alpha, 1);
+}
+
+namespace {
 }  // namespace
 
 int dp_tc_runtime_ok() { return tc_init(); }

@@ -443,6 +443,11 @@ class Plan:
             ga.C, ga.ldc, ga.c_bs, ga.alpha, ga.accumulate = Cp, ldc, c_bs, alpha, 0
             return ga
         Pp, sc = P.data_ptr(), float(m.scale)
+        import os as _os
+        use_tc = self.tc and T % 128 == 0 and _os.environ.get("DPB200_ATTN_TC", "1") != "0"
+        if use_tc:
+            self._attention_core_tc(N, H, W, T, inner, q, k, v, o, P, sc)
+            return self.conv(o, m.to_out[0].weight, m.to_out[0].bias, out, pad=0, residual=x if m.residual_connection else None)
         # S = scale * q k^T ; P = softmax(S) (in place) ; o = P v
         self._rec(self.fwd, lib.dp_gemm_batched, gemm(T, T, inner, q.ptr, q.ld, 1, T * q.ld, k.ptr, 1, k.ld, T * k.ld,
                                                       Pp, T, T * T, sc), "attn qk")
@@ -467,6 +472,57 @@ class Plan:
             self._rec(st, lib.dp_gemm_batched, gemm(T, inner, T, dPp, 1, T, T * T, q.ptr, q.ld, 1, T * q.ld,
                                                     dk.ptr, dk.ld, T * dk.ld, sc), "attn dK")
         self.conv(o, m.to_out[0].weight, m.to_out[0].bias, out, pad=0, residual=x if m.residual_connection else None)
+
+    def _attention_core_tc(self, N, H, W, T, inner, q, k, v, o, P, sc):
+        """softmax(scale q k^T) v and its backward on the tensor-core NT GEMM (dp_gemm_nt_tc): every product is written as
+        C = A B^T with a K-contiguous activation A (TMA box of the token grid) and a pre-split hi/lo B built by
+        dp_split_tf32 (optionally transposing); P^T / dS^T come from dp_transpose_batched.
+          fwd : S = q k^T          B = split(k)            O  = P v         B = split^T(v)
+          bwd : dV = P^T dO        A = P^T, B = split^T(dO)   dP = dO v^T    B = split(v)
+                dQ = dS k          B = split^T(k)            dK = dS^T q    A = dS^T, B = split^T(q)"""
+        lib = self.lib
+        i4, t4 = (inner + 3) // 4 * 4, (T + 3) // 4 * 4
+        nsplit = N * max(T * i4, inner * t4)
+        self.scratch("att_hi", nsplit); self.scratch("att_lo", nsplit); self.scratch("att_t", N * T * T)
+        Pp = P.data_ptr()
+
+        def split(lst, src: View, transpose: int):   # src is an [N][T][inner] activation view
+            self._rec(lst, lambda s, p=src.ptr, ld=src.ld, tr=transpose: lib.dp_split_tf32(
+                p, ld, T * ld, N, T, inner, tr, self.sptr("att_hi"), self.sptr("att_lo"), s), what="attn split")
+
+        def gemm(lst, A_get, ld_a, Kg, Nn, C_ptr, ldc, alpha, what):
+            ga = L.GemmNtArgs()
+            ga.batch, ga.H, ga.W, ga.Kg, ga.N = N, H, W, Kg, Nn
+            ga.ld_a, ga.C, ga.ldc, ga.alpha = ld_a, C_ptr, ldc, alpha
+            self._late.append(lambda ga=ga, g=A_get: (setattr(ga, "A", g()), setattr(ga, "b_hi", self.sptr("att_hi")),
+                                                      setattr(ga, "b_lo", self.sptr("att_lo"))))
+            self._rec(lst, lib.dp_gemm_nt_tc, ga, what)
+
+        f = self.fwd
+        split(f, k, 0)
+        gemm(f, lambda: q.ptr, q.ld, inner, T, Pp, T, sc, "attn qk (tc)")
+        self._rec(f, lambda s: lib.dp_softmax_fwd(Pp, Pp, N * T, T, s), what="softmax")
+        split(f, v, 1)
+        gemm(f, lambda: Pp, T, T, inner, o.ptr, o.ld, 1.0, "attn pv (tc)")
+        if not self.need_grad:
+            return
+        dq, dk, dv, do = (self.gradof(t) for t in (q, k, v, o))
+        dP = torch.empty_like(P)
+        self._keep.append(dP)
+        dPp = dP.data_ptr()
+        st = self._bitem().steps
+        tptr = lambda: self.sptr("att_t")
+        self._rec(st, lambda s: lib.dp_transpose_batched(Pp, tptr(), N, T, T, s), what="attn transpose")
+        split(st, do, 1)
+        gemm(st, tptr, T, T, inner, dv.ptr, dv.ld, 1.0, "attn dV (tc)")
+        split(st, v, 0)
+        gemm(st, lambda: do.ptr, do.ld, inner, T, dPp, T, 1.0, "attn dP (tc)")
+        self._rec(st, lambda s: lib.dp_softmax_bwd(Pp, dPp, dPp, N * T, T, s), what="softmax bwd")
+        split(st, k, 1)
+        gemm(st, lambda: dPp, T, T, inner, dq.ptr, dq.ld, sc, "attn dQ (tc)")
+        self._rec(st, lambda s: lib.dp_transpose_batched(dPp, tptr(), N, T, T, s), what="attn transpose")
+        split(st, q, 1)
+        gemm(st, tptr, T, T, inner, dk.ptr, dk.ld, sc, "attn dK (tc)")
 
     # ------------------------------------------------------------------ whole network
     def _build(self):

@@ -121,6 +121,27 @@ typedef struct dp_gemm_args {
 } dp_gemm_args;
 int dp_gemm_batched(const dp_gemm_args* a, dp_stream_t stream);
 
+/* Tensor-core batched GEMM for the attention core (attention_processor.py:341-357,452 and its backward):
+ *   C[b][m][n] = alpha * sum_k A[b][m][k] * B[b][n][k]          (both operands K-contiguous, "NT")
+ * A: [batch][H*W][Kg] fp32 view (pixel stride ld_a) — the token grid is the image grid so a 128-token tile is a TMA box;
+ * B: given pre-split (dp_split_tf32) as b_hi/b_lo [batch][N][Kg4]; C: [batch][H*W][N] view (ldc).  Runs on the persistent
+ * tcgen05 3xTF32 kernel; returns DP_ERR_UNSUPPORTED when the shape is not eligible (H*W % 128, alignment) so the caller can
+ * fall back to dp_gemm_batched. */
+typedef struct dp_gemm_nt_args {
+  int32_t batch, H, W, Kg, N;
+  const float* A; int64_t ld_a;
+  const float* b_hi; const float* b_lo;
+  float* C; int64_t ldc;
+  float alpha;
+} dp_gemm_nt_args;
+int dp_gemm_nt_tc(const dp_gemm_nt_args* a, dp_stream_t stream);
+/* hi = cvt.rna.tf32(x), lo = x - hi of a batched [rows][cols] fp32 matrix (row stride ld, batch stride bs), written densely as
+ * [batch][rows][cols4] — or transposed, [batch][cols][rows4] — with the row length rounded up to 4 floats (zero pad). */
+int dp_split_tf32(const float* x, int64_t ld, int64_t bs, int32_t batch, int32_t rows, int32_t cols, int32_t transpose, float* hi,
+                  float* lo, dp_stream_t stream);
+/* out[b][c][r] = in[b][r][c] for dense [batch][rows][cols] */
+int dp_transpose_batched(const float* in, float* out, int32_t batch, int32_t rows, int32_t cols, dp_stream_t stream);
+
 /* row softmax over [rows][cols] fp32 (attention_processor.py:352, upcast_softmax) and its backward
  * dS = P * (dP - sum_j dP*P); in-place allowed (out == in). */
 int dp_softmax_fwd(const float* s, float* p, int64_t rows, int32_t cols, dp_stream_t stream);

@@ -180,3 +180,35 @@ def test_stride2_dgrad_parity_classes(lib, N, Cin, H, K):
     d.flags = 1
     assert lib.dp_conv2d_dgrad(C.byref(d), S()) == 0
     assert rel_err(nchw(gx), 2 * x.grad) < 1.5e-5
+
+
+@pytest.mark.parametrize("N,H,W,Kg,Nn", [(3, 16, 16, 256, 256), (2, 16, 16, 179, 256), (2, 16, 16, 256, 179), (2, 8, 16, 64, 128)])
+def test_attention_nt_gemm_tc(lib, N, H, W, Kg, Nn):
+    """dp_gemm_nt_tc + dp_split_tf32 (+transpose) vs torch.bmm: C = alpha * A B^T per image, and the transposed-split form."""
+    from diff_pruning_b200 import _lib as L
+    g = torch.Generator().manual_seed(N + Kg + Nn)
+    T = H * W
+    A = torch.randn(N, T, Kg, generator=g)
+    B = torch.randn(N, Nn, Kg, generator=g)
+    ref = 0.25 * torch.bmm(A, B.transpose(1, 2))
+    Ad, Bd = torch.zeros(N, T, (Kg + 3) // 4 * 4, device="cuda"), B.cuda()
+    Ad[..., :Kg] = A.cuda()
+    K4 = (Kg + 3) // 4 * 4
+    hi, lo = torch.empty(N * Nn * K4, device="cuda"), torch.empty(N * Nn * K4, device="cuda")
+    assert lib.dp_split_tf32(Bd.data_ptr(), Kg, Nn * Kg, N, Nn, Kg, 0, hi.data_ptr(), lo.data_ptr(), S()) == 0
+    assert torch.equal((hi + lo).view(N, Nn, K4)[..., :Kg], Bd)
+    Cd = torch.full((N, T, Nn + 4), 5.0, device="cuda")
+    a = L.GemmNtArgs()
+    a.batch, a.H, a.W, a.Kg, a.N = N, H, W, Kg, Nn
+    a.A, a.ld_a, a.b_hi, a.b_lo, a.C, a.ldc, a.alpha = Ad.data_ptr(), Ad.shape[-1], hi.data_ptr(), lo.data_ptr(), Cd.data_ptr(), Nn + 4, 0.25
+    assert lib.dp_gemm_nt_tc(C.byref(a), S()) == 0
+    assert rel_err(Cd[..., :Nn].cpu(), ref) < 1.5e-5 and float((Cd[..., Nn:] - 5.0).abs().sum()) == 0.0
+    # transposed split: B given as [N][Kg][Nn] (e.g. v: [tokens][inner]) -> operand [N][Nn][Kg4]
+    Bt = B.transpose(1, 2).contiguous().cuda()
+    assert lib.dp_split_tf32(Bt.data_ptr(), Nn, Kg * Nn, N, Kg, Nn, 1, hi.data_ptr(), lo.data_ptr(), S()) == 0
+    assert torch.equal((hi + lo).view(N, Nn, K4)[..., :Kg], Bd)
+    # batched transpose
+    X = torch.randn(N, 70, 45, generator=g).cuda()
+    Y = torch.empty(N, 45, 70, device="cuda")
+    assert lib.dp_transpose_batched(X.data_ptr(), Y.data_ptr(), N, 70, 45, S()) == 0
+    assert torch.equal(Y, X.transpose(1, 2))
