@@ -8,3 +8,10 @@ from .models import (  # noqa: F401
 )
 
 __version__ = "0.1.0"
+
+
+def __getattr__(name):   # lazy: sampling pulls in the engine / the shared library
+    if name in ("DDIMScheduler", "DDIMPipeline"):
+        from . import sampling
+        return getattr(sampling, name)
+    raise AttributeError(name)

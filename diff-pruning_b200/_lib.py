@@ -92,6 +92,7 @@ _SIGS = {
     "dp_sumsq_partials": (i64, [i64]),
     "dp_sumsq": (C.c_int, [vp, i64, vp, vp, vp]),
     "dp_adam_clip_ema": (C.c_int, [C.POINTER(AdamArgs), vp]),
+    "dp_ddim_step": (C.c_int, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, vp]),
     "dp_scale": (C.c_int, [vp, i64, f32, vp]),
 }
 EXPORTS = tuple(_SIGS)

@@ -168,6 +168,17 @@ __global__ void softmax_bwd_kernel(const float* __restrict__ p, const float* __r
   dot = warp_sum(dot);
   for (int j = lane; j < cols; j += 32) o[j] = pr[j] * (dr[j] - dot);
 }
+__global__ void ddim_step_kernel(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ nz,
+                                 float* __restrict__ out, long long n, float sb, float sa, float clip, float sap, float dir, float sigma) {
+  for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) {
+    float e = eps[i];
+    float x0 = (x[i] - sb * e) / sa;
+    if (clip > 0.f) x0 = fminf(fmaxf(x0, -clip), clip);
+    float v = sap * x0 + dir * e;
+    if (nz) v += sigma * nz[i];
+    out[i] = v;
+  }
+}
 __global__ void scale_kernel(float* __restrict__ x, long long n, float s) {
   for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) x[i] *= s;
 }
@@ -252,6 +263,14 @@ extern "C" int dp_softmax_bwd(const float* p, const float* dp, float* ds, int64_
   long long nb = (rows + NT / 32 - 1) / (NT / 32);
   DP_REQUIRE(nb < (1ll << 31), DP_ERR_SHAPE);
   softmax_bwd_kernel<<<(unsigned)nb, NT, 0, (cudaStream_t)st>>>(p, dp, ds, rows, cols);
+  return dp_check_launch();
+}
+extern "C" int dp_ddim_step(const float* x, const float* eps, const float* noise, float* out, int64_t n, float sqrt_beta_t,
+                            float sqrt_alpha_t, float clip, float sqrt_alpha_prev, float dir_coef, float sigma, dp_stream_t st) {
+  DP_REQUIRE(x && eps && out, DP_ERR_NULL); DP_REQUIRE(n > 0 && sqrt_alpha_t > 0.f, DP_ERR_SHAPE);
+  DP_REQUIRE(sigma == 0.f || noise, DP_ERR_NULL);
+  ddim_step_kernel<<<nblocks(n, NT), NT, 0, (cudaStream_t)st>>>(x, eps, sigma != 0.f ? noise : nullptr, out, n, sqrt_beta_t, sqrt_alpha_t,
+                                                              clip, sqrt_alpha_prev, dir_coef, sigma);
   return dp_check_launch();
 }
 extern "C" int dp_scale(float* x, int64_t n, float s, dp_stream_t st) {

@@ -1,0 +1,128 @@
+"""DDIM sampling on the device — SURVEY.md §8(f) item 1: the step right after finetune in BASELINE config 2 and the tail of
+ddpm_prune.py:138-147 / ddpm_sample.py.
+
+DDIMScheduler  — diffusers/schedulers/scheduling_ddim.py as MODIFIED by the reference: `skip_type` uniform|quad timestep
+                 spacing (:257-266) and `prev_timestep = t - T // S` (:324, kept although it is inconsistent with that spacing).
+DDIMPipeline   — diffusers/pipelines/ddim/pipeline_ddim.py:45-122: randn image -> S x [UNet forward, scheduler.step] ->
+                 (x/2+0.5).clamp(0,1) -> NHWC numpy.  The UNet forward is the planned engine (no-grad plan), the update is one
+                 fused kernel (dp_ddim_step); per-step coefficients are formed in fp32 torch scalars like the reference.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .engine import _stream
+from .models import DDPMScheduler, UNet2DModel
+
+
+class DDIMScheduler:
+    def __init__(self, num_train_timesteps=1000, beta_start=1e-4, beta_end=0.02, beta_schedule="linear", skip_type="uniform",
+                 clip_sample=True, set_alpha_to_one=True, steps_offset=0, prediction_type="epsilon", clip_sample_range=1.0,
+                 **unused):
+        if beta_schedule != "linear" or prediction_type != "epsilon":
+            raise NotImplementedError("only the linear-beta epsilon-prediction DDPM family is on the hot path")
+        self.config = SimpleNamespace(num_train_timesteps=num_train_timesteps, beta_start=beta_start, beta_end=beta_end,
+                                      beta_schedule=beta_schedule, clip_sample=clip_sample, set_alpha_to_one=set_alpha_to_one,
+                                      steps_offset=steps_offset, prediction_type=prediction_type,
+                                      clip_sample_range=clip_sample_range)
+        self.betas = torch.linspace(beta_start, beta_end, num_train_timesteps, dtype=torch.float32)
+        self.alphas = 1.0 - self.betas
+        self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
+        self.skip_type = skip_type
+        self.final_alpha_cumprod = torch.tensor(1.0) if set_alpha_to_one else self.alphas_cumprod[0]
+        self.init_noise_sigma = 1.0
+        self.num_inference_steps = None
+        self.timesteps = torch.from_numpy(np.arange(0, num_train_timesteps)[::-1].copy().astype(np.int64))
+
+    @classmethod
+    def from_config(cls, config, **kw):
+        d = dict(vars(config)) if not isinstance(config, dict) else dict(config)
+        d.update(kw)
+        return cls(**d)
+
+    def set_timesteps(self, num_inference_steps: int, device=None):
+        T = self.config.num_train_timesteps
+        if num_inference_steps > T:
+            raise ValueError(f"`num_inference_steps`: {num_inference_steps} cannot be larger than `self.config.train_timesteps`: {T}")
+        self.num_inference_steps = num_inference_steps
+        if self.skip_type == "uniform":
+            ratio = (T - 1) / (num_inference_steps - 1)
+            ts = (np.arange(0, num_inference_steps) * ratio).round()[::-1].copy().astype(np.int64)
+        elif self.skip_type == "quad":
+            ratio = (T - 1) / (num_inference_steps - 1) ** 2
+            ts = (np.arange(0, num_inference_steps) ** 2 * ratio).round()[::-1].copy().astype(np.int64)
+        else:
+            raise NotImplementedError(f"skip_type {self.skip_type} is not implemented")
+        self.timesteps = torch.from_numpy(ts) + self.config.steps_offset
+
+    def _coefficients(self, timestep: int, eta: float):
+        prev = timestep - self.config.num_train_timesteps // self.num_inference_steps
+        a_t = self.alphas_cumprod[timestep]
+        a_prev = self.alphas_cumprod[prev] if prev >= 0 else self.final_alpha_cumprod
+        b_t = 1 - a_t
+        variance = ((1 - a_prev) / b_t) * (1 - a_t / a_prev)          # scheduling_ddim.py:194-202
+        std = eta * variance ** 0.5
+        return (float(b_t ** 0.5), float(a_t ** 0.5), float(a_prev ** 0.5), float((1 - a_prev - std ** 2) ** 0.5), float(std))
+
+    def step(self, model_output, timestep, sample, eta: float = 0.0, use_clipped_model_output=False, generator=None,
+             variance_noise=None, return_dict=True):
+        if self.num_inference_steps is None:
+            raise ValueError("Number of inference steps is 'None', you need to run 'set_timesteps' after creating the scheduler")
+        if use_clipped_model_output:
+            raise NotImplementedError("use_clipped_model_output")
+        if not sample.is_cuda:
+            raise RuntimeError("diff_pruning_b200: DDIMScheduler.step is a CUDA op (no CPU fallback)")
+        sb, sa, sap, dirc, sigma = self._coefficients(int(timestep), eta)
+        x, e = sample.contiguous(), model_output.contiguous()
+        noise = None
+        if eta > 0:
+            noise = variance_noise if variance_noise is not None else \
+                torch.randn(e.shape, generator=generator, device=generator.device if generator is not None else e.device,
+                            dtype=e.dtype)
+            noise = noise.to(e.device).contiguous()
+        out = torch.empty_like(x)
+        clip = float(self.config.clip_sample_range) if self.config.clip_sample else 0.0
+        L.check(L.load().dp_ddim_step(x.data_ptr(), e.data_ptr(), noise.data_ptr() if noise is not None else None, out.data_ptr(),
+                                      x.numel(), sb, sa, clip, sap, dirc, sigma, _stream()), "ddim_step")
+        return SimpleNamespace(prev_sample=out) if return_dict else (out,)
+
+
+class DDIMPipeline:
+    def __init__(self, unet: UNet2DModel, scheduler):
+        self.unet = unet
+        self.scheduler = DDIMScheduler.from_config(scheduler.config) if not isinstance(scheduler, DDIMScheduler) else scheduler
+        self._pbar = {}
+
+    @property
+    def device(self):
+        return next(self.unet.parameters()).device
+
+    def to(self, device):
+        self.unet.to(device)
+        return self
+
+    def set_progress_bar_config(self, **kw):
+        self._pbar = kw
+
+    @torch.no_grad()
+    def __call__(self, batch_size=1, generator=None, eta=0.0, num_inference_steps=50, use_clipped_model_output=None,
+                 output_type="pil", return_dict=True):
+        cfg = self.unet.config
+        size = cfg.sample_size if isinstance(cfg.sample_size, int) else None
+        shape = (batch_size, cfg.in_channels, size, size) if size is not None else (batch_size, cfg.in_channels, *cfg.sample_size)
+        gdev = generator.device if generator is not None else self.device
+        image = torch.randn(shape, generator=generator, device=gdev, dtype=torch.float32).to(self.device)
+        self.scheduler.set_timesteps(num_inference_steps)
+        for t in self.scheduler.timesteps:
+            eps = self.unet(image, int(t)).sample
+            image = self.scheduler.step(eps, int(t), image, eta=eta, generator=generator).prev_sample
+        image = (image / 2 + 0.5).clamp(0, 1).cpu().permute(0, 2, 3, 1).numpy()
+        if output_type == "pil":
+            from PIL import Image  # optional dependency, like the reference
+            image = [Image.fromarray((im * 255).round().astype("uint8")) for im in image]
+        return SimpleNamespace(images=image) if return_dict else (image,)

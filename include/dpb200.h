@@ -256,6 +256,12 @@ typedef struct dp_adam_args {
 } dp_adam_args;
 int dp_adam_clip_ema(const dp_adam_args* a, dp_stream_t stream);
 
+/* One DDIM update (scheduling_ddim.py:324-390, epsilon prediction), elementwise over n values:
+ *   x0 = (x - sqrt_beta_t * eps) / sqrt_alpha_t ; if clip > 0: x0 = clamp(x0, -clip, clip)
+ *   out = sqrt_alpha_prev * x0 + dir_coef * eps (+ sigma * noise)        noise may be NULL when sigma == 0 */
+int dp_ddim_step(const float* x, const float* eps, const float* noise, float* out, int64_t n, float sqrt_beta_t, float sqrt_alpha_t,
+                 float clip, float sqrt_alpha_prev, float dir_coef, float sigma, dp_stream_t stream);
+
 /* y[i] = x[i] * s  (gradient averaging after all-reduce etc.) */
 int dp_scale(float* x, int64_t n, float s, dp_stream_t stream);
 

@@ -85,3 +85,15 @@ def test_lsun_config_param_count():
     torch.manual_seed(0)
     m = dp.UNet2DModel(**dp.LSUN256_DDPM_CONFIG)
     assert round(sum(p.numel() for p in m.parameters()) / 1e6, 3) == 113.673   # SURVEY.md §8 "C3"
+
+
+def test_ddim_timesteps_host_logic():
+    """The reference's modified timestep spacing (scheduling_ddim.py:257-266) — pure host logic."""
+    from diff_pruning_b200.sampling import DDIMScheduler
+    G = load_golden("ddim_tiny.pt")
+    for name in ("uniform_eta0", "quad_eta05"):
+        s = DDIMScheduler(num_train_timesteps=1000, skip_type=G[name]["skip_type"])
+        s.set_timesteps(G[name]["steps"])
+        assert torch.equal(s.timesteps, G[name]["timesteps"])
+    s = DDIMScheduler.from_config(dp.DDPMScheduler(num_train_timesteps=1000).config)
+    assert s.config.clip_sample and s.skip_type == "uniform"

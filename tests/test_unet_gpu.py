@@ -227,3 +227,21 @@ def test_lsun256_architecture_one_pass_vs_oracle():
     assert sc.step(t).item() == pytest.approx(ref.item(), rel=1e-5)
     worst = worst_grad_err(((k, p.grad) for k, p in m.named_parameters()), {k: v.grad for k, v in sd.items()})
     assert worst < 2e-4, worst
+
+
+def test_ddim_sampling_matches_reference_pipeline():
+    """DDIMPipeline + the reference's modified DDIMScheduler (skip_type, prev_timestep rule) on the device: images of a 10-step
+    eta=0 uniform run and a 7-step eta=0.5 quad run (CPU generator for the initial latent and the variance noise, like the
+    fixture) within 2e-4 of the reference's CPU pipeline (errors of the 1e-5-grade UNet compound over the chain)."""
+    G = load_golden("ddim_tiny.pt")
+    from diff_pruning_b200.sampling import DDIMPipeline
+    m = build(G["cfg"])
+    for name in ("uniform_eta0", "quad_eta05"):
+        R = G[name]
+        pipe = DDIMPipeline(unet=m, scheduler=dp.DDPMScheduler(num_train_timesteps=1000))
+        pipe.scheduler.skip_type = R["skip_type"]
+        g = torch.Generator().manual_seed(0)
+        out = pipe(batch_size=2, generator=g, eta=R["eta"], num_inference_steps=R["steps"], output_type="numpy").images
+        assert torch.equal(pipe.scheduler.timesteps, R["timesteps"])
+        assert out.shape == tuple(R["images"].shape) and out.min() >= 0.0 and out.max() <= 1.0
+        assert float((torch.from_numpy(out) - R["images"]).abs().max()) < 2e-4, name

@@ -13,6 +13,7 @@ Outputs (all small, committed):
                                    post-prune shapes / param+MAC counts / pruned-model eps
     tests/golden/cifar_cfg1_s3.pt  same with 3 timesteps (fast CPU check of the oracle)
     tests/golden/finetune_tiny.pt  2 finetune steps on TINY (Adam + clip + EMA), dropout 0
+    tests/golden/ddim_tiny.pt      DDIMPipeline samples (uniform/eta 0/10 steps, quad/eta 0.5/7 steps) on TINY
 """
 import argparse
 import hashlib
@@ -321,13 +322,31 @@ def gen_finetune():
     print("finetune", [s["loss"] for s in rec["steps"]], [s["grad_norm"] for s in rec["steps"]])
 
 
+def gen_ddim():
+    """DDIMPipeline (pipeline_ddim.py:45-122) + the reference's modified DDIMScheduler on the TINY UNet, CPU generator."""
+    from diffusers import DDIMPipeline
+    cfg = dict(dp.TINY_TEST_CONFIG)
+    m = build(cfg)
+    res = {"cfg": cfg}
+    for name, skip, eta, steps in (("uniform_eta0", "uniform", 0.0, 10), ("quad_eta05", "quad", 0.5, 7)):
+        pipe = DDIMPipeline(unet=m, scheduler=DDPMScheduler(num_train_timesteps=1000))
+        pipe.scheduler.skip_type = skip
+        pipe.set_progress_bar_config(disable=True)
+        g = torch.Generator().manual_seed(0)
+        out = pipe(batch_size=2, generator=g, eta=eta, num_inference_steps=steps, output_type="numpy").images
+        res[name] = {"skip_type": skip, "eta": eta, "steps": steps, "images": torch.from_numpy(out),
+                     "timesteps": pipe.scheduler.timesteps.clone()}
+    torch.save(res, os.path.join(OUT, "ddim_tiny.pt"))
+    print("ddim", {k: float(v["images"].mean()) for k, v in res.items() if k != "cfg"})
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--skip-cfg1", action="store_true")
     ap.add_argument("--only", default=None)
     a = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
-    jobs = {"tiny": gen_tiny, "blocks": gen_blocks, "finetune": gen_finetune, "cifar_fwd": gen_cifar_fwd,
+    jobs = {"ddim": gen_ddim, "tiny": gen_tiny, "blocks": gen_blocks, "finetune": gen_finetune, "cifar_fwd": gen_cifar_fwd,
             "cfg1_s3": gen_cfg1_s3, "cfg1": gen_cfg1}
     for name, fn in jobs.items():
         if a.only and name != a.only:
