@@ -239,7 +239,7 @@ def _timed_pass(scorer, events):
             if tag:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(s); f(s_int); e1.record(s)
-                pairs.append((e0, e1))
+                pairs.append((e0, e1, getattr(f, "what", "conv")))
             else:
                 f(s_int)
     is_conv = lambda f: getattr(f, "what", "").startswith("conv")
@@ -252,7 +252,10 @@ def _timed_pass(scorer, events):
     run_list(p.bwd_steps, [is_conv(f) for f in p.bwd_steps])
     torch.cuda.synchronize()
     p.grad_arena.copy_(saved)
-    return sum(a.elapsed_time(b) for a, b in pairs) * 1e-3, len(pairs)
+    by_tag = {}
+    for a, b, tag in pairs:
+        by_tag[tag] = by_tag.get(tag, 0.0) + a.elapsed_time(b)
+    return sum(a.elapsed_time(b) for a, b, _ in pairs) * 1e-3, len(pairs), {k: round(v, 3) for k, v in sorted(by_tag.items())}
 
 
 def run_ours(args, rank, world, local_rank):
@@ -336,7 +339,7 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
     # ---------------- roofline of the dominant kernel (conv implicit GEMM), live CUDA events
-    conv_s, n_conv = _timed_pass(sc, None) if rank == 0 else (1.0, 0)
+    conv_s, n_conv, conv_by_tag = _timed_pass(sc, None) if rank == 0 else (1.0, 0, {})
     plan_B = sc.plan.B
     del sc
     if hasattr(model, "_dpb200_plans"):
@@ -355,7 +358,7 @@ def run_ours(args, rank, world, local_rank):
         tj = json.load(open(tp))
         traffic = tj["dram_read_bytes"] + tj["dram_write_bytes"]
     roofline = {"bound": "tensor", "achieved": achieved, "peak": tf_sus, "unit": "TFLOP/s", "frac": achieved / tf_sus,
-                "traffic": traffic,
+                "traffic": traffic, "breakdown_ms": conv_by_tag,
                 "kernel": "conv implicit GEMM (fprop+dgrad+wgrad launches of one pass: %d)" % n_conv,
                 "note": (f"algorithmic conv FLOPs/pass = {B} x 34.27 GFLOP (SURVEY.md §8d) / summed conv-launch device time "
                          f"{conv_s * 1e3:.2f} ms of a {ms / args.steps:.2f} ms step; peak = bf16_tflops_sustained ({which}); "

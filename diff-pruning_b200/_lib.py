@@ -61,6 +61,7 @@ _SIGS = {
     "dp_last_cuda_error": (C.c_int, []),
     "dp_launch_count": (i64, []),
     "dp_tc_available": (C.c_int, []),
+    "dp_conv_tc_set_trace": (C.c_int, [C.c_void_p]),
     "dp_conv2d_fprop": (C.c_int, [C.POINTER(ConvArgs), vp]),
     "dp_conv2d_dgrad": (C.c_int, [C.POINTER(ConvArgs), vp]),
     "dp_conv2d_wgrad": (C.c_int, [C.POINTER(ConvArgs), vp]),
@@ -109,11 +110,12 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("DPB200_LIB", LIB_PATH)   # developer knob: A/B an alternative build of the same sources
+    if not os.path.exists(path):
         raise DpError(
             f"diff_pruning_b200: {LIB_PATH} not found. Build it with `python -c 'import __graft_entry__ as g; "
             "g.build()'` (nvcc, sm_100a). There is no CPU / PyTorch fallback for the hot path.")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, (res, args) in _SIGS.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args

@@ -40,6 +40,11 @@ struct TcParams {
   int os, oa, ob, Ho, Wo;   // output pixel = (p*os + oa, q*os + ob) on an [Ho][Wo] grid
   float alpha;              // epilogue scale of the accumulator (attention logits); 1 for convolutions
   int b_from_img;           // batched GEMM: the B tile index is the tile's image (bn == 1) instead of a filter tap
+  int two_issuers;          // persistent kernel: number of MMA-issuing warps taking alternate pipeline stages (DPB200_TC_ISSUERS=1|2)
+  int wide_n;               // persistent kernel: fuse a_hi x b_hi and a_hi x b_lo into one N=256 instruction (DPB200_TC_WIDE_N=0 switches it off)
+  int dbg_skip;             // timing experiments only (DPB200_TC_DEBUG_SKIP bitmask: 1 no A load, 2 no B_hi, 4 no B_lo) — results are then wrong
+  long long* trace;         // pipeline trace buffer (dp_conv_tc_set_trace; nullptr = off): CTA 0 stamps clock64() per stage / actor
+  int b_sub;                // decoupled-ring kernel: weight tiles fetched as b_sub boxes of BN/b_sub rows (experiment knob DPB200_B_SUB)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -90,6 +95,22 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// warp-converged single-lane election (elect.sync): lets ptxas keep descriptors / barrier addresses in UNIFORM registers and emit
+// straight-line UTCHMMA / UTMALDG; a plain `if (lane == 0)` makes it wrap every such instruction in an ELECT / BRA.U.ANY loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// A whole (converged) warp waits on a barrier.
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+#ifdef DPB200_POLL_LANE0   // measured 14 % slower on the C1 pass than letting every lane poll (hardware-suspended try_wait)
+  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+  __syncwarp();
+#else
+  mbar_wait(bar, parity);
+#endif
 }
 __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t r;
@@ -532,6 +553,226 @@ conv_tc_ts_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 }
 
 
+// ------------------------------------------------------------------------------------------------ decoupled-ring variant
+// The measured limiter of the kernels above is not a throughput resource but the per-stage dependency CHAIN (TMA arrival ->
+// split -> fence -> barrier -> MMA -> commit -> barrier -> next TMA ~ 3000 cycles for 768 cycles of MMA) with one ring that
+// holds A and B together.  Here the two operands get their own rings and their own producers:
+//   A ring : 6 x 16 KB raw tiles in shared memory -> splitter warps -> 4 hi/lo slots in TENSOR MEMORY; a shared-memory slot is
+//            released by the SPLITTER (as soon as the tile is in registers), so the A TMA runs several stages ahead
+//   B ring : 3 x (hi 16 KB + lo 16 KB); released by tcgen05.commit; its chain has no splitter hop at all
+//   MMA    : waits "A slot in TMEM" + "B stage landed", issues 12 MMAs (A from TMEM), commits to both rings
+// warps: 0 TMA-A | 1 TMA-B | 2 MMA (+TMEM alloc) | 3-6 splitter then epilogue (TMEM lane quarter = warp & 3).
+constexpr int AB_THREADS = 224, AB_SA = 6, AB_SB = 3, AB_TA = 4;
+
+__global__ void __launch_bounds__(AB_THREADS, 1)
+conv_tc_ab_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBh,
+                  const __grid_constant__ CUtensorMap mapBl, const TcParams p) {
+  constexpr int BN = 128;
+  constexpr int B_BYTES = BN * BK * 4;
+  constexpr uint32_t A_COL0 = 2 * BN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t pad_to = ((raw + 1023u) & ~1023u) - raw;
+  uint8_t* smem = smem_raw + pad_to;
+  const uint32_t sbase = raw + pad_to;
+  const uint32_t a_base = sbase, b_base = sbase + AB_SA * A_BYTES;
+  constexpr int DATA_BYTES = AB_SA * A_BYTES + AB_SB * 2 * B_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DATA_BYTES);
+  const uint32_t bar0 = sbase + DATA_BYTES;
+  auto fullA = [&](int i) { return bar0 + 8u * i; };
+  auto emptyA = [&](int i) { return bar0 + 8u * (AB_SA + i); };
+  auto fullB = [&](int i) { return bar0 + 8u * (2 * AB_SA + i); };
+  auto emptyB = [&](int i) { return bar0 + 8u * (2 * AB_SA + AB_SB + i); };
+  auto convT = [&](int i) { return bar0 + 8u * (2 * AB_SA + 2 * AB_SB + i); };
+  auto emptyT = [&](int i) { return bar0 + 8u * (2 * AB_SA + 2 * AB_SB + AB_TA + i); };
+  const uint32_t tmem_full_bar = bar0 + 8u * (2 * AB_SA + 2 * AB_SB + 2 * AB_TA);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * AB_SA + 2 * AB_SB + 2 * AB_TA + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < AB_SA; ++i) { mbar_init(fullA(i), 1); mbar_init(emptyA(i), 128); }
+    for (int i = 0; i < AB_SB; ++i) { mbar_init(fullB(i), 1); mbar_init(emptyB(i), 1); }
+    for (int i = 0; i < AB_TA; ++i) { mbar_init(convT(i), 128); mbar_init(emptyT(i), 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tile_m = blockIdx.x, nblk = blockIdx.y;
+  const int tw = tile_m % p.tiles_w;
+  const int th = (tile_m / p.tiles_w) % p.tiles_h;
+  const int tn = tile_m / (p.tiles_w * p.tiles_h);
+  const int q0 = tw * p.bw, p0 = th * p.bh, n0 = tn * p.bn;
+  const int num_iters = p.ntaps * p.kchunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
+      for (int it = 0; it < num_iters; ++it) {
+        const int s = it % AB_SA;
+        const uint32_t ph = (uint32_t)(it / AB_SA) & 1u;
+        mbar_wait(emptyA(s), ph ^ 1u);
+        mbar_expect_tx(fullA(s), A_BYTES);
+        const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
+        tma_load_4d(a_base + s * A_BYTES, &mapA, fullA(s), kc * BK, q0 + p.dw[tap], p0 + p.dh[tap], n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapBh)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapBl)) : "memory");
+      for (int it = 0; it < num_iters; ++it) {
+        const int s = it % AB_SB;
+        const uint32_t ph = (uint32_t)(it / AB_SB) & 1u;
+        mbar_wait(emptyB(s), ph ^ 1u);
+        mbar_expect_tx(fullB(s), 2 * B_BYTES);
+        const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
+        const int tapb = p.b_from_img ? n0 : p.wt[tap];
+        const uint32_t st = b_base + s * 2 * B_BYTES;
+        if (p.b_sub <= 1) {
+          tma_load_3d(st, &mapBh, fullB(s), kc * BK, nblk * BN, tapb);
+          tma_load_3d(st + B_BYTES, &mapBl, fullB(s), kc * BK, nblk * BN, tapb);
+        } else {   // the same bytes as p.b_sub smaller boxes per operand: more TMA operations in flight, shorter per-load latency
+          const int rows = BN / p.b_sub;
+          for (int j = 0; j < p.b_sub; ++j) {
+            tma_load_3d(st + j * rows * 128, &mapBh, fullB(s), kc * BK, nblk * BN + j * rows, tapb);
+            tma_load_3d(st + B_BYTES + j * rows * 128, &mapBl, fullB(s), kc * BK, nblk * BN + j * rows, tapb);
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    if (lane == 0) {
+      const int n_valid = min(BN, p.Nout - nblk * BN);
+      const uint32_t n_instr = (uint32_t)((n_valid + 15) & ~15);
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((n_instr >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      for (int it = 0; it < num_iters; ++it) {
+        const int sb = it % AB_SB, ta = it % AB_TA;
+        mbar_wait(convT(ta), (uint32_t)(it / AB_TA) & 1u);     // A hi/lo of this step sit in TMEM slot ta
+        mbar_wait(fullB(sb), (uint32_t)(it / AB_SB) & 1u);     // B hi/lo landed in shared memory
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t st = b_base + sb * 2 * B_BYTES;
+        const uint32_t a_t = tmem_base + A_COL0 + 64u * ta;
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k) {
+          const uint64_t b_hi = umma_desc(st + k * 32), b_lo = umma_desc(st + B_BYTES + k * 32);
+          const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
+          umma_tf32_ts(tmem_base + BN, a_t + 32 + k * 8, b_hi, idesc, first);   // lo * hi
+          umma_tf32_ts(tmem_base + BN, a_t + k * 8, b_lo, idesc, 1u);           // hi * lo
+          umma_tf32_ts(tmem_base, a_t + k * 8, b_hi, idesc, first);             // hi * hi
+        }
+        umma_commit(emptyB(sb));
+        umma_commit(emptyT(ta));
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    for (int it = 0; it < num_iters; ++it) {
+      const int sa = it % AB_SA, ta = it % AB_TA;
+      mbar_wait(fullA(sa), (uint32_t)(it / AB_SA) & 1u);
+      const uint8_t* arow = smem + sa * A_BYTES + row * 128;
+      uint32_t hi[32], lo[32];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 v = *reinterpret_cast<const float4*>(arow + ((j ^ (row & 7)) << 4));
+        const float h0 = tf32_rna(v.x), h1 = tf32_rna(v.y), h2 = tf32_rna(v.z), h3 = tf32_rna(v.w);
+        hi[4 * j + 0] = __float_as_uint(h0); hi[4 * j + 1] = __float_as_uint(h1);
+        hi[4 * j + 2] = __float_as_uint(h2); hi[4 * j + 3] = __float_as_uint(h3);
+        lo[4 * j + 0] = __float_as_uint(v.x - h0); lo[4 * j + 1] = __float_as_uint(v.y - h1);
+        lo[4 * j + 2] = __float_as_uint(v.z - h2); lo[4 * j + 3] = __float_as_uint(v.w - h3);
+      }
+      mbar_arrive(emptyA(sa));                                  // tile is in registers: the A TMA may refill this slot
+      mbar_wait(emptyT(ta), ((uint32_t)(it / AB_TA) & 1u) ^ 1u);   // the MMAs that read TMEM slot ta (4 steps ago) are done
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a_t = tmem_base + lane_addr + A_COL0 + 64u * ta;
+      tmem_st32(a_t, hi);
+      tmem_st32(a_t + 32, lo);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(convT(ta));
+    }
+    // ---- epilogue
+    mbar_wait(tmem_full_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int w_l = row % p.bw, h_l = (row / p.bw) % p.bh, n_l = row / (p.bw * p.bh);
+    const int img = n0 + n_l;
+    const bool row_ok = img < p.Nimg;
+    const long long m = ((long long)img * p.Ho + ((p0 + h_l) * p.os + p.oa)) * p.Wo + ((q0 + w_l) * p.os + p.ob);
+    float* yrow = p.y + m * p.ldy;
+    const float* rrow = p.residual ? p.residual + m * p.ld_res : nullptr;
+    const float* arow2 = p.rowadd ? p.rowadd + (long long)img * p.ld_rowadd : nullptr;
+#pragma unroll 1
+    for (int j = 0; j < BN / 32; ++j) {
+      uint32_t v[32], u[32];
+      const uint32_t taddr = tmem_base + lane_addr + (uint32_t)(j * 32);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+            "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+            "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr));
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+            "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
+            "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
+            "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+          : "r"(taddr + (uint32_t)BN));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (row_ok) {
+        const int c0 = nblk * BN + j * 32;
+        if (p.vec4 && c0 + 32 <= p.Nout) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            float4 o = make_float4(p.alpha * (__uint_as_float(v[i]) + __uint_as_float(u[i])), p.alpha * (__uint_as_float(v[i + 1]) + __uint_as_float(u[i + 1])),
+                                   p.alpha * (__uint_as_float(v[i + 2]) + __uint_as_float(u[i + 2])), p.alpha * (__uint_as_float(v[i + 3]) + __uint_as_float(u[i + 3])));
+            if (p.bias) { float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + i)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+            if (arow2) { float4 t = __ldg(reinterpret_cast<const float4*>(arow2 + c0 + i)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+            if (rrow) { float4 t = __ldg(reinterpret_cast<const float4*>(rrow + c0 + i)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+            float4* dst = reinterpret_cast<float4*>(yrow + c0 + i);
+            if (p.accumulate) { float4 t = *dst; o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+            *dst = o;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int c = c0 + i;
+            if (c < p.Nout) {
+              float o = p.alpha * (__uint_as_float(v[i]) + __uint_as_float(u[i]));
+              if (p.bias) o += __ldg(p.bias + c);
+              if (arow2) o += __ldg(arow2 + c);
+              if (rrow) o += __ldg(rrow + c);
+              if (p.accumulate) o += yrow[c];
+              yrow[c] = o;
+            }
+          }
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ persistent variant
 // One CTA per SM loops over output tiles (static stride), 10 warps: TMA producer | MMA issuer | 4 splitter warps |
 // 4 epilogue warps.  Two accumulator sets in TMEM (2 x [main 128 | correction 128] = 512 columns) let the epilogue of tile
@@ -616,6 +857,7 @@ conv_tc_ps_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         const int n_valid = min(BN, p.Nout - nblk * BN);
         const uint32_t n_instr = (uint32_t)((n_valid + 15) & ~15);
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((n_instr >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        const uint32_t idesc256 = (1u << 4) | (2u << 7) | (2u << 10) | ((256u >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
         const uint32_t b = tl & 1u, use = tl >> 1;
         mbar_wait(tempty_bar(b), (use & 1u) ^ 1u);          // epilogue has drained this accumulator set
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -631,9 +873,14 @@ conv_tc_ps_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             const uint64_t a_hi = umma_desc(st + k * 32), a_lo = umma_desc(st + A_BYTES + k * 32);
             const uint64_t b_hi = umma_desc(st + 2 * A_BYTES + k * 32), b_lo = umma_desc(st + 2 * A_BYTES + B_BYTES + k * 32);
             const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
-            umma_tf32(acc + 128, a_lo, b_hi, idesc, first);
-            umma_tf32(acc + 128, a_hi, b_lo, idesc, 1u);
-            umma_tf32(acc, a_hi, b_hi, idesc, first);
+            if (p.wide_n) {   // a_hi x [b_hi | b_lo] -> [main | correction] as ONE N=256 instruction (the two B tiles are adjacent)
+              umma_tf32(acc, a_hi, b_hi, idesc256, first);
+              umma_tf32(acc + 128, a_lo, b_hi, idesc, 1u);
+            } else {
+              umma_tf32(acc + 128, a_lo, b_hi, idesc, first);
+              umma_tf32(acc + 128, a_hi, b_lo, idesc, 1u);
+              umma_tf32(acc, a_hi, b_hi, idesc, first);
+            }
           }
           umma_commit(empty_bar(s));
         }
@@ -750,6 +997,296 @@ conv_tc_ps_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   }
 }
 
+// ---- experimental successor of conv_tc_ps_kernel (DPB200_TC_PERSISTENT=3): warp-converged elect.sync issue, two MMA-issuer
+// warps on alternate stages, optional 16-float stages x 7, optional N=256 fused instruction, per-stage clock64() trace
+// (dp_conv_tc_set_trace).  Measured in profiles/r01_experiments.md; not the default because on the whole C1 pass it is
+// ~8 % slower than the kernel above (21.7 vs 20.0 ms of fprop+dgrad) although its steady-state stage period is shorter.
+constexpr int PS2_THREADS = 352;   // warps: 0 TMA producer | 1, 10 MMA issuers (alternate stages) | 2-5 splitters | 6-9 epilogue
+// K-chunk per pipeline stage and ring depth: 16 floats (64-byte swizzle atoms, 32 KB stages) x 7, or 32 floats (128-byte atoms, 64 KB) x 3.
+// The per-stage round trip (slot freed -> TMA -> split -> MMA -> commit) is ~3000 clk; 3 x 768 clk of MMA work in flight cannot
+// cover it, 7 x 384 clk with a shorter split/MMA leg can (profiles/r01_experiments.md).
+template <int BKT> struct PsCfg { static constexpr int STAGES = (BKT == 16) ? 7 : 3; };
+template <int BKT> __device__ __forceinline__ uint64_t umma_desc_ps(uint32_t saddr) {
+  if (BKT == 32) return umma_desc(saddr);
+  // K-major SWIZZLE_64B: 8-row groups of 64-byte rows, SBO = 512 B, layout_type 4
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
+}   // warps: 0 TMA producer | 1 MMA issuer (even stages) | 2-5 splitters | 6-9 epilogue | 10 MMA issuer (odd stages)
+
+constexpr int TRACE_STAGES = 1024;
+#define DP_TRACE_TILE(slot, tl) do { if (p.trace && blockIdx.x == 0 && (tl) < 64u) p.trace[TRACE_STAGES * 16 + (tl) * 4 + (slot)] = clock64(); } while (0)
+#define DP_TRACE(slot, g) do { if (p.trace && blockIdx.x == 0 && (g) < (uint32_t)TRACE_STAGES) p.trace[(g) * 16 + (slot)] = clock64(); } while (0)
+
+template <int BKT>
+__global__ void __launch_bounds__(PS2_THREADS, 1)
+conv_tc_ps2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBh,
+                  const __grid_constant__ CUtensorMap mapBl, const TcParams p, const int tiles_m, const int total_tiles) {
+  constexpr int BN = 128;
+  constexpr int PS_STAGES = PsCfg<BKT>::STAGES;
+  constexpr int BK = BKT;                       // shadows the file-scope K chunk
+  constexpr int A_BYTES = BM * BKT * 4;
+  constexpr int B_BYTES = BN * BK * 4;
+  constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t pad_to = ((raw + 1023u) & ~1023u) - raw;
+  uint8_t* smem = smem_raw + pad_to;
+  const uint32_t sbase = raw + pad_to;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PS_STAGES * STAGE_BYTES);
+  const uint32_t bar0 = sbase + PS_STAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto conv_bar = [&](int s) { return bar0 + 8u * (PS_STAGES + s); };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (2 * PS_STAGES + s); };
+  auto tfull_bar = [&](int b) { return bar0 + 8u * (3 * PS_STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar0 + 8u * (3 * PS_STAGES + 2 + b); };
+  auto iss_bar = [&](int s) { return bar0 + 8u * (3 * PS_STAGES + 4 + s); };   // "MMAs of the stage in slot s are in the tensor queue"
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * PS_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < PS_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(conv_bar(s), 128); mbar_init(empty_bar(s), 1); mbar_init(iss_bar(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  const int iters_per_tile = p.ntaps * p.kchunks;
+
+  auto tile_coords = [&](int tile, int& q0, int& p0, int& n0, int& nblk) {
+    nblk = tile / tiles_m;
+    const int tile_m = tile - nblk * tiles_m;
+    const int tw = tile_m % p.tiles_w;
+    const int th = (tile_m / p.tiles_w) % p.tiles_h;
+    const int tn = tile_m / (p.tiles_w * p.tiles_h);
+    q0 = tw * p.bw; p0 = th * p.bh; n0 = tn * p.bn;
+  };
+
+  if (warp == 0) {
+    if (elect_one()) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapBh)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapBl)) : "memory");
+    }
+    __syncwarp();
+    uint32_t g = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int q0, p0, n0, nblk;
+      tile_coords(tile, q0, p0, n0, nblk);
+      int tap = 0, kc = 0;
+      for (int it = 0; it < iters_per_tile; ++it, ++g) {
+        const int s = g % PS_STAGES;
+        const uint32_t ph = (g / PS_STAGES) & 1u;
+        const int c_k = kc * BK, c_w = q0 + p.dw[tap], c_h = p0 + p.dh[tap];
+        const int tapb = p.b_from_img ? n0 : p.wt[tap];
+        const uint32_t st = sbase + s * STAGE_BYTES;
+        if (++kc == p.kchunks) { kc = 0; ++tap; }
+        mbar_wait_warp(empty_bar(s), ph ^ 1u);
+        if (elect_one()) {
+          DP_TRACE(0, g);
+          if (p.dbg_skip == 0) {
+            mbar_expect_tx(full_bar(s), A_BYTES + 2 * B_BYTES);
+            tma_load_4d(st, &mapA, full_bar(s), c_k, c_w, c_h, n0);
+            tma_load_3d(st + 2 * A_BYTES, &mapBh, full_bar(s), c_k, nblk * BN, tapb);
+            tma_load_3d(st + 2 * A_BYTES + B_BYTES, &mapBl, full_bar(s), c_k, nblk * BN, tapb);
+          } else {   // timing experiments: drop some of the loads
+            const int sk = p.dbg_skip;
+            mbar_expect_tx(full_bar(s), ((sk & 1) ? 0 : A_BYTES) + ((sk & 2) ? 0 : B_BYTES) + ((sk & 4) ? 0 : B_BYTES));
+            if (!(sk & 1)) tma_load_4d(st, &mapA, full_bar(s), c_k, c_w, c_h, n0);
+            if (!(sk & 2)) tma_load_3d(st + 2 * A_BYTES, &mapBh, full_bar(s), c_k, nblk * BN, tapb);
+            if (!(sk & 4)) tma_load_3d(st + 2 * A_BYTES + B_BYTES, &mapBl, full_bar(s), c_k, nblk * BN, tapb);
+          }
+          DP_TRACE(1, g);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1 || warp == 10) {
+    // Two issuer warps take alternate pipeline stages.  Every tcgen05.mma / tcgen05.commit holds its uniform-register
+    // operands until the tensor queue has consumed it, so ptxas makes the issuing warp wait on that scoreboard before it
+    // may set up the next stage: a lone issuer therefore stalls until ITS stage has drained and the tensor pipe idles for
+    // the ~450 clk it then needs to poll the barrier and rebuild descriptors (profiles/r01_experiments.md, pipeline trace).
+    // With two warps one is always ahead, queueing stage g+1 behind stage g.  Queue order across the two warps is kept by
+    // the iss_bar hand-off (arrive after the stage's MMAs are issued; the other warp waits on it before issuing).
+    const uint32_t mw = (warp == 1) ? 0u : 1u;
+    const uint32_t ni = (uint32_t)p.two_issuers;   // number of issuer warps in the rotation (1 or 2)
+    const uint32_t two = ni > 1u ? 1u : 0u;
+    if (mw < ni) {
+      uint32_t g = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+        const int nblk = tile / tiles_m;
+        const int n_valid = min(BN, p.Nout - nblk * BN);
+        const uint32_t n_instr = (uint32_t)((n_valid + 15) & ~15);
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((n_instr >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        const uint32_t idesc256 = (1u << 4) | (2u << 7) | (2u << 10) | ((256u >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        const uint32_t b = tl & 1u, use = tl >> 1;
+        mbar_wait_warp(tempty_bar(b), (use & 1u) ^ 1u);          // epilogue has drained this accumulator set
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (mw == 0 && lane == 0) DP_TRACE_TILE(3, tl);
+        const uint32_t acc = tmem_base + b * 256u;
+        for (int it = 0; it < iters_per_tile; ++it, ++g) {
+          if (g % ni != mw) continue;
+          const int s = g % PS_STAGES;
+          const uint32_t ph = (g / PS_STAGES) & 1u;
+          if (lane == 0) DP_TRACE(8, g);
+          mbar_wait_warp(conv_bar(s), ph);
+          if (lane == 0) DP_TRACE(9, g);
+          if (two && g > 0) mbar_wait_warp(iss_bar((g - 1) % PS_STAGES), ((g - 1) / PS_STAGES) & 1u);
+          if (lane == 0) DP_TRACE(10, g);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t st = sbase + s * STAGE_BYTES;
+          if (elect_one()) {
+            DP_TRACE(4, g);
+            const uint64_t a_hi0 = umma_desc_ps<BKT>(st), a_lo0 = umma_desc_ps<BKT>(st + A_BYTES);
+            const uint64_t b_hi0 = umma_desc_ps<BKT>(st + 2 * A_BYTES), b_lo0 = umma_desc_ps<BKT>(st + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / 8; ++k) {   // +32 B per K step = +2 in the descriptor's 16-byte address field
+              const uint64_t a_hi = a_hi0 + 2 * k, a_lo = a_lo0 + 2 * k, b_hi = b_hi0 + 2 * k, b_lo = b_lo0 + 2 * k;
+              const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
+              if (p.wide_n) {
+                // B_hi and B_lo are adjacent 128-row tiles: ONE N=256 instruction computes a_hi x [b_hi | b_lo] into
+                // [main | correction] (acc .. acc+255); a_lo x b_hi then adds into the correction half.  Same tensor time as
+                // three N=128 instructions, but 2/3 of the instructions and 5/6 of the operand reads from shared memory.
+                umma_tf32(acc, a_hi, b_hi, idesc256, first);
+                umma_tf32(acc + 128, a_lo, b_hi, idesc, 1u);
+              } else {
+                umma_tf32(acc + 128, a_lo, b_hi, idesc, first);
+                umma_tf32(acc + 128, a_hi, b_lo, idesc, 1u);
+                umma_tf32(acc, a_hi, b_hi, idesc, first);
+              }
+            }
+            umma_commit(empty_bar(s));
+            if (it == iters_per_tile - 1) umma_commit(tfull_bar(b));
+            if (two) {
+              asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+              mbar_arrive(iss_bar(s));
+            }
+            DP_TRACE(5, g);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp < 6) {
+    // ---- splitter warps 2..5: A tile -> tf32 hi (in place) + lo (side buffer), elementwise so the swizzle is irrelevant
+    const int ct = (int)threadIdx.x - 64;
+    uint32_t g = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int it = 0; it < iters_per_tile; ++it, ++g) {
+        const int s = g % PS_STAGES;
+        const uint32_t ph = (g / PS_STAGES) & 1u;
+        mbar_wait(full_bar(s), ph);
+        if (ct == 0) DP_TRACE(2, g);
+        float4* A = reinterpret_cast<float4*>(smem + s * STAGE_BYTES);
+        float4* Al = reinterpret_cast<float4*>(smem + s * STAGE_BYTES + A_BYTES);
+#pragma unroll
+        for (int i = 0; i < A_BYTES / 16 / 128; ++i) {
+          const int idx = ct + 128 * i;
+          float4 v = A[idx], h, l;
+          h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+          l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+          A[idx] = h;
+          Al[idx] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (ct == 0) DP_TRACE(6, g);
+        mbar_arrive(conv_bar(s));
+        if ((ct & 31) == 0) DP_TRACE(12 + (ct >> 5), g);   // per-warp arrival
+      }
+    }
+  } else if (warp < 10) {
+    // ---- epilogue warps 6..9 (TMEM lane quarter = warp & 3)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const int w_l = row % p.bw, h_l = (row / p.bw) % p.bh, n_l = row / (p.bw * p.bh);
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+      int q0, p0, n0, nblk;
+      tile_coords(tile, q0, p0, n0, nblk);
+      const uint32_t b = tl & 1u, use = tl >> 1;
+      mbar_wait(tfull_bar(b), use & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (threadIdx.x == 6 * 32) DP_TRACE_TILE(0, tl);
+      const int img = n0 + n_l;
+      const bool row_ok = img < p.Nimg;
+      const long long m = ((long long)img * p.Ho + ((p0 + h_l) * p.os + p.oa)) * p.Wo + ((q0 + w_l) * p.os + p.ob);
+      float* yrow = p.y + m * p.ldy;
+      const float* rrow = p.residual ? p.residual + m * p.ld_res : nullptr;
+      const float* arow2 = p.rowadd ? p.rowadd + (long long)img * p.ld_rowadd : nullptr;
+#pragma unroll 1
+      for (int j = 0; j < BN / 32; ++j) {
+        uint32_t v[32], u[32];
+        const uint32_t taddr = tmem_base + lane_addr + b * 256u + (uint32_t)(j * 32);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr));
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+              "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
+              "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
+              "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+            : "r"(taddr + 128u));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (j == BN / 32 - 1) {   // accumulators are in registers: hand the TMEM set back to the MMA warp
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          mbar_arrive(tempty_bar(b));
+          if (threadIdx.x == 6 * 32) DP_TRACE_TILE(1, tl);
+        }
+        if (row_ok) {
+          const int c0 = nblk * BN + j * 32;
+          if (p.vec4 && c0 + 32 <= p.Nout) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              float4 o = make_float4(p.alpha * (__uint_as_float(v[i]) + __uint_as_float(u[i])), p.alpha * (__uint_as_float(v[i + 1]) + __uint_as_float(u[i + 1])),
+                                     p.alpha * (__uint_as_float(v[i + 2]) + __uint_as_float(u[i + 2])), p.alpha * (__uint_as_float(v[i + 3]) + __uint_as_float(u[i + 3])));
+              if (p.bias) { float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + i)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+              if (arow2) { float4 t = __ldg(reinterpret_cast<const float4*>(arow2 + c0 + i)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+              if (rrow) { float4 t = __ldg(reinterpret_cast<const float4*>(rrow + c0 + i)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+              float4* dst = reinterpret_cast<float4*>(yrow + c0 + i);
+              if (p.accumulate) { float4 t = *dst; o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+              *dst = o;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int c = c0 + i;
+              if (c < p.Nout) {
+                float o = p.alpha * (__uint_as_float(v[i]) + __uint_as_float(u[i]));
+                if (p.bias) o += __ldg(p.bias + c);
+                if (arow2) o += __ldg(arow2 + c);
+                if (rrow) o += __ldg(rrow + c);
+                if (p.accumulate) o += yrow[c];
+                yrow[c] = o;
+              }
+            }
+          }
+        }
+      }
+      if (threadIdx.x == 6 * 32) DP_TRACE_TILE(2, tl);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ wgrad
 // dW[k][tap][c] = sum_pix dy[pix][k] * x[pix @ tap][c]  as GEMM  M = k (128), N = c (128), K = pixels.
 // Both operands are activations stored pixel-major / channel-contiguous, i.e. "MN-major" for the tensor core:
@@ -764,6 +1301,7 @@ struct WgParams {
   int total_chunks, chunks_per_split;
   int c_tiles;
   float* ws;
+  int two_issuers, wide_n;   // DPB200_TC_ISSUERS / DPB200_TC_WIDE_N (see TcParams)
 };
 constexpr int WG_KPIX = 32, WG_T = 128 * WG_KPIX * 4;   // one operand tile = 16 KB
 
@@ -775,7 +1313,8 @@ __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | (256ull << 16) | (32ull << 32) | (1ull << 46) | (1ull << 61);
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+constexpr int WG_THREADS = 224;   // warps: 0 TMA | 1, 6 MMA issuers (alternate stages, see conv_tc_ps_kernel) | 2-5 splitters + epilogue
+__global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ CUtensorMap mapX, const WgParams p) {
   // stage smem: dy raw (16 KB, read once by the splitter) | x (hi in place, 16 KB) | x_lo (16 KB)
   // The A operand (dY^T: lane = out-channel, column = pixel) is built in TENSOR MEMORY: thread <-> out-channel reads its
@@ -795,10 +1334,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant
   auto conv_bar = [&](int s) { return bar0 + 8u * (WSTAGES + s); };
   auto empty_bar = [&](int s) { return bar0 + 8u * (2 * WSTAGES + s); };
   const uint32_t tmem_full_bar = bar0 + 8u * (3 * WSTAGES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * WSTAGES + 1);
+  auto iss_bar = [&](int s) { return bar0 + 8u * (3 * WSTAGES + 1 + s); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * WSTAGES + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < WSTAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(conv_bar(s), 128); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < WSTAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(conv_bar(s), 128); mbar_init(empty_bar(s), 1); mbar_init(iss_bar(s), 1); }
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -843,31 +1383,53 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant
         }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // B MN-major (bit 16); A comes from TMEM
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  } else if (warp == 1 || warp == 6) {
+    // two issuer warps on alternate stages, warp-converged with one elected lane (see conv_tc_ps_kernel)
+    const uint32_t mw = (warp == 1) ? 0u : 1u;
+    const uint32_t two = p.two_issuers ? 1u : 0u;
+    // B MN-major (bit 16); A comes from TMEM
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc256 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    if (num_iters == 0 && mw == 0) {   // empty split: release the epilogue (it writes zeros)
+      if (elect_one()) umma_commit(tmem_full_bar);
+      __syncwarp();
+    }
+    if (two || mw == 0) {
       for (int it = 0; it < num_iters; ++it) {
+        if (two && ((uint32_t)it & 1u) != mw) continue;
         const int s = it % WSTAGES;
         const uint32_t ph = (uint32_t)(it / WSTAGES) & 1u;
-        mbar_wait(conv_bar(s), ph);
-        mbar_wait(full_bar(s), ph);
+        mbar_wait_warp(conv_bar(s), ph);
+        mbar_wait_warp(full_bar(s), ph);
+        if (two && it > 0) mbar_wait_warp(iss_bar((it - 1) % WSTAGES), (uint32_t)((it - 1) / WSTAGES) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t st = sbase + s * STAGE_BYTES;
         const uint32_t a_t = tmem_base + 256u + 64u * s;
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < WG_KPIX / 8; ++k) {
-          const uint64_t b_hi = umma_desc_mn(st + WG_T + k * 1024), b_lo = umma_desc_mn(st + 2 * WG_T + k * 1024);
-          const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
-          umma_tf32_ts(tmem_base + 128, a_t + 32 + k * 8, b_hi, idesc, first);
-          umma_tf32_ts(tmem_base + 128, a_t + k * 8, b_lo, idesc, 1u);
-          umma_tf32_ts(tmem_base, a_t + k * 8, b_hi, idesc, first);
+          for (int k = 0; k < WG_KPIX / 8; ++k) {
+            const uint64_t b_hi = umma_desc_mn(st + WG_T + k * 1024), b_lo = umma_desc_mn(st + 2 * WG_T + k * 1024);
+            const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
+            if (p.wide_n) {   // x_hi | x_lo are adjacent 4 x 32-channel block groups: a_hi x [x_hi | x_lo] -> [main | correction]
+              umma_tf32_ts(tmem_base, a_t + k * 8, b_hi, idesc256, first);
+              umma_tf32_ts(tmem_base + 128, a_t + 32 + k * 8, b_hi, idesc, 1u);
+            } else {
+              umma_tf32_ts(tmem_base + 128, a_t + 32 + k * 8, b_hi, idesc, first);
+              umma_tf32_ts(tmem_base + 128, a_t + k * 8, b_lo, idesc, 1u);
+              umma_tf32_ts(tmem_base, a_t + k * 8, b_hi, idesc, first);
+            }
+          }
+          umma_commit(empty_bar(s));
+          if (it == num_iters - 1) umma_commit(tmem_full_bar);
+          if (two) {
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(iss_bar(s));
+          }
         }
-        umma_commit(empty_bar(s));
+        __syncwarp();
       }
-      umma_commit(tmem_full_bar);
     }
-  } else {
+  } else if (warp < 6) {
     const int tid = threadIdx.x - 64;
     const int q = warp & 3;                   // TMEM lane quarter == 32-channel block of dy
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
@@ -967,7 +1529,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn g_encode = nullptr;
 int g_tc_state = -1;  // -1 unknown, 0 unavailable, 1 ok
 bool g_use_ss = false;
-int g_persistent = 1;  // DPB200_TC_PERSISTENT=0: one tile per CTA (TS kernel) instead of the persistent kernel
+int g_persistent = 1;  // DPB200_TC_PERSISTENT: 1 = persistent SS kernel, 2 = decoupled A/B-ring TS kernel, 3 = two-issuer experimental kernel, 0 = one-ring TS kernel
+static int g_ps_bk = 32;               // DPB200_TC_PS_BK: K chunk per stage of the persistent kernel (16 -> 7 stages, 32 -> 3 stages)
+static constexpr int ps_smem_bytes(int bk) { return (bk == 16 ? 7 : 3) * 4 * 128 * bk * 4 + 2048; }
+static long long* g_trace = nullptr;   // see dp_conv_tc_set_trace
 int g_num_sms = 148;
 int g_cluster = 1;     // DPB200_TC_CLUSTER=2|4: CTAs per cluster sharing (TMA-multicasting) one weight tile.  Measured on B200
                        // (profiles/r01_experiments.md): 46.7 / 47.5 / 48.3 ms per pass for 1 / 2 / 4 -> off by default. // DPB200_TC_SS=1: keep the A operand in shared memory (SS-mode kernel) instead of TMEM (TS-mode)
@@ -997,7 +1562,11 @@ int tc_init() {
   ok = ok && cudaFuncSetAttribute(conv_tc_ts_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem64) == cudaSuccess;
   if (const char* e = getenv("DPB200_TC_CLUSTER")) g_cluster = atoi(e);
   ok = ok && cudaFuncSetAttribute(conv_tc_ps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PS_STAGES * (2 * A_BYTES + 2 * 128 * BK * 4) + 2048) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(conv_tc_ps2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ps_smem_bytes(32)) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(conv_tc_ps2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ps_smem_bytes(16)) == cudaSuccess;
+  if (const char* e = getenv("DPB200_TC_PS_BK")) g_ps_bk = atoi(e) == 32 ? 32 : 16;
   if (const char* e = getenv("DPB200_TC_PERSISTENT")) g_persistent = atoi(e);
+  ok = ok && cudaFuncSetAttribute(conv_tc_ab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SA * A_BYTES + AB_SB * 2 * 128 * BK * 4 + 2048) == cudaSuccess;
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev); }
   g_use_ss = getenv("DPB200_TC_SS") != nullptr;
   ok = ok && cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 3 * WG_T + 2048) == cudaSuccess;
@@ -1065,8 +1634,11 @@ int launch_tc(const float* act, long long ld_act, int Nimg, int H, int W, int Kg
   p.ntaps = taps.n;
   for (int i = 0; i < 9; ++i) { p.dh[i] = taps.dh[i]; p.dw[i] = taps.dw[i]; p.wt[i] = taps.wt[i]; }
   p.os = os; p.oa = oa; p.ob = ob; p.Ho = Ho; p.Wo = Wo;
-  p.alpha = alpha; p.b_from_img = b_from_img;
-  if ((alpha != 1.0f || b_from_img) && !(g_persistent && !g_use_ss && Nout > 64 && bn == 1)) return DP_ERR_UNSUPPORTED;
+  p.alpha = alpha; p.b_from_img = b_from_img; p.trace = g_trace;
+  { static const int skip = getenv("DPB200_TC_DEBUG_SKIP") ? atoi(getenv("DPB200_TC_DEBUG_SKIP")) : 0; p.dbg_skip = skip; }
+  { static const int issuers = getenv("DPB200_TC_ISSUERS") ? atoi(getenv("DPB200_TC_ISSUERS")) : 2; p.two_issuers = issuers >= 2 ? 2 : 1; }
+  { static const int wn = getenv("DPB200_TC_WIDE_N") ? atoi(getenv("DPB200_TC_WIDE_N")) : 1; p.wide_n = wn; }
+  if ((alpha != 1.0f || b_from_img) && !(g_persistent && !g_use_ss && Nout > 64 && bn == 1)) return DP_ERR_UNSUPPORTED;   // ps and ab kernels apply alpha / image-indexed B
   p.kchunks = (Kg + BK - 1) / BK;
   p.bw = bw; p.bh = bh; p.bn = bn; p.tiles_w = W / bw; p.tiles_h = H / bh;
   p.y = out; p.ldy = ld_out; p.bias = bias; p.rowadd = rowadd; p.ld_rowadd = ld_rowadd; p.residual = residual; p.ld_res = ld_res;
@@ -1078,6 +1650,38 @@ int launch_tc(const float* act, long long ld_act, int Nimg, int H, int W, int Kg
   if (g_use_ss) {
     if (BN == 64) conv_tc_kernel<64><<<grid, NTHREADS, STAGES * (2 * A_BYTES + 2 * 64 * BK * 4) + 2048, st>>>(mA, mBh, mBl, p);
     else conv_tc_kernel<128><<<grid, NTHREADS, STAGES * (2 * A_BYTES + 2 * 128 * BK * 4) + 2048, st>>>(mA, mBh, mBl, p);
+  } else if (BN == 128 && g_persistent == 2) {
+    static const int bsub = getenv("DPB200_B_SUB") ? atoi(getenv("DPB200_B_SUB")) : 1;
+    if (bsub > 1) {
+      const cuuint64_t Kg4 = (cuuint64_t)((Kg + 3) & ~3);
+      cuuint64_t dims[3] = {Kg4, (cuuint64_t)Nout, (cuuint64_t)T};
+      cuuint64_t str[2] = {Kg4 * 4, (cuuint64_t)Nout * Kg4 * 4};
+      cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)(128 / bsub), 1};
+      if (!make_map(&mBh, w_hi, 3, dims, str, box) || !make_map(&mBl, w_lo, 3, dims, str, box)) return DP_ERR_UNSUPPORTED;
+      p.b_sub = bsub;
+    }
+    conv_tc_ab_kernel<<<grid, AB_THREADS, AB_SA * A_BYTES + AB_SB * 2 * 128 * BK * 4 + 2048, st>>>(mA, mBh, mBl, p);
+  } else if (BN == 128 && g_persistent == 3) {
+    const int tiles_m = (int)grid.x, total = (int)(grid.x * grid.y);
+    const int ctas = total < g_num_sms ? total : g_num_sms;
+    if (g_ps_bk == 16) {   // 16-float K chunks: 64-byte-swizzled boxes
+      {
+        cuuint64_t dims[4] = {(cuuint64_t)Kg, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Nimg};
+        cuuint64_t str[3] = {(cuuint64_t)ld_act * 4, (cuuint64_t)W * ld_act * 4, (cuuint64_t)H * W * ld_act * 4};
+        cuuint32_t box[4] = {16, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+        if (!make_map(&mA, act, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B)) return DP_ERR_UNSUPPORTED;
+        const cuuint64_t Kg4 = (cuuint64_t)((Kg + 3) & ~3);
+        cuuint64_t bdims[3] = {Kg4, (cuuint64_t)Nout, (cuuint64_t)T};
+        cuuint64_t bstr[2] = {Kg4 * 4, (cuuint64_t)Nout * Kg4 * 4};
+        cuuint32_t bbox[3] = {16, 128, 1};
+        if (!make_map(&mBh, w_hi, 3, bdims, bstr, bbox, CU_TENSOR_MAP_SWIZZLE_64B) ||
+            !make_map(&mBl, w_lo, 3, bdims, bstr, bbox, CU_TENSOR_MAP_SWIZZLE_64B)) return DP_ERR_UNSUPPORTED;
+      }
+      p.kchunks = (Kg + 15) / 16;
+      conv_tc_ps2_kernel<16><<<ctas, PS2_THREADS, ps_smem_bytes(16), st>>>(mA, mBh, mBl, p, tiles_m, total);
+    } else {
+      conv_tc_ps2_kernel<32><<<ctas, PS2_THREADS, ps_smem_bytes(32), st>>>(mA, mBh, mBl, p, tiles_m, total);
+    }
   } else if (BN == 128 && g_persistent) {
     const int tiles_m = (int)grid.x, total = (int)(grid.x * grid.y);
     const int ctas = total < g_num_sms ? total : g_num_sms;
@@ -1318,7 +1922,9 @@ int dp_conv2d_wgrad_tc(const dp_conv_args* a, dp_stream_t stream) {
   p.ws = a->workspace;
   const int k_tiles = (a->K + 127) / 128;
   dim3 grid((unsigned)(k_tiles * p.c_tiles * a->R * a->S), (unsigned)a->splits);
-  wgrad_tc_kernel<<<grid, NTHREADS, 4 * 3 * WG_T + 2048, (cudaStream_t)stream>>>(mDy, mX, p);
+  { static const int issuers = getenv("DPB200_TC_ISSUERS") ? atoi(getenv("DPB200_TC_ISSUERS")) : 2; p.two_issuers = issuers >= 2; }
+  { static const int wn = getenv("DPB200_TC_WIDE_N") ? atoi(getenv("DPB200_TC_WIDE_N")) : 1; p.wide_n = wn; }
+  wgrad_tc_kernel<<<grid, WG_THREADS, 4 * 3 * WG_T + 2048, (cudaStream_t)stream>>>(mDy, mX, p);
   return dp_check_launch();
 }
 
@@ -1332,3 +1938,8 @@ extern "C" int dp_pack_conv_weight_tc(const float* w, int32_t K, int32_t C, int3
   pack_tc_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, K, C, R * S, kc_hi, kc_lo, ck_hi, ck_lo);
   return dp_check_launch();
 }
+
+// Debug hook: CTA 0 of every following persistent conv launch stamps clock64() into buf[stage*8 + slot] for its first 1024 pipeline
+// stages (slots: 0 producer woke on "empty", 1 TMA issued, 2 splitter woke on "full", 6 split+fence done, 3 splitter arrived,
+// 4 MMA lane woke on "converted", 5 MMAs + commit issued).  nullptr switches it off.  buf must hold 16640 int64 (16 slots per stage; 8..10: issuer at loop top / after the "converted" wait / after the hand-off wait) (the last 256: per tile, epilogue woke / released TMEM / done, issuer got the accumulator).
+extern "C" int dp_conv_tc_set_trace(long long* buf) { g_trace = buf; return 0; }
