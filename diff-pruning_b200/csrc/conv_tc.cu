@@ -98,6 +98,13 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 }
 // warp-converged single-lane election (elect.sync): lets ptxas keep descriptors / barrier addresses in UNIFORM registers and emit
 // straight-line UTCHMMA / UTMALDG; a plain `if (lane == 0)` makes it wrap every such instruction in an ELECT / BRA.U.ANY loop.
+// the N=256 fused hi-product instruction is compiled in unconditionally (-DDPB200_RUNTIME_WIDE_N restores the DPB200_TC_WIDE_N=0|1
+// run-time switch; the extra code path costs ~0.7 % of the C1 pass)
+#ifdef DPB200_RUNTIME_WIDE_N
+#define DP_WIDE_N(p) ((p).wide_n != 0)
+#else
+#define DP_WIDE_N(p) true
+#endif
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
@@ -873,7 +880,7 @@ conv_tc_ps_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             const uint64_t a_hi = umma_desc(st + k * 32), a_lo = umma_desc(st + A_BYTES + k * 32);
             const uint64_t b_hi = umma_desc(st + 2 * A_BYTES + k * 32), b_lo = umma_desc(st + 2 * A_BYTES + B_BYTES + k * 32);
             const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
-            if (p.wide_n) {   // a_hi x [b_hi | b_lo] -> [main | correction] as ONE N=256 instruction (the two B tiles are adjacent)
+            if (DP_WIDE_N(p)) {   // a_hi x [b_hi | b_lo] -> [main | correction] as ONE N=256 instruction (the two B tiles are adjacent)
               umma_tf32(acc, a_hi, b_hi, idesc256, first);
               umma_tf32(acc + 128, a_lo, b_hi, idesc, 1u);
             } else {
@@ -1147,7 +1154,7 @@ conv_tc_ps2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
             for (int k = 0; k < BK / 8; ++k) {   // +32 B per K step = +2 in the descriptor's 16-byte address field
               const uint64_t a_hi = a_hi0 + 2 * k, a_lo = a_lo0 + 2 * k, b_hi = b_hi0 + 2 * k, b_lo = b_lo0 + 2 * k;
               const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
-              if (p.wide_n) {
+              if (DP_WIDE_N(p)) {
                 // B_hi and B_lo are adjacent 128-row tiles: ONE N=256 instruction computes a_hi x [b_hi | b_lo] into
                 // [main | correction] (acc .. acc+255); a_lo x b_hi then adds into the correction half.  Same tensor time as
                 // three N=128 instructions, but 2/3 of the instructions and 5/6 of the operand reads from shared memory.
@@ -1410,7 +1417,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant
           for (int k = 0; k < WG_KPIX / 8; ++k) {
             const uint64_t b_hi = umma_desc_mn(st + WG_T + k * 1024), b_lo = umma_desc_mn(st + 2 * WG_T + k * 1024);
             const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
-            if (p.wide_n) {   // x_hi | x_lo are adjacent 4 x 32-channel block groups: a_hi x [x_hi | x_lo] -> [main | correction]
+            if (DP_WIDE_N(p)) {   // x_hi | x_lo are adjacent 4 x 32-channel block groups: a_hi x [x_hi | x_lo] -> [main | correction]
               umma_tf32_ts(tmem_base, a_t + k * 8, b_hi, idesc256, first);
               umma_tf32_ts(tmem_base + 128, a_t + 32 + k * 8, b_hi, idesc, 1u);
             } else {

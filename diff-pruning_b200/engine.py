@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
@@ -29,6 +30,28 @@ from .models import (Attention, Downsample2D, ResnetBlock2D, UNet2DModel, Upsamp
 
 _byref = C.byref
 Step = Callable[[int], None]
+
+
+_SM_COUNT = 148            # B200; the wgrad kernel runs one CTA per SM (192 KB of shared memory)
+_WGRAD_CTA_OVERHEAD = 12   # per-CTA prologue + pipeline fill + TMEM->workspace epilogue, in units of one 32-pixel stage
+
+
+def _wgrad_splits(tiles, chunks, env=os.environ.get("DPB200_WGRAD_WAVES")):
+    """Split-K factor of the tensor-core wgrad: grid = tiles x splits CTAs, each walking ceil(chunks / splits) pixel chunks.
+    One CTA per SM, so the launch runs in ceil(grid / 148) strict waves: pick the split count whose modelled time
+    waves x (overhead + chunks per CTA) is smallest, never overshooting a wave boundary by a few CTAs (592 -> 594 CTAs
+    used to cost a fifth, almost empty, wave) and never leaving a trailing split empty."""
+    best = None
+    max_waves = int(env) if env else 4
+    for waves in range(1, max_waves + 1):
+        sp = max(1, min((waves * _SM_COUNT) // tiles, chunks))
+        cps = -(-chunks // sp)
+        sp = -(-chunks // cps)                       # drop empty trailing splits
+        w = -(-(tiles * sp) // _SM_COUNT)
+        cost = w * (_WGRAD_CTA_OVERHEAD + cps)
+        if best is None or cost < best[0]:
+            best = (cost, sp)
+    return best[1]
 
 
 def _stream() -> int:
@@ -307,9 +330,8 @@ class Plan:
         # 2. wgrad -> split-K workspace -> fixed-order reduce into Parameter.grad
         TC = R * S * Cin
         tiles = ((K + 127) // 128) * ((TC + 127) // 128)
-        splits = max(1, min((592 + tiles - 1) // tiles, (out.rows + 511) // 512))
-        chunks = max(1, out.rows // 32)              # tensor-core wgrad walks 32-pixel chunks: avoid empty trailing splits
-        splits = -(-chunks // -(-chunks // splits)) if splits <= chunks else splits
+        chunks = max(1, out.rows // 32)              # tensor-core wgrad walks 32-pixel chunks
+        splits = _wgrad_splits(tiles, chunks)
         self.scratch("wgrad_ws", splits * K * TC)
         wa = _copy_args(a)
         wa.flags, wa.splits = 0, splits
