@@ -38,6 +38,7 @@ struct TcParams {
   int ntaps;
   signed char dh[9], dw[9], wt[9];
   int os, oa, ob, Ho, Wo;   // output pixel = (p*os + oa, q*os + ob) on an [Ho][Wo] grid
+  int in_stride;            // strided fprop: input pixel = in_stride * output pixel + tap offset (the A map traverses W, H with that stride)
   float alpha;              // epilogue scale of the accumulator (attention logits); 1 for convolutions
   int b_from_img;           // batched GEMM: the B tile index is the tile's image (bn == 1) instead of a filter tap
   int two_issuers;          // persistent kernel: number of MMA-issuing warps taking alternate pipeline stages (DPB200_TC_ISSUERS=1|2)
@@ -849,7 +850,7 @@ conv_tc_ps_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           mbar_expect_tx(full_bar(s), A_BYTES + 2 * B_BYTES);
           const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
           const uint32_t st = sbase + s * STAGE_BYTES;
-          tma_load_4d(st, &mapA, full_bar(s), kc * BK, q0 + p.dw[tap], p0 + p.dh[tap], n0);
+          tma_load_4d(st, &mapA, full_bar(s), kc * BK, q0 * p.in_stride + p.dw[tap], p0 * p.in_stride + p.dh[tap], n0);
           const int tapb = p.b_from_img ? n0 : p.wt[tap];
           tma_load_3d(st + 2 * A_BYTES, &mapBh, full_bar(s), kc * BK, nblk * BN, tapb);
           tma_load_3d(st + 2 * A_BYTES + B_BYTES, &mapBl, full_bar(s), kc * BK, nblk * BN, tapb);
@@ -1309,6 +1310,7 @@ struct WgParams {
   int c_tiles;
   float* ws;
   int two_issuers, wide_n;   // DPB200_TC_ISSUERS / DPB200_TC_WIDE_N (see TcParams)
+  int in_stride;             // x pixel = in_stride * dy pixel + tap offset
 };
 constexpr int WG_KPIX = 32, WG_T = 128 * WG_KPIX * 4;   // one operand tile = 16 KB
 
@@ -1386,7 +1388,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant
 #pragma unroll
         for (int b = 0; b < 4; ++b) {   // 4 blocks of 32 channels = 128 channels per operand
           tma_load_4d(st + b * 4096, &mapDy, full_bar(s), kt * 128 + b * 32, q0, p0, n0);
-          tma_load_4d(st + WG_T + b * 4096, &mapX, full_bar(s), ct * 128 + b * 32, q0 + sx - p.pad, p0 + r - p.pad, n0);
+          tma_load_4d(st + WG_T + b * 4096, &mapX, full_bar(s), ct * 128 + b * 32, q0 * p.in_stride + sx - p.pad, p0 * p.in_stride + r - p.pad, n0);
         }
       }
     }
@@ -1582,9 +1584,11 @@ int tc_init() {
   return 1;
 }
 
+// pix_stride > 1 (strided convolution): dims 1 and 2 (W, H) are traversed with that element stride; the caller passes the box
+// extents in traversed elements (box = loaded pixels x pix_stride)
 bool make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-              const cuuint32_t* box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+              const cuuint32_t* box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, int pix_stride = 1) {
+  cuuint32_t estr[5] = {1, (cuuint32_t)pix_stride, (cuuint32_t)pix_stride, 1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1615,7 +1619,7 @@ struct TapTable { int n; signed char dh[9], dw[9], wt[9]; };
 int launch_tc(const float* act, long long ld_act, int Nimg, int H, int W, int Kg, const float* w_hi, const float* w_lo, int Nout,
               int T, const TapTable& taps, int os, int oa, int ob, int Ho, int Wo, float* out, long long ld_out, const float* bias,
               const float* rowadd, long long ld_rowadd, const float* residual, long long ld_res, int accumulate, cudaStream_t st,
-              float alpha = 1.0f, int b_from_img = 0) {
+              float alpha = 1.0f, int b_from_img = 0, int in_stride = 1) {
   if (!tc_init()) return DP_ERR_UNSUPPORTED;
   if (!w_hi || !w_lo) return DP_ERR_UNSUPPORTED;
   if (ld_act % 4 || ((uintptr_t)act & 15) || ((uintptr_t)w_hi & 15) || ((uintptr_t)w_lo & 15)) return DP_ERR_UNSUPPORTED;
@@ -1623,12 +1627,17 @@ int launch_tc(const float* act, long long ld_act, int Nimg, int H, int W, int Kg
   if (!pick_box(Nimg, H, W, bw, bh, bn)) return DP_ERR_UNSUPPORTED;
   CUtensorMap mA, mBh, mBl;
   {
-    cuuint64_t dims[4] = {(cuuint64_t)Kg, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Nimg};
-    cuuint64_t str[3] = {(cuuint64_t)ld_act * 4, (cuuint64_t)W * ld_act * 4, (cuuint64_t)H * W * ld_act * 4};
-    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
-    if (!make_map(&mA, act, 4, dims, str, box)) return DP_ERR_UNSUPPORTED;
+    // strided fprop: the M tiles live on the OUTPUT grid [H][W]; the activation is [H*in_stride][W*in_stride] and the box picks every
+    // in_stride-th pixel (TMA element strides), so a tile is still one 128-pixel box
+    const cuuint64_t Hin = (cuuint64_t)H * in_stride, Win = (cuuint64_t)W * in_stride;
+    cuuint64_t dims[4] = {(cuuint64_t)Kg, Win, Hin, (cuuint64_t)Nimg};
+    cuuint64_t str[3] = {(cuuint64_t)ld_act * 4, Win * ld_act * 4, Hin * Win * ld_act * 4};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(bw * in_stride), (cuuint32_t)(bh * in_stride), (cuuint32_t)bn};
+    if (box[1] > 256 || box[2] > 256) return DP_ERR_UNSUPPORTED;
+    if (!make_map(&mA, act, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, in_stride)) return DP_ERR_UNSUPPORTED;
   }
   const int BN = (Nout <= 64) ? 64 : 128;
+  if (in_stride != 1 && !(BN == 128 && g_persistent == 1 && !g_use_ss)) return DP_ERR_UNSUPPORTED;   // only the default persistent kernel scales the tile origin
   {
     const cuuint64_t Kg4 = (cuuint64_t)((Kg + 3) & ~3);   // dp_pack_conv_weight_tc pads rows to 16 B
     cuuint64_t dims[3] = {Kg4, (cuuint64_t)Nout, (cuuint64_t)T};
@@ -1641,7 +1650,7 @@ int launch_tc(const float* act, long long ld_act, int Nimg, int H, int W, int Kg
   p.ntaps = taps.n;
   for (int i = 0; i < 9; ++i) { p.dh[i] = taps.dh[i]; p.dw[i] = taps.dw[i]; p.wt[i] = taps.wt[i]; }
   p.os = os; p.oa = oa; p.ob = ob; p.Ho = Ho; p.Wo = Wo;
-  p.alpha = alpha; p.b_from_img = b_from_img; p.trace = g_trace;
+  p.alpha = alpha; p.b_from_img = b_from_img; p.trace = g_trace; p.in_stride = in_stride;
   { static const int skip = getenv("DPB200_TC_DEBUG_SKIP") ? atoi(getenv("DPB200_TC_DEBUG_SKIP")) : 0; p.dbg_skip = skip; }
   { static const int issuers = getenv("DPB200_TC_ISSUERS") ? atoi(getenv("DPB200_TC_ISSUERS")) : 2; p.two_issuers = issuers >= 2 ? 2 : 1; }
   { static const int wn = getenv("DPB200_TC_WIDE_N") ? atoi(getenv("DPB200_TC_WIDE_N")) : 1; p.wide_n = wn; }
@@ -1840,12 +1849,15 @@ static TapTable dense_taps(int R, int S, int pad, bool flip) {
 
 int dp_conv2d_fprop_tc(const dp_conv_args* a, dp_stream_t stream) {
   if (!a || !a->x || !a->y) return DP_ERR_UNSUPPORTED;   // let the SIMT entry produce the precise error
-  if (a->stride != 1 || a->R != a->S || (a->R != 1 && a->R != 3) || a->pad_t != (a->R - 1) / 2 || a->pad_l != a->pad_t) return DP_ERR_UNSUPPORTED;
-  if (a->P != a->H || a->Q != a->W) return DP_ERR_UNSUPPORTED;
+  if (a->R != a->S || (a->R != 1 && a->R != 3) || a->pad_l != a->pad_t) return DP_ERR_UNSUPPORTED;
+  // stride 1: 'same' padding.  stride 2: 3x3 with pad 1, or pad 0 + the (0,1,0,1) zero border of Downsample2D (resnet.py:213-218) which
+  // TMA out-of-bounds zero fill provides for free
+  if (!((a->stride == 1 && a->pad_t == (a->R - 1) / 2) || (a->stride == 2 && a->R == 3 && (a->pad_t == 0 || a->pad_t == 1)))) return DP_ERR_UNSUPPORTED;
+  if (a->P * a->stride != a->H || a->Q * a->stride != a->W) return DP_ERR_UNSUPPORTED;   // stride 2: even extents, out = in / 2 (Downsample2D, pad 1)
   if (a->N <= 0 || a->H <= 0 || a->W <= 0 || a->C <= 0 || a->K <= 0 || a->ldx < a->C || a->ldy < a->K) return DP_ERR_UNSUPPORTED;
-  return launch_tc((const float*)a->x, a->ldx, a->N, a->H, a->W, a->C, a->w_tc_hi, a->w_tc_lo, a->K, a->R * a->S,
-                   dense_taps(a->R, a->S, a->pad_t, false), 1, 0, 0, a->H, a->W, (float*)a->y, a->ldy, a->bias, a->rowadd,
-                   a->ld_rowadd, a->residual, a->ld_res, (a->flags & DP_CONV_ACCUMULATE) ? 1 : 0, (cudaStream_t)stream);
+  return launch_tc((const float*)a->x, a->ldx, a->N, a->P, a->Q, a->C, a->w_tc_hi, a->w_tc_lo, a->K, a->R * a->S,
+                   dense_taps(a->R, a->S, a->pad_t, false), 1, 0, 0, a->P, a->Q, (float*)a->y, a->ldy, a->bias, a->rowadd,
+                   a->ld_rowadd, a->residual, a->ld_res, (a->flags & DP_CONV_ACCUMULATE) ? 1 : 0, (cudaStream_t)stream, 1.0f, 0, a->stride);
 }
 
 // stride-1 dgrad == fprop of dy with the taps flipped and the (K,C) roles swapped: dx[n,h,w,c] = sum dy[n,h+1-r,w+1-s,k] W[k,c,r,s].
@@ -1901,28 +1913,31 @@ static bool pick_box32(int H, int W, int& bw, int& bh, int& bn) {
 int dp_conv2d_wgrad_tc(const dp_conv_args* a, dp_stream_t stream) {
   if (!a || !a->x || !a->y || !a->workspace) return DP_ERR_UNSUPPORTED;
   if (!tc_init()) return DP_ERR_UNSUPPORTED;
-  if (a->stride != 1 || a->R != a->S || (a->R != 1 && a->R != 3) || a->pad_t != (a->R - 1) / 2 || a->pad_l != a->pad_t) return DP_ERR_UNSUPPORTED;
-  if (a->P != a->H || a->Q != a->W || a->splits < 1) return DP_ERR_UNSUPPORTED;
+  if (a->R != a->S || (a->R != 1 && a->R != 3) || a->pad_l != a->pad_t) return DP_ERR_UNSUPPORTED;
+  // stride 1: 'same' padding.  stride 2: 3x3 with pad 1, or pad 0 + the (0,1,0,1) zero border of Downsample2D (resnet.py:213-218) which
+  // TMA out-of-bounds zero fill provides for free
+  if (!((a->stride == 1 && a->pad_t == (a->R - 1) / 2) || (a->stride == 2 && a->R == 3 && (a->pad_t == 0 || a->pad_t == 1)))) return DP_ERR_UNSUPPORTED;
+  if (a->P * a->stride != a->H || a->Q * a->stride != a->W || a->splits < 1) return DP_ERR_UNSUPPORTED;
   if (a->ldx % 4 || a->ldy % 4 || ((uintptr_t)a->x & 15) || ((uintptr_t)a->y & 15)) return DP_ERR_UNSUPPORTED;
   int bw, bh, bn;
-  if (!pick_box32(a->H, a->W, bw, bh, bn)) return DP_ERR_UNSUPPORTED;
+  if (!pick_box32(a->P, a->Q, bw, bh, bn)) return DP_ERR_UNSUPPORTED;   // 32-pixel chunks of the dy (output) grid
   if (a->N % bn) return DP_ERR_UNSUPPORTED;   // a partial image box would be fine (OOB zero) but keep chunks exact
   CUtensorMap mDy, mX;
   {
-    cuuint64_t dims[4] = {(cuuint64_t)a->K, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->N};
-    cuuint64_t str[3] = {(cuuint64_t)a->ldy * 4, (cuuint64_t)a->W * a->ldy * 4, (cuuint64_t)a->H * a->W * a->ldy * 4};
+    cuuint64_t dims[4] = {(cuuint64_t)a->K, (cuuint64_t)a->Q, (cuuint64_t)a->P, (cuuint64_t)a->N};
+    cuuint64_t str[3] = {(cuuint64_t)a->ldy * 4, (cuuint64_t)a->Q * a->ldy * 4, (cuuint64_t)a->P * a->Q * a->ldy * 4};
     cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
     if (!make_map(&mDy, a->y, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return DP_ERR_UNSUPPORTED;
   }
-  {
+  {   // x is sampled at stride * (output pixel) + tap offset: TMA element strides on W, H
     cuuint64_t dims[4] = {(cuuint64_t)a->C, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->N};
     cuuint64_t str[3] = {(cuuint64_t)a->ldx * 4, (cuuint64_t)a->W * a->ldx * 4, (cuuint64_t)a->H * a->W * a->ldx * 4};
-    cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
-    if (!make_map(&mX, a->x, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return DP_ERR_UNSUPPORTED;
+    cuuint32_t box[4] = {32, (cuuint32_t)(bw * a->stride), (cuuint32_t)(bh * a->stride), (cuuint32_t)bn};
+    if (!make_map(&mX, a->x, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, a->stride)) return DP_ERR_UNSUPPORTED;
   }
   WgParams p{};
-  p.Nimg = a->N; p.H = a->H; p.W = a->W; p.C = a->C; p.K = a->K; p.R = a->R; p.S = a->S; p.pad = a->pad_t;
-  p.bw = bw; p.bh = bh; p.bn = bn; p.tiles_w = a->W / bw; p.tiles_h = a->H / bh;
+  p.Nimg = a->N; p.H = a->P; p.W = a->Q; p.C = a->C; p.K = a->K; p.R = a->R; p.S = a->S; p.pad = a->pad_t; p.in_stride = a->stride;
+  p.bw = bw; p.bh = bh; p.bn = bn; p.tiles_w = a->Q / bw; p.tiles_h = a->P / bh;
   p.total_chunks = p.tiles_w * p.tiles_h * (a->N / bn);
   p.chunks_per_split = (p.total_chunks + a->splits - 1) / a->splits;
   p.c_tiles = (a->C + 127) / 128;

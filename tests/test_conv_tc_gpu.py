@@ -182,6 +182,57 @@ def test_stride2_dgrad_parity_classes(lib, N, Cin, H, K):
     assert rel_err(nchw(gx), 2 * x.grad) < 1.5e-5
 
 
+@pytest.mark.parametrize("N,Cin,H,K,pad", [(2, 64, 16, 128, 0), (4, 128, 8, 96, 0), (1, 32, 32, 160, 1), (8, 256, 8, 256, 0)])
+def test_stride2_fprop_wgrad_tc(lib, N, Cin, H, K, pad):
+    """Downsample2D forward + weight gradient (stride 2; pad 0 with the (0,1,0,1) border folded into TMA zero fill, or pad 1)
+    on the tensor-core kernels: the activation boxes are fetched with TMA element strides (2, 2)."""
+    from diff_pruning_b200 import _lib as L
+    g = torch.Generator().manual_seed(N + Cin + pad)
+    x = torch.randn(N, Cin, H, H, generator=g)
+    w = (torch.randn(K, Cin, 3, 3, generator=g) / math.sqrt(Cin * 9)).requires_grad_(True)
+    b = torch.randn(K, generator=g)
+    xin = F.pad(x, (0, 1, 0, 1)) if pad == 0 else x
+    y = F.conv2d(xin, w, b, stride=2, padding=pad)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    P = H // 2
+    assert y.shape[-1] == P
+    wd = w.detach().contiguous().cuda()
+    packs = [torch.empty(w.numel(), device="cuda") for _ in range(4)]
+    assert lib.dp_pack_conv_weight_tc(wd.data_ptr(), K, Cin, 3, 3, *[p.data_ptr() for p in packs], S()) == 0
+    ck, kc = torch.empty(w.numel(), device="cuda"), torch.empty(w.numel(), device="cuda")
+    assert lib.dp_pack_conv_weight(wd.data_ptr(), K, Cin, 3, 3, ck.data_ptr(), kc.data_ptr(), S()) == 0
+    xd, gyd, bd = nhwc(x), nhwc(gy), b.cuda()
+    yd = torch.full((N, P, P, K), float("nan"), device="cuda")
+    a = L.ConvArgs()
+    a.N, a.H, a.W, a.C, a.P, a.Q, a.K = N, H, H, Cin, P, P, K
+    a.R = a.S = 3
+    a.stride, a.pad_t, a.pad_l, a.splits = 2, pad, pad, 1
+    a.x, a.ldx, a.y, a.ldy = xd.data_ptr(), Cin, yd.data_ptr(), K
+    a.w, a.w_tc_hi, a.w_tc_lo, a.bias = ck.data_ptr(), packs[0].data_ptr(), packs[1].data_ptr(), bd.data_ptr()
+    assert lib.dp_conv2d_fprop(C.byref(a), S()) == 0
+    assert rel_err(nchw(yd), y.detach()) < 1.5e-5
+    y2 = torch.empty_like(yd)                      # the SIMT path (exact fp32) agrees
+    a2 = L.ConvArgs()
+    C.memmove(C.byref(a2), C.byref(a), C.sizeof(a))
+    a2.flags, a2.y = 2, y2.data_ptr()
+    assert lib.dp_conv2d_fprop(C.byref(a2), S()) == 0
+    assert rel_err(yd, y2) < 1.5e-5
+    chunks = N * P * P // 32
+    for splits in sorted({1, min(3, chunks)}):
+        ws = torch.full((splits * K * 9 * Cin,), float("nan"), device="cuda")
+        wg = L.ConvArgs()
+        C.memmove(C.byref(wg), C.byref(a), C.sizeof(a))
+        wg.flags, wg.splits, wg.y, wg.ldy, wg.workspace, wg.bias = 0, splits, gyd.data_ptr(), K, ws.data_ptr(), None
+        assert lib.dp_conv2d_wgrad(C.byref(wg), S()) == 0
+        dw = torch.zeros(K, Cin, 3, 3, device="cuda")
+        r = L.WgradReduceArgs()
+        r.K, r.C, r.R, r.S, r.splits = K, Cin, 3, 3, splits
+        r.workspace, r.dw = ws.data_ptr(), dw.data_ptr()
+        assert lib.dp_conv2d_wgrad_reduce(C.byref(r), S()) == 0
+        assert rel_err(dw.cpu(), w.grad) < 1.5e-5
+
+
 @pytest.mark.parametrize("N,H,W,Kg,Nn", [(3, 16, 16, 256, 256), (2, 16, 16, 179, 256), (2, 16, 16, 256, 179), (2, 8, 16, 64, 128)])
 def test_attention_nt_gemm_tc(lib, N, H, W, Kg, Nn):
     """dp_gemm_nt_tc + dp_split_tf32 (+transpose) vs torch.bmm: C = alpha * A B^T per image, and the transposed-split form."""
