@@ -190,18 +190,19 @@ __global__ void __launch_bounds__(NT) gn_bwd_finalize_kernel(const dp_gn_args a,
   }
 }
 
-__global__ void __launch_bounds__(256) gn_bwd_param_kernel(const dp_gn_args a, const float* __restrict__ fin) {
-  // block = 32 channels x 8 image lanes; fixed-order tree over the lanes (deterministic), coalesced 128-byte rows
-  __shared__ double sb[8][32], sg[8][32];
+__global__ void __launch_bounds__(1024) gn_bwd_param_kernel(const dp_gn_args a, const float* __restrict__ fin) {
+  // block = 32 channels x 32 image lanes; fixed-order tree over the lanes (deterministic), coalesced 128-byte rows.  The grid is
+  // only C/32 blocks, so the per-lane serial walk over images is the critical path: 32 lanes keep it at N/32 dependent loads.
+  __shared__ double sb[32][33], sg[32][33];
   const int cx = threadIdx.x & 31, ly = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
   double tb = 0, tg = 0;
   if (c < a.C)
-    for (int n = ly; n < a.N; n += 8) { tb += fin[((long long)n * 2) * a.C + c]; tg += fin[((long long)n * 2 + 1) * a.C + c]; }
+    for (int n = ly; n < a.N; n += 32) { tb += fin[((long long)n * 2) * a.C + c]; tg += fin[((long long)n * 2 + 1) * a.C + c]; }
   sb[ly][cx] = tb; sg[ly][cx] = tg;
   __syncthreads();
   if (ly == 0 && c < a.C) {
-    for (int l = 1; l < 8; ++l) { tb += sb[l][cx]; tg += sg[l][cx]; }
+    for (int l = 1; l < 32; ++l) { tb += sb[l][cx]; tg += sg[l][cx]; }
     if (a.dbeta) a.dbeta[c] += (float)tb;
     if (a.dgamma) a.dgamma[c] += (float)tg;
   }
@@ -460,7 +461,7 @@ extern "C" int dp_groupnorm_bwd(const dp_gn_args* a, dp_stream_t stream) {
   gn_bwd_finalize_kernel<<<a->N, NT, 2 * a->C * sizeof(float), st>>>(*a, mp, part, fin, coef);
   if ((rc = dp_check_launch())) return rc;
   if (a->dgamma || a->dbeta) {
-    gn_bwd_param_kernel<<<(a->C + 31) / 32, 256, 0, st>>>(*a, fin);
+    gn_bwd_param_kernel<<<(a->C + 31) / 32, 1024, 0, st>>>(*a, fin);
     if ((rc = dp_check_launch())) return rc;
   }
   if (v4) gn_bwd_apply4_kernel<<<grid, NT, 0, st>>>(*a, mp, coef);
