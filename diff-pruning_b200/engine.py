@@ -39,16 +39,16 @@ _WGRAD_CTA_OVERHEAD = 12   # per-CTA prologue + pipeline fill + TMEM->workspace 
 def _wgrad_splits(tiles, chunks, env=os.environ.get("DPB200_WGRAD_WAVES")):
     """Split-K factor of the tensor-core wgrad: grid = tiles x splits CTAs, each walking ceil(chunks / splits) pixel chunks.
     One CTA per SM, so the launch runs in ceil(grid / 148) strict waves: pick the split count whose modelled time
-    waves x (overhead + chunks per CTA) is smallest, never overshooting a wave boundary by a few CTAs (592 -> 594 CTAs
-    used to cost a fifth, almost empty, wave) and never leaving a trailing split empty."""
+    waves x (overhead + chunks per CTA) is smallest (ties: fewer splits = smaller workspace), so a grid never overshoots a
+    wave boundary by a few CTAs (592 -> 594 CTAs used to cost a fifth, almost empty, wave) and no trailing split is empty."""
+    max_waves = int(env) if env else 8
+    hi = max(1, min(chunks, max(2, (max_waves * _SM_COUNT) // tiles)))
     best = None
-    max_waves = int(env) if env else 4
-    for waves in range(1, max_waves + 1):
-        sp = max(1, min((waves * _SM_COUNT) // tiles, chunks))
+    for sp in range(1, hi + 1):
         cps = -(-chunks // sp)
-        sp = -(-chunks // cps)                       # drop empty trailing splits
-        w = -(-(tiles * sp) // _SM_COUNT)
-        cost = w * (_WGRAD_CTA_OVERHEAD + cps)
+        if cps * (sp - 1) >= chunks:                 # would leave the last split empty: same as a smaller split count
+            continue
+        cost = -(-(tiles * sp) // _SM_COUNT) * (_WGRAD_CTA_OVERHEAD + cps)
         if best is None or cost < best[0]:
             best = (cost, sp)
     return best[1]

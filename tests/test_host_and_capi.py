@@ -97,3 +97,26 @@ def test_ddim_timesteps_host_logic():
         assert torch.equal(s.timesteps, G[name]["timesteps"])
     s = DDIMScheduler.from_config(dp.DDPMScheduler(num_train_timesteps=1000).config)
     assert s.config.clip_sample and s.skip_type == "uniform"
+
+
+def test_wgrad_split_count_respects_wave_boundaries():
+    """engine._wgrad_splits: the tensor-core wgrad runs one CTA per SM, so tiles x splits must not spill a few CTAs into an
+    extra wave (the 592 -> 594 CTA bug), every split must be non-empty, and the modelled cost must beat the old rule."""
+    import diff_pruning_b200  # noqa: F401
+    from diff_pruning_b200.engine import _wgrad_splits, _SM_COUNT, _WGRAD_CTA_OVERHEAD
+    cases = [(9, 4096), (36, 1024), (144, 256), (54, 1024), (72, 1024), (4, 1024), (1, 4096), (144, 64), (18, 4096), (7, 4096),
+             (1, 1), (300, 64), (2, 3)]
+    for tiles, chunks in cases:
+        sp = _wgrad_splits(tiles, chunks)
+        assert 1 <= sp <= chunks
+        cps = -(-chunks // sp)
+        assert cps * (sp - 1) < chunks, (tiles, chunks, sp)          # last split non-empty
+        ctas = tiles * sp
+        waves = -(-ctas // _SM_COUNT)
+        if tiles <= _SM_COUNT:
+            # the last wave is not a near-empty straggler: either one wave, or the grid fills >= 80 % of its waves
+            assert waves == 1 or ctas >= 0.8 * waves * _SM_COUNT, (tiles, chunks, sp, ctas)
+        old = max(1, min((592 + tiles - 1) // tiles, (chunks * 32 + 511) // 512))
+        old = -(-chunks // -(-chunks // old)) if old <= chunks else old
+        cost = lambda s: -(-(tiles * s) // _SM_COUNT) * (_WGRAD_CTA_OVERHEAD + -(-chunks // s))
+        assert cost(sp) <= cost(min(old, chunks)), (tiles, chunks, sp, old)
