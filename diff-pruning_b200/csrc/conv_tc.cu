@@ -1541,6 +1541,14 @@ bool g_use_ss = false;
 int g_persistent = 1;  // DPB200_TC_PERSISTENT: 1 = persistent SS kernel, 2 = decoupled A/B-ring TS kernel, 3 = two-issuer experimental kernel, 0 = one-ring TS kernel
 static int g_ps_bk = 32;               // DPB200_TC_PS_BK: K chunk per stage of the persistent kernel (16 -> 7 stages, 32 -> 3 stages)
 static constexpr int ps_smem_bytes(int bk) { return (bk == 16 ? 7 : 3) * 4 * 128 * bk * 4 + 2048; }
+// Row length of the packed TF32 weight tiles (dp_pack_conv_weight_tc): rows longer than 32 floats are zero-padded to a multiple of 32
+// floats (128 B) so that every 32-float TMA box row is exactly one aligned 128-byte line; short rows to a multiple of 4 (the TMA
+// 16-byte stride rule).  With 16-byte padding only, pruned widths (90 / 179 input channels) ran 20-25 % slower than the next
+// multiple of 32 (scripts/time_conv_shapes.py: 90 -> 90 3x3 @32x32 167 us vs 134 us).  DPB200_WROW_PAD=4 restores the old layout.
+static int wrow(int c) {
+  static const int pad = getenv("DPB200_WROW_PAD") ? atoi(getenv("DPB200_WROW_PAD")) : 32;
+  return (pad == 32 && c > 32) ? ((c + 31) & ~31) : ((c + 3) & ~3);
+}
 static long long* g_trace = nullptr;   // see dp_conv_tc_set_trace
 int g_num_sms = 148;
 int g_cluster = 1;     // DPB200_TC_CLUSTER=2|4: CTAs per cluster sharing (TMA-multicasting) one weight tile.  Measured on B200
@@ -1619,7 +1627,8 @@ struct TapTable { int n; signed char dh[9], dw[9], wt[9]; };
 int launch_tc(const float* act, long long ld_act, int Nimg, int H, int W, int Kg, const float* w_hi, const float* w_lo, int Nout,
               int T, const TapTable& taps, int os, int oa, int ob, int Ho, int Wo, float* out, long long ld_out, const float* bias,
               const float* rowadd, long long ld_rowadd, const float* residual, long long ld_res, int accumulate, cudaStream_t st,
-              float alpha = 1.0f, int b_from_img = 0, int in_stride = 1) {
+              float alpha = 1.0f, int b_from_img = 0, int in_stride = 1, int ldb = -1) {
+  if (ldb < 0) ldb = wrow(Kg);   // packed conv weights; batched GEMM callers pass their own row pitch
   if (!tc_init()) return DP_ERR_UNSUPPORTED;
   if (!w_hi || !w_lo) return DP_ERR_UNSUPPORTED;
   if (ld_act % 4 || ((uintptr_t)act & 15) || ((uintptr_t)w_hi & 15) || ((uintptr_t)w_lo & 15)) return DP_ERR_UNSUPPORTED;
@@ -1639,7 +1648,7 @@ int launch_tc(const float* act, long long ld_act, int Nimg, int H, int W, int Kg
   const int BN = (Nout <= 64) ? 64 : 128;
   if (in_stride != 1 && !(BN == 128 && g_persistent == 1 && !g_use_ss)) return DP_ERR_UNSUPPORTED;   // only the default persistent kernel scales the tile origin
   {
-    const cuuint64_t Kg4 = (cuuint64_t)((Kg + 3) & ~3);   // dp_pack_conv_weight_tc pads rows to 16 B
+    const cuuint64_t Kg4 = (cuuint64_t)ldb;   // dp_pack_conv_weight_tc pads rows to 16 B
     cuuint64_t dims[3] = {Kg4, (cuuint64_t)Nout, (cuuint64_t)T};
     cuuint64_t str[2] = {Kg4 * 4, (cuuint64_t)Nout * Kg4 * 4};
     cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BN, 1};
@@ -1669,7 +1678,7 @@ int launch_tc(const float* act, long long ld_act, int Nimg, int H, int W, int Kg
   } else if (BN == 128 && g_persistent == 2) {
     static const int bsub = getenv("DPB200_B_SUB") ? atoi(getenv("DPB200_B_SUB")) : 1;
     if (bsub > 1) {
-      const cuuint64_t Kg4 = (cuuint64_t)((Kg + 3) & ~3);
+      const cuuint64_t Kg4 = (cuuint64_t)ldb;
       cuuint64_t dims[3] = {Kg4, (cuuint64_t)Nout, (cuuint64_t)T};
       cuuint64_t str[2] = {Kg4 * 4, (cuuint64_t)Nout * Kg4 * 4};
       cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)(128 / bsub), 1};
@@ -1686,7 +1695,7 @@ int launch_tc(const float* act, long long ld_act, int Nimg, int H, int W, int Kg
         cuuint64_t str[3] = {(cuuint64_t)ld_act * 4, (cuuint64_t)W * ld_act * 4, (cuuint64_t)H * W * ld_act * 4};
         cuuint32_t box[4] = {16, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
         if (!make_map(&mA, act, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B)) return DP_ERR_UNSUPPORTED;
-        const cuuint64_t Kg4 = (cuuint64_t)((Kg + 3) & ~3);
+        const cuuint64_t Kg4 = (cuuint64_t)ldb;
         cuuint64_t bdims[3] = {Kg4, (cuuint64_t)Nout, (cuuint64_t)T};
         cuuint64_t bstr[2] = {Kg4 * 4, (cuuint64_t)Nout * Kg4 * 4};
         cuuint32_t bbox[3] = {16, 128, 1};
@@ -1713,7 +1722,7 @@ int launch_tc(const float* act, long long ld_act, int Nimg, int H, int W, int Kg
     } else {
       // weight-tile slices of 128/cl rows per CTA need their own (smaller-box) tensor maps
       CUtensorMap sBh, sBl;
-      const cuuint64_t Kg4 = (cuuint64_t)((Kg + 3) & ~3);
+      const cuuint64_t Kg4 = (cuuint64_t)ldb;
       cuuint64_t dims[3] = {Kg4, (cuuint64_t)Nout, (cuuint64_t)T};
       cuuint64_t str[2] = {Kg4 * 4, (cuuint64_t)Nout * Kg4 * 4};
       cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)(128 / cl), 1};
@@ -1732,10 +1741,9 @@ int launch_tc(const float* act, long long ld_act, int Nimg, int H, int W, int Kg
   return dp_check_launch();
 }
 
-__global__ void pack_tc_kernel(const float* __restrict__ w, int K, int C, int RS, float* __restrict__ kc_hi, float* __restrict__ kc_lo,
-                               float* __restrict__ ck_hi, float* __restrict__ ck_lo) {
-  // rows are padded to a multiple of 4 floats (16 B, a TMA stride requirement) with zeros: kc [RS][K][C4], ck [RS][C][K4]
-  const int C4 = (C + 3) & ~3, K4 = (K + 3) & ~3;
+__global__ void pack_tc_kernel(const float* __restrict__ w, int K, int C, int RS, int C4, int K4, float* __restrict__ kc_hi,
+                               float* __restrict__ kc_lo, float* __restrict__ ck_hi, float* __restrict__ ck_lo) {
+  // rows are zero-padded to C4 = dp_tc_weight_row(C), K4 = dp_tc_weight_row(K): kc [RS][K][C4], ck [RS][C][K4]
   const long long na = (long long)RS * K * C4, nb = (long long)RS * C * K4;
   const long long total = na > nb ? na : nb;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -1827,7 +1835,7 @@ extern "C" int dp_gemm_nt_tc(const dp_gemm_nt_args* a, dp_stream_t stream) {
   TapTable t{};
   t.n = 1;
   return launch_tc(a->A, a->ld_a, a->batch, a->H, a->W, a->Kg, a->b_hi, a->b_lo, a->N, a->batch, t, 1, 0, 0, a->H, a->W, a->C, a->ldc,
-                   nullptr, nullptr, 0, nullptr, 0, 0, (cudaStream_t)stream, a->alpha, 1);
+                   nullptr, nullptr, 0, nullptr, 0, 0, (cudaStream_t)stream, a->alpha, 1, 1, (a->Kg + 3) & ~3);
 }
 
 namespace {
@@ -1954,10 +1962,11 @@ extern "C" int dp_pack_conv_weight_tc(const float* w, int32_t K, int32_t C, int3
                                       float* ck_hi, float* ck_lo, dp_stream_t stream) {
   DP_REQUIRE(w, DP_ERR_NULL);
   DP_REQUIRE(K > 0 && C > 0 && R > 0 && S > 0, DP_ERR_SHAPE);
-  long long total = (long long)R * S * ((long long)K * ((C + 3) & ~3) > (long long)C * ((K + 3) & ~3) ? (long long)K * ((C + 3) & ~3) : (long long)C * ((K + 3) & ~3));
+  const int C4 = wrow(C), K4 = wrow(K);
+  long long total = (long long)R * S * ((long long)K * C4 > (long long)C * K4 ? (long long)K * C4 : (long long)C * K4);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  pack_tc_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, K, C, R * S, kc_hi, kc_lo, ck_hi, ck_lo);
+  pack_tc_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, K, C, R * S, C4, K4, kc_hi, kc_lo, ck_hi, ck_lo);
   return dp_check_launch();
 }
 
@@ -1965,3 +1974,5 @@ extern "C" int dp_pack_conv_weight_tc(const float* w, int32_t K, int32_t C, int3
 // stages (slots: 0 producer woke on "empty", 1 TMA issued, 2 splitter woke on "full", 6 split+fence done, 3 splitter arrived,
 // 4 MMA lane woke on "converted", 5 MMAs + commit issued).  nullptr switches it off.  buf must hold 16640 int64 (16 slots per stage; 8..10: issuer at loop top / after the "converted" wait / after the hand-off wait) (the last 256: per tile, epilogue woke / released TMEM / done, issuer got the accumulator).
 extern "C" int dp_conv_tc_set_trace(long long* buf) { g_trace = buf; return 0; }
+
+extern "C" int dp_tc_weight_row(int channels) { return channels > 0 ? wrow(channels) : 0; }

@@ -245,7 +245,7 @@ class Plan:
         tc = None
         if self.tc and K * Cin >= 256:
             RS = R * S
-            na, nb = RS * K * ((Cin + 3) // 4 * 4), RS * Cin * ((K + 3) // 4 * 4)
+            na, nb = RS * K * lib.dp_tc_weight_row(Cin), RS * Cin * lib.dp_tc_weight_row(K)   # rows padded for aligned TMA box rows
             tc = tuple(torch.empty(n, device=self.dev, dtype=torch.float32) for n in (na, na, nb, nb))  # kc_hi kc_lo ck_hi ck_lo
             self._rec(self.pack, lambda s, w=w, K=K, Cin=Cin, R=R, S=S, t=tc:
                       lib.dp_pack_conv_weight_tc(w.data_ptr(), K, Cin, R, S, t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(),

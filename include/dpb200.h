@@ -69,7 +69,7 @@ typedef struct dp_conv_args {
   int64_t ldy;
   const float* w;      /* fprop: packed [R*S][C][K] | dgrad: packed [R*S][K][C] (dp_pack_conv_weight) */
   const float* w_tc_hi; /* optional tensor-core operand (dp_pack_conv_weight_tc): TF32-rounded part, GEMM-K contiguous: */
-  const float* w_tc_lo; /*   fprop [R*S][K][C4] | dgrad [R*S][C][K4]; w_tc_lo = w - w_tc_hi (3xTF32 split). NULL => SIMT path */
+  const float* w_tc_lo; /*   fprop [R*S][K][C4] | dgrad [R*S][C][K4] (C4/K4 = dp_tc_weight_row); w_tc_lo = w - w_tc_hi (3xTF32 split). NULL => SIMT path */
   const float* bias;   /* fprop epilogue: + bias[K]                                   (nullable) */
   const float* rowadd; /* fprop epilogue: + rowadd[n*ld_rowadd + k] per image n (temb, resnet.py:618-621) (nullable) */
   int64_t ld_rowadd;
@@ -103,9 +103,11 @@ int dp_pack_conv_weight(const float* w_oihw, int32_t K, int32_t C, int32_t R, in
                         dp_stream_t stream);
 
 /* 3xTF32 operands for the tcgen05 path: hi = cvt.rna.tf32(w), lo = w - hi (exact), each in both K-major forms:
- *   kc_* [R*S][K][C4] (fprop B operand, GEMM-K = C)   ck_* [R*S][C][K4] (dgrad B operand, GEMM-K = K), where C4 / K4 round the
- *   row length up to a multiple of 4 floats (zero padded: TMA needs 16-byte row pitches; pruned widths like 179 / 358 are
- *   not).  Any output may be NULL. */
+ *   kc_* [R*S][K][C4] (fprop B operand, GEMM-K = C)   ck_* [R*S][C][K4] (dgrad B operand, GEMM-K = K), where
+ *   C4 = dp_tc_weight_row(C), K4 = dp_tc_weight_row(K) are the zero-padded row lengths: a multiple of 32 floats for rows longer
+ *   than 32 (every 32-float TMA box row is then one aligned 128-byte line — pruned widths such as 90 / 179 / 358 otherwise run
+ *   20-25 % slower), else a multiple of 4 (TMA needs 16-byte row pitches).  Any output may be NULL. */
+int dp_tc_weight_row(int channels);
 int dp_pack_conv_weight_tc(const float* w_oihw, int32_t K, int32_t C, int32_t R, int32_t S, float* kc_hi, float* kc_lo,
                            float* ck_hi, float* ck_lo, dp_stream_t stream);
 

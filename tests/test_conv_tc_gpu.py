@@ -65,7 +65,8 @@ def test_conv_tc_fprop_dgrad(lib, N, Cin, H, W, K, R, ldx, ldy):
     gy = torch.randn(N, K, H, W, generator=g)
     y_ref.backward(gy)
     wd = w.contiguous().cuda()
-    C4, K4 = (Cin + 3) // 4 * 4, (K + 3) // 4 * 4
+    C4, K4 = lib.dp_tc_weight_row(Cin), lib.dp_tc_weight_row(K)     # 4-float multiple up to 32 channels, 32-float multiple beyond
+    assert C4 >= Cin and C4 % 4 == 0 and (Cin <= 32 or C4 % 32 == 0)
     packs = [torch.empty(n, device="cuda") for n in (R * R * K * C4, R * R * K * C4, R * R * Cin * K4, R * R * Cin * K4)]
     assert lib.dp_pack_conv_weight_tc(wd.data_ptr(), K, Cin, R, R, *[p.data_ptr() for p in packs], S()) == 0
     simt_ck, simt_kc = torch.empty(w.numel(), device="cuda"), torch.empty(w.numel(), device="cuda")
