@@ -120,3 +120,13 @@ def test_wgrad_split_count_respects_wave_boundaries():
         old = -(-chunks // -(-chunks // old)) if old <= chunks else old
         cost = lambda s: -(-(tiles * s) // _SM_COUNT) * (_WGRAD_CTA_OVERHEAD + -(-chunks // s))
         assert cost(sp) <= cost(min(old, chunks)), (tiles, chunks, sp, old)
+
+
+def test_tc_weight_row_padding_rule():
+    """dp_tc_weight_row (host function of the C-ABI): 16-byte multiples up to 32 channels, 128-byte multiples beyond."""
+    from diff_pruning_b200 import _lib as L
+    lib = L.load()
+    for c, want in [(1, 4), (3, 4), (4, 4), (27, 28), (32, 32), (33, 64), (90, 96), (96, 96), (128, 128), (179, 192), (358, 384),
+                    (512, 512)]:
+        assert lib.dp_tc_weight_row(c) == want, (c, lib.dp_tc_weight_row(c), want)
+    assert lib.dp_tc_weight_row(0) == 0
