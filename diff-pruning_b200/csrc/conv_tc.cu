@@ -1295,6 +1295,283 @@ conv_tc_ps2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   }
 }
 
+// ------------------------------------------------------------------------------------------------ persistent TS variant
+// Round-2 candidate built from what the pipeline timeline showed (profiles/r01_experiments.md), DPB200_TC_PERSISTENT=4:
+//  * A operand through TENSOR MEMORY (TS mode): the raw fp32 A box lands in a 6-deep ring of 16 KB stages, a splitter thread
+//    per pixel row converts it in registers and writes hi/lo with tcgen05.st into a 4-deep ring of TMEM slots — the raw
+//    stage is free as soon as it is in registers, no generic->async proxy fence, and the MMA reads only B from shared memory;
+//  * B (pre-split weights, hi | lo adjacent) in its own 3-deep ring of 32 KB stages: 192 KB in total, but the A, B and TMEM
+//    rings are released independently, so the ~3000-clk TMA -> split -> MMA -> commit round trip is covered;
+//  * per 8-float K step two instructions: a_hi x [b_hi | b_lo] (N=256) -> [main | correction], a_lo x b_hi (N=128) -> correction;
+//  * two issuer warps on alternate stages (a lone issuer cannot run ahead of the tensor queue);
+//  * persistent tiles with ONE accumulator set (the A slots use the other 256 TMEM columns): the epilogue warps first drain
+//    main + correction into 128 registers per thread (a few hundred clk), hand the accumulator back, and only then do the
+//    bias / residual / store work, which overlaps the next tile's main loop.
+constexpr int PT_THREADS = 384;   // warps: 0 A producer | 1 B producer | 2, 11 MMA issuers | 3-6 splitters | 7-10 epilogue
+constexpr int PT_SA = 6, PT_SB = 3, PT_TA = 4;
+
+__global__ void __launch_bounds__(PT_THREADS, 1)
+conv_tc_pt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBh,
+                  const __grid_constant__ CUtensorMap mapBl, const TcParams p, const int tiles_m, const int total_tiles) {
+  constexpr int BN = 128;
+  constexpr int B_BYTES = BN * BK * 4;
+  constexpr uint32_t A_COL0 = 2 * BN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t pad_to = ((raw + 1023u) & ~1023u) - raw;
+  uint8_t* smem = smem_raw + pad_to;
+  const uint32_t sbase = raw + pad_to;
+  const uint32_t a_base = sbase, b_base = sbase + PT_SA * A_BYTES;
+  constexpr int DATA_BYTES = PT_SA * A_BYTES + PT_SB * 2 * B_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DATA_BYTES);
+  const uint32_t bar0 = sbase + DATA_BYTES;
+  auto fullA = [&](int i) { return bar0 + 8u * i; };
+  auto emptyA = [&](int i) { return bar0 + 8u * (PT_SA + i); };
+  auto fullB = [&](int i) { return bar0 + 8u * (2 * PT_SA + i); };
+  auto emptyB = [&](int i) { return bar0 + 8u * (2 * PT_SA + PT_SB + i); };
+  auto convT = [&](int i) { return bar0 + 8u * (2 * PT_SA + 2 * PT_SB + i); };
+  auto emptyT = [&](int i) { return bar0 + 8u * (2 * PT_SA + 2 * PT_SB + PT_TA + i); };
+  auto issT = [&](int i) { return bar0 + 8u * (2 * PT_SA + 2 * PT_SB + 2 * PT_TA + i); };   // "stage in TMEM slot i is queued"
+  constexpr int NB0 = 2 * PT_SA + 2 * PT_SB + 3 * PT_TA;
+  const uint32_t tfull_bar = bar0 + 8u * NB0, tempty_bar = bar0 + 8u * (NB0 + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NB0 + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < PT_SA; ++i) { mbar_init(fullA(i), 1); mbar_init(emptyA(i), 128); }
+    for (int i = 0; i < PT_SB; ++i) { mbar_init(fullB(i), 1); mbar_init(emptyB(i), 1); }
+    for (int i = 0; i < PT_TA; ++i) { mbar_init(convT(i), 128); mbar_init(emptyT(i), 1); mbar_init(issT(i), 1); }
+    mbar_init(tfull_bar, 1); mbar_init(tempty_bar, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  const int iters_per_tile = p.ntaps * p.kchunks;
+
+  auto tile_coords = [&](int tile, int& q0, int& p0, int& n0, int& nblk) {
+    nblk = tile / tiles_m;
+    const int tile_m = tile - nblk * tiles_m;
+    const int tw = tile_m % p.tiles_w;
+    const int th = (tile_m / p.tiles_w) % p.tiles_h;
+    const int tn = tile_m / (p.tiles_w * p.tiles_h);
+    q0 = tw * p.bw; p0 = th * p.bh; n0 = tn * p.bn;
+  };
+
+  if (warp == 0) {
+    // ---- A producer
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
+      uint32_t g = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int q0, p0, n0, nblk;
+        tile_coords(tile, q0, p0, n0, nblk);
+        int tap = 0, kc = 0;
+        for (int it = 0; it < iters_per_tile; ++it, ++g) {
+          const int s = g % PT_SA;
+          const int c_k = kc * BK, c_w = q0 * p.in_stride + p.dw[tap], c_h = p0 * p.in_stride + p.dh[tap];
+          if (++kc == p.kchunks) { kc = 0; ++tap; }
+          mbar_wait(emptyA(s), ((g / PT_SA) & 1u) ^ 1u);
+          mbar_expect_tx(fullA(s), A_BYTES);
+          tma_load_4d(a_base + s * A_BYTES, &mapA, fullA(s), c_k, c_w, c_h, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---- B producer (hi | lo adjacent: one N=256 descriptor covers both)
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapBh)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapBl)) : "memory");
+      uint32_t g = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int q0, p0, n0, nblk;
+        tile_coords(tile, q0, p0, n0, nblk);
+        int tap = 0, kc = 0;
+        for (int it = 0; it < iters_per_tile; ++it, ++g) {
+          const int s = g % PT_SB;
+          const int c_k = kc * BK;
+          const int tapb = p.b_from_img ? n0 : p.wt[tap];
+          if (++kc == p.kchunks) { kc = 0; ++tap; }
+          mbar_wait(emptyB(s), ((g / PT_SB) & 1u) ^ 1u);
+          const uint32_t st = b_base + s * 2 * B_BYTES;
+          if (p.dbg_skip == 0) {
+            mbar_expect_tx(fullB(s), 2 * B_BYTES);
+            tma_load_3d(st, &mapBh, fullB(s), c_k, nblk * BN, tapb);
+            tma_load_3d(st + B_BYTES, &mapBl, fullB(s), c_k, nblk * BN, tapb);
+          } else {   // timing experiments (DPB200_TC_DEBUG_SKIP: 2 no B_hi, 4 no B_lo): results are then wrong
+            mbar_expect_tx(fullB(s), ((p.dbg_skip & 2) ? 0 : B_BYTES) + ((p.dbg_skip & 4) ? 0 : B_BYTES));
+            if (!(p.dbg_skip & 2)) tma_load_3d(st, &mapBh, fullB(s), c_k, nblk * BN, tapb);
+            if (!(p.dbg_skip & 4)) tma_load_3d(st + B_BYTES, &mapBl, fullB(s), c_k, nblk * BN, tapb);
+          }
+        }
+      }
+    }
+  } else if (warp == 2 || warp == 11) {
+    // ---- two MMA issuer warps on alternate stages (warp-converged, one elected lane; queue order kept by the issT hand-off)
+    const uint32_t mw = (warp == 2) ? 0u : 1u;
+    const uint32_t ni = (uint32_t)p.two_issuers;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    const uint32_t idesc256 = (1u << 4) | (2u << 7) | (2u << 10) | ((256u >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    if (mw < ni) {
+      uint32_t g = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+        mbar_wait(tempty_bar, (tl & 1u) ^ 1u);            // the epilogue has drained the accumulator of the previous tile
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int it = 0; it < iters_per_tile; ++it, ++g) {
+          if (g % ni != mw) continue;
+          const int sb = g % PT_SB, ta = g % PT_TA;
+          mbar_wait(convT(ta), (g / PT_TA) & 1u);         // A hi/lo of this stage sit in TMEM slot ta
+          mbar_wait(fullB(sb), (g / PT_SB) & 1u);         // B hi/lo landed in shared memory
+          if (ni > 1u && g > 0) mbar_wait(issT((g - 1) % PT_TA), ((g - 1) / PT_TA) & 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t st = b_base + sb * 2 * B_BYTES;
+          const uint32_t a_t = tmem_base + A_COL0 + 64u * ta;
+          if (elect_one()) {
+            const uint64_t b_hi0 = umma_desc(st);
+#pragma unroll
+            for (int k = 0; k < BK / 8; ++k) {
+              const uint64_t b_hi = b_hi0 + 2 * k;
+              const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
+              umma_tf32_ts(tmem_base, a_t + k * 8, b_hi, idesc256, first);        // a_hi x [b_hi | b_lo] -> [main | correction]
+              umma_tf32_ts(tmem_base + BN, a_t + 32 + k * 8, b_hi, idesc, 1u);    // a_lo x b_hi -> correction
+            }
+            umma_commit(emptyB(sb));
+            umma_commit(emptyT(ta));
+            if (it == iters_per_tile - 1) umma_commit(tfull_bar);
+            if (ni > 1u) {
+              asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+              mbar_arrive(issT(ta));
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp < 7) {
+    // ---- splitter warps 3..6: thread <-> pixel row (TMEM lane quarter = warp & 3)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    uint32_t g = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int it = 0; it < iters_per_tile; ++it, ++g) {
+        const int sa = g % PT_SA, ta = g % PT_TA;
+        mbar_wait(fullA(sa), (g / PT_SA) & 1u);
+        const uint8_t* arow = smem + sa * A_BYTES + row * 128;
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {   // SWIZZLE_128B: 16-byte chunk j of row r sits at chunk position j ^ (r & 7)
+          const float4 v = *reinterpret_cast<const float4*>(arow + ((j ^ (row & 7)) << 4));
+          const float h0 = tf32_rna(v.x), h1 = tf32_rna(v.y), h2 = tf32_rna(v.z), h3 = tf32_rna(v.w);
+          hi[4 * j + 0] = __float_as_uint(h0); hi[4 * j + 1] = __float_as_uint(h1);
+          hi[4 * j + 2] = __float_as_uint(h2); hi[4 * j + 3] = __float_as_uint(h3);
+          lo[4 * j + 0] = __float_as_uint(v.x - h0); lo[4 * j + 1] = __float_as_uint(v.y - h1);
+          lo[4 * j + 2] = __float_as_uint(v.z - h2); lo[4 * j + 3] = __float_as_uint(v.w - h3);
+        }
+        mbar_arrive(emptyA(sa));                                     // tile is in registers: the A TMA may refill this slot
+        mbar_wait(emptyT(ta), ((g / PT_TA) & 1u) ^ 1u);              // the MMAs that read TMEM slot ta (4 stages ago) are done
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_t = tmem_base + lane_addr + A_COL0 + 64u * ta;
+        tmem_st32(a_t, hi);
+        tmem_st32(a_t + 32, lo);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(convT(ta));
+      }
+    }
+  } else if (warp < 11) {
+    // ---- epilogue warps 7..10 (TMEM lane quarter = warp & 3): drain main + correction into registers, release, then store
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const int w_l = row % p.bw, h_l = (row / p.bw) % p.bh, n_l = row / (p.bw * p.bh);
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+      int q0, p0, n0, nblk;
+      tile_coords(tile, q0, p0, n0, nblk);
+      mbar_wait(tfull_bar, tl & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      float acc[BN];
+#pragma unroll
+      for (int j = 0; j < BN / 32; ++j) {
+        uint32_t v[32], u[32];
+        const uint32_t taddr = tmem_base + lane_addr + (uint32_t)(j * 32);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr));
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+              "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
+              "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
+              "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+            : "r"(taddr + 128u));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[j * 32 + i] = p.alpha * (__uint_as_float(v[i]) + __uint_as_float(u[i]));
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(tempty_bar);                                        // the issuers may start the next tile
+      const int img = n0 + n_l;
+      if (img < p.Nimg) {
+        const long long m = ((long long)img * p.Ho + ((p0 + h_l) * p.os + p.oa)) * p.Wo + ((q0 + w_l) * p.os + p.ob);
+        float* yrow = p.y + m * p.ldy;
+        const float* rrow = p.residual ? p.residual + m * p.ld_res : nullptr;
+        const float* arow2 = p.rowadd ? p.rowadd + (long long)img * p.ld_rowadd : nullptr;
+#pragma unroll
+        for (int j = 0; j < BN / 32; ++j) {
+          const int c0 = nblk * BN + j * 32;
+          if (p.vec4 && c0 + 32 <= p.Nout) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              float4 o = make_float4(acc[j * 32 + i], acc[j * 32 + i + 1], acc[j * 32 + i + 2], acc[j * 32 + i + 3]);
+              if (p.bias) { float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + i)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+              if (arow2) { float4 t = __ldg(reinterpret_cast<const float4*>(arow2 + c0 + i)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+              if (rrow) { float4 t = __ldg(reinterpret_cast<const float4*>(rrow + c0 + i)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+              float4* dst = reinterpret_cast<float4*>(yrow + c0 + i);
+              if (p.accumulate) { float4 t = *dst; o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+              *dst = o;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int c = c0 + i;
+              if (c < p.Nout) {
+                float o = acc[j * 32 + i];
+                if (p.bias) o += __ldg(p.bias + c);
+                if (arow2) o += __ldg(arow2 + c);
+                if (rrow) o += __ldg(rrow + c);
+                if (p.accumulate) o += yrow[c];
+                yrow[c] = o;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+
 // ------------------------------------------------------------------------------------------------ wgrad
 // dW[k][tap][c] = sum_pix dy[pix][k] * x[pix @ tap][c]  as GEMM  M = k (128), N = c (128), K = pixels.
 // Both operands are activations stored pixel-major / channel-contiguous, i.e. "MN-major" for the tensor core:
@@ -1538,7 +1815,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn g_encode = nullptr;
 int g_tc_state = -1;  // -1 unknown, 0 unavailable, 1 ok
 bool g_use_ss = false;
-int g_persistent = 1;  // DPB200_TC_PERSISTENT: 1 = persistent SS kernel, 2 = decoupled A/B-ring TS kernel, 3 = two-issuer experimental kernel, 0 = one-ring TS kernel
+int g_persistent = 1;  // DPB200_TC_PERSISTENT: 1 = persistent SS kernel, 2 = decoupled A/B-ring TS kernel, 3 = two-issuer experimental kernel, 4 = persistent TS kernel (round-2 candidate), 0 = one-ring TS kernel
 static int g_ps_bk = 32;               // DPB200_TC_PS_BK: K chunk per stage of the persistent kernel (16 -> 7 stages, 32 -> 3 stages)
 static constexpr int ps_smem_bytes(int bk) { return (bk == 16 ? 7 : 3) * 4 * 128 * bk * 4 + 2048; }
 // Row length of the packed TF32 weight tiles (dp_pack_conv_weight_tc): rows longer than 32 floats are zero-padded to a multiple of 32
@@ -1579,6 +1856,7 @@ int tc_init() {
   ok = ok && cudaFuncSetAttribute(conv_tc_ts_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem64) == cudaSuccess;
   if (const char* e = getenv("DPB200_TC_CLUSTER")) g_cluster = atoi(e);
   ok = ok && cudaFuncSetAttribute(conv_tc_ps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PS_STAGES * (2 * A_BYTES + 2 * 128 * BK * 4) + 2048) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(conv_tc_pt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SA * A_BYTES + PT_SB * 2 * 128 * BK * 4 + 2048) == cudaSuccess;
   ok = ok && cudaFuncSetAttribute(conv_tc_ps2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ps_smem_bytes(32)) == cudaSuccess;
   ok = ok && cudaFuncSetAttribute(conv_tc_ps2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ps_smem_bytes(16)) == cudaSuccess;
   if (const char* e = getenv("DPB200_TC_PS_BK")) g_ps_bk = atoi(e) == 32 ? 32 : 16;
@@ -1646,7 +1924,7 @@ int launch_tc(const float* act, long long ld_act, int Nimg, int H, int W, int Kg
     if (!make_map(&mA, act, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, in_stride)) return DP_ERR_UNSUPPORTED;
   }
   const int BN = (Nout <= 64) ? 64 : 128;
-  if (in_stride != 1 && !(BN == 128 && g_persistent == 1 && !g_use_ss)) return DP_ERR_UNSUPPORTED;   // only the default persistent kernel scales the tile origin
+  if (in_stride != 1 && !(BN == 128 && (g_persistent == 1 || g_persistent == 4) && !g_use_ss)) return DP_ERR_UNSUPPORTED;   // only these kernels scale the tile origin
   {
     const cuuint64_t Kg4 = (cuuint64_t)ldb;   // dp_pack_conv_weight_tc pads rows to 16 B
     cuuint64_t dims[3] = {Kg4, (cuuint64_t)Nout, (cuuint64_t)T};
@@ -1686,6 +1964,10 @@ int launch_tc(const float* act, long long ld_act, int Nimg, int H, int W, int Kg
       p.b_sub = bsub;
     }
     conv_tc_ab_kernel<<<grid, AB_THREADS, AB_SA * A_BYTES + AB_SB * 2 * 128 * BK * 4 + 2048, st>>>(mA, mBh, mBl, p);
+  } else if (BN == 128 && g_persistent == 4) {
+    const int tiles_m = (int)grid.x, total = (int)(grid.x * grid.y);
+    const int ctas = total < g_num_sms ? total : g_num_sms;
+    conv_tc_pt_kernel<<<ctas, PT_THREADS, PT_SA * A_BYTES + PT_SB * 2 * 128 * BK * 4 + 2048, st>>>(mA, mBh, mBl, p, tiles_m, total);
   } else if (BN == 128 && g_persistent == 3) {
     const int tiles_m = (int)grid.x, total = (int)(grid.x * grid.y);
     const int ctas = total < g_num_sms ? total : g_num_sms;

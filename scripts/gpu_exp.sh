@@ -1,4 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo rc=$?; cut -c1-330 gpurun_out/bench.json
-python bench.py --impl reference --steps 10 --warmup 3 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo rc=$?; cut -c1-200 gpurun_out/bench_ref.json
+for sk in 0 4 6; do
+echo "pt skip $sk: $(ONE_SHAPE=1 DPB200_TC_PERSISTENT=4 DPB200_TC_DEBUG_SKIP=$sk timeout 60 python scripts/time_conv_shapes.py 2>&1 | cut -c1-44)"
+done

@@ -11,7 +11,8 @@ from diff_pruning_b200 import _lib as L  # noqa: E402
 lib = L.load()
 S = lambda: torch.cuda.current_stream().cuda_stream
 R = 3
-for Cin, K, H, N in [(128, 128, 32, 128), (96, 96, 32, 128), (92, 92, 32, 128), (90, 90, 32, 128), (90, 128, 32, 128), (128, 90, 32, 128),
+SHAPES = [(128, 128, 32, 128)] if os.environ.get('ONE_SHAPE') else None
+for Cin, K, H, N in SHAPES or [(128, 128, 32, 128), (96, 96, 32, 128), (92, 92, 32, 128), (90, 90, 32, 128), (90, 128, 32, 128), (128, 90, 32, 128),
                      (256, 256, 16, 128), (192, 192, 16, 128), (180, 180, 16, 128), (179, 179, 16, 128), (358, 179, 16, 128)]:
     q = int(os.environ.get('DPB200_PITCH', '4'))
     ldx, ldy = (Cin + q - 1) // q * q, (K + q - 1) // q * q
