@@ -12,6 +12,18 @@
 //   warps 2..5  splitter: A (in place) -> hi, A_lo <- lo, smem->reg->smem, then fence.proxy.async + mbarrier
 //   warp 1      MMA issuer (one lane): 4 k-steps x 3 tcgen05.mma.kind::tf32 per stage, tcgen05.commit frees the stage
 //   warps 2..5  epilogue: tcgen05.ld accumulator rows, + bias / + per-image temb row / + residual / accumulate, store
+//
+// Kernels in this file (launch_tc picks one; DPB200_TC_PERSISTENT / DPB200_TC_SS / DPB200_TC_CLUSTER select the non-defaults):
+//   conv_tc_ps_kernel        DEFAULT fprop/dgrad for > 64 output channels: persistent (1 CTA/SM loops over tiles), A hi/lo in
+//                            shared memory (SS), 3 x 64 KB stages, two accumulator sets, N=256 fused hi-product instruction
+//   conv_tc_ts_kernel<BN,CL> one tile per CTA, A through TMEM (TS); default for <= 64 output channels; CL > 1 = weight multicast
+//   conv_tc_kernel<BN>       first SS kernel (DPB200_TC_SS), one tile per CTA
+//   conv_tc_ab_kernel        (=2) one tile per CTA, TS, decoupled A / B / TMEM rings
+//   conv_tc_ps2_kernel<BK>   (=3) ps + elect.sync issue, two issuer warps, optional 16-float stages x 7, clock64() trace stamps
+//   conv_tc_pt_kernel        (=4) persistent TS: decoupled rings, two issuers, register-drained epilogue (round-2 candidate)
+//   wgrad_tc_kernel          weight gradient: dY^T through TMEM, X split in shared memory, split-K over pixels
+//   pack_tc / split_tf32 / transpose_batched helpers, dp_gemm_nt_tc (attention GEMMs on the persistent kernel)
+// Measurements of every variant: profiles/r01_experiments.md.
 #include <cuda.h>
 #include <cstdlib>
 #include <mutex>
