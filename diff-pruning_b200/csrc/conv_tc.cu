@@ -1389,8 +1389,10 @@ conv_tc_pt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           const int c_k = kc * BK, c_w = q0 * p.in_stride + p.dw[tap], c_h = p0 * p.in_stride + p.dh[tap];
           if (++kc == p.kchunks) { kc = 0; ++tap; }
           mbar_wait(emptyA(s), ((g / PT_SA) & 1u) ^ 1u);
+          DP_TRACE(0, g);
           mbar_expect_tx(fullA(s), A_BYTES);
           tma_load_4d(a_base + s * A_BYTES, &mapA, fullA(s), c_k, c_w, c_h, n0);
+          DP_TRACE(1, g);
         }
       }
     }
@@ -1434,16 +1436,22 @@ conv_tc_pt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
         mbar_wait(tempty_bar, (tl & 1u) ^ 1u);            // the epilogue has drained the accumulator of the previous tile
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (mw == 0 && lane == 0) DP_TRACE_TILE(3, tl);
         for (int it = 0; it < iters_per_tile; ++it, ++g) {
           if (g % ni != mw) continue;
           const int sb = g % PT_SB, ta = g % PT_TA;
+          if (lane == 0) DP_TRACE(8, g);
           mbar_wait(convT(ta), (g / PT_TA) & 1u);         // A hi/lo of this stage sit in TMEM slot ta
+          if (lane == 0) DP_TRACE(9, g);
           mbar_wait(fullB(sb), (g / PT_SB) & 1u);         // B hi/lo landed in shared memory
+          if (lane == 0) DP_TRACE(7, g);
           if (ni > 1u && g > 0) mbar_wait(issT((g - 1) % PT_TA), ((g - 1) / PT_TA) & 1u);
+          if (lane == 0) DP_TRACE(10, g);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t st = b_base + sb * 2 * B_BYTES;
           const uint32_t a_t = tmem_base + A_COL0 + 64u * ta;
           if (elect_one()) {
+            DP_TRACE(4, g);
             const uint64_t b_hi0 = umma_desc(st);
 #pragma unroll
             for (int k = 0; k < BK / 8; ++k) {
@@ -1459,6 +1467,7 @@ conv_tc_pt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
               asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
               mbar_arrive(issT(ta));
             }
+            DP_TRACE(5, g);
           }
           __syncwarp();
         }
@@ -1474,6 +1483,7 @@ conv_tc_pt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       for (int it = 0; it < iters_per_tile; ++it, ++g) {
         const int sa = g % PT_SA, ta = g % PT_TA;
         mbar_wait(fullA(sa), (g / PT_SA) & 1u);
+        if (row == 0) DP_TRACE(2, g);
         const uint8_t* arow = smem + sa * A_BYTES + row * 128;
         uint32_t hi[32], lo[32];
 #pragma unroll
@@ -1486,7 +1496,9 @@ conv_tc_pt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           lo[4 * j + 2] = __float_as_uint(v.z - h2); lo[4 * j + 3] = __float_as_uint(v.w - h3);
         }
         mbar_arrive(emptyA(sa));                                     // tile is in registers: the A TMA may refill this slot
+        if (row == 0) DP_TRACE(6, g);
         mbar_wait(emptyT(ta), ((g / PT_TA) & 1u) ^ 1u);              // the MMAs that read TMEM slot ta (4 stages ago) are done
+        if (row == 0) DP_TRACE(11, g);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t a_t = tmem_base + lane_addr + A_COL0 + 64u * ta;
         tmem_st32(a_t, hi);
@@ -1494,6 +1506,8 @@ conv_tc_pt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         mbar_arrive(convT(ta));
+        if (lane == 0) DP_TRACE(12 + q, g);   // per-warp arrival (slot 12 + TMEM lane quarter); row 0 is quarter 0
+        if (row == 0) DP_TRACE(3, g);
       }
     }
   } else if (warp < 11) {
@@ -1508,6 +1522,7 @@ conv_tc_pt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       tile_coords(tile, q0, p0, n0, nblk);
       mbar_wait(tfull_bar, tl & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (row == 0) DP_TRACE_TILE(0, tl);
       float acc[BN];
 #pragma unroll
       for (int j = 0; j < BN / 32; ++j) {
@@ -1537,6 +1552,7 @@ conv_tc_pt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(tempty_bar);                                        // the issuers may start the next tile
+      if (row == 0) DP_TRACE_TILE(1, tl);
       const int img = n0 + n_l;
       if (img < p.Nimg) {
         const long long m = ((long long)img * p.Ho + ((p0 + h_l) * p.os + p.oa)) * p.Wo + ((q0 + w_l) * p.os + p.ob);
@@ -1573,6 +1589,7 @@ conv_tc_pt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           }
         }
       }
+      if (row == 0) DP_TRACE_TILE(2, tl);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -2265,7 +2282,7 @@ extern "C" int dp_pack_conv_weight_tc(const float* w, int32_t K, int32_t C, int3
 }
 
 // Debug hook: CTA 0 of every following persistent conv launch stamps clock64() into buf[stage*8 + slot] for its first 1024 pipeline
-// stages (slots: 0 producer woke on "empty", 1 TMA issued, 2 splitter woke on "full", 6 split+fence done, 3 splitter arrived,
+// stages (conv_tc_ps2_kernel / conv_tc_pt_kernel; slots: 0 producer woke on "empty", 1 TMA issued, 2 splitter woke on "full", 6 split done, 3 splitter arrived,
 // 4 MMA lane woke on "converted", 5 MMAs + commit issued).  nullptr switches it off.  buf must hold 16640 int64 (16 slots per stage; 8..10: issuer at loop top / after the "converted" wait / after the hand-off wait) (the last 256: per tile, epilogue woke / released TMEM / done, issuer got the accumulator).
 extern "C" int dp_conv_tc_set_trace(long long* buf) { g_trace = buf; return 0; }
 
