@@ -20,6 +20,7 @@ Execution:
 from __future__ import annotations
 
 import contextlib
+import inspect
 import math
 from dataclasses import dataclass
 from types import SimpleNamespace
@@ -413,6 +414,23 @@ class UNet2DModel(nn.Module):
             t = t[None].to(sample.device)
         return t * torch.ones(sample.shape[0], dtype=t.dtype, device=t.device)
 
+    # ---- checkpoint I/O in the diffusers directory layout (checkpoint.py; modeling_utils.py:250-330, 333-680)
+    def save_pretrained(self, save_directory, safe_serialization=False, **unused):
+        from . import checkpoint
+        checkpoint.save_model(self, save_directory, safe_serialization=safe_serialization)
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, subfolder=None, **overrides):
+        from . import checkpoint
+        overrides = {k: v for k, v in overrides.items() if k in inspect.signature(cls.__init__).parameters}
+        return checkpoint.load_model(cls, pretrained_model_name_or_path, subfolder=subfolder, **overrides)
+
+    @classmethod
+    def from_config(cls, config, **kw):
+        from . import checkpoint
+        cfg = dict(vars(config)) if not isinstance(config, dict) else dict(config)
+        return checkpoint.build_from_config(cls, cfg, **kw)
+
     def forward(self, sample, timestep, class_labels=None, return_dict=True):
         if self.config.center_input_sample:
             sample = 2 * sample - 1.0
@@ -465,6 +483,23 @@ class DDPMScheduler:
         self.alphas = 1.0 - self.betas
         self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
         self._dev_tables = {}
+
+    # ---- scheduler_config.json I/O (checkpoint.py; configuration_utils.py:138-170, scheduling_utils.py:83-160)
+    def save_pretrained(self, save_directory, **unused):
+        from . import checkpoint
+        checkpoint.save_config(self, save_directory, checkpoint.SCHEDULER_CONFIG_NAME)
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, subfolder=None, **kw):
+        from . import checkpoint
+        cfg = checkpoint.load_config(pretrained_model_name_or_path, checkpoint.SCHEDULER_CONFIG_NAME, subfolder)
+        return checkpoint.build_from_config(cls, cfg, **kw)
+
+    @classmethod
+    def from_config(cls, config, **kw):
+        from . import checkpoint
+        cfg = dict(vars(config)) if not isinstance(config, dict) else dict(config)
+        return checkpoint.build_from_config(cls, cfg, **kw)
 
     def add_noise(self, original_samples, noise, timesteps):
         if original_samples.is_cuda and not tracing():

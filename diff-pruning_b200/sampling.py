@@ -41,9 +41,21 @@ class DDIMScheduler:
 
     @classmethod
     def from_config(cls, config, **kw):
+        from . import checkpoint
         d = dict(vars(config)) if not isinstance(config, dict) else dict(config)
-        d.update(kw)
-        return cls(**d)
+        return checkpoint.build_from_config(cls, d, **kw)
+
+    # ---- scheduler_config.json I/O (checkpoint.py); `DDIMScheduler.from_pretrained(save_path, subfolder="scheduler")` re-reads
+    # a DDPM scheduler's config, as ddpm_prune.py:140 and ddpm_sample.py:34 do
+    def save_pretrained(self, save_directory, **unused):
+        from . import checkpoint
+        checkpoint.save_config(self, save_directory, checkpoint.SCHEDULER_CONFIG_NAME)
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, subfolder=None, **kw):
+        from . import checkpoint
+        cfg = checkpoint.load_config(pretrained_model_name_or_path, checkpoint.SCHEDULER_CONFIG_NAME, subfolder)
+        return checkpoint.build_from_config(cls, cfg, **kw)
 
     def set_timesteps(self, num_inference_steps: int, device=None):
         T = self.config.num_train_timesteps
@@ -109,6 +121,16 @@ class DDIMPipeline:
     def set_progress_bar_config(self, **kw):
         self._pbar = kw
 
+    # ---- model_index.json + unet/ + scheduler/ (checkpoint.py; pipeline_utils.py:485-560, 563-1000)
+    def save_pretrained(self, save_directory, safe_serialization=False, **unused):
+        from . import checkpoint
+        checkpoint.save_pipeline(self, save_directory, safe_serialization=safe_serialization)
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, **kw):
+        from . import checkpoint
+        return checkpoint.load_pipeline(cls, pretrained_model_name_or_path, **kw)
+
     @torch.no_grad()
     def __call__(self, batch_size=1, generator=None, eta=0.0, num_inference_steps=50, use_clipped_model_output=None,
                  output_type="pil", return_dict=True):
@@ -126,3 +148,38 @@ class DDIMPipeline:
             from PIL import Image  # optional dependency, like the reference
             image = [Image.fromarray((im * 255).round().astype("uint8")) for im in image]
         return SimpleNamespace(images=image) if return_dict else (image,)
+
+
+class DDPMPipeline:
+    """Container the reference scripts use to carry (unet, scheduler) to and from disk (`DDPMPipeline.from_pretrained(model_path)`
+    at ddpm_prune.py:50, `pipeline.save_pretrained(save_path)` at :132, ddpm_train.py:304-308,498).  Sampling on the hot path is
+    DDIM (`DDIMPipeline`, which the scripts build from this pipeline's unet and the re-read scheduler config); the 1000-step
+    ancestral sampler of pipeline_ddpm.py is not rebuilt."""
+
+    def __init__(self, unet: UNet2DModel, scheduler):
+        self.unet = unet
+        self.scheduler = scheduler
+
+    @property
+    def device(self):
+        return next(self.unet.parameters()).device
+
+    def to(self, device):
+        self.unet.to(device)
+        return self
+
+    def set_progress_bar_config(self, **kw):
+        pass
+
+    def save_pretrained(self, save_directory, safe_serialization=False, **unused):
+        from . import checkpoint
+        checkpoint.save_pipeline(self, save_directory, safe_serialization=safe_serialization)
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, **kw):
+        from . import checkpoint
+        return checkpoint.load_pipeline(cls, pretrained_model_name_or_path, **kw)
+
+    def __call__(self, *a, **kw):
+        raise NotImplementedError("diff_pruning_b200: ancestral DDPM sampling is not on the hot path; build "
+                                  "DDIMPipeline(unet=pipeline.unet, scheduler=DDIMScheduler.from_config(pipeline.scheduler.config))")

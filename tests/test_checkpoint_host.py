@@ -1,0 +1,108 @@
+"""Checkpoint I/O in the diffusers directory layout (diff_pruning_b200/checkpoint.py) against files written by the reference's own
+`DDPMPipeline.save_pretrained` (tests/golden/ckpt_tiny_ref/, tools/gen_golden.py job `ckpt`).  Host-only."""
+import hashlib
+import json
+import os
+import shutil
+
+import pytest
+import torch
+
+import diff_pruning_b200 as dp
+from diff_pruning_b200 import checkpoint
+from diff_pruning_b200.sampling import DDIMPipeline, DDIMScheduler, DDPMPipeline
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "ckpt_tiny_ref")
+
+
+def _digest(sd):
+    h = hashlib.sha256()
+    for k, v in sd.items():
+        h.update(k.encode()); h.update(v.contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+def _seeded_tiny():
+    torch.manual_seed(0)
+    return dp.UNet2DModel(**dp.TINY_TEST_CONFIG)
+
+
+def _ref_dir_with_weights(tmp_path):
+    """The reference-written JSON files + the weights file the reference wrote next to them (same seeded tiny UNet: the digest
+    of its state dict is pinned in weights_digest.json)."""
+    d = str(tmp_path / "ref_ckpt")
+    shutil.copytree(GOLD, d)
+    m = _seeded_tiny()
+    want = json.load(open(os.path.join(GOLD, "weights_digest.json")))
+    assert len(m.state_dict()) == want["n_tensors"]
+    assert _digest(m.state_dict()) == want["state_dict_sha256"]          # bit-identical to what the reference saved
+    torch.save(m.state_dict(), os.path.join(d, "unet", checkpoint.WEIGHTS_NAME))
+    return d, m
+
+
+def test_load_reference_written_pipeline(tmp_path):
+    d, m = _ref_dir_with_weights(tmp_path)
+    pipe = DDPMPipeline.from_pretrained(d)                                # ddpm_prune.py:50
+    assert isinstance(pipe.unet, dp.UNet2DModel) and isinstance(pipe.scheduler, dp.DDPMScheduler)
+    assert not pipe.unet.training
+    for (k1, v1), (k2, v2) in zip(m.state_dict().items(), pipe.unet.state_dict().items()):
+        assert k1 == k2 and torch.equal(v1, v2)
+    cfg = json.load(open(os.path.join(GOLD, "unet", "config.json")))
+    for k, v in cfg.items():
+        if not k.startswith("_"):
+            got = getattr(pipe.unet.config, k)
+            assert (list(got) if isinstance(got, tuple) else got) == v, k
+    assert pipe.scheduler.config.num_train_timesteps == 1000
+    # the scheduler keys this implementation does not interpret survive a round trip
+    assert pipe.scheduler._extra_config["variance_type"] == "fixed_small"
+    unet = dp.UNet2DModel.from_pretrained(d, subfolder="unet")            # ddpm_train.py:296
+    assert _digest(unet.state_dict()) == _digest(m.state_dict())
+    ddim = DDIMScheduler.from_pretrained(d, subfolder="scheduler")        # ddpm_prune.py:140: DDPM config read as DDIM
+    assert ddim.config.clip_sample is True and ddim.config.beta_end == 0.02
+    p2 = DDIMPipeline.from_pretrained(d)                                  # ddpm_sample.py:39
+    assert isinstance(p2.scheduler, DDIMScheduler)
+
+
+def test_save_matches_reference_files_and_round_trips(tmp_path):
+    d, m = _ref_dir_with_weights(tmp_path)
+    pipe = DDPMPipeline.from_pretrained(d)
+    out = str(tmp_path / "ours")
+    pipe.save_pretrained(out)                                             # ddpm_prune.py:132
+    for rel in ("model_index.json", "unet/config.json", "scheduler/scheduler_config.json"):
+        ours, ref = json.load(open(os.path.join(out, rel))), json.load(open(os.path.join(GOLD, rel)))
+        assert ours == ref, rel                                           # same keys, same values, same class names
+    assert sorted(os.listdir(os.path.join(out, "unet"))) == json.load(open(os.path.join(GOLD, "weights_digest.json")))["files"]
+    sd = torch.load(os.path.join(out, "unet", checkpoint.WEIGHTS_NAME), map_location="cpu", weights_only=True)
+    assert list(sd.keys()) == list(m.state_dict().keys()) and _digest(sd) == _digest(m.state_dict())
+    again = DDPMPipeline.from_pretrained(out)
+    assert _digest(again.unet.state_dict()) == _digest(m.state_dict())
+    # safetensors variant
+    out2 = str(tmp_path / "ours_st")
+    pipe.unet.save_pretrained(out2, safe_serialization=True)
+    assert os.path.isfile(os.path.join(out2, checkpoint.SAFETENSORS_WEIGHTS_NAME))
+    assert _digest(dp.UNet2DModel.from_pretrained(out2).state_dict()) == _digest(m.state_dict())
+
+
+def test_pruned_network_is_saved_as_a_whole_module(tmp_path):
+    """ddpm_prune.py:135 / ddpm_train.py:292: torch.save(model) / torch.load of the pruned module (its shapes no longer match
+    config.json, so from_pretrained must refuse it with a pointer to that path)."""
+    from diff_pruning_b200.pruning import prune_out_channels
+    m = _seeded_tiny()
+    prune_out_channels(m.down_blocks[0].resnets[0].conv1, [0, 5])
+    fn = str(tmp_path / "unet_pruned.pth")
+    torch.save(m, fn)
+    m2 = torch.load(fn, map_location="cpu", weights_only=False)
+    assert m2.down_blocks[0].resnets[0].conv1.weight.shape[0] == m.down_blocks[0].resnets[0].conv1.weight.shape[0]
+    assert _digest(m2.state_dict()) == _digest(m.state_dict())
+    d = str(tmp_path / "pruned_dir")
+    m.save_pretrained(d)
+    with pytest.raises(RuntimeError, match="whole modules"):
+        dp.UNet2DModel.from_pretrained(d)
+
+
+def test_ddpm_pipeline_is_a_container_only():
+    pipe = DDPMPipeline(unet=_seeded_tiny(), scheduler=dp.DDPMScheduler())
+    with pytest.raises(NotImplementedError):
+        pipe(batch_size=1)
+    with pytest.raises(OSError):
+        DDPMPipeline.from_pretrained("google/ddpm-cifar10-32")          # no hub access: local directories only

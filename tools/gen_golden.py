@@ -340,13 +340,39 @@ def gen_ddim():
     print("ddim", {k: float(v["images"].mean()) for k, v in res.items() if k != "cfg"})
 
 
+def gen_ckpt():
+    """`DDPMPipeline.save_pretrained` of the reference's vendored diffusers (pipeline_utils.py:485-560, modeling_utils.py:250-330,
+    configuration_utils.py:138-170) on the TINY UNet: keeps the three JSON files (the weights are the seeded tiny UNet, whose
+    state-dict keys/shapes are pinned elsewhere) as tests/golden/ckpt_tiny_ref/, plus a digest of the state-dict it wrote."""
+    import hashlib
+    import shutil
+    import tempfile
+    from diffusers import DDPMPipeline
+    m = build(dict(dp.TINY_TEST_CONFIG))
+    pipe = DDPMPipeline(unet=m, scheduler=DDPMScheduler(num_train_timesteps=1000))
+    tmp = tempfile.mkdtemp()
+    pipe.save_pretrained(tmp)
+    dst = os.path.join(OUT, "ckpt_tiny_ref")
+    for rel in ("model_index.json", "unet/config.json", "scheduler/scheduler_config.json"):
+        os.makedirs(os.path.dirname(os.path.join(dst, rel)), exist_ok=True)
+        shutil.copy(os.path.join(tmp, rel), os.path.join(dst, rel))
+    sd = torch.load(os.path.join(tmp, "unet", "diffusion_pytorch_model.bin"), map_location="cpu")
+    h = hashlib.sha256()
+    for k, v in sd.items():
+        h.update(k.encode()); h.update(v.contiguous().numpy().tobytes())
+    json.dump({"files": sorted(os.listdir(os.path.join(tmp, "unet"))), "n_tensors": len(sd), "state_dict_sha256": h.hexdigest()},
+              open(os.path.join(dst, "weights_digest.json"), "w"), indent=1)
+    shutil.rmtree(tmp)
+    print("ckpt", len(sd), h.hexdigest()[:16])
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--skip-cfg1", action="store_true")
     ap.add_argument("--only", default=None)
     a = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
-    jobs = {"ddim": gen_ddim, "tiny": gen_tiny, "blocks": gen_blocks, "finetune": gen_finetune, "cifar_fwd": gen_cifar_fwd,
+    jobs = {"ckpt": gen_ckpt, "ddim": gen_ddim, "tiny": gen_tiny, "blocks": gen_blocks, "finetune": gen_finetune, "cifar_fwd": gen_cifar_fwd,
             "cfg1_s3": gen_cfg1_s3, "cfg1": gen_cfg1}
     for name, fn in jobs.items():
         if a.only and name != a.only:
