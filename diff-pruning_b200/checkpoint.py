@@ -83,6 +83,8 @@ def build_from_config(cls, cfg: dict, **overrides):
     cfg_ns = getattr(obj, "config", None)
     if isinstance(cfg_ns, SimpleNamespace):
         extra = {k: v for k, v in extra.items() if not hasattr(cfg_ns, k)}
+        for k, v in extra.items():       # visible through `.config` too, so `OtherScheduler.from_config(this.config)` sees them
+            setattr(cfg_ns, k, v)        # (e.g. a DDPM scheduler's clip_sample / prediction_type re-read as DDIM, ddpm_prune.py:140)
     obj._extra_config = extra
     return obj
 

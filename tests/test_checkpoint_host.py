@@ -59,6 +59,8 @@ def test_load_reference_written_pipeline(tmp_path):
     assert _digest(unet.state_dict()) == _digest(m.state_dict())
     ddim = DDIMScheduler.from_pretrained(d, subfolder="scheduler")        # ddpm_prune.py:140: DDPM config read as DDIM
     assert ddim.config.clip_sample is True and ddim.config.beta_end == 0.02
+    ddim2 = DDIMScheduler.from_config(pipe.scheduler.config)              # ddpm_train.py / pipeline re-wrap: extras travel via .config
+    assert ddim2.config.clip_sample is True and ddim2.config.prediction_type == "epsilon"
     p2 = DDIMPipeline.from_pretrained(d)                                  # ddpm_sample.py:39
     assert isinstance(p2.scheduler, DDIMScheduler)
 
