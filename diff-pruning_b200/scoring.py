@@ -16,6 +16,7 @@ from __future__ import annotations
 import math
 from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 import torch.nn as nn
 
@@ -128,26 +129,86 @@ class TaylorScorer:
         self._refresh_noise()
         return float(self.step(t).item())
 
-    def run(self, timesteps: Iterable[int], shard: bool = True) -> torch.Tensor:
-        """The whole loop of ddpm_prune.py:97-102; with torch.distributed initialised, timesteps are sharded
-        (t_k for k = rank mod world) and the gradient arena is all-reduced (SUM) once at the end."""
+    def run(self, timesteps: Iterable[int], shard: bool = True, thr: Optional[float] = None) -> torch.Tensor:
+        """The whole loop of ddpm_prune.py:97-106; with torch.distributed initialised, timesteps are sharded
+        (t_k for k = rank mod world) and the gradient arena is all-reduced (SUM) once at the end.
+
+        `thr` is the `--pruner diff-pruning` rule of ddpm_prune.py:104-106: track the running maximum loss and stop after the
+        first timestep whose loss falls below `thr * loss_max` (that timestep's gradient is still accumulated — its backward ran
+        before the check).  Returns the losses of the timesteps that were used."""
         ts = list(timesteps)
         world, rank = 1, 0
         if shard and _dist_ready():
             import torch.distributed as dist
             world, rank = dist.get_world_size(), dist.get_rank()
-        losses = torch.zeros(len(ts), device=self.dev, dtype=torch.float32)
-        for k, t in enumerate(ts):
-            if k % world != rank:
-                continue
-            losses[k:k + 1].copy_(self.step(t))
+        if thr is not None:
+            losses = self._run_thresholded(ts, float(thr), world, rank)
+        else:
+            losses = torch.zeros(len(ts), device=self.dev, dtype=torch.float32)
+            for k, t in enumerate(ts):
+                if k % world != rank:
+                    continue
+                losses[k:k + 1].copy_(self.step(t))
         if world > 1:
             import torch.distributed as dist
             dist.all_reduce(self.plan.grad_arena, op=dist.ReduceOp.SUM)
-            dist.all_reduce(losses, op=dist.ReduceOp.SUM)
+            if thr is None:
+                dist.all_reduce(losses, op=dist.ReduceOp.SUM)
             if self.plan.fused_scores:
                 dist.all_reduce(self.plan.score_arena, op=dist.ReduceOp.SUM)
         return losses
+
+    def _run_thresholded(self, ts, thr: float, world: int, rank: int) -> torch.Tensor:
+        """Rounds of `world` consecutive timesteps (rank r takes the r-th of each round).  The stop rule is sequential, so after
+        every round the ranks exchange their losses (one tiny all-reduce; the reference syncs on the loss every step as well) and
+        replay the reference's scalar logic; a rank whose timestep lies beyond the stopping one restores the gradient arena from
+        the snapshot taken before its speculative pass, so the accumulated gradient is exactly that of the sequential loop."""
+        used = []
+        loss_max = np.float32(0.0)
+        thr32 = np.float32(thr)
+        snap = snap_scores = None
+        for r0 in range(0, len(ts), world):
+            k = r0 + rank
+            mine = k < len(ts)
+            if world > 1 and mine and rank > 0:      # rank 0's timestep is the first of the round: never undone
+                snap = self.plan.grad_arena.clone() if snap is None else snap.copy_(self.plan.grad_arena)
+                if self.plan.fused_scores:
+                    snap_scores = self.plan.score_arena.clone() if snap_scores is None else snap_scores.copy_(self.plan.score_arena)
+            rl = torch.zeros(world, device=self.dev, dtype=torch.float32)
+            if mine:
+                rl[rank:rank + 1].copy_(self.step(ts[k]))
+            if world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(rl, op=dist.ReduceOp.SUM)
+            stop_at = None
+            for j, l in enumerate(rl.tolist()[:min(world, len(ts) - r0)]):
+                l = np.float32(l)
+                if l > loss_max:
+                    loss_max = l
+                used.append(float(l))
+                if l < loss_max * thr32:             # fp32 product, as `loss < loss_max * args.thr` on 0-dim fp32 tensors
+                    stop_at = j
+                    break
+            if stop_at is not None:
+                if mine and rank > stop_at:
+                    self.plan.grad_arena.copy_(snap)
+                    if self.plan.fused_scores:
+                        self.plan.score_arena.copy_(snap_scores)
+                break
+        return torch.tensor(used, device=self.dev, dtype=torch.float32)
+
+
+def threshold_stop(losses, thr: float) -> int:
+    """Number of timesteps the `diff-pruning` loop of ddpm_prune.py:97-106 consumes for a given loss sequence (host helper,
+    same fp32 comparisons as TaylorScorer.run(thr=...))."""
+    loss_max, thr32 = np.float32(0.0), np.float32(thr)
+    for n, l in enumerate(losses, 1):
+        l = np.float32(l)
+        if l > loss_max:
+            loss_max = l
+        if l < loss_max * thr32:
+            return n
+    return len(losses)
 
 
 # --------------------------------------------------------------------------------------------------------

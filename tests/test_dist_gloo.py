@@ -52,3 +52,94 @@ def test_timestep_sharding_allreduce_equals_sequential():
         p.join(60)
         assert p.exitcode == 0
     assert err < 1e-6
+
+
+# ---- the `--pruner diff-pruning` stop rule (ddpm_prune.py:104-106) through TaylorScorer.run(thr=...), host logic only: the
+# per-pass engine is replaced by a stub that adds a known per-timestep "gradient" and returns a preset loss
+LOSS_SEQ = [1.10, 1.25, 1.05, 0.90, 0.70, 0.40, 0.20, 0.061, 0.0624, 0.05, 0.30, 0.01]   # thr 0.05 -> stops at index 7 (0.061 < 0.0625)
+
+
+def _reference_loop(losses, thr):
+    """Literal transcription of ddpm_prune.py:97-106 on fp32 0-dim tensors; returns the timesteps whose backward ran."""
+    used, loss_max = [], 0
+    for k, v in enumerate(losses):
+        loss = torch.tensor(v, dtype=torch.float32)
+        used.append(k)                                   # loss.backward()
+        if loss > loss_max:
+            loss_max = loss
+        if loss < loss_max * thr:
+            break
+    return used
+
+
+def _stub_scorer():
+    from types import SimpleNamespace
+    from diff_pruning_b200.scoring import TaylorScorer
+    sc = TaylorScorer.__new__(TaylorScorer)
+    sc.dev = torch.device("cpu")
+    sc.plan = SimpleNamespace(grad_arena=torch.zeros(16), fused_scores=True, score_arena=torch.zeros(4))
+
+    def step(t):
+        g = torch.Generator().manual_seed(1000 + t)
+        sc.plan.grad_arena += torch.randn(16, generator=g)
+        sc.plan.score_arena += float(t + 1)
+        return torch.tensor([LOSS_SEQ[t]], dtype=torch.float32)
+    sc.step = step
+    return sc
+
+
+def _expected(used):
+    arena, score = torch.zeros(16), torch.zeros(4)
+    for t in used:
+        arena += torch.randn(16, generator=torch.Generator().manual_seed(1000 + t))
+        score += float(t + 1)
+    return arena, score
+
+
+def test_threshold_stop_single_process_matches_reference_loop():
+    sys.path.insert(0, ROOT)
+    from diff_pruning_b200.scoring import threshold_stop
+    for thr in (0.05, 0.5, 0.9, 1e-6, 1.0):
+        used = _reference_loop(LOSS_SEQ, thr)
+        assert threshold_stop(LOSS_SEQ, thr) == len(used)
+        sc = _stub_scorer()
+        losses = sc.run(range(len(LOSS_SEQ)), thr=thr)
+        assert losses.numel() == len(used)
+        assert torch.equal(losses, torch.tensor(LOSS_SEQ[:len(used)], dtype=torch.float32))
+        arena, score = _expected(used)
+        assert torch.equal(sc.plan.grad_arena, arena) and torch.equal(sc.plan.score_arena, score)
+    assert _reference_loop(LOSS_SEQ, 0.05) == list(range(8))          # stops on 0.061 < fp32(1.25 * 0.05), keeps that step
+
+
+def _thr_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    out = []
+    for thr in (0.05, 0.5, 1e-6):
+        sc = _stub_scorer()
+        losses = sc.run(range(len(LOSS_SEQ)), thr=thr)                  # sharded: rank r takes t = r, r + W, ...
+        used = _reference_loop(LOSS_SEQ, thr)
+        arena, score = _expected(used)
+        out.append((losses.numel() == len(used), float((sc.plan.grad_arena - arena).abs().max()),
+                    float((sc.plan.score_arena - score).abs().max())))
+    if rank == 0:
+        q.put(out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_threshold_stop_sharded_over_ranks_equals_sequential():
+    for world in (2, 3):
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        port = 31500 + (os.getpid() % 2000) + world
+        procs = [ctx.Process(target=_thr_worker, args=(r, world, port, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        out = q.get(timeout=300)
+        for p in procs:
+            p.join(60)
+            assert p.exitcode == 0
+        for ok, e_arena, e_score in out:
+            assert ok and e_arena < 1e-5 and e_score == 0.0, (world, out)
