@@ -108,3 +108,16 @@ def test_ddpm_pipeline_is_a_container_only():
         pipe(batch_size=1)
     with pytest.raises(OSError):
         DDPMPipeline.from_pretrained("google/ddpm-cifar10-32")          # no hub access: local directories only
+
+
+def test_lr_multipliers_match_reference_get_scheduler():
+    """schedules.lr_multiplier vs LambdaLR values recorded from the reference's diffusers.optimization.get_scheduler
+    (tests/golden/lr_schedules.json, tools/gen_golden.py job `lr`)."""
+    from diff_pruning_b200.schedules import lr_multiplier
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "lr_schedules.json")))
+    assert len(gold) == 12
+    for key, vals in gold.items():
+        name, warm, total = key.split("|")
+        for step, want in vals.items():
+            got = lr_multiplier(name, int(step), int(warm), int(total))
+            assert abs(got - want) <= 1e-12 * max(1.0, abs(want)), (key, step, got, want)

@@ -366,13 +366,33 @@ def gen_ckpt():
     print("ckpt", len(sd), h.hexdigest()[:16])
 
 
+def gen_lr():
+    """diffusers.optimization.get_scheduler (optimization.py:282-340) sampled at a few optimiser steps: multipliers of the base lr."""
+    from diffusers.optimization import get_scheduler
+    out = {}
+    for name in ("constant", "constant_with_warmup", "linear", "cosine"):
+        for warm, total in ((0, 100), (5, 100), (500, 10000)):
+            steps = sorted({0, 1, 2, warm - 1, warm, warm + 1, total // 2, total - 1, total, total + 3} - {-1})
+            prm = torch.nn.Parameter(torch.zeros(1))
+            opt = torch.optim.SGD([prm], lr=1.0)
+            sch = get_scheduler(name, opt, num_warmup_steps=warm, num_training_steps=total)
+            vals, k = {}, 0
+            for s in range(max(steps) + 1):
+                if s in steps:
+                    vals[str(s)] = sch.get_last_lr()[0]
+                opt.step(); sch.step()
+            out[f"{name}|{warm}|{total}"] = vals
+    json.dump(out, open(os.path.join(OUT, "lr_schedules.json"), "w"), indent=1)
+    print("lr", len(out))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--skip-cfg1", action="store_true")
     ap.add_argument("--only", default=None)
     a = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
-    jobs = {"ckpt": gen_ckpt, "ddim": gen_ddim, "tiny": gen_tiny, "blocks": gen_blocks, "finetune": gen_finetune, "cifar_fwd": gen_cifar_fwd,
+    jobs = {"lr": gen_lr, "ckpt": gen_ckpt, "ddim": gen_ddim, "tiny": gen_tiny, "blocks": gen_blocks, "finetune": gen_finetune, "cifar_fwd": gen_cifar_fwd,
             "cfg1_s3": gen_cfg1_s3, "cfg1": gen_cfg1}
     for name, fn in jobs.items():
         if a.only and name != a.only:
