@@ -20,7 +20,7 @@
 //   conv_tc_kernel<BN>       first SS kernel (DPB200_TC_SS), one tile per CTA
 //   conv_tc_ab_kernel        (=2) one tile per CTA, TS, decoupled A / B / TMEM rings
 //   conv_tc_ps2_kernel<BK>   (=3) ps + elect.sync issue, two issuer warps, optional 16-float stages x 7, clock64() trace stamps
-//   conv_tc_pt_kernel        (=4) persistent TS: decoupled rings, two issuers, register-drained epilogue (round-2 candidate)
+//   conv_tc_pt_kernel        (=4; =5 picks it per layer for tiles with >= 27 stages) persistent TS: decoupled rings, two issuers, register-drained epilogue (round-2 candidate)
 //   wgrad_tc_kernel          weight gradient: dY^T through TMEM, X split in shared memory, split-K over pixels
 //   pack_tc / split_tf32 / transpose_batched helpers, dp_gemm_nt_tc (attention GEMMs on the persistent kernel)
 // Measurements of every variant: profiles/r01_experiments.md.
@@ -1844,7 +1844,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn g_encode = nullptr;
 int g_tc_state = -1;  // -1 unknown, 0 unavailable, 1 ok
 bool g_use_ss = false;
-int g_persistent = 1;  // DPB200_TC_PERSISTENT: 1 = persistent SS kernel, 2 = decoupled A/B-ring TS kernel, 3 = two-issuer experimental kernel, 4 = persistent TS kernel (round-2 candidate), 0 = one-ring TS kernel
+int g_persistent = 1;  // DPB200_TC_PERSISTENT: 1 = persistent SS kernel, 2 = decoupled A/B-ring TS kernel, 3 = two-issuer experimental kernel, 4 = persistent TS kernel (round-2 candidate), 5 = TS kernel for long-K tiles / default kernel otherwise, 0 = one-ring TS kernel
+static int g_pt_min_stages = 27;        // DPB200_TC_PT_MIN_STAGES: with DPB200_TC_PERSISTENT=5, tiles with at least this many pipeline stages use conv_tc_pt_kernel
 static int g_ps_bk = 32;               // DPB200_TC_PS_BK: K chunk per stage of the persistent kernel (16 -> 7 stages, 32 -> 3 stages)
 static constexpr int ps_smem_bytes(int bk) { return (bk == 16 ? 7 : 3) * 4 * 128 * bk * 4 + 2048; }
 // Row length of the packed TF32 weight tiles (dp_pack_conv_weight_tc): rows longer than 32 floats are zero-padded to a multiple of 32
@@ -1889,6 +1890,7 @@ int tc_init() {
   ok = ok && cudaFuncSetAttribute(conv_tc_ps2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ps_smem_bytes(32)) == cudaSuccess;
   ok = ok && cudaFuncSetAttribute(conv_tc_ps2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ps_smem_bytes(16)) == cudaSuccess;
   if (const char* e = getenv("DPB200_TC_PS_BK")) g_ps_bk = atoi(e) == 32 ? 32 : 16;
+  if (const char* e = getenv("DPB200_TC_PT_MIN_STAGES")) g_pt_min_stages = atoi(e);
   if (const char* e = getenv("DPB200_TC_PERSISTENT")) g_persistent = atoi(e);
   ok = ok && cudaFuncSetAttribute(conv_tc_ab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SA * A_BYTES + AB_SB * 2 * 128 * BK * 4 + 2048) == cudaSuccess;
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev); }
@@ -1953,7 +1955,7 @@ int launch_tc(const float* act, long long ld_act, int Nimg, int H, int W, int Kg
     if (!make_map(&mA, act, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, in_stride)) return DP_ERR_UNSUPPORTED;
   }
   const int BN = (Nout <= 64) ? 64 : 128;
-  if (in_stride != 1 && !(BN == 128 && (g_persistent == 1 || g_persistent == 4) && !g_use_ss)) return DP_ERR_UNSUPPORTED;   // only these kernels scale the tile origin
+  if (in_stride != 1 && !(BN == 128 && (g_persistent == 1 || g_persistent == 4 || g_persistent == 5) && !g_use_ss)) return DP_ERR_UNSUPPORTED;   // only these kernels scale the tile origin
   {
     const cuuint64_t Kg4 = (cuuint64_t)ldb;   // dp_pack_conv_weight_tc pads rows to 16 B
     cuuint64_t dims[3] = {Kg4, (cuuint64_t)Nout, (cuuint64_t)T};
@@ -1993,7 +1995,7 @@ int launch_tc(const float* act, long long ld_act, int Nimg, int H, int W, int Kg
       p.b_sub = bsub;
     }
     conv_tc_ab_kernel<<<grid, AB_THREADS, AB_SA * A_BYTES + AB_SB * 2 * 128 * BK * 4 + 2048, st>>>(mA, mBh, mBl, p);
-  } else if (BN == 128 && g_persistent == 4) {
+  } else if (BN == 128 && (g_persistent == 4 || (g_persistent == 5 && p.ntaps * p.kchunks >= g_pt_min_stages))) {   // 5 = per layer: long-K tiles on the TS kernel
     const int tiles_m = (int)grid.x, total = (int)(grid.x * grid.y);
     const int ctas = total < g_num_sms ? total : g_num_sms;
     conv_tc_pt_kernel<<<ctas, PT_THREADS, PT_SA * A_BYTES + PT_SB * 2 * 128 * BK * 4 + 2048, st>>>(mA, mBh, mBl, p, tiles_m, total);
