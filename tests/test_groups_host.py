@@ -40,3 +40,36 @@ def test_groups_lsun_family_counts():
     prod = {n for g in gs for n, k, _ in g["items"] if k == "out"}
     layers = {n for n, mod in m.named_modules() if isinstance(mod, (torch.nn.Conv2d, torch.nn.Linear))}
     assert prod == layers - {"conv_out"}          # every conv / linear output is in exactly one group
+
+
+def test_lsun_architecture_magnitude_prune_sequence_matches_reference():
+    """BASELINE config 3's six-level architecture (reduced widths), `--pruner magnitude`, ratio 0.05, through the compat call
+    sequence of ddpm_prune.py:79-116: group order / members / ch_groups, the channels the reference selected in every group,
+    post-prune shapes and the op / parameter counts (tests/golden/lsun_struct_magnitude.pt, tools/gen_golden.py `lsun_struct`)."""
+    import os
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "diff-pruning_b200", "compat"))
+    import torch_pruning as tp
+    from diffusers.models.resnet import Downsample2D, Upsample2D
+    G = load_golden("lsun_struct_magnitude.pt")
+    torch.manual_seed(0)
+    m = dp.UNet2DModel(**G["cfg"]).eval()
+    ex = {"sample": torch.randn(1, 3, 64, 64), "timestep": torch.ones((1,)).long()}
+    macs, params = tp.utils.count_ops_and_params(m, ex)
+    assert [macs, params] == G["base"]
+    pr = tp.pruner.MagnitudePruner(m, ex, importance=tp.importance.MagnitudeImportance(), iterative_steps=1, channel_groups={},
+                                   ch_sparsity=G["ratio"], ignored_layers=[m.conv_out])
+    seen = []
+    for g, ref in zip(pr.step(interactive=True), G["groups"]):
+        assert g.root == ref["root"] and g.channels == ref["channels"], (g.root, ref["root"])
+        assert norm(g.items) == norm((n, k, expand(i)) for n, k, i in ref["items"]), ref["root"]
+        assert sorted(g.idxs) == sorted(ref["idxs"]), ref["root"]            # the same channels go
+        seen.append(g.root)
+        g.prune()
+    assert seen == [g["root"] for g in G["groups"]]
+    for mod in m.modules():
+        if isinstance(mod, (Upsample2D, Downsample2D)):
+            mod.channels = mod.conv.in_channels
+    assert {k: list(v.shape) for k, v in m.state_dict().items()} == G["pruned_shapes"]
+    assert list(tp.utils.count_ops_and_params(m, ex)) == G["pruned"]

@@ -386,13 +386,47 @@ def gen_lr():
     print("lr", len(out))
 
 
+def gen_lsun_struct(ratio=0.05):
+    """The six-level LSUN-256 architecture (google/ddpm-ema-bedroom-256: BASELINE config 3, ratio 0.05) at reduced widths
+    (32, 32, 64, 64, 128, 128), `--pruner magnitude` (ddpm_prune.py:70-71: tp.importance.MagnitudeImportance()) through the
+    interactive prune sequence: pins the structural group derivation, ch_groups, the per-group magnitude scores and the selected
+    channel indices for the second headline architecture.  No gradients needed."""
+    cfg = dict(dp.LSUN256_DDPM_CONFIG, block_out_channels=(32, 32, 64, 64, 128, 128))
+    m = build(cfg)
+    example = {"sample": torch.randn(1, 3, 64, 64), "timestep": torch.ones((1,)).long()}
+    names = {mod: n for n, mod in m.named_modules()}
+    imp = tp.importance.MagnitudeImportance()
+    pruner = tp.pruner.MagnitudePruner(m, example, importance=imp, iterative_steps=1, channel_groups={}, ch_sparsity=ratio,
+                                       ignored_layers=[m.conv_out])
+    base_macs, base_params = tp.utils.count_ops_and_params(m, example)
+    groups = []
+    for g in pruner.step(interactive=True):
+        module, fn = g[0][0].target.module, g[0][0].handler
+        cur = pruner.DG.get_out_channels(module)
+        full = pruner.DG.get_pruning_group(module, fn, list(range(cur)))
+        ch_groups = pruner.get_channel_groups(full)
+        sc = imp(full, ch_groups=ch_groups)
+        groups.append({"root": names[module], "root_kind": KIND[fn], "ch_groups": int(ch_groups), "channels": int(cur),
+                       "items": [(n, k, compress(i)) for n, k, i in describe_group(full, names)],
+                       "imp": sc.clone(), "idxs": [int(i) for i in g[0][1]]})
+        g.prune()
+    for mod in m.modules():
+        if isinstance(mod, (Upsample2D, Downsample2D)):
+            mod.channels = mod.conv.in_channels
+    macs, params = tp.utils.count_ops_and_params(m, example)
+    res = {"cfg": cfg, "ratio": ratio, "groups": groups, "base": [base_macs, base_params], "pruned": [macs, params],
+           "pruned_shapes": {k: list(v.shape) for k, v in m.state_dict().items()}}
+    torch.save(res, os.path.join(OUT, "lsun_struct_magnitude.pt"))
+    print("lsun_struct", len(groups), base_params, params, base_macs, macs)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--skip-cfg1", action="store_true")
     ap.add_argument("--only", default=None)
     a = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
-    jobs = {"lr": gen_lr, "ckpt": gen_ckpt, "ddim": gen_ddim, "tiny": gen_tiny, "blocks": gen_blocks, "finetune": gen_finetune, "cifar_fwd": gen_cifar_fwd,
+    jobs = {"lsun_struct": gen_lsun_struct, "lr": gen_lr, "ckpt": gen_ckpt, "ddim": gen_ddim, "tiny": gen_tiny, "blocks": gen_blocks, "finetune": gen_finetune, "cifar_fwd": gen_cifar_fwd,
             "cfg1_s3": gen_cfg1_s3, "cfg1": gen_cfg1}
     for name, fn in jobs.items():
         if a.only and name != a.only:
