@@ -11,7 +11,7 @@ __version__ = "0.1.0"
 
 
 def __getattr__(name):   # lazy: sampling pulls in the engine / the shared library
-    if name in ("DDIMScheduler", "DDIMPipeline", "DDPMPipeline"):
+    if name in ("DDIMScheduler", "DDIMPipeline", "DDPMPipeline", "DiffusionPipeline"):
         from . import sampling
         return getattr(sampling, name)
     raise AttributeError(name)

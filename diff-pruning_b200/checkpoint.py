@@ -113,6 +113,7 @@ def load_model(cls, path: str, subfolder: Optional[str] = None, **overrides):
         sd = torch.load(bn, map_location="cpu", weights_only=True)
     else:
         raise OSError(f"diff_pruning_b200: no {SAFETENSORS_WEIGHTS_NAME} or {WEIGHTS_NAME} in {d}")
+    sd = convert_deprecated_attention_keys(sd)
     hint = ("pruned networks are stored as whole modules (torch.save(model) / torch.load, ddpm_prune.py:135, "
             "ddpm_train.py:292), not as a state dict next to the unpruned config.json")
     try:
@@ -123,6 +124,55 @@ def load_model(cls, path: str, subfolder: Optional[str] = None, **overrides):
         raise RuntimeError(f"diff_pruning_b200: weights in {d} do not match the architecture of its config.json "
                            f"(missing {list(missing)[:4]}, unexpected {list(unexpected)[:4]}): {hint}")
     return model.eval()                                   # modeling_utils.py:640 puts loaded models in eval mode
+
+
+_DEPRECATED_ATTN = (("query", "to_q"), ("key", "to_k"), ("value", "to_v"), ("proj_attn", "to_out.0"))
+
+
+def convert_deprecated_attention_keys(sd: dict) -> dict:
+    """Hub DDPM checkpoints (google/ddpm-cifar10-32, ddpm-ema-bedroom-256, ...) predate the Attention refactor and store the
+    attention projections as `<block>.query / key / value / proj_attn`; the reference renames them at load time
+    (modeling_utils.py:809-851, for blocks built with `_from_deprecated_attn_block=True`: unet_2d_blocks.py:441,730,1805).
+    Every attention block of UNet2DModel is such a block, so the rename is purely by key suffix; already-converted files pass through."""
+    out = {}
+    for k, v in sd.items():
+        parts = k.rsplit(".", 2)
+        if len(parts) == 3 and parts[2] in ("weight", "bias") and ".attentions." in k:
+            for old, new in _DEPRECATED_ATTN:
+                if parts[1] == old:
+                    k = f"{parts[0]}.{new}.{parts[2]}"
+                    break
+        out[k] = v
+    return out
+
+
+def allow_module_pickles():
+    """torch >= 2.6 defaults torch.load to weights_only=True; the reference stores and reloads WHOLE modules (`torch.save(model)`
+    ddpm_prune.py:135 / `torch.load(path)` ddpm_train.py:292, ddpm_sample.py:27).  Allow-list the classes such a pickle contains
+    (this package's module classes + the torch.nn leaves + the config containers) so the unchanged `torch.load` call works."""
+    import collections
+    import sys
+    import torch.nn as nn
+    from types import SimpleNamespace as _NS
+    from . import models
+    cls = [getattr(models, n) for n in ("UNet2DModel", "UNet2DOutput", "Timesteps", "TimestepEmbedding", "Upsample2D", "Downsample2D",
+                                        "ResnetBlock2D", "Attention", "DownBlock2D", "AttnDownBlock2D", "UNetMidBlock2D", "UpBlock2D",
+                                        "AttnUpBlock2D")]
+    cls += [nn.Conv2d, nn.Linear, nn.GroupNorm, nn.SiLU, nn.Dropout, nn.ModuleList, nn.Identity, nn.Parameter, _NS,
+            collections.OrderedDict, set]
+    # the module paths a REFERENCE-written pickle names (the weights-only unpickler matches globals by that string)
+    ref_paths = {"diffusers.models.unet_2d": ("UNet2DModel",), "diffusers.models.embeddings": ("Timesteps", "TimestepEmbedding"),
+                 "diffusers.models.resnet": ("Upsample2D", "Downsample2D", "ResnetBlock2D"),
+                 "diffusers.models.attention_processor": ("Attention",),
+                 "diffusers.models.unet_2d_blocks": ("DownBlock2D", "AttnDownBlock2D", "UNetMidBlock2D", "UpBlock2D", "AttnUpBlock2D")}
+    cls += [(getattr(models, n), f"{path}.{n}") for path, names in ref_paths.items() for n in names]
+    # the weights-only unpickler only fills plain dict / OrderedDict instances (SETITEMS), so the config container of a reference
+    # pickle (FrozenDict, an OrderedDict subclass) is materialised as the OrderedDict it is
+    cls.append((collections.OrderedDict, "diffusers.configuration_utils.FrozenDict"))
+    mod = sys.modules.get("diffusers.models.attention_processor")
+    if mod is not None and "compat" in (getattr(mod, "__file__", "") or ""):
+        cls += [getattr(mod, n) for n in ("AttnProcessor", "AttnProcessor2_0")]
+    torch.serialization.add_safe_globals(cls)
 
 
 # ------------------------------------------------------------------------------------------------ pipelines

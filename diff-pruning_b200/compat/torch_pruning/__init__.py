@@ -85,7 +85,9 @@ class MagnitudePruner:
     def step(self, interactive=False):
         def gen():
             for root in list(self._init):
-                g = next(gg for gg in _pr.build_groups(self.model, self.ignored_layers, self._order) if gg["root"] == root)
+                g = _pr.group_of_root(self.model, root, self.ignored_layers, self._order)
+                if g is None:
+                    continue
                 n_pruned = g["channels"] - int(self._init[root] * (1 - self.ch_sparsity))
                 if self.round_to:
                     n_pruned -= n_pruned % self.round_to

@@ -123,6 +123,8 @@ class Plan:
         self.dropout_seed_dev = torch.zeros(1, device=self.dev, dtype=torch.int64)
         self._n_dropout = 0
         self.fused_scores = fused_scores and need_grad
+        self.generation = 0            # forward counter of the autograd boundary (see _UNetFunction)
+        self._calls = 0                # module-forward counter: advances the dropout stream on the autograd / compat path
         self.scores: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
         if self.fused_scores:   # one flat vector: [out-channel | in-channel] signed scores of every conv / linear weight
             n = sum(p.shape[0] + p.shape[1] for p in self.params if p.dim() >= 2)
@@ -193,7 +195,11 @@ class Plan:
         return tuple((p.data_ptr(), tuple(p.shape)) for p in self.params)
 
     def weight_version(self):
-        return sum(p._version for p in self.params)
+        """(sum of autograd version counters, explicit weights epoch of the model).  The version counters catch optimiser steps and
+        load_state_dict; writes torch does not track — `param.data.copy_()` (how EMAModel.copy_to / restore write weights,
+        training_utils.py:216-224 of the reference's diffusers) and kernels that update the parameter arena through raw pointers
+        (FinetuneStepper) — are covered by the epoch, bumped by invalidate_packs()."""
+        return (sum(p._version for p in self.params), self.model.__dict__.get("_dpb200_weights_epoch", 0))
 
     def _score_views(self, w: nn.Parameter, K: int, Cin: int):
         got = self.scores.get(id(w))
@@ -719,11 +725,18 @@ class Plan:
         for f in self.pack:
             f(s)
 
-    def ensure_packed(self):
+    def ensure_packed(self, force: bool = False):
         v = self.weight_version()
-        if v != self._packed_version:
+        if force or v != self._packed_version:
             self.run_pack()
             self._packed_version = v
+
+    def check_current(self):
+        """Raises when the model's parameters were replaced (pruned / re-pointed) after this plan was built: its launch lists
+        still address the old Parameter storage and would silently accumulate into an arena that is no longer `.grad`."""
+        if tuple((p.data_ptr(), tuple(p.shape)) for p in self.model.parameters()) != self.signature():
+            raise RuntimeError("diff_pruning_b200: the model's parameters were replaced after this plan was built "
+                               "(pruning / load / re-pointing); create a new TaylorScorer / FinetuneStepper")
 
     def run_forward(self, s: Optional[int] = None):
         s = _stream() if s is None else s
@@ -768,15 +781,20 @@ class Plan:
 class _UNetFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, sample, timesteps, plan, *params):
-        plan.ensure_packed()
         plan.load_input_nchw(sample, timesteps)
         plan.run_forward()
         ctx.plan = plan
+        plan.generation += 1          # activations live in the plan's buffers: a later forward overwrites them
+        ctx.generation = plan.generation
         return plan.output_nchw()
 
     @staticmethod
     def backward(ctx, gout):
         plan: Plan = ctx.plan
+        if plan.generation != ctx.generation:
+            raise RuntimeError("diff_pruning_b200: backward() of a UNet forward whose activations were overwritten by a later forward "
+                               "of the same (batch, resolution) plan (two forwards before one backward: gradient accumulation over "
+                               "micro-batches, or sampling between forward and backward).  Call backward() before the next forward.")
         plan.attach_grads()
         plan.load_grad_nchw(gout)
         plan.run_backward()
@@ -803,13 +821,58 @@ def unet_apply(model: UNet2DModel, sample: torch.Tensor, timesteps: torch.Tensor
         raise TypeError("diff_pruning_b200 engine computes in fp32; got %s" % sample.dtype)
     B, Cc, H, W = sample.shape
     need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in model.parameters())
+    if need_grad and sample.requires_grad:
+        raise RuntimeError("diff_pruning_b200: the engine does not produce d(loss)/d(sample) (the reference loops never need it: "
+                           "noisy images are leaves without grad, ddpm_prune.py:99-100); detach the input")
     plan = get_plan(model, B, H, W, sample.device, need_grad)
+    # Packed weight copies: this module-forward path cannot see every way weights get written (`param.data.copy_` leaves no trace),
+    # so it re-packs on EVERY call (~230 small launches, < 1 ms at C1) unless the caller froze the weights for a loop
+    # (frozen_weights(): the DDIM pipelines) — the explicit TaylorScorer / FinetuneStepper APIs manage their own packs.
+    plan.ensure_packed(force=not model.__dict__.get("_dpb200_frozen", False))
+    if plan.training and plan._n_dropout:
+        plan._calls += 1                # a fresh dropout stream per forward (and per rank), like torch's advancing Philox offset
+        plan.dropout_seed_dev.fill_(_dropout_seed(plan._calls))
     if need_grad:
         return _UNetFunction.apply(sample, timesteps, plan, *plan.params)
-    plan.ensure_packed()
     plan.load_input_nchw(sample, timesteps)
     plan.run_forward()
     return plan.output_nchw()
+
+
+def _dropout_seed(step: int) -> int:
+    """Per-step dropout seed, decorrelated across data-parallel ranks (every rank must draw its own masks)."""
+    rank = 0
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            rank = dist.get_rank()
+    except Exception:
+        rank = 0
+    return (0x5DEECE66D * step + 0x9E3779B97F4A7C15 * rank) & 0x7FFFFFFFFFFF
+
+
+def invalidate_packs(model: UNet2DModel) -> None:
+    """Tell every cached plan of `model` that its weights changed through a path torch's version counters do not see
+    (`param.data.copy_`, raw-pointer kernels).  The next forward of any plan re-packs."""
+    model.__dict__["_dpb200_weights_epoch"] = model.__dict__.get("_dpb200_weights_epoch", 0) + 1
+
+
+class frozen_weights:
+    """`with frozen_weights(model):` — weights are packed once on entry and the per-call re-pack of the module-forward path is
+    skipped inside (sampling loops: 100 forwards on fixed weights)."""
+
+    def __init__(self, model: UNet2DModel):
+        self.model = model
+
+    def __enter__(self):
+        invalidate_packs(self.model)            # the first forward inside packs whatever the weights are NOW
+        self.prev = self.model.__dict__.get("_dpb200_frozen", False)
+        self.model.__dict__["_dpb200_frozen"] = True
+        return self
+
+    def __exit__(self, *exc):
+        self.model.__dict__["_dpb200_frozen"] = self.prev
+        return False
 
 
 def add_noise_cuda(sched, x0: torch.Tensor, noise: torch.Tensor, timesteps: torch.Tensor) -> torch.Tensor:

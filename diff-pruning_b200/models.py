@@ -396,7 +396,47 @@ class UNet2DModel(nn.Module):
         # (torch.save(model) at ddpm_prune.py:135 and copy.deepcopy in op counters must keep working)
         d = self.__dict__.copy()
         d.pop("_dpb200_plans", None)
+        d.pop("_dpb200_frozen", None)
+        d.pop("_dpb200_weights_epoch", None)
         return d
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        if "config" not in self.__dict__ and "_internal_dict" in self.__dict__:
+            self._adopt_reference_layout()
+
+    def _adopt_reference_layout(self):
+        """This instance was unpickled from a whole-module pickle written by the REFERENCE (`torch.save(model)`, ddpm_prune.py:135 /
+        ddpm_train.py:487-493): its attribute soup is diffusers' (config in `_internal_dict`, processors, ...), its leaves carry
+        the (possibly pruned) weights.  Rebuild this package's module tree from the stored config and transplant every leaf's
+        tensors and widths; `Attention.scale` keeps the pickled (stale after pruning, attention_processor.py:87) value."""
+        names = set(inspect.signature(UNet2DModel.__init__).parameters) - {"self", "unused"}
+        cfg = {k: v for k, v in dict(self.__dict__["_internal_dict"]).items() if k in names and not k.startswith("_")}
+        new = UNet2DModel(**cfg)
+        for name, leaf in new.named_modules():
+            if isinstance(leaf, (nn.Conv2d, nn.Linear, nn.GroupNorm)):
+                src = self.get_submodule(name)
+                leaf.weight = nn.Parameter(src.weight.detach().clone(), requires_grad=src.weight.requires_grad)
+                if src.bias is not None:
+                    leaf.bias = nn.Parameter(src.bias.detach().clone(), requires_grad=src.bias.requires_grad)
+                if isinstance(leaf, nn.Conv2d):
+                    leaf.out_channels, leaf.in_channels = leaf.weight.shape[0], leaf.weight.shape[1]
+                elif isinstance(leaf, nn.Linear):
+                    leaf.out_features, leaf.in_features = leaf.weight.shape
+                else:
+                    leaf.num_channels = leaf.weight.shape[0]
+            elif isinstance(leaf, Attention):
+                leaf.scale = float(self.get_submodule(name).scale)
+            elif isinstance(leaf, nn.Dropout):
+                leaf.p = float(self.get_submodule(name).p)
+            elif isinstance(leaf, (Upsample2D, Downsample2D)):
+                leaf.channels, leaf.out_channels = leaf.conv.in_channels, leaf.conv.out_channels
+        for m in new.modules():      # widths of the containers' convs were set above; refresh the static attributes (ddpm_prune.py:112-116)
+            if isinstance(m, (Upsample2D, Downsample2D)):
+                m.channels, m.out_channels = m.conv.in_channels, m.conv.out_channels
+        new.train(bool(self.__dict__.get("training", False)))
+        self.__dict__.clear()
+        self.__dict__.update(new.__dict__)
 
     @property
     def dtype(self):

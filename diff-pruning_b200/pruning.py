@@ -277,6 +277,22 @@ def build_groups(model, ignored_layers: Sequence[nn.Module] = (), module_order: 
     return groups
 
 
+def group_of_root(model, root: str, ignored_layers: Sequence[nn.Module] = (), module_order: Sequence[str] = None):
+    """The CURRENT group rooted at `root` (the reference re-derives every group from the live graph right before it is pruned,
+    metapruner.py:208), or None when it must be skipped: the reference's `_check_sparsity` (metapruner.py:172-194) refuses a group
+    one of whose members is down to a single channel."""
+    for g in build_groups(model, ignored_layers, module_order):
+        if g["root"] == root:
+            mods = dict(model.named_modules())
+            for name, kind, _ in g["items"]:
+                w = mods[name].weight
+                if (w.shape[1] if kind == "in" else w.shape[0]) == 1:
+                    return None
+            return g
+    raise KeyError(f"diff_pruning_b200: pruning group rooted at {root!r} no longer exists in the model (was the module tree edited "
+                   "between MagnitudePruner(...) and step()?)")
+
+
 def taylor_prune(model, ratio: float, variant: str = "taylor", ignored_layers: Sequence[nn.Module] = (), round_to=None) -> List[dict]:
     """ddpm_prune.py:79-116 without torch_pruning: for each group in the reference's order, score it ON DEVICE from the
     accumulated Parameter.grad (dp_taylor_reduce), select the lowest-importance channels (metapruner.py:225-249), slice
@@ -287,7 +303,9 @@ def taylor_prune(model, ratio: float, variant: str = "taylor", ignored_layers: S
     init = {g["root"]: g["channels"] for g in build_groups(model, ignored_layers, morder)}
     record = []
     for root in list(init):
-        g = next(gg for gg in build_groups(model, ignored_layers, morder) if gg["root"] == root)
+        g = group_of_root(model, root, ignored_layers, morder)
+        if g is None:
+            continue
         mods = dict(model.named_modules())
         n_pruned = g["channels"] - int(init[root] * (1 - ratio))
         if round_to:

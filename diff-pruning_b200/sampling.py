@@ -140,9 +140,11 @@ class DDIMPipeline:
         gdev = generator.device if generator is not None else self.device
         image = torch.randn(shape, generator=generator, device=gdev, dtype=torch.float32).to(self.device)
         self.scheduler.set_timesteps(num_inference_steps)
-        for t in self.scheduler.timesteps:
-            eps = self.unet(image, int(t)).sample
-            image = self.scheduler.step(eps, int(t), image, eta=eta, generator=generator).prev_sample
+        from .engine import frozen_weights
+        with frozen_weights(self.unet):           # weights are packed once for the whole loop (whatever they are NOW: EMA copy_to etc.)
+            for t in self.scheduler.timesteps.tolist():
+                eps = self.unet(image, t).sample
+                image = self.scheduler.step(eps, t, image, eta=eta, generator=generator).prev_sample
         image = (image / 2 + 0.5).clamp(0, 1).cpu().permute(0, 2, 3, 1).numpy()
         if output_type == "pil":
             from PIL import Image  # optional dependency, like the reference
@@ -183,3 +185,20 @@ class DDPMPipeline:
     def __call__(self, *a, **kw):
         raise NotImplementedError("diff_pruning_b200: ancestral DDPM sampling is not on the hot path; build "
                                   "DDIMPipeline(unet=pipeline.unet, scheduler=DDIMScheduler.from_config(pipeline.scheduler.config))")
+
+
+class DiffusionPipeline:
+    """`DiffusionPipeline.from_pretrained(dir)` (pipeline_utils.py:563-1000; imported at ddpm_prune.py:1): reads model_index.json and
+    builds the pipeline class it names (DDPMPipeline / DDIMPipeline — the two of this path)."""
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, **kw):
+        import json
+        import os
+        from . import checkpoint
+        fn = os.path.join(pretrained_model_name_or_path, checkpoint.MODEL_INDEX_NAME)
+        name = json.load(open(fn, encoding="utf-8")).get("_class_name", "DDPMPipeline") if os.path.isfile(fn) else "DDPMPipeline"
+        classes = {"DDPMPipeline": DDPMPipeline, "DDIMPipeline": DDIMPipeline}
+        if name not in classes:
+            raise NotImplementedError(f"diff_pruning_b200: pipeline class {name} is outside the DDPM path")
+        return classes[name].from_pretrained(pretrained_model_name_or_path, **kw)

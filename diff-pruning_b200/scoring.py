@@ -21,7 +21,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib as L
-from .engine import Plan, _stream, get_plan
+from .engine import Plan, _dropout_seed, _stream, get_plan, invalidate_packs
 from .models import UNet2DModel, ddpm_alphas_cumprod
 
 
@@ -106,6 +106,7 @@ class TaylorScorer:
     def step(self, t) -> torch.Tensor:
         """One pass at timestep(s) t (int, or a (B,) tensor).  Returns the device loss scalar (no sync)."""
         p = self.plan
+        p.check_current()
         p.attach_grads()
         p.ensure_packed()
         if torch.is_tensor(t):
@@ -389,6 +390,7 @@ class FinetuneStepper:
         if self.plan is None:
             self._setup(B, C_, H, W)
         p = self.plan
+        p.check_current()
         self.clean.copy_(clean, non_blocking=True)
         self.noise.copy_(noise, non_blocking=True)
         p.t_dev.copy_(timesteps.to(device=self.dev, dtype=torch.int64), non_blocking=True)
@@ -396,7 +398,7 @@ class FinetuneStepper:
         t = self.steps_done
         bc = torch.tensor([self.lr / (1.0 - self.betas[0] ** t), math.sqrt(1.0 - self.betas[1] ** t)], dtype=torch.float32)
         self.step_scalars.copy_(bc, non_blocking=True)
-        p.dropout_seed_dev.fill_(0x5DEECE66D * t & 0x7FFFFFFFFFFF)
+        p.dropout_seed_dev.fill_(_dropout_seed(t))   # per step AND per rank: data-parallel ranks draw different masks
         if self.use_graph and self.g_main is None:
             # warm-up once outside capture (lazy module loading), on a side stream as torch requires
             side = torch.cuda.Stream(device=self.dev)
@@ -416,4 +418,5 @@ class FinetuneStepper:
             self.g_tail.replay()
         else:
             self._tail()
+        invalidate_packs(self.model)   # the Adam kernel wrote the parameter arena through raw pointers: other cached plans are stale
         return self.loss

@@ -212,27 +212,44 @@ class VariantTaylor:
         return torch.stack([i for i in imps if len(i) == size], 0).sum(0)
 
 
-def gen_cfg1(n_steps=100, ratio=0.3, B=16, out_name="cifar_cfg1.pt"):
+def gen_cfg1(n_steps=100, ratio=0.3, B=16, out_name="cifar_cfg1.pt", cfg=None, hw=32, timesteps=None, eps_stride=None):
     import copy
     os.chdir("/tmp")  # prune_local writes ./run/pruning_logs
-    m0 = build(cifar_cfg())
+    m0 = build(cifar_cfg() if cfg is None else cfg)
     sched = DDPMScheduler(num_train_timesteps=1000)
-    clean, noise = inputs(B, 32)
-    example = {"sample": torch.randn(1, 3, 32, 32), "timestep": torch.ones((1,)).long()}
+    clean, noise = inputs(B, hw)
+    example = {"sample": torch.randn(1, 3, hw, hw), "timestep": torch.ones((1,)).long()}
     m0.zero_grad()
     m0.eval()
-    losses = []
+    losses, eps_sub = [], []
     t0 = time.time()
-    for k in range(n_steps):
+    timesteps = list(range(n_steps)) if timesteps is None else list(timesteps)
+    cache = os.path.join("/tmp", out_name + ".passes")          # scratch cache of the (slow) passes while iterating on this script
+    if os.path.exists(cache):
+        c = torch.load(cache, weights_only=False)
+        losses, eps_sub = c["losses"], c["eps_sub"]
+        for k_, p_ in m0.named_parameters():
+            p_.grad = c["grads"][k_]
+        timesteps_run = []
+    else:
+        timesteps_run = timesteps
+    for k in timesteps_run:
         t = (k * torch.ones(B)).long()
         out = m0(sched.add_noise(clean, noise, t), t).sample
         loss = torch.nn.functional.mse_loss(out, noise)
         loss.backward()
         losses.append(loss.item())
-        if k % 10 == 0:
-            print(f"  cfg1 pass {k} loss {losses[-1]:.7f} ({time.time() - t0:.0f}s)", flush=True)
+        if eps_stride:   # strided sample of eps_hat (the full tensor would be MBs per timestep)
+            eps_sub.append(out.detach()[:, :, ::eps_stride, ::eps_stride].clone())
+        if k % 10 == 0 or hw > 32:
+            print(f"  {out_name} pass t={k} loss {losses[-1]:.7f} ({time.time() - t0:.0f}s)", flush=True)
+    if hw > 32 and not os.path.exists(cache):
+        torch.save({"losses": losses, "eps_sub": eps_sub, "grads": {k_: p_.grad for k_, p_ in m0.named_parameters()}}, cache)
     grad_fp = {k: fp(p.grad) for k, p in m0.named_parameters()}
-    res = {"n_steps": n_steps, "ratio": ratio, "B": B, "losses": losses, "grad_fp": grad_fp, "variants": {}}
+    res = {"n_steps": len(timesteps), "timesteps": timesteps, "ratio": ratio, "B": B, "hw": hw, "losses": losses, "grad_fp": grad_fp,
+           "variants": {}}
+    if eps_stride:
+        res["eps_stride"], res["eps_sub"] = eps_stride, eps_sub
     for variant in ("vendored", "taylor", "diff"):
         m = copy.deepcopy(m0)
         for (k, p), (_, q) in zip(m.named_parameters(), m0.named_parameters()):
@@ -262,8 +279,10 @@ def gen_cfg1(n_steps=100, ratio=0.3, B=16, out_name="cifar_cfg1.pt"):
             pr_items = describe_group(g, names)
             # index mapping is positional: pruned idxs of every item == its full idxs at the selected positions
             # (same traversal => same item order; a layer may appear twice when both halves of a concat are in the group)
-            assert len(full_items) == len(pr_items)
-            for (n, k, i), (n2, k2, fi) in zip(pr_items, full_items):
+            # (a GroupNorm-coupled group whose per-GN-group quota n_pruned // 32 is 0 — every such group at ratio 0.05 — is yielded
+            #  with an EMPTY selection and prunes nothing: metapruner.py:237-246)
+            assert len(full_items) == len(pr_items) or not sel
+            for (n, k, i), (n2, k2, fi) in zip(pr_items if sel else [], full_items):
                 # a layer fed by BOTH halves of a concat owned by this group appears once with the two index lists
                 # merged (len = parts * channels); such items are skipped by the importance (:422-426) but pruned.
                 parts = len(fi) // cur
@@ -283,13 +302,22 @@ def gen_cfg1(n_steps=100, ratio=0.3, B=16, out_name="cifar_cfg1.pt"):
             t = (10 * torch.ones(2)).long()
             out = m(sched.add_noise(clean[:2], noise[:2], t), t).sample
         res["variants"][variant] = {"groups": groups, "base": [base_macs, base_params], "pruned": [macs, params],
-                                    "pruned_shapes": shapes, "pruned_eps_b2_t10": out.clone()}
+                                    "pruned_shapes": shapes,
+                                    "pruned_eps_b2_t10": (out[:, :, ::eps_stride, ::eps_stride] if eps_stride else out).clone()}
         print("cfg1", variant, base_params, params, macs, len(groups), sum(len(g["idxs"]) for g in groups), flush=True)
     torch.save(res, os.path.join(OUT, out_name))
 
 
 def gen_cfg1_s3():
     gen_cfg1(n_steps=3, out_name="cifar_cfg1_s3.pt")
+
+
+def gen_cfg3_s3():
+    """BASELINE config 3 (google/ddpm-ema-bedroom-256 architecture, README.md:140-148: --batch_size 4 --pruning_ratio 0.05) with 3 of
+    the 1000 timesteps (t = 0, 500, 999): losses, a strided sample of eps_hat, gradient fingerprints and the interactive prune
+    sequence (scores + selected channels) for all three importance variants.  ~2 CPU-minutes for the passes."""
+    gen_cfg1(ratio=0.05, B=4, out_name="lsun_cfg3_s3.pt", cfg=dict(dp.LSUN256_DDPM_CONFIG), hw=256, timesteps=(0, 500, 999),
+             eps_stride=4)
 
 
 def gen_finetune():
@@ -420,17 +448,49 @@ def gen_lsun_struct(ratio=0.05):
     print("lsun_struct", len(groups), base_params, params, base_macs, macs)
 
 
+def gen_ref_pickle():
+    """A whole-module pickle exactly as the reference writes it (`torch.save(model)`, ddpm_prune.py:135) for a small member of the
+    family after a `--pruner magnitude` prune at ratio 0.3 — default AttnProcessor2_0 objects, FrozenDict config and all — plus eps_hat
+    of that network (legacy processor, the only one that runs on pruned widths).  Pins `torch.load(pruned_ckpt)` at ddpm_train.py:292
+    / ddpm_sample.py:27 against this package's classes."""
+    os.chdir("/tmp")
+    cfg = dict(dp.TINY_TEST_CONFIG, block_out_channels=(16, 32))
+    torch.manual_seed(0)
+    m = UNet2DModel(**cfg).eval()
+    example = {"sample": torch.randn(1, 3, 16, 16), "timestep": torch.ones((1,)).long()}
+    pruner = tp.pruner.MagnitudePruner(m, example, importance=tp.importance.MagnitudeImportance(), iterative_steps=1,
+                                       channel_groups={}, ch_sparsity=0.3, ignored_layers=[m.conv_out])
+    for g in pruner.step(interactive=True):
+        g.prune()
+    for mod in m.modules():
+        if isinstance(mod, (Upsample2D, Downsample2D)):
+            mod.channels = mod.conv.in_channels
+    m.zero_grad()
+    del pruner
+    torch.save(m, os.path.join(OUT, "ref_pruned_small.pth"))
+    legacy_attn(m)
+    sched = DDPMScheduler(num_train_timesteps=1000)
+    clean, noise = inputs(2, 16)
+    t = torch.tensor([3, 950]).long()
+    with torch.no_grad():
+        out = m(sched.add_noise(clean, noise, t), t).sample
+    torch.save({"cfg": cfg, "t": t, "eps": out, "shapes": {k: list(v.shape) for k, v in m.state_dict().items()},
+                "scales": {n: float(a.scale) for n, a in m.named_modules() if isinstance(a, Attention)}},
+               os.path.join(OUT, "ref_pruned_small_out.pt"))
+    print("ref_pickle", os.path.getsize(os.path.join(OUT, "ref_pruned_small.pth")), sum(p.numel() for p in m.parameters()))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--skip-cfg1", action="store_true")
     ap.add_argument("--only", default=None)
     a = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
-    jobs = {"lsun_struct": gen_lsun_struct, "lr": gen_lr, "ckpt": gen_ckpt, "ddim": gen_ddim, "tiny": gen_tiny, "blocks": gen_blocks, "finetune": gen_finetune, "cifar_fwd": gen_cifar_fwd,
-            "cfg1_s3": gen_cfg1_s3, "cfg1": gen_cfg1}
+    jobs = {"ref_pickle": gen_ref_pickle, "lsun_struct": gen_lsun_struct, "lr": gen_lr, "ckpt": gen_ckpt, "ddim": gen_ddim, "tiny": gen_tiny, "blocks": gen_blocks, "finetune": gen_finetune, "cifar_fwd": gen_cifar_fwd,
+            "cfg1_s3": gen_cfg1_s3, "cfg3_s3": gen_cfg3_s3, "cfg1": gen_cfg1}
     for name, fn in jobs.items():
         if a.only and name != a.only:
             continue
-        if name.startswith("cfg1") and a.skip_cfg1:
+        if name.startswith("cfg") and a.skip_cfg1:
             continue
         fn()
