@@ -1,13 +1,17 @@
 #!/usr/bin/env python
 """bench.py — Taylor-score UNet fwd+bwd passes/sec (BASELINE.json metric) on N B200s.
 
-A "step" = one pass of ddpm_prune.py:97-102 (add_noise -> UNet fwd -> mse -> full bwd, gradients accumulated) over
-one synthetic Gaussian batch.  Workload (config.workload): C1 = CIFAR-10 DDPM UNet (tools/ddpm_cifar10_config.json,
-seed-0 random init), batch 128 x 3x32x32 — BASELINE configs[1] ("DDPM CIFAR-10 32x32 ... 1xB200"; batch from
-scripts/prune_ddpm_cifar10.sh).  Multi-GPU: timesteps are sharded across ranks (weak scaling: every rank runs K
-steps on its own timesteps) and the flat gradient arena is all-reduced ONCE at the end, inside the timed region.
+A "step" = one pass of ddpm_prune.py:97-102 (add_noise -> UNet fwd -> mse -> full bwd, gradients accumulated) over one synthetic
+Gaussian batch.  Workloads (--config):
+  c1 (default)  CIFAR-10 DDPM UNet (tools/ddpm_cifar10_config.json, seed-0 random init), batch 128 x 3x32x32 — BASELINE configs[1]
+                ("DDPM CIFAR-10 32x32 ... 1xB200"; batch from scripts/prune_ddpm_cifar10.sh).
+  c3            google/ddpm-ema-bedroom-256 architecture (seed-0 random init), batch 4 x 3x256x256, ratio 0.05 — BASELINE configs[2]
+                (README.md:140-148), the configuration the north star shards over 8 GPUs.
+Multi-GPU: timesteps are sharded across ranks (weak scaling: every rank runs K steps on its own timesteps) and the flat gradient arena
+is all-reduced ONCE at the end, inside the timed region.  Secondary leg (`finetune`): the pruned-UNet finetune step of
+ddpm_train.py:437-469 on the ratio-0.3 network (imgs/s; fp32-grade and, separately, the bf16 tier of BASELINE configs[3]).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--no-graph]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c1|c3] [--batch B] [--no-graph]
 Under torchrun the usual RANK/LOCAL_RANK/WORLD_SIZE/MASTER_* env is used; rank 0 prints ONE JSON line.
 """
 import argparse
@@ -17,7 +21,6 @@ import statistics
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -27,7 +30,16 @@ import torch  # noqa: E402
 
 METRIC = "taylor_score_unet_fwd_bwd_passes_per_sec"
 UNIT = "passes/s"
-CONV_FLOP_PER_IMAGE_PASS = 34.27e9   # 6 x 5.712 G MACs-equivalents, conv layers only
+
+# conv_flop: algorithmic FLOPs of the 4-D-weight convolutions per image per pass (fprop + dgrad + wgrad = 6 x MACs), SURVEY.md §8(d)
+CONFIGS = {
+    "c1": dict(model="CIFAR10_DDPM_CONFIG", hw=32, batch=128, conv_flop=34.27e9, ratio=0.3,
+               name="C1 CIFAR-10 DDPM UNet2DModel (35.7M params, seed-0 init)",
+               cpu_sample=(128, 32)),                # the reference arm runs the SAME batch (one full pass ~ seconds on the host cores)
+    "c3": dict(model="LSUN256_DDPM_CONFIG", hw=256, batch=4, conv_flop=1.4806e12, ratio=0.05,
+               name="C3 LSUN-256 DDPM UNet2DModel (113.7M params, google/ddpm-ema-bedroom-256 architecture, seed-0 init)",
+               cpu_sample=(1, 128)),                 # a full B=4 256x256 CPU pass takes minutes: bounded sample = 1 image at 128x128 (1/16 of the conv work)
+}
 
 
 def peaks():
@@ -80,24 +92,34 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def synth_batch(B, seed_off=0):
+def synth_batch(B, hw=32, seed_off=0):
     g1, g2 = torch.Generator().manual_seed(1 + seed_off), torch.Generator().manual_seed(2 + seed_off)
-    return torch.randn(B, 3, 32, 32, generator=g1), torch.randn(B, 3, 32, 32, generator=g2)
+    return torch.randn(B, 3, hw, hw, generator=g1), torch.randn(B, 3, hw, hw, generator=g2)
 
 
-def _cpu_setup(sample_B):
+# ------------------------------------------------------------------------------------------------------------------------
+# baselines: the oracle port (torch ATen ops = the reference's own backend) on the host cores, and the same modules torch-eager
+# on the GPU (cuDNN, TF32 on/off) — SURVEY.md §8(d): "time torch-eager on the same B200 as the real bar to beat"
+# ------------------------------------------------------------------------------------------------------------------------
+def _oracle_setup(cfg_key, sample_B, sample_hw, device="cpu"):
     import diff_pruning_b200 as dp
     from oracle import unet_oracle as orc
+    mcfg = getattr(dp, CONFIGS[cfg_key]["model"])
     torch.manual_seed(0)
-    sd = {k: v.detach().clone().requires_grad_(True) for k, v in dp.UNet2DModel(**dp.CIFAR10_DDPM_CONFIG).state_dict().items()}
-    ac = orc.alphas_cumprod()
-    clean, noise = synth_batch(sample_B)
-    return (lambda k: orc.taylor_pass(sd, dp.CIFAR10_DDPM_CONFIG, ac, clean, noise, (k * torch.ones(sample_B)).long()))
+    sd = {k: v.detach().clone().to(device).requires_grad_(True) for k, v in dp.UNet2DModel(**mcfg).state_dict().items()}
+    ac = orc.alphas_cumprod().to(device)
+    clean, noise = synth_batch(sample_B, sample_hw)
+    clean, noise = clean.to(device), noise.to(device)
+
+    def one_pass(k):
+        t = torch.full((sample_B,), int(k), dtype=torch.long, device=device)
+        return orc.taylor_pass(sd, mcfg, ac, clean, noise, t)
+    return one_pass
 
 
 def best_cpu_threads(one_pass):
-    """Give the CPU arm its best thread count: torch's intra-op pool over-subscribes badly on 100+ core hosts for
-    these small convs (measured 79 s/pass at 128 threads vs ~1.5 s at 8-32), so try a few and keep the fastest."""
+    """Give the CPU arm its best thread count: torch's intra-op pool over-subscribes badly on 100+ core hosts for these convs
+    (measured 79 s/pass at 128 threads vs ~1.5 s at 8-32, C1 batch 16), so try a few and keep the fastest."""
     ncpu = os.cpu_count() or 1
     cands = sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu})
     best, best_t = cands[0], None
@@ -107,94 +129,220 @@ def best_cpu_threads(one_pass):
         t0 = time.time(); one_pass(1); dt = time.time() - t0
         if best_t is None or dt < best_t:
             best, best_t = c, dt
-        if dt > 1.25 * best_t:            # past the knee (larger pools only get worse: 128 threads = 79 s/pass): stop
+        if dt > 1.25 * best_t:            # past the knee (larger pools only get worse): stop
             break
     torch.set_num_threads(best)
-    return best
+    return best, best_t
 
 
-def cpu_oracle_passes(batch_equiv, sample_B, min_seconds, max_passes, threads=None):
-    """Times the CPU restatement of the reference path (oracle port; torch CPU ATen ops, the reference's own backend)."""
-    one_pass = _cpu_setup(sample_B)
-    threads = threads or best_cpu_threads(one_pass)
-    torch.set_num_threads(threads)
+def _sample_plan(cfg_key, B, budget_s, n_steps):
+    """(sample_B, sample_hw, work fraction of one full step): the full batch when n_steps of it fit the budget, else the bounded sample
+    the config names."""
+    c = CONFIGS[cfg_key]
+    sB, shw = c["cpu_sample"]
+    sB = min(sB, B)
+    return sB, shw, (sB * shw * shw) / float(B * c["hw"] * c["hw"])
+
+
+def cpu_oracle_passes(cfg_key, B, min_seconds, max_passes):
+    """cpu_baseline: the CPU restatement of the reference path (oracle port) timed on the host cores, bounded sample."""
+    c = CONFIGS[cfg_key]
+    sB, shw = (16, 32) if cfg_key == "c1" else c["cpu_sample"]        # ~10-30 s of CPU work inside the default GPU run
+    frac = (sB * shw * shw) / float(B * c["hw"] * c["hw"])
+    one_pass = _oracle_setup(cfg_key, sB, shw)
+    threads, _ = best_cpu_threads(one_pass)
     one_pass(0)
-    times = []
-    t_all = time.time()
-    k = 1
+    times, t_all, k = [], time.time(), 1
     while len(times) < max_passes and (time.time() - t_all < min_seconds or len(times) < 2):
-        t0 = time.time()
-        one_pass(k)
-        times.append(time.time() - t0)
-        k += 1
+        t0 = time.time(); one_pass(k); times.append(time.time() - t0); k += 1
     med = statistics.median(times)
-    return {"value": (sample_B / med) / batch_equiv, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{threads} of {os.cpu_count()} host threads (fastest of a short sweep); {len(times)} timed + 1 warm-up oracle passes at batch {sample_B} (median {med:.2f} s/pass, best "
-                      f"{min(times):.2f}), scaled by {sample_B}/{batch_equiv} to batch-{batch_equiv} passes; loadavg {os.getloadavg()[0]:.1f}"}
+    return {"value": frac / med, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{threads} of {os.cpu_count()} host threads (fastest of a short sweep); {len(times)} timed + 1 warm-up oracle passes at batch {sB} x "
+                      f"{shw}x{shw} (median {med:.2f} s, best {min(times):.2f}) = {frac:.4g} of the conv work of one batch-{B} {c['hw']}x{c['hw']} pass, scaled by "
+                      f"that fraction; loadavg {os.getloadavg()[0]:.1f}"}
+
+
+def gpu_eager_passes(cfg_key, B, dev, n=5):
+    """The reference's modules as torch-eager ops on THIS GPU (cuDNN / cuBLAS / ATen), same batch and resolution: the bar SURVEY.md
+    §0.1 sets.  torch's default is cudnn.allow_tf32=True (convolutions in single-pass TF32) and matmul.allow_tf32=False; the fp32 row
+    switches cuDNN's TF32 off as well, which is the precision class the 3xTF32 tier of this repo delivers."""
+    c = CONFIGS[cfg_key]
+    out = {}
+    prev = torch.backends.cudnn.allow_tf32
+    try:
+        one_pass = _oracle_setup(cfg_key, B, c["hw"], device=dev)
+        for name, tf32 in (("cudnn_tf32", True), ("fp32", False)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            for k in range(3):
+                one_pass(k)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for k in range(n):
+                one_pass(3 + k)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / n
+            out[name] = {"passes_per_s": 1e3 / ms, "ms_per_pass": ms}
+    except Exception as e:                      # an OOM of the eager graph must not cost the bench line
+        out["error"] = f"{type(e).__name__}: {str(e)[:160]}"
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    out["what"] = (f"oracle port (torch functional ops = the reference's ATen/cuDNN path) on the same B200, batch {B} x {c['hw']}x{c['hw']}, "
+                   f"CUDA events over {n} passes after 3 warm-ups; cudnn_tf32 = torch default (conv in TF32), fp32 = cudnn.allow_tf32 False")
+    torch.cuda.empty_cache()
+    return out
+
+
+def measure_tf32_peak(dev):
+    """One cuBLAS TF32 GEMM (8192^3, torch.matmul with allow_tf32), same recipe as MEASURED_PEAKS.json's bf16 figure: burst = best of 10,
+    sustained = back to back for ~2 s.  The 3xTF32 tier's arithmetic ceiling is a third of it."""
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device=dev); b = torch.randn(n, n, device=dev)
+        for _ in range(3):
+            a @ b
+        torch.cuda.synchronize(dev)
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); a @ b; e1.record(); torch.cuda.synchronize(dev)
+            best = min(best, e0.elapsed_time(e1))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(10, int(2000.0 / best))
+        e0.record()
+        for _ in range(reps):
+            a @ b
+        e1.record(); torch.cuda.synchronize(dev)
+        fl = 2.0 * n ** 3
+        return {"tf32_tflops": fl / (best * 1e-3) / 1e12, "tf32_tflops_sustained": fl * reps / (e0.elapsed_time(e1) * 1e-3) / 1e12,
+                "how": f"torch.matmul fp32 {n}^3 with allow_tf32 (cuBLAS), best of 10 / {reps} back to back"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
 
 
 def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path (torch ATen ops through the oracle port — the reference
+    is an un-packaged Python script tree that cannot travel to the GPU box) on the host cores, same config, metric and unit."""
     if rank != 0:
         return
+    c = CONFIGS[args.config]
     B = args.batch
-    sample_B = 16   # the reference's own CPU-runnable case (BASELINE configs[0])
-    one_pass = _cpu_setup(sample_B)
-    threads = best_cpu_threads(one_pass)
+    sB, shw, frac = _sample_plan(args.config, B, 300.0, args.steps + args.warmup)
+    one_pass = _oracle_setup(args.config, sB, shw)
+    threads, t_pass = best_cpu_threads(one_pass)
+    same = (sB == B and shw == c["hw"])
+    if same and t_pass * (args.steps + args.warmup) > 420.0:
+        # the full-batch step does not fit "a few minutes" on this host: fall back to a bounded sub-batch of 16 images
+        sB, frac, same = 16, 16.0 / B, False
+        one_pass = _oracle_setup(args.config, sB, shw)
+        one_pass(0)
     for w in range(args.warmup):
         one_pass(w)
     t0 = time.time()
     for k in range(args.steps):
         one_pass(k)
     dt = time.time() - t0
-    value = (sample_B * args.steps / dt) / B
-    sample = (f"each step = one oracle (torch CPU fp32) Taylor pass at batch {sample_B} on {threads} of {os.cpu_count()} host threads (fastest of a short sweep), "
-              f"scaled by {sample_B}/{B} to batch-{B} passes")
+    value = frac * args.steps / dt
+    sample = (f"each step = one oracle (torch CPU fp32, ATen/oneDNN = the reference's backend) Taylor pass at batch {sB} x {shw}x{shw} on {threads} of "
+              f"{os.cpu_count()} host threads (fastest of a short sweep)" +
+              ("" if same else f" = {frac:.4g} of the conv work of one batch-{B} {c['hw']}x{c['hw']} pass; value scaled by that fraction"))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"C1 CIFAR-10 DDPM UNet2DModel Taylor pass, batch {B} 3x32x32 (CPU sample batch {sample_B})"},
+        "config": {"workload": f"{c['name']} Taylor pass, batch {B} x 3x{c['hw']}x{c['hw']}", "same_config": same,
+                   "cpu_sample_batch": sB, "cpu_sample_hw": shw},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}), flush=True)
 
 
-def pruned_c1_model(dev):
-    """C1 pruned at ratio 0.3 to the reference's 19.85 M-parameter architecture (tests/golden/cifar_cfg1.pt records which
-    channel positions the reference removed in BASELINE config 1); weights are the seed-0 random init, sliced."""
+# ------------------------------------------------------------------------------------------------------------------------
+# ours
+# ------------------------------------------------------------------------------------------------------------------------
+def timed_conv_launches(plan, prologue=None, midlogue=None):
+    """Runs one eager pass of `plan` step by step with CUDA events around every launch tagged conv (fprop / dgrad / wgrad / split-K
+    reduce): (summed seconds, launch count, ms by tag, ms by (tag, layer shape))."""
+    s_int = torch.cuda.current_stream().cuda_stream
+    s = torch.cuda.current_stream()
+    pairs = []
+
+    def run_list(steps):
+        for f in steps:
+            if getattr(f, "what", "").startswith("conv"):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(s); f(s_int); e1.record(s)
+                pairs.append((e0, e1, f.what, getattr(f, "info", "")))
+            else:
+                f(s_int)
+    if prologue:
+        prologue(s_int)
+    run_list(plan.fwd)
+    if midlogue:
+        midlogue(s_int)
+    saved = plan.grad_arena.clone()
+    plan.gradof(plan.silu_temb).t.zero_()
+    run_list(plan.bwd_steps)
+    torch.cuda.synchronize()
+    plan.grad_arena.copy_(saved)
+    by_tag, by_layer = {}, {}
+    for a, b, tag, info in pairs:
+        ms = a.elapsed_time(b)
+        by_tag[tag] = by_tag.get(tag, 0.0) + ms
+        if info:
+            key = f"{tag.replace('conv ', '')} {info}"
+            cnt, tot = by_layer.get(key, (0, 0.0))
+            by_layer[key] = (cnt + 1, tot + ms)
+    total = sum(a.elapsed_time(b) for a, b, _, _ in pairs) * 1e-3
+    top = sorted(by_layer.items(), key=lambda kv: -kv[1][1])[:12]
+    return total, len(pairs), {k: round(v, 3) for k, v in sorted(by_tag.items())}, {k: {"n": n, "ms": round(t, 3)} for k, (n, t) in top}
+
+
+def pruned_model(cfg_key, dev, ratio=0.3):
+    """The network the finetune leg trains: the config's UNet pruned at `ratio` by this package's own Taylor path (three accumulated
+    scoring passes on the device, then pruning.taylor_prune — ddpm_prune.py:79-116).  Widths depend on the ratio only; for C1 this is the
+    reference's 19.85 M-parameter architecture."""
     import diff_pruning_b200 as dp
     from diff_pruning_b200 import pruning
-    path = os.path.join(ROOT, "tests", "golden", "cifar_cfg1.pt")
-    if not os.path.exists(path):
-        return None
-    G = torch.load(path, map_location="cpu", weights_only=False)
+    from diff_pruning_b200.scoring import TaylorScorer
+    c = CONFIGS[cfg_key]
     torch.manual_seed(0)
-    m = dp.UNet2DModel(**dp.CIFAR10_DDPM_CONFIG)
-    mods = dict(m.named_modules())
-    expand = lambda i: list(range(i[1], i[1] + i[2])) if isinstance(i, tuple) and i and i[0] == "range" else list(i)
-    for g in G["variants"]["taylor"]["groups"]:
-        pruning.apply_group(mods, [(n, k, expand(i)) for n, k, i in g["items"]], g["idxs"], g["channels"])
-    pruning.fix_static_attributes(m)
-    return m.to(dev)
+    m = dp.UNet2DModel(**getattr(dp, c["model"])).eval().to(dev)
+    clean, noise = synth_batch(min(4, c["batch"]), c["hw"])
+    m.zero_grad()
+    sc = TaylorScorer(m, clean.to(dev), noise.to(dev), use_graph=False)
+    for t in (0, 500, 999):
+        sc.step(t)
+    torch.cuda.synchronize(dev)
+    del sc
+    pruning.taylor_prune(m, ratio, "taylor", ignored_layers=[m.conv_out])
+    m.zero_grad(set_to_none=True)
+    if hasattr(m, "_dpb200_plans"):
+        m._dpb200_plans.clear()
+    torch.cuda.empty_cache()
+    return m
 
 
-def finetune_bench(args, rank, world, dev, barrier):
-    """Secondary metric of BASELINE.json: finetune imgs/sec on the pruned C1 network — ddpm_train.py:437-469
-    (antithetic timesteps, add_noise, fwd, loss, bwd, clip 1.0, Adam 2e-4, EMA 0.9999, dropout 0.1), batch 128 per GPU,
-    gradient all-reduce (mean) per step when N > 1."""
+def finetune_bench(args, rank, world, dev, barrier, compute="fp32"):
+    """Secondary metric of BASELINE.json: finetune imgs/sec on the ratio-0.3 pruned network — ddpm_train.py:437-469 (antithetic
+    timesteps, add_noise, fwd, loss, bwd, clip 1.0, Adam 2e-4, EMA 0.9999, dropout 0.1), config batch per GPU, gradient all-reduce
+    (mean) per step when N > 1.  compute = "fp32" (3xTF32 tier) or "bf16" (single-pass tier, ddpm_train.py --mixed_precision bf16)."""
     import torch.distributed as dist
     from diff_pruning_b200.scoring import FinetuneStepper
-    m = pruned_c1_model(dev)
-    if m is None:
-        return None
+    c = CONFIGS[args.config]
+    m = pruned_model(args.config, dev, 0.3)
     for mod in m.modules():
         if isinstance(mod, torch.nn.Dropout):
             mod.p = 0.1                      # scripts/finetune_ddpm_cifar10.sh --dropout 0.1 (utils.set_dropout)
     m.train()
-    B = args.batch
-    st = FinetuneStepper(m, lr=2e-4, ema_decay=0.9999, max_grad_norm=1.0, use_graph=not args.no_graph)
+    B, hw = args.batch, c["hw"]
+    kw = {"compute": compute} if compute != "fp32" else {}
+    st = FinetuneStepper(m, lr=2e-4, ema_decay=0.9999, max_grad_norm=1.0, use_graph=not args.no_graph, **kw)
     g = torch.Generator().manual_seed(7 + rank)
-    clean, noise = torch.randn(B, 3, 32, 32, generator=g).to(dev), torch.randn(B, 3, 32, 32, generator=g).to(dev)
+    clean, noise = torch.randn(B, 3, hw, hw, generator=g).to(dev), torch.randn(B, 3, hw, hw, generator=g).to(dev)
     t = torch.randint(0, 1000, (B // 2 + 1,), generator=g)
     t = torch.cat([t, 1000 - t - 1])[:B].to(dev)
     K = max(3, min(args.steps, 10))
@@ -212,50 +360,24 @@ def finetune_bench(args, rank, world, dev, barrier):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms[0])
     nparams = sum(p.numel() for p in m.parameters())
-    return {"metric": "finetune_imgs_per_sec", "value": world * B * K / (ms * 1e-3), "unit": "imgs/s", "ms_per_step": ms / K, "steps": K,
-            "config": f"pruned C1 ({nparams / 1e6:.3f} M params, ratio 0.3 architecture), batch {B}/GPU, dropout 0.1, Adam+clip+EMA, "
-                      f"{world} GPU(s)", "loss": float(st.loss.item())}
-
-
-def conv_flops(plan):
-    """Algorithmic FLOPs of the 4-D-weight convolutions in one pass (fprop + dgrad + wgrad), from the plan."""
-    return plan.B * CONV_FLOP_PER_IMAGE_PASS
-
-
-def _timed_pass(scorer, events):
-    """Runs one pass step by step with events around the steps tagged as conv launches."""
-    p = scorer.plan
-    s_int = torch.cuda.current_stream().cuda_stream
-    s = torch.cuda.current_stream()
-    lib = p.lib
-    from diff_pruning_b200 import _lib as L
-    p.t_dev.fill_(3)
-    L.check(lib.dp_add_noise(scorer.clean.data_ptr(), scorer.noise.data_ptr(), p.t_dev.data_ptr(), scorer.acp.data_ptr(),
-                             p.x_in.ptr, scorer.B, scorer.C, scorer.H, scorer.W, 1, p.x_in.ld, s_int))
-    pairs = []
-
-    def run_list(steps, tags):
-        for f, tag in zip(steps, tags):
-            if tag:
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(s); f(s_int); e1.record(s)
-                pairs.append((e0, e1, getattr(f, "what", "conv")))
-            else:
-                f(s_int)
-    is_conv = lambda f: getattr(f, "what", "").startswith("conv")
-    run_list(p.fwd, [is_conv(f) for f in p.fwd])
-    gy = p.gradof(p.y_out)
-    L.check(lib.dp_mse_loss_grad(p.y_out.ptr, scorer.noise_nhwc.data_ptr(), gy.ptr, scorer.n, scorer.loss_scale, scorer.grad_scale,
-                                 scorer.partial.data_ptr(), scorer.loss.data_ptr(), s_int))
-    saved = p.grad_arena.clone()
-    p.gradof(p.silu_temb).t.zero_()
-    run_list(p.bwd_steps, [is_conv(f) for f in p.bwd_steps])
-    torch.cuda.synchronize()
-    p.grad_arena.copy_(saved)
-    by_tag = {}
-    for a, b, tag in pairs:
-        by_tag[tag] = by_tag.get(tag, 0.0) + a.elapsed_time(b)
-    return sum(a.elapsed_time(b) for a, b, _ in pairs) * 1e-3, len(pairs), {k: round(v, 3) for k, v in sorted(by_tag.items())}
+    res = {"metric": "finetune_imgs_per_sec", "value": world * B * K / (ms * 1e-3), "unit": "imgs/s", "ms_per_step": ms / K, "steps": K,
+           "dtype": compute,
+           "config": f"{args.config.upper()} pruned at ratio 0.3 by taylor_prune ({nparams / 1e6:.3f} M params), batch {B}/GPU, dropout 0.1, Adam+clip+EMA, "
+                     f"{world} GPU(s)", "loss": float(st.loss.item())}
+    if rank == 0:
+        _, tf_sus, _, which = peaks()
+        conv_s, n_conv, by_tag, _ = timed_conv_launches(st.plan)
+        flops = 6.0 * st.plan.conv_macs
+        res["roofline"] = {"bound": "tensor", "achieved": flops / conv_s / 1e12, "peak": tf_sus, "unit": "TFLOP/s",
+                           "frac": flops / conv_s / 1e12 / tf_sus, "conv_ms": round(conv_s * 1e3, 3), "breakdown_ms": by_tag,
+                           "conv_gflop_per_image": 6.0 * st.plan.conv_macs / B / 1e9,
+                           "note": f"6 x conv MACs of the pruned network (from the launch plan) / summed conv-launch time of one step; peak = bf16_tflops_sustained ({which})"}
+    del st
+    if hasattr(m, "_dpb200_plans"):
+        m._dpb200_plans.clear()
+    del m
+    torch.cuda.empty_cache()
+    return res
 
 
 def run_ours(args, rank, world, local_rank):
@@ -271,13 +393,13 @@ def run_ours(args, rank, world, local_rank):
     lib = L.load()
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
-    B = args.batch
+    c = CONFIGS[args.config]
+    B, hw = args.batch, c["hw"]
     torch.manual_seed(0)
-    model = dp.UNet2DModel(**dp.CIFAR10_DDPM_CONFIG).eval().to(dev)
-    clean, noise = synth_batch(B, seed_off=100 * rank)
+    model = dp.UNet2DModel(**getattr(dp, c["model"])).eval().to(dev)
+    clean, noise = synth_batch(B, hw, seed_off=100 * rank)
     clean_pin, noise_pin = clean.pin_memory(), noise.pin_memory()
     model.zero_grad()
-    l0 = lib.dp_launch_count()
     sc = TaylorScorer(model, clean.to(dev), noise.to(dev), use_graph=not (args.no_graph or args.profile_pass))
     if args.profile_pass:   # for ncu: `--profile-from-start off`; exactly one eager pass inside the profiler range
         for k in range(2):
@@ -338,45 +460,69 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
-    # ---------------- roofline of the dominant kernel (conv implicit GEMM), live CUDA events
-    conv_s, n_conv, conv_by_tag = _timed_pass(sc, None) if rank == 0 else (1.0, 0, {})
-    plan_B = sc.plan.B
+    # ---------------- roofline of the dominant kernel family (conv implicit GEMM), live CUDA events
+    if rank == 0:
+        p = sc.plan
+
+        def pro(s_int):
+            p.t_dev.fill_(3)
+            L.check(lib.dp_add_noise(sc.clean.data_ptr(), sc.noise.data_ptr(), p.t_dev.data_ptr(), sc.acp.data_ptr(),
+                                     p.x_in.ptr, sc.B, sc.C, sc.H, sc.W, 1, p.x_in.ld, s_int))
+
+        def mid(s_int):
+            gy = p.gradof(p.y_out)
+            L.check(lib.dp_mse_loss_grad(p.y_out.ptr, sc.noise_nhwc.data_ptr(), gy.ptr, sc.n, sc.loss_scale, sc.grad_scale,
+                                         sc.partial.data_ptr(), sc.loss.data_ptr(), s_int))
+        conv_s, n_conv, conv_by_tag, conv_by_layer = timed_conv_launches(p, pro, mid)
+    else:
+        conv_s, n_conv, conv_by_tag, conv_by_layer = 1.0, 0, {}, {}
+    plan_B, plan_macs, plan_bytes = sc.plan.B, sc.plan.conv_macs, sc.plan.bytes_allocated()
     del sc
     if hasattr(model, "_dpb200_plans"):
         model._dpb200_plans.clear()
+    del model
     torch.cuda.empty_cache()
-    finetune_leg = finetune_bench(args, rank, world, dev, barrier) if not args.no_finetune else None
+    finetune_leg = finetune_bf16 = None
+    if not args.no_finetune:
+        finetune_leg = finetune_bench(args, rank, world, dev, barrier)
+        from diff_pruning_b200 import engine as _eng
+        if getattr(_eng, "BF16_TIER", False):
+            finetune_bf16 = finetune_bench(args, rank, world, dev, barrier, compute="bf16")
     if rank != 0:
         return
     hbm, tf_sus, tf_burst, which = peaks()
-    flops = plan_B * CONV_FLOP_PER_IMAGE_PASS
+    flops = plan_B * c["conv_flop"]
     achieved = flops / conv_s / 1e12
     tc = bool(lib.dp_tc_available())
+    tf32 = measure_tf32_peak(dev)
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
-    if os.path.exists(tp) and B == 128:   # dram__bytes_read+write summed over the conv launches of one pass (committed ncu capture)
+    tp = os.path.join(ROOT, "profiles", "r02_conv_traffic.json" if os.path.exists(os.path.join(ROOT, "profiles", "r02_conv_traffic.json"))
+                      else "r01_conv_traffic.json")
+    if os.path.exists(tp) and B == 128 and args.config == "c1":   # dram__bytes_read+write summed over the conv launches of one pass (committed ncu capture)
         tj = json.load(open(tp))
         traffic = tj["dram_read_bytes"] + tj["dram_write_bytes"]
+    tier_ceiling = tf32["tf32_tflops_sustained"] / 3.0
     roofline = {"bound": "tensor", "achieved": achieved, "peak": tf_sus, "unit": "TFLOP/s", "frac": achieved / tf_sus,
-                "traffic": traffic, "breakdown_ms": conv_by_tag,
+                "traffic": traffic, "breakdown_ms": conv_by_tag, "top_layers_ms": conv_by_layer,
+                "tf32_peak_measured": tf32, "tier_ceiling_tflops": tier_ceiling, "frac_of_tier_ceiling": achieved / tier_ceiling,
+                "plan_conv_gflop_per_image": 6.0 * plan_macs / plan_B / 1e9,
                 "kernel": "conv implicit GEMM (fprop+dgrad+wgrad launches of one pass: %d)" % n_conv,
-                "note": (f"algorithmic conv FLOPs/pass = {B} x 34.27 GFLOP (SURVEY.md §8d) / summed conv-launch device time "
+                "note": (f"algorithmic conv FLOPs/pass = {B} x {c['conv_flop'] / 1e9:.2f} GFLOP (SURVEY.md §8d) / summed conv-launch device time "
                          f"{conv_s * 1e3:.2f} ms of a {ms / args.steps:.2f} ms step; peak = bf16_tflops_sustained ({which}); "
-                         "fp32-exact tier: " + ("tcgen05 3xTF32 (3 tensor instructions per product: attainable ceiling = 1/6 of this bf16 peak)" if tc
+                         "fp32-exact tier: " + ("tcgen05 3xTF32 (3 tensor instructions per product: tier ceiling = measured cuBLAS TF32 sustained / 3)" if tc
                                                  else "CUDA-core FFMA (SIMT) — tensor path not active") +
-                         "; traffic = DRAM bytes of all conv launches of one pass (profiles/r01_conv_traffic.json), algorithmic conv "
-                         "I/O of the pass is ~13 GB (3 x 128 x 8.49 M fp32 conv in+out elements, SURVEY.md §8d)")}
+                         "; traffic = DRAM bytes of all conv launches of one pass (committed ncu capture, C1 only)")}
     value = world * args.steps / (ms * 1e-3)
     e2e = world * args.steps / (ms_e2e * 1e-3)
-    cpu = cpu_oracle_passes(B, 16, min_seconds=12.0, max_passes=8) if args.gpus == 1 and not args.no_cpu else None
-    fin = finetune_leg
+    cpu = cpu_oracle_passes(args.config, B, min_seconds=12.0, max_passes=8) if args.gpus == 1 and not args.no_cpu else None
+    eager = gpu_eager_passes(args.config, B, dev) if args.gpus == 1 and not args.no_cpu else None
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"C1 CIFAR-10 DDPM UNet2DModel (35.7M params, seed-0 init) Taylor pass, batch {B} x 3x32x32 per GPU, "
+        "config": {"workload": f"{c['name']} Taylor pass, batch {B} x 3x{hw}x{hw} per GPU, "
                                f"timesteps sharded over {world} GPU(s), one grad all-reduce at the end",
-                   "l2": "per-pass working set (activations+grads, GBs) >> 126 MB L2: inputs larger than L2, no explicit flush",
+                   "l2": f"per-pass working set (activations+grads, {plan_bytes / 2**30:.1f} GiB) >> 126 MB L2: inputs larger than L2, no explicit flush",
                    "cuda_graph": not args.no_graph, "imgs_per_s": value * B},
         "clocks": clocks, "gpu_launches": int(gpu_launches),
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(2 * clean.numel() * 4 + 8 * B), "d2h_bytes_per_step": 4,
@@ -385,8 +531,12 @@ def run_ours(args, rank, world, local_rank):
     }
     if cpu is not None:
         out["cpu_baseline"] = cpu
-    if fin is not None:
-        out["finetune"] = fin
+    if eager is not None:
+        out["gpu_eager_baseline"] = eager
+    if finetune_leg is not None:
+        out["finetune"] = finetune_leg
+    if finetune_bf16 is not None:
+        out["finetune_bf16"] = finetune_bf16
     print(json.dumps(out), flush=True)
 
 
@@ -396,12 +546,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=128)
+    ap.add_argument("--config", default=os.environ.get("DPB200_BENCH_CONFIG", "c1"), choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline and gpu_eager_baseline legs (profiling runs)")
     ap.add_argument("--profile-pass", action="store_true", help="run one eager pass inside cudaProfilerStart/Stop (ncu)")
-    ap.add_argument("--no-finetune", action="store_true", help="skip the secondary finetune imgs/s leg")
+    ap.add_argument("--no-finetune", action="store_true", help="skip the secondary finetune imgs/s legs")
     args = ap.parse_args()
+    if args.batch is None:
+        args.batch = CONFIGS[args.config]["batch"]
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     rank, world, local_rank = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":

@@ -40,7 +40,13 @@ class GnArgs(C.Structure):
                 ("x", vp), ("ldx", i64), ("y", vp), ("ldy", i64), ("gamma", vp), ("beta", vp), ("mean", vp),
                 ("rstd", vp), ("dy", vp), ("lddy", i64), ("dx", vp), ("lddx", i64), ("dx_add", vp), ("ldadd", i64),
                 ("dx_add2", vp), ("ldadd2", i64), ("dgamma", vp), ("dbeta", vp), ("workspace", vp),
-                ("dropout_p", f32), ("dropout_seed", u64), ("dropout_seed_dev", vp)]
+                ("dropout_p", f32), ("dropout_seed", u64), ("dropout_seed_dev", vp), ("y_bf16", vp), ("ldyb", i64)]
+
+
+class ConvBf16Args(C.Structure):
+    _fields_ = [(n, i32) for n in ("N", "H", "W", "C", "P", "Q", "K", "R", "S", "stride", "pad_t", "pad_l", "flags", "splits")] + [
+        ("x_bf16", vp), ("ldx", i64), ("dy_bf16", vp), ("lddy", i64), ("out", vp), ("ld_out", i64), ("w_bf16", vp), ("bias", vp),
+        ("rowadd", vp), ("ld_rowadd", i64), ("residual", vp), ("ld_res", i64), ("workspace", vp)]
 
 
 class TaylorArgs(C.Structure):
@@ -69,6 +75,15 @@ _SIGS = {
     "dp_conv2d_wgrad_reduce": (C.c_int, [C.POINTER(WgradReduceArgs), vp]),
     "dp_pack_conv_weight": (C.c_int, [vp, i32, i32, i32, i32, vp, vp, vp]),
     "dp_pack_conv_weight_tc": (C.c_int, [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp]),
+    "dp_bf16_available": (C.c_int, []),
+    "dp_bf16_weight_row": (C.c_int, [C.c_int]),
+    "dp_bf16_wgrad_ctile": (C.c_int, [C.c_int]),
+    "dp_conv2d_fprop_bf16": (C.c_int, [C.POINTER(ConvBf16Args), vp]),
+    "dp_conv2d_dgrad_bf16": (C.c_int, [C.POINTER(ConvBf16Args), vp]),
+    "dp_conv2d_wgrad_bf16": (C.c_int, [C.POINTER(ConvBf16Args), vp]),
+    "dp_conv_bf16_eligible": (C.c_int, [C.POINTER(ConvBf16Args), C.c_int]),
+    "dp_cvt_bf16": (C.c_int, [vp, i64, i64, i32, vp, i64, vp]),
+    "dp_pack_conv_weight_bf16": (C.c_int, [vp, i32, i32, i32, i32, vp, vp, vp]),
     "dp_gemm_batched": (C.c_int, [C.POINTER(GemmArgs), vp]),
     "dp_gemm_nt_tc": (C.c_int, [C.POINTER(GemmNtArgs), vp]),
     "dp_split_tf32": (C.c_int, [vp, i64, i64, i32, i32, i32, i32, vp, vp, vp]),

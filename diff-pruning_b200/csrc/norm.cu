@@ -1,6 +1,7 @@
 // norm.cu — GroupNorm (+SiLU, +dropout) forward/backward over NHWC views.  HBM-bound: every kernel reads rows
 // of C contiguous floats (coalesced), each thread owns fixed channel(s) so per-channel scale/shift live in
 // registers, and all cross-block reductions go through fixed-order partial buffers (no atomics).
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace {
@@ -107,7 +108,8 @@ __global__ void __launch_bounds__(NT) gn_apply_kernel(const dp_gn_args a, const 
         float y = fmaf(__ldg(row + c), sc[u], shf[u]);
         if (a.silu) y = y * sigmoidf_acc(y);
         if (a.dropout_p > 0.f) y *= keep_scale(a.dropout_seed + (a.dropout_seed_dev ? *a.dropout_seed_dev : 0ull), ((uint64_t)n * a.HW + pix) * a.C + c, a.dropout_p);
-        orow[c] = y;
+        if (a.y) orow[c] = y;
+        if (a.y_bf16) reinterpret_cast<__nv_bfloat16*>(a.y_bf16)[((long long)n * a.HW + pix) * a.ldyb + c] = __float2bfloat16_rn(y);
       }
     }
   }
@@ -314,7 +316,12 @@ __global__ void __launch_bounds__(NT) gn_apply4_kernel(const dp_gn_args a, const
       if (a.silu) y[e] = y[e] * sigmoidf_acc(y[e]);
       if (a.dropout_p > 0.f) y[e] *= keep_scale(seed, ((uint64_t)n * a.HW + pix) * a.C + c0 + e, a.dropout_p);
     }
-    *reinterpret_cast<float4*>(yb + (long long)pix * a.ldy) = make_float4(y[0], y[1], y[2], y[3]);
+    if (a.y) *reinterpret_cast<float4*>(yb + (long long)pix * a.ldy) = make_float4(y[0], y[1], y[2], y[3]);
+    if (a.y_bf16) {   // the next convolution's bf16 operand (c0 % 4 == 0 and ldyb % 8 == 0: 8-byte aligned)
+      __nv_bfloat162 lo = __floats2bfloat162_rn(y[0], y[1]), hi = __floats2bfloat162_rn(y[2], y[3]);
+      uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.y_bf16) + ((long long)n * a.HW + pix) * a.ldyb + c0) = pk;
+    }
   }
 }
 
@@ -421,8 +428,9 @@ static int gn_validate(const dp_gn_args* a) {
 extern "C" int dp_groupnorm_fwd(const dp_gn_args* a, dp_stream_t stream) {
   int rc = gn_validate(a);
   if (rc) return rc;
-  DP_REQUIRE(a->y, DP_ERR_NULL);
-  DP_REQUIRE(a->ldy >= a->C, DP_ERR_SHAPE);
+  DP_REQUIRE(a->y || a->y_bf16, DP_ERR_NULL);
+  DP_REQUIRE(!a->y || a->ldy >= a->C, DP_ERR_SHAPE);
+  DP_REQUIRE(!a->y_bf16 || (a->ldyb >= a->C && a->ldyb % 8 == 0 && (((uintptr_t)a->y_bf16) & 15) == 0), DP_ERR_ALIGN);
   cudaStream_t st = (cudaStream_t)stream;
   const bool v4 = (a->C % 4 == 0) && al16(a->x, a->ldx) && al16(a->y, a->ldy);
   Map mp = v4 ? make_map4(a->HW, a->C) : make_map(a->HW, a->C);

@@ -101,9 +101,20 @@ class Plan:
     """Static forward/backward launch lists for one (model, batch, H, W)."""
 
     def __init__(self, model: UNet2DModel, batch: int, height: int, width: int, device, training: bool = False,
-                 need_grad: bool = True, fused_scores: bool = False):
+                 need_grad: bool = True, fused_scores: bool = False, compute: str = "fp32"):
         self.lib = L.load()
         self.tc = bool(self.lib.dp_tc_available()) if torch.device(device).type == "cuda" else False
+        if compute not in ("fp32", "bf16"):
+            raise ValueError(f"compute must be 'fp32' (3xTF32, fp32-grade) or 'bf16' (single-pass tensor tier), got {compute!r}")
+        if compute == "bf16" and not (torch.device(device).type == "cuda" and self.lib.dp_bf16_available()):
+            raise RuntimeError("diff_pruning_b200: the bf16 tensor tier needs an sm_100a device (no fallback)")
+        # bf16 tier (ddpm_train.py --mixed_precision bf16 -> torch.autocast: conv / linear operands in bf16, everything else fp32):
+        # eligible convolutions read bf16 operands (written by GroupNorm+SiLU directly, or by dp_cvt_bf16) on the kind::f16 kernels
+        self.compute = compute
+        self.bf16 = compute == "bf16"
+        self._bf_cache: Dict[Tuple[int, int, int], Tuple[torch.Tensor, int]] = {}
+        self._bf_packs: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
+        self.n_bf16_convs = 0
         self.model = model
         self.B, self.H, self.W = batch, height, width
         self.dev = torch.device(device)
@@ -123,6 +134,7 @@ class Plan:
         self.dropout_seed_dev = torch.zeros(1, device=self.dev, dtype=torch.int64)
         self._n_dropout = 0
         self.fused_scores = fused_scores and need_grad
+        self.conv_macs = 0             # MACs of one forward over the 4-D-weight convolutions (set while building)
         self.generation = 0            # forward counter of the autograd boundary (see _UNetFunction)
         self._calls = 0                # module-forward counter: advances the dropout stream on the autograd / compat path
         self.scores: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
@@ -211,7 +223,7 @@ class Plan:
         return got
 
     # ------------------------------------------------------------------ launch recording
-    def _rec(self, lst: List[Step], fn, args=None, what=""):
+    def _rec(self, lst: List[Step], fn, args=None, what="", info=""):
         check = L.check
         if args is not None:
             self._keep.append(args)
@@ -227,6 +239,7 @@ class Plan:
                 if rc:
                     check(rc, what)
         run.what = what
+        run.info = info          # shape tag for per-layer timing tables (bench.py, scripts/trace_pass.py)
         lst.append(run)
 
     def _bitem(self) -> BItem:
@@ -258,6 +271,61 @@ class Plan:
                                                  t[3].data_ptr(), s), what="pack tc")
         self._packs[id(w)] = (wck, wkc, tc)
         return wck, wkc, tc
+
+    # ------------------------------------------------------------------ bf16 tier plumbing
+    def _bf_geom(self, x: View, out: View, w: nn.Parameter, stride: int, pad: int) -> "L.ConvBf16Args":
+        a = L.ConvBf16Args()
+        a.N, a.H, a.W, a.C = x.N, x.H, x.W, x.C
+        a.P, a.Q, a.K = out.H, out.W, w.shape[0]
+        a.R = w.shape[2] if w.dim() == 4 else 1
+        a.S = w.shape[3] if w.dim() == 4 else 1
+        a.stride, a.pad_t, a.pad_l, a.splits = stride, pad, pad, 1
+        a.ldx, a.lddy, a.ld_out = (x.C + 7) // 8 * 8, (w.shape[0] + 7) // 8 * 8, max(out.ld, x.ld)
+        return a
+
+    def conv_bf16_ok(self, x: View, out: View, w: nn.Parameter, stride: int = 1, pad: int = 1, need_dx: bool = True) -> bool:
+        """Does this convolution run on the bf16 kernels?  All of its launches (fprop, wgrad, dgrad) or none.  Small GEMMs (the
+        time-embedding MLP, per-image temb projections: rows = batch) and 3-channel ends (conv_in / conv_out) stay fp32-grade:
+        they are launch-latency-sized and cost nothing to keep exact."""
+        if not self.bf16 or x.rows < 256 or w.shape[1] < 16 or w.shape[0] < 16:
+            return False
+        g = self._bf_geom(x, out, w, stride, pad)
+        ops = [0] + ([2] + ([1] if need_dx else []) if self.need_grad else [])
+        return all(self.lib.dp_conv_bf16_eligible(_byref(g), op) == 0 for op in ops)
+
+    def _bf_new(self, rows: int, C_: int) -> Tuple[torch.Tensor, int]:
+        ld = (C_ + 7) // 8 * 8
+        t = torch.empty((rows, ld), device=self.dev, dtype=torch.bfloat16)
+        self._keep.append(t)
+        return t, ld
+
+    def _bf16_of(self, v: View) -> Tuple[torch.Tensor, int]:
+        """The bf16 operand copy of an activation view: written by its producer when one registered it (GroupNorm), else by ONE
+        dp_cvt_bf16 launch recorded at the first consumer (the buffer is stable from there to the end of the backward pass)."""
+        key = (v.t.data_ptr(), v.off, v.C)
+        got = self._bf_cache.get(key)
+        if got is None:
+            got = self._bf_new(v.rows, v.C)
+            self._bf_cache[key] = got
+            t, ld = got
+            self._rec(self.fwd, lambda s, p=v.ptr, ldv=v.ld, r=v.rows, c=v.C, d=t.data_ptr(), ld=ld:
+                      self.lib.dp_cvt_bf16(p, ldv, r, c, d, ld, s), what="cvt bf16")
+        return got
+
+    def _packed_bf16(self, w: nn.Parameter):
+        got = self._bf_packs.get(id(w))
+        if got is None:
+            K, Cin = w.shape[0], w.shape[1]
+            R = w.shape[2] if w.dim() == 4 else 1
+            S = w.shape[3] if w.dim() == 4 else 1
+            lib = self.lib
+            kc = torch.empty(R * S * K * lib.dp_bf16_weight_row(Cin), device=self.dev, dtype=torch.bfloat16)
+            ck = torch.empty(R * S * Cin * lib.dp_bf16_weight_row(K), device=self.dev, dtype=torch.bfloat16)
+            self._rec(self.pack, lambda s, w=w, K=K, Cin=Cin, R=R, S=S, a=kc, b=ck:
+                      lib.dp_pack_conv_weight_bf16(w.data_ptr(), K, Cin, R, S, a.data_ptr(), b.data_ptr(), s), what="pack bf16")
+            got = (kc, ck)
+            self._bf_packs[id(w)] = got
+        return got
 
     def _colsum_tree(self, steps: List[Step], src_ptr: int, ld: int, rows: int, per_img: int, cols: int,
                      seg_name: Optional[str]) -> str:
@@ -292,6 +360,9 @@ class Plan:
         R = w.shape[2] if w.dim() == 4 else 1
         S = w.shape[3] if w.dim() == 4 else 1
         assert x.C == Cin and out.C == K, (x.C, Cin, out.C, K)
+        use_bf = dy_dense is None and self.conv_bf16_ok(x, out, w, stride, pad, need_dx)
+        if use_bf:
+            return self._conv_bf16(x, w, b, out, stride, pad, rowadd, residual, accumulate_out, need_dx, dx_scratch, seg_out, dx_into)
         wck, wkc, wtc = self._packed(w)
         a = L.ConvArgs()
         if wtc is not None:
@@ -308,7 +379,10 @@ class Plan:
             a.rowadd, a.ld_rowadd = rowadd.ptr, rowadd.ld
         if residual is not None:
             a.residual, a.ld_res = residual.ptr, residual.ld
-        self._rec(self.fwd, lib.dp_conv2d_fprop, a, "conv fprop")
+        info = f"{Cin}->{K} {R}x{S}" + (f" s{stride}" if stride != 1 else "") + f" @{out.H}x{out.W}"
+        if w.dim() == 4:
+            self.conv_macs += out.rows * K * Cin * R * S      # 4-D-weight convolutions only: the roofline denominator
+        self._rec(self.fwd, lib.dp_conv2d_fprop, a, "conv fprop", info)
         if not self.need_grad:
             return
         it = self._bitem()
@@ -344,7 +418,7 @@ class Plan:
         wa.ldy = dy_ld
         wa.rowadd, wa.residual, wa.bias = None, None, None
         self._late.append(lambda wa=wa, g=dy_get: (setattr(wa, "y", g()), setattr(wa, "workspace", self.sptr("wgrad_ws"))))
-        self._rec(steps, lib.dp_conv2d_wgrad, wa, "conv wgrad")
+        self._rec(steps, lib.dp_conv2d_wgrad, wa, "conv wgrad", info)
         ra = L.WgradReduceArgs()
         ra.K, ra.C, ra.R, ra.S, ra.splits = K, Cin, R, S, splits
         ra.dw = self.pgrad(w)
@@ -372,15 +446,92 @@ class Plan:
                 gx = self.gradof(tgt)
                 da.x, da.ldx = gx.ptr, gx.ld
                 it.writes.append((tgt, lambda init, da=da: setattr(da, "flags", 1 if init else 0)))
-            self._rec(steps, lib.dp_conv2d_dgrad, da, "conv dgrad")
+            self._rec(steps, lib.dp_conv2d_dgrad, da, "conv dgrad", info)
 
-    def gn(self, x: View, norm: nn.GroupNorm, out: View, silu: bool, dropout_p: float = 0.0):
+    def _conv_bf16(self, x, w, b, out, stride, pad, rowadd, residual, accumulate_out, need_dx, dx_scratch, seg_out, dx_into):
+        """conv() on the bf16 tensor tier: same launch structure and fp32 outputs, operands as bf16 copies."""
+        lib = self.lib
+        K, Cin = w.shape[0], w.shape[1]
+        R = w.shape[2] if w.dim() == 4 else 1
+        S = w.shape[3] if w.dim() == 4 else 1
+        kc, ck = self._packed_bf16(w)
+        xb, ldxb = self._bf16_of(x)
+        self.n_bf16_convs += 1
+        a = self._bf_geom(x, out, w, stride, pad)
+        a.flags = 1 if accumulate_out else 0
+        a.x_bf16, a.ldx = xb.data_ptr(), ldxb
+        a.out, a.ld_out = out.ptr, out.ld
+        a.w_bf16 = kc.data_ptr()
+        a.bias = b.data_ptr() if b is not None else None
+        if rowadd is not None:
+            a.rowadd, a.ld_rowadd = rowadd.ptr, rowadd.ld
+        if residual is not None:
+            a.residual, a.ld_res = residual.ptr, residual.ld
+        info = f"{Cin}->{K} {R}x{S}" + (f" s{stride}" if stride != 1 else "") + f" @{out.H}x{out.W} bf16"
+        if w.dim() == 4:
+            self.conv_macs += out.rows * K * Cin * R * S
+        self._rec(self.fwd, lib.dp_conv2d_fprop_bf16, a, "conv fprop", info)
+        if not self.need_grad:
+            return
+        it = self._bitem()
+        steps = it.steps
+        dout = self.gradof(out)
+        # 1. bias gradient / per-image sums (fp32, from the fp32 dy)
+        if b is not None or seg_out is not None:
+            seg = self._colsum_tree(steps, dout.ptr, dout.ld, out.rows, out.H * out.W, K, seg_out)
+            if b is not None:
+                self._rec(steps, lambda s, seg=seg, b=b, n=x.N: lib.dp_colsum(self.sptr(seg), K, n, K, n, self.pgrad(b), K, 1, s),
+                          what="bias grad")
+        # 2. dy -> bf16 once for wgrad and dgrad
+        lddyb = (K + 7) // 8 * 8
+        self.scratch("dy_bf16", (out.rows * lddyb + 1) // 2)
+        self._rec(steps, lambda s, p=dout.ptr, ld=dout.ld, r=out.rows: lib.dp_cvt_bf16(p, ld, r, K, self.sptr("dy_bf16"), lddyb, s),
+                  what="cvt bf16")
+        # 3. wgrad -> split-K workspace -> fixed-order reduce into Parameter.grad
+        TC = R * S * Cin
+        ctw = lib.dp_bf16_wgrad_ctile(Cin)
+        tiles = ((K + 127) // 128) * ((Cin + ctw - 1) // ctw) * R * S
+        chunks = max(1, out.rows // 64)
+        splits = _wgrad_splits(tiles, chunks)
+        self.scratch("wgrad_ws", splits * K * TC)
+        wa = _copy_args(a)
+        wa.flags, wa.splits, wa.lddy = 0, splits, lddyb
+        wa.rowadd, wa.residual, wa.bias, wa.out = None, None, None, None
+        self._late.append(lambda wa=wa: (setattr(wa, "dy_bf16", self.sptr("dy_bf16")), setattr(wa, "workspace", self.sptr("wgrad_ws"))))
+        self._rec(steps, lib.dp_conv2d_wgrad_bf16, wa, "conv wgrad", info)
+        ra = L.WgradReduceArgs()
+        ra.K, ra.C, ra.R, ra.S, ra.splits = K, Cin, R, S, splits
+        ra.dw = self.pgrad(w)
+        self._late.append(lambda ra=ra: setattr(ra, "workspace", self.sptr("wgrad_ws")))
+        self._rec(steps, lib.dp_conv2d_wgrad_reduce, ra, "conv wgrad reduce")
+        # 4. dgrad
+        if need_dx:
+            da = _copy_args(a)
+            da.lddy, da.w_bf16, da.flags = lddyb, ck.data_ptr(), 0
+            da.rowadd, da.residual, da.bias, da.x_bf16 = None, None, None, None
+            self._late.append(lambda da=da: setattr(da, "dy_bf16", self.sptr("dy_bf16")))
+            if dx_scratch is not None:
+                self.scratch(dx_scratch, x.rows * x.C)
+                da.ld_out = x.C
+                self._late.append(lambda da=da, n=dx_scratch: setattr(da, "out", self.sptr(n)))
+            else:
+                tgt = dx_into if dx_into is not None else x
+                gx = self.gradof(tgt)
+                da.out, da.ld_out = gx.ptr, gx.ld
+                it.writes.append((tgt, lambda init, da=da: setattr(da, "flags", 1 if init else 0)))
+            self._rec(steps, lib.dp_conv2d_dgrad_bf16, da, "conv dgrad", info)
+
+    def gn(self, x: View, norm: nn.GroupNorm, out: View, silu: bool, dropout_p: float = 0.0, bf16_only: bool = False):
         """fwd: out = dropout?(silu?(GN(x))).  Returns the fwd args (the backward reuses stats / dropout seed)."""
         lib = self.lib
         a = L.GnArgs()
         a.N, a.HW, a.C, a.G = x.N, x.H * x.W, x.C, norm.num_groups
         a.eps, a.silu = norm.eps, 1 if silu else 0
         a.x, a.ldx, a.y, a.ldy = x.ptr, x.ld, out.ptr, out.ld
+        if bf16_only:   # every consumer of `out` is a bf16 convolution: write the operand directly, skip the fp32 tensor
+            yb, ldyb = self._bf_new(out.rows, out.C)
+            self._bf_cache[(out.t.data_ptr(), out.off, out.C)] = (yb, ldyb)
+            a.y, a.y_bf16, a.ldyb = None, yb.data_ptr(), ldyb
         a.gamma, a.beta = norm.weight.data_ptr(), norm.bias.data_ptr()
         stats = torch.empty(2 * x.N * norm.num_groups, device=self.dev, dtype=torch.float32)
         self._keep.append(stats)
@@ -426,14 +577,14 @@ class Plan:
         tp = self.new(self.B, 1, 1, Cout)
         has_sc = m.conv_shortcut is not None
         da = lambda: self.sptr("da")
-        g1 = self.gn(x, m.norm1, a1, silu=True)
+        g1 = self.gn(x, m.norm1, a1, silu=True, bf16_only=self.conv_bf16_ok(a1, h1, m.conv1.weight))
         if self.need_grad:
             self.gn_bwd(g1, x, m.norm1, da, x.C, add2=None if has_sc else self.gradof(out))
         # time_emb_proj(silu(temb)) -> per-image row added in conv1's epilogue; its dY are conv1's per-image sums
         self.conv(self.silu_temb, m.time_emb_proj.weight, m.time_emb_proj.bias, tp, pad=0, dy_dense="seg",
                   dx_into=self.silu_temb)
         self.conv(a1, m.conv1.weight, m.conv1.bias, h1, rowadd=tp, seg_out="seg", dx_scratch="da")
-        g2 = self.gn(h1, m.norm2, a2, silu=True, dropout_p=p_drop)
+        g2 = self.gn(h1, m.norm2, a2, silu=True, dropout_p=p_drop, bf16_only=self.conv_bf16_ok(a2, out, m.conv2.weight))
         if self.need_grad:
             self.gn_bwd(g2, h1, m.norm2, da, Cout)
         if has_sc:
@@ -455,7 +606,8 @@ class Plan:
         q, k, v, o = (self.new(N, H, W, inner) for _ in range(4))
         P = torch.empty((N, T, T), device=self.dev, dtype=torch.float32)
         self._keep.append(P)
-        g = self.gn(x, m.group_norm, xn, silu=False)
+        g = self.gn(x, m.group_norm, xn, silu=False,
+                    bf16_only=all(self.conv_bf16_ok(xn, q, l.weight, 1, 0) for l in (m.to_q, m.to_k, m.to_v)))
         if self.need_grad:
             self.gn_bwd(g, x, m.group_norm, lambda xn=xn: self.gradof(xn).ptr, x.C,
                         add2=self.gradof(out) if m.residual_connection else None)
@@ -801,16 +953,21 @@ class _UNetFunction(torch.autograd.Function):
         return (None, None, None) + (None,) * len(plan.params)
 
 
-def get_plan(model: UNet2DModel, batch: int, H: int, W: int, device, need_grad: bool, fused_scores: bool = False) -> Plan:
+BF16_TIER = True   # conv_bf16.cu is part of this build (bench.py reports the bf16 finetune leg separately)
+
+
+def get_plan(model: UNet2DModel, batch: int, H: int, W: int, device, need_grad: bool, fused_scores: bool = False,
+             compute: str = "fp32") -> Plan:
     cache = model.__dict__.setdefault("_dpb200_plans", {})
     training = bool(model.training)
-    key = (batch, H, W, str(device), need_grad, training, fused_scores)
+    drop = tuple(float(mod.p) for mod in model.modules() if isinstance(mod, nn.Dropout)) if training else ()
+    key = (batch, H, W, str(device), need_grad, training, fused_scores, drop, compute)   # dropout rates are baked into the launch plan
     plan = cache.get(key)
     sig = tuple((p.data_ptr(), tuple(p.shape)) for p in model.parameters())
     if plan is None or plan.signature() != sig:
         if plan is not None or any(pl.signature() != sig for pl in cache.values()):
             cache.clear()  # weights were replaced (e.g. pruned): every cached plan is stale
-        plan = Plan(model, batch, H, W, device, training=training, need_grad=need_grad, fused_scores=fused_scores)
+        plan = Plan(model, batch, H, W, device, training=training, need_grad=need_grad, fused_scores=fused_scores, compute=compute)
         cache[key] = plan
     return plan
 
@@ -824,7 +981,10 @@ def unet_apply(model: UNet2DModel, sample: torch.Tensor, timesteps: torch.Tensor
     if need_grad and sample.requires_grad:
         raise RuntimeError("diff_pruning_b200: the engine does not produce d(loss)/d(sample) (the reference loops never need it: "
                            "noisy images are leaves without grad, ddpm_prune.py:99-100); detach the input")
-    plan = get_plan(model, B, H, W, sample.device, need_grad)
+    # `accelerator.prepare(model)` with mixed_precision="bf16" (compat/accelerate) selects the bf16 tier for TRAINING forwards, the
+    # analogue of running the forward under torch.autocast(bfloat16) at ddpm_train.py:255-261,458
+    compute = model.__dict__.get("_dpb200_compute", "fp32") if (need_grad and model.training) else "fp32"
+    plan = get_plan(model, B, H, W, sample.device, need_grad, compute=compute)
     # Packed weight copies: this module-forward path cannot see every way weights get written (`param.data.copy_` leaves no trace),
     # so it re-packs on EVERY call (~230 small launches, < 1 ms at C1) unless the caller froze the weights for a loop
     # (frozen_weights(): the DDIM pipelines) — the explicit TaylorScorer / FinetuneStepper APIs manage their own packs.

@@ -292,9 +292,10 @@ class FinetuneStepper:
 
     def __init__(self, model: UNet2DModel, lr: float = 2e-4, betas=(0.9, 0.999), eps: float = 1e-8,
                  ema_decay: float = 0.9999, max_grad_norm: float = 1.0, use_ema: bool = True,
-                 num_train_timesteps: int = 1000, use_graph: bool = True):
+                 num_train_timesteps: int = 1000, use_graph: bool = True, compute: str = "fp32"):
         self.lib = L.load()
         self.model = model
+        self.compute = compute      # "fp32": 3xTF32 fp32-grade tier | "bf16": single-pass tensor tier (ddpm_train.py --mixed_precision bf16)
         self.dev = next(model.parameters()).device
         assert self.dev.type == "cuda"
         self.lr, self.betas, self.eps = lr, betas, eps
@@ -336,7 +337,7 @@ class FinetuneStepper:
 
     def _setup(self, B, C_, H, W):
         self.model.train()
-        self.plan = get_plan(self.model, B, H, W, self.dev, need_grad=True)
+        self.plan = get_plan(self.model, B, H, W, self.dev, need_grad=True, compute=self.compute)
         self.B, self.C, self.H, self.W = B, C_, H, W
         self.clean = torch.empty((B, C_, H, W), device=self.dev, dtype=torch.float32)
         self.noise = torch.empty_like(self.clean)

@@ -112,6 +112,39 @@ int dp_pack_conv_weight_tc(const float* w_oihw, int32_t K, int32_t C, int32_t R,
                            float* ck_hi, float* ck_lo, dp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * bf16 tensor tier (conv_bf16.cu): tcgen05.mma kind::f16 on BF16 operands, fp32 accumulation — what torch.autocast(bfloat16) makes of
+ * aten::convolution / linear in the finetune step (ddpm_train.py:200-208,255-261 `--mixed_precision bf16`; BASELINE configs[3]).
+ * Operands are bf16 NHWC views (pixel stride in ELEMENTS, a multiple of 8) produced by dp_cvt_bf16 or by dp_groupnorm_fwd's y_bf16
+ * output; outputs (y, dx, the wgrad workspace) are fp32 exactly as in dp_conv_args, so bias / temb / residual epilogues, the
+ * split-K reduce and everything downstream are shared with the fp32-grade tier.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct dp_conv_bf16_args {
+  int32_t N, H, W, C;
+  int32_t P, Q, K;
+  int32_t R, S, stride, pad_t, pad_l;
+  int32_t flags;            /* DP_CONV_ACCUMULATE */
+  int32_t splits;           /* wgrad */
+  const void* x_bf16; int64_t ldx;    /* fprop / wgrad input  [N][H][W][ldx]  bf16 */
+  const void* dy_bf16; int64_t lddy;  /* dgrad / wgrad input  [N][P][Q][lddy] bf16 */
+  float* out; int64_t ld_out;         /* fprop: y [N][P][Q][ld_out] | dgrad: dx [N][H][W][ld_out]   fp32 */
+  const void* w_bf16;       /* dp_pack_conv_weight_bf16: fprop kc [R*S][K][Cp] | dgrad ck [R*S][C][Kp], Cp/Kp = dp_bf16_weight_row */
+  const float* bias; const float* rowadd; int64_t ld_rowadd; const float* residual; int64_t ld_res;   /* fprop epilogue, as dp_conv_args */
+  float* workspace;         /* wgrad: [splits][K][R*S*C] fp32 partial sums (dp_conv2d_wgrad_reduce finishes) */
+} dp_conv_bf16_args;
+int dp_bf16_available(void);
+int dp_bf16_weight_row(int channels);      /* packed weight row length: channels rounded up to 64 (one 128-byte TMA row) */
+int dp_bf16_wgrad_ctile(int in_channels);  /* in-channel tile width of dp_conv2d_wgrad_bf16 (grid sizing for the split-K choice) */
+int dp_conv2d_fprop_bf16(const dp_conv_bf16_args* a, dp_stream_t stream);
+int dp_conv2d_dgrad_bf16(const dp_conv_bf16_args* a, dp_stream_t stream);
+int dp_conv2d_wgrad_bf16(const dp_conv_bf16_args* a, dp_stream_t stream);
+/* op: 0 fprop, 1 dgrad, 2 wgrad — DP_OK when the bf16 kernels take this geometry (pointers not needed), else DP_ERR_UNSUPPORTED */
+int dp_conv_bf16_eligible(const dp_conv_bf16_args* a, int op);
+/* fp32 [rows][ld] view with C valid channels -> bf16 (RNE) [rows][ld_dst], ld_dst a multiple of 8, pads zeroed */
+int dp_cvt_bf16(const float* src, int64_t ld, int64_t rows, int32_t C, void* dst, int64_t ld_dst, dp_stream_t stream);
+/* OIHW fp32 -> bf16 K-major operands kc [R*S][K][Cp] and ck [R*S][C][Kp] (either may be NULL) */
+int dp_pack_conv_weight_bf16(const float* w_oihw, int32_t K, int32_t C, int32_t R, int32_t S, void* kc, void* ck, dp_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Batched strided GEMM  C[b] (=|+=) alpha * A[b] x B[b]   (attention core: aten::baddbmm/bmm,
  * attention_processor.py:341-357,452).  A(m,k) = A[b*a_bs + m*a_rs + k*a_cs], one of a_rs/a_cs must be 1;
  * B(k,n) = B[b*b_bs + k*b_rs + n*b_cs], one of b_rs/b_cs must be 1; C row-major with ldc.
@@ -176,6 +209,9 @@ typedef struct dp_gn_args {
   float dropout_p; uint64_t dropout_seed;
   const uint64_t* dropout_seed_dev; /* optional DEVICE scalar added to dropout_seed (lets a captured CUDA graph
                                        draw a fresh mask every replay) */
+  /* bf16 tier: the forward additionally (or, with y == NULL, only) writes its output rounded to bf16 (RNE) as the next
+   * convolution's operand — [N][HW][ldyb] with ldyb a multiple of 8; pad columns are left untouched (never read: TMA bounds) */
+  void* y_bf16; int64_t ldyb;
 } dp_gn_args;
 size_t dp_groupnorm_workspace_bytes(int32_t N, int32_t HW, int32_t C, int32_t G);
 int dp_groupnorm_fwd(const dp_gn_args* a, dp_stream_t stream);

@@ -207,26 +207,225 @@ def test_fused_signed_scores_fall_out_of_backward():
     assert worst < 2e-5, worst
 
 
-def test_lsun256_architecture_one_pass_vs_oracle():
-    """BASELINE config 3 architecture (google/ddpm-ema-bedroom-256: 113.7 M params, 3x256x256), batch 1, one Taylor pass on
-    the GPU vs the CPU oracle: loss and every parameter gradient."""
-    from oracle import unet_oracle as orc
+def test_cfg3_lsun256_b4_scores_and_masks_bit_exact():
+    """BASELINE config 3 (google/ddpm-ema-bedroom-256 architecture, 113.7 M params, batch 4 x 3x256x256, ratio 0.05, README.md:140-148)
+    on the GPU against tests/golden/lsun_cfg3_s3.pt — produced by the UNMODIFIED reference on 3 of the 1000 timesteps (t = 0, 500, 999):
+    losses, eps_hat (strided sample) <= 1e-4, accumulated-gradient fingerprints, then for all three importance variants the interactive
+    prune sequence: group order, per-group importance vectors, and the pruned channel-index sets BIT-EXACT (at ratio 0.05 the 59
+    GroupNorm-coupled groups get a per-GN-group quota of 0 and prune nothing, metapruner.py:237-246; the 12 others carry the mask)."""
+    G = load_golden("lsun_cfg3_s3.pt")
     cfg = dp.LSUN256_DDPM_CONFIG
-    torch.manual_seed(0)
-    m = dp.UNet2DModel(**cfg).eval()
+    m = build(cfg)
     assert round(sum(p.numel() for p in m.parameters()) / 1e6, 3) == 113.673
-    sd = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
-    g = torch.Generator().manual_seed(4)
-    clean, noise = torch.randn(1, 3, 256, 256, generator=g), torch.randn(1, 3, 256, 256, generator=g)
-    t = torch.tensor([321])
-    torch.set_num_threads(min(32, torch.get_num_threads()))
-    ref = orc.taylor_pass(sd, cfg, orc.alphas_cumprod(), clean, noise, t)
-    m = m.cuda()
+    clean, noise = inputs(G["B"], G["hw"])
     m.zero_grad()
     sc = TaylorScorer(m, clean.cuda(), noise.cuda(), use_graph=False)
-    assert sc.step(t).item() == pytest.approx(ref.item(), rel=1e-5)
-    worst = worst_grad_err(((k, p.grad) for k, p in m.named_parameters()), {k: v.grad for k, v in sd.items()})
-    assert worst < 2e-4, worst
+    st = G["eps_stride"]
+    for t, l_ref, e_ref in zip(G["timesteps"], G["losses"], G["eps_sub"]):
+        assert sc.step(t).item() == pytest.approx(l_ref, rel=5e-6), t
+        assert max_rel(sc.plan.output_nchw()[:, :, ::st, ::st], e_ref) < 1e-4, t
+    for k, p in m.named_parameters():
+        assert float((p.grad.double() ** 2).sum()) == pytest.approx(G["grad_fp"][k][2], rel=5e-3), k
+    grads = {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+    del sc
+    m._dpb200_plans.clear()
+    torch.cuda.empty_cache()
+    sched = dp.DDPMScheduler()
+    for variant, V in G["variants"].items():
+        mv = copy.deepcopy(m)
+        for k, p in mv.named_parameters():
+            p.grad = grads[k].clone()
+        rec = pruning.taylor_prune(mv, G["ratio"], variant, ignored_layers=[mv.conv_out])
+        assert [r["root"] for r in rec] == [g["root"] for g in V["groups"]]
+        worst_imp, n_sel = 0.0, 0
+        for r, g in zip(rec, V["groups"]):
+            worst_imp = max(worst_imp, rel_err(r["imp"], g["imp"]))
+            assert sorted(r["idxs"]) == sorted(g["idxs"]), (variant, g["root"], worst_imp)   # bit-exact mask
+            n_sel += len(g["idxs"])
+        assert n_sel == 267 and worst_imp < 2e-3, (variant, n_sel, worst_imp)
+        assert {k: list(v.shape) for k, v in mv.state_dict().items()} == V["pruned_shapes"]
+        assert sum(p.numel() for p in mv.parameters()) == V["pruned"][1] == 112648617
+        with torch.no_grad():
+            t = (10 * torch.ones(2, device="cuda")).long()
+            out = mv(sched.add_noise(clean[:2].cuda(), noise[:2].cuda(), t), t).sample
+        assert max_rel(out[:, :, ::st, ::st], V["pruned_eps_b2_t10"]) < 1e-4, variant
+        del mv
+        torch.cuda.empty_cache()
+
+
+def _pruned_c1(batch=8):
+    """C1 pruned at ratio 0.3 by the product path (3 accumulated scoring passes, taylor_prune): the 19.85 M-parameter architecture."""
+    m = build(dp.CIFAR10_DDPM_CONFIG)
+    clean, noise = inputs(batch, 32)
+    m.zero_grad()
+    sc = TaylorScorer(m, clean.cuda(), noise.cuda(), use_graph=False)
+    for t in (0, 500, 999):
+        sc.step(t)
+    del sc
+    pruning.taylor_prune(m, 0.3, "taylor", ignored_layers=[m.conv_out])
+    m.zero_grad(set_to_none=True)
+    assert sum(p.numel() for p in m.parameters()) == 19851157
+    return m
+
+
+def test_finetune_two_steps_on_pruned_c1_vs_oracle():
+    """The network bench.py's finetune leg times (C1 at ratio 0.3: widths 96 / 192 / 179 / 358, stale attention scale) through two
+    optimisation steps of ddpm_train.py:437-469 (dropout 0) against the CPU oracle: loss, pre-clip gradient norm, parameters and EMA."""
+    from oracle import unet_oracle as orc
+    m = _pruned_c1().train()
+    cfg = dp.CIFAR10_DDPM_CONFIG
+    params = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    ema = {k: v.detach().clone() for k, v in params.items()}
+    opt = torch.optim.Adam(list(params.values()), lr=2e-4, betas=(0.9, 0.999), weight_decay=0.0, eps=1e-8)
+    ac = orc.alphas_cumprod()
+    st = FinetuneStepper(m, lr=2e-4, ema_decay=0.9999, max_grad_norm=1.0, use_graph=True)
+    g = torch.Generator().manual_seed(11)
+    torch.set_num_threads(min(32, torch.get_num_threads()))
+    for step in range(2):
+        clean, noise = torch.randn(8, 3, 32, 32, generator=g), torch.randn(8, 3, 32, 32, generator=g)
+        t = orc.antithetic_timesteps(8, 1000, generator=g)
+        l_ref, gn_ref = orc.finetune_step(params, cfg, ac, clean, noise, t, opt, ema)
+        loss = st.step(clean.cuda(), noise.cuda(), t.cuda())
+        assert loss.item() == pytest.approx(l_ref.item(), rel=2e-5), step
+        assert float(st.sumsq.sqrt()) == pytest.approx(gn_ref.item(), rel=2e-4), step
+    e = st.ema_state()
+    for k, p in m.named_parameters():
+        assert rel_err(p, params[k]) < 5e-5, k
+        assert rel_err(e[k], ema[k]) < 5e-5, k
+
+
+def test_sharded_scoring_equals_sequential_on_two_streams():
+    """Timestep sharding exercised on ONE GPU: two replicas of the model act as ranks 0 / 1 on two CUDA streams
+    (t = r, r+2, ...), their gradient arenas are summed (what the NCCL all-reduce does) and compared with the sequential loop —
+    so the driver's single-GPU box checks sharded == sequential too (tests/test_multi_gpu.py needs 2 GPUs)."""
+    m = build(dp.TINY_TEST_CONFIG)
+    clean, noise = (x.cuda() for x in inputs(2, 16))
+    ts = list(range(0, 1000, 125))
+    m.zero_grad()
+    seq = TaylorScorer(m, clean, noise, use_graph=False)
+    l_seq = seq.run(ts, shard=False)
+    reps, streams, losses = [], [torch.cuda.Stream(), torch.cuda.Stream()], {}
+    for r in range(2):
+        mr = copy.deepcopy(m)
+        mr.zero_grad(set_to_none=True)
+        reps.append(TaylorScorer(mr, clean, noise, use_graph=False))
+    torch.cuda.synchronize()
+    for k, t in enumerate(ts):
+        with torch.cuda.stream(streams[k % 2]):
+            losses[k] = reps[k % 2].step(t).clone()
+    torch.cuda.synchronize()
+    total = reps[0].plan.grad_arena + reps[1].plan.grad_arena
+    assert rel_err(total, seq.plan.grad_arena) < 1e-6
+    assert torch.allclose(torch.stack([losses[k] for k in range(len(ts))]).flatten(), l_seq, rtol=1e-6)
+
+
+def test_diff_pruning_threshold_rule_on_gpu():
+    """`--pruner diff-pruning` (ddpm_prune.py:104-106): run(thr=) stops after the first timestep whose loss drops below thr x the running
+    maximum; that timestep's gradient is included.  Against the sequential loop replayed step by step on a second replica."""
+    from diff_pruning_b200.scoring import threshold_stop
+    m = build(dp.TINY_TEST_CONFIG)
+    clean, noise = (x.cuda() for x in inputs(2, 16))
+    ts = list(range(0, 1000, 40))
+    ref = copy.deepcopy(m)
+    ref.zero_grad(set_to_none=True)
+    rs = TaylorScorer(ref, clean, noise, use_graph=False)
+    all_losses = [rs.step(t).item() for t in ts]
+    thr = 0.5 * (1.0 + min(all_losses[3:]) / max(all_losses[:3]))     # a threshold the sequence crosses part-way
+    n_used = threshold_stop(all_losses, thr)
+    assert 1 < n_used < len(ts), (n_used, all_losses)
+    ref.zero_grad(set_to_none=True)
+    ref._dpb200_plans.clear()
+    rs = TaylorScorer(ref, clean, noise, use_graph=False)
+    for t in ts[:n_used]:
+        rs.step(t)
+    m.zero_grad()
+    sc = TaylorScorer(m, clean, noise, use_graph=True)
+    used = sc.run(ts, thr=thr)
+    assert len(used) == n_used and used.cpu().tolist() == pytest.approx(all_losses[:n_used], rel=1e-6)
+    assert rel_err(sc.plan.grad_arena, rs.plan.grad_arena) < 1e-6
+
+
+def test_fused_scores_match_the_oracle_item_score():
+    """fused_scores=True: the wgrad reduce accumulates sum_t sum_k W*dW_t per in/out channel; |.| of it is the `multivariable=True`
+    Taylor score of the UNSLICED layer (importance.py:393,407 with the abs outside the sum).  Checked against the oracle's item_score on
+    the accumulated gradient.  (Later groups of an interactive prune see already-sliced layers, so the product's taylor_prune re-reads
+    W and dW per group; the fused vector is exact for each layer's first evaluation and as the small all-reduce payload.)"""
+    from oracle import unet_oracle as orc
+    m = build(dp.TINY_TEST_CONFIG)
+    clean, noise = inputs(2, 16)
+    sc = TaylorScorer(m, clean.cuda(), noise.cuda(), use_graph=True, fused_scores=True)
+    for t in (3, 250, 600, 990):
+        sc.step(t)
+    params = dict(m.named_parameters())
+    worst = 0.0
+    for name, (so, si) in sc.signed_scores().items():
+        w, dw = params[name].detach().cpu(), params[name].grad.detach().cpu()
+        ref_o = orc.item_score(w, dw, "out", list(range(w.shape[0])), "taylor")
+        ref_i = orc.item_score(w, dw, "in", list(range(w.shape[1])), "taylor")
+        scale = float(orc.item_score(w, dw, "out", list(range(w.shape[0])), "diff").max())   # sum |w dw|: size of the summands
+        worst = max(worst, float((so.abs().cpu() - ref_o).abs().max()) / scale, float((si.abs().cpu() - ref_i).abs().max()) / scale)
+    assert worst < 2e-5, worst
+
+
+def test_forward_after_finetune_step_uses_current_weights():
+    """the Adam kernel writes the parameter arena through raw pointers and `param.data.copy_` (EMAModel.copy_to /
+    restore) leaves torch's version counters untouched — a cached no-grad plan must not keep the packs of its first use."""
+    from diff_pruning_b200 import engine
+    m = build(dp.TINY_TEST_CONFIG).train()
+    st = FinetuneStepper(m, lr=1e-2, ema_decay=0.9, max_grad_norm=1.0, use_graph=True)
+    g = torch.Generator().manual_seed(3)
+    clean, noise = torch.randn(4, 3, 16, 16, generator=g).cuda(), torch.randn(4, 3, 16, 16, generator=g).cuda()
+    t = torch.tensor([5, 300, 700, 994]).cuda()
+    x = torch.randn(2, 3, 16, 16, generator=g).cuda()
+
+    def fresh(model):       # the same weights through a plan that has never been used
+        m2 = copy.deepcopy(model).eval()
+        with torch.no_grad():
+            return m2(x, 50).sample
+    m.eval()
+    for it in range(2):
+        m.train(); st.step(clean, noise, t); m.eval()
+        with torch.no_grad():
+            y = m(x, 50).sample
+        assert torch.equal(y, fresh(m)), it
+    # EMA copy_to-style write (no version bump) followed by sampling inside frozen_weights, then restore
+    saved = [p.detach().clone() for p in m.parameters()]
+    with torch.no_grad():
+        for p, e in zip(m.parameters(), st.ema_state().values()):
+            p.data.copy_(e)
+    with engine.frozen_weights(m), torch.no_grad():
+        y_ema = m(x, 50).sample
+        assert torch.equal(y_ema, m(x, 50).sample)
+    assert torch.equal(y_ema, fresh(m))
+    with torch.no_grad():
+        for p, s_ in zip(m.parameters(), saved):
+            p.data.copy_(s_)
+        assert torch.equal(m(x, 50).sample, y)
+
+
+def test_autograd_path_guards_and_dropout_stream():
+    """(a) two forwards before one backward must raise instead of producing gradients from overwritten
+    activations; (b) an input that requires grad is refused (the engine does not produce dL/dsample); (c) in train mode with dropout
+    every forward draws a fresh mask (the unmodified ddpm_train.py loop with --dropout 0.1)."""
+    m = build(dp.TINY_TEST_CONFIG)
+    x = torch.randn(2, 3, 16, 16, device="cuda")
+    y1 = m(x, 10).sample
+    y2 = m(x, 20).sample
+    with pytest.raises(RuntimeError, match="overwritten"):
+        y1.sum().backward()
+    y2.sum().backward()
+    with pytest.raises(RuntimeError, match="d\\(loss\\)/d\\(sample\\)"):
+        m(x.clone().requires_grad_(True), 10)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.3
+    m.train()
+    with torch.no_grad():
+        a, b = m(x, 10).sample, m(x, 10).sample
+    assert not torch.equal(a, b)
+    m.eval()
+    with torch.no_grad():
+        assert torch.equal(m(x, 10).sample, m(x, 10).sample)
 
 
 def test_ddim_sampling_matches_reference_pipeline():
