@@ -67,7 +67,6 @@ _SIGS = {
     "dp_last_cuda_error": (C.c_int, []),
     "dp_launch_count": (i64, []),
     "dp_tc_available": (C.c_int, []),
-    "dp_conv_tc_set_trace": (C.c_int, [C.c_void_p]),
     "dp_tc_weight_row": (C.c_int, [C.c_int]),
     "dp_conv2d_fprop": (C.c_int, [C.POINTER(ConvArgs), vp]),
     "dp_conv2d_dgrad": (C.c_int, [C.POINTER(ConvArgs), vp]),

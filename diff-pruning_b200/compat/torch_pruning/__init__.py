@@ -35,6 +35,29 @@ class TaylorImportance(_Importance):
         return _sc.group_importance(group.items, named_w, named_g, self.variant)
 
 
+class FullTaylorImportance(TaylorImportance):
+    """ddpm_exp/torch_pruning/importance.py:438-548 (order 1 or 2)."""
+
+    def __init__(self, order=1, group_reduction="mean", normalizer="mean"):
+        if order not in (1, 2):
+            raise NotImplementedError(order)
+        self.variant = f"full{order}"
+
+
+class AbsTaylorImportance(TaylorImportance):
+    """ddpm_exp/torch_pruning/importance.py:553-670 (the per-layer criterion; its accum_abs_grad helper is an experiment-side loop)."""
+
+    def __init__(self, order=1, group_reduction="mean", normalizer="mean"):
+        self.variant = "abs"
+
+
+class FisherImportance(TaylorImportance):
+    """ddpm_exp/torch_pruning/importance.py:672-781."""
+
+    def __init__(self, group_reduction="mean", normalizer="mean"):
+        self.variant = "fisher"
+
+
 class MagnitudeImportance(_Importance):
     """L2 norm of the weights per channel, summed over the group's equally-sized members (importance.py:18-126, p=2)."""
 
@@ -60,7 +83,8 @@ class RandomImportance(_Importance):
 
 
 importance = SimpleNamespace(TaylorImportance=TaylorImportance, MagnitudeImportance=MagnitudeImportance,
-                             RandomImportance=RandomImportance, Importance=_Importance)
+                             RandomImportance=RandomImportance, Importance=_Importance, FullTaylorImportance=FullTaylorImportance,
+                             AbsTaylorImportance=AbsTaylorImportance, FisherImportance=FisherImportance)
 
 
 class _Group:

@@ -240,7 +240,8 @@ def taylor_layer_scores(weight: torch.Tensor, grad: torch.Tensor) -> Dict[str, t
     return res
 
 
-_VARIANT_KEY = {"vendored": "sq", "taylor": "signed", "diff": "abs"}
+_VARIANT_KEY = {"vendored": "sq", "taylor": "signed", "diff": "abs", "abs": "abs"}
+EXP_VARIANTS = ("full1", "full2", "abs", "fisher")   # ddpm_exp/torch_pruning/importance.py:438-781
 
 
 def group_importance(items: Sequence[Tuple[str, str, Sequence[int]]], named_weights: Dict[str, torch.Tensor],
@@ -248,17 +249,28 @@ def group_importance(items: Sequence[Tuple[str, str, Sequence[int]]], named_weig
                      cache: Optional[dict] = None) -> Optional[torch.Tensor]:
     """importance.py:375-434 for one group given as (layer_name, kind in {out,in,gn}, idxs) items.
     variant: 'taylor' = |sum_k w dw| (multivariable=True, ddpm_prune.py:60), 'diff' = sum_k |w dw|
-    (multivariable=False, :66), 'vendored' = sum_k (w dw)^2 (vendored importance.py:393).  GroupNorm: |w dw| (:416)."""
+    (multivariable=False, :66), 'vendored' = sum_k (w dw)^2 (vendored importance.py:393).  GroupNorm: |w dw| (:416).
+    The ddpm_exp criteria go through the same device reductions: 'full1' / 'full2' = FullTaylorImportance(order) (:438-548: signed
+    sum_k w dw, + sum_k (w dw)^2 for order 2, abs AFTER the group sum), 'abs' = AbsTaylorImportance (:553-670, = 'diff' per item),
+    'fisher' = FisherImportance (:672-781: sum_k dw^2 — dp_taylor_reduce with w := dw — and (w dw)^2 for GroupNorm)."""
     cache = {} if cache is None else cache
     imps = []
     for name, kind, idxs in items:
-        sc = cache.get(name)
+        w, g = named_weights[name + ".weight"], named_grads[name + ".weight"]
+        ck = (name, "fisher") if (variant == "fisher" and kind != "gn") else name
+        sc = cache.get(ck)
         if sc is None:
-            sc = taylor_layer_scores(named_weights[name + ".weight"], named_grads[name + ".weight"])
-            cache[name] = sc
+            sc = taylor_layer_scores(g, g) if ck != name else taylor_layer_scores(w, g)
+            cache[ck] = sc
         idx = torch.as_tensor(sorted(idxs), device=sc["out_abs"].device, dtype=torch.long)
         if kind == "gn":
-            v = sc["out_abs"][idx]
+            v = {"full1": sc["out_signed"], "full2": sc["out_signed"] + sc["out_sq"], "fisher": sc["out_sq"]}.get(variant, sc["out_abs"])[idx]
+        elif variant == "full1":
+            v = sc[f"{kind}_signed"][idx]
+        elif variant == "full2":
+            v = sc[f"{kind}_signed"][idx] + sc[f"{kind}_sq"][idx]
+        elif variant == "fisher":
+            v = sc[f"{kind}_signed"][idx]            # sum_k dw*dw
         else:
             v = sc[f"{kind}_{_VARIANT_KEY[variant]}"][idx]
             if variant == "taylor":
@@ -267,7 +279,8 @@ def group_importance(items: Sequence[Tuple[str, str, Sequence[int]]], named_weig
     if not imps:
         return None
     size = len(imps[0])
-    return torch.stack([i for i in imps if len(i) == size], dim=0).sum(0)
+    total = torch.stack([i for i in imps if len(i) == size], dim=0).sum(0)
+    return total.abs() if variant in ("full1", "full2") else total
 
 
 def select_pruning_idxs(imp: torch.Tensor, ch_groups: int, n_pruned: int) -> List[int]:

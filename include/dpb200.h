@@ -41,9 +41,6 @@ int dp_last_cuda_error(void);
 int64_t dp_launch_count(void);
 /* 1 if the tcgen05/TMA tensor-core path is compiled in and usable on the current device, else 0 */
 int dp_tc_available(void);
-/* profiling hook (profiles/r01_experiments.md): CTA 0 of each following persistent tensor-core conv launch stamps clock64()
- * per pipeline stage and actor into buf (16640 int64, device memory); NULL switches it off. */
-int dp_conv_tc_set_trace(long long* buf);
 
 /* ------------------------------------------------------------------------------------------------
  * Convolution as implicit GEMM.  Replaces aten::convolution / convolution_backward reached from

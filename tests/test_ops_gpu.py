@@ -384,3 +384,27 @@ def test_adam_clip_ema_matches_torch(lib):
             a.step_scalars, a.step = scal.data_ptr(), 1
         assert lib.dp_adam_clip_ema(C.byref(a), S()) == 0
         assert rel_err(pd.cpu(), pt.detach()) < 1e-6 and rel_err(ed.cpu(), ema_ref) < 1e-6
+
+
+def test_exp_importance_variants_on_device():
+    """ddpm_exp criteria (FullTaylor order 1/2, AbsTaylor, Fisher — importance.py:438-781) through dp_taylor_reduce against the unmodified
+    vendored classes (tests/golden/exp_importance_tiny.pt): gradients from two accumulated engine passes."""
+    from conftest import expand, load_golden
+    import diff_pruning_b200 as dp
+    from diff_pruning_b200.scoring import EXP_VARIANTS, TaylorScorer, group_importance
+    G = load_golden("exp_importance_tiny.pt")
+    torch.manual_seed(0)
+    m = dp.UNet2DModel(**G["cfg"]).eval().cuda()
+    g1, g2 = torch.Generator().manual_seed(1), torch.Generator().manual_seed(2)
+    clean, noise = torch.randn(2, 3, 16, 16, generator=g1), torch.randn(2, 3, 16, 16, generator=g2)
+    m.zero_grad()
+    sc = TaylorScorer(m, clean.cuda(), noise.cuda(), use_graph=False)
+    sc.step(7); sc.step(400)
+    w = {k: p for k, p in m.named_parameters()}
+    dw = {k: p.grad for k, p in m.named_parameters()}
+    for g in G["groups"]:
+        items = [(n, k, expand(i)) for n, k, i in g["items"]]
+        for variant in EXP_VARIANTS:
+            got = group_importance(items, w, dw, variant).cpu()
+            ref = g["imp"][variant]
+            assert float((got - ref).abs().max()) <= 5e-4 * float(ref.abs().max()) + 1e-12, (g["root"], variant)

@@ -168,3 +168,27 @@ def test_cfg1_published_counts():
     assert round(V["pruned"][0] / 1e9, 3) == 3.392
     assert len(V["groups"]) == 50 and sum(len(g["idxs"]) for g in V["groups"]) == 3164
     assert G["losses"][0] == pytest.approx(1.1193706, rel=1e-6) and G["losses"][99] == pytest.approx(1.1028205, rel=1e-6)
+
+
+def test_exp_importance_variants_match_the_vendored_classes():
+    """FullTaylor(order 1, 2) / AbsTaylor / Fisher (ddpm_exp/torch_pruning/importance.py:438-781): the oracle's item scores on the
+    fixture's groups, with gradients re-derived by the oracle's own two accumulated passes."""
+    from conftest import expand
+    G = load_golden("exp_importance_tiny.pt")
+    cfg = G["cfg"]
+    torch.manual_seed(0)
+    import diff_pruning_b200 as dp
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in dp.UNet2DModel(**cfg).state_dict().items()}
+    g1, g2 = torch.Generator().manual_seed(1), torch.Generator().manual_seed(2)
+    clean, noise = torch.randn(2, 3, 16, 16, generator=g1), torch.randn(2, 3, 16, 16, generator=g2)
+    for tt in (7, 400):
+        orc.taylor_pass(sd, cfg, orc.alphas_cumprod(), clean, noise, (tt * torch.ones(2)).long())
+    w = {k: v.detach() for k, v in sd.items()}
+    dw = {k: v.grad for k, v in sd.items()}
+    assert len(G["groups"]) == 22
+    for g in G["groups"]:
+        items = [(n, k, expand(i)) for n, k, i in g["items"]]
+        for variant in orc.EXP_VARIANTS:
+            got = orc.group_importance(items, w, dw, variant)
+            ref = g["imp"][variant]
+            assert float((got - ref).abs().max()) <= 2e-4 * float(ref.abs().max()) + 1e-12, (g["root"], variant)

@@ -448,6 +448,33 @@ def gen_lsun_struct(ratio=0.05):
     print("lsun_struct", len(groups), base_params, params, base_macs, macs)
 
 
+def gen_exp_importance():
+    """The ddpm_exp importance criteria (ddpm_exp/torch_pruning/importance.py:438-548 FullTaylor order 1/2, :553-670 AbsTaylor,
+    :672-781 Fisher) evaluated by the UNMODIFIED vendored classes on every pruning group of the TINY UNet after two accumulated passes."""
+    os.chdir("/tmp")
+    cfg = dict(dp.TINY_TEST_CONFIG)
+    m = build(cfg)
+    sched = DDPMScheduler(num_train_timesteps=1000)
+    clean, noise = inputs(2, 16)
+    m.zero_grad()
+    for tt in (7, 400):
+        t = (tt * torch.ones(2)).long()
+        torch.nn.functional.mse_loss(m(sched.add_noise(clean, noise, t), t).sample, noise).backward()
+    example = {"sample": torch.randn(1, 3, 16, 16), "timestep": torch.ones((1,)).long()}
+    pruner = tp.pruner.MagnitudePruner(m, example, importance=tp.importance.MagnitudeImportance(), iterative_steps=1, channel_groups={},
+                                       ch_sparsity=0.3, ignored_layers=[m.conv_out])
+    names = {mod: n for n, mod in m.named_modules()}
+    crits = {"full1": tp.importance.FullTaylorImportance(order=1), "full2": tp.importance.FullTaylorImportance(order=2),
+             "abs": tp.importance.AbsTaylorImportance(), "fisher": tp.importance.FisherImportance()}
+    groups = []
+    for g in pruner.DG.get_all_groups(ignored_layers=pruner.ignored_layers, root_module_types=pruner.root_module_types):
+        items = describe_group_c(g, names)
+        groups.append({"root": names[g[0][0].target.module], "items": items,
+                       "imp": {k: c(g).clone() for k, c in crits.items()}})
+    torch.save({"cfg": cfg, "groups": groups}, os.path.join(OUT, "exp_importance_tiny.pt"))
+    print("exp_importance", len(groups), os.path.getsize(os.path.join(OUT, "exp_importance_tiny.pt")))
+
+
 def gen_ref_pickle():
     """A whole-module pickle exactly as the reference writes it (`torch.save(model)`, ddpm_prune.py:135) for a small member of the
     family after a `--pruner magnitude` prune at ratio 0.3 — default AttnProcessor2_0 objects, FrozenDict config and all — plus eps_hat
@@ -486,7 +513,7 @@ if __name__ == "__main__":
     ap.add_argument("--only", default=None)
     a = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
-    jobs = {"ref_pickle": gen_ref_pickle, "lsun_struct": gen_lsun_struct, "lr": gen_lr, "ckpt": gen_ckpt, "ddim": gen_ddim, "tiny": gen_tiny, "blocks": gen_blocks, "finetune": gen_finetune, "cifar_fwd": gen_cifar_fwd,
+    jobs = {"exp_importance": gen_exp_importance, "ref_pickle": gen_ref_pickle, "lsun_struct": gen_lsun_struct, "lr": gen_lr, "ckpt": gen_ckpt, "ddim": gen_ddim, "tiny": gen_tiny, "blocks": gen_blocks, "finetune": gen_finetune, "cifar_fwd": gen_cifar_fwd,
             "cfg1_s3": gen_cfg1_s3, "cfg3_s3": gen_cfg3_s3, "cfg1": gen_cfg1}
     for name, fn in jobs.items():
         if a.only and name != a.only:
