@@ -121,7 +121,7 @@ def best_cpu_threads(one_pass):
     """Give the CPU arm its best thread count: torch's intra-op pool over-subscribes badly on 100+ core hosts for these convs
     (measured 79 s/pass at 128 threads vs ~1.5 s at 8-32, C1 batch 16), so try a few and keep the fastest."""
     ncpu = os.cpu_count() or 1
-    cands = sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu})
+    cands = sorted({c for c in (8, 16, 32, 64) if c <= ncpu}) or [ncpu]
     best, best_t = cands[0], None
     for c in cands:
         torch.set_num_threads(c)
@@ -297,8 +297,13 @@ def timed_conv_launches(plan, prologue=None, midlogue=None):
             cnt, tot = by_layer.get(key, (0, 0.0))
             by_layer[key] = (cnt + 1, tot + ms)
     total = sum(a.elapsed_time(b) for a, b, _, _ in pairs) * 1e-3
-    top = sorted(by_layer.items(), key=lambda kv: -kv[1][1])[:12]
-    return total, len(pairs), {k: round(v, 3) for k, v in sorted(by_tag.items())}, {k: {"n": n, "ms": round(t, 3)} for k, (n, t) in top}
+    ranked = sorted(by_layer.items(), key=lambda kv: -kv[1][1])
+    dump = os.environ.get("DPB200_LAYERS_OUT")           # developer knob: append the full per-layer table of every timed plan to a file
+    if dump:
+        with open(dump, "a") as f:
+            f.write(json.dumps({"compute": getattr(plan, "compute", "fp32"), "B": plan.B, "H": plan.H, "total_ms": round(total * 1e3, 3),
+                                "layers": {k: {"n": n, "ms": round(t, 4)} for k, (n, t) in ranked}}) + "\n")
+    return total, len(pairs), {k: round(v, 3) for k, v in sorted(by_tag.items())}, {k: {"n": n, "ms": round(t, 3)} for k, (n, t) in ranked[:12]}
 
 
 def pruned_model(cfg_key, dev, ratio=0.3):
@@ -366,16 +371,76 @@ def finetune_bench(args, rank, world, dev, barrier, compute="fp32"):
                      f"{world} GPU(s)", "loss": float(st.loss.item())}
     if rank == 0:
         _, tf_sus, _, which = peaks()
-        conv_s, n_conv, by_tag, _ = timed_conv_launches(st.plan)
+        conv_s, n_conv, by_tag, by_layer = timed_conv_launches(st.plan)
         flops = 6.0 * st.plan.conv_macs
         res["roofline"] = {"bound": "tensor", "achieved": flops / conv_s / 1e12, "peak": tf_sus, "unit": "TFLOP/s",
-                           "frac": flops / conv_s / 1e12 / tf_sus, "conv_ms": round(conv_s * 1e3, 3), "breakdown_ms": by_tag,
+                           "frac": flops / conv_s / 1e12 / tf_sus, "conv_ms": round(conv_s * 1e3, 3), "breakdown_ms": by_tag, "top_layers_ms": by_layer,
                            "conv_gflop_per_image": 6.0 * st.plan.conv_macs / B / 1e9,
                            "note": f"6 x conv MACs of the pruned network (from the launch plan) / summed conv-launch time of one step; peak = bf16_tflops_sustained ({which})"}
     del st
     if hasattr(m, "_dpb200_plans"):
         m._dpb200_plans.clear()
     del m
+    torch.cuda.empty_cache()
+    return res
+
+
+def secondary_scoring_leg(cfg_key, args, rank, world, dev, barrier):
+    """The Taylor-scoring metric on ANOTHER BASELINE configuration inside the default run (the driver only launches `bench.py --gpus N`):
+    c3 = LSUN-256 architecture, batch 4 per GPU, timesteps sharded over the ranks, one gradient all-reduce at the end."""
+    import torch.distributed as dist
+    import diff_pruning_b200 as dp
+    from diff_pruning_b200 import _lib as L
+    from diff_pruning_b200.scoring import TaylorScorer
+    lib = L.load()
+    c = CONFIGS[cfg_key]
+    B, hw = c["batch"], c["hw"]
+    torch.manual_seed(0)
+    model = dp.UNet2DModel(**getattr(dp, c["model"])).eval().to(dev)
+    clean, noise = synth_batch(B, hw, seed_off=100 * rank)
+    model.zero_grad()
+    sc = TaylorScorer(model, clean.to(dev), noise.to(dev), use_graph=not args.no_graph)
+    K, Wm = max(3, min(args.steps, 8)), 3
+    ts = [(rank + k * world) % 1000 for k in range(Wm + K)]
+    for k in range(Wm):
+        sc.step(ts[k])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(K):
+        sc.step(ts[Wm + k])
+    if world > 1:
+        dist.all_reduce(sc.plan.grad_arena, op=dist.ReduceOp.SUM)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    res = {"metric": METRIC, "value": world * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / K, "steps": K, "warmup": Wm, "dtype": "f32",
+           "config": {"workload": f"{c['name']} Taylor pass, batch {B} x 3x{hw}x{hw} per GPU, timesteps sharded over {world} GPU(s), one grad all-reduce at the end"}}
+    if rank == 0:
+        p = sc.plan
+
+        def pro(s_int):
+            p.t_dev.fill_(3)
+            L.check(lib.dp_add_noise(sc.clean.data_ptr(), sc.noise.data_ptr(), p.t_dev.data_ptr(), sc.acp.data_ptr(),
+                                     p.x_in.ptr, sc.B, sc.C, sc.H, sc.W, 1, p.x_in.ld, s_int))
+
+        def mid(s_int):
+            gy = p.gradof(p.y_out)
+            L.check(lib.dp_mse_loss_grad(p.y_out.ptr, sc.noise_nhwc.data_ptr(), gy.ptr, sc.n, sc.loss_scale, sc.grad_scale,
+                                         sc.partial.data_ptr(), sc.loss.data_ptr(), s_int))
+        conv_s, n_conv, by_tag, by_layer = timed_conv_launches(p, pro, mid)
+        _, tf_sus, _, which = peaks()
+        ach = B * c["conv_flop"] / conv_s / 1e12
+        res["roofline"] = {"bound": "tensor", "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus,
+                           "conv_ms": round(conv_s * 1e3, 3), "breakdown_ms": by_tag, "top_layers_ms": by_layer,
+                           "note": f"{B} x {c['conv_flop'] / 1e12:.4f} TFLOP algorithmic conv work per pass (SURVEY.md §8d) / summed conv-launch time; peak = bf16_tflops_sustained ({which}); 3xTF32 tier"}
+    del sc
+    if hasattr(model, "_dpb200_plans"):
+        model._dpb200_plans.clear()
+    del model
     torch.cuda.empty_cache()
     return res
 
@@ -488,6 +553,9 @@ def run_ours(args, rank, world, local_rank):
         from diff_pruning_b200 import engine as _eng
         if getattr(_eng, "BF16_TIER", False):
             finetune_bf16 = finetune_bench(args, rank, world, dev, barrier, compute="bf16")
+    config3 = None
+    if args.config == "c1" and not args.no_c3:
+        config3 = secondary_scoring_leg("c3", args, rank, world, dev, barrier)
     if rank != 0:
         return
     hbm, tf_sus, tf_burst, which = peaks()
@@ -537,6 +605,8 @@ def run_ours(args, rank, world, local_rank):
         out["finetune"] = finetune_leg
     if finetune_bf16 is not None:
         out["finetune_bf16"] = finetune_bf16
+    if config3 is not None:
+        out["config3"] = config3
     print(json.dumps(out), flush=True)
 
 
@@ -552,6 +622,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline and gpu_eager_baseline legs (profiling runs)")
     ap.add_argument("--profile-pass", action="store_true", help="run one eager pass inside cudaProfilerStart/Stop (ncu)")
     ap.add_argument("--no-finetune", action="store_true", help="skip the secondary finetune imgs/s legs")
+    ap.add_argument("--no-c3", action="store_true", help="skip the secondary BASELINE-config-3 (LSUN-256) scoring leg of the default run")
     args = ap.parse_args()
     if args.batch is None:
         args.batch = CONFIGS[args.config]["batch"]

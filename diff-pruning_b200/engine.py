@@ -97,6 +97,21 @@ def _copy_args(a):
     return b
 
 
+ARENA_ALIGN = 64   # floats: every parameter's slice of a flat arena starts on a 256-byte boundary
+
+
+def arena_offsets(params):
+    """Offsets of the parameters inside a flat fp32 arena (gradients / parameters / Adam moments / EMA), each aligned to ARENA_ALIGN
+    floats.  Pruned widths (179, 358, 90 ...) otherwise leave every later tensor at an odd float offset: bias / weight pointers then
+    fail the 16-byte test of the float4 epilogues and TMA descriptors and the kernels fall back to scalar paths (the round-1 'pruned
+    finetune is as slow as the unpruned pass' anomaly).  Gap elements stay zero in every arena (zero grad -> zero Adam update)."""
+    offs, o = [], 0
+    for p in params:
+        offs.append(o)
+        o += (p.numel() + ARENA_ALIGN - 1) // ARENA_ALIGN * ARENA_ALIGN
+    return offs, o
+
+
 class Plan:
     """Static forward/backward launch lists for one (model, batch, H, W)."""
 
@@ -184,13 +199,11 @@ class Plan:
         return self._grad_views[id(p)].data_ptr()
 
     def _setup_param_grads(self):
-        total = sum(p.numel() for p in self.params)
+        offs, total = arena_offsets(self.params)
         self.grad_arena = torch.zeros(total, device=self.dev, dtype=torch.float32)
         self._grad_views = {}
-        o = 0
-        for p in self.params:
+        for p, o in zip(self.params, offs):
             self._grad_views[id(p)] = self.grad_arena[o:o + p.numel()].view_as(p)
-            o += p.numel()
 
     def attach_grads(self):
         """Make every Parameter.grad the plan's arena view (accumulating semantics are preserved)."""

@@ -109,6 +109,7 @@ class DDIMPipeline:
         self.unet = unet
         self.scheduler = DDIMScheduler.from_config(scheduler.config) if not isinstance(scheduler, DDIMScheduler) else scheduler
         self._pbar = {}
+        self.use_graph = True        # replay the UNet forward as one CUDA graph per sampling step
 
     @property
     def device(self):
@@ -134,17 +135,55 @@ class DDIMPipeline:
     @torch.no_grad()
     def __call__(self, batch_size=1, generator=None, eta=0.0, num_inference_steps=50, use_clipped_model_output=None,
                  output_type="pil", return_dict=True):
+        """pipeline_ddim.py:45-122.  The UNet forward of the whole loop is ONE captured CUDA graph (static launch plan, the timestep
+        lives in device memory) replayed per step, followed by the fused scheduler update (dp_ddim_step): no per-step Python walk over
+        the ~400 launches of a forward and no host synchronisation inside the loop."""
         cfg = self.unet.config
         size = cfg.sample_size if isinstance(cfg.sample_size, int) else None
         shape = (batch_size, cfg.in_channels, size, size) if size is not None else (batch_size, cfg.in_channels, *cfg.sample_size)
         gdev = generator.device if generator is not None else self.device
         image = torch.randn(shape, generator=generator, device=gdev, dtype=torch.float32).to(self.device)
         self.scheduler.set_timesteps(num_inference_steps)
-        from .engine import frozen_weights
-        with frozen_weights(self.unet):           # weights are packed once for the whole loop (whatever they are NOW: EMA copy_to etc.)
-            for t in self.scheduler.timesteps.tolist():
-                eps = self.unet(image, t).sample
-                image = self.scheduler.step(eps, t, image, eta=eta, generator=generator).prev_sample
+        timesteps = self.scheduler.timesteps.tolist()
+        if not image.is_cuda:
+            raise RuntimeError("diff_pruning_b200: DDIMPipeline samples on a CUDA device (no CPU fallback); call pipeline.to('cuda')")
+        from .engine import frozen_weights, get_plan
+        was_training = self.unet.training
+        self.unet.eval()
+        try:
+            with frozen_weights(self.unet):       # weights are packed once for the loop (whatever they are NOW: EMA copy_to etc.)
+                if self.use_graph:
+                    plan = get_plan(self.unet, shape[0], shape[2], shape[3], image.device, need_grad=False)
+                    plan.ensure_packed(force=True)
+                    x_static, eps = image.clone(), torch.empty_like(image)
+
+                    def body():
+                        L.check(L.load().dp_nchw_to_nhwc(x_static.data_ptr(), plan.x_in.ptr, plan.x_in.ld, plan.B, plan.x_in.C, plan.H, plan.W,
+                                                         _stream()), "nchw->nhwc")
+                        plan.run_forward()
+                        L.check(L.load().dp_nhwc_to_nchw(plan.y_out.ptr, plan.y_out.ld, eps.data_ptr(), plan.B, plan.y_out.C, plan.H, plan.W, 0,
+                                                         _stream()), "nhwc->nchw")
+                    torch.cuda.synchronize(image.device)
+                    side = torch.cuda.Stream(device=image.device)
+                    side.wait_stream(torch.cuda.current_stream(image.device))
+                    with torch.cuda.stream(side):     # warm-up outside capture (lazy module loading)
+                        body()
+                    torch.cuda.current_stream(image.device).wait_stream(side)
+                    torch.cuda.synchronize(image.device)
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        body()
+                    for t in timesteps:
+                        plan.t_dev.fill_(t)
+                        graph.replay()
+                        x_static.copy_(self.scheduler.step(eps, t, x_static, eta=eta, generator=generator).prev_sample)
+                    image = x_static
+                else:
+                    for t in timesteps:
+                        eps = self.unet(image, t).sample
+                        image = self.scheduler.step(eps, t, image, eta=eta, generator=generator).prev_sample
+        finally:
+            self.unet.train(was_training)
         image = (image / 2 + 0.5).clamp(0, 1).cpu().permute(0, 2, 3, 1).numpy()
         if output_type == "pil":
             from PIL import Image  # optional dependency, like the reference

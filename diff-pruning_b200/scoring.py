@@ -21,7 +21,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib as L
-from .engine import Plan, _dropout_seed, _stream, get_plan, invalidate_packs
+from .engine import Plan, _dropout_seed, _stream, arena_offsets, get_plan, invalidate_packs
 from .models import UNet2DModel, ddpm_alphas_cumprod
 
 
@@ -314,16 +314,14 @@ class FinetuneStepper:
         self.lr, self.betas, self.eps = lr, betas, eps
         self.ema_decay, self.max_grad_norm = ema_decay, max_grad_norm
         self.params = list(model.parameters())
-        total = sum(p.numel() for p in self.params)
+        self._offs, total = arena_offsets(self.params)     # the same 256-byte-aligned layout as the plan's gradient arena
         self.n = total
-        self.param_arena = torch.empty(total, device=self.dev, dtype=torch.float32)
-        o = 0
+        self.param_arena = torch.zeros(total, device=self.dev, dtype=torch.float32)
         with torch.no_grad():
-            for p in self.params:
+            for p, o in zip(self.params, self._offs):
                 v = self.param_arena[o:o + p.numel()].view_as(p)
                 v.copy_(p.data)
                 p.data = v
-                o += p.numel()
         self.m = torch.zeros(total, device=self.dev, dtype=torch.float32)
         self.v = torch.zeros(total, device=self.dev, dtype=torch.float32)
         self.ema = self.param_arena.clone() if use_ema else None
@@ -342,10 +340,9 @@ class FinetuneStepper:
             self.world = dist.get_world_size()
 
     def ema_state(self) -> Dict[str, torch.Tensor]:
-        out, o = {}, 0
-        for (name, p) in self.model.named_parameters():
+        out = {}
+        for (name, p), o in zip(self.model.named_parameters(), self._offs):
             out[name] = self.ema[o:o + p.numel()].view_as(p)
-            o += p.numel()
         return out
 
     def _setup(self, B, C_, H, W):

@@ -143,3 +143,59 @@ def test_threshold_stop_sharded_over_ranks_equals_sequential():
             assert p.exitcode == 0
         for ok, e_arena, e_score in out:
             assert ok and e_arena < 1e-5 and e_score == 0.0, (world, out)
+
+
+# ---- accelerate shim (compat/accelerate): DDP semantics over torch.distributed — sharded batches, averaged gradients, barriers
+def _acc_worker(rank, world, port, q):
+    sys.path[:0] = [os.path.join(ROOT, "diff-pruning_b200", "compat"), ROOT]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.set_num_threads(1)
+    from accelerate import Accelerator
+    acc = Accelerator(gradient_accumulation_steps=1, mixed_precision="no")
+    assert acc.num_processes == world and acc.process_index == rank and acc.is_main_process == (rank == 0)
+    torch.manual_seed(0)
+    model = torch.nn.Linear(4, 3)
+    data = torch.arange(8 * 4, dtype=torch.float32).view(8, 4) / 10.0
+    loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(data), batch_size=2, shuffle=False)
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    model, opt, loader = acc.prepare(model, opt, loader)
+    assert len(loader) == 2                        # 4 batches over 2 processes
+    seen = []
+    for (xb,) in loader:
+        seen.append(xb.clone())
+        with acc.accumulate(model):
+            opt.zero_grad()
+            loss = model(xb).square().sum()
+            acc.backward(loss)
+            assert acc.sync_gradients
+            acc.clip_grad_norm_(model.parameters(), 1e9)
+        break
+    acc.wait_for_everyone()
+    q.put((rank, seen[0].tolist(), model.weight.grad.tolist()))   # plain lists: tensors would travel as shared-memory handles
+    acc.wait_for_everyone()
+    torch.distributed.destroy_process_group()
+
+
+def test_accelerate_shim_shards_batches_and_averages_gradients():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_acc_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=120) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    (r0, x0, g0), (r1, x1, g1) = [(r, torch.tensor(x), torch.tensor(g)) for r, x, g in got]
+    data = torch.arange(8 * 4, dtype=torch.float32).view(8, 4) / 10.0
+    assert torch.equal(x0, data[0:2]) and torch.equal(x1, data[2:4])       # batch k -> process k mod world
+    assert torch.equal(g0, g1)                                             # identical after the all-reduce
+    torch.manual_seed(0)
+    ref = torch.nn.Linear(4, 3)
+    gs = []
+    for xb in (x0, x1):
+        ref.zero_grad()
+        ref(xb).square().sum().backward()
+        gs.append(ref.weight.grad.clone())
+    assert torch.allclose(g0, (gs[0] + gs[1]) / 2, rtol=1e-6, atol=1e-7)   # the MEAN over processes (DDP)
