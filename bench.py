@@ -271,7 +271,11 @@ def timed_conv_launches(plan, prologue=None, midlogue=None):
     pairs = []
 
     def run_list(steps):
-        for f in steps:
+        for i, f in enumerate(steps):
+            if i % 64 == 0:
+                # keep the GPU busy with a spin kernel (~3 ms) while the host enqueues the next launches: a CUDA-event pair around a
+                # short kernel otherwise measures the host's launch latency (ctypes call + tensor-map encodes, ~20 us), not the kernel
+                torch.cuda._sleep(6_000_000)
             if getattr(f, "what", "").startswith("conv"):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(s); f(s_int); e1.record(s)

@@ -102,9 +102,11 @@ def test_conv_bf16_fprop_dgrad_wgrad(lib, N, Cin, H, W, K, R, stride, pad):
     a.w_bf16 = kc.data_ptr()
     bd, rd, resd = b.cuda(), rowadd.cuda().contiguous(), res.permute(0, 2, 3, 1).contiguous().cuda()
     a.bias, a.rowadd, a.ld_rowadd, a.residual, a.ld_res = bd.data_ptr(), rd.data_ptr(), K, resd.data_ptr(), K
-    a.lddy = (K + 7) // 8 * 8
+    e = L.ConvBf16Args()                  # geometry-only copy for the eligibility query (dgrad writes [.., C]: its pitch must cover C)
+    C.memmove(C.byref(e), C.byref(a), C.sizeof(a))
+    e.lddy, e.ld_out = (K + 7) // 8 * 8, max(ldy, Cin)
     for op in (0, 1, 2):
-        assert lib.dp_conv_bf16_eligible(C.byref(a), op) == 0, op
+        assert lib.dp_conv_bf16_eligible(C.byref(e), op) == 0, op
     assert lib.dp_conv2d_fprop_bf16(C.byref(a), S()) == 0
     torch.cuda.synchronize()
     y_full = (y_ref.detach() + rowadd[:, :, None, None] + res).float()

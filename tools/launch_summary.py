@@ -23,6 +23,12 @@ for row in csv.DictReader(lines):
     m = re.search(r"wgrad_tc_kernel", row["Kernel Name"])
     if m:
         name = "wgrad_tc_kernel (tcgen05 3xTF32 wgrad)"
+    for kn, label in (("conv_tc_ps_kernel", "conv_tc_ps_kernel (tcgen05 3xTF32 fprop/dgrad, persistent)"),
+                      ("conv_tc_ts_kernel", "conv_tc_ts_kernel<64> (tcgen05 3xTF32 fprop/dgrad, <= 64 channels)"),
+                      ("conv_bf16_kernel", "conv_bf16_kernel (tcgen05 kind::f16 fprop/dgrad, persistent)"),
+                      ("wgrad_bf16_kernel", "wgrad_bf16_kernel (tcgen05 kind::f16 wgrad)")):
+        if kn in row["Kernel Name"]:
+            name = label
     agg[name][0] += 1; agg[name][1] += v; tot += v
 print(f"total {tot/1e3:.2f} ms over {sum(n for n, _ in agg.values())} launches\n")
 print("| kernel | launches | time (ms) | share |\n|---|---:|---:|---:|")
