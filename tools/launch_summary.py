@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Aggregate an `ncu --metrics gpu__time_duration.sum --csv` launch list by kernel (shares, not absolutes)."""
-import collections, csv, re, sys
+import collections, csv, re, signal, sys
+signal.signal(signal.SIGPIPE, signal.SIG_DFL)
 path = sys.argv[1]
 lines = [l for l in open(path) if not l.startswith("==")]
 agg = collections.defaultdict(lambda: [0, 0.0]); tot = 0.0
