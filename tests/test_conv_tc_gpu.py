@@ -48,6 +48,12 @@ CASES = [
     (2, 192, 16, 16, 179, 1, 0, 1),     # pruned attention to_q: 192 -> 179 (odd N, output view with a 180-float pitch)
     (2, 179, 16, 16, 192, 1, 1, 0),     # pruned attention to_out: 179 -> 192 (odd GEMM-K: padded weight rows, 180-float pitch)
     (64, 358, 1, 1, 96, 1, 2, 0),       # pruned time_emb_proj: 358 -> 96
+    # >= 74 pairs of pixel tiles: the cta_group::2 pair kernel (conv_tc_pair_kernel)
+    (32, 128, 32, 32, 128, 3, 0, 0),    # 256 tiles -> 128 supertiles, full N tile (64 weight rows per CTA)
+    (151, 64, 8, 16, 128, 3, 0, 0),     # ODD tile count (151): the last pair's second tile lies past the batch (TMA zero fill, no store)
+    (40, 256, 16, 16, 256, 3, 0, 0),    # two N tiles x 80 pixel-tile pairs
+    (10, 96, 64, 64, 96, 3, 0, 0),      # pruned width 96: N = 96 instruction, 48 weight rows from each CTA
+    (40, 192, 32, 32, 179, 1, 1, 1),    # odd N (179): second N tile of 51 -> N = 64 instruction, masked store; strided views
 ]
 
 
@@ -150,7 +156,7 @@ def test_single_pass_tf32_would_not_be_enough(lib):
     assert rel_err(one, exact) > 1e-4 and rel_err(three, exact) < 1e-6
 
 
-@pytest.mark.parametrize("N,Cin,H,K", [(2, 64, 16, 64), (4, 128, 8, 96), (1, 32, 32, 160)])
+@pytest.mark.parametrize("N,Cin,H,K", [(2, 64, 16, 64), (4, 128, 8, 96), (1, 32, 32, 160), (80, 128, 32, 128)])   # the last: pair kernel
 def test_stride2_dgrad_parity_classes(lib, N, Cin, H, K):
     """Downsample2D backward (stride 2, F.pad(0,1,0,1) folded, resnet.py:213-218) as 4 tensor-core parity-class GEMMs."""
     from diff_pruning_b200 import _lib as L
@@ -183,7 +189,7 @@ def test_stride2_dgrad_parity_classes(lib, N, Cin, H, K):
     assert rel_err(nchw(gx), 2 * x.grad) < 1.5e-5
 
 
-@pytest.mark.parametrize("N,Cin,H,K,pad", [(2, 64, 16, 128, 0), (4, 128, 8, 96, 0), (1, 32, 32, 160, 1), (8, 256, 8, 256, 0)])
+@pytest.mark.parametrize("N,Cin,H,K,pad", [(2, 64, 16, 128, 0), (4, 128, 8, 96, 0), (1, 32, 32, 160, 1), (8, 256, 8, 256, 0), (80, 128, 32, 128, 0)])
 def test_stride2_fprop_wgrad_tc(lib, N, Cin, H, K, pad):
     """Downsample2D forward + weight gradient (stride 2; pad 0 with the (0,1,0,1) border folded into TMA zero fill, or pad 1)
     on the tensor-core kernels: the activation boxes are fetched with TMA element strides (2, 2)."""
