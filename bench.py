@@ -39,7 +39,35 @@ CONFIGS = {
     "c3": dict(model="LSUN256_DDPM_CONFIG", hw=256, batch=4, conv_flop=1.4806e12, ratio=0.05,
                name="C3 LSUN-256 DDPM UNet2DModel (113.7M params, google/ddpm-ema-bedroom-256 architecture, seed-0 init)",
                cpu_sample=(1, 128)),                 # a full B=4 256x256 CPU pass takes minutes: bounded sample = 1 image at 128x128 (1/16 of the conv work)
+    # BASELINE configs[4]: the class-conditional ImageNet latent-diffusion UNet (ldm_exp/prune_ldm.py: 6 latents of 3x64x64 per step, one
+    # context token per latent).  conv_flop here = GEMM-class work of the conv + linear launches, 6 x 99.8 G MACs (SURVEY.md §2.5 / §8d;
+    # the 4.5 G MACs of the attention cores are not in the timed conv-tagged launches)
+    "c5": dict(model="ldm:CIN256_V2_CONFIG", hw=64, batch=6, conv_flop=598.8e9, ratio=0.3,
+               name="C5 LDM ImageNet-256 UNetModel cin256-v2 (400.9M params, seed-0 init, zero-initialised convolutions re-drawn)",
+               cpu_sample=(1, 64)),
 }
+
+
+def make_model(cfg_key):
+    """(model, scorer kwargs builder): the DDPM UNet2DModel configs, or the LDM UNetModel with its sqrt-linear schedule and a context."""
+    import diff_pruning_b200 as dp
+    name = CONFIGS[cfg_key]["model"]
+    torch.manual_seed(0)
+    if name.startswith("ldm:"):
+        from diff_pruning_b200 import ldm
+        cfg = getattr(ldm, name[4:])
+        m = ldm.UNetModel(**cfg)
+        g = torch.Generator().manual_seed(5)
+        for p in m.parameters():          # a freshly constructed LDM UNet outputs exactly 0 (zero_module convolutions): re-draw them
+            if p.dim() > 1 and float(p.detach().abs().sum()) == 0:
+                p.data.copy_(torch.randn(p.shape, generator=g) * 0.02)
+
+        def extra(B, dev):
+            ctx = torch.randn(B, 1, cfg["context_dim"], generator=torch.Generator().manual_seed(9)).to(dev)
+            return {"alphas_cumprod": ldm.ldm_alphas_cumprod(), "context": ctx}
+        return m, cfg, extra
+    cfg = getattr(dp, name)
+    return dp.UNet2DModel(**cfg), cfg, (lambda B, dev: {})
 
 
 def peaks():
@@ -102,14 +130,22 @@ def synth_batch(B, hw=32, seed_off=0):
 # on the GPU (cuDNN, TF32 on/off) — SURVEY.md §8(d): "time torch-eager on the same B200 as the real bar to beat"
 # ------------------------------------------------------------------------------------------------------------------------
 def _oracle_setup(cfg_key, sample_B, sample_hw, device="cpu"):
-    import diff_pruning_b200 as dp
-    from oracle import unet_oracle as orc
-    mcfg = getattr(dp, CONFIGS[cfg_key]["model"])
-    torch.manual_seed(0)
-    sd = {k: v.detach().clone().to(device).requires_grad_(True) for k, v in dp.UNet2DModel(**mcfg).state_dict().items()}
-    ac = orc.alphas_cumprod().to(device)
+    model, mcfg, extra = make_model(cfg_key)
+    sd = {k: v.detach().clone().to(device).requires_grad_(True) for k, v in model.state_dict().items()}
+    del model
     clean, noise = synth_batch(sample_B, sample_hw)
     clean, noise = clean.to(device), noise.to(device)
+    if CONFIGS[cfg_key]["model"].startswith("ldm:"):
+        from oracle import ldm_oracle as lorc
+        ac = lorc.alphas_cumprod().to(device)
+        ctx = extra(sample_B, device)["context"]
+
+        def one_pass(k):
+            t = torch.full((sample_B,), int(k), dtype=torch.long, device=device)
+            return lorc.taylor_pass(sd, mcfg, ac, clean, noise, t, ctx)
+        return one_pass
+    from oracle import unet_oracle as orc
+    ac = orc.alphas_cumprod().to(device)
 
     def one_pass(k):
         t = torch.full((sample_B,), int(k), dtype=torch.long, device=device)
@@ -399,11 +435,11 @@ def secondary_scoring_leg(cfg_key, args, rank, world, dev, barrier):
     lib = L.load()
     c = CONFIGS[cfg_key]
     B, hw = c["batch"], c["hw"]
-    torch.manual_seed(0)
-    model = dp.UNet2DModel(**getattr(dp, c["model"])).eval().to(dev)
+    model, _, extra = make_model(cfg_key)
+    model = model.eval().to(dev)
     clean, noise = synth_batch(B, hw, seed_off=100 * rank)
     model.zero_grad()
-    sc = TaylorScorer(model, clean.to(dev), noise.to(dev), use_graph=not args.no_graph)
+    sc = TaylorScorer(model, clean.to(dev), noise.to(dev), use_graph=not args.no_graph, **extra(B, dev))
     K, Wm = max(3, min(args.steps, 8)), 3
     ts = [(rank + k * world) % 1000 for k in range(Wm + K)]
     for k in range(Wm):
@@ -464,12 +500,12 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(dev)
     c = CONFIGS[args.config]
     B, hw = args.batch, c["hw"]
-    torch.manual_seed(0)
-    model = dp.UNet2DModel(**getattr(dp, c["model"])).eval().to(dev)
+    model, _, extra = make_model(args.config)
+    model = model.eval().to(dev)
     clean, noise = synth_batch(B, hw, seed_off=100 * rank)
     clean_pin, noise_pin = clean.pin_memory(), noise.pin_memory()
     model.zero_grad()
-    sc = TaylorScorer(model, clean.to(dev), noise.to(dev), use_graph=not (args.no_graph or args.profile_pass))
+    sc = TaylorScorer(model, clean.to(dev), noise.to(dev), use_graph=not (args.no_graph or args.profile_pass), **extra(B, dev))
     if args.profile_pass:   # for ncu: `--profile-from-start off`; exactly one eager pass inside the profiler range
         for k in range(2):
             sc.step(k)
@@ -546,13 +582,14 @@ def run_ours(args, rank, world, local_rank):
     else:
         conv_s, n_conv, conv_by_tag, conv_by_layer = 1.0, 0, {}, {}
     plan_B, plan_macs, plan_bytes = sc.plan.B, sc.plan.conv_macs, sc.plan.bytes_allocated()
+    plan_lin_macs = getattr(sc.plan, "lin_macs", 0)
     del sc
     if hasattr(model, "_dpb200_plans"):
         model._dpb200_plans.clear()
     del model
     torch.cuda.empty_cache()
     finetune_leg = finetune_bf16 = None
-    if not args.no_finetune:
+    if not args.no_finetune and not c["model"].startswith("ldm:"):      # the reference's LDM path is prune_ldm.py only (no finetune script in scope)
         finetune_leg = finetune_bench(args, rank, world, dev, barrier)
         from diff_pruning_b200 import engine as _eng
         if getattr(_eng, "BF16_TIER", False):
@@ -577,7 +614,7 @@ def run_ours(args, rank, world, local_rank):
     roofline = {"bound": "tensor", "achieved": achieved, "peak": tf_sus, "unit": "TFLOP/s", "frac": achieved / tf_sus,
                 "traffic": traffic, "breakdown_ms": conv_by_tag, "top_layers_ms": conv_by_layer,
                 "tf32_peak_measured": tf32, "tier_ceiling_tflops": tier_ceiling, "frac_of_tier_ceiling": achieved / tier_ceiling,
-                "plan_conv_gflop_per_image": 6.0 * plan_macs / plan_B / 1e9,
+                "plan_conv_gflop_per_image": 6.0 * plan_macs / plan_B / 1e9, "plan_linear_gflop_per_image": 6.0 * plan_lin_macs / plan_B / 1e9,
                 "kernel": "conv implicit GEMM (fprop+dgrad+wgrad launches of one pass: %d)" % n_conv,
                 "note": (f"algorithmic conv FLOPs/pass = {B} x {c['conv_flop'] / 1e9:.2f} GFLOP (SURVEY.md §8d) / summed conv-launch device time "
                          f"{conv_s * 1e3:.2f} ms of a {ms / args.steps:.2f} ms step; peak = bf16_tflops_sustained ({which}); "

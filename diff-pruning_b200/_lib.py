@@ -94,6 +94,8 @@ _SIGS = {
     "dp_groupnorm_bwd": (C.c_int, [C.POINTER(GnArgs), vp]),
     "dp_silu_fwd": (C.c_int, [vp, vp, i64, vp]),
     "dp_silu_bwd": (C.c_int, [vp, vp, vp, i64, i32, vp]),
+    "dp_geglu_fwd": (C.c_int, [vp, i64, vp, i64, i64, i32, vp]),
+    "dp_geglu_bwd": (C.c_int, [vp, i64, vp, i64, vp, i64, i64, i32, vp]),
     "dp_timestep_embedding": (C.c_int, [vp, vp, vp, i32, i32, i32, vp]),
     "dp_add_noise": (C.c_int, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i64, vp]),
     "dp_nchw_to_nhwc": (C.c_int, [vp, vp, i64, i32, i32, i32, i32, vp]),

@@ -25,6 +25,29 @@ __global__ void silu_bwd_kernel(const float* __restrict__ x, const float* __rest
     dx[i] = acc ? dx[i] + g : g;
   }
 }
+// GEGLU (ldm/modules/attention.py:37-44): u = [a | gate] per row, out = a * gelu(gate), gelu = exact erf form (F.gelu default)
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  return 0.5f * (1.f + erff(x * 0.70710678118654752440f)) + x * 0.39894228040143267794f * expf(-0.5f * x * x);
+}
+__global__ void geglu_fwd_kernel(const float* __restrict__ u, long long ldu, float* __restrict__ out, long long ldo, long long rows, int I) {
+  const long long total = rows * I;
+  for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+    const long long r = i / I; const int c = (int)(i - r * I);
+    const float a = u[r * ldu + c], g = u[r * ldu + I + c];
+    out[r * ldo + c] = a * gelu_erf(g);
+  }
+}
+__global__ void geglu_bwd_kernel(const float* __restrict__ u, long long ldu, const float* __restrict__ dout, long long lddo,
+                                 float* __restrict__ du, long long lddu, long long rows, int I) {
+  const long long total = rows * I;
+  for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+    const long long r = i / I; const int c = (int)(i - r * I);
+    const float a = u[r * ldu + c], g = u[r * ldu + I + c], d = dout[r * lddo + c];
+    du[r * lddu + c] = d * gelu_erf(g);
+    du[r * lddu + I + c] = d * a * gelu_erf_grad(g);
+  }
+}
 __global__ void temb_kernel(const int64_t* __restrict__ t, const float* __restrict__ freqs, float* __restrict__ out,
                             int B, int half, int flip) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -192,6 +215,18 @@ extern "C" int dp_silu_fwd(const float* x, float* y, int64_t n, dp_stream_t st) 
 extern "C" int dp_silu_bwd(const float* x, const float* dy, float* dx, int64_t n, int32_t acc, dp_stream_t st) {
   DP_REQUIRE(x && dy && dx, DP_ERR_NULL); DP_REQUIRE(n > 0, DP_ERR_SHAPE);
   silu_bwd_kernel<<<nblocks(n, NT), NT, 0, (cudaStream_t)st>>>(x, dy, dx, n, acc);
+  return dp_check_launch();
+}
+extern "C" int dp_geglu_fwd(const float* u, int64_t ldu, float* out, int64_t ldo, int64_t rows, int32_t inner, dp_stream_t st) {
+  DP_REQUIRE(u && out, DP_ERR_NULL); DP_REQUIRE(rows > 0 && inner > 0 && ldu >= 2 * (int64_t)inner && ldo >= inner, DP_ERR_SHAPE);
+  geglu_fwd_kernel<<<nblocks(rows * inner, NT), NT, 0, (cudaStream_t)st>>>(u, ldu, out, ldo, rows, inner);
+  return dp_check_launch();
+}
+extern "C" int dp_geglu_bwd(const float* u, int64_t ldu, const float* dout, int64_t lddo, float* du, int64_t lddu, int64_t rows, int32_t inner,
+                            dp_stream_t st) {
+  DP_REQUIRE(u && dout && du, DP_ERR_NULL);
+  DP_REQUIRE(rows > 0 && inner > 0 && ldu >= 2 * (int64_t)inner && lddu >= 2 * (int64_t)inner && lddo >= inner, DP_ERR_SHAPE);
+  geglu_bwd_kernel<<<nblocks(rows * inner, NT), NT, 0, (cudaStream_t)st>>>(u, ldu, dout, lddo, du, lddu, rows, inner);
   return dp_check_launch();
 }
 extern "C" int dp_timestep_embedding(const int64_t* t, const float* freqs, float* out, int32_t B, int32_t half, int32_t flip, dp_stream_t st) {

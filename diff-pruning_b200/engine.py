@@ -149,6 +149,7 @@ class Plan:
         self.dropout_seed_dev = torch.zeros(1, device=self.dev, dtype=torch.int64)
         self._n_dropout = 0
         self.fused_scores = fused_scores and need_grad
+        self.lin_macs = 0
         self.conv_macs = 0             # MACs of one forward over the 4-D-weight convolutions (set while building)
         self.generation = 0            # forward counter of the autograd boundary (see _UNetFunction)
         self._calls = 0                # module-forward counter: advances the dropout stream on the autograd / compat path
@@ -395,6 +396,8 @@ class Plan:
         info = f"{Cin}->{K} {R}x{S}" + (f" s{stride}" if stride != 1 else "") + f" @{out.H}x{out.W}"
         if w.dim() == 4:
             self.conv_macs += out.rows * K * Cin * R * S      # 4-D-weight convolutions only: the roofline denominator
+        else:
+            self.lin_macs += out.rows * K * Cin               # nn.Linear layers (the LDM transformer blocks are linear-heavy)
         self._rec(self.fwd, lib.dp_conv2d_fprop, a, "conv fprop", info)
         if not self.need_grad:
             return
@@ -483,6 +486,8 @@ class Plan:
         info = f"{Cin}->{K} {R}x{S}" + (f" s{stride}" if stride != 1 else "") + f" @{out.H}x{out.W} bf16"
         if w.dim() == 4:
             self.conv_macs += out.rows * K * Cin * R * S
+        else:
+            self.lin_macs += out.rows * K * Cin
         self._rec(self.fwd, lib.dp_conv2d_fprop_bf16, a, "conv fprop", info)
         if not self.need_grad:
             return
@@ -534,11 +539,12 @@ class Plan:
                 it.writes.append((tgt, lambda init, da=da: setattr(da, "flags", 1 if init else 0)))
             self._rec(steps, lib.dp_conv2d_dgrad_bf16, da, "conv dgrad", info)
 
-    def gn(self, x: View, norm: nn.GroupNorm, out: View, silu: bool, dropout_p: float = 0.0, bf16_only: bool = False):
+    def gn(self, x: View, norm: nn.Module, out: View, silu: bool, dropout_p: float = 0.0, bf16_only: bool = False, groups: Optional[int] = None):
         """fwd: out = dropout?(silu?(GN(x))).  Returns the fwd args (the backward reuses stats / dropout seed)."""
         lib = self.lib
         a = L.GnArgs()
-        a.N, a.HW, a.C, a.G = x.N, x.H * x.W, x.C, norm.num_groups
+        G = groups if groups is not None else norm.num_groups
+        a.N, a.HW, a.C, a.G = x.N, x.H * x.W, x.C, G
         a.eps, a.silu = norm.eps, 1 if silu else 0
         a.x, a.ldx, a.y, a.ldy = x.ptr, x.ld, out.ptr, out.ld
         if bf16_only:   # every consumer of `out` is a bf16 convolution: write the operand directly, skip the fp32 tensor
@@ -546,9 +552,9 @@ class Plan:
             self._bf_cache[(out.t.data_ptr(), out.off, out.C)] = (yb, ldyb)
             a.y, a.y_bf16, a.ldyb = None, yb.data_ptr(), ldyb
         a.gamma, a.beta = norm.weight.data_ptr(), norm.bias.data_ptr()
-        stats = torch.empty(2 * x.N * norm.num_groups, device=self.dev, dtype=torch.float32)
+        stats = torch.empty(2 * x.N * G, device=self.dev, dtype=torch.float32)
         self._keep.append(stats)
-        a.mean, a.rstd = stats.data_ptr(), stats.data_ptr() + 4 * x.N * norm.num_groups
+        a.mean, a.rstd = stats.data_ptr(), stats.data_ptr() + 4 * x.N * G
         if dropout_p > 0:
             self._n_dropout += 1
             a.dropout_p = dropout_p
@@ -608,17 +614,13 @@ class Plan:
 
     def attention(self, m: Attention, x: View, out: View):
         """Attention + legacy AttnProcessor — attention_processor.py:415-470 (heads = 1, explicit stale scale)."""
-        lib = self.lib
         if m.heads != 1:
             raise NotImplementedError("multi-head attention blocks are outside the DDPM UNet2DModel configs (heads=1)")
         assert m.rescale_output_factor == 1.0
         N, H, W = x.N, x.H, x.W
-        T = H * W
         inner = m.to_q.out_features
         xn = self.new(N, H, W, x.C)
         q, k, v, o = (self.new(N, H, W, inner) for _ in range(4))
-        P = torch.empty((N, T, T), device=self.dev, dtype=torch.float32)
-        self._keep.append(P)
         g = self.gn(x, m.group_norm, xn, silu=False,
                     bf16_only=all(self.conv_bf16_ok(xn, q, l.weight, 1, 0) for l in (m.to_q, m.to_k, m.to_v)))
         if self.need_grad:
@@ -627,6 +629,17 @@ class Plan:
         self.conv(xn, m.to_q.weight, m.to_q.bias, q, pad=0)
         self.conv(xn, m.to_k.weight, m.to_k.bias, k, pad=0)
         self.conv(xn, m.to_v.weight, m.to_v.bias, v, pad=0)
+        self._attn_core(q, k, v, o, float(m.scale))
+        self.conv(o, m.to_out[0].weight, m.to_out[0].bias, out, pad=0, residual=x if m.residual_connection else None)
+
+    def _attn_core(self, q: View, k: View, v: View, o: View, sc: float):
+        """o = softmax(sc * q k^T) v per image over the H*W tokens (single head) and its backward: tcgen05 NT GEMMs when the token
+        count is a multiple of 128, the exact SIMT batched GEMM otherwise."""
+        lib = self.lib
+        N, H, W, inner = q.N, q.H, q.W, q.C
+        T = H * W
+        P = torch.empty((N, T, T), device=self.dev, dtype=torch.float32)
+        self._keep.append(P)
 
         def gemm(M, Nn, Kd, A, a_rs, a_cs, a_bs, Bp, b_rs, b_cs, b_bs, Cp, ldc, c_bs, alpha):
             ga = L.GemmArgs()
@@ -635,12 +648,9 @@ class Plan:
             ga.B, ga.b_rs, ga.b_cs, ga.b_bs = Bp, b_rs, b_cs, b_bs
             ga.C, ga.ldc, ga.c_bs, ga.alpha, ga.accumulate = Cp, ldc, c_bs, alpha, 0
             return ga
-        Pp, sc = P.data_ptr(), float(m.scale)
-        import os as _os
-        use_tc = self.tc and T % 128 == 0 and _os.environ.get("DPB200_ATTN_TC", "1") != "0"
-        if use_tc:
-            self._attention_core_tc(N, H, W, T, inner, q, k, v, o, P, sc)
-            return self.conv(o, m.to_out[0].weight, m.to_out[0].bias, out, pad=0, residual=x if m.residual_connection else None)
+        Pp = P.data_ptr()
+        if self.tc and T % 128 == 0:
+            return self._attention_core_tc(N, H, W, T, inner, q, k, v, o, P, sc)
         # S = scale * q k^T ; P = softmax(S) (in place) ; o = P v
         self._rec(self.fwd, lib.dp_gemm_batched, gemm(T, T, inner, q.ptr, q.ld, 1, T * q.ld, k.ptr, 1, k.ld, T * k.ld,
                                                       Pp, T, T * T, sc), "attn qk")
@@ -664,7 +674,6 @@ class Plan:
                                                     dq.ptr, dq.ld, T * dq.ld, sc), "attn dQ")
             self._rec(st, lib.dp_gemm_batched, gemm(T, inner, T, dPp, 1, T, T * T, q.ptr, q.ld, 1, T * q.ld,
                                                     dk.ptr, dk.ld, T * dk.ld, sc), "attn dK")
-        self.conv(o, m.to_out[0].weight, m.to_out[0].bias, out, pad=0, residual=x if m.residual_connection else None)
 
     def _attention_core_tc(self, N, H, W, T, inner, q, k, v, o, P, sc):
         """softmax(scale q k^T) v and its backward on the tensor-core NT GEMM (dp_gemm_nt_tc): every product is written as
@@ -719,6 +728,8 @@ class Plan:
 
     # ------------------------------------------------------------------ whole network
     def _build(self):
+        if hasattr(self.model, "input_blocks"):      # latent-diffusion UNetModel (ldm.py)
+            return self._build_ldm()
         m, lib = self.model, self.lib
         B, H, W = self.B, self.H, self.W
         cfg = m.config
@@ -868,6 +879,9 @@ class Plan:
         self.gradof(self.y_out).t.zero_()
         self.conv(a, m.conv_out.weight, m.conv_out.bias, self.y_out, dx_scratch="da")
 
+        self._finalize_build()
+
+    def _finalize_build(self):
         # ---- allocate shared scratch, bind late pointers, resolve (=|+=) of every gradient write in EXECUTION order
         for name, n in self._scratch_need.items():
             self._scratch[name] = torch.empty(max(n, 1), device=self.dev, dtype=torch.float32)
@@ -883,6 +897,221 @@ class Plan:
                     self.g_mark(view)
         self._packed_version = None
         self.bwd_steps: List[Step] = [f for it in reversed(self.bwd) for f in it.steps]
+
+    # ------------------------------------------------------------------ latent-diffusion UNetModel (ldm.py; BASELINE configs[4])
+    def _tokens(self, v: View) -> View:
+        """The same storage seen as N*H*W one-pixel images (LayerNorm = GroupNorm with one group over the channels of a token)."""
+        return View(v.t.view(v.rows, 1, 1, v.ld), v.off, v.C)
+
+    def layernorm(self, x: View, ln: nn.LayerNorm, out: View, add2: Optional[View] = None):
+        """nn.LayerNorm over the channel dimension of every token (attention.py:204-206), forward + backward (dx += add2: the residual
+        branch's gradient)."""
+        xt, ot = self._tokens(x), self._tokens(out)
+        g = self.gn(xt, ln, ot, silu=False, groups=1)
+        if self.need_grad:
+            self.gn_bwd(g, xt, ln, lambda o=out: self.gradof(o).ptr, self.gradof(out).ld, add2=add2)
+
+    def transformer_block(self, blk, x: View) -> View:
+        """BasicTransformerBlock (attention.py:196-212) for a one-token context:
+             x2 = attn1(LN1(x)) + x + attn2(LN2(.), context)      x3 = ff(LN3(x2)) + x2
+        Cross-attention over ONE context token is softmax over a single logit = 1, so attn2(., c) = to_out(to_v(c)) for every query token
+        whatever to_q / to_k / LN2 hold: a per-image row, added in the epilogue of attn1's output projection.  Their gradients are
+        exactly zero in the reference as well (softmax backward of a single element), so nothing is launched for them."""
+        lib = self.lib
+        N, H, W, d = x.N, x.H, x.W, x.C
+        a1, a2, ff = blk.attn1, blk.attn2, blk.ff
+        if a1.heads != 1 or a2.heads != 1:
+            raise NotImplementedError("multi-head transformer blocks (cin256-v2 uses num_heads = 1)")
+        if self.ctx_in.H * self.ctx_in.W != 1:
+            raise NotImplementedError("cross-attention over more than one context token")
+        inner = a1.to_q.out_features
+        # cross-attention contribution (per image): octx = to_out(to_v(context))
+        vctx, octx = self.new(self.B, 1, 1, a2.to_v.out_features), self.new(self.B, 1, 1, d)
+        self.conv(self.ctx_in, a2.to_v.weight, None, vctx, pad=0, need_dx=False)
+        self.conv(vctx, a2.to_out[0].weight, a2.to_out[0].bias, octx, pad=0, dy_dense="seg_ctx")
+        # self-attention
+        x2 = self.new(N, H, W, d)
+        h1 = self.new(N, H, W, d)
+        self.layernorm(x, blk.norm1, h1, add2=self.gradof(x2))
+        q, k, v, o = (self.new(N, H, W, inner) for _ in range(4))
+        self.conv(h1, a1.to_q.weight, None, q, pad=0)
+        self.conv(h1, a1.to_k.weight, None, k, pad=0)
+        self.conv(h1, a1.to_v.weight, None, v, pad=0)
+        self._attn_core(q, k, v, o, float(a1.scale))
+        self.conv(o, a1.to_out[0].weight, a1.to_out[0].bias, x2, pad=0, residual=x, rowadd=octx, seg_out="seg_ctx")
+        # GEGLU feed-forward
+        x3 = self.new(N, H, W, d)
+        h3 = self.new(N, H, W, d)
+        self.layernorm(x2, blk.norm3, h3, add2=self.gradof(x3))
+        proj, lin2 = ff.net[0].proj, ff.net[2]
+        I = lin2.in_features
+        u, gg = self.new(N, H, W, 2 * I), self.new(N, H, W, I)
+        self.conv(h3, proj.weight, proj.bias, u, pad=0)
+        rows = u.rows
+        self._rec(self.fwd, lambda s: lib.dp_geglu_fwd(u.ptr, u.ld, gg.ptr, gg.ld, rows, I, s), what="geglu")
+        if self.need_grad:
+            it = self._bitem()
+            it.writes.append((u, lambda init: None))        # du is written (=) exactly once, by this op
+            self._rec(it.steps, lambda s: lib.dp_geglu_bwd(u.ptr, u.ld, self.gradof(gg).ptr, gg.ld, self.gradof(u).ptr, u.ld, rows, I, s),
+                      what="geglu bwd")
+        self.conv(gg, lin2.weight, lin2.bias, x3, pad=0, residual=x2)
+        return x3
+
+    def spatial_transformer(self, m, x: View, out: View):
+        """SpatialTransformer (attention.py:215-257): GroupNorm(32, eps 1e-6) -> 1x1 proj_in -> transformer blocks over the H*W tokens
+        -> 1x1 proj_out ; + x."""
+        h = self.new(x.N, x.H, x.W, m.proj_in.out_channels)
+        xn = self.new(x.N, x.H, x.W, x.C)
+        g = self.gn(x, m.norm, xn, silu=False, bf16_only=self.conv_bf16_ok(xn, h, m.proj_in.weight, 1, 0))
+        if self.need_grad:
+            self.gn_bwd(g, x, m.norm, lambda xn=xn: self.gradof(xn).ptr, x.C, add2=self.gradof(out))
+        self.conv(xn, m.proj_in.weight, m.proj_in.bias, h, pad=0)
+        for blk in m.transformer_blocks:
+            h = self.transformer_block(blk, h)
+        self.conv(h, m.proj_out.weight, m.proj_out.bias, out, pad=0, residual=x)
+
+    def _build_ldm(self):
+        """UNetModel.forward (openaimodel.py:710-742) as a static launch plan; same HBM conventions as the DDPM UNet (NHWC fp32 views,
+        zero-copy skip concatenation, epilogue-fused bias / embedding row / residual)."""
+        from types import SimpleNamespace as NS
+        m, lib = self.model, self.lib
+        B, H, W = self.B, self.H, self.W
+        cfg = m.config
+        self._setup_param_grads()
+        self.t_dev = torch.zeros(B, device=self.dev, dtype=torch.int64)
+
+        def padded(n, h, w, c):
+            t = torch.zeros((n, h, w, (c + 3) // 4 * 4), device=self.dev, dtype=torch.float32)
+            self._keep.append(t)
+            return View(t, 0, c)
+        self.x_in = padded(B, H, W, cfg.in_channels)
+        self.ctx_in = padded(B, 1, 1, cfg.context_dim)
+        mc = cfg.model_channels
+        half = mc // 2
+        self.freqs = sinusoidal_frequencies(mc, 0).to(self.dev)        # exp(-ln(1e4) i / half), util.py:160-162
+        temb0 = self.new(B, 1, 1, 2 * half)
+        te1, te2 = m.time_embed[0], m.time_embed[2]
+        l1, s1 = self.new(B, 1, 1, te1.out_features), self.new(B, 1, 1, te1.out_features)
+        emb = self.new(B, 1, 1, te2.out_features)
+        self.silu_temb = self.new(B, 1, 1, emb.C)
+        # cos | sin order (util.py:164) = the DDPM kernel with the halves flipped
+        self._rec(self.fwd, lambda s: lib.dp_timestep_embedding(self.t_dev.data_ptr(), self.freqs.data_ptr(), temb0.ptr, B, half, 1, s), what="temb")
+        self.conv(temb0, te1.weight, te1.bias, l1, pad=0, need_dx=False)
+        n1, n2 = B * l1.ld, B * emb.ld
+        self._rec(self.fwd, lambda s: lib.dp_silu_fwd(l1.ptr, s1.ptr, n1, s), what="silu")
+        if self.need_grad:
+            self._rec(self._bitem().steps, lambda s: lib.dp_silu_bwd(l1.ptr, self.gradof(s1).ptr, self.gradof(l1).ptr, n1, 0, s), what="silu bwd")
+        self.conv(s1, te2.weight, te2.bias, emb, pad=0)
+        self._rec(self.fwd, lambda s: lib.dp_silu_fwd(emb.ptr, self.silu_temb.ptr, n2, s), what="silu")
+        if self.need_grad:
+            self._rec(self._bitem().steps,
+                      lambda s: lib.dp_silu_bwd(emb.ptr, self.gradof(self.silu_temb).ptr, self.gradof(emb).ptr, n2, 0, s), what="silu bwd")
+
+        def as_resnet(rb):     # ResBlock (openaimodel.py:163-275) in the attribute vocabulary of Plan.resnet()
+            sk = rb.skip_connection
+            return NS(norm1=rb.in_layers[0], conv1=rb.in_layers[2], time_emb_proj=rb.emb_layers[1], norm2=rb.out_layers[0],
+                      dropout=rb.out_layers[2], conv2=rb.out_layers[3], conv_shortcut=sk if isinstance(sk, nn.Conv2d) else None,
+                      output_scale_factor=1.0)
+
+        # ---- skip geometry: the output of every input block is concatenated (as the UPPER channels) in front of one output block
+        shapes, ch, hh, ww = [], None, H, W
+        for blk in m.input_blocks:
+            for layer in blk:
+                if isinstance(layer, nn.Conv2d):
+                    ch = layer.out_channels
+                elif hasattr(layer, "in_layers"):
+                    ch = layer.out_channels
+                elif hasattr(layer, "op"):
+                    ch, hh, ww = layer.op.out_channels, hh // 2, ww // 2
+            shapes.append((hh, ww, ch))
+        consumers = [blk[0] for blk in m.output_blocks]
+        assert len(consumers) == len(shapes)
+        cat_total = [0] * len(shapes)
+        for j, rb in enumerate(consumers):
+            cat_total[len(shapes) - 1 - j] = rb.in_layers[0].num_channels
+        counter = [0]
+
+        def new_skip() -> View:
+            i = counter[0]
+            counter[0] += 1
+            hh_, ww_, c = shapes[i]
+            buf = self.new(B, hh_, ww_, cat_total[i])
+            assert cat_total[i] - c > 0
+            return View(buf.t, cat_total[i] - c, c)
+        h_half = lambda skip: View(skip.t, 0, skip.off)
+        cat_of = lambda skip: View(skip.t, 0, skip.off + skip.C)
+
+        def run_layers(layers, x: View, dest: View) -> View:
+            """A TimestepEmbedSequential: the last layer writes `dest`, the others fresh buffers."""
+            layers = list(layers)
+            for li, layer in enumerate(layers):
+                last = li == len(layers) - 1
+                if isinstance(layer, nn.Conv2d):
+                    y = dest
+                    self.conv(x, layer.weight, layer.bias, y, need_dx=False)
+                elif hasattr(layer, "in_layers"):
+                    y = dest if last else self.new(x.N, x.H, x.W, layer.out_channels)
+                    self.resnet(as_resnet(layer), x, y)
+                elif hasattr(layer, "transformer_blocks"):
+                    y = dest if last else self.new(x.N, x.H, x.W, x.C)
+                    self.spatial_transformer(layer, x, y)
+                elif hasattr(layer, "op"):
+                    y = dest
+                    self.conv(x, layer.op.weight, layer.op.bias, y, stride=2, pad=1)
+                elif hasattr(layer, "conv"):      # Upsample: nearest x2 then 3x3 conv
+                    up = self.new(x.N, 2 * x.H, 2 * x.W, x.C)
+                    xx = x
+                    self._rec(self.fwd, lambda s, xx=xx, up=up: lib.dp_upsample2x_fwd(xx.ptr, xx.ld, up.ptr, up.ld, xx.N, xx.H, xx.W, xx.C, s),
+                              what="upsample")
+                    if self.need_grad:
+                        it = self._bitem()
+                        accf = [0]
+                        it.writes.append((xx, lambda init, accf=accf: accf.__setitem__(0, 1 if init else 0)))
+                        self._rec(it.steps, lambda s, xx=xx, up=up, accf=accf: lib.dp_upsample2x_bwd(
+                            self.gradof(up).ptr, up.ld, self.gradof(xx).ptr, self.gradof(xx).ld, xx.N, xx.H, xx.W, xx.C, accf[0], s),
+                            what="upsample bwd")
+                    y = dest
+                    self.conv(up, layer.conv.weight, layer.conv.bias, y)
+                else:
+                    raise NotImplementedError(type(layer).__name__)
+                x = y
+            return x
+
+        x, skips = self.x_in, []
+        for blk in m.input_blocks:
+            x = run_layers(blk, x, new_skip())
+            skips.append(x)
+        # the middle block's last layer writes straight into the h-half of the first concatenation
+        dest = h_half(skips[-1])
+        assert dest.C == x.C and dest.H == x.H, (dest.C, x.C)
+        x = run_layers(m.middle_block, x, dest)
+        nblk = len(m.output_blocks)
+        for bi, blk in enumerate(m.output_blocks):
+            cat = cat_of(skips.pop())
+            layers = list(blk)
+            out_ch = layers[0].out_channels
+            up = hasattr(layers[-1], "conv") and not hasattr(layers[-1], "in_layers")
+            if skips:
+                dest = h_half(skips[-1])
+                assert dest.C == out_ch and dest.H == cat.H * (2 if up else 1), (bi, dest.C, out_ch, dest.H, cat.H)
+            else:
+                dest = self.new(cat.N, cat.H, cat.W, out_ch)
+            x = run_layers(layers, cat, dest)
+        assert not skips
+        a = self.new(x.N, x.H, x.W, x.C)
+        g = self.gn(x, m.out[0], a, silu=True)
+        if self.need_grad:
+            self.gn_bwd(g, x, m.out[0], lambda: self.sptr("da"), x.C)
+        self.y_out = padded(B, H, W, cfg.out_channels)
+        self.gradof(self.y_out).t.zero_()
+        self.conv(a, m.out[2].weight, m.out[2].bias, self.y_out, dx_scratch="da")
+        self._finalize_build()
+
+    def load_context(self, context: torch.Tensor):
+        """context: (B, 1, context_dim) fp32 -> the plan's conditioning buffer (cross-attention input; no gradient)."""
+        c = context.reshape(self.B, -1).to(device=self.dev, dtype=torch.float32)
+        assert c.shape[1] == self.ctx_in.C, (tuple(context.shape), self.ctx_in.C)
+        self.ctx_in.t.view(self.B, -1)[:, :self.ctx_in.C].copy_(c, non_blocking=True)
 
     # ------------------------------------------------------------------ execution
     def run_pack(self, s: Optional[int] = None):
@@ -985,7 +1214,7 @@ def get_plan(model: UNet2DModel, batch: int, H: int, W: int, device, need_grad: 
     return plan
 
 
-def unet_apply(model: UNet2DModel, sample: torch.Tensor, timesteps: torch.Tensor) -> torch.Tensor:
+def unet_apply(model, sample: torch.Tensor, timesteps: torch.Tensor, context: Optional[torch.Tensor] = None) -> torch.Tensor:
     """UNet2DModel.forward on CUDA (models.py).  unet_2d.py:219-316."""
     if sample.dtype != torch.float32:
         raise TypeError("diff_pruning_b200 engine computes in fp32; got %s" % sample.dtype)
@@ -1005,6 +1234,10 @@ def unet_apply(model: UNet2DModel, sample: torch.Tensor, timesteps: torch.Tensor
     if plan.training and plan._n_dropout:
         plan._calls += 1                # a fresh dropout stream per forward (and per rank), like torch's advancing Philox offset
         plan.dropout_seed_dev.fill_(_dropout_seed(plan._calls))
+    if hasattr(plan, "ctx_in"):
+        if context is None:
+            raise ValueError("the LDM UNetModel is cross-attention conditioned: pass context=(B, 1, context_dim)")
+        plan.load_context(context)
     if need_grad:
         return _UNetFunction.apply(sample, timesteps, plan, *plan.params)
     plan.load_input_nchw(sample, timesteps)

@@ -35,7 +35,7 @@ class TaylorScorer:
 
     def __init__(self, model: UNet2DModel, clean_images: torch.Tensor, noise: torch.Tensor,
                  num_train_timesteps: int = 1000, alphas_cumprod: Optional[torch.Tensor] = None, use_graph: bool = True,
-                 fused_scores: bool = False):
+                 fused_scores: bool = False, context: Optional[torch.Tensor] = None):
         assert clean_images.is_cuda and clean_images.shape == noise.shape and clean_images.dtype == torch.float32
         self.lib = L.load()
         self.model = model
@@ -53,6 +53,10 @@ class TaylorScorer:
         self.plan: Plan = get_plan(model, B, H, W, self.dev, need_grad=True, fused_scores=fused_scores)
         if was_training:
             model.train()
+        if hasattr(self.plan, "ctx_in"):      # latent-diffusion UNetModel: cross-attention conditioning, fixed for the whole loop (prune_ldm.py:106-122)
+            if context is None:
+                raise ValueError("the LDM UNetModel needs context=(B, 1, context_dim)")
+            self.plan.load_context(context)
         ldo = self.plan.y_out.ld                      # y_out is a C-channel view of a zero-padded ld-channel buffer
         self.noise_nhwc = torch.zeros((B, H, W, ldo), device=self.dev, dtype=torch.float32)
         n = B * C_ * H * W

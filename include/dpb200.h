@@ -221,6 +221,12 @@ int dp_groupnorm_bwd(const dp_gn_args* a, dp_stream_t stream);
 int dp_silu_fwd(const float* x, float* y, int64_t n, dp_stream_t stream);
 int dp_silu_bwd(const float* x, const float* dy, float* dx, int64_t n, int32_t accumulate, dp_stream_t stream);
 
+/* GEGLU feed-forward gate of the LDM transformer blocks (ldm_exp/ldm/modules/attention.py:37-44): u = [a | gate] ([rows][2*inner]),
+ * out = a * gelu(gate) (exact erf GELU); backward writes du = [dout * gelu(gate) | dout * a * gelu'(gate)]. */
+int dp_geglu_fwd(const float* u, int64_t ldu, float* out, int64_t ldo, int64_t rows, int32_t inner, dp_stream_t stream);
+int dp_geglu_bwd(const float* u, int64_t ldu, const float* dout, int64_t lddo, float* du, int64_t lddu, int64_t rows, int32_t inner,
+                 dp_stream_t stream);
+
 /* out[b][0:half]=sin(t_b*f_i), out[b][half:]=cos(...) (swapped if flip)  — embeddings.py:44-57; freqs [half] */
 int dp_timestep_embedding(const int64_t* t, const float* freqs, float* out, int32_t B, int32_t half, int32_t flip,
                           dp_stream_t stream);

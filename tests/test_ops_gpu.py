@@ -185,7 +185,8 @@ def test_softmax_fwd_bwd(lib, rows, cols):
 
 GN_CASES = [(2, 8, 8, 32, 8, 1, 0), (3, 4, 4, 96, 32, 1, 16), (2, 16, 16, 128, 32, 0, 0), (2, 4, 4, 512, 32, 1, 0),
             (2, 2, 2, 768, 32, 1, 0), (1, 32, 32, 192, 32, 1, 64), (4, 3, 5, 24, 3, 0, 0),
-            (2, 8, 8, 30, 3, 1, 0), (2, 8, 8, 64, 8, 1, 2), (2, 4, 4, 358, 2, 1, 0)]   # scalar path: C%4!=0 / misaligned view
+            (2, 8, 8, 30, 3, 1, 0), (2, 8, 8, 64, 8, 1, 2), (2, 4, 4, 358, 2, 1, 0),   # scalar path: C%4!=0 / misaligned view
+            (1, 64, 64, 128, 32, 1, 0), (3, 32, 32, 96, 32, 1, 0), (2, 16, 16, 384, 32, 1, 8)]   # chunked float4 path (HW too large for a slab) / slab path: pruned 96, concat 384
 
 
 @pytest.mark.parametrize("N,H,W,Cc,G,silu,ldx", GN_CASES)

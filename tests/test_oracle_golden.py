@@ -192,3 +192,53 @@ def test_exp_importance_variants_match_the_vendored_classes():
             got = orc.group_importance(items, w, dw, variant)
             ref = g["imp"][variant]
             assert float((got - ref).abs().max()) <= 2e-4 * float(ref.abs().max()) + 1e-12, (g["root"], variant)
+
+
+def fp(t):
+    t = t.detach().double()
+    return [float(t.sum()), float(t.abs().sum()), float((t * t).sum())]
+
+
+def ldm_tiny_model(G):
+    """Rebuild the fixture's weights: seed-0 construction, then the zero-initialised convolutions re-drawn exactly as tools/gen_golden.py did."""
+    import hashlib
+    from diff_pruning_b200 import ldm
+    torch.manual_seed(0)
+    m = ldm.UNetModel(**G["cfg"]).eval()
+    g = torch.Generator().manual_seed(5)
+    redrawn = []
+    for k, p in m.named_parameters():
+        if float(p.detach().abs().sum()) == 0 and p.dim() > 1:
+            p.data.copy_(torch.randn(p.shape, generator=g) * 0.05)
+            redrawn.append(k)
+    ctx = torch.randn(2, 1, G["cfg"]["context_dim"], generator=g)
+    assert redrawn == G["redrawn"] and list(m.state_dict().keys()) == G["sd_keys"]
+    assert hashlib.sha256(b"".join(v.detach().numpy().tobytes() for v in m.state_dict().values())).hexdigest() == G["sd_sha"]
+    assert torch.equal(ctx, G["context"])
+    return m
+
+
+def test_ldm_module_tree_and_oracle_match_the_reference():
+    """BASELINE configs[4] (ldm_exp UNetModel): this package's module tree reproduces the reference's parameters bit for bit (state-dict
+    keys + digest; 400 920 579 parameters for cin256-v2), and the LDM oracle reproduces the reference's loss / eps_hat / gradients of two
+    accumulated Taylor passes (tests/golden/ldm_tiny.pt, generated from the unmodified reference modules)."""
+    from oracle import ldm_oracle as lorc
+    from diff_pruning_b200 import ldm
+    G = load_golden("ldm_tiny.pt")
+    assert G["cin256_v2_params"] == 400920579
+    m = ldm_tiny_model(G)
+    ac = lorc.alphas_cumprod()
+    assert fp(ac) == pytest.approx(G["alphas_cumprod_fp"], rel=1e-6)
+    assert torch.equal(ac, ldm.ldm_alphas_cumprod())
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    g1, g2 = torch.Generator().manual_seed(1), torch.Generator().manual_seed(2)
+    clean, noise = torch.randn(2, 3, 16, 16, generator=g1), torch.randn(2, 3, 16, 16, generator=g2)
+    losses = [lorc.taylor_pass(sd, G["cfg"], ac, clean, noise, (tt * torch.ones(2)).long(), G["context"]).item() for tt in (7, 400)]
+    assert losses == pytest.approx(G["losses"], rel=1e-6)
+    for k, v in sd.items():
+        assert float((v.grad - G["grads"][k]).abs().max()) <= 2e-5 * float(G["grads"][k].abs().max()) + 1e-9, k
+    # trace-mode forward of the module tree == oracle forward
+    with dp.trace_mode(), torch.no_grad():
+        t = (400 * torch.ones(2)).long()
+        out = m(lorc.q_sample(ac, clean, noise, t), t, context=G["context"])
+    assert max_rel(out, G["out_last"]) < 1e-5

@@ -545,3 +545,38 @@ def test_ddpm_train_loop_through_the_compat_surface_bf16():
     with torch.no_grad():
         y = model(x, 50).sample
         assert torch.equal(y, copy.deepcopy(model)(x, 50).sample)   # and the live weights are back after ema.restore
+
+
+def test_ldm_unet_two_accumulated_passes_vs_reference():
+    """BASELINE configs[4]: the latent-diffusion UNetModel (ResBlocks, SpatialTransformer with LayerNorm / self-attention / one-token
+    cross-attention / GEGLU feed-forward, strided-conv down- and nearest+conv up-sampling) through the engine: loss, eps_hat and every
+    parameter gradient after two accumulated Taylor passes against the UNMODIFIED reference modules (tests/golden/ldm_tiny.pt);
+    the to_q / to_k / norm2 parameters of the cross-attention receive exactly zero gradient on both sides."""
+    from test_oracle_golden import ldm_tiny_model
+    from diff_pruning_b200 import ldm
+    G = load_golden("ldm_tiny.pt")
+    for use_graph in (False, True):
+        m = ldm_tiny_model(G).cuda()
+        clean, noise = inputs(2, 16)
+        m.zero_grad()
+        sc = TaylorScorer(m, clean.cuda(), noise.cuda(), alphas_cumprod=ldm.ldm_alphas_cumprod(), use_graph=use_graph, context=G["context"].cuda())
+        losses = [sc.step(7).item(), sc.step(400).item()]
+        assert losses == pytest.approx(G["losses"], rel=5e-6), use_graph
+        assert max_rel(sc.plan.output_nchw(), G["out_last"]) < 1e-4
+        worst = worst_grad_err(((k, p.grad) for k, p in m.named_parameters()), G["grads"])
+        assert worst < 1e-4, (use_graph, worst)
+        for k, p in m.named_parameters():
+            if float(G["grads"][k].abs().max()) == 0.0:
+                assert float(p.grad.abs().max()) == 0.0, k
+    # the module-forward path (what prune_ldm.py's model.apply_model reaches): autograd boundary + context argument
+    m = ldm_tiny_model(G).cuda()
+    ac = ldm.ldm_alphas_cumprod().cuda()
+    clean, noise, ctx = clean.cuda(), noise.cuda(), G["context"].cuda()
+    m.zero_grad()
+    for tt in (7, 400):
+        t = torch.full((2,), tt, device="cuda", dtype=torch.long)
+        xt = (ac[t] ** 0.5).reshape(-1, 1, 1, 1) * clean + ((1 - ac[t]) ** 0.5).reshape(-1, 1, 1, 1) * noise
+        loss = F.mse_loss(m(xt, t, context=ctx), noise)
+        loss.backward()
+    assert loss.item() == pytest.approx(G["losses"][1], rel=5e-6)
+    assert worst_grad_err(((k, p.grad) for k, p in m.named_parameters()), G["grads"]) < 1e-4

@@ -475,6 +475,55 @@ def gen_exp_importance():
     print("exp_importance", len(groups), os.path.getsize(os.path.join(OUT, "exp_importance_tiny.pt")))
 
 
+def gen_ldm_tiny():
+    """The latent-diffusion UNetModel (BASELINE configs[4]) from the UNMODIFIED reference modules
+    (ldm_exp/ldm/modules/diffusionmodules/openaimodel.py + ldm_exp/ldm/modules/attention.py; omegaconf is stubbed, openaimodel.py:476):
+    a small member of the cin256-v2 family whose zero-initialised convolutions are re-drawn (a random-init network otherwise outputs 0
+    and back-propagates nothing into most layers): state-dict keys, eps_hat, loss and all gradients after two accumulated Taylor passes
+    (q_sample with the LDM sqrt-linear schedule, mse loss — what `get_loss_at_t` returns, ddpm.py:881-889,1022-1056); plus the parameter
+    count of the full cin256-v2 network."""
+    import types
+    sys.path.insert(0, os.path.join(ref_shim.REF, "ldm_exp"))
+    oc, lc = types.ModuleType("omegaconf"), types.ModuleType("omegaconf.listconfig")
+    lc.ListConfig = type("ListConfig", (list,), {})
+    oc.listconfig = lc
+    sys.modules.setdefault("omegaconf", oc)
+    sys.modules.setdefault("omegaconf.listconfig", lc)
+    from ldm.modules.diffusionmodules.openaimodel import UNetModel as RefUNet
+    from diff_pruning_b200 import ldm as L
+    cfg = dict(L.LDM_TINY_CONFIG)
+    torch.manual_seed(0)
+    m = RefUNet(**cfg).eval()
+    g = torch.Generator().manual_seed(5)
+    redrawn = []
+    for k, p in m.named_parameters():
+        if float(p.detach().abs().sum()) == 0 and p.dim() > 1:
+            p.data.copy_(torch.randn(p.shape, generator=g) * 0.05)
+            redrawn.append(k)
+    betas = torch.linspace(0.0015 ** 0.5, 0.0195 ** 0.5, 1000, dtype=torch.float64) ** 2
+    ac = torch.cumprod(1.0 - betas, dim=0).to(torch.float32)
+    clean, noise = inputs(2, 16)
+    ctx = torch.randn(2, 1, cfg["context_dim"], generator=g)
+    m.zero_grad()
+    losses = []
+    for tt in (7, 400):
+        t = (tt * torch.ones(2)).long()
+        xt = (ac[t] ** 0.5).reshape(-1, 1, 1, 1) * clean + ((1 - ac[t]) ** 0.5).reshape(-1, 1, 1, 1) * noise
+        out = m(xt, t, context=ctx)
+        loss = torch.nn.functional.mse_loss(out, noise)
+        loss.backward()
+        losses.append(loss.item())
+    torch.manual_seed(0)
+    n_full = sum(p.numel() for p in RefUNet(**L.CIN256_V2_CONFIG).parameters())
+    import hashlib
+    sha = hashlib.sha256(b"".join(v.detach().numpy().tobytes() for v in m.state_dict().values())).hexdigest()
+    # weights are reproducible (seed 0 construction + the redraw loop above with Generator(5), context drawn right after): only their digest is stored
+    torch.save({"cfg": cfg, "redrawn": redrawn, "sd_keys": list(m.state_dict().keys()), "sd_sha": sha, "context": ctx, "losses": losses,
+                "out_last": out.detach(), "grads": {k: p.grad.clone() for k, p in m.named_parameters()}, "alphas_cumprod_fp": fp(ac),
+                "cin256_v2_params": n_full}, os.path.join(OUT, "ldm_tiny.pt"))
+    print("ldm_tiny", losses, n_full, len(redrawn), os.path.getsize(os.path.join(OUT, "ldm_tiny.pt")))
+
+
 def gen_ref_pickle():
     """A whole-module pickle exactly as the reference writes it (`torch.save(model)`, ddpm_prune.py:135) for a small member of the
     family after a `--pruner magnitude` prune at ratio 0.3 — default AttnProcessor2_0 objects, FrozenDict config and all — plus eps_hat
@@ -513,7 +562,7 @@ if __name__ == "__main__":
     ap.add_argument("--only", default=None)
     a = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
-    jobs = {"exp_importance": gen_exp_importance, "ref_pickle": gen_ref_pickle, "lsun_struct": gen_lsun_struct, "lr": gen_lr, "ckpt": gen_ckpt, "ddim": gen_ddim, "tiny": gen_tiny, "blocks": gen_blocks, "finetune": gen_finetune, "cifar_fwd": gen_cifar_fwd,
+    jobs = {"ldm_tiny": gen_ldm_tiny, "exp_importance": gen_exp_importance, "ref_pickle": gen_ref_pickle, "lsun_struct": gen_lsun_struct, "lr": gen_lr, "ckpt": gen_ckpt, "ddim": gen_ddim, "tiny": gen_tiny, "blocks": gen_blocks, "finetune": gen_finetune, "cifar_fwd": gen_cifar_fwd,
             "cfg1_s3": gen_cfg1_s3, "cfg3_s3": gen_cfg3_s3, "cfg1": gen_cfg1}
     for name, fn in jobs.items():
         if a.only and name != a.only:
