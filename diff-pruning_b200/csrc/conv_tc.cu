@@ -14,7 +14,9 @@
 //   wgrad_tc_kernel       weight gradient: dY^T through TMEM, X split in shared memory, both MN-major, split-K over pixels
 //   pack_tc / split_tf32 / transpose_batched helpers; dp_gemm_nt_tc runs the attention GEMMs on the persistent kernel.
 // The experimental variants measured in round 1 (SS one-tile, cluster multicast, decoupled rings, two-issuer, persistent TS, 16-float
-// stages, the clock64() stage tracer; profiles/r01_experiments.md) live on the git tag `lab-kernels-r01`, not in the product library.
+// stages, the clock64() stage tracer; profiles/r01_experiments.md) live on the git tag `lab-kernels-r01`, the cta_group::2 CTA-pair
+// kernel of round 2 (correct, 1.4x SLOWER: the kernel is shared-memory-bandwidth bound, profiles/r02_experiments.md) on
+// `lab-pair-kernel-r02` — neither is in the product library.
 #include <cuda.h>
 #include <mutex>
 #include "common.cuh"
@@ -544,288 +546,6 @@ conv_tc_ps_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   }
 }
 
-// ------------------------------------------------------------------------------------------------ CTA-pair variant (cta_group::2)
-// The persistent kernel above moves 48 KB of operands from L2 into one SM per 768-clock stage (62 B/clk): it sits on the SM's L2 ingest
-// rate (~8.4 TB/s over the chip in the ncu captures), not on the tensor pipe.  Here two CTAs on the two SMs of a TPC form a pair
-// (thread-block cluster of 2) and one tcgen05.mma.cta_group::2 instruction computes a 256-pixel x N tile: each CTA holds its own 128
-// pixels of A (raw -> hi/lo by its own splitter warps) and HALF of the weight tile (the tensor cores read the two halves out of both
-// CTAs' shared memory), so a stage costs 16 KB (A) + 16 KB (B hi/lo halves) per SM — 42 B/clk — and four 48 KB stages fit.
-//   rank 0 (leader): issues every MMA; its barriers collect both CTAs: fullB (TMA bytes of both weight halves, the peer's loads signal
-//                    it through cp.async.bulk.tensor.cta_group::2), conv (256 splitter arrivals), tempty (256 epilogue arrivals)
-//   both ranks     : TMA producer (own A box + own weight half), splitters (own A tile), epilogue (own 128 TMEM lanes); stage release
-//                    (empty) and accumulator-ready (tfull) reach both CTAs through tcgen05.commit ... multicast::cluster.
-// Three N-wide instructions per 8-float K step (hi*hi -> main, lo*hi and hi*lo -> correction): with M = 256 per instruction that is
-// 6 instructions per 128-pixel tile-equivalent, fewer than the single-CTA kernel's 8.
-constexpr int P2_THREADS = 320, P2_STAGES = 4;
-constexpr int P2_BH = 64 * BK * 4;                       // 8 KB: the 64 weight rows one CTA contributes to one (hi or lo) tile
-constexpr int P2_STAGE = 2 * A_BYTES + 2 * P2_BH;        // 48 KB
-constexpr int P2_SMEM = P2_STAGES * P2_STAGE + 2048;
-
-__device__ __forceinline__ uint32_t leader_addr(uint32_t local) {   // the same shared-memory offset in CTA 0 of the cluster
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(0));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // arrivals may come from the peer CTA
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-// weight-half load of a CTA pair: data lands in THIS CTA's shared memory, the transaction bytes are counted on the LEADER's barrier
-// (cute::SM100_TMA_2SM_LOAD: the barrier address with the peer bit cleared)
-__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {   // arrive on the barrier at this offset in BOTH CTAs of the pair
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
-__global__ void __launch_bounds__(P2_THREADS, 1)
-conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBh,
-                    const __grid_constant__ CUtensorMap mapBl, const TcParams p, const int tiles_m, const int pairs_m, const int total_super) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t pad_to = ((raw + 1023u) & ~1023u) - raw;
-  uint8_t* smem = smem_raw + pad_to;
-  const uint32_t sbase = raw + pad_to;
-  const uint32_t bar0 = sbase + P2_STAGES * P2_STAGE;
-  auto fullA_bar = [&](int s) { return bar0 + 8u * s; };                       // local: my A box landed
-  auto fullB_bar = [&](int s) { return bar0 + 8u * (P2_STAGES + s); };         // leader: both weight halves landed
-  auto conv_bar = [&](int s) { return bar0 + 8u * (2 * P2_STAGES + s); };      // leader: both A tiles are split (256 arrivals)
-  auto empty_bar = [&](int s) { return bar0 + 8u * (3 * P2_STAGES + s); };     // both: the MMAs have read this stage
-  auto tfull_bar = [&](int b) { return bar0 + 8u * (4 * P2_STAGES + b); };     // both: accumulator set b is complete
-  auto tempty_bar = [&](int b) { return bar0 + 8u * (4 * P2_STAGES + 2 + b); };  // leader: both epilogues drained set b (256 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + P2_STAGES * P2_STAGE + 8 * (4 * P2_STAGES + 4));
-
-  uint32_t rank;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
-  const bool leader = rank == 0;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < P2_STAGES; ++s) {
-      mbar_init(fullA_bar(s), 1); mbar_init(fullB_bar(s), 1); mbar_init(conv_bar(s), 256); mbar_init(empty_bar(s), 1);
-    }
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 256); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  cluster_sync_all();        // the peer's barriers exist before any remote arrive / multicast commit / cta_group::2 load can reach them
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot;
-  const int iters_per_tile = p.ntaps * p.kchunks;
-  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-
-  // supertile = (pair of neighbouring 128-pixel tiles, N tile); this CTA owns pixel tile 2*mp + rank (a tile index past the end — odd
-  // tile counts — addresses images >= Nimg: TMA fills zeros, the epilogue stores nothing)
-  auto tile_coords = [&](int st, int& q0, int& p0, int& n0, int& nblk) {
-    nblk = st / pairs_m;
-    const int tile_m = 2 * (st - nblk * pairs_m) + (int)rank;
-    const int tw = tile_m % p.tiles_w;
-    const int th = (tile_m / p.tiles_w) % p.tiles_h;
-    const int tn = tile_m / (p.tiles_w * p.tiles_h);
-    q0 = tw * p.bw; p0 = th * p.bh; n0 = tn * p.bn;
-  };
-  auto n_instr_of = [&](int nblk) { return (uint32_t)((min(128, p.Nout - nblk * 128) + 15) & ~15); };
-
-  if (warp == 0) {
-    if (elect_one()) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapBh)) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapBl)) : "memory");
-      int s = 0; uint32_t ph = 0;
-      for (int st = pair; st < total_super; st += npairs) {
-        int q0, p0, n0, nblk;
-        tile_coords(st, q0, p0, n0, nblk);
-        // the tensor cores take the first n_instr/2 weight rows of the tile from CTA 0 and the next n_instr/2 from CTA 1
-        const int row0 = nblk * 128 + (int)rank * (int)(n_instr_of(nblk) >> 1);
-        for (int it = 0; it < iters_per_tile; ++it) {
-          mbar_wait_cluster(empty_bar(s), ph ^ 1u);
-          const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
-          const uint32_t stg = sbase + s * P2_STAGE;
-          mbar_expect_tx(fullA_bar(s), A_BYTES);
-          tma_load_4d(stg, &mapA, fullA_bar(s), kc * BK, q0 * p.in_stride + p.dw[tap], p0 * p.in_stride + p.dh[tap], n0);
-          if (leader) mbar_expect_tx(fullB_bar(s), 4 * P2_BH);        // hi + lo halves of both CTAs
-          const int tapb = p.wt[tap];
-          tma_load_3d_2sm(stg + 2 * A_BYTES, &mapBh, fullB_bar(s), kc * BK, row0, tapb);
-          tma_load_3d_2sm(stg + 2 * A_BYTES + P2_BH, &mapBl, fullB_bar(s), kc * BK, row0, tapb);
-          if (++s == P2_STAGES) { s = 0; ph ^= 1u; }
-        }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    if (leader) {
-      int s = 0; uint32_t ph = 0, tl = 0;
-      for (int st = pair; st < total_super; st += npairs, ++tl) {
-        const int nblk = st / pairs_m;
-        // D = F32 | A, B = TF32 | K-major | N >> 3 at bit 17 | M = 256 (>> 4) at bit 24
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((n_instr_of(nblk) >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-        const uint32_t b = tl & 1u, use = tl >> 1;
-        mbar_wait_cluster(tempty_bar(b), (use & 1u) ^ 1u);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t acc = tmem_base + b * 256u;
-        for (int it = 0; it < iters_per_tile; ++it) {
-          mbar_wait_cluster(conv_bar(s), ph);
-          mbar_wait_cluster(fullB_bar(s), ph);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t stg = sbase + s * P2_STAGE;
-          if (elect_one()) {
-#pragma unroll
-            for (int k = 0; k < BK / 8; ++k) {
-              const uint64_t a_hi = umma_desc(stg + k * 32), a_lo = umma_desc(stg + A_BYTES + k * 32);
-              const uint64_t b_hi = umma_desc(stg + 2 * A_BYTES + k * 32), b_lo = umma_desc(stg + 2 * A_BYTES + P2_BH + k * 32);
-              const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
-              umma_tf32_2sm(acc + 128, a_lo, b_hi, idesc, first);
-              umma_tf32_2sm(acc + 128, a_hi, b_lo, idesc, 1u);
-              umma_tf32_2sm(acc, a_hi, b_hi, idesc, first);
-            }
-            umma_commit_2sm(empty_bar(s));
-            if (it == iters_per_tile - 1) umma_commit_2sm(tfull_bar(b));
-          }
-          __syncwarp();
-          if (++s == P2_STAGES) { s = 0; ph ^= 1u; }
-        }
-      }
-    }
-  } else if (warp < 6) {
-    // ---- splitter warps 2..5: my raw A tile -> hi (in place) / lo, then tell the LEADER's MMA warp
-    const int ct = threadIdx.x - 64;
-    int s = 0; uint32_t ph = 0;
-    for (int st = pair; st < total_super; st += npairs) {
-      for (int it = 0; it < iters_per_tile; ++it) {
-        mbar_wait(fullA_bar(s), ph);
-        float4* A = reinterpret_cast<float4*>(smem + s * P2_STAGE);
-        float4* Al = reinterpret_cast<float4*>(smem + s * P2_STAGE + A_BYTES);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int idx = ct + 128 * i;
-          float4 v = A[idx], h, l;
-          h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-          l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-          A[idx] = h;
-          Al[idx] = l;
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive_cluster(leader_addr(conv_bar(s)));
-        if (++s == P2_STAGES) { s = 0; ph ^= 1u; }
-      }
-    }
-  } else {
-    // ---- epilogue warps 6..9: my 128 TMEM lanes (TMEM lane quarter = warp & 3)
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const int w_l = row % p.bw, h_l = (row / p.bw) % p.bh, n_l = row / (p.bw * p.bh);
-    uint32_t tl = 0;
-    for (int st = pair; st < total_super; st += npairs, ++tl) {
-      int q0, p0, n0, nblk;
-      tile_coords(st, q0, p0, n0, nblk);
-      const uint32_t b = tl & 1u, use = tl >> 1;
-      mbar_wait_cluster(tfull_bar(b), use & 1u);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int img = n0 + n_l;
-      const bool row_ok = img < p.Nimg;
-      const long long m = ((long long)img * p.Ho + ((p0 + h_l) * p.os + p.oa)) * p.Wo + ((q0 + w_l) * p.os + p.ob);
-      float* yrow = p.y + m * p.ldy;
-      const float* rrow = p.residual ? p.residual + m * p.ld_res : nullptr;
-      const float* arow2 = p.rowadd ? p.rowadd + (long long)img * p.ld_rowadd : nullptr;
-#pragma unroll 1
-      for (int j = 0; j < 4; ++j) {
-        uint32_t v[32], u[32];
-        const uint32_t taddr = tmem_base + lane_addr + b * 256u + (uint32_t)(j * 32);
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-            : "r"(taddr));
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
-              "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
-              "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
-              "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
-            : "r"(taddr + 128u));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (j == 3) {   // accumulators are in registers: hand the TMEM set back to the leader's MMA warp
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          mbar_arrive_cluster(leader_addr(tempty_bar(b)));
-        }
-        if (row_ok) {
-          const int c0 = nblk * 128 + j * 32;
-          if (p.vec4 && c0 + 32 <= p.Nout) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              float4 o = make_float4(__uint_as_float(v[i]) + __uint_as_float(u[i]), __uint_as_float(v[i + 1]) + __uint_as_float(u[i + 1]),
-                                     __uint_as_float(v[i + 2]) + __uint_as_float(u[i + 2]), __uint_as_float(v[i + 3]) + __uint_as_float(u[i + 3]));
-              if (p.bias) { float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + i)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
-              if (arow2) { float4 t = __ldg(reinterpret_cast<const float4*>(arow2 + c0 + i)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
-              if (rrow) { float4 t = __ldg(reinterpret_cast<const float4*>(rrow + c0 + i)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
-              float4* dst = reinterpret_cast<float4*>(yrow + c0 + i);
-              if (p.accumulate) { float4 t = *dst; o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
-              *dst = o;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int c = c0 + i;
-              if (c < p.Nout) {
-                float o = __uint_as_float(v[i]) + __uint_as_float(u[i]);
-                if (p.bias) o += __ldg(p.bias + c);
-                if (arow2) o += __ldg(arow2 + c);
-                if (rrow) o += __ldg(rrow + c);
-                if (p.accumulate) o += yrow[c];
-                yrow[c] = o;
-              }
-            }
-          }
-        }
-      }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  }
-  __syncthreads();
-  cluster_sync_all();        // nobody frees TMEM or exits while the peer may still signal / read
-  if (warp == 1) {
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
-  }
-}
-
 // ------------------------------------------------------------------------------------------------ wgrad
 // dW[k][tap][c] = sum_pix dy[pix][k] * x[pix @ tap][c]  as GEMM  M = k (128), N = c (128), K = pixels.
 // Both operands are activations stored pixel-major / channel-contiguous, i.e. "MN-major" for the tensor core:
@@ -1067,7 +787,6 @@ std::mutex g_tc_mutex;
 constexpr int PS_SMEM = PS_STAGES * (2 * A_BYTES + 2 * 128 * BK * 4) + 2048;
 constexpr int TS64_SMEM = STAGES_TS * (A_BYTES + 2 * 64 * BK * 4) + 2048;
 constexpr int WG_SMEM = 4 * 3 * WG_T + 2048;
-int g_pairs = 0;      // CTA pairs (clusters of 2) the device runs concurrently with the pair kernel's resources; 0 = pair kernel unusable
 
 // Row length of the packed TF32 weight tiles (dp_pack_conv_weight_tc): rows longer than 32 floats are zero-padded to a multiple of 32
 // floats (128 B) so that every 32-float TMA box row is exactly one aligned 128-byte line; short rows to a multiple of 4 (the TMA
@@ -1092,16 +811,6 @@ int tc_init() {
   ok = ok && cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM) == cudaSuccess;
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   if (!ok) { (void)cudaGetLastError(); return 0; }
-  if (cudaFuncSetAttribute(conv_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM) == cudaSuccess) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)(g_num_sms & ~1)); cfg.blockDim = dim3(P2_THREADS); cfg.dynamicSmemBytes = P2_SMEM;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, conv_tc_pair_kernel, &cfg) == cudaSuccess && n > 0) g_pairs = n;
-  }
   (void)cudaGetLastError();
   g_tc_state = 1;
   return 1;
@@ -1184,25 +893,7 @@ int launch_tc(const float* act, long long ld_act, int Nimg, int H, int W, int Kg
   p.vec4 = (al16(out, ld_out) && al16(bias, 0) && al16(rowadd, ld_rowadd) && al16(residual, ld_res)) ? 1 : 0;
   const int tiles_n = (Nimg + bn - 1) / bn;
   dim3 grid((unsigned)(p.tiles_w * p.tiles_h * tiles_n), (unsigned)((Nout + BN - 1) / BN));
-  if (BN == 128 && g_pairs > 0 && !b_from_img && alpha == 1.0f && (int)(((grid.x + 1) / 2) * grid.y) >= g_pairs) {
-    // enough pixel tiles for at least one full wave of CTA pairs: the cta_group::2 kernel (half the weight traffic per SM)
-    CUtensorMap hBh, hBl;   // the pair kernel fetches 64-row weight boxes (each CTA its half of the tile)
-    const cuuint64_t Kg4 = (cuuint64_t)ldb;
-    cuuint64_t dims[3] = {Kg4, (cuuint64_t)Nout, (cuuint64_t)T};
-    cuuint64_t str[2] = {Kg4 * 4, (cuuint64_t)Nout * Kg4 * 4};
-    cuuint32_t box[3] = {(cuuint32_t)BK, 64, 1};
-    if (!make_map(&hBh, w_hi, 3, dims, str, box) || !make_map(&hBl, w_lo, 3, dims, str, box)) return DP_ERR_UNSUPPORTED;
-    const int tiles_m = (int)grid.x, pairs_m = (tiles_m + 1) / 2, total_super = pairs_m * (int)grid.y;
-    const int npairs = total_super < g_pairs ? total_super : g_pairs;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)(2 * npairs)); cfg.blockDim = dim3(P2_THREADS); cfg.dynamicSmemBytes = P2_SMEM; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_pair_kernel, mA, hBh, hBl, p, tiles_m, pairs_m, total_super);
-    if (e != cudaSuccess) { g_dp_last_cuda_error = (int)e; (void)cudaGetLastError(); return DP_ERR_CUDA; }
-  } else if (BN == 128) {
+  if (BN == 128) {
     const int tiles_m = (int)grid.x, total = (int)(grid.x * grid.y);
     const int ctas = total < g_num_sms ? total : g_num_sms;
     conv_tc_ps_kernel<<<ctas, PS_THREADS, PS_SMEM, st>>>(mA, mBh, mBl, p, tiles_m, total);

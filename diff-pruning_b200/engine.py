@@ -649,7 +649,7 @@ class Plan:
             ga.C, ga.ldc, ga.c_bs, ga.alpha, ga.accumulate = Cp, ldc, c_bs, alpha, 0
             return ga
         Pp = P.data_ptr()
-        if self.tc and T % 128 == 0:
+        if self.tc and T % 128 == 0 and inner > 64:      # the NT GEMM rides the 128-wide persistent kernel (N tiles of 128)
             return self._attention_core_tc(N, H, W, T, inner, q, k, v, o, P, sc)
         # S = scale * q k^T ; P = softmax(S) (in place) ; o = P v
         self._rec(self.fwd, lib.dp_gemm_batched, gemm(T, T, inner, q.ptr, q.ld, 1, T * q.ld, k.ptr, 1, k.ld, T * k.ld,
