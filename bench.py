@@ -581,6 +581,32 @@ def run_ours(args, rank, world, local_rank):
         conv_s, n_conv, conv_by_tag, conv_by_layer = timed_conv_launches(p, pro, mid)
     else:
         conv_s, n_conv, conv_by_tag, conv_by_layer = 1.0, 0, {}, {}
+    sampling = None
+    if c["model"].startswith("ldm:") and rank == 0:
+        # the other half of prune_ldm.py's step (prune_ldm.py:111-118): class-conditional DDIM-20 sampling with classifier-free guidance =
+        # 2 x 20 UNet forwards per batch of latents; forward-only launch plan, CUDA-graph replay
+        from diff_pruning_b200.engine import frozen_weights, get_plan
+        kw = extra(B, dev)
+        with torch.no_grad(), frozen_weights(model):
+            fplan = get_plan(model, B, hw, hw, dev, need_grad=False)
+            fplan.ensure_packed(force=True)
+            fplan.load_context(kw["context"])
+            fplan.load_input_nchw(clean.to(dev), torch.full((B,), 500, device=dev, dtype=torch.long))
+            fplan.run_forward(); torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fplan.run_forward()
+            for _ in range(3):
+                g.replay()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(20):
+                g.replay()
+            s1.record(); torch.cuda.synchronize(dev)
+            fms = s0.elapsed_time(s1) / 20
+        sampling = {"unet_forward_ms": fms, "latents_per_forward": B, "ddim20_cfg_batches_per_s": 1e3 / (40 * fms),
+                    "note": "forward-only UNet step (no-grad plan, CUDA graph); a DDIM-20 sample with classifier-free guidance costs 40 of them (prune_ldm.py:111-118)"}
+        del fplan, g
     plan_B, plan_macs, plan_bytes = sc.plan.B, sc.plan.conv_macs, sc.plan.bytes_allocated()
     plan_lin_macs = getattr(sc.plan, "lin_macs", 0)
     del sc
@@ -648,6 +674,8 @@ def run_ours(args, rank, world, local_rank):
         out["finetune_bf16"] = finetune_bf16
     if config3 is not None:
         out["config3"] = config3
+    if sampling is not None:
+        out["sampling"] = sampling
     print(json.dumps(out), flush=True)
 
 

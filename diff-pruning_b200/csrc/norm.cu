@@ -401,217 +401,10 @@ __global__ void __launch_bounds__(NT) gn_bwd_apply4_kernel(const dp_gn_args a, c
 }
 
 
-// ------------------------------------------------------------------------------------------------------------
-// Slab kernels: ONE launch per GroupNorm direction for activations whose per-image channel slab fits in shared memory
-// (HW <= 1024 for the widths of the DDPM UNets: every layer of the CIFAR network, the <= 32x32 levels of LSUN-256).
-// A CTA owns (image n, `cw` consecutive channels = whole groups): it reads its slab from HBM exactly once into shared memory,
-// reduces the group statistics with warp shuffles (fixed tree: deterministic), and normalises / differentiates out of shared
-// memory — the chunked path above needs 3 (forward) / 4 (backward) launches and reads the activation twice in each direction.
-struct SlabCfg { int cw, nslab, LG; size_t smem; };
-
-// 16-byte asynchronous global -> shared copy (LDGSTS): every thread queues all of its slab rows before anybody waits, so the whole
-// slab is in flight at once (a register-staged loop of 256 threads keeps only a few KB outstanding per SM)
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-}
-
-static inline int lcm_i(int a, int b) { int x = a, y = b; while (y) { int t = x % y; x = y; y = t; } return a / x * b; }
-
-// cw = slab width (channels): a multiple of lcm(channels per group, 4), as wide as `budget` bytes of slab allow; 0 = not eligible
-static inline SlabCfg slab_cfg(int HW, int C, int G, size_t extra_per_ch, size_t extra_fixed) {
-  SlabCfg s{0, 0, 0, 0};
-  const int cpg = C / G;
-  if (C % 4 || cpg < 3 || HW < 16) return s;      // HW = 1 is LayerNorm over tokens: the chunked path spreads the channels over the CTA
-  const int L = lcm_i(cpg, 4);
-  const size_t budget = 200 * 1024 - extra_fixed;
-  long long maxcw = (long long)(budget / ((size_t)HW * 4 + extra_per_ch));
-  if (maxcw >= C) maxcw = C;
-  int cw = (int)(maxcw / L) * L;
-  if (cw < 32 && cw != C) return s;
-  if (cw <= 0) return s;
-  const int gpb = cw / cpg;
-  int lg = gpb <= 8 ? 32 : gpb <= 16 ? 16 : gpb <= 32 ? 8 : gpb <= 64 ? 4 : 0;
-  if (!lg) return s;
-  s.cw = cw; s.nslab = (C + cw - 1) / cw; s.LG = lg;
-  s.smem = (size_t)HW * cw * 4 + (size_t)cw * extra_per_ch + extra_fixed + 256;
-  return s;
-}
-
-__global__ void __launch_bounds__(NT) gn_fwd_slab_kernel(const dp_gn_args a, const int cw, const int LG) {
-  extern __shared__ float sm[];
-  const int n = blockIdx.y, c0 = blockIdx.x * cw, cwv = min(cw, a.C - c0), QR = cwv >> 2, tid = threadIdx.x;
-  const int cpg = a.C / a.G, gpb = cwv / cpg;
-  float* slab = sm;                         // [HW][cwv]
-  float* sc = sm + (size_t)a.HW * cwv;      // [cwv] rstd * gamma
-  float* sh = sc + cwv;                     // [cwv] beta - mean * rstd * gamma
-  const float* xb = a.x + (long long)n * a.HW * a.ldx + c0;
-  const int nq = a.HW * QR;
-  for (int i = tid; i < nq; i += NT) {
-    const int pix = i / QR, q = i - pix * QR;
-    cp_async16(reinterpret_cast<float4*>(slab) + i, xb + (long long)pix * a.ldx + 4 * q);
-  }
-  cp_async_wait_all();
-  __syncthreads();
-  {   // group statistics: LG lanes per group walk the pixels, xor-shuffle tree inside the LG-lane segment
-    const int gi = tid / LG, lane = tid % LG;
-    double s = 0.0, ss = 0.0;
-    if (gi < gpb) {
-      const float* gp = slab + gi * cpg;
-      for (int pix = lane; pix < a.HW; pix += LG)
-        for (int e = 0; e < cpg; ++e) { const float v = gp[(size_t)pix * cwv + e]; s += v; ss += (double)v * v; }
-    }
-    for (int o = LG >> 1; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
-    if (gi < gpb) {
-      const double m = (double)a.HW * cpg;
-      const double mean = s / m;
-      double var = ss / m - mean * mean;
-      if (var < 0) var = 0;
-      const float mu = (float)mean, rs = (float)(1.0 / sqrt(var + (double)a.eps));
-      const int g = c0 / cpg + gi;
-      if (lane == 0) { a.mean[n * a.G + g] = mu; a.rstd[n * a.G + g] = rs; }
-      for (int e = lane; e < cpg; e += LG) {
-        const int cl = gi * cpg + e;
-        const float ga = __ldg(a.gamma + c0 + cl), be = __ldg(a.beta + c0 + cl);
-        sc[cl] = rs * ga; sh[cl] = be - mu * rs * ga;
-      }
-    }
-  }
-  __syncthreads();
-  const uint64_t seed = a.dropout_seed + (a.dropout_seed_dev ? *a.dropout_seed_dev : 0ull);
-  float* yb = a.y ? a.y + (long long)n * a.HW * a.ldy + c0 : nullptr;
-  __nv_bfloat16* ybf = a.y_bf16 ? reinterpret_cast<__nv_bfloat16*>(a.y_bf16) + (long long)n * a.HW * a.ldyb + c0 : nullptr;
-  for (int i = tid; i < nq; i += NT) {
-    const int pix = i / QR, q = i - pix * QR;
-    const float4 v = reinterpret_cast<const float4*>(slab)[i];
-    const float4 s4 = reinterpret_cast<const float4*>(sc)[q], h4 = reinterpret_cast<const float4*>(sh)[q];
-    float y[4] = {fmaf(v.x, s4.x, h4.x), fmaf(v.y, s4.y, h4.y), fmaf(v.z, s4.z, h4.z), fmaf(v.w, s4.w, h4.w)};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      if (a.silu) y[e] = y[e] * sigmoidf_acc(y[e]);
-      if (a.dropout_p > 0.f) y[e] *= keep_scale(seed, ((uint64_t)n * a.HW + pix) * a.C + c0 + 4 * q + e, a.dropout_p);
-    }
-    if (yb) *reinterpret_cast<float4*>(yb + (long long)pix * a.ldy + 4 * q) = make_float4(y[0], y[1], y[2], y[3]);
-    if (ybf) {
-      __nv_bfloat162 lo = __floats2bfloat162_rn(y[0], y[1]), hi = __floats2bfloat162_rn(y[2], y[3]);
-      *reinterpret_cast<uint2*>(ybf + (long long)pix * a.ldyb + 4 * q) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
-    }
-  }
-}
-
-// backward: x_hat of the slab in shared memory; dy is streamed twice (the second pass hits L2: the CTA's slice is <= 196 KB)
-__global__ void __launch_bounds__(NT) gn_bwd_slab_kernel(const dp_gn_args a, const int cw, float* __restrict__ fin) {
-  extern __shared__ float sm[];
-  const int n = blockIdx.y, c0 = blockIdx.x * cw, cwv = min(cw, a.C - c0), QR = cwv >> 2, tid = threadIdx.x;
-  const int cpg = a.C / a.G, gpb = cwv / cpg;
-  const int RP = NT / QR;                         // pixel rows per sweep; threads tid >= RP * QR idle in the row-mapped passes
-  float* xh = sm;                                 // [HW][cwv]
-  float* ga = xh + (size_t)a.HW * cwv;            // [cwv] gamma | beta | rstd | k1 | k2 | S1 | S2
-  float* be = ga + cwv; float* rsc = be + cwv; float* k1 = rsc + cwv; float* k2 = k1 + cwv; float* S1 = k2 + cwv; float* S2 = S1 + cwv;
-  float* P1 = S2 + cwv;                           // [RP][cwv] per-row partial sums (RP * cwv = RP * QR * 4 <= 1024)
-  float* P2 = P1 + 1024;
-  for (int c = tid; c < cwv; c += NT) {
-    const int g = (c0 + c) / cpg;
-    ga[c] = __ldg(a.gamma + c0 + c); be[c] = __ldg(a.beta + c0 + c); rsc[c] = a.rstd[n * a.G + g];
-    k1[c] = a.mean[n * a.G + g];                  // k1 holds the mean until the coefficients are known
-  }
-  __syncthreads();
-  const float* xb = a.x + (long long)n * a.HW * a.ldx + c0;
-  const int nq = a.HW * QR;
-  for (int i = tid; i < nq; i += NT) {
-    const int pix = i / QR, q = i - pix * QR;
-    cp_async16(reinterpret_cast<float4*>(xh) + i, xb + (long long)pix * a.ldx + 4 * q);
-  }
-  cp_async_wait_all();
-  __syncthreads();      // k1 (mean) / rsc are visible; every thread normalises the elements it copied itself
-  for (int i = tid; i < nq; i += NT) {
-    const int q = i % QR;
-    const float4 v = reinterpret_cast<const float4*>(xh)[i];
-    const float4 m4 = reinterpret_cast<const float4*>(k1)[q], r4 = reinterpret_cast<const float4*>(rsc)[q];
-    reinterpret_cast<float4*>(xh)[i] = make_float4((v.x - m4.x) * r4.x, (v.y - m4.y) * r4.y, (v.z - m4.z) * r4.z, (v.w - m4.w) * r4.w);
-  }
-  __syncthreads();
-  const float* db = a.dy + (long long)n * a.HW * a.lddy + c0;
-  const int q = tid % QR, r = tid / QR;
-  const bool act = r < RP;
-  float gq[4], bq[4];
-#pragma unroll
-  for (int e = 0; e < 4; ++e) { gq[e] = ga[4 * q + e]; bq[e] = be[4 * q + e]; }
-  {   // pass A: per-channel sums of g and g * x_hat
-    float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
-    if (act)
-#pragma unroll 4
-      for (int pix = r; pix < a.HW; pix += RP) {
-        const float4 dv = ld4(db + (long long)pix * a.lddy + 4 * q), xv = reinterpret_cast<const float4*>(xh)[pix * QR + q];
-        const float ds[4] = {dv.x, dv.y, dv.z, dv.w}, xs[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float g = gn_dy(a, ds[e], fmaf(xs[e], gq[e], bq[e]), ((uint64_t)n * a.HW + pix) * a.C + c0 + 4 * q + e);
-          s1[e] += g; s2[e] += g * xs[e];
-        }
-      }
-    if (act) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) { P1[r * cwv + 4 * q + e] = s1[e]; P2[r * cwv + 4 * q + e] = s2[e]; }
-    }
-  }
-  __syncthreads();
-  for (int c = tid; c < cwv; c += NT) {
-    double t1 = 0, t2 = 0;
-    for (int l = 0; l < RP; ++l) { t1 += P1[l * cwv + c]; t2 += P2[l * cwv + c]; }
-    S1[c] = (float)t1; S2[c] = (float)t2;
-    fin[((long long)n * 2) * a.C + c0 + c] = (float)t1;            // per-image channel sums for dbeta / dgamma (gn_bwd_param_kernel)
-    fin[((long long)n * 2 + 1) * a.C + c0 + c] = (float)t2;
-  }
-  __syncthreads();
-  if (tid < gpb) {
-    const double inv_m = 1.0 / ((double)a.HW * cpg);
-    double u1 = 0, u2 = 0;
-    for (int e = 0; e < cpg; ++e) { const int c = tid * cpg + e; u1 += (double)(S1[c] * ga[c]); u2 += (double)(S2[c] * ga[c]); }
-    for (int e = 0; e < cpg; ++e) { const int c = tid * cpg + e; k1[c] = (float)(u1 * inv_m); k2[c] = (float)(u2 * inv_m); }
-  }
-  __syncthreads();
-  float* ob = a.dx + (long long)n * a.HW * a.lddx + c0;
-  const float* ab = a.dx_add ? a.dx_add + (long long)n * a.HW * a.ldadd + c0 : nullptr;
-  const float* ab2 = a.dx_add2 ? a.dx_add2 + (long long)n * a.HW * a.ldadd2 + c0 : nullptr;
-  if (act) {
-    float rq[4], c1[4], c2[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) { rq[e] = rsc[4 * q + e]; c1[e] = k1[4 * q + e]; c2[e] = k2[4 * q + e]; }
-#pragma unroll 4
-    for (int pix = r; pix < a.HW; pix += RP) {
-      const float4 dv = ld4(db + (long long)pix * a.lddy + 4 * q), xv = reinterpret_cast<const float4*>(xh)[pix * QR + q];
-      const float ds[4] = {dv.x, dv.y, dv.z, dv.w}, xs[4] = {xv.x, xv.y, xv.z, xv.w};
-      float d[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float g = gn_dy(a, ds[e], fmaf(xs[e], gq[e], bq[e]), ((uint64_t)n * a.HW + pix) * a.C + c0 + 4 * q + e);
-        d[e] = rq[e] * (gq[e] * g - c1[e] - xs[e] * c2[e]);
-      }
-      if (ab) { const float4 t = *reinterpret_cast<const float4*>(ab + (long long)pix * a.ldadd + 4 * q); d[0] += t.x; d[1] += t.y; d[2] += t.z; d[3] += t.w; }
-      if (ab2) { const float4 t = ld4(ab2 + (long long)pix * a.ldadd2 + 4 * q); d[0] += t.x; d[1] += t.y; d[2] += t.z; d[3] += t.w; }
-      *reinterpret_cast<float4*>(ob + (long long)pix * a.lddx + 4 * q) = make_float4(d[0], d[1], d[2], d[3]);
-    }
-  }
-}
-
 static inline bool al16(const void* p, long long ld) { return p == nullptr || ((((uintptr_t)p) & 15) == 0 && (ld % 4) == 0); }
 
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
-// the slab kernels need up to ~200 KB of dynamic shared memory: opt in once per process
-static bool slab_ok() {
-  static int state = -1;
-  if (state < 0) {
-    bool ok = cudaFuncSetAttribute(gn_fwd_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(gn_bwd_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) == cudaSuccess;
-    if (!ok) (void)cudaGetLastError();
-    state = ok ? 1 : 0;
-  }
-  return state == 1;
-}
 }  // namespace
 
 extern "C" size_t dp_groupnorm_workspace_bytes(int32_t N, int32_t HW, int32_t C, int32_t G) {
@@ -642,13 +435,6 @@ extern "C" int dp_groupnorm_fwd(const dp_gn_args* a, dp_stream_t stream) {
   DP_REQUIRE(!a->y_bf16 || (a->ldyb >= a->C && a->ldyb % 8 == 0 && (((uintptr_t)a->y_bf16) & 15) == 0), DP_ERR_ALIGN);
   cudaStream_t st = (cudaStream_t)stream;
   const bool v4 = (a->C % 4 == 0) && al16(a->x, a->ldx) && al16(a->y, a->ldy);
-  if (v4 && slab_ok()) {
-    const SlabCfg sc = slab_cfg(a->HW, a->C, a->G, 2 * sizeof(float), 0);
-    if (sc.cw) {
-      gn_fwd_slab_kernel<<<dim3(sc.nslab, a->N), NT, sc.smem, st>>>(*a, sc.cw, sc.LG);
-      return dp_check_launch();
-    }
-  }
   Map mp = v4 ? make_map4(a->HW, a->C) : make_map(a->HW, a->C);
   dim3 grid(mp.nchunks, a->N);
   if (v4) {
@@ -673,20 +459,6 @@ extern "C" int dp_groupnorm_bwd(const dp_gn_args* a, dp_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const bool v4 = (a->C % 4 == 0) && al16(a->x, a->ldx) && al16(a->dy, a->lddy) && al16(a->dx, a->lddx) &&
                   al16(a->dx_add, a->ldadd) && al16(a->dx_add2, a->ldadd2);
-  if (v4 && slab_ok()) {
-    // per channel: gamma, beta, rstd, k1, k2, S1, S2; fixed: the two per-row partial-sum tables (RP x cwv <= 1024 floats each)
-    SlabCfg sc = slab_cfg(a->HW, a->C, a->G, 7 * sizeof(float), 2 * 1024 * sizeof(float));
-    if (sc.cw) {
-      float* fin = (float*)a->workspace;       // [N][2][C] per-image channel sums
-      gn_bwd_slab_kernel<<<dim3(sc.nslab, a->N), NT, sc.smem, st>>>(*a, sc.cw, fin);
-      if ((rc = dp_check_launch())) return rc;
-      if (a->dgamma || a->dbeta) {
-        gn_bwd_param_kernel<<<(a->C + 31) / 32, 1024, 0, st>>>(*a, fin);
-        rc = dp_check_launch();
-      }
-      return rc;
-    }
-  }
   Map mp = v4 ? make_map4(a->HW, a->C) : make_map(a->HW, a->C);
   char* ws = (char*)a->workspace;
   float* part = (float*)ws;

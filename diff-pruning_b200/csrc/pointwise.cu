@@ -137,22 +137,44 @@ __global__ void upsample_bwd_kernel(const float* __restrict__ dy, long long lddy
     dx[p * lddx + c] = acc ? dx[p * lddx + c] + s : s;
   }
 }
-__global__ void colsum_kernel(const float* __restrict__ x, long long ld, long long rows, int cols, long long seg_rows,
-                              float* __restrict__ out, long long ld_out, int acc) {
-  // grid (nseg, ceil(cols/64)), block (64, 4)
-  __shared__ float red[4][64];
-  long long seg = blockIdx.x;
-  int c = blockIdx.y * 64 + threadIdx.x;
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, long long ld, long long rows, int cols, long long seg_rows,
+                                                     float* __restrict__ out, long long ld_out, int acc, int vec) {
+  // grid (nseg, ceil(cols/64)), block (16 column quads, 16 row lanes): float4 loads (vec: 16-byte aligned rows), four independent rows in
+  // flight per thread, fixed-order tree over the 16 lanes (deterministic)
+  __shared__ float red[16][64];
+  const long long seg = blockIdx.x;
+  const int qx = threadIdx.x, ly = threadIdx.y;
+  const int c0 = blockIdx.y * 64 + qx * 4;
   long long r0 = seg * seg_rows, r1 = r0 + seg_rows;
   if (r1 > rows) r1 = rows;
-  float s = 0.f;
-  if (c < cols) for (long long r = r0 + threadIdx.y; r < r1; r += 4) s += __ldg(x + r * ld + c);
-  red[threadIdx.y][threadIdx.x] = s;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (vec && c0 + 4 <= cols) {
+#pragma unroll 4
+    for (long long r = r0 + ly; r < r1; r += 16) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * ld + c0));
+      s0 += v.x; s1 += v.y; s2 += v.z; s3 += v.w;
+    }
+  } else if (c0 < cols) {
+    for (long long r = r0 + ly; r < r1; r += 16) {
+      const float* row = x + r * ld + c0;
+      s0 += __ldg(row);
+      if (c0 + 1 < cols) s1 += __ldg(row + 1);
+      if (c0 + 2 < cols) s2 += __ldg(row + 2);
+      if (c0 + 3 < cols) s3 += __ldg(row + 3);
+    }
+  }
+  red[ly][qx * 4 + 0] = s0; red[ly][qx * 4 + 1] = s1; red[ly][qx * 4 + 2] = s2; red[ly][qx * 4 + 3] = s3;
   __syncthreads();
-  if (threadIdx.y == 0 && c < cols) {
-    float t = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
-    float* o = out + seg * ld_out + c;
-    *o = acc ? *o + t : t;
+  const int t = ly * 16 + qx;          // threads 0..63 finish one column each
+  if (t < 64) {
+    const int c = blockIdx.y * 64 + t;
+    if (c < cols) {
+      float tot = 0.f;
+#pragma unroll
+      for (int l = 0; l < 16; ++l) tot += red[l][t];
+      float* o = out + seg * ld_out + c;
+      *o = acc ? *o + tot : tot;
+    }
   }
 }
 __global__ void add_views_kernel(const float* __restrict__ a, long long lda, const float* __restrict__ b, long long ldb,
@@ -278,7 +300,8 @@ extern "C" int dp_colsum(const float* x, int64_t ld, int64_t rows, int32_t cols,
   DP_REQUIRE(x && out, DP_ERR_NULL); DP_REQUIRE(rows > 0 && cols > 0 && seg_rows > 0 && ld >= cols && ld_out >= cols, DP_ERR_SHAPE);
   long long nseg = (rows + seg_rows - 1) / seg_rows;
   DP_REQUIRE(nseg < (1ll << 31) && (cols + 63) / 64 <= 65535, DP_ERR_SHAPE);
-  colsum_kernel<<<dim3((unsigned)nseg, (cols + 63) / 64), dim3(64, 4), 0, (cudaStream_t)st>>>(x, ld, rows, cols, seg_rows, out, ld_out, acc);
+  const int vec = (((uintptr_t)x & 15) == 0 && ld % 4 == 0) ? 1 : 0;
+  colsum_kernel<<<dim3((unsigned)nseg, (cols + 63) / 64), dim3(16, 16), 0, (cudaStream_t)st>>>(x, ld, rows, cols, seg_rows, out, ld_out, acc, vec);
   return dp_check_launch();
 }
 extern "C" int dp_add_views(const float* a, int64_t lda, const float* b, int64_t ldb, float* y, int64_t ldy, int64_t rows, int32_t cols, dp_stream_t st) {

@@ -539,50 +539,73 @@ class Plan:
                 it.writes.append((tgt, lambda init, da=da: setattr(da, "flags", 1 if init else 0)))
             self._rec(steps, lib.dp_conv2d_dgrad_bf16, da, "conv dgrad", info)
 
+    GN_MAX_C = 1024      # channels one dp_groupnorm launch handles (256 threads x 4 channel slots); wider tensors are split by groups
+
     def gn(self, x: View, norm: nn.Module, out: View, silu: bool, dropout_p: float = 0.0, bf16_only: bool = False, groups: Optional[int] = None):
-        """fwd: out = dropout?(silu?(GN(x))).  Returns the fwd args (the backward reuses stats / dropout seed)."""
+        """fwd: out = dropout?(silu?(GN(x))).  Returns the forward argument structs, one per channel part (the backward reuses stats /
+        dropout seed).  Groups are independent, so a tensor wider than GN_MAX_C (the LDM's concatenated 1920-channel inputs) runs as
+        k launches over k disjoint ranges of whole groups."""
         lib = self.lib
-        a = L.GnArgs()
         G = groups if groups is not None else norm.num_groups
-        a.N, a.HW, a.C, a.G = x.N, x.H * x.W, x.C, G
-        a.eps, a.silu = norm.eps, 1 if silu else 0
-        a.x, a.ldx, a.y, a.ldy = x.ptr, x.ld, out.ptr, out.ld
+        parts = 1
+        while x.C // parts > self.GN_MAX_C:
+            parts += 1
+            while G % parts or x.C % parts or (x.C // parts) % 4:
+                parts += 1
+                if parts > G:
+                    raise NotImplementedError(f"GroupNorm over {x.C} channels in {G} groups cannot be split into parts of <= {self.GN_MAX_C}")
+        if dropout_p > 0:
+            self._n_dropout += 1
+        yb = ldyb = None
         if bf16_only:   # every consumer of `out` is a bf16 convolution: write the operand directly, skip the fp32 tensor
             yb, ldyb = self._bf_new(out.rows, out.C)
             self._bf_cache[(out.t.data_ptr(), out.off, out.C)] = (yb, ldyb)
-            a.y, a.y_bf16, a.ldyb = None, yb.data_ptr(), ldyb
-        a.gamma, a.beta = norm.weight.data_ptr(), norm.bias.data_ptr()
-        stats = torch.empty(2 * x.N * G, device=self.dev, dtype=torch.float32)
-        self._keep.append(stats)
-        a.mean, a.rstd = stats.data_ptr(), stats.data_ptr() + 4 * x.N * G
-        if dropout_p > 0:
-            self._n_dropout += 1
-            a.dropout_p = dropout_p
-            a.dropout_seed = 0x9E3779B97F4A7C15 * self._n_dropout & 0xFFFFFFFFFFFFFFFF
-            a.dropout_seed_dev = self.dropout_seed_dev.data_ptr()
-        self.scratch("gn_ws", (lib.dp_groupnorm_workspace_bytes(a.N, a.HW, a.C, a.G) + 3) // 4)
-        self._late.append(lambda a=a: setattr(a, "workspace", self.sptr("gn_ws")))
-        self._rec(self.fwd, lib.dp_groupnorm_fwd, a, "gn fwd")
-        return a
+        cp, gp = x.C // parts, G // parts
+        args = []
+        for i in range(parts):
+            c0 = i * cp
+            a = L.GnArgs()
+            a.N, a.HW, a.C, a.G = x.N, x.H * x.W, cp, gp
+            a.eps, a.silu = norm.eps, 1 if silu else 0
+            a.x, a.ldx, a.y, a.ldy = x.ptr + 4 * c0, x.ld, out.ptr + 4 * c0, out.ld
+            if bf16_only:
+                a.y, a.y_bf16, a.ldyb = None, yb.data_ptr() + 2 * c0, ldyb
+            a.gamma, a.beta = norm.weight.data_ptr() + 4 * c0, norm.bias.data_ptr() + 4 * c0
+            stats = torch.empty(2 * x.N * gp, device=self.dev, dtype=torch.float32)
+            self._keep.append(stats)
+            a.mean, a.rstd = stats.data_ptr(), stats.data_ptr() + 4 * x.N * gp
+            if dropout_p > 0:
+                a.dropout_p = dropout_p
+                a.dropout_seed = (0x9E3779B97F4A7C15 * self._n_dropout + 0x632BE59BD9B4E019 * i) & 0xFFFFFFFFFFFFFFFF
+                a.dropout_seed_dev = self.dropout_seed_dev.data_ptr()
+            self.scratch("gn_ws", (lib.dp_groupnorm_workspace_bytes(a.N, a.HW, a.C, a.G) + 3) // 4)
+            self._late.append(lambda a=a: setattr(a, "workspace", self.sptr("gn_ws")))
+            self._rec(self.fwd, lib.dp_groupnorm_fwd, a, "gn fwd")
+            args.append((a, c0))
+        return args
 
-    def gn_bwd(self, a_fwd, x: View, norm: nn.GroupNorm, dy_get: Callable[[], int], lddy: int,
+    def gn_bwd(self, a_fwd, x: View, norm: nn.Module, dy_get: Callable[[], int], lddy: int,
                add2: Optional[View] = None):
-        """x.grad (=|+=) GN(+SiLU)(+dropout) backward (+ add2); dgamma/dbeta += ."""
+        """x.grad (=|+=) GN(+SiLU)(+dropout) backward (+ add2); dgamma/dbeta += .  a_fwd: what gn() returned."""
         lib = self.lib
-        b = _copy_args(a_fwd)
         gx = self.gradof(x)
-        b.dx, b.lddx, b.lddy = gx.ptr, gx.ld, lddy
-        if add2 is not None:
-            b.dx_add2, b.ldadd2 = add2.ptr, add2.ld
-        b.dgamma, b.dbeta = self.pgrad(norm.weight), self.pgrad(norm.bias)
-        self._late.append(lambda b=b: (setattr(b, "dy", dy_get()), setattr(b, "workspace", self.sptr("gn_ws"))))
         it = self._bitem()
+        parts = []
+        for a_part, c0 in a_fwd:
+            b = _copy_args(a_part)
+            b.dx, b.lddx, b.lddy = gx.ptr + 4 * c0, gx.ld, lddy
+            if add2 is not None:
+                b.dx_add2, b.ldadd2 = add2.ptr + 4 * c0, add2.ld
+            b.dgamma, b.dbeta = self.pgrad(norm.weight) + 4 * c0, self.pgrad(norm.bias) + 4 * c0
+            self._late.append(lambda b=b, c0=c0: (setattr(b, "dy", dy_get() + 4 * c0), setattr(b, "workspace", self.sptr("gn_ws"))))
+            parts.append((b, c0))
+            self._rec(it.steps, lib.dp_groupnorm_bwd, b, "gn bwd")
 
-        def resolve(init, b=b, gx=gx):
+        def resolve(init, parts=parts, gx=gx):
             if init:
-                b.dx_add, b.ldadd = gx.ptr, gx.ld
+                for b, c0 in parts:
+                    b.dx_add, b.ldadd = gx.ptr + 4 * c0, gx.ld
         it.writes.append((x, resolve))
-        self._rec(it.steps, lib.dp_groupnorm_bwd, b, "gn bwd")
 
     # ------------------------------------------------------------------ blocks
     def resnet(self, m: ResnetBlock2D, x: View, out: View):

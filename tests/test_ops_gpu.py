@@ -330,6 +330,12 @@ def test_pointwise_ops(lib):
     o = torch.ones(4, 70, device="cuda")
     assert lib.dp_colsum(md.data_ptr(), 70, 96, 70, 24, o.data_ptr(), 70, 1, S()) == 0
     assert rel_err(o.cpu() - 1, m.view(4, 24, 70).sum(1)) < 1e-6
+    # float4 path: 16-byte aligned view of 180 columns inside a 192-float pitch (ragged last column block), 300-row segments
+    mw = torch.randn(900, 192, generator=g)
+    mwd = mw.cuda()
+    o2 = torch.zeros(3, 180, device="cuda")
+    assert lib.dp_colsum(mwd.data_ptr() + 16, 192, 900, 180, 300, o2.data_ptr(), 180, 0, S()) == 0
+    assert rel_err(o2.cpu(), mw[:, 4:184].reshape(3, 300, 180).sum(1)) < 1e-6
     # add views / scale
     a_, b_ = torch.randn(10, 7, generator=g), torch.randn(10, 7, generator=g)
     yv = torch.zeros(10, 9, device="cuda")
