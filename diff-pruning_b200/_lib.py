@@ -71,6 +71,7 @@ _SIGS = {
     "dp_conv2d_fprop": (C.c_int, [C.POINTER(ConvArgs), vp]),
     "dp_conv2d_dgrad": (C.c_int, [C.POINTER(ConvArgs), vp]),
     "dp_conv2d_wgrad": (C.c_int, [C.POINTER(ConvArgs), vp]),
+    "dp_conv_splitk_workspace_floats": (i64, [C.POINTER(ConvArgs), C.c_int]),
     "dp_conv2d_wgrad_reduce": (C.c_int, [C.POINTER(WgradReduceArgs), vp]),
     "dp_pack_conv_weight": (C.c_int, [vp, i32, i32, i32, i32, vp, vp, vp]),
     "dp_pack_conv_weight_tc": (C.c_int, [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp]),

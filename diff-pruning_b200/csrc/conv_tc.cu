@@ -44,6 +44,11 @@ struct TcParams {
   int in_stride;            // strided fprop: input pixel = in_stride * output pixel + tap offset (the A map traverses W, H with that stride)
   float alpha;              // epilogue scale of the accumulator (attention logits); 1 for convolutions
   int b_from_img;           // batched GEMM: the B tile index is the tile's image (bn == 1) instead of a filter tap
+  // split-K (persistent kernel, launches with fewer tiles than half the SMs: the 4x4 / 8x8 / 16x16 levels): work item = (tile, K split);
+  // a split walks `it_per_split` pipeline stages of the tile and writes its raw accumulator to ws[split][row][channel]
+  // (row = tile_m * 128 + TMEM lane, pitch ws_ld); splitk_epilogue_kernel sums the splits in fixed order and applies the epilogue
+  int ksplit, it_per_split;
+  float* ws; long long ws_split_stride; int ws_ld;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -337,6 +342,7 @@ constexpr int PS_THREADS = 320, PS_STAGES = 3;
 __global__ void __launch_bounds__(PS_THREADS, 1)
 conv_tc_ps_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBh,
                   const __grid_constant__ CUtensorMap mapBl, const TcParams p, const int tiles_m, const int total_tiles) {
+  const int total_work = total_tiles * p.ksplit;     // work item wi = split * total_tiles + tile (the splits of one tile run on different SMs)
   constexpr int BN = 128;
   constexpr int B_BYTES = BN * BK * 4;
   constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
@@ -385,10 +391,11 @@ conv_tc_ps_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapBh)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapBl)) : "memory");
       uint32_t g = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int wi = blockIdx.x; wi < total_work; wi += gridDim.x) {
+        const int tile = wi % total_tiles, it0 = (wi / total_tiles) * p.it_per_split, it1 = min(iters_per_tile, it0 + p.it_per_split);
         int q0, p0, n0, nblk;
         tile_coords(tile, q0, p0, n0, nblk);
-        for (int it = 0; it < iters_per_tile; ++it, ++g) {
+        for (int it = it0; it < it1; ++it, ++g) {
           const int s = g % PS_STAGES;
           const uint32_t ph = (g / PS_STAGES) & 1u;
           mbar_wait(empty_bar(s), ph ^ 1u);
@@ -405,7 +412,8 @@ conv_tc_ps_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   } else if (warp == 1) {
     if (lane == 0) {
       uint32_t g = 0, tl = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+      for (int wi = blockIdx.x; wi < total_work; wi += gridDim.x, ++tl) {
+        const int tile = wi % total_tiles, it0 = (wi / total_tiles) * p.it_per_split, it1 = min(iters_per_tile, it0 + p.it_per_split);
         const int nblk = tile / tiles_m;
         const int n_valid = min(BN, p.Nout - nblk * BN);
         const uint32_t n_instr = (uint32_t)((n_valid + 15) & ~15);
@@ -415,7 +423,7 @@ conv_tc_ps_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         mbar_wait(tempty_bar(b), (use & 1u) ^ 1u);          // epilogue has drained this accumulator set
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t acc = tmem_base + b * 256u;
-        for (int it = 0; it < iters_per_tile; ++it, ++g) {
+        for (int it = it0; it < it1; ++it, ++g) {
           const int s = g % PS_STAGES;
           const uint32_t ph = (g / PS_STAGES) & 1u;
           mbar_wait(conv_bar(s), ph);
@@ -425,7 +433,7 @@ conv_tc_ps_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           for (int k = 0; k < BK / 8; ++k) {
             const uint64_t a_hi = umma_desc(st + k * 32), a_lo = umma_desc(st + A_BYTES + k * 32);
             const uint64_t b_hi = umma_desc(st + 2 * A_BYTES + k * 32);
-            const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
+            const uint32_t first = (it > it0 || k > 0) ? 1u : 0u;
             // a_hi x [b_hi | b_lo] -> [main | correction] as ONE N=256 instruction (the two B tiles are adjacent in shared memory):
             // 8 instead of 12 instructions per stage and 5/6 of the operand reads
             umma_tf32(acc, a_hi, b_hi, idesc256, first);
@@ -440,8 +448,9 @@ conv_tc_ps_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     // ---- splitter warps 2..5
     const int ct = threadIdx.x - 64;
     uint32_t g = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      for (int it = 0; it < iters_per_tile; ++it, ++g) {
+    for (int wi = blockIdx.x; wi < total_work; wi += gridDim.x) {
+      const int it0 = (wi / total_tiles) * p.it_per_split, it1 = min(iters_per_tile, it0 + p.it_per_split);
+      for (int it = it0; it < it1; ++it, ++g) {
         const int s = g % PS_STAGES;
         const uint32_t ph = (g / PS_STAGES) & 1u;
         mbar_wait(full_bar(s), ph);
@@ -467,7 +476,8 @@ conv_tc_ps_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const int w_l = row % p.bw, h_l = (row / p.bw) % p.bh, n_l = row / (p.bw * p.bh);
     uint32_t tl = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+    for (int wi = blockIdx.x; wi < total_work; wi += gridDim.x, ++tl) {
+      const int tile = wi % total_tiles;
       int q0, p0, n0, nblk;
       tile_coords(tile, q0, p0, n0, nblk);
       const uint32_t b = tl & 1u, use = tl >> 1;
@@ -506,7 +516,13 @@ conv_tc_ps_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           mbar_arrive(tempty_bar(b));
         }
-        if (row_ok) {
+        if (p.ksplit > 1) {   // split-K: raw partial sums into this split's slab of the (padded) workspace; splitk_epilogue_kernel finishes
+          float* wrow = p.ws + (long long)(wi / total_tiles) * p.ws_split_stride + ((long long)(tile - nblk * tiles_m) * BM + row) * p.ws_ld + nblk * BN + j * 32;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4*>(wrow + i) = make_float4(__uint_as_float(v[i]) + __uint_as_float(u[i]), __uint_as_float(v[i + 1]) + __uint_as_float(u[i + 1]),
+                                                               __uint_as_float(v[i + 2]) + __uint_as_float(u[i + 2]), __uint_as_float(v[i + 3]) + __uint_as_float(u[i + 3]));
+        } else if (row_ok) {
           const int c0 = nblk * BN + j * 32;
           if (p.vec4 && c0 + 32 <= p.Nout) {
 #pragma unroll
@@ -543,6 +559,43 @@ conv_tc_ps_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// Sums the K splits of conv_tc_ps_kernel in fixed order (deterministic) and applies its epilogue: alpha, bias, per-image row, residual,
+// accumulate, the (strided) output pixel mapping.  One thread per (GEMM row, 4 channels).
+__global__ void __launch_bounds__(256) splitk_epilogue_kernel(const TcParams p, const int tiles_m) {
+  const int c4 = (p.Nout + 3) >> 2;
+  const long long total = (long long)tiles_m * BM * c4;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const long long grow = i / c4;
+    const int c = (int)(i - grow * c4) << 2;
+    const int tile_m = (int)(grow / BM), row = (int)(grow - (long long)tile_m * BM);
+    const int tw = tile_m % p.tiles_w, th = (tile_m / p.tiles_w) % p.tiles_h, tn = tile_m / (p.tiles_w * p.tiles_h);
+    const int w_l = row % p.bw, h_l = (row / p.bw) % p.bh, n_l = row / (p.bw * p.bh);
+    const int img = tn * p.bn + n_l;
+    if (img >= p.Nimg) continue;
+    const float* src = p.ws + grow * p.ws_ld + c;
+    float4 acc = *reinterpret_cast<const float4*>(src);
+    for (int ks = 1; ks < p.ksplit; ++ks) {
+      const float4 t = *reinterpret_cast<const float4*>(src + ks * p.ws_split_stride);
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    float o[4] = {p.alpha * acc.x, p.alpha * acc.y, p.alpha * acc.z, p.alpha * acc.w};
+    const long long m = ((long long)img * p.Ho + ((th * p.bh + h_l) * p.os + p.oa)) * p.Wo + ((tw * p.bw + w_l) * p.os + p.ob);
+    float* yrow = p.y + m * p.ldy;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int cc = c + e;
+      if (cc < p.Nout) {
+        float v = o[e];
+        if (p.bias) v += __ldg(p.bias + cc);
+        if (p.rowadd) v += __ldg(p.rowadd + (long long)img * p.ld_rowadd + cc);
+        if (p.residual) v += __ldg(p.residual + m * p.ld_res + cc);
+        if (p.accumulate) v += yrow[cc];
+        yrow[cc] = v;
+      }
+    }
   }
 }
 
@@ -846,19 +899,42 @@ bool pick_box(int N, int H, int W, int& bw, int& bh, int& bn) {
 }
 
 struct TapTable { int n; signed char dh[9], dw[9], wt[9]; };
+// K splits of a persistent-kernel launch with `tiles` output tiles of `iters` pipeline stages each: enough work items to fill the SMs,
+// at least 4 stages per split, none when the tiles already cover half the machine
+static int pick_ksplit(int tiles, int iters, int& it_per_split) {
+  it_per_split = iters;
+  if (tiles * 2 > g_num_sms || iters < 8) return 1;
+  int ks = g_num_sms / tiles;
+  if (ks > iters / 4) ks = iters / 4;
+  if (ks > 16) ks = 16;
+  if (ks < 2) return 1;
+  it_per_split = (iters + ks - 1) / ks;
+  return (iters + it_per_split - 1) / it_per_split;      // no empty split
+}
+
 // Shared launcher.  act: [Nimg][H][W][Kg] view (ld_act) = A operand on whose pixel grid the M tiles live; w_hi/w_lo: [T][Nout][Kg];
 // out: [Nimg][Ho][Wo][Nout] view, output pixel = (p*os+oa, q*os+ob).
+// ws: optional split-K workspace (dp_conv_splitk_workspace_floats floats); *ws_need != nullptr: only report the floats a split launch needs
 int launch_tc(const float* act, long long ld_act, int Nimg, int H, int W, int Kg, const float* w_hi, const float* w_lo, int Nout,
               int T, const TapTable& taps, int os, int oa, int ob, int Ho, int Wo, float* out, long long ld_out, const float* bias,
               const float* rowadd, long long ld_rowadd, const float* residual, long long ld_res, int accumulate, cudaStream_t st,
-              float alpha = 1.0f, int b_from_img = 0, int in_stride = 1, int ldb = -1) {
+              float alpha = 1.0f, int b_from_img = 0, int in_stride = 1, int ldb = -1, float* ws = nullptr, long long* ws_need = nullptr) {
   if (ldb < 0) ldb = wrow(Kg);   // packed conv weights; batched GEMM callers pass their own row pitch
   if (!tc_init()) return DP_ERR_UNSUPPORTED;
-  if (!w_hi || !w_lo) return DP_ERR_UNSUPPORTED;
-  if (ld_act % 4 || ((uintptr_t)act & 15) || ((uintptr_t)w_hi & 15) || ((uintptr_t)w_lo & 15)) return DP_ERR_UNSUPPORTED;
+  if (!ws_need && (!w_hi || !w_lo)) return DP_ERR_UNSUPPORTED;
+  if (!ws_need && (ld_act % 4 || ((uintptr_t)act & 15) || ((uintptr_t)w_hi & 15) || ((uintptr_t)w_lo & 15))) return DP_ERR_UNSUPPORTED;
   int bw, bh, bn;
   if (!pick_box(Nimg, H, W, bw, bh, bn)) return DP_ERR_UNSUPPORTED;
   const int BN = (Nout <= 64) ? 64 : 128;
+  if (ws_need) {     // geometry-only query
+    *ws_need = 0;
+    if (BN != 128 || b_from_img) return DP_OK;
+    const int tiles_m = (W / bw) * (H / bh) * ((Nimg + bn - 1) / bn), n_tiles = (Nout + 127) / 128;
+    int ips;
+    const int ks = pick_ksplit(tiles_m * n_tiles, taps.n * ((Kg + BK - 1) / BK), ips);
+    if (ks > 1) *ws_need = (long long)ks * tiles_m * BM * n_tiles * 128;
+    return DP_OK;
+  }
   if ((in_stride != 1 || alpha != 1.0f || b_from_img) && BN != 128) return DP_ERR_UNSUPPORTED;   // only the persistent kernel scales the tile origin / applies alpha / image-indexed B
   if (b_from_img && bn != 1) return DP_ERR_UNSUPPORTED;
   CUtensorMap mA, mBh, mBl;
@@ -893,10 +969,24 @@ int launch_tc(const float* act, long long ld_act, int Nimg, int H, int W, int Kg
   p.vec4 = (al16(out, ld_out) && al16(bias, 0) && al16(rowadd, ld_rowadd) && al16(residual, ld_res)) ? 1 : 0;
   const int tiles_n = (Nimg + bn - 1) / bn;
   dim3 grid((unsigned)(p.tiles_w * p.tiles_h * tiles_n), (unsigned)((Nout + BN - 1) / BN));
+  p.ksplit = 1; p.it_per_split = p.ntaps * p.kchunks;
   if (BN == 128) {
     const int tiles_m = (int)grid.x, total = (int)(grid.x * grid.y);
-    const int ctas = total < g_num_sms ? total : g_num_sms;
+    if (ws && !b_from_img) {
+      p.ksplit = pick_ksplit(total, p.ntaps * p.kchunks, p.it_per_split);
+      p.ws = ws; p.ws_ld = (int)grid.y * 128; p.ws_split_stride = (long long)tiles_m * BM * p.ws_ld;
+    }
+    const int work = total * p.ksplit;
+    const int ctas = work < g_num_sms ? work : g_num_sms;
     conv_tc_ps_kernel<<<ctas, PS_THREADS, PS_SMEM, st>>>(mA, mBh, mBl, p, tiles_m, total);
+    if (p.ksplit > 1) {
+      int rc = dp_check_launch();
+      if (rc) return rc;
+      const long long items = (long long)tiles_m * BM * ((Nout + 3) / 4);
+      long long blocks = (items + 255) / 256;
+      if (blocks > g_num_sms * 8) blocks = g_num_sms * 8;
+      splitk_epilogue_kernel<<<(int)blocks, 256, 0, st>>>(p, tiles_m);
+    }
   } else {
     conv_tc_ts_kernel<64><<<grid, NTHREADS, TS64_SMEM, st>>>(mA, mBh, mBl, p);
   }
@@ -1024,7 +1114,8 @@ int dp_conv2d_fprop_tc(const dp_conv_args* a, dp_stream_t stream) {
   if (a->N <= 0 || a->H <= 0 || a->W <= 0 || a->C <= 0 || a->K <= 0 || a->ldx < a->C || a->ldy < a->K) return DP_ERR_UNSUPPORTED;
   return launch_tc((const float*)a->x, a->ldx, a->N, a->P, a->Q, a->C, a->w_tc_hi, a->w_tc_lo, a->K, a->R * a->S,
                    dense_taps(a->R, a->S, a->pad_t, false), 1, 0, 0, a->P, a->Q, (float*)a->y, a->ldy, a->bias, a->rowadd,
-                   a->ld_rowadd, a->residual, a->ld_res, (a->flags & DP_CONV_ACCUMULATE) ? 1 : 0, (cudaStream_t)stream, 1.0f, 0, a->stride);
+                   a->ld_rowadd, a->residual, a->ld_res, (a->flags & DP_CONV_ACCUMULATE) ? 1 : 0, (cudaStream_t)stream, 1.0f, 0, a->stride, -1,
+                   a->workspace);
 }
 
 // stride-1 dgrad == fprop of dy with the taps flipped and the (K,C) roles swapped: dx[n,h,w,c] = sum dy[n,h+1-r,w+1-s,k] W[k,c,r,s].
@@ -1039,7 +1130,7 @@ int dp_conv2d_dgrad_tc(const dp_conv_args* a, dp_stream_t stream) {
     if (a->pad_t != (a->R - 1) / 2 || a->pad_l != a->pad_t || a->P != a->H || a->Q != a->W) return DP_ERR_UNSUPPORTED;
     return launch_tc((const float*)a->y, a->ldy, a->N, a->H, a->W, a->K, a->w_tc_hi, a->w_tc_lo, a->C, a->R * a->S,
                      dense_taps(a->R, a->S, a->pad_t, true), 1, 0, 0, a->H, a->W, (float*)a->x, a->ldx, nullptr, nullptr, 0, nullptr, 0,
-                     acc, (cudaStream_t)stream);
+                     acc, (cudaStream_t)stream, 1.0f, 0, 1, -1, a->workspace);
   }
   if (a->stride != 2 || a->R != 3 || a->H != 2 * a->P || a->W != 2 * a->Q) return DP_ERR_UNSUPPORTED;
   TapTable cls[4];
@@ -1059,10 +1150,37 @@ int dp_conv2d_dgrad_tc(const dp_conv_args* a, dp_stream_t stream) {
   for (int ca = 0; ca < 2; ++ca)
     for (int cb = 0; cb < 2; ++cb) {
       int rc = launch_tc((const float*)a->y, a->ldy, a->N, a->P, a->Q, a->K, a->w_tc_hi, a->w_tc_lo, a->C, 9, cls[ca * 2 + cb], 2, ca, cb,
-                         a->H, a->W, (float*)a->x, a->ldx, nullptr, nullptr, 0, nullptr, 0, acc, (cudaStream_t)stream);
+                         a->H, a->W, (float*)a->x, a->ldx, nullptr, nullptr, 0, nullptr, 0, acc, (cudaStream_t)stream, 1.0f, 0, 1, -1,
+                         a->workspace);
       if (rc != DP_OK) return (ca == 0 && cb == 0) ? rc : (rc == DP_ERR_UNSUPPORTED ? DP_ERR_SHAPE : rc);
     }
   return DP_OK;
+}
+
+// Floats of split-K workspace dp_conv2d_fprop (op 0) / dp_conv2d_dgrad (op 1) can use for this geometry (0: the launch fills the SMs
+// without splitting).  With a->workspace == NULL the launch simply does not split.
+extern "C" long long dp_conv_splitk_workspace_floats(const dp_conv_args* a, int op) {
+  if (!a || a->N <= 0 || a->H <= 0 || a->W <= 0 || a->C <= 0 || a->K <= 0 || a->R != a->S || (a->R != 1 && a->R != 3)) return 0;
+  long long need = 0;
+  TapTable t{};
+  if (op == 0) {
+    t.n = a->R * a->S;
+    launch_tc(nullptr, 0, a->N, a->P, a->Q, a->C, nullptr, nullptr, a->K, t.n, t, 1, 0, 0, a->P, a->Q, nullptr, 0, nullptr, nullptr, 0, nullptr, 0,
+              0, nullptr, 1.0f, 0, a->stride, -1, nullptr, &need);
+  } else if (a->stride == 1) {
+    t.n = a->R * a->S;
+    launch_tc(nullptr, 0, a->N, a->H, a->W, a->K, nullptr, nullptr, a->C, t.n, t, 1, 0, 0, a->H, a->W, nullptr, 0, nullptr, nullptr, 0, nullptr, 0,
+              0, nullptr, 1.0f, 0, 1, -1, nullptr, &need);
+  } else {
+    for (int taps = 1; taps <= 4; taps *= 2) {     // the parity classes of a stride-2 3x3 dgrad have 1 / 2 / 2 / 4 taps and run back to back
+      long long n = 0;
+      t.n = taps;
+      launch_tc(nullptr, 0, a->N, a->P, a->Q, a->K, nullptr, nullptr, a->C, 9, t, 2, 0, 0, a->H, a->W, nullptr, 0, nullptr, nullptr, 0, nullptr, 0,
+                0, nullptr, 1.0f, 0, 1, -1, nullptr, &n);
+      if (n > need) need = n;
+    }
+  }
+  return need;
 }
 
 // 32-pixel K-chunk box of an [N][H][W] grid

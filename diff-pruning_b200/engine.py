@@ -97,6 +97,7 @@ def _copy_args(a):
     return b
 
 
+SPLITK = True      # small-M fprop / dgrad launches split their K loop over idle SMs (dp_conv_splitk_workspace_floats)
 ARENA_ALIGN = 64   # floats: every parameter's slice of a flat arena starts on a 256-byte boundary
 
 
@@ -398,6 +399,7 @@ class Plan:
             self.conv_macs += out.rows * K * Cin * R * S      # 4-D-weight convolutions only: the roofline denominator
         else:
             self.lin_macs += out.rows * K * Cin               # nn.Linear layers (the LDM transformer blocks are linear-heavy)
+        self._splitk(a, 0)
         self._rec(self.fwd, lib.dp_conv2d_fprop, a, "conv fprop", info)
         if not self.need_grad:
             return
@@ -462,7 +464,16 @@ class Plan:
                 gx = self.gradof(tgt)
                 da.x, da.ldx = gx.ptr, gx.ld
                 it.writes.append((tgt, lambda init, da=da: setattr(da, "flags", 1 if init else 0)))
+            da.workspace = None
+            self._splitk(da, 1)
             self._rec(steps, lib.dp_conv2d_dgrad, da, "conv dgrad", info)
+
+    def _splitk(self, a, op: int):
+        """Small-M launches (4x4 .. 16x16 levels) split their K loop over the idle SMs: one shared scratch, bound late."""
+        need = int(self.lib.dp_conv_splitk_workspace_floats(C.byref(a), op)) if SPLITK else 0
+        if need > 0:
+            self.scratch("splitk_ws", need)
+            self._late.append(lambda a=a: setattr(a, "workspace", self.sptr("splitk_ws")))
 
     def _conv_bf16(self, x, w, b, out, stride, pad, rowadd, residual, accumulate_out, need_dx, dx_scratch, seg_out, dx_into):
         """conv() on the bf16 tensor tier: same launch structure and fp32 outputs, operands as bf16 copies."""

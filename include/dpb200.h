@@ -72,11 +72,16 @@ typedef struct dp_conv_args {
   int64_t ld_rowadd;
   const float* residual; /* fprop epilogue: + residual[pixel*ld_res + k] (resnet.py:637, attention_processor.py:466) (nullable) */
   int64_t ld_res;
-  float* workspace;    /* wgrad: [splits][K][R*S*C] fp32 partial sums */
+  float* workspace;    /* wgrad: [splits][K][R*S*C] fp32 partial sums; fprop / dgrad: optional split-K scratch
+                          (dp_conv_splitk_workspace_floats), NULL = never split */
 } dp_conv_args;
 
 int dp_conv2d_fprop(const dp_conv_args* a, dp_stream_t stream);
 int dp_conv2d_dgrad(const dp_conv_args* a, dp_stream_t stream);
+/* Launches with fewer 128-pixel x 128-channel tiles than half the SMs (the 4x4 / 8x8 / 16x16 levels of the UNets) split
+ * their K loop over the idle SMs when a->workspace holds this many floats (op 0: fprop, 1: dgrad); 0 = the geometry does not split.
+ * The splits are summed in fixed order by a second launch: results stay deterministic (ddpm_prune.py:102 accumulates across steps). */
+long long dp_conv_splitk_workspace_floats(const dp_conv_args* a, int op);
 /* writes split partial sums to a->workspace; dp_conv2d_wgrad_reduce finishes the job */
 int dp_conv2d_wgrad(const dp_conv_args* a, dp_stream_t stream);
 

@@ -35,6 +35,16 @@ def nchw(x):
     return x.permute(0, 3, 1, 2).contiguous().cpu()
 
 
+def splitk_ws(lib, args, op):
+    """Split-K scratch for a small-M fprop (op 0) / dgrad (op 1) launch, NaN-filled; None when the geometry does not split."""
+    need = lib.dp_conv_splitk_workspace_floats(C.byref(args), op)
+    if need <= 0:
+        return None
+    ws = torch.full((need,), float("nan"), device="cuda")
+    args.workspace = ws.data_ptr()
+    return ws
+
+
 CASES = [
     # N, C, H, W, K, R, ld_extra_in, ld_extra_out
     (2, 64, 16, 16, 128, 3, 0, 0),
@@ -54,7 +64,13 @@ CASES = [
     (40, 256, 16, 16, 256, 3, 0, 0),    # two N tiles x 80 pixel-tile pairs
     (10, 96, 64, 64, 96, 3, 0, 0),      # pruned width 96: N = 96 instruction, 48 weight rows from each CTA
     (40, 192, 32, 32, 179, 1, 1, 1),    # odd N (179): second N tile of 51 -> N = 64 instruction, masked store; strided views
+    # small-M launches that split their K loop over the idle SMs (dp_conv_splitk_workspace_floats > 0), as do several cases above
+    (6, 960, 8, 8, 960, 3, 0, 0),       # LDM 8x8 level: 3 x 8 tiles, 270 stages -> 6 splits of 45
+    (4, 512, 8, 8, 512, 3, 0, 0),       # LSUN 8x8 level: 2 x 4 tiles, 144 stages -> 16 splits of 9
+    (16, 256, 4, 4, 512, 3, 64, 32),    # 4x4 images, views inside wider buffers
+    (5, 179, 8, 8, 358, 3, 1, 2),       # pruned widths, odd pitches (scalar epilogue), last pixel tile half outside the batch
 ]
+MUST_SPLIT = {(6, 960, 8, 960), (4, 512, 8, 512), (16, 256, 4, 512), (5, 179, 8, 358), (8, 256, 4, 256), (3, 96, 8, 96)}
 
 
 @pytest.mark.parametrize("N,Cin,H,W,K,R,ldx,ldy", CASES)
@@ -98,6 +114,24 @@ def test_conv_tc_fprop_dgrad(lib, N, Cin, H, W, K, R, ldx, ldy):
     y_full = y_ref.detach() + rowadd[:, :, None, None] + res
     assert rel_err(nchw(yb[..., ldy:]), y_full) < 1.5e-5
     assert float((yb[..., :ldy] - 7.0).abs().sum()) == 0.0          # neighbours in the wider buffer untouched
+    # the same launch with the split-K scratch: K loop spread over idle SMs, fixed-order reduce -> same result to rounding, run to run identical
+    ws = splitk_ws(lib, a, 0)
+    assert ws is not None or (N, Cin, H, K) not in MUST_SPLIT
+    assert ws is None or N * H * W <= 74 * 128                     # never when the pixel tiles alone cover half the SMs
+    if ws is not None:
+        y_plain = yb.clone()
+        outs = []
+        for _ in range(2):
+            yb.fill_(7.0)
+            n1 = lib.dp_launch_count()
+            assert lib.dp_conv2d_fprop(C.byref(a), S()) == 0
+            on_tc = (Cin + ldx) % 4 == 0 and ldx % 4 == 0           # TMA needs 16-byte aligned views; others take the SIMT kernel (1 launch)
+            assert lib.dp_launch_count() - n1 == (2 if on_tc else 1)  # persistent kernel + split reduce / epilogue
+            outs.append(yb.clone())
+        assert torch.equal(outs[0], outs[1])
+        assert rel_err(nchw(yb[..., ldy:]), y_full) < 1.5e-5 and rel_err(yb, y_plain) < 3e-6
+        assert float((yb[..., :ldy] - 7.0).abs().sum()) == 0.0
+        assert not bool(torch.isnan(ws).all())
     # same call forced onto the SIMT path agrees (and is the exact-fp32 reference on device)
     y2 = torch.zeros(N, H, W, K, device="cuda")
     a2 = L.ConvArgs()
@@ -117,6 +151,8 @@ def test_conv_tc_fprop_dgrad(lib, N, Cin, H, W, K, R, ldx, ldy):
     d.flags = 0
     d.x, d.ldx, d.y, d.ldy = gxb.data_ptr() + 4 * ldx, Cin + ldx, gyd.data_ptr(), K
     d.w, d.w_tc_hi, d.w_tc_lo = simt_kc.data_ptr(), packs[2].data_ptr(), packs[3].data_ptr()
+    d.workspace = None
+    wsd = splitk_ws(lib, d, 1)                                      # dgrad and its accumulate run split when the geometry allows
     assert lib.dp_conv2d_dgrad(C.byref(d), S()) == 0
     print("fprop err", rel_err(nchw(yb[..., ldy:]), y_full + (y_ref.detach() - b[None, :, None, None])), "dgrad err", rel_err(nchw(gxb[..., ldx:]), xr.grad))
     assert rel_err(nchw(gxb[..., ldx:]), xr.grad) < 1.5e-5
@@ -191,6 +227,15 @@ def test_stride2_dgrad_parity_classes(lib, N, Cin, H, K):
     d.flags = 1
     assert lib.dp_conv2d_dgrad(C.byref(d), S()) == 0
     assert rel_err(nchw(gx), 2 * x.grad) < 1.5e-5
+    if splitk_ws(lib, d, 1) is not None:            # small grids: the classes with enough taps split their K loop (one more launch each)
+        gx.fill_(float("nan"))
+        d.flags = 0
+        n0 = lib.dp_launch_count()
+        assert lib.dp_conv2d_dgrad(C.byref(d), S()) == 0
+        assert 4 < lib.dp_launch_count() - n0 <= 8
+        assert rel_err(nchw(gx), x.grad) < 1.5e-5
+    else:
+        assert (N, Cin, H, K) != (4, 128, 8, 96)
 
 
 @pytest.mark.parametrize("N,Cin,H,K,pad", [(2, 64, 16, 128, 0), (4, 128, 8, 96, 0), (1, 32, 32, 160, 1), (8, 256, 8, 256, 0), (80, 128, 32, 128, 0)])
@@ -229,6 +274,12 @@ def test_stride2_fprop_wgrad_tc(lib, N, Cin, H, K, pad):
     a2.flags, a2.y = 2, y2.data_ptr()
     assert lib.dp_conv2d_fprop(C.byref(a2), S()) == 0
     assert rel_err(yd, y2) < 1.5e-5
+    if splitk_ws(lib, a, 0) is not None:           # split-K variant of the same strided launch
+        yd.fill_(float("nan"))
+        assert lib.dp_conv2d_fprop(C.byref(a), S()) == 0
+        assert rel_err(nchw(yd), y.detach()) < 1.5e-5 and rel_err(yd, y2) < 1.5e-5
+    else:
+        assert (N, Cin, H, K, pad) not in {(8, 256, 8, 256, 0), (4, 128, 8, 96, 0)}
     chunks = N * P * P // 32
     base = max(1, -(-(N * P * P) // 2048))       # keep a CTA's pixel chain short enough for the 1.5e-5 bound (TMEM accumulation truncates)
     for splits in sorted({base, min(3 * base, chunks)}):
