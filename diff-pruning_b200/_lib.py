@@ -15,7 +15,7 @@ class ConvArgs(C.Structure):
     _fields_ = [(n, i32) for n in ("N", "H", "W", "C", "P", "Q", "K", "R", "S", "stride", "pad_t", "pad_l", "flags",
                                    "splits")] + [
         ("x", vp), ("ldx", i64), ("y", vp), ("ldy", i64), ("w", vp), ("w_tc_hi", vp), ("w_tc_lo", vp), ("bias", vp), ("rowadd", vp),
-        ("ld_rowadd", i64), ("residual", vp), ("ld_res", i64), ("workspace", vp)]
+        ("ld_rowadd", i64), ("residual", vp), ("ld_res", i64), ("workspace", vp), ("amax_x", vp), ("amax_y", vp), ("amax_w", vp)]
 
 
 class WgradReduceArgs(C.Structure):
@@ -32,7 +32,7 @@ class GemmArgs(C.Structure):
 
 class GemmNtArgs(C.Structure):
     _fields_ = [("batch", i32), ("H", i32), ("W", i32), ("Kg", i32), ("N", i32), ("A", vp), ("ld_a", i64), ("b_hi", vp),
-                ("b_lo", vp), ("C", vp), ("ldc", i64), ("alpha", f32)]
+                ("b_lo", vp), ("C", vp), ("ldc", i64), ("alpha", f32), ("amax_a", vp), ("amax_b", vp)]
 
 
 class GnArgs(C.Structure):
@@ -74,7 +74,9 @@ _SIGS = {
     "dp_conv_splitk_workspace_floats": (i64, [C.POINTER(ConvArgs), C.c_int]),
     "dp_conv2d_wgrad_reduce": (C.c_int, [C.POINTER(WgradReduceArgs), vp]),
     "dp_pack_conv_weight": (C.c_int, [vp, i32, i32, i32, i32, vp, vp, vp]),
-    "dp_pack_conv_weight_tc": (C.c_int, [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp]),
+    "dp_pack_conv_weight_tc": (C.c_int, [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
+    "dp_amax": (C.c_int, [vp, i64, i64, i32, vp, vp]),
+    "dp_zero_u32": (C.c_int, [vp, i64, vp]),
     "dp_bf16_available": (C.c_int, []),
     "dp_bf16_weight_row": (C.c_int, [C.c_int]),
     "dp_bf16_wgrad_ctile": (C.c_int, [C.c_int]),
@@ -86,7 +88,7 @@ _SIGS = {
     "dp_pack_conv_weight_bf16": (C.c_int, [vp, i32, i32, i32, i32, vp, vp, vp]),
     "dp_gemm_batched": (C.c_int, [C.POINTER(GemmArgs), vp]),
     "dp_gemm_nt_tc": (C.c_int, [C.POINTER(GemmNtArgs), vp]),
-    "dp_split_tf32": (C.c_int, [vp, i64, i64, i32, i32, i32, i32, vp, vp, vp]),
+    "dp_split_h3": (C.c_int, [vp, i64, i64, i32, i32, i32, i32, vp, vp, vp, vp]),
     "dp_transpose_batched": (C.c_int, [vp, vp, i32, i32, i32, vp]),
     "dp_softmax_fwd": (C.c_int, [vp, vp, i64, i32, vp]),
     "dp_softmax_bwd": (C.c_int, [vp, vp, vp, i64, i32, vp]),

@@ -1,35 +1,43 @@
-// conv_tc.cu — tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a, fp32-grade via the 3xTF32 split:
-//     x*w ~= hi(x)*hi(w) + lo(x)*hi(w) + hi(x)*lo(w),   hi = cvt.rna.tf32(.), lo = . - hi  (exact in fp32)
-// with fp32 accumulation in TMEM (a separate correction accumulator holds the two small terms).
+// conv_tc.cu — tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a, fp32-grade through a THREE-PRODUCT SPLIT.
+//
+// fprop / dgrad / attention GEMMs (conv_tc_ps_kernel): 3 x FP16.  Every operand is scaled by a power of two taken from its "amax slot"
+// (an upper bound of max|v|: dp_amax for activations / gradients, dp_pack_conv_weight_tc for weights) so that |s*v| < 2^14, then
+//     s*v = hi + lo,   hi = fp16(s*v) (11 significant bits),  lo' = fp16((s*v - hi) * 2^11)            (22 bits kept, as 3xTF32 does)
+//     x*w ~= [hi(x)*hi(w)] + 2^-11 * [hi(x)*lo'(w) + lo'(x)*hi(w)]
+// with both brackets accumulated in fp32 in TMEM (main | correction accumulator) by tcgen05.mma kind::f16 — twice the rate of
+// kind::tf32 and half the shared-memory operand bytes, which is what bounded the 3xTF32 kernel (profiles/r02_experiments.md).  Elements
+// more than 2^28 below the tensor's maximum lose RELATIVE precision (absolute error <= 2^-50 of the maximum): below fp32 round-off of any
+// sum they take part in.
+// wgrad (wgrad_tc_kernel) still uses the 3xTF32 split of round 1:  hi = cvt.rna.tf32(.), lo = . - hi.
 //
 // GEMM view: M = N*H*W output pixels (tile of 128 = one TMA box of the NHWC activation), N = output channels, K = taps x input
-// channels, one pipeline stage = (one tap, 32 channels) = a 128-byte swizzle row.  The activation box is im2col-free: the tap shift is
-// a coordinate offset, image borders are TMA out-of-bounds zero fill, stride 2 is a TMA element stride.
+// channels, one pipeline stage = (one tap, 64 channels).  The activation box is im2col-free: the tap shift is a coordinate offset,
+// image borders are TMA out-of-bounds zero fill, stride 2 is a TMA element stride.
 //
-// Kernels (launch_tc picks by output width):
-//   conv_tc_ps_kernel     fprop / dgrad for > 64 output channels: persistent (1 CTA per SM loops over tiles), A hi/lo in shared memory,
-//                         3 x 64 KB stages, two TMEM accumulator sets (the epilogue of tile i overlaps the main loop of tile i+1), and
-//                         a_hi x [b_hi | b_lo] issued as ONE N=256 instruction into [main | correction]
-//   conv_tc_ts_kernel<64> <= 64 output channels: one tile per CTA, the split A operand goes through TENSOR MEMORY (tcgen05.st)
+// Kernels:
+//   conv_tc_ps_kernel     fprop / dgrad / NT GEMM: persistent (1 CTA per SM loops over (tile, K split) work items), the raw fp32 A boxes
+//                         are split IN PLACE into fp16 hi | lo' tiles by 4 warps, B = pre-split fp16 weights by TMA, 3 x 64 KB stages,
+//                         two TMEM accumulator sets (the epilogue of tile i overlaps the main loop of tile i+1), and
+//                         a_hi x [b_hi | b_lo'] issued as ONE N=256 instruction into [main | correction]
+//   splitk_epilogue_kernel  fixed-order sum of the K splits + the epilogue (small-M launches)
 //   wgrad_tc_kernel       weight gradient: dY^T through TMEM, X split in shared memory, both MN-major, split-K over pixels
-//   pack_tc / split_tf32 / transpose_batched helpers; dp_gemm_nt_tc runs the attention GEMMs on the persistent kernel.
-// The experimental variants measured in round 1 (SS one-tile, cluster multicast, decoupled rings, two-issuer, persistent TS, 16-float
-// stages, the clock64() stage tracer; profiles/r01_experiments.md) live on the git tag `lab-kernels-r01`, the cta_group::2 CTA-pair
-// kernel of round 2 (correct, 1.4x SLOWER: the kernel is shared-memory-bandwidth bound, profiles/r02_experiments.md) on
-// `lab-pair-kernel-r02` — neither is in the product library.
+//   pack / split / transpose helpers; dp_gemm_nt_tc runs the attention GEMMs on the persistent kernel.
+// History (git tags): `lab-kernels-r01` round-1 experimental variants; `lab-pair-kernel-r02` the cta_group::2 CTA-pair kernel (correct,
+// 1.4x slower); `tf32x3-r02` the all-3xTF32 build this file replaced.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <mutex>
 #include "common.cuh"
 
 namespace {
 
-constexpr int BM = 128, BK = 32, NTHREADS = 192;
-constexpr int A_BYTES = BM * BK * 4;  // 16 KB
+constexpr int BM = 128, BK = 64;          // pixel tile, K elements (channels of one tap) per pipeline stage
+constexpr int A_BYTES = BM * 32 * 4;      // 16 KB: one raw fp32 TMA box of 32 channels = one fp16 tile of 64 channels
 
 struct TcParams {
   int Nimg, H, W;
   int Nout;            // GEMM N (valid output channels)
-  int kchunks;         // ceil(Kg / 32)
+  int kchunks;         // ceil(Kg / 64)
   int bw, bh, bn, tiles_w, tiles_h;
   float* y; long long ldy;
   const float* bias;
@@ -44,6 +52,8 @@ struct TcParams {
   int in_stride;            // strided fprop: input pixel = in_stride * output pixel + tap offset (the A map traverses W, H with that stride)
   float alpha;              // epilogue scale of the accumulator (attention logits); 1 for convolutions
   int b_from_img;           // batched GEMM: the B tile index is the tile's image (bn == 1) instead of a filter tap
+  const uint32_t* amax_a;   // amax slots of the A operand (activation / gradient view) and of the B operand (weights / split activation)
+  const uint32_t* amax_b;
   // split-K (persistent kernel, launches with fewer tiles than half the SMs: the 4x4 / 8x8 / 16x16 levels): work item = (tile, K split);
   // a split walks `it_per_split` pipeline stages of the tile and writes its raw accumulator to ws[split][row][channel]
   // (row = tile_m * 128 + TMEM lane, pitch ws_ld); splitk_epilogue_kernel sums the splits in fixed order and applies the epilogue
@@ -90,12 +100,29 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
+}
+// amax slot -> power-of-two scale.  E = biased exponent of the bound (|v| < 2^(E-126)), clamped so that both factors are normal floats;
+// up = 2^(140-E) brings the operand below 2^14 (fp16 overflows at 65504), dn = 2^(E-140) undoes it in the epilogue.
+__device__ __forceinline__ int amax_exponent(const uint32_t* slot) {
+  const int E = (int)((__ldg(slot) >> 23) & 0xFFu);
+  return min(max(E, 14), 254);
+}
+__device__ __forceinline__ float scale_up(int E) { return __uint_as_float((uint32_t)(267 - E) << 23); }
+__device__ __forceinline__ float scale_dn(int E) { return __uint_as_float((uint32_t)(E - 13) << 23); }
+constexpr float LO_SCALE = 2048.f, LO_UNSCALE = 1.f / 2048.f;   // lo' = lo * 2^11 keeps the residual in fp16's normal range
+// two scaled values -> packed fp16 hi pair and lo' pair (low half = first element = lower address)
+__device__ __forceinline__ void split2(float a, float b, uint32_t& h, uint32_t& l) {
+  const __half2 hh = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(hh);
+  const __half2 ll = __floats2half2_rn((a - hf.x) * LO_SCALE, (b - hf.y) * LO_SCALE);
+  h = *reinterpret_cast<const uint32_t*>(&hh);
+  l = *reinterpret_cast<const uint32_t*>(&ll);
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -109,26 +136,6 @@ __device__ __forceinline__ bool elect_one() {
 }
 // A whole (converged) warp waits on a barrier (every lane polls: hardware-suspended try_wait; lane-0-only polling measured 14 % slower).
 __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
-__device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
-
-
-// ------------------------------------------------------------------------------------------------ TS kernel (<= 64 output channels)
-// The split A operand goes registers -> TENSOR MEMORY (tcgen05.st) and the MMA reads A from TMEM (tcgen05.mma [d], [a_tmem], b_desc):
-// the shared-memory pipe only carries the TMA writes, one read of the raw A tile and the B operand reads.
-// TMEM map (512 columns): [0,BN) main accumulator | [BN,2BN) correction accumulator | 2BN + 64*s: A_hi(32) A_lo(32) of stage s.
-constexpr int STAGES_TS = 4;
-constexpr int PF_DIST = 8;   // L2 prefetch distance (stages) for the activation boxes
-__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -140,200 +147,23 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
         "r"(v[30]), "r"(v[31])
       : "memory");
 }
-template <int BN>
-__global__ void __launch_bounds__(NTHREADS, 1)
-conv_tc_ts_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBh,
-                  const __grid_constant__ CUtensorMap mapBl, const TcParams p) {
-  constexpr int B_BYTES = BN * BK * 4;
-  constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;
-  constexpr uint32_t A_COL0 = 2 * BN;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t pad_to = ((raw + 1023u) & ~1023u) - raw;
-  uint8_t* smem = smem_raw + pad_to;
-  const uint32_t sbase = raw + pad_to;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES_TS * STAGE_BYTES);
-  const uint32_t bar0 = sbase + STAGES_TS * STAGE_BYTES;
-  auto full_bar = [&](int s) { return bar0 + 8u * s; };
-  auto conv_bar = [&](int s) { return bar0 + 8u * (STAGES_TS + s); };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES_TS + s); };
-  const uint32_t tmem_full_bar = bar0 + 8u * (3 * STAGES_TS);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES_TS + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES_TS; ++s) { mbar_init(full_bar(s), 1); mbar_init(conv_bar(s), 128); mbar_init(empty_bar(s), 1); }
-    mbar_init(tmem_full_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot;
-
-  const int tile_m = blockIdx.x, nblk = blockIdx.y;
-  const int tw = tile_m % p.tiles_w;
-  const int th = (tile_m / p.tiles_w) % p.tiles_h;
-  const int tn = tile_m / (p.tiles_w * p.tiles_h);
-  const int q0 = tw * p.bw, p0 = th * p.bh, n0 = tn * p.bn;
-  const int num_iters = p.ntaps * p.kchunks;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapBh)) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapBl)) : "memory");
-      for (int it = 0; it < num_iters; ++it) {
-        const int s = it % STAGES_TS;
-        const uint32_t ph = (uint32_t)(it / STAGES_TS) & 1u;
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        mbar_expect_tx(full_bar(s), A_BYTES + 2 * B_BYTES);
-        const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
-        const uint32_t st = sbase + s * STAGE_BYTES;
-        tma_load_4d(st, &mapA, full_bar(s), kc * BK, q0 + p.dw[tap], p0 + p.dh[tap], n0);
-        if (it + PF_DIST < num_iters) {   // pull the A box of a later stage into L2 while this one is in flight
-          const int it2 = it + PF_DIST, tap2 = it2 / p.kchunks, kc2 = it2 - tap2 * p.kchunks;
-          asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
-                       ::"l"(reinterpret_cast<uint64_t>(&mapA)), "r"(kc2 * BK), "r"(q0 + p.dw[tap2]), "r"(p0 + p.dh[tap2]), "r"(n0) : "memory");
-        }
-        const int tapb = p.wt[tap];
-        tma_load_3d(st + A_BYTES, &mapBh, full_bar(s), kc * BK, nblk * BN, tapb);
-        tma_load_3d(st + A_BYTES + B_BYTES, &mapBl, full_bar(s), kc * BK, nblk * BN, tapb);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // UMMA N = valid channels of this N tile rounded up to 16 (pruned widths 96 / 192 / 179 do not pay for 128)
-      const int n_valid = min(BN, p.Nout - nblk * BN);
-      const uint32_t n_instr = (uint32_t)((n_valid + 15) & ~15);
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((n_instr >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      for (int it = 0; it < num_iters; ++it) {
-        const int s = it % STAGES_TS;
-        const uint32_t ph = (uint32_t)(it / STAGES_TS) & 1u;
-        mbar_wait(conv_bar(s), ph);     // A hi/lo of this stage are in TMEM (and, transitively, B has landed in smem)
-        mbar_wait(full_bar(s), ph);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t st = sbase + s * STAGE_BYTES;
-        const uint32_t a_t = tmem_base + A_COL0 + 64u * s;
-#pragma unroll
-        for (int k = 0; k < BK / 8; ++k) {
-          const uint64_t b_hi = umma_desc(st + A_BYTES + k * 32), b_lo = umma_desc(st + A_BYTES + B_BYTES + k * 32);
-          const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
-          umma_tf32_ts(tmem_base + BN, a_t + 32 + k * 8, b_hi, idesc, first);   // lo * hi
-          umma_tf32_ts(tmem_base + BN, a_t + k * 8, b_lo, idesc, 1u);           // hi * lo
-          umma_tf32_ts(tmem_base, a_t + k * 8, b_hi, idesc, first);             // hi * hi
-        }
-        umma_commit(empty_bar(s));
-      }
-      umma_commit(tmem_full_bar);
-    }
-  } else {
-    // ---- splitter: thread <-> tile row (TMEM lane).  Row r of the 128B-swizzled tile: 16-byte chunk j sits at (j ^ (r & 7)).
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    for (int it = 0; it < num_iters; ++it) {
-      const int s = it % STAGES_TS;
-      const uint32_t ph = (uint32_t)(it / STAGES_TS) & 1u;
-      mbar_wait(full_bar(s), ph);
-      const uint8_t* arow = smem + s * STAGE_BYTES + row * 128;
-      uint32_t hi[32], lo[32];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 v = *reinterpret_cast<const float4*>(arow + ((j ^ (row & 7)) << 4));
-        const float h0 = tf32_rna(v.x), h1 = tf32_rna(v.y), h2 = tf32_rna(v.z), h3 = tf32_rna(v.w);
-        hi[4 * j + 0] = __float_as_uint(h0); hi[4 * j + 1] = __float_as_uint(h1);
-        hi[4 * j + 2] = __float_as_uint(h2); hi[4 * j + 3] = __float_as_uint(h3);
-        lo[4 * j + 0] = __float_as_uint(v.x - h0); lo[4 * j + 1] = __float_as_uint(v.y - h1);
-        lo[4 * j + 2] = __float_as_uint(v.z - h2); lo[4 * j + 3] = __float_as_uint(v.w - h3);
-      }
-      const uint32_t a_t = tmem_base + lane_addr + A_COL0 + 64u * s;
-      tmem_st32(a_t, hi);
-      tmem_st32(a_t + 32, lo);
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(conv_bar(s));
-    }
-    // ---- epilogue
-    mbar_wait(tmem_full_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int w_l = row % p.bw, h_l = (row / p.bw) % p.bh, n_l = row / (p.bw * p.bh);
-    const int img = n0 + n_l;
-    const bool row_ok = img < p.Nimg;
-    const long long m = ((long long)img * p.Ho + ((p0 + h_l) * p.os + p.oa)) * p.Wo + ((q0 + w_l) * p.os + p.ob);
-    float* yrow = p.y + m * p.ldy;
-    const float* rrow = p.residual ? p.residual + m * p.ld_res : nullptr;
-    const float* arow2 = p.rowadd ? p.rowadd + (long long)img * p.ld_rowadd : nullptr;
-#pragma unroll 1
-    for (int j = 0; j < BN / 32; ++j) {
-      uint32_t v[32], u[32];
-      const uint32_t taddr = tmem_base + lane_addr + (uint32_t)(j * 32);
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-            "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-            "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-          : "r"(taddr));
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
-            "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
-            "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
-            "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
-          : "r"(taddr + (uint32_t)BN));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (row_ok) {
-        const int c0 = nblk * BN + j * 32;
-        if (p.vec4 && c0 + 32 <= p.Nout) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            float4 o = make_float4(__uint_as_float(v[i]) + __uint_as_float(u[i]), __uint_as_float(v[i + 1]) + __uint_as_float(u[i + 1]),
-                                   __uint_as_float(v[i + 2]) + __uint_as_float(u[i + 2]), __uint_as_float(v[i + 3]) + __uint_as_float(u[i + 3]));
-            if (p.bias) { float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + i)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
-            if (arow2) { float4 t = __ldg(reinterpret_cast<const float4*>(arow2 + c0 + i)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
-            if (rrow) { float4 t = __ldg(reinterpret_cast<const float4*>(rrow + c0 + i)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
-            float4* dst = reinterpret_cast<float4*>(yrow + c0 + i);
-            if (p.accumulate) { float4 t = *dst; o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
-            *dst = o;
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int c = c0 + i;
-            if (c < p.Nout) {
-              float o = __uint_as_float(v[i]) + __uint_as_float(u[i]);
-              if (p.bias) o += __ldg(p.bias + c);
-              if (arow2) o += __ldg(arow2 + c);
-              if (rrow) o += __ldg(rrow + c);
-              if (p.accumulate) o += yrow[c];
-              yrow[c] = o;
-            }
-          }
-        }
-      }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  }
-  __syncthreads();
-  if (warp == 1) {
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
-  }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {   // caller issues tcgen05.wait::ld
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
 }
 
-
 // ------------------------------------------------------------------------------------------------ persistent variant
-// One CTA per SM loops over output tiles (static stride), 10 warps: TMA producer | MMA issuer | 4 splitter warps |
-// 4 epilogue warps.  Two accumulator sets in TMEM (2 x [main 128 | correction 128] = 512 columns) let the epilogue of tile
+// One CTA per SM loops over (tile, K split) work items (static stride), 10 warps: TMA producer | MMA issuer | 4 splitter warps |
+// 4 epilogue warps.  Stage = [A box k 0..31 -> a_hi | A box k 32..63 -> a_lo' | b_hi | b_lo'] x 16 KB: splitter thread r owns pixel row r
+// of both raw boxes (2 x 128 B, TMA 128B-swizzled), reads its 64 floats and overwrites the same two rows with the row's 64 fp16 hi
+// values and 64 fp16 lo' values in the K-major SWIZZLE_128B layout the MMA descriptors expect — no second buffer, no cross-thread hazard.  Two accumulator sets in TMEM (2 x [main 128 | correction 128] = 512 columns) let the epilogue of tile
 // i (TMEM -> registers -> global, ~20-50 % of a short-K tile) overlap the main loop of tile i+1; barrier init, TMEM
 // allocation and descriptor prefetch are paid once per SM instead of once per tile.  A operand hi/lo in shared memory
 // (SS mode; the TS variant needs the TMEM columns the second accumulator set occupies).
@@ -344,7 +174,7 @@ conv_tc_ps_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                   const __grid_constant__ CUtensorMap mapBl, const TcParams p, const int tiles_m, const int total_tiles) {
   const int total_work = total_tiles * p.ksplit;     // work item wi = split * total_tiles + tile (the splits of one tile run on different SMs)
   constexpr int BN = 128;
-  constexpr int B_BYTES = BN * BK * 4;
+  constexpr int B_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -399,10 +229,12 @@ conv_tc_ps_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           const int s = g % PS_STAGES;
           const uint32_t ph = (g / PS_STAGES) & 1u;
           mbar_wait(empty_bar(s), ph ^ 1u);
-          mbar_expect_tx(full_bar(s), A_BYTES + 2 * B_BYTES);
+          mbar_expect_tx(full_bar(s), 2 * A_BYTES + 2 * B_BYTES);
           const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
           const uint32_t st = sbase + s * STAGE_BYTES;
-          tma_load_4d(st, &mapA, full_bar(s), kc * BK, q0 * p.in_stride + p.dw[tap], p0 * p.in_stride + p.dh[tap], n0);
+          const int aw = q0 * p.in_stride + p.dw[tap], ah = p0 * p.in_stride + p.dh[tap];
+          tma_load_4d(st, &mapA, full_bar(s), kc * BK, aw, ah, n0);
+          tma_load_4d(st + A_BYTES, &mapA, full_bar(s), kc * BK + 32, aw, ah, n0);     // past the last channel: TMA zero fill
           const int tapb = p.b_from_img ? n0 : p.wt[tap];
           tma_load_3d(st + 2 * A_BYTES, &mapBh, full_bar(s), kc * BK, nblk * BN, tapb);
           tma_load_3d(st + 2 * A_BYTES + B_BYTES, &mapBl, full_bar(s), kc * BK, nblk * BN, tapb);
@@ -417,8 +249,9 @@ conv_tc_ps_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         const int nblk = tile / tiles_m;
         const int n_valid = min(BN, p.Nout - nblk * BN);
         const uint32_t n_instr = (uint32_t)((n_valid + 15) & ~15);
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((n_instr >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-        const uint32_t idesc256 = (1u << 4) | (2u << 7) | (2u << 10) | ((256u >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        // kind::f16 instruction descriptor: D = fp32 (bit 4), A / B format 0 = fp16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+        const uint32_t idesc = (1u << 4) | ((n_instr >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        const uint32_t idesc256 = (1u << 4) | ((256u >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
         const uint32_t b = tl & 1u, use = tl >> 1;
         mbar_wait(tempty_bar(b), (use & 1u) ^ 1u);          // epilogue has drained this accumulator set
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -430,14 +263,14 @@ conv_tc_ps_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t st = sbase + s * STAGE_BYTES;
 #pragma unroll
-          for (int k = 0; k < BK / 8; ++k) {
+          for (int k = 0; k < BK / 16; ++k) {      // one instruction = 16 fp16 along K = 32 bytes of every 128-byte row
             const uint64_t a_hi = umma_desc(st + k * 32), a_lo = umma_desc(st + A_BYTES + k * 32);
             const uint64_t b_hi = umma_desc(st + 2 * A_BYTES + k * 32);
             const uint32_t first = (it > it0 || k > 0) ? 1u : 0u;
-            // a_hi x [b_hi | b_lo] -> [main | correction] as ONE N=256 instruction (the two B tiles are adjacent in shared memory):
+            // a_hi x [b_hi | b_lo'] -> [main | correction] as ONE N=256 instruction (the two B tiles are adjacent in shared memory):
             // 8 instead of 12 instructions per stage and 5/6 of the operand reads
-            umma_tf32(acc, a_hi, b_hi, idesc256, first);
-            umma_tf32(acc + 128, a_lo, b_hi, idesc, 1u);
+            umma_f16(acc, a_hi, b_hi, idesc256, first);
+            umma_f16(acc + 128, a_lo, b_hi, idesc, 1u);
           }
           umma_commit(empty_bar(s));
         }
@@ -446,7 +279,9 @@ conv_tc_ps_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     }
   } else if (warp < 6) {
     // ---- splitter warps 2..5
-    const int ct = threadIdx.x - 64;
+    const int r = threadIdx.x - 64;                  // pixel row of the tile
+    const uint32_t sw = (uint32_t)(r & 7);           // 128B swizzle: 16-byte chunk c of row r sits at chunk position c ^ (r & 7)
+    const float sa = scale_up(amax_exponent(p.amax_a));
     uint32_t g = 0;
     for (int wi = blockIdx.x; wi < total_work; wi += gridDim.x) {
       const int it0 = (wi / total_tiles) * p.it_per_split, it1 = min(iters_per_tile, it0 + p.it_per_split);
@@ -454,16 +289,24 @@ conv_tc_ps_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         const int s = g % PS_STAGES;
         const uint32_t ph = (g / PS_STAGES) & 1u;
         mbar_wait(full_bar(s), ph);
-        float4* A = reinterpret_cast<float4*>(smem + s * STAGE_BYTES);
-        float4* Al = reinterpret_cast<float4*>(smem + s * STAGE_BYTES + A_BYTES);
+        uint8_t* a0 = smem + s * STAGE_BYTES + r * 128;      // row r of the k 0..31 box  -> row r of a_hi
+        uint8_t* a1 = a0 + A_BYTES;                          // row r of the k 32..63 box -> row r of a_lo'
+        float4 v[16];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int idx = ct + 128 * i;
-          float4 v = A[idx], h, l;
-          h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-          l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-          A[idx] = h;
-          Al[idx] = l;
+        for (int c = 0; c < 8; ++c) {       // a quarter warp (8 consecutive rows) touches 8 distinct chunk positions: conflict-free
+          v[c] = *reinterpret_cast<const float4*>(a0 + ((c ^ sw) << 4));
+          v[8 + c] = *reinterpret_cast<const float4*>(a1 + ((c ^ sw) << 4));
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {       // output chunk c = k 8c .. 8c+7
+          const float4 x0 = v[2 * c], x1 = v[2 * c + 1];
+          uint4 h, l;
+          split2(x0.x * sa, x0.y * sa, h.x, l.x);
+          split2(x0.z * sa, x0.w * sa, h.y, l.y);
+          split2(x1.x * sa, x1.y * sa, h.z, l.z);
+          split2(x1.z * sa, x1.w * sa, h.w, l.w);
+          *reinterpret_cast<uint4*>(a0 + ((c ^ sw) << 4)) = h;
+          *reinterpret_cast<uint4*>(a1 + ((c ^ sw) << 4)) = l;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(conv_bar(s));
@@ -475,6 +318,9 @@ conv_tc_ps_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     const int row = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const int w_l = row % p.bw, h_l = (row / p.bw) % p.bh, n_l = row / (p.bw * p.bh);
+    // accumulators hold (s_a s_b) x the products: f1 * f2 undoes the two power-of-two operand scales (two factors: their product may underflow)
+    const float f1 = scale_dn(amax_exponent(p.amax_a)), f2 = scale_dn(amax_exponent(p.amax_b)) * p.alpha;
+    auto fin = [&](uint32_t main, uint32_t corr) { return fmaf(__uint_as_float(corr), LO_UNSCALE, __uint_as_float(main)) * f1 * f2; };
     uint32_t tl = 0;
     for (int wi = blockIdx.x; wi < total_work; wi += gridDim.x, ++tl) {
       const int tile = wi % total_tiles;
@@ -520,15 +366,13 @@ conv_tc_ps_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           float* wrow = p.ws + (long long)(wi / total_tiles) * p.ws_split_stride + ((long long)(tile - nblk * tiles_m) * BM + row) * p.ws_ld + nblk * BN + j * 32;
 #pragma unroll
           for (int i = 0; i < 32; i += 4)
-            *reinterpret_cast<float4*>(wrow + i) = make_float4(__uint_as_float(v[i]) + __uint_as_float(u[i]), __uint_as_float(v[i + 1]) + __uint_as_float(u[i + 1]),
-                                                               __uint_as_float(v[i + 2]) + __uint_as_float(u[i + 2]), __uint_as_float(v[i + 3]) + __uint_as_float(u[i + 3]));
+            *reinterpret_cast<float4*>(wrow + i) = make_float4(fin(v[i], u[i]), fin(v[i + 1], u[i + 1]), fin(v[i + 2], u[i + 2]), fin(v[i + 3], u[i + 3]));
         } else if (row_ok) {
           const int c0 = nblk * BN + j * 32;
           if (p.vec4 && c0 + 32 <= p.Nout) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-              float4 o = make_float4(p.alpha * (__uint_as_float(v[i]) + __uint_as_float(u[i])), p.alpha * (__uint_as_float(v[i + 1]) + __uint_as_float(u[i + 1])),
-                                     p.alpha * (__uint_as_float(v[i + 2]) + __uint_as_float(u[i + 2])), p.alpha * (__uint_as_float(v[i + 3]) + __uint_as_float(u[i + 3])));
+              float4 o = make_float4(fin(v[i], u[i]), fin(v[i + 1], u[i + 1]), fin(v[i + 2], u[i + 2]), fin(v[i + 3], u[i + 3]));
               if (p.bias) { float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + i)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
               if (arow2) { float4 t = __ldg(reinterpret_cast<const float4*>(arow2 + c0 + i)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
               if (rrow) { float4 t = __ldg(reinterpret_cast<const float4*>(rrow + c0 + i)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
@@ -541,7 +385,7 @@ conv_tc_ps_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             for (int i = 0; i < 32; ++i) {
               const int c = c0 + i;
               if (c < p.Nout) {
-                float o = p.alpha * (__uint_as_float(v[i]) + __uint_as_float(u[i]));
+                float o = fin(v[i], u[i]);
                 if (p.bias) o += __ldg(p.bias + c);
                 if (arow2) o += __ldg(arow2 + c);
                 if (rrow) o += __ldg(rrow + c);
@@ -562,7 +406,7 @@ conv_tc_ps_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   }
 }
 
-// Sums the K splits of conv_tc_ps_kernel in fixed order (deterministic) and applies its epilogue: alpha, bias, per-image row, residual,
+// Sums the K splits of conv_tc_ps_kernel in fixed order (deterministic) and applies its epilogue: bias, per-image row, residual,
 // accumulate, the (strided) output pixel mapping.  One thread per (GEMM row, 4 channels).
 __global__ void __launch_bounds__(256) splitk_epilogue_kernel(const TcParams p, const int tiles_m) {
   const int c4 = (p.Nout + 3) >> 2;
@@ -581,7 +425,7 @@ __global__ void __launch_bounds__(256) splitk_epilogue_kernel(const TcParams p, 
       const float4 t = *reinterpret_cast<const float4*>(src + ks * p.ws_split_stride);
       acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
     }
-    float o[4] = {p.alpha * acc.x, p.alpha * acc.y, p.alpha * acc.z, p.alpha * acc.w};
+    float o[4] = {acc.x, acc.y, acc.z, acc.w};     // the splits were written with the operand scales and alpha already undone
     const long long m = ((long long)img * p.Ho + ((th * p.bh + h_l) * p.os + p.oa)) * p.Wo + ((tw * p.bw + w_l) * p.os + p.ob);
     float* yrow = p.y + m * p.ldy;
 #pragma unroll
@@ -600,41 +444,50 @@ __global__ void __launch_bounds__(256) splitk_epilogue_kernel(const TcParams p, 
 }
 
 // ------------------------------------------------------------------------------------------------ wgrad
-// dW[k][tap][c] = sum_pix dy[pix][k] * x[pix @ tap][c]  as GEMM  M = k (128), N = c (128), K = pixels.
-// Both operands are activations stored pixel-major / channel-contiguous, i.e. "MN-major" for the tensor core:
-// a stage = 32 pixels (one TMA box of the pixel grid) x 128 channels = 4 swizzle blocks [32 px][128 B] per operand
-// (MN-block stride LBO = 4 KB, 8-pixel K-group stride SBO = 1 KB).  Both tiles are split hi/lo in shared memory.
+// dW[k][tap][c] = sum_pixels dy[pix][k] * x[pix @ tap][c]: M = out-channels (128 per tile), N = in-channels of one tap (128 per tile),
+// GEMM-K = pixels, 64 per pipeline stage.  Both operands are pixel-major fp32 activations, i.e. MN-major for this product:
+//   dy: 4 raw TMA boxes [64 px][32 ch] (128-byte rows, SWIZZLE_128B).  Thread <-> out-channel reads its channel down the 64 pixel rows
+//       (a warp reads one conflict-free 128 B row per instruction), scales, splits into fp16 hi / lo' and writes 2 x 32 packed columns
+//       of TENSOR MEMORY with tcgen05.st: the MMA then runs in TS mode (A from TMEM), so dy never goes back to shared memory.
+//   x:  4 raw boxes; the boxes of channels [64j, 64j+32) and [64j+32, 64j+64) land where the fp16 blocks x_hi[j] and x_lo'[j] will live
+//       ([hi0 | hi1 | lo0 | lo1], 8 KB each = [64 px][64 ch] fp16, MN-major SWIZZLE_128B: LBO = 8 KB between 64-channel blocks, SBO = 1 KB
+//       between 8-pixel K groups); splitter thread <-> (block j, pixel row) rewrites its two 128-byte rows in place.
+//   a_hi x [x_hi | x_lo'] -> [main | correction] is ONE N=256 instruction, a_lo' x x_hi adds to the correction half.
+// TMEM: [0,128) main acc | [128,256) correction acc | 256 + 64*s: a_hi (32 columns = 64 pixels) a_lo' (32) of stage s.
 // grid = (k tiles * c tiles * taps, splits): split z covers pixel chunks [z*cps, (z+1)*cps) and writes its partial
 // tile to workspace[z][k][tap*C + c]; dp_conv2d_wgrad_reduce sums splits in fixed order (deterministic).
 struct WgParams {
   int Nimg, H, W, C, K;
   int R, S, pad;
-  int bw, bh, bn, tiles_w, tiles_h;   // 32-pixel box
+  int bw, bh, bn, tiles_w, tiles_h;   // 64-pixel box of the dy grid
   int total_chunks, chunks_per_split;
   int c_tiles;
   float* ws;
   int in_stride;             // x pixel = in_stride * dy pixel + tap offset
+  const uint32_t* amax_x; const uint32_t* amax_y;
 };
-constexpr int WG_KPIX = 32, WG_T = 128 * WG_KPIX * 4;   // one operand tile = 16 KB
+constexpr int WG_KPIX = 64;                  // pixels per stage
+constexpr int WG_BLK = WG_KPIX * 128;        // 8 KB: one raw fp32 box [64 px][32 ch] = one fp16 block [64 px][64 ch]
+constexpr int WG_STAGES = 3, WG_STAGE_BYTES = 8 * WG_BLK;
 
-// MN-major TF32 operands must use the SWIZZLE_128B_BASE32B layout (cute: Layout_MN_SW128_32B_Atom, "the only available
-// smem layout for mn-major tf32"): atoms of 4 K-rows x 128 B with the four 32-byte chunks of a row XOR-ed by (row & 3);
-// TMA writes it with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  LBO = 4096 B between 32-channel blocks, SBO = 512 B between
-// 4-pixel K-groups, layout_type = 1.
+// MN-major fp16 operand, 128B-swizzled (canonical ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units): LBO = 8 KB between 64-channel
+// blocks, SBO = 1 KB between 8-pixel K groups
 __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (256ull << 16) | (32ull << 32) | (1ull << 46) | (1ull << 61);
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(WG_BLK >> 4) << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
 }
 
-constexpr int WG_THREADS = 224;   // warps: 0 TMA | 1, 6 MMA issuers (alternate stages, see conv_tc_ps_kernel) | 2-5 splitters + epilogue
+constexpr int WG_THREADS = 224;   // warps: 0 TMA | 1, 6 MMA issuers (alternate stages) | 2-5 splitters + epilogue
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ CUtensorMap mapX, const WgParams p) {
-  // stage smem: dy raw (16 KB, read once by the splitter) | x (hi in place, 16 KB) | x_lo (16 KB)
-  // The A operand (dY^T: lane = out-channel, column = pixel) is built in TENSOR MEMORY: thread <-> out-channel reads its
-  // channel across the 32 pixel rows of the (32B-atom swizzled) tile — one conflict-free 128 B row per warp instruction —
-  // splits hi/lo and writes 2 x 32 columns with tcgen05.st; the MMA then runs in TS mode (A from TMEM, B = x MN-major smem).
-  // TMEM: [0,128) main acc | [128,256) correction acc | 256 + 64*s: A_hi(32) A_lo(32) of stage s (4 stages -> 512 columns).
-  constexpr int WSTAGES = 4;
-  constexpr int STAGE_BYTES = 3 * WG_T;
+  constexpr int WSTAGES = WG_STAGES;
+  constexpr int STAGE_BYTES = WG_STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t pad_to = ((raw + 1023u) & ~1023u) - raw;
@@ -681,98 +534,106 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant
         const int s = it % WSTAGES;
         const uint32_t ph = (uint32_t)(it / WSTAGES) & 1u;
         mbar_wait(empty_bar(s), ph ^ 1u);
-        mbar_expect_tx(full_bar(s), 2 * WG_T);
+        mbar_expect_tx(full_bar(s), 8 * WG_BLK);
         const int chunk = chunk0 + it;
         const int tw = chunk % p.tiles_w;
         const int th = (chunk / p.tiles_w) % p.tiles_h;
         const int tn = chunk / (p.tiles_w * p.tiles_h);
         const int q0 = tw * p.bw, p0 = th * p.bh, n0 = tn * p.bn;
         const uint32_t st = sbase + s * STAGE_BYTES;
+        const int xw = q0 * p.in_stride + sx - p.pad, xh = p0 * p.in_stride + r - p.pad;
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {   // 4 blocks of 32 channels = 128 channels per operand
-          tma_load_4d(st + b * 4096, &mapDy, full_bar(s), kt * 128 + b * 32, q0, p0, n0);
-          tma_load_4d(st + WG_T + b * 4096, &mapX, full_bar(s), ct * 128 + b * 32, q0 * p.in_stride + sx - p.pad, p0 * p.in_stride + r - p.pad, n0);
+        for (int b = 0; b < 4; ++b)     // dy: 4 boxes of 32 out-channels
+          tma_load_4d(st + b * WG_BLK, &mapDy, full_bar(s), kt * 128 + b * 32, q0, p0, n0);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {   // x: channels [64j, 64j+32) -> future x_hi[j], [64j+32, 64j+64) -> future x_lo'[j]
+          tma_load_4d(st + (4 + j) * WG_BLK, &mapX, full_bar(s), ct * 128 + 64 * j, xw, xh, n0);
+          tma_load_4d(st + (6 + j) * WG_BLK, &mapX, full_bar(s), ct * 128 + 64 * j + 32, xw, xh, n0);
         }
       }
     }
   } else if (warp == 1 || warp == 6) {
-    // two issuer warps on alternate stages, warp-converged with one elected lane
+    // two issuer warps on alternate stages (a lone issuer cannot run ahead of the tensor queue, profiles/r01_experiments.md),
+    // warp-converged with one elected lane
     const uint32_t mw = (warp == 1) ? 0u : 1u;
-    const uint32_t two = 1u;   // two issuer warps on alternate stages: a lone issuer cannot run ahead of the tensor queue (profiles/r01_experiments.md)
-    // B MN-major (bit 16); A comes from TMEM
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const uint32_t idesc256 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    // kind::f16, D = fp32, A = fp16 from TMEM, B = fp16 MN-major (bit 16)
+    const uint32_t idesc = (1u << 4) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc256 = (1u << 4) | (1u << 16) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     if (num_iters == 0 && mw == 0) {   // empty split: release the epilogue (it writes zeros)
       if (elect_one()) umma_commit(tmem_full_bar);
       __syncwarp();
     }
-    if (two || mw == 0) {
-      for (int it = 0; it < num_iters; ++it) {
-        if (two && ((uint32_t)it & 1u) != mw) continue;
-        const int s = it % WSTAGES;
-        const uint32_t ph = (uint32_t)(it / WSTAGES) & 1u;
-        mbar_wait_warp(conv_bar(s), ph);
-        mbar_wait_warp(full_bar(s), ph);
-        if (two && it > 0) mbar_wait_warp(iss_bar((it - 1) % WSTAGES), (uint32_t)((it - 1) / WSTAGES) & 1u);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t st = sbase + s * STAGE_BYTES;
-        const uint32_t a_t = tmem_base + 256u + 64u * s;
-        if (elect_one()) {
+    for (int it = 0; it < num_iters; ++it) {
+      if (((uint32_t)it & 1u) != mw) continue;
+      const int s = it % WSTAGES;
+      const uint32_t ph = (uint32_t)(it / WSTAGES) & 1u;
+      mbar_wait_warp(conv_bar(s), ph);
+      mbar_wait_warp(full_bar(s), ph);
+      if (it > 0) mbar_wait_warp(iss_bar((it - 1) % WSTAGES), (uint32_t)((it - 1) / WSTAGES) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t st = sbase + s * STAGE_BYTES;
+      const uint32_t a_t = tmem_base + 256u + 64u * s;
+      if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < WG_KPIX / 8; ++k) {
-            const uint64_t b_hi = umma_desc_mn(st + WG_T + k * 1024);
-            const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
-            // x_hi | x_lo are adjacent 4 x 32-channel block groups: a_hi x [x_hi | x_lo] -> [main | correction] in one N=256 instruction
-            umma_tf32_ts(tmem_base, a_t + k * 8, b_hi, idesc256, first);
-            umma_tf32_ts(tmem_base + 128, a_t + 32 + k * 8, b_hi, idesc, 1u);
-          }
-          umma_commit(empty_bar(s));
-          if (it == num_iters - 1) umma_commit(tmem_full_bar);
-          if (two) {
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(iss_bar(s));
-          }
+        for (int k = 0; k < WG_KPIX / 16; ++k) {     // 16 pixels per instruction = 8 packed TMEM columns of A, two 8-pixel groups (2 KB) of B
+          const uint64_t b_hi = umma_desc_mn(st + 4 * WG_BLK + k * 2048);
+          const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
+          umma_f16_ts(tmem_base, a_t + k * 8, b_hi, idesc256, first);
+          umma_f16_ts(tmem_base + 128, a_t + 32 + k * 8, b_hi, idesc, 1u);
         }
-        __syncwarp();
+        umma_commit(empty_bar(s));
+        if (it == num_iters - 1) umma_commit(tmem_full_bar);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(iss_bar(s));
       }
+      __syncwarp();
     }
   } else if (warp < 6) {
     const int tid = threadIdx.x - 64;
-    const int q = warp & 3;                   // TMEM lane quarter == 32-channel block of dy
+    const int q = warp & 3;                   // TMEM lane quarter == 32-channel box of dy
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const int Ey = amax_exponent(p.amax_y), Ex = amax_exponent(p.amax_x);
+    const float sy = scale_up(Ey), sxs = scale_up(Ex);
+    const int xj = tid >> 6, xp = tid & 63;   // x task of this thread: 64-channel block, pixel row
+    const uint32_t xsw = (uint32_t)(xp & 7);
     for (int it = 0; it < num_iters; ++it) {
       const int s = it % WSTAGES;
       const uint32_t ph = (uint32_t)(it / WSTAGES) & 1u;
       mbar_wait(full_bar(s), ph);
-      // (1) dy^T -> TMEM.  Block q holds channels 32q..32q+31 as rows [pix][32 ch]; SWIZZLE_128B_ATOM_32B: the 32-byte
-      //     chunk j of row `pix` sits at chunk position j ^ (pix & 3).
+      // (1) dy^T -> TMEM: channel `lane` of box q, pixel rows 0..63; 16-byte chunk j of row `pix` sits at chunk position j ^ (pix & 7)
       {
-        const uint8_t* blk = smem + s * STAGE_BYTES + q * 4096;
+        const uint8_t* blk = smem + s * STAGE_BYTES + q * WG_BLK + (lane & 3) * 4;
         uint32_t hi[32], lo[32];
 #pragma unroll
-        for (int pix = 0; pix < 32; ++pix) {
-          const int chunk = (lane >> 3) ^ (pix & 3);
-          const float v = *reinterpret_cast<const float*>(blk + pix * 128 + chunk * 32 + (lane & 7) * 4);
-          const float h = tf32_rna(v);
-          hi[pix] = __float_as_uint(h);
-          lo[pix] = __float_as_uint(v - h);
+        for (int j = 0; j < 32; ++j) {
+          const float v0 = *reinterpret_cast<const float*>(blk + (2 * j) * 128 + ((((lane >> 2) ^ (2 * j)) & 7) << 4));
+          const float v1 = *reinterpret_cast<const float*>(blk + (2 * j + 1) * 128 + ((((lane >> 2) ^ (2 * j + 1)) & 7) << 4));
+          split2(v0 * sy, v1 * sy, hi[j], lo[j]);      // TMEM column j = pixels (2j, 2j+1), low half first
         }
         const uint32_t a_t = tmem_base + lane_addr + 256u + 64u * s;
         tmem_st32(a_t, hi);
         tmem_st32(a_t + 32, lo);
       }
-      // (2) x tile: hi in place, lo to the side (elementwise, layout agnostic)
+      // (2) x: rows xp of the two raw boxes of block xj -> row xp of x_hi[xj] and of x_lo'[xj], in place
       {
-        float4* A = reinterpret_cast<float4*>(smem + s * STAGE_BYTES + WG_T);
-        float4* Al = reinterpret_cast<float4*>(smem + s * STAGE_BYTES + 2 * WG_T);
+        uint8_t* a0 = smem + s * STAGE_BYTES + (4 + xj) * WG_BLK + xp * 128;
+        uint8_t* a1 = a0 + 2 * WG_BLK;
+        float4 v[16];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int idx = tid + 128 * i;
-          float4 v = A[idx], h, l;
-          h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-          l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-          A[idx] = h;
-          Al[idx] = l;
+        for (int c = 0; c < 8; ++c) {
+          v[c] = *reinterpret_cast<const float4*>(a0 + ((c ^ xsw) << 4));
+          v[8 + c] = *reinterpret_cast<const float4*>(a1 + ((c ^ xsw) << 4));
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 x0 = v[2 * c], x1 = v[2 * c + 1];
+          uint4 h, l;
+          split2(x0.x * sxs, x0.y * sxs, h.x, l.x);
+          split2(x0.z * sxs, x0.w * sxs, h.y, l.y);
+          split2(x1.x * sxs, x1.y * sxs, h.z, l.z);
+          split2(x1.z * sxs, x1.w * sxs, h.w, l.w);
+          *reinterpret_cast<uint4*>(a0 + ((c ^ xsw) << 4)) = h;
+          *reinterpret_cast<uint4*>(a1 + ((c ^ xsw) << 4)) = l;
         }
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -782,6 +643,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant
     }
     mbar_wait(tmem_full_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const float f1 = scale_dn(Ey), f2 = scale_dn(Ex);
     const int row = q * 32 + lane;            // k_out within the tile
     const int kout = kt * 128 + row;
     const long long TC_ = (long long)T * p.C;
@@ -794,30 +656,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant
     for (int j = 0; j < 4; ++j) {
       uint32_t v[32], u[32];
       const uint32_t taddr = tmem_base + lane_addr + (uint32_t)(j * 32);
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-            "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-            "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-          : "r"(taddr));
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
-            "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
-            "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
-            "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
-          : "r"(taddr + 128u));
+      tmem_ld32(taddr, v);
+      tmem_ld32(taddr + 128u, u);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       if (kout < p.K) {
         const int c0 = ct * 128 + j * 32;
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-          if (c0 + i < p.C) wrow[c0 + i] = __uint_as_float(v[i]) + __uint_as_float(u[i]);
+          if (c0 + i < p.C) wrow[c0 + i] = fmaf(__uint_as_float(u[i]), LO_UNSCALE, __uint_as_float(v[i])) * f1 * f2;
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -837,15 +683,13 @@ EncodeTiledFn g_encode = nullptr;
 int g_tc_state = -1;  // -1 unknown, 0 unavailable, 1 ok
 int g_num_sms = 148;
 std::mutex g_tc_mutex;
-constexpr int PS_SMEM = PS_STAGES * (2 * A_BYTES + 2 * 128 * BK * 4) + 2048;
-constexpr int TS64_SMEM = STAGES_TS * (A_BYTES + 2 * 64 * BK * 4) + 2048;
-constexpr int WG_SMEM = 4 * 3 * WG_T + 2048;
+constexpr int PS_SMEM = PS_STAGES * (2 * A_BYTES + 2 * 128 * BK * 2) + 2048;
+constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + 2048;
 
-// Row length of the packed TF32 weight tiles (dp_pack_conv_weight_tc): rows longer than 32 floats are zero-padded to a multiple of 32
-// floats (128 B) so that every 32-float TMA box row is exactly one aligned 128-byte line; short rows to a multiple of 4 (the TMA
-// 16-byte stride rule).  With 16-byte padding only, pruned widths (90 / 179 input channels) ran 20-25 % slower than the next
-// multiple of 32 (scripts/time_conv_shapes.py: 90 -> 90 3x3 @32x32 167 us vs 134 us).
-static int wrow(int c) { return c > 32 ? ((c + 31) & ~31) : ((c + 3) & ~3); }
+// Row length (fp16 elements) of the packed weight tiles (dp_pack_conv_weight_tc): rows longer than 64 are zero-padded to a multiple of
+// 64 elements (128 B) so that every 64-element TMA box row is exactly one aligned 128-byte line; short rows to a multiple of 8 (the TMA
+// 16-byte stride rule).  With 16-byte padding only, pruned widths (90 / 179 input channels) ran 20-25 % slower (round 1, 3xTF32 rows).
+static int wrow(int c) { return c > 64 ? ((c + 63) & ~63) : ((c + 7) & ~7); }
 
 int tc_init() {
   std::lock_guard<std::mutex> lk(g_tc_mutex);
@@ -859,8 +703,7 @@ int tc_init() {
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
       qres != cudaDriverEntryPointSuccess) { (void)cudaGetLastError(); return 0; }
   g_encode = (EncodeTiledFn)fn;
-  bool ok = cudaFuncSetAttribute(conv_tc_ts_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS64_SMEM) == cudaSuccess;
-  ok = ok && cudaFuncSetAttribute(conv_tc_ps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PS_SMEM) == cudaSuccess;
+  bool ok = cudaFuncSetAttribute(conv_tc_ps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PS_SMEM) == cudaSuccess;
   ok = ok && cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM) == cudaSuccess;
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   if (!ok) { (void)cudaGetLastError(); return 0; }
@@ -872,9 +715,10 @@ int tc_init() {
 // pix_stride > 1 (strided convolution): dims 1 and 2 (W, H) are traversed with that element stride; the caller passes the box
 // extents in traversed elements (box = loaded pixels x pix_stride)
 bool make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-              const cuuint32_t* box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, int pix_stride = 1) {
+              const cuuint32_t* box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, int pix_stride = 1,
+              CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT32) {
   cuuint32_t estr[5] = {1, (cuuint32_t)pix_stride, (cuuint32_t)pix_stride, 1, 1};
-  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+  CUresult r = g_encode(m, dtype, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
@@ -912,30 +756,30 @@ static int pick_ksplit(int tiles, int iters, int& it_per_split) {
   return (iters + it_per_split - 1) / it_per_split;      // no empty split
 }
 
-// Shared launcher.  act: [Nimg][H][W][Kg] view (ld_act) = A operand on whose pixel grid the M tiles live; w_hi/w_lo: [T][Nout][Kg];
-// out: [Nimg][Ho][Wo][Nout] view, output pixel = (p*os+oa, q*os+ob).
+// Shared launcher.  act: [Nimg][H][W][Kg] fp32 view (ld_act) = A operand on whose pixel grid the M tiles live, amax_a its amax slot;
+// w_hi / w_lo: fp16 [T][Nout][ldb] with the scale of slot amax_b; out: [Nimg][Ho][Wo][Nout] view, output pixel = (p*os+oa, q*os+ob).
 // ws: optional split-K workspace (dp_conv_splitk_workspace_floats floats); *ws_need != nullptr: only report the floats a split launch needs
-int launch_tc(const float* act, long long ld_act, int Nimg, int H, int W, int Kg, const float* w_hi, const float* w_lo, int Nout,
-              int T, const TapTable& taps, int os, int oa, int ob, int Ho, int Wo, float* out, long long ld_out, const float* bias,
-              const float* rowadd, long long ld_rowadd, const float* residual, long long ld_res, int accumulate, cudaStream_t st,
-              float alpha = 1.0f, int b_from_img = 0, int in_stride = 1, int ldb = -1, float* ws = nullptr, long long* ws_need = nullptr) {
+int launch_tc(const float* act, long long ld_act, const uint32_t* amax_a, int Nimg, int H, int W, int Kg, const void* w_hi, const void* w_lo,
+              const uint32_t* amax_b, int Nout, int T, const TapTable& taps, int os, int oa, int ob, int Ho, int Wo, float* out,
+              long long ld_out, const float* bias, const float* rowadd, long long ld_rowadd, const float* residual, long long ld_res,
+              int accumulate, cudaStream_t st, float alpha = 1.0f, int b_from_img = 0, int in_stride = 1, int ldb = -1, float* ws = nullptr,
+              long long* ws_need = nullptr) {
   if (ldb < 0) ldb = wrow(Kg);   // packed conv weights; batched GEMM callers pass their own row pitch
   if (!tc_init()) return DP_ERR_UNSUPPORTED;
-  if (!ws_need && (!w_hi || !w_lo)) return DP_ERR_UNSUPPORTED;
+  if (!ws_need && (!w_hi || !w_lo || !amax_a || !amax_b)) return DP_ERR_UNSUPPORTED;
   if (!ws_need && (ld_act % 4 || ((uintptr_t)act & 15) || ((uintptr_t)w_hi & 15) || ((uintptr_t)w_lo & 15))) return DP_ERR_UNSUPPORTED;
   int bw, bh, bn;
   if (!pick_box(Nimg, H, W, bw, bh, bn)) return DP_ERR_UNSUPPORTED;
-  const int BN = (Nout <= 64) ? 64 : 128;
+  constexpr int BN = 128;
   if (ws_need) {     // geometry-only query
     *ws_need = 0;
-    if (BN != 128 || b_from_img) return DP_OK;
+    if (b_from_img) return DP_OK;
     const int tiles_m = (W / bw) * (H / bh) * ((Nimg + bn - 1) / bn), n_tiles = (Nout + 127) / 128;
     int ips;
     const int ks = pick_ksplit(tiles_m * n_tiles, taps.n * ((Kg + BK - 1) / BK), ips);
     if (ks > 1) *ws_need = (long long)ks * tiles_m * BM * n_tiles * 128;
     return DP_OK;
   }
-  if ((in_stride != 1 || alpha != 1.0f || b_from_img) && BN != 128) return DP_ERR_UNSUPPORTED;   // only the persistent kernel scales the tile origin / applies alpha / image-indexed B
   if (b_from_img && bn != 1) return DP_ERR_UNSUPPORTED;
   CUtensorMap mA, mBh, mBl;
   {
@@ -944,23 +788,25 @@ int launch_tc(const float* act, long long ld_act, int Nimg, int H, int W, int Kg
     const cuuint64_t Hin = (cuuint64_t)H * in_stride, Win = (cuuint64_t)W * in_stride;
     cuuint64_t dims[4] = {(cuuint64_t)Kg, Win, Hin, (cuuint64_t)Nimg};
     cuuint64_t str[3] = {(cuuint64_t)ld_act * 4, Win * ld_act * 4, Hin * Win * ld_act * 4};
-    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(bw * in_stride), (cuuint32_t)(bh * in_stride), (cuuint32_t)bn};
+    cuuint32_t box[4] = {32u, (cuuint32_t)(bw * in_stride), (cuuint32_t)(bh * in_stride), (cuuint32_t)bn};   // two boxes of 32 fp32 channels per stage
     if (box[1] > 256 || box[2] > 256) return DP_ERR_UNSUPPORTED;
     if (!make_map(&mA, act, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, in_stride)) return DP_ERR_UNSUPPORTED;
   }
   {
-    const cuuint64_t Kg4 = (cuuint64_t)ldb;
-    cuuint64_t dims[3] = {Kg4, (cuuint64_t)Nout, (cuuint64_t)T};
-    cuuint64_t str[2] = {Kg4 * 4, (cuuint64_t)Nout * Kg4 * 4};
+    const cuuint64_t Kp = (cuuint64_t)ldb;
+    if (Kp % 8) return DP_ERR_UNSUPPORTED;
+    cuuint64_t dims[3] = {Kp, (cuuint64_t)Nout, (cuuint64_t)T};
+    cuuint64_t str[2] = {Kp * 2, (cuuint64_t)Nout * Kp * 2};
     cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BN, 1};
-    if (!make_map(&mBh, w_hi, 3, dims, str, box) || !make_map(&mBl, w_lo, 3, dims, str, box)) return DP_ERR_UNSUPPORTED;
+    if (!make_map(&mBh, w_hi, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, 1, CU_TENSOR_MAP_DATA_TYPE_FLOAT16) ||
+        !make_map(&mBl, w_lo, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, 1, CU_TENSOR_MAP_DATA_TYPE_FLOAT16)) return DP_ERR_UNSUPPORTED;
   }
   TcParams p{};
   p.Nimg = Nimg; p.H = H; p.W = W; p.Nout = Nout;
   p.ntaps = taps.n;
   for (int i = 0; i < 9; ++i) { p.dh[i] = taps.dh[i]; p.dw[i] = taps.dw[i]; p.wt[i] = taps.wt[i]; }
   p.os = os; p.oa = oa; p.ob = ob; p.Ho = Ho; p.Wo = Wo;
-  p.alpha = alpha; p.b_from_img = b_from_img; p.in_stride = in_stride;
+  p.alpha = alpha; p.b_from_img = b_from_img; p.in_stride = in_stride; p.amax_a = amax_a; p.amax_b = amax_b;
   p.kchunks = (Kg + BK - 1) / BK;
   p.bw = bw; p.bh = bh; p.bn = bn; p.tiles_w = W / bw; p.tiles_h = H / bh;
   p.y = out; p.ldy = ld_out; p.bias = bias; p.rowadd = rowadd; p.ld_rowadd = ld_rowadd; p.residual = residual; p.ld_res = ld_res;
@@ -970,7 +816,7 @@ int launch_tc(const float* act, long long ld_act, int Nimg, int H, int W, int Kg
   const int tiles_n = (Nimg + bn - 1) / bn;
   dim3 grid((unsigned)(p.tiles_w * p.tiles_h * tiles_n), (unsigned)((Nout + BN - 1) / BN));
   p.ksplit = 1; p.it_per_split = p.ntaps * p.kchunks;
-  if (BN == 128) {
+  {
     const int tiles_m = (int)grid.x, total = (int)(grid.x * grid.y);
     if (ws && !b_from_img) {
       p.ksplit = pick_ksplit(total, p.ntaps * p.kchunks, p.it_per_split);
@@ -987,61 +833,61 @@ int launch_tc(const float* act, long long ld_act, int Nimg, int H, int W, int Kg
       if (blocks > g_num_sms * 8) blocks = g_num_sms * 8;
       splitk_epilogue_kernel<<<(int)blocks, 256, 0, st>>>(p, tiles_m);
     }
-  } else {
-    conv_tc_ts_kernel<64><<<grid, NTHREADS, TS64_SMEM, st>>>(mA, mBh, mBl, p);
   }
   return dp_check_launch();
 }
 
-__global__ void pack_tc_kernel(const float* __restrict__ w, int K, int C, int RS, int C4, int K4, float* __restrict__ kc_hi,
-                               float* __restrict__ kc_lo, float* __restrict__ ck_hi, float* __restrict__ ck_lo) {
-  // rows are zero-padded to C4 = dp_tc_weight_row(C), K4 = dp_tc_weight_row(K): kc [RS][K][C4], ck [RS][C][K4]
-  const long long na = (long long)RS * K * C4, nb = (long long)RS * C * K4;
+// one scaled fp32 value -> fp16 hi and lo' = (v - hi) * 2^11
+__device__ __forceinline__ void split1(float v, __half& h, __half& l) {
+  h = __float2half_rn(v);
+  l = __float2half_rn((v - __half2float(h)) * LO_SCALE);
+}
+__global__ void pack_tc_kernel(const float* __restrict__ w, int K, int C, int RS, int Cp, int Kp, __half* __restrict__ kc_hi,
+                               __half* __restrict__ kc_lo, __half* __restrict__ ck_hi, __half* __restrict__ ck_lo,
+                               const uint32_t* __restrict__ amax) {
+  // rows are zero-padded to Cp = dp_tc_weight_row(C), Kp = dp_tc_weight_row(K): kc [RS][K][Cp] (fprop B), ck [RS][C][Kp] (dgrad B)
+  const float sw = scale_up(amax_exponent(amax));
+  const long long na = (long long)RS * K * Cp, nb = (long long)RS * C * Kp;
   const long long total = na > nb ? na : nb;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    if (i < na && (kc_hi || kc_lo)) {
-      int c = (int)(i % C4); long long t = i / C4; int k = (int)(t % K), tap = (int)(t / K);
-      float v = c < C ? w[((long long)k * C + c) * RS + tap] : 0.f, h = tf32_rna(v);
-      if (kc_hi) kc_hi[i] = h;
-      if (kc_lo) kc_lo[i] = v - h;
+    if (i < na && kc_hi) {
+      int c = (int)(i % Cp); long long t = i / Cp; int k = (int)(t % K), tap = (int)(t / K);
+      split1(c < C ? w[((long long)k * C + c) * RS + tap] * sw : 0.f, kc_hi[i], kc_lo[i]);
     }
-    if (i < nb && (ck_hi || ck_lo)) {
-      int k = (int)(i % K4); long long t = i / K4; int c = (int)(t % C), tap = (int)(t / C);
-      float v = k < K ? w[((long long)k * C + c) * RS + tap] : 0.f, h = tf32_rna(v);
-      if (ck_hi) ck_hi[i] = h;
-      if (ck_lo) ck_lo[i] = v - h;
+    if (i < nb && ck_hi) {
+      int k = (int)(i % Kp); long long t = i / Kp; int c = (int)(t % C), tap = (int)(t / C);
+      split1(k < K ? w[((long long)k * C + c) * RS + tap] * sw : 0.f, ck_hi[i], ck_lo[i]);
     }
   }
 }
-__global__ void split_tf32_kernel(const float* __restrict__ x, long long ld, long long bs, int rows, int cols, int transpose,
-                                  float* __restrict__ hi, float* __restrict__ lo) {
+__global__ void split_h3_kernel(const float* __restrict__ x, long long ld, long long bs, int rows, int cols, int transpose,
+                                __half* __restrict__ hi, __half* __restrict__ lo, const uint32_t* __restrict__ amax) {
   // 32x32 tile through shared memory so both the read (along cols) and the transposed write (along rows) are coalesced
   __shared__ float t[32][33];
+  const float sx = scale_up(amax_exponent(amax));
   const int b = blockIdx.z, r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
   const float* xb = x + (long long)b * bs;
   for (int i = threadIdx.y; i < 32; i += 8) {
     int r = r0 + i, c = c0 + threadIdx.x;
-    t[i][threadIdx.x] = (r < rows && c < cols) ? xb[(long long)r * ld + c] : 0.f;
+    t[i][threadIdx.x] = (r < rows && c < cols) ? xb[(long long)r * ld + c] * sx : 0.f;
   }
   __syncthreads();
   if (!transpose) {
-    const int cols4 = (cols + 3) & ~3;
+    const int cols8 = (cols + 7) & ~7;
     for (int i = threadIdx.y; i < 32; i += 8) {
       int r = r0 + i, c = c0 + threadIdx.x;
-      if (r < rows && c < cols4) {
-        float v = t[i][threadIdx.x], h = tf32_rna(v);
-        long long o = ((long long)b * rows + r) * cols4 + c;
-        hi[o] = h; lo[o] = v - h;
+      if (r < rows && c < cols8) {
+        long long o = ((long long)b * rows + r) * cols8 + c;
+        split1(t[i][threadIdx.x], hi[o], lo[o]);
       }
     }
   } else {
-    const int rows4 = (rows + 3) & ~3;
+    const int rows8 = (rows + 7) & ~7;
     for (int i = threadIdx.y; i < 32; i += 8) {
       int c = c0 + i, r = r0 + threadIdx.x;
-      if (c < cols && r < rows4) {
-        float v = t[threadIdx.x][i], h = tf32_rna(v);
-        long long o = ((long long)b * cols + c) * rows4 + r;
-        hi[o] = h; lo[o] = v - h;
+      if (c < cols && r < rows8) {
+        long long o = ((long long)b * cols + c) * rows8 + r;
+        split1(t[threadIdx.x][i], hi[o], lo[o]);
       }
     }
   }
@@ -1063,14 +909,14 @@ __global__ void transpose_batched_kernel(const float* __restrict__ in, float* __
 }
 }  // namespace
 
-extern "C" int dp_split_tf32(const float* x, int64_t ld, int64_t bs, int32_t batch, int32_t rows, int32_t cols, int32_t transpose,
-                             float* hi, float* lo, dp_stream_t stream) {
-  DP_REQUIRE(x && hi && lo, DP_ERR_NULL);
+extern "C" int dp_split_h3(const float* x, int64_t ld, int64_t bs, int32_t batch, int32_t rows, int32_t cols, int32_t transpose,
+                           const uint32_t* amax, void* hi, void* lo, dp_stream_t stream) {
+  DP_REQUIRE(x && hi && lo && amax, DP_ERR_NULL);
   DP_REQUIRE(batch > 0 && rows > 0 && cols > 0 && ld >= cols && batch <= 65535, DP_ERR_SHAPE);
-  // the padded tail of a row (cols4 / rows4) must be covered by the grid: round the covered extent up
-  const int ccov = transpose ? cols : ((cols + 3) & ~3), rcov = transpose ? ((rows + 3) & ~3) : rows;
+  // the padded tail of a row (cols8 / rows8) must be covered by the grid: round the covered extent up
+  const int ccov = transpose ? cols : ((cols + 7) & ~7), rcov = transpose ? ((rows + 7) & ~7) : rows;
   dim3 grid((ccov + 31) / 32, (rcov + 31) / 32, batch);
-  split_tf32_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(x, ld, bs, rows, cols, transpose, hi, lo);
+  split_h3_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(x, ld, bs, rows, cols, transpose, (__half*)hi, (__half*)lo, amax);
   return dp_check_launch();
 }
 extern "C" int dp_transpose_batched(const float* in, float* out, int32_t batch, int32_t rows, int32_t cols, dp_stream_t stream) {
@@ -1086,8 +932,8 @@ extern "C" int dp_gemm_nt_tc(const dp_gemm_nt_args* a, dp_stream_t stream) {
   if (a->batch > 127) { /* the B "tap" index travels in a signed char table only for real taps; images use n0 directly */ }
   TapTable t{};
   t.n = 1;
-  return launch_tc(a->A, a->ld_a, a->batch, a->H, a->W, a->Kg, a->b_hi, a->b_lo, a->N, a->batch, t, 1, 0, 0, a->H, a->W, a->C, a->ldc,
-                   nullptr, nullptr, 0, nullptr, 0, 0, (cudaStream_t)stream, a->alpha, 1, 1, (a->Kg + 3) & ~3);
+  return launch_tc(a->A, a->ld_a, a->amax_a, a->batch, a->H, a->W, a->Kg, a->b_hi, a->b_lo, a->amax_b, a->N, a->batch, t, 1, 0, 0, a->H,
+                   a->W, a->C, a->ldc, nullptr, nullptr, 0, nullptr, 0, 0, (cudaStream_t)stream, a->alpha, 1, 1, (a->Kg + 7) & ~7);
 }
 
 int dp_tc_runtime_ok() { return tc_init(); }
@@ -1112,7 +958,7 @@ int dp_conv2d_fprop_tc(const dp_conv_args* a, dp_stream_t stream) {
   if (!((a->stride == 1 && a->pad_t == (a->R - 1) / 2) || (a->stride == 2 && a->R == 3 && (a->pad_t == 0 || a->pad_t == 1)))) return DP_ERR_UNSUPPORTED;
   if (a->P * a->stride != a->H || a->Q * a->stride != a->W) return DP_ERR_UNSUPPORTED;   // stride 2: even extents, out = in / 2 (Downsample2D, pad 1)
   if (a->N <= 0 || a->H <= 0 || a->W <= 0 || a->C <= 0 || a->K <= 0 || a->ldx < a->C || a->ldy < a->K) return DP_ERR_UNSUPPORTED;
-  return launch_tc((const float*)a->x, a->ldx, a->N, a->P, a->Q, a->C, a->w_tc_hi, a->w_tc_lo, a->K, a->R * a->S,
+  return launch_tc((const float*)a->x, a->ldx, a->amax_x, a->N, a->P, a->Q, a->C, a->w_tc_hi, a->w_tc_lo, a->amax_w, a->K, a->R * a->S,
                    dense_taps(a->R, a->S, a->pad_t, false), 1, 0, 0, a->P, a->Q, (float*)a->y, a->ldy, a->bias, a->rowadd,
                    a->ld_rowadd, a->residual, a->ld_res, (a->flags & DP_CONV_ACCUMULATE) ? 1 : 0, (cudaStream_t)stream, 1.0f, 0, a->stride, -1,
                    a->workspace);
@@ -1128,7 +974,7 @@ int dp_conv2d_dgrad_tc(const dp_conv_args* a, dp_stream_t stream) {
   const int acc = (a->flags & DP_CONV_ACCUMULATE) ? 1 : 0;
   if (a->stride == 1) {
     if (a->pad_t != (a->R - 1) / 2 || a->pad_l != a->pad_t || a->P != a->H || a->Q != a->W) return DP_ERR_UNSUPPORTED;
-    return launch_tc((const float*)a->y, a->ldy, a->N, a->H, a->W, a->K, a->w_tc_hi, a->w_tc_lo, a->C, a->R * a->S,
+    return launch_tc((const float*)a->y, a->ldy, a->amax_y, a->N, a->H, a->W, a->K, a->w_tc_hi, a->w_tc_lo, a->amax_w, a->C, a->R * a->S,
                      dense_taps(a->R, a->S, a->pad_t, true), 1, 0, 0, a->H, a->W, (float*)a->x, a->ldx, nullptr, nullptr, 0, nullptr, 0,
                      acc, (cudaStream_t)stream, 1.0f, 0, 1, -1, a->workspace);
   }
@@ -1149,7 +995,7 @@ int dp_conv2d_dgrad_tc(const dp_conv_args* a, dp_stream_t stream) {
     }
   for (int ca = 0; ca < 2; ++ca)
     for (int cb = 0; cb < 2; ++cb) {
-      int rc = launch_tc((const float*)a->y, a->ldy, a->N, a->P, a->Q, a->K, a->w_tc_hi, a->w_tc_lo, a->C, 9, cls[ca * 2 + cb], 2, ca, cb,
+      int rc = launch_tc((const float*)a->y, a->ldy, a->amax_y, a->N, a->P, a->Q, a->K, a->w_tc_hi, a->w_tc_lo, a->amax_w, a->C, 9, cls[ca * 2 + cb], 2, ca, cb,
                          a->H, a->W, (float*)a->x, a->ldx, nullptr, nullptr, 0, nullptr, 0, acc, (cudaStream_t)stream, 1.0f, 0, 1, -1,
                          a->workspace);
       if (rc != DP_OK) return (ca == 0 && cb == 0) ? rc : (rc == DP_ERR_UNSUPPORTED ? DP_ERR_SHAPE : rc);
@@ -1165,26 +1011,26 @@ extern "C" long long dp_conv_splitk_workspace_floats(const dp_conv_args* a, int 
   TapTable t{};
   if (op == 0) {
     t.n = a->R * a->S;
-    launch_tc(nullptr, 0, a->N, a->P, a->Q, a->C, nullptr, nullptr, a->K, t.n, t, 1, 0, 0, a->P, a->Q, nullptr, 0, nullptr, nullptr, 0, nullptr, 0,
-              0, nullptr, 1.0f, 0, a->stride, -1, nullptr, &need);
+    launch_tc(nullptr, 0, nullptr, a->N, a->P, a->Q, a->C, nullptr, nullptr, nullptr, a->K, t.n, t, 1, 0, 0, a->P, a->Q, nullptr, 0, nullptr,
+              nullptr, 0, nullptr, 0, 0, nullptr, 1.0f, 0, a->stride, -1, nullptr, &need);
   } else if (a->stride == 1) {
     t.n = a->R * a->S;
-    launch_tc(nullptr, 0, a->N, a->H, a->W, a->K, nullptr, nullptr, a->C, t.n, t, 1, 0, 0, a->H, a->W, nullptr, 0, nullptr, nullptr, 0, nullptr, 0,
-              0, nullptr, 1.0f, 0, 1, -1, nullptr, &need);
+    launch_tc(nullptr, 0, nullptr, a->N, a->H, a->W, a->K, nullptr, nullptr, nullptr, a->C, t.n, t, 1, 0, 0, a->H, a->W, nullptr, 0, nullptr,
+              nullptr, 0, nullptr, 0, 0, nullptr, 1.0f, 0, 1, -1, nullptr, &need);
   } else {
     for (int taps = 1; taps <= 4; taps *= 2) {     // the parity classes of a stride-2 3x3 dgrad have 1 / 2 / 2 / 4 taps and run back to back
       long long n = 0;
       t.n = taps;
-      launch_tc(nullptr, 0, a->N, a->P, a->Q, a->K, nullptr, nullptr, a->C, 9, t, 2, 0, 0, a->H, a->W, nullptr, 0, nullptr, nullptr, 0, nullptr, 0,
-                0, nullptr, 1.0f, 0, 1, -1, nullptr, &n);
+      launch_tc(nullptr, 0, nullptr, a->N, a->P, a->Q, a->K, nullptr, nullptr, nullptr, a->C, 9, t, 2, 0, 0, a->H, a->W, nullptr, 0, nullptr,
+                nullptr, 0, nullptr, 0, 0, nullptr, 1.0f, 0, 1, -1, nullptr, &n);
       if (n > need) need = n;
     }
   }
   return need;
 }
 
-// 32-pixel K-chunk box of an [N][H][W] grid
-static bool pick_box32(int H, int W, int& bw, int& bh, int& bn) {
+// 64-pixel K-chunk box of an [N][H][W] grid
+static bool pick_box64(int H, int W, int& bw, int& bh, int& bn) {
   if (W >= WG_KPIX) { if (W % WG_KPIX) return false; bw = WG_KPIX; bh = 1; bn = 1; return true; }
   if (WG_KPIX % W) return false;
   bw = W;
@@ -1205,25 +1051,28 @@ int dp_conv2d_wgrad_tc(const dp_conv_args* a, dp_stream_t stream) {
   if (a->P * a->stride != a->H || a->Q * a->stride != a->W || a->splits < 1) return DP_ERR_UNSUPPORTED;
   if (a->ldx % 4 || a->ldy % 4 || ((uintptr_t)a->x & 15) || ((uintptr_t)a->y & 15)) return DP_ERR_UNSUPPORTED;
   int bw, bh, bn;
-  if (!pick_box32(a->P, a->Q, bw, bh, bn)) return DP_ERR_UNSUPPORTED;   // 32-pixel chunks of the dy (output) grid
-  if (a->N % bn) return DP_ERR_UNSUPPORTED;   // a partial image box would be fine (OOB zero) but keep chunks exact
+  if (!a->amax_x || !a->amax_y) return DP_ERR_UNSUPPORTED;
+  if (!pick_box64(a->P, a->Q, bw, bh, bn)) return DP_ERR_UNSUPPORTED;   // 64-pixel chunks of the dy (output) grid; images past the batch
+  const int img_boxes = (a->N + bn - 1) / bn;                           // in the last box are TMA zero fill: they add nothing
   CUtensorMap mDy, mX;
   {
     cuuint64_t dims[4] = {(cuuint64_t)a->K, (cuuint64_t)a->Q, (cuuint64_t)a->P, (cuuint64_t)a->N};
     cuuint64_t str[3] = {(cuuint64_t)a->ldy * 4, (cuuint64_t)a->Q * a->ldy * 4, (cuuint64_t)a->P * a->Q * a->ldy * 4};
     cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
-    if (!make_map(&mDy, a->y, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return DP_ERR_UNSUPPORTED;
+    if (!make_map(&mDy, a->y, 4, dims, str, box)) return DP_ERR_UNSUPPORTED;
   }
   {   // x is sampled at stride * (output pixel) + tap offset: TMA element strides on W, H
     cuuint64_t dims[4] = {(cuuint64_t)a->C, (cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->N};
     cuuint64_t str[3] = {(cuuint64_t)a->ldx * 4, (cuuint64_t)a->W * a->ldx * 4, (cuuint64_t)a->H * a->W * a->ldx * 4};
     cuuint32_t box[4] = {32, (cuuint32_t)(bw * a->stride), (cuuint32_t)(bh * a->stride), (cuuint32_t)bn};
-    if (!make_map(&mX, a->x, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, a->stride)) return DP_ERR_UNSUPPORTED;
+    if (box[1] > 256 || box[2] > 256) return DP_ERR_UNSUPPORTED;
+    if (!make_map(&mX, a->x, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, a->stride)) return DP_ERR_UNSUPPORTED;
   }
   WgParams p{};
   p.Nimg = a->N; p.H = a->P; p.W = a->Q; p.C = a->C; p.K = a->K; p.R = a->R; p.S = a->S; p.pad = a->pad_t; p.in_stride = a->stride;
   p.bw = bw; p.bh = bh; p.bn = bn; p.tiles_w = a->Q / bw; p.tiles_h = a->P / bh;
-  p.total_chunks = p.tiles_w * p.tiles_h * (a->N / bn);
+  p.total_chunks = p.tiles_w * p.tiles_h * img_boxes;
+  p.amax_x = a->amax_x; p.amax_y = a->amax_y;
   p.chunks_per_split = (p.total_chunks + a->splits - 1) / a->splits;
   p.c_tiles = (a->C + 127) / 128;
   p.ws = a->workspace;
@@ -1233,15 +1082,21 @@ int dp_conv2d_wgrad_tc(const dp_conv_args* a, dp_stream_t stream) {
   return dp_check_launch();
 }
 
-extern "C" int dp_pack_conv_weight_tc(const float* w, int32_t K, int32_t C, int32_t R, int32_t S, float* kc_hi, float* kc_lo,
-                                      float* ck_hi, float* ck_lo, dp_stream_t stream) {
-  DP_REQUIRE(w, DP_ERR_NULL);
+extern "C" int dp_pack_conv_weight_tc(const float* w, int32_t K, int32_t C, int32_t R, int32_t S, void* kc_hi, void* kc_lo,
+                                      void* ck_hi, void* ck_lo, uint32_t* amax_w, dp_stream_t stream) {
+  DP_REQUIRE(w && amax_w, DP_ERR_NULL);
+  DP_REQUIRE((kc_hi == nullptr) == (kc_lo == nullptr) && (ck_hi == nullptr) == (ck_lo == nullptr), DP_ERR_NULL);
   DP_REQUIRE(K > 0 && C > 0 && R > 0 && S > 0, DP_ERR_SHAPE);
-  const int C4 = wrow(C), K4 = wrow(K);
-  long long total = (long long)R * S * ((long long)K * C4 > (long long)C * K4 ? (long long)K * C4 : (long long)C * K4);
+  // the weight's own amax slot first (one scale per tensor), then both fp16 hi / lo' orientations with that scale
+  if (cudaMemsetAsync(amax_w, 0, sizeof(uint32_t), (cudaStream_t)stream) != cudaSuccess) return dp_check_launch();
+  int rc = dp_amax(w, (int64_t)C * R * S, K, C * R * S, amax_w, stream);
+  if (rc) return rc;
+  const int Cp = wrow(C), Kp = wrow(K);
+  long long total = (long long)R * S * ((long long)K * Cp > (long long)C * Kp ? (long long)K * Cp : (long long)C * Kp);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  pack_tc_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, K, C, R * S, C4, K4, kc_hi, kc_lo, ck_hi, ck_lo);
+  pack_tc_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, K, C, R * S, Cp, Kp, (__half*)kc_hi, (__half*)kc_lo, (__half*)ck_hi, (__half*)ck_lo,
+                                                           amax_w);
   return dp_check_launch();
 }
 

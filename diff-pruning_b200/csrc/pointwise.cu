@@ -1,5 +1,6 @@
 // pointwise.cu — small fused elementwise / reduction kernels of the Taylor-scoring and finetune path.
-// All are HBM- or latency-bound; reductions are two-stage with fixed order (deterministic, no atomics).
+// All are HBM- or latency-bound; sums are two-stage with fixed order (deterministic, no atomics); the one atomic is the max of dp_amax,
+// which is order-independent.
 #include "common.cuh"
 
 namespace {
@@ -9,6 +10,32 @@ static inline int nblocks(long long n, int per_block, int cap = 148 * 32) {
   if (b < 1) b = 1;
   if (b > cap) b = cap;
   return (int)b;
+}
+
+// max |x| over a [rows][cols] view, accumulated into an "amax slot" as the BIT PATTERN of the float (monotone for non-negative floats):
+// atomicMax on it is order-independent, so the slot — and everything scaled by it — is run-to-run identical although blocks race.
+__global__ void amax_kernel(const float* __restrict__ x, long long ld, long long rows, long long cols, int vec, uint32_t* __restrict__ slot) {
+  float m = 0.f;
+  if (vec) {
+    const long long c4 = cols >> 2, total = rows * c4;
+    for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+      const long long r = i / c4;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * ld + ((i - r * c4) << 2)));
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+  } else {
+    const long long total = rows * cols;
+    for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+      const long long r = i / cols;
+      m = fmaxf(m, fabsf(__ldg(x + r * ld + (i - r * cols))));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(slot, __float_as_uint(m));
+}
+__global__ void zero_u32_kernel(uint32_t* __restrict__ p, long long n) {
+  for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) p[i] = 0u;
 }
 
 __global__ void silu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long n) {
@@ -229,6 +256,21 @@ __global__ void scale_kernel(float* __restrict__ x, long long n, float s) {
 }
 }  // namespace
 
+extern "C" int dp_amax(const float* x, int64_t ld, int64_t rows, int32_t cols, uint32_t* slot, dp_stream_t st) {
+  DP_REQUIRE(x && slot, DP_ERR_NULL);
+  DP_REQUIRE(rows > 0 && cols > 0 && ld >= cols, DP_ERR_SHAPE);
+  long long r = rows, c = cols;
+  if (ld == cols) { c = r * c; r = 1; }                     // dense: one long row
+  const int vec = ((((uintptr_t)x) & 15) == 0 && c % 4 == 0 && (r == 1 || ld % 4 == 0)) ? 1 : 0;
+  amax_kernel<<<nblocks(vec ? r * (c >> 2) : r * c, NT * 4, 148 * 8), NT, 0, (cudaStream_t)st>>>(x, ld, r, c, vec, slot);
+  return dp_check_launch();
+}
+extern "C" int dp_zero_u32(uint32_t* p, int64_t n, dp_stream_t st) {
+  DP_REQUIRE(p, DP_ERR_NULL);
+  DP_REQUIRE(n > 0, DP_ERR_SHAPE);
+  zero_u32_kernel<<<nblocks(n, NT, 148), NT, 0, (cudaStream_t)st>>>(p, n);
+  return dp_check_launch();
+}
 extern "C" int dp_silu_fwd(const float* x, float* y, int64_t n, dp_stream_t st) {
   DP_REQUIRE(x && y, DP_ERR_NULL); DP_REQUIRE(n > 0, DP_ERR_SHAPE);
   silu_fwd_kernel<<<nblocks(n, NT), NT, 0, (cudaStream_t)st>>>(x, y, n);

@@ -33,7 +33,7 @@ Step = Callable[[int], None]
 
 
 _SM_COUNT = 148            # B200; the wgrad kernel runs one CTA per SM (192 KB of shared memory)
-_WGRAD_CTA_OVERHEAD = 12   # per-CTA prologue + pipeline fill + TMEM->workspace epilogue, in units of one 32-pixel stage
+_WGRAD_CTA_OVERHEAD = 8    # per-CTA prologue + pipeline fill + TMEM->workspace epilogue, in units of one 64-pixel stage
 
 
 def _wgrad_splits(tiles, chunks, env=os.environ.get("DPB200_WGRAD_WAVES")):
@@ -97,6 +97,7 @@ def _copy_args(a):
     return b
 
 
+AMAX_SLOTS = 8192  # capacity of a plan's amax-slot arrays (one uint32 per tensor-core operand use)
 SPLITK = True      # small-M fprop / dgrad launches split their K loop over idle SMs (dp_conv_splitk_workspace_floats)
 ARENA_ALIGN = 64   # floats: every parameter's slice of a flat arena starts on a 256-byte boundary
 
@@ -146,6 +147,12 @@ class Plan:
         self._scratch_need: Dict[str, int] = {}
         self._late: List[Callable[[], None]] = []   # pointer fix-ups once scratch buffers exist
         self._packs: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
+        # amax slots of the tensor-core operands (3 x fp16 split, conv_tc.cu): activations / gradients get a slot per use, zeroed at the
+        # start of every forward and filled by dp_amax right before the launch that reads it; weights keep theirs across passes
+        self._slots = torch.zeros(AMAX_SLOTS, device=self.dev, dtype=torch.int32)
+        self._wslots = torch.zeros(AMAX_SLOTS, device=self.dev, dtype=torch.int32)
+        self._n_slots = self._n_wslots = 0
+        self._amax_fwd: Dict[Tuple[int, int, int, int], int] = {}
         self.params = [p for p in model.parameters()]
         self.dropout_seed_dev = torch.zeros(1, device=self.dev, dtype=torch.int64)
         self._n_dropout = 0
@@ -280,12 +287,30 @@ class Plan:
         if self.tc and K * Cin >= 256:
             RS = R * S
             na, nb = RS * K * lib.dp_tc_weight_row(Cin), RS * Cin * lib.dp_tc_weight_row(K)   # rows padded for aligned TMA box rows
-            tc = tuple(torch.empty(n, device=self.dev, dtype=torch.float32) for n in (na, na, nb, nb))  # kc_hi kc_lo ck_hi ck_lo
+            wslot = self._wslots.data_ptr() + 4 * self._n_wslots
+            self._n_wslots += 1
+            assert self._n_wslots <= AMAX_SLOTS
+            # fp16 kc_hi kc_lo ck_hi ck_lo + the weight's amax slot (one power-of-two scale per tensor)
+            tc = tuple(torch.empty(n, device=self.dev, dtype=torch.float16) for n in (na, na, nb, nb)) + (wslot,)
             self._rec(self.pack, lambda s, w=w, K=K, Cin=Cin, R=R, S=S, t=tc:
                       lib.dp_pack_conv_weight_tc(w.data_ptr(), K, Cin, R, S, t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(),
-                                                 t[3].data_ptr(), s), what="pack tc")
+                                                 t[3].data_ptr(), t[4], s), what="pack tc")
         self._packs[id(w)] = (wck, wkc, tc)
         return wck, wkc, tc
+
+    def _amax(self, lst: List[Step], ptr_get, ld: int, rows: int, cols: int, fwd_key=None) -> int:
+        """Records dp_amax over a [rows][cols] view into a fresh amax slot; returns the slot's device address.  Forward activations are
+        written once per pass, so consumers of the same view share one slot (fwd_key)."""
+        if fwd_key is not None and fwd_key in self._amax_fwd:
+            return self._amax_fwd[fwd_key]
+        slot = self._slots.data_ptr() + 4 * self._n_slots
+        self._n_slots += 1
+        assert self._n_slots <= AMAX_SLOTS, "raise engine.AMAX_SLOTS"
+        lib = self.lib
+        self._rec(lst, lambda s, g=ptr_get: lib.dp_amax(g(), ld, rows, cols, slot, s), what="amax")
+        if fwd_key is not None:
+            self._amax_fwd[fwd_key] = slot
+        return slot
 
     # ------------------------------------------------------------------ bf16 tier plumbing
     def _bf_geom(self, x: View, out: View, w: nn.Parameter, stride: int, pad: int) -> "L.ConvBf16Args":
@@ -381,7 +406,8 @@ class Plan:
         wck, wkc, wtc = self._packed(w)
         a = L.ConvArgs()
         if wtc is not None:
-            a.w_tc_hi, a.w_tc_lo = wtc[0].data_ptr(), wtc[1].data_ptr()
+            a.w_tc_hi, a.w_tc_lo, a.amax_w = wtc[0].data_ptr(), wtc[1].data_ptr(), wtc[4]
+            a.amax_x = self._amax(self.fwd, lambda p=x.ptr: p, x.ld, x.rows, x.C, fwd_key=(x.ptr, x.ld, x.rows, x.C))
         a.N, a.H, a.W, a.C = x.N, x.H, x.W, x.C
         a.P, a.Q, a.K = out.H, out.W, K
         a.R, a.S, a.stride, a.pad_t, a.pad_l = R, S, stride, pad, pad
@@ -428,10 +454,12 @@ class Plan:
         # 2. wgrad -> split-K workspace -> fixed-order reduce into Parameter.grad
         TC = R * S * Cin
         tiles = ((K + 127) // 128) * ((TC + 127) // 128)
-        chunks = max(1, out.rows // 32)              # tensor-core wgrad walks 32-pixel chunks
+        chunks = max(1, out.rows // 64)              # tensor-core wgrad walks 64-pixel chunks
         splits = _wgrad_splits(tiles, chunks)
         self.scratch("wgrad_ws", splits * K * TC)
+        amax_dy = self._amax(steps, dy_get, dy_ld, out.rows, K) if wtc is not None else None
         wa = _copy_args(a)
+        wa.amax_y = amax_dy
         wa.flags, wa.splits = 0, splits
         wa.ldy = dy_ld
         wa.rowadd, wa.residual, wa.bias = None, None, None
@@ -451,7 +479,7 @@ class Plan:
             da.ldy = dy_ld
             da.w = wkc.data_ptr()
             if wtc is not None:
-                da.w_tc_hi, da.w_tc_lo = wtc[2].data_ptr(), wtc[3].data_ptr()
+                da.w_tc_hi, da.w_tc_lo, da.amax_y = wtc[2].data_ptr(), wtc[3].data_ptr(), amax_dy
             da.flags = 0
             da.rowadd, da.residual, da.bias = None, None, None
             self._late.append(lambda da=da, g=dy_get: setattr(da, "y", g()))
@@ -717,19 +745,23 @@ class Plan:
           bwd : dV = P^T dO        A = P^T, B = split^T(dO)   dP = dO v^T    B = split(v)
                 dQ = dS k          B = split^T(k)            dK = dS^T q    A = dS^T, B = split^T(q)"""
         lib = self.lib
-        i4, t4 = (inner + 3) // 4 * 4, (T + 3) // 4 * 4
-        nsplit = N * max(T * i4, inner * t4)
-        self.scratch("att_hi", nsplit); self.scratch("att_lo", nsplit); self.scratch("att_t", N * T * T)
+        i8, t8 = (inner + 7) // 8 * 8, (T + 7) // 8 * 8
+        nsplit = N * max(T * i8, inner * t8)          # fp16 elements; the scratch is counted in floats
+        self.scratch("att_hi", (nsplit + 1) // 2); self.scratch("att_lo", (nsplit + 1) // 2); self.scratch("att_t", N * T * T)
         Pp = P.data_ptr()
+        bslot = [None]
 
         def split(lst, src: View, transpose: int):   # src is an [N][T][inner] activation view
-            self._rec(lst, lambda s, p=src.ptr, ld=src.ld, tr=transpose: lib.dp_split_tf32(
-                p, ld, T * ld, N, T, inner, tr, self.sptr("att_hi"), self.sptr("att_lo"), s), what="attn split")
+            slot = self._amax(lst, lambda p=src.ptr: p, src.ld, N * T, inner)
+            bslot[0] = slot
+            self._rec(lst, lambda s, p=src.ptr, ld=src.ld, tr=transpose: lib.dp_split_h3(
+                p, ld, T * ld, N, T, inner, tr, slot, self.sptr("att_hi"), self.sptr("att_lo"), s), what="attn split")
 
         def gemm(lst, A_get, ld_a, Kg, Nn, C_ptr, ldc, alpha, what):
             ga = L.GemmNtArgs()
             ga.batch, ga.H, ga.W, ga.Kg, ga.N = N, H, W, Kg, Nn
             ga.ld_a, ga.C, ga.ldc, ga.alpha = ld_a, C_ptr, ldc, alpha
+            ga.amax_a, ga.amax_b = self._amax(lst, A_get, ld_a, N * T, Kg), bslot[0]
             self._late.append(lambda ga=ga, g=A_get: (setattr(ga, "A", g()), setattr(ga, "b_hi", self.sptr("att_hi")),
                                                       setattr(ga, "b_lo", self.sptr("att_lo"))))
             self._rec(lst, lib.dp_gemm_nt_tc, ga, what)
@@ -930,6 +962,11 @@ class Plan:
                     setter(self.g_is_init(view))
                     self.g_mark(view)
         self._packed_version = None
+        if self._n_slots:       # every activation / gradient amax slot starts the pass at zero
+            zero: List[Step] = []
+            n, ptr, lib = self._n_slots, self._slots.data_ptr(), self.lib
+            self._rec(zero, lambda s: lib.dp_zero_u32(ptr, n, s), what="amax zero")
+            self.fwd.insert(0, zero[0])
         self.bwd_steps: List[Step] = [f for it in reversed(self.bwd) for f in it.steps]
 
     # ------------------------------------------------------------------ latent-diffusion UNetModel (ldm.py; BASELINE configs[4])
@@ -1198,7 +1235,8 @@ class Plan:
     def bytes_allocated(self) -> int:
         n = sum(t.numel() * t.element_size() for t in self._keep if isinstance(t, torch.Tensor))
         n += sum(t.numel() * 4 for t in self._gbuf.values()) + sum(t.numel() * 4 for t in self._scratch.values())
-        n += sum(a.numel() * (8 + (16 if tc else 0)) for a, _, tc in self._packs.values()) + self.grad_arena.numel() * 4
+        n += sum(a.numel() * 8 + (sum(t.numel() * 2 for t in tc[:4]) if tc else 0) for a, _, tc in self._packs.values())
+        n += self.grad_arena.numel() * 4
         return n
 
 

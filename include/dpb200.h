@@ -65,8 +65,8 @@ typedef struct dp_conv_args {
   void* y;             /* fprop: out  | dgrad: in (dy)  | wgrad: in (dy) */
   int64_t ldy;
   const float* w;      /* fprop: packed [R*S][C][K] | dgrad: packed [R*S][K][C] (dp_pack_conv_weight) */
-  const float* w_tc_hi; /* optional tensor-core operand (dp_pack_conv_weight_tc): TF32-rounded part, GEMM-K contiguous: */
-  const float* w_tc_lo; /*   fprop [R*S][K][C4] | dgrad [R*S][C][K4] (C4/K4 = dp_tc_weight_row); w_tc_lo = w - w_tc_hi (3xTF32 split). NULL => SIMT path */
+  const void* w_tc_hi; /* optional tensor-core operand (dp_pack_conv_weight_tc): fp16 hi part of the scaled weight, GEMM-K contiguous: */
+  const void* w_tc_lo; /*   fprop [R*S][K][Cp] | dgrad [R*S][C][Kp] (Cp/Kp = dp_tc_weight_row); w_tc_lo = fp16 scaled residual. NULL => SIMT path */
   const float* bias;   /* fprop epilogue: + bias[K]                                   (nullable) */
   const float* rowadd; /* fprop epilogue: + rowadd[n*ld_rowadd + k] per image n (temb, resnet.py:618-621) (nullable) */
   int64_t ld_rowadd;
@@ -74,6 +74,10 @@ typedef struct dp_conv_args {
   int64_t ld_res;
   float* workspace;    /* wgrad: [splits][K][R*S*C] fp32 partial sums; fprop / dgrad: optional split-K scratch
                           (dp_conv_splitk_workspace_floats), NULL = never split */
+  /* Tensor-core path (3 x fp16 split, conv_tc.cu): "amax slots" = one device uint32 each holding the bit pattern of an upper bound of
+   * max|v| over the operand — amax_x for x, amax_y for y / dy (both accumulated by dp_amax), amax_w for the packed weight
+   * (written by dp_pack_conv_weight_tc).  A NULL slot sends the launch to the exact-fp32 SIMT kernel. */
+  const uint32_t* amax_x; const uint32_t* amax_y; const uint32_t* amax_w;
 } dp_conv_args;
 
 int dp_conv2d_fprop(const dp_conv_args* a, dp_stream_t stream);
@@ -104,14 +108,19 @@ int dp_conv2d_wgrad_reduce(const dp_wgrad_reduce_args* a, dp_stream_t stream);
 int dp_pack_conv_weight(const float* w_oihw, int32_t K, int32_t C, int32_t R, int32_t S, float* w_ck, float* w_kc,
                         dp_stream_t stream);
 
-/* 3xTF32 operands for the tcgen05 path: hi = cvt.rna.tf32(w), lo = w - hi (exact), each in both K-major forms:
- *   kc_* [R*S][K][C4] (fprop B operand, GEMM-K = C)   ck_* [R*S][C][K4] (dgrad B operand, GEMM-K = K), where
- *   C4 = dp_tc_weight_row(C), K4 = dp_tc_weight_row(K) are the zero-padded row lengths: a multiple of 32 floats for rows longer
- *   than 32 (every 32-float TMA box row is then one aligned 128-byte line — pruned widths such as 90 / 179 / 358 otherwise run
- *   20-25 % slower), else a multiple of 4 (TMA needs 16-byte row pitches).  Any output may be NULL. */
+/* Operands of the tcgen05 path (3 x fp16 split, fp32-grade).  With s = the power of two that brings the tensor's max|w| below 2^14:
+ *   hi = fp16(s*w), lo = fp16((s*w - hi) * 2^11), each in both K-major forms:
+ *   kc_* [R*S][K][Cp] (fprop B operand, GEMM-K = C)   ck_* [R*S][C][Kp] (dgrad B operand, GEMM-K = K), where
+ *   Cp = dp_tc_weight_row(C), Kp = dp_tc_weight_row(K) are the zero-padded row lengths in fp16 ELEMENTS: a multiple of 64 for rows
+ *   longer than 64 (every 64-element TMA box row is then one aligned 128-byte line), else a multiple of 8 (16-byte row pitches).
+ *   amax_w receives the weight's amax slot (the kernels derive s from it).  A NULL kc pair or ck pair is skipped. */
 int dp_tc_weight_row(int channels);
-int dp_pack_conv_weight_tc(const float* w_oihw, int32_t K, int32_t C, int32_t R, int32_t S, float* kc_hi, float* kc_lo,
-                           float* ck_hi, float* ck_lo, dp_stream_t stream);
+int dp_pack_conv_weight_tc(const float* w_oihw, int32_t K, int32_t C, int32_t R, int32_t S, void* kc_hi, void* kc_lo,
+                           void* ck_hi, void* ck_lo, uint32_t* amax_w, dp_stream_t stream);
+/* amax slots.  dp_amax: *slot = max(*slot, bits(max |x[r*ld + c]|)) over a [rows][cols] fp32 view (atomicMax on the bit pattern of
+ * |v|, which is order-independent: results are run-to-run identical); callers zero their slots once per pass with dp_zero_u32. */
+int dp_amax(const float* x, int64_t ld, int64_t rows, int32_t cols, uint32_t* slot, dp_stream_t stream);
+int dp_zero_u32(uint32_t* p, int64_t n, dp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * bf16 tensor tier (conv_bf16.cu): tcgen05.mma kind::f16 on BF16 operands, fp32 accumulation — what torch.autocast(bfloat16) makes of
@@ -164,21 +173,23 @@ int dp_gemm_batched(const dp_gemm_args* a, dp_stream_t stream);
 /* Tensor-core batched GEMM for the attention core (attention_processor.py:341-357,452 and its backward):
  *   C[b][m][n] = alpha * sum_k A[b][m][k] * B[b][n][k]          (both operands K-contiguous, "NT")
  * A: [batch][H*W][Kg] fp32 view (pixel stride ld_a) — the token grid is the image grid so a 128-token tile is a TMA box;
- * B: given pre-split (dp_split_tf32) as b_hi/b_lo [batch][N][Kg4]; C: [batch][H*W][N] view (ldc).  Runs on the persistent
- * tcgen05 3xTF32 kernel; returns DP_ERR_UNSUPPORTED when the shape is not eligible (H*W % 128, alignment) so the caller can
- * fall back to dp_gemm_batched. */
+ * B: given pre-split (dp_split_h3) as fp16 b_hi/b_lo [batch][N][Kg8]; C: [batch][H*W][N] view (ldc); amax_a / amax_b: amax slots of
+ * A and of the matrix B was split from.  Runs on the persistent tcgen05 kernel; returns DP_ERR_UNSUPPORTED when the shape is not
+ * eligible (H*W % 128, alignment) so the caller can fall back to dp_gemm_batched. */
 typedef struct dp_gemm_nt_args {
   int32_t batch, H, W, Kg, N;
   const float* A; int64_t ld_a;
-  const float* b_hi; const float* b_lo;
+  const void* b_hi; const void* b_lo;
   float* C; int64_t ldc;
   float alpha;
+  const uint32_t* amax_a; const uint32_t* amax_b;
 } dp_gemm_nt_args;
 int dp_gemm_nt_tc(const dp_gemm_nt_args* a, dp_stream_t stream);
-/* hi = cvt.rna.tf32(x), lo = x - hi of a batched [rows][cols] fp32 matrix (row stride ld, batch stride bs), written densely as
- * [batch][rows][cols4] — or transposed, [batch][cols][rows4] — with the row length rounded up to 4 floats (zero pad). */
-int dp_split_tf32(const float* x, int64_t ld, int64_t bs, int32_t batch, int32_t rows, int32_t cols, int32_t transpose, float* hi,
-                  float* lo, dp_stream_t stream);
+/* fp16 hi / lo' split (see dp_pack_conv_weight_tc) of a batched [rows][cols] fp32 matrix (row stride ld, batch stride bs) with the scale of
+ * its amax slot (dp_amax over the same matrix must have run), written densely as [batch][rows][cols8] — or transposed,
+ * [batch][cols][rows8] — with the row length rounded up to 8 elements (zero pad). */
+int dp_split_h3(const float* x, int64_t ld, int64_t bs, int32_t batch, int32_t rows, int32_t cols, int32_t transpose,
+                const uint32_t* amax, void* hi, void* lo, dp_stream_t stream);
 /* out[b][c][r] = in[b][r][c] for dense [batch][rows][cols] */
 int dp_transpose_batched(const float* in, float* out, int32_t batch, int32_t rows, int32_t cols, dp_stream_t stream);
 

@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     from diff_pruning_b200 import _lib as L
-    assert ctypes.sizeof(L.ConvArgs) == 56 + 13 * 8
+    assert ctypes.sizeof(L.ConvArgs) == 56 + 16 * 8
     assert ctypes.sizeof(L.GemmArgs) == 16 + 11 * 8 + 8
     assert ctypes.sizeof(L.WgradReduceArgs) == 24 + 5 * 8
     assert ctypes.sizeof(L.TaylorArgs) == 16 + 8 * 8
@@ -124,10 +124,10 @@ def test_wgrad_split_count_respects_wave_boundaries():
 
 
 def test_tc_weight_row_padding_rule():
-    """dp_tc_weight_row (host function of the C-ABI): 16-byte multiples up to 32 channels, 128-byte multiples beyond."""
+    """dp_tc_weight_row (host function of the C-ABI), fp16 elements: 16-byte multiples up to 64 channels, 128-byte multiples beyond."""
     from diff_pruning_b200 import _lib as L
     lib = L.load()
-    for c, want in [(1, 4), (3, 4), (4, 4), (27, 28), (32, 32), (33, 64), (90, 96), (96, 96), (128, 128), (179, 192), (358, 384),
+    for c, want in [(1, 8), (3, 8), (8, 8), (27, 32), (64, 64), (65, 128), (90, 128), (96, 128), (128, 128), (179, 192), (358, 384),
                     (512, 512)]:
         assert lib.dp_tc_weight_row(c) == want, (c, lib.dp_tc_weight_row(c), want)
     assert lib.dp_tc_weight_row(0) == 0
