@@ -201,7 +201,7 @@ def cpu_oracle_passes(cfg_key, B, min_seconds, max_passes):
 def gpu_eager_passes(cfg_key, B, dev, n=5):
     """The reference's modules as torch-eager ops on THIS GPU (cuDNN / cuBLAS / ATen), same batch and resolution: the bar SURVEY.md
     §0.1 sets.  torch's default is cudnn.allow_tf32=True (convolutions in single-pass TF32) and matmul.allow_tf32=False; the fp32 row
-    switches cuDNN's TF32 off as well, which is the precision class the 3xTF32 tier of this repo delivers."""
+    switches cuDNN's TF32 off as well, which is the precision class the fp32-grade tier of this repo delivers."""
     c = CONFIGS[cfg_key]
     out = {}
     prev = torch.backends.cudnn.allow_tf32
@@ -232,7 +232,7 @@ def gpu_eager_passes(cfg_key, B, dev, n=5):
 
 def measure_tf32_peak(dev):
     """One cuBLAS TF32 GEMM (8192^3, torch.matmul with allow_tf32), same recipe as MEASURED_PEAKS.json's bf16 figure: burst = best of 10,
-    sustained = back to back for ~2 s.  The 3xTF32 tier's arithmetic ceiling is a third of it."""
+    sustained = back to back for ~2 s.  Context for the gpu_eager rows: cuDNN's default convolution runs single-pass TF32."""
     prev = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = True
     try:
@@ -374,7 +374,7 @@ def pruned_model(cfg_key, dev, ratio=0.3):
 def finetune_bench(args, rank, world, dev, barrier, compute="fp32"):
     """Secondary metric of BASELINE.json: finetune imgs/sec on the ratio-0.3 pruned network — ddpm_train.py:437-469 (antithetic
     timesteps, add_noise, fwd, loss, bwd, clip 1.0, Adam 2e-4, EMA 0.9999, dropout 0.1), config batch per GPU, gradient all-reduce
-    (mean) per step when N > 1.  compute = "fp32" (3xTF32 tier) or "bf16" (single-pass tier, ddpm_train.py --mixed_precision bf16)."""
+    (mean) per step when N > 1.  compute = "fp32" (fp32-grade 3 x fp16 split tier) or "bf16" (single-pass tier, ddpm_train.py --mixed_precision bf16)."""
     import torch.distributed as dist
     from diff_pruning_b200.scoring import FinetuneStepper
     c = CONFIGS[args.config]
@@ -476,7 +476,7 @@ def secondary_scoring_leg(cfg_key, args, rank, world, dev, barrier):
         ach = B * c["conv_flop"] / conv_s / 1e12
         res["roofline"] = {"bound": "tensor", "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus,
                            "conv_ms": round(conv_s * 1e3, 3), "breakdown_ms": by_tag, "top_layers_ms": by_layer,
-                           "note": f"{B} x {c['conv_flop'] / 1e12:.4f} TFLOP algorithmic conv work per pass (SURVEY.md §8d) / summed conv-launch time; peak = bf16_tflops_sustained ({which}); 3xTF32 tier"}
+                           "note": f"{B} x {c['conv_flop'] / 1e12:.4f} TFLOP algorithmic conv work per pass (SURVEY.md §8d) / summed conv-launch time; peak = bf16_tflops_sustained ({which}); fp32-grade 3 x fp16 split tier"}
     del sc
     if hasattr(model, "_dpb200_plans"):
         model._dpb200_plans.clear()
@@ -636,7 +636,7 @@ def run_ours(args, rank, world, local_rank):
     if os.path.exists(tp) and B == 128 and args.config == "c1":   # dram__bytes_read+write summed over the conv launches of one pass (committed ncu capture)
         tj = json.load(open(tp))
         traffic = tj["dram_read_bytes"] + tj["dram_write_bytes"]
-    tier_ceiling = tf32["tf32_tflops_sustained"] / 3.0
+    tier_ceiling = tf_sus / 3.0      # 3 kind::f16 tensor instructions per product (fp16 runs at the bf16 rate MEASURED_PEAKS.json holds)
     roofline = {"bound": "tensor", "achieved": achieved, "peak": tf_sus, "unit": "TFLOP/s", "frac": achieved / tf_sus,
                 "traffic": traffic, "breakdown_ms": conv_by_tag, "top_layers_ms": conv_by_layer,
                 "tf32_peak_measured": tf32, "tier_ceiling_tflops": tier_ceiling, "frac_of_tier_ceiling": achieved / tier_ceiling,
@@ -644,7 +644,8 @@ def run_ours(args, rank, world, local_rank):
                 "kernel": "conv implicit GEMM (fprop+dgrad+wgrad launches of one pass: %d)" % n_conv,
                 "note": (f"algorithmic conv FLOPs/pass = {B} x {c['conv_flop'] / 1e9:.2f} GFLOP (SURVEY.md §8d) / summed conv-launch device time "
                          f"{conv_s * 1e3:.2f} ms of a {ms / args.steps:.2f} ms step; peak = bf16_tflops_sustained ({which}); "
-                         "fp32-exact tier: " + ("tcgen05 3xTF32 (3 tensor instructions per product: tier ceiling = measured cuBLAS TF32 sustained / 3)" if tc
+                         "fp32-grade tier: " + ("tcgen05 kind::f16 on a 3-product fp16 hi/lo split of power-of-two-scaled operands (22 bits per operand, fp32 accumulation: "
+                                                 "tier ceiling = peak / 3; tf32_peak_measured = cuBLAS TF32, the rate torch-eager's cuDNN default runs at)" if tc
                                                  else "CUDA-core FFMA (SIMT) — tensor path not active") +
                          "; traffic = DRAM bytes of all conv launches of one pass (committed ncu capture, C1 only)")}
     value = world * args.steps / (ms * 1e-3)

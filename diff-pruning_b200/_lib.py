@@ -40,7 +40,8 @@ class GnArgs(C.Structure):
                 ("x", vp), ("ldx", i64), ("y", vp), ("ldy", i64), ("gamma", vp), ("beta", vp), ("mean", vp),
                 ("rstd", vp), ("dy", vp), ("lddy", i64), ("dx", vp), ("lddx", i64), ("dx_add", vp), ("ldadd", i64),
                 ("dx_add2", vp), ("ldadd2", i64), ("dgamma", vp), ("dbeta", vp), ("workspace", vp),
-                ("dropout_p", f32), ("dropout_seed", u64), ("dropout_seed_dev", vp), ("y_bf16", vp), ("ldyb", i64)]
+                ("dropout_p", f32), ("dropout_seed", u64), ("dropout_seed_dev", vp), ("y_bf16", vp), ("ldyb", i64),
+                ("amax_y", vp), ("amax_dx", vp)]
 
 
 class ConvBf16Args(C.Structure):

@@ -5,7 +5,7 @@
 // at the convolution boundary by their producers (dp_cvt_bf16, or the GroupNorm+SiLU kernel writing bf16 directly); products are exact
 // in the tensor core and accumulate in fp32; outputs, the residual stream and all gradients stay fp32.
 //
-// Unlike the 3xTF32 kernels (conv_tc.cu) nothing has to touch the operands between TMA and the MMA: TMA -> swizzled shared memory ->
+// Unlike the fp32-grade split kernels (conv_tc.cu) nothing has to touch the operands between TMA and the MMA: TMA -> swizzled shared memory ->
 // tcgen05.mma, no splitter warps, no proxy fence in the loop.  One pipeline stage = 64 bf16 of GEMM-K = one 128-byte swizzle row.
 //   conv_bf16_kernel   fprop / dgrad (stride-1 dgrad = tap-flipped fprop; stride 2 through TMA element strides / parity classes):
 //                      persistent, 1 CTA per SM, tile 128 pixels x up to 256 output channels (one N tile covers every layer of the

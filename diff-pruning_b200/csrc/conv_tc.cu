@@ -8,7 +8,7 @@
 // kind::tf32 and half the shared-memory operand bytes, which is what bounded the 3xTF32 kernel (profiles/r02_experiments.md).  Elements
 // more than 2^28 below the tensor's maximum lose RELATIVE precision (absolute error <= 2^-50 of the maximum): below fp32 round-off of any
 // sum they take part in.
-// wgrad (wgrad_tc_kernel) still uses the 3xTF32 split of round 1:  hi = cvt.rna.tf32(.), lo = . - hi.
+// The weight gradient (wgrad_tc_kernel) uses the same split with both operands scaled by their own slots.
 //
 // GEMM view: M = N*H*W output pixels (tile of 128 = one TMA box of the NHWC activation), N = output channels, K = taps x input
 // channels, one pipeline stage = (one tap, 64 channels).  The activation box is im2col-free: the tap shift is a coordinate offset,
@@ -20,7 +20,8 @@
 //                         two TMEM accumulator sets (the epilogue of tile i overlaps the main loop of tile i+1), and
 //                         a_hi x [b_hi | b_lo'] issued as ONE N=256 instruction into [main | correction]
 //   splitk_epilogue_kernel  fixed-order sum of the K splits + the epilogue (small-M launches)
-//   wgrad_tc_kernel       weight gradient: dY^T through TMEM, X split in shared memory, both MN-major, split-K over pixels
+//   wgrad_tc_kernel       weight gradient: dY^T split into TMEM (TS mode), X split in place in shared memory, both MN-major, 64-pixel
+//                         stages, split-K over pixels
 //   pack / split / transpose helpers; dp_gemm_nt_tc runs the attention GEMMs on the persistent kernel.
 // History (git tags): `lab-kernels-r01` round-1 experimental variants; `lab-pair-kernel-r02` the cta_group::2 CTA-pair kernel (correct,
 // 1.4x slower); `tf32x3-r02` the all-3xTF32 build this file replaced.
@@ -483,7 +484,9 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
       : "memory");
 }
 
-constexpr int WG_THREADS = 224;   // warps: 0 TMA | 1, 6 MMA issuers (alternate stages) | 2-5 splitters + epilogue
+// warps: 0 TMA | 1, 6 MMA issuers (alternate stages) | 2-5 splitters of the even stages + epilogue | 7-10 splitters of the odd stages
+// (~850 instructions per thread and stage: one group of four warps alone held the kernel at 2150 clocks per stage)
+constexpr int WG_THREADS = 352;
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ CUtensorMap mapX, const WgParams p) {
   constexpr int WSTAGES = WG_STAGES;
@@ -588,15 +591,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant
       }
       __syncwarp();
     }
-  } else if (warp < 6) {
-    const int tid = threadIdx.x - 64;
-    const int q = warp & 3;                   // TMEM lane quarter == 32-channel box of dy
+  } else {
+    const int grp = warp > 6 ? 1 : 0;         // splitter group: stages it % 2 == grp
+    const int tid = (threadIdx.x - (grp ? 224 : 64));
+    const int q = warp & 3;                   // TMEM lane quarter == 32-channel box of dy (each group covers the four quarters)
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const int Ey = amax_exponent(p.amax_y), Ex = amax_exponent(p.amax_x);
     const float sy = scale_up(Ey), sxs = scale_up(Ex);
     const int xj = tid >> 6, xp = tid & 63;   // x task of this thread: 64-channel block, pixel row
     const uint32_t xsw = (uint32_t)(xp & 7);
-    for (int it = 0; it < num_iters; ++it) {
+    for (int it = grp; it < num_iters; it += 2) {
       const int s = it % WSTAGES;
       const uint32_t ph = (uint32_t)(it / WSTAGES) & 1u;
       mbar_wait(full_bar(s), ph);
@@ -641,6 +645,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(conv_bar(s));
     }
+    // epilogue: group 0 drains accumulator columns [0, 64), group 1 [64, 128)
     mbar_wait(tmem_full_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const float f1 = scale_dn(Ey), f2 = scale_dn(Ex);
@@ -650,10 +655,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant
     float* wrow = p.ws + ((long long)blockIdx.y * p.K + kout) * TC_ + (long long)tap * p.C;
     if (num_iters == 0) {                     // nothing was accumulated (TMEM holds garbage): this split contributes zeros
       if (kout < p.K)
-        for (int c = ct * 128; c < min(p.C, ct * 128 + 128); ++c) wrow[c] = 0.f;
+        for (int c = ct * 128 + grp * 64; c < min(p.C, ct * 128 + grp * 64 + 64); ++c) wrow[c] = 0.f;
     } else
 #pragma unroll 1
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 2 * grp; j < 2 * grp + 2; ++j) {
       uint32_t v[32], u[32];
       const uint32_t taddr = tmem_base + lane_addr + (uint32_t)(j * 32);
       tmem_ld32(taddr, v);

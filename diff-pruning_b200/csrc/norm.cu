@@ -80,6 +80,14 @@ __global__ void gn_finalize_kernel(const dp_gn_args a, const Map mp, const doubl
   a.rstd[i] = (float)(1.0 / sqrt(var + (double)a.eps));
 }
 
+// max |v| of the values a thread wrote -> the output's amax slot (dp_amax semantics: atomicMax on the bit pattern, order-independent),
+// one atomic per converged warp
+__device__ __forceinline__ void amax_commit(uint32_t* slot, float m) {
+  const unsigned mask = __activemask();
+  const uint32_t r = __reduce_max_sync(mask, __float_as_uint(m));
+  if ((threadIdx.x & 31) == (unsigned)(__ffs(mask) - 1) && r) atomicMax(slot, r);
+}
+
 __global__ void __launch_bounds__(NT) gn_apply_kernel(const dp_gn_args a, const Map mp) {
   const int n = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
   const int ct = tid % mp.CT, pl = tid / mp.CT;
@@ -98,6 +106,7 @@ __global__ void __launch_bounds__(NT) gn_apply_kernel(const dp_gn_args a, const 
   }
   const float* xb = a.x + (long long)n * a.HW * a.ldx;
   float* yb = a.y + (long long)n * a.HW * a.ldy;
+  float amax = 0.f;
   for (int pix = p0 + pl; pix < p1; pix += mp.PL) {
     const float* row = xb + (long long)pix * a.ldx;
     float* orow = yb + (long long)pix * a.ldy;
@@ -110,9 +119,11 @@ __global__ void __launch_bounds__(NT) gn_apply_kernel(const dp_gn_args a, const 
         if (a.dropout_p > 0.f) y *= keep_scale(a.dropout_seed + (a.dropout_seed_dev ? *a.dropout_seed_dev : 0ull), ((uint64_t)n * a.HW + pix) * a.C + c, a.dropout_p);
         if (a.y) orow[c] = y;
         if (a.y_bf16) reinterpret_cast<__nv_bfloat16*>(a.y_bf16)[((long long)n * a.HW + pix) * a.ldyb + c] = __float2bfloat16_rn(y);
+        amax = fmaxf(amax, fabsf(y));
       }
     }
   }
+  if (a.amax_y) amax_commit(a.amax_y, amax);
 }
 
 // ---- backward ----
@@ -229,6 +240,7 @@ __global__ void __launch_bounds__(NT) gn_bwd_apply_kernel(const dp_gn_args a, co
   float* ob = a.dx + (long long)n * a.HW * a.lddx;
   const float* ab = a.dx_add ? a.dx_add + (long long)n * a.HW * a.ldadd : nullptr;
   const float* ab2 = a.dx_add2 ? a.dx_add2 + (long long)n * a.HW * a.ldadd2 : nullptr;
+  float amax = 0.f;
   for (int pix = p0 + pl; pix < p1; pix += mp.PL) {
 #pragma unroll
     for (int u = 0; u < MAXCPT; ++u) {
@@ -241,9 +253,11 @@ __global__ void __launch_bounds__(NT) gn_bwd_apply_kernel(const dp_gn_args a, co
         if (ab) d += ab[(long long)pix * a.ldadd + c];
         if (ab2) d += ab2[(long long)pix * a.ldadd2 + c];
         ob[(long long)pix * a.lddx + c] = d;
+        amax = fmaxf(amax, fabsf(d));
       }
     }
   }
+  if (a.amax_dx) amax_commit(a.amax_dx, amax);
 }
 
 
@@ -307,6 +321,7 @@ __global__ void __launch_bounds__(NT) gn_apply4_kernel(const dp_gn_args a, const
   const float* xb = a.x + (long long)n * a.HW * a.ldx + c0;
   float* yb = a.y + (long long)n * a.HW * a.ldy + c0;
   const uint64_t seed = a.dropout_seed + (a.dropout_seed_dev ? *a.dropout_seed_dev : 0ull);
+  float amax = 0.f;
 #pragma unroll 4
   for (int pix = p0 + pl; pix < p1; pix += mp.PL) {
     float4 v = ld4(xb + (long long)pix * a.ldx);
@@ -322,7 +337,9 @@ __global__ void __launch_bounds__(NT) gn_apply4_kernel(const dp_gn_args a, const
       uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
       *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.y_bf16) + ((long long)n * a.HW + pix) * a.ldyb + c0) = pk;
     }
+    amax = fmaxf(fmaxf(amax, fmaxf(fabsf(y[0]), fabsf(y[1]))), fmaxf(fabsf(y[2]), fabsf(y[3])));
   }
+  if (a.amax_y) amax_commit(a.amax_y, amax);
 }
 
 __global__ void __launch_bounds__(NT) gn_bwd_partial4_kernel(const dp_gn_args a, const Map mp, float* __restrict__ part) {
@@ -384,6 +401,7 @@ __global__ void __launch_bounds__(NT) gn_bwd_apply4_kernel(const dp_gn_args a, c
   float* ob = a.dx + (long long)n * a.HW * a.lddx + c0;
   const float* ab = a.dx_add ? a.dx_add + (long long)n * a.HW * a.ldadd + c0 : nullptr;
   const float* ab2 = a.dx_add2 ? a.dx_add2 + (long long)n * a.HW * a.ldadd2 + c0 : nullptr;
+  float amax = 0.f;
 #pragma unroll 2
   for (int pix = p0 + pl; pix < p1; pix += mp.PL) {
     float4 xv = ld4(xb + (long long)pix * a.ldx), dv = ld4(db + (long long)pix * a.lddy);
@@ -397,7 +415,9 @@ __global__ void __launch_bounds__(NT) gn_bwd_apply4_kernel(const dp_gn_args a, c
     if (ab) { float4 t = *reinterpret_cast<const float4*>(ab + (long long)pix * a.ldadd); d[0] += t.x; d[1] += t.y; d[2] += t.z; d[3] += t.w; }
     if (ab2) { float4 t = ld4(ab2 + (long long)pix * a.ldadd2); d[0] += t.x; d[1] += t.y; d[2] += t.z; d[3] += t.w; }
     *reinterpret_cast<float4*>(ob + (long long)pix * a.lddx) = make_float4(d[0], d[1], d[2], d[3]);
+    amax = fmaxf(fmaxf(amax, fmaxf(fabsf(d[0]), fabsf(d[1]))), fmaxf(fabsf(d[2]), fabsf(d[3])));
   }
+  if (a.amax_dx) amax_commit(a.amax_dx, amax);
 }
 
 

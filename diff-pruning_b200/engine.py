@@ -122,7 +122,7 @@ class Plan:
         self.lib = L.load()
         self.tc = bool(self.lib.dp_tc_available()) if torch.device(device).type == "cuda" else False
         if compute not in ("fp32", "bf16"):
-            raise ValueError(f"compute must be 'fp32' (3xTF32, fp32-grade) or 'bf16' (single-pass tensor tier), got {compute!r}")
+            raise ValueError(f"compute must be 'fp32' (3 x fp16 split, fp32-grade) or 'bf16' (single-pass tensor tier), got {compute!r}")
         if compute == "bf16" and not (torch.device(device).type == "cuda" and self.lib.dp_bf16_available()):
             raise RuntimeError("diff_pruning_b200: the bf16 tensor tier needs an sm_100a device (no fallback)")
         # bf16 tier (ddpm_train.py --mixed_precision bf16 -> torch.autocast: conv / linear operands in bf16, everything else fp32):
@@ -298,14 +298,19 @@ class Plan:
         self._packs[id(w)] = (wck, wkc, tc)
         return wck, wkc, tc
 
+    def _new_slot(self) -> int:
+        """Device address of a fresh per-pass amax slot (zeroed by the first launch of every forward)."""
+        slot = self._slots.data_ptr() + 4 * self._n_slots
+        self._n_slots += 1
+        assert self._n_slots <= AMAX_SLOTS, "raise engine.AMAX_SLOTS"
+        return slot
+
     def _amax(self, lst: List[Step], ptr_get, ld: int, rows: int, cols: int, fwd_key=None) -> int:
         """Records dp_amax over a [rows][cols] view into a fresh amax slot; returns the slot's device address.  Forward activations are
         written once per pass, so consumers of the same view share one slot (fwd_key)."""
         if fwd_key is not None and fwd_key in self._amax_fwd:
             return self._amax_fwd[fwd_key]
-        slot = self._slots.data_ptr() + 4 * self._n_slots
-        self._n_slots += 1
-        assert self._n_slots <= AMAX_SLOTS, "raise engine.AMAX_SLOTS"
+        slot = self._new_slot()
         lib = self.lib
         self._rec(lst, lambda s, g=ptr_get: lib.dp_amax(g(), ld, rows, cols, slot, s), what="amax")
         if fwd_key is not None:
@@ -391,10 +396,11 @@ class Plan:
     def conv(self, x: View, w: nn.Parameter, b: Optional[nn.Parameter], out: View, stride=1, pad=1,
              rowadd: Optional[View] = None, residual: Optional[View] = None, accumulate_out=False, need_dx=True,
              dx_scratch: Optional[str] = None, seg_out: Optional[str] = None, dy_dense: Optional[str] = None,
-             dx_into: Optional[View] = None):
+             dx_into: Optional[View] = None, dy_slot: Optional[int] = None):
         """Records fprop (fwd) and bias-grad / wgrad / dgrad (bwd).
         dgrad target: `dx_scratch` (shared dense scratch [rows][C]) or the gradient view of `dx_into` / `x`.
-        dy source: out.grad, or the dense scratch `dy_dense` ([rows][K]) when the consumer provides it."""
+        dy source: out.grad, or the dense scratch `dy_dense` ([rows][K]) when the consumer provides it.
+        dy_slot: amax slot of dy that the (single) producer of out.grad fills itself (gn_bwd(amax_dx=)); else a dp_amax launch is recorded."""
         lib = self.lib
         K, Cin = w.shape[0], w.shape[1]
         R = w.shape[2] if w.dim() == 4 else 1
@@ -457,7 +463,7 @@ class Plan:
         chunks = max(1, out.rows // 64)              # tensor-core wgrad walks 64-pixel chunks
         splits = _wgrad_splits(tiles, chunks)
         self.scratch("wgrad_ws", splits * K * TC)
-        amax_dy = self._amax(steps, dy_get, dy_ld, out.rows, K) if wtc is not None else None
+        amax_dy = (dy_slot or self._amax(steps, dy_get, dy_ld, out.rows, K)) if wtc is not None else None
         wa = _copy_args(a)
         wa.amax_y = amax_dy
         wa.flags, wa.splits = 0, splits
@@ -601,9 +607,14 @@ class Plan:
             self._bf_cache[(out.t.data_ptr(), out.off, out.C)] = (yb, ldyb)
         cp, gp = x.C // parts, G // parts
         args = []
+        yslot = None
+        if self.tc and not bf16_only:   # the tensor-core convolutions that read `out` find its amax slot already filled
+            yslot = self._new_slot()
+            self._amax_fwd[(out.ptr, out.ld, out.rows, out.C)] = yslot
         for i in range(parts):
             c0 = i * cp
             a = L.GnArgs()
+            a.amax_y = yslot
             a.N, a.HW, a.C, a.G = x.N, x.H * x.W, cp, gp
             a.eps, a.silu = norm.eps, 1 if silu else 0
             a.x, a.ldx, a.y, a.ldy = x.ptr + 4 * c0, x.ld, out.ptr + 4 * c0, out.ld
@@ -624,14 +635,16 @@ class Plan:
         return args
 
     def gn_bwd(self, a_fwd, x: View, norm: nn.Module, dy_get: Callable[[], int], lddy: int,
-               add2: Optional[View] = None):
-        """x.grad (=|+=) GN(+SiLU)(+dropout) backward (+ add2); dgamma/dbeta += .  a_fwd: what gn() returned."""
+               add2: Optional[View] = None, amax_dx: Optional[int] = None):
+        """x.grad (=|+=) GN(+SiLU)(+dropout) backward (+ add2); dgamma/dbeta += .  a_fwd: what gn() returned.
+        amax_dx: amax slot the kernel fills with max|x.grad| — only when this call is the ONLY writer of x.grad (see conv(dy_slot=))."""
         lib = self.lib
         gx = self.gradof(x)
         it = self._bitem()
         parts = []
         for a_part, c0 in a_fwd:
             b = _copy_args(a_part)
+            b.amax_y, b.amax_dx = None, amax_dx
             b.dx, b.lddx, b.lddy = gx.ptr + 4 * c0, gx.ld, lddy
             if add2 is not None:
                 b.dx_add2, b.ldadd2 = add2.ptr + 4 * c0, add2.ld
@@ -664,10 +677,12 @@ class Plan:
         # time_emb_proj(silu(temb)) -> per-image row added in conv1's epilogue; its dY are conv1's per-image sums
         self.conv(self.silu_temb, m.time_emb_proj.weight, m.time_emb_proj.bias, tp, pad=0, dy_dense="seg",
                   dx_into=self.silu_temb)
-        self.conv(a1, m.conv1.weight, m.conv1.bias, h1, rowadd=tp, seg_out="seg", dx_scratch="da")
+        # h1 feeds norm2 only, so norm2's backward writes all of h1.grad = conv1's dy and leaves its amax on the way
+        s_h1 = self._new_slot() if (self.tc and self.need_grad) else None
+        self.conv(a1, m.conv1.weight, m.conv1.bias, h1, rowadd=tp, seg_out="seg", dx_scratch="da", dy_slot=s_h1)
         g2 = self.gn(h1, m.norm2, a2, silu=True, dropout_p=p_drop, bf16_only=self.conv_bf16_ok(a2, out, m.conv2.weight))
         if self.need_grad:
-            self.gn_bwd(g2, h1, m.norm2, da, Cout)
+            self.gn_bwd(g2, h1, m.norm2, da, Cout, amax_dx=s_h1)
         if has_sc:
             self.conv(a2, m.conv2.weight, m.conv2.bias, out, dx_scratch="da")
             self.conv(x, m.conv_shortcut.weight, m.conv_shortcut.bias, out, pad=0, accumulate_out=True)
@@ -740,7 +755,7 @@ class Plan:
     def _attention_core_tc(self, N, H, W, T, inner, q, k, v, o, P, sc):
         """softmax(scale q k^T) v and its backward on the tensor-core NT GEMM (dp_gemm_nt_tc): every product is written as
         C = A B^T with a K-contiguous activation A (TMA box of the token grid) and a pre-split hi/lo B built by
-        dp_split_tf32 (optionally transposing); P^T / dS^T come from dp_transpose_batched.
+        dp_split_h3 (optionally transposing); P^T / dS^T come from dp_transpose_batched.
           fwd : S = q k^T          B = split(k)            O  = P v         B = split^T(v)
           bwd : dV = P^T dO        A = P^T, B = split^T(dO)   dP = dO v^T    B = split(v)
                 dQ = dS k          B = split^T(k)            dK = dS^T q    A = dS^T, B = split^T(q)"""

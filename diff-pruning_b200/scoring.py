@@ -312,7 +312,7 @@ class FinetuneStepper:
                  num_train_timesteps: int = 1000, use_graph: bool = True, compute: str = "fp32"):
         self.lib = L.load()
         self.model = model
-        self.compute = compute      # "fp32": 3xTF32 fp32-grade tier | "bf16": single-pass tensor tier (ddpm_train.py --mixed_precision bf16)
+        self.compute = compute      # "fp32": fp32-grade 3 x fp16 split tier | "bf16": single-pass tensor tier (ddpm_train.py --mixed_precision bf16)
         self.dev = next(model.parameters()).device
         assert self.dev.type == "cuda"
         self.lr, self.betas, self.eps = lr, betas, eps

@@ -225,6 +225,9 @@ typedef struct dp_gn_args {
   /* bf16 tier: the forward additionally (or, with y == NULL, only) writes its output rounded to bf16 (RNE) as the next
    * convolution's operand — [N][HW][ldyb] with ldyb a multiple of 8; pad columns are left untouched (never read: TMA bounds) */
   void* y_bf16; int64_t ldyb;
+  /* optional amax slots (dp_amax semantics) of the tensors this call writes: forward y, backward dx — the tensor-core convolution
+   * that consumes them then needs no separate dp_amax pass */
+  uint32_t* amax_y; uint32_t* amax_dx;
 } dp_gn_args;
 size_t dp_groupnorm_workspace_bytes(int32_t N, int32_t HW, int32_t C, int32_t G);
 int dp_groupnorm_fwd(const dp_gn_args* a, dp_stream_t stream);
