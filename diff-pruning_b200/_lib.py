@@ -15,7 +15,7 @@ class ConvArgs(C.Structure):
     _fields_ = [(n, i32) for n in ("N", "H", "W", "C", "P", "Q", "K", "R", "S", "stride", "pad_t", "pad_l", "flags",
                                    "splits")] + [
         ("x", vp), ("ldx", i64), ("y", vp), ("ldy", i64), ("w", vp), ("w_tc_hi", vp), ("w_tc_lo", vp), ("bias", vp), ("rowadd", vp),
-        ("ld_rowadd", i64), ("residual", vp), ("ld_res", i64), ("workspace", vp), ("amax_x", vp), ("amax_y", vp), ("amax_w", vp)]
+        ("ld_rowadd", i64), ("residual", vp), ("ld_res", i64), ("workspace", vp), ("amax_x", vp), ("amax_y", vp), ("amax_w", vp), ("amax_out", vp)]
 
 
 class WgradReduceArgs(C.Structure):
@@ -32,7 +32,7 @@ class GemmArgs(C.Structure):
 
 class GemmNtArgs(C.Structure):
     _fields_ = [("batch", i32), ("H", i32), ("W", i32), ("Kg", i32), ("N", i32), ("A", vp), ("ld_a", i64), ("b_hi", vp),
-                ("b_lo", vp), ("C", vp), ("ldc", i64), ("alpha", f32), ("amax_a", vp), ("amax_b", vp)]
+                ("b_lo", vp), ("C", vp), ("ldc", i64), ("alpha", f32), ("amax_a", vp), ("amax_b", vp), ("amax_out", vp)]
 
 
 class GnArgs(C.Structure):
@@ -92,7 +92,7 @@ _SIGS = {
     "dp_split_h3": (C.c_int, [vp, i64, i64, i32, i32, i32, i32, vp, vp, vp, vp]),
     "dp_transpose_batched": (C.c_int, [vp, vp, i32, i32, i32, vp]),
     "dp_softmax_fwd": (C.c_int, [vp, vp, i64, i32, vp]),
-    "dp_softmax_bwd": (C.c_int, [vp, vp, vp, i64, i32, vp]),
+    "dp_softmax_bwd": (C.c_int, [vp, vp, vp, i64, i32, vp, vp]),
     "dp_groupnorm_workspace_bytes": (C.c_size_t, [i32, i32, i32, i32]),
     "dp_groupnorm_fwd": (C.c_int, [C.POINTER(GnArgs), vp]),
     "dp_groupnorm_bwd": (C.c_int, [C.POINTER(GnArgs), vp]),

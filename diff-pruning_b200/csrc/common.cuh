@@ -45,4 +45,11 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
+// max |v| of the values a thread wrote -> the output tensor's amax slot (dp_amax semantics: atomicMax on the bit pattern of a
+// non-negative float is order-independent, so slots are run-to-run identical); one atomic per converged warp
+__device__ __forceinline__ void amax_commit(uint32_t* slot, float m) {
+  const unsigned mask = __activemask();
+  const uint32_t r = __reduce_max_sync(mask, __float_as_uint(m));
+  if ((threadIdx.x & 31) == (unsigned)(__ffs(mask) - 1) && r) atomicMax(slot, r);
+}
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }

@@ -55,6 +55,7 @@ struct TcParams {
   int b_from_img;           // batched GEMM: the B tile index is the tile's image (bn == 1) instead of a filter tap
   const uint32_t* amax_a;   // amax slots of the A operand (activation / gradient view) and of the B operand (weights / split activation)
   const uint32_t* amax_b;
+  uint32_t* amax_out;       // optional amax slot of the output tensor
   // split-K (persistent kernel, launches with fewer tiles than half the SMs: the 4x4 / 8x8 / 16x16 levels): work item = (tile, K split);
   // a split walks `it_per_split` pipeline stages of the tile and writes its raw accumulator to ws[split][row][channel]
   // (row = tile_m * 128 + TMEM lane, pitch ws_ld); splitk_epilogue_kernel sums the splits in fixed order and applies the epilogue
@@ -322,6 +323,7 @@ conv_tc_ps_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     // accumulators hold (s_a s_b) x the products: f1 * f2 undoes the two power-of-two operand scales (two factors: their product may underflow)
     const float f1 = scale_dn(amax_exponent(p.amax_a)), f2 = scale_dn(amax_exponent(p.amax_b)) * p.alpha;
     auto fin = [&](uint32_t main, uint32_t corr) { return fmaf(__uint_as_float(corr), LO_UNSCALE, __uint_as_float(main)) * f1 * f2; };
+    float amax = 0.f;         // max |value written| by this thread (split launches: splitk_epilogue_kernel writes, and tracks, the outputs)
     uint32_t tl = 0;
     for (int wi = blockIdx.x; wi < total_work; wi += gridDim.x, ++tl) {
       const int tile = wi % total_tiles;
@@ -380,6 +382,7 @@ conv_tc_ps_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
               float4* dst = reinterpret_cast<float4*>(yrow + c0 + i);
               if (p.accumulate) { float4 t = *dst; o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
               *dst = o;
+              amax = fmaxf(fmaxf(amax, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
             }
           } else {
 #pragma unroll
@@ -392,12 +395,14 @@ conv_tc_ps_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                 if (rrow) o += __ldg(rrow + c);
                 if (p.accumulate) o += yrow[c];
                 yrow[c] = o;
+                amax = fmaxf(amax, fabsf(o));
               }
             }
           }
         }
       }
     }
+    if (p.amax_out && p.ksplit == 1) amax_commit(p.amax_out, amax);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
@@ -412,6 +417,7 @@ conv_tc_ps_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 __global__ void __launch_bounds__(256) splitk_epilogue_kernel(const TcParams p, const int tiles_m) {
   const int c4 = (p.Nout + 3) >> 2;
   const long long total = (long long)tiles_m * BM * c4;
+  float amax = 0.f;
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
     const long long grow = i / c4;
     const int c = (int)(i - grow * c4) << 2;
@@ -439,9 +445,11 @@ __global__ void __launch_bounds__(256) splitk_epilogue_kernel(const TcParams p, 
         if (p.residual) v += __ldg(p.residual + m * p.ld_res + cc);
         if (p.accumulate) v += yrow[cc];
         yrow[cc] = v;
+        amax = fmaxf(amax, fabsf(v));
       }
     }
   }
+  if (p.amax_out) amax_commit(p.amax_out, amax);
 }
 
 // ------------------------------------------------------------------------------------------------ wgrad
@@ -484,9 +492,10 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
       : "memory");
 }
 
-// warps: 0 TMA | 1, 6 MMA issuers (alternate stages) | 2-5 splitters of the even stages + epilogue | 7-10 splitters of the odd stages
-// (~850 instructions per thread and stage: one group of four warps alone held the kernel at 2150 clocks per stage)
-constexpr int WG_THREADS = 352;
+// warps: 0 TMA | 1, 6 MMA issuers (alternate stages) | 2-5 splitters + epilogue.  (A second splitter group on alternate stages was
+// measured: no gain — the kernel is not instruction-bound — and with an odd stage count a group that visits a barrier only every
+// second phase can be lapped, so it is gone.)
+constexpr int WG_THREADS = 224;
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ CUtensorMap mapX, const WgParams p) {
   constexpr int WSTAGES = WG_STAGES;
@@ -591,16 +600,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant
       }
       __syncwarp();
     }
-  } else {
-    const int grp = warp > 6 ? 1 : 0;         // splitter group: stages it % 2 == grp
-    const int tid = (threadIdx.x - (grp ? 224 : 64));
-    const int q = warp & 3;                   // TMEM lane quarter == 32-channel box of dy (each group covers the four quarters)
+  } else if (warp < 6) {
+    const int tid = threadIdx.x - 64;
+    const int q = warp & 3;                   // TMEM lane quarter == 32-channel box of dy
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const int Ey = amax_exponent(p.amax_y), Ex = amax_exponent(p.amax_x);
     const float sy = scale_up(Ey), sxs = scale_up(Ex);
     const int xj = tid >> 6, xp = tid & 63;   // x task of this thread: 64-channel block, pixel row
     const uint32_t xsw = (uint32_t)(xp & 7);
-    for (int it = grp; it < num_iters; it += 2) {
+    for (int it = 0; it < num_iters; ++it) {
       const int s = it % WSTAGES;
       const uint32_t ph = (uint32_t)(it / WSTAGES) & 1u;
       mbar_wait(full_bar(s), ph);
@@ -645,7 +653,6 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(conv_bar(s));
     }
-    // epilogue: group 0 drains accumulator columns [0, 64), group 1 [64, 128)
     mbar_wait(tmem_full_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const float f1 = scale_dn(Ey), f2 = scale_dn(Ex);
@@ -655,10 +662,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant
     float* wrow = p.ws + ((long long)blockIdx.y * p.K + kout) * TC_ + (long long)tap * p.C;
     if (num_iters == 0) {                     // nothing was accumulated (TMEM holds garbage): this split contributes zeros
       if (kout < p.K)
-        for (int c = ct * 128 + grp * 64; c < min(p.C, ct * 128 + grp * 64 + 64); ++c) wrow[c] = 0.f;
+        for (int c = ct * 128; c < min(p.C, ct * 128 + 128); ++c) wrow[c] = 0.f;
     } else
 #pragma unroll 1
-    for (int j = 2 * grp; j < 2 * grp + 2; ++j) {
+    for (int j = 0; j < 4; ++j) {
       uint32_t v[32], u[32];
       const uint32_t taddr = tmem_base + lane_addr + (uint32_t)(j * 32);
       tmem_ld32(taddr, v);
@@ -768,7 +775,7 @@ int launch_tc(const float* act, long long ld_act, const uint32_t* amax_a, int Ni
               const uint32_t* amax_b, int Nout, int T, const TapTable& taps, int os, int oa, int ob, int Ho, int Wo, float* out,
               long long ld_out, const float* bias, const float* rowadd, long long ld_rowadd, const float* residual, long long ld_res,
               int accumulate, cudaStream_t st, float alpha = 1.0f, int b_from_img = 0, int in_stride = 1, int ldb = -1, float* ws = nullptr,
-              long long* ws_need = nullptr) {
+              long long* ws_need = nullptr, uint32_t* amax_out = nullptr) {
   if (ldb < 0) ldb = wrow(Kg);   // packed conv weights; batched GEMM callers pass their own row pitch
   if (!tc_init()) return DP_ERR_UNSUPPORTED;
   if (!ws_need && (!w_hi || !w_lo || !amax_a || !amax_b)) return DP_ERR_UNSUPPORTED;
@@ -811,7 +818,7 @@ int launch_tc(const float* act, long long ld_act, const uint32_t* amax_a, int Ni
   p.ntaps = taps.n;
   for (int i = 0; i < 9; ++i) { p.dh[i] = taps.dh[i]; p.dw[i] = taps.dw[i]; p.wt[i] = taps.wt[i]; }
   p.os = os; p.oa = oa; p.ob = ob; p.Ho = Ho; p.Wo = Wo;
-  p.alpha = alpha; p.b_from_img = b_from_img; p.in_stride = in_stride; p.amax_a = amax_a; p.amax_b = amax_b;
+  p.alpha = alpha; p.b_from_img = b_from_img; p.in_stride = in_stride; p.amax_a = amax_a; p.amax_b = amax_b; p.amax_out = amax_out;
   p.kchunks = (Kg + BK - 1) / BK;
   p.bw = bw; p.bh = bh; p.bn = bn; p.tiles_w = W / bw; p.tiles_h = H / bh;
   p.y = out; p.ldy = ld_out; p.bias = bias; p.rowadd = rowadd; p.ld_rowadd = ld_rowadd; p.residual = residual; p.ld_res = ld_res;
@@ -938,7 +945,8 @@ extern "C" int dp_gemm_nt_tc(const dp_gemm_nt_args* a, dp_stream_t stream) {
   TapTable t{};
   t.n = 1;
   return launch_tc(a->A, a->ld_a, a->amax_a, a->batch, a->H, a->W, a->Kg, a->b_hi, a->b_lo, a->amax_b, a->N, a->batch, t, 1, 0, 0, a->H,
-                   a->W, a->C, a->ldc, nullptr, nullptr, 0, nullptr, 0, 0, (cudaStream_t)stream, a->alpha, 1, 1, (a->Kg + 7) & ~7);
+                   a->W, a->C, a->ldc, nullptr, nullptr, 0, nullptr, 0, 0, (cudaStream_t)stream, a->alpha, 1, 1, (a->Kg + 7) & ~7, nullptr,
+                   nullptr, a->amax_out);
 }
 
 int dp_tc_runtime_ok() { return tc_init(); }
@@ -966,7 +974,7 @@ int dp_conv2d_fprop_tc(const dp_conv_args* a, dp_stream_t stream) {
   return launch_tc((const float*)a->x, a->ldx, a->amax_x, a->N, a->P, a->Q, a->C, a->w_tc_hi, a->w_tc_lo, a->amax_w, a->K, a->R * a->S,
                    dense_taps(a->R, a->S, a->pad_t, false), 1, 0, 0, a->P, a->Q, (float*)a->y, a->ldy, a->bias, a->rowadd,
                    a->ld_rowadd, a->residual, a->ld_res, (a->flags & DP_CONV_ACCUMULATE) ? 1 : 0, (cudaStream_t)stream, 1.0f, 0, a->stride, -1,
-                   a->workspace);
+                   a->workspace, nullptr, a->amax_out);
 }
 
 // stride-1 dgrad == fprop of dy with the taps flipped and the (K,C) roles swapped: dx[n,h,w,c] = sum dy[n,h+1-r,w+1-s,k] W[k,c,r,s].
@@ -981,7 +989,7 @@ int dp_conv2d_dgrad_tc(const dp_conv_args* a, dp_stream_t stream) {
     if (a->pad_t != (a->R - 1) / 2 || a->pad_l != a->pad_t || a->P != a->H || a->Q != a->W) return DP_ERR_UNSUPPORTED;
     return launch_tc((const float*)a->y, a->ldy, a->amax_y, a->N, a->H, a->W, a->K, a->w_tc_hi, a->w_tc_lo, a->amax_w, a->C, a->R * a->S,
                      dense_taps(a->R, a->S, a->pad_t, true), 1, 0, 0, a->H, a->W, (float*)a->x, a->ldx, nullptr, nullptr, 0, nullptr, 0,
-                     acc, (cudaStream_t)stream, 1.0f, 0, 1, -1, a->workspace);
+                     acc, (cudaStream_t)stream, 1.0f, 0, 1, -1, a->workspace, nullptr, a->amax_out);
   }
   if (a->stride != 2 || a->R != 3 || a->H != 2 * a->P || a->W != 2 * a->Q) return DP_ERR_UNSUPPORTED;
   TapTable cls[4];
@@ -1002,7 +1010,7 @@ int dp_conv2d_dgrad_tc(const dp_conv_args* a, dp_stream_t stream) {
     for (int cb = 0; cb < 2; ++cb) {
       int rc = launch_tc((const float*)a->y, a->ldy, a->amax_y, a->N, a->P, a->Q, a->K, a->w_tc_hi, a->w_tc_lo, a->amax_w, a->C, 9, cls[ca * 2 + cb], 2, ca, cb,
                          a->H, a->W, (float*)a->x, a->ldx, nullptr, nullptr, 0, nullptr, 0, acc, (cudaStream_t)stream, 1.0f, 0, 1, -1,
-                         a->workspace);
+                         a->workspace, nullptr, a->amax_out);
       if (rc != DP_OK) return (ca == 0 && cb == 0) ? rc : (rc == DP_ERR_UNSUPPORTED ? DP_ERR_SHAPE : rc);
     }
   return DP_OK;

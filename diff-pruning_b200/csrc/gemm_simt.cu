@@ -36,6 +36,7 @@ struct GemmParams {
   const float* bias;
   const float* rowadd; long long ld_rowadd; int rows_per_img;
   const float* residual; long long ld_res;
+  uint32_t* amax_out;   // optional amax slot of C
   Gather g;
 };
 
@@ -225,6 +226,7 @@ __global__ void __launch_bounds__(NTHREADS) gemm_simt_kernel(const GemmParams p)
   }
 
   // ---- epilogue ----
+  float amax = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
@@ -242,8 +244,10 @@ __global__ void __launch_bounds__(NTHREADS) gemm_simt_kernel(const GemmParams p)
       if (res) v += __ldg(res + n);
       if (p.accumulate) v += crow[n];
       crow[n] = v;
+      amax = fmaxf(amax, fabsf(v));
     }
   }
+  if (p.amax_out) amax_commit(p.amax_out, amax);
 }
 
 template <int AM, int BMODE>
@@ -256,7 +260,7 @@ int launch_gemm(const GemmParams& p, int zdim, cudaStream_t st) {
 
 void clear_epilogue(GemmParams& p) {
   p.bias = nullptr; p.rowadd = nullptr; p.residual = nullptr; p.ld_rowadd = 0; p.ld_res = 0; p.rows_per_img = 1;
-  p.k_per_split = 0; p.alpha = 1.f; p.accumulate = 0;
+  p.k_per_split = 0; p.alpha = 1.f; p.accumulate = 0; p.amax_out = nullptr;
   p.a_bs = p.b_bs = p.c_bs = 0;
 }
 
@@ -291,6 +295,7 @@ int dp_conv2d_fprop_simt(const dp_conv_args* a, dp_stream_t stream) {
   p.accumulate = (a->flags & DP_CONV_ACCUMULATE) ? 1 : 0;
   p.bias = a->bias; p.rowadd = a->rowadd; p.ld_rowadd = a->ld_rowadd; p.rows_per_img = a->P * a->Q;
   p.residual = a->residual; p.ld_res = a->ld_res;
+  p.amax_out = a->amax_out;
   Gather& g = p.g;
   g.src = (const float*)a->x; g.ld = a->ldx; g.H = a->H; g.W = a->W; g.C = a->C;
   g.P = a->P; g.Q = a->Q; g.PQ = a->P * a->Q; g.S = a->S;
@@ -310,6 +315,7 @@ int dp_conv2d_dgrad_simt(const dp_conv_args* a, dp_stream_t stream) {
   p.B = a->w; p.b_rs = a->C; p.b_cs = 1;  // packed [R*S][K][C]
   p.C = (float*)a->x; p.ldc = a->ldx;
   p.accumulate = (a->flags & DP_CONV_ACCUMULATE) ? 1 : 0;
+  p.amax_out = a->amax_out;
   Gather& g = p.g;
   g.src = (const float*)a->y; g.ld = a->ldy; g.H = a->P; g.W = a->Q; g.C = a->K;
   g.P = a->H; g.Q = a->W; g.PQ = a->H * a->W; g.S = a->S;

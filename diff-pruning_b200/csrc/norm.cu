@@ -80,14 +80,6 @@ __global__ void gn_finalize_kernel(const dp_gn_args a, const Map mp, const doubl
   a.rstd[i] = (float)(1.0 / sqrt(var + (double)a.eps));
 }
 
-// max |v| of the values a thread wrote -> the output's amax slot (dp_amax semantics: atomicMax on the bit pattern, order-independent),
-// one atomic per converged warp
-__device__ __forceinline__ void amax_commit(uint32_t* slot, float m) {
-  const unsigned mask = __activemask();
-  const uint32_t r = __reduce_max_sync(mask, __float_as_uint(m));
-  if ((threadIdx.x & 31) == (unsigned)(__ffs(mask) - 1) && r) atomicMax(slot, r);
-}
-
 __global__ void __launch_bounds__(NT) gn_apply_kernel(const dp_gn_args a, const Map mp) {
   const int n = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
   const int ct = tid % mp.CT, pl = tid / mp.CT;

@@ -228,7 +228,8 @@ __global__ void softmax_fwd_kernel(const float* __restrict__ s, float* __restric
   float inv = 1.0f / sum;
   for (int j = lane; j < cols; j += 32) out[j] = expf(in[j] - mx) * inv;
 }
-__global__ void softmax_bwd_kernel(const float* __restrict__ p, const float* __restrict__ dp, float* __restrict__ ds, long long rows, int cols) {
+__global__ void softmax_bwd_kernel(const float* __restrict__ p, const float* __restrict__ dp, float* __restrict__ ds, long long rows, int cols,
+                                   uint32_t* __restrict__ amax_ds) {
   long long row = blockIdx.x * (long long)(NT / 32) + (threadIdx.x >> 5);
   if (row >= rows) return;
   int lane = threadIdx.x & 31;
@@ -238,7 +239,13 @@ __global__ void softmax_bwd_kernel(const float* __restrict__ p, const float* __r
   float dot = 0.f;
   for (int j = lane; j < cols; j += 32) dot += pr[j] * dr[j];
   dot = warp_sum(dot);
-  for (int j = lane; j < cols; j += 32) o[j] = pr[j] * (dr[j] - dot);
+  float amax = 0.f;
+  for (int j = lane; j < cols; j += 32) {
+    const float v = pr[j] * (dr[j] - dot);
+    o[j] = v;
+    amax = fmaxf(amax, fabsf(v));
+  }
+  if (amax_ds) amax_commit(amax_ds, amax);
 }
 __global__ void ddim_step_kernel(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ nz,
                                  float* __restrict__ out, long long n, float sb, float sa, float clip, float sap, float dir, float sigma) {
@@ -358,11 +365,11 @@ extern "C" int dp_softmax_fwd(const float* s, float* p, int64_t rows, int32_t co
   softmax_fwd_kernel<<<(unsigned)nb, NT, 0, (cudaStream_t)st>>>(s, p, rows, cols);
   return dp_check_launch();
 }
-extern "C" int dp_softmax_bwd(const float* p, const float* dp, float* ds, int64_t rows, int32_t cols, dp_stream_t st) {
+extern "C" int dp_softmax_bwd(const float* p, const float* dp, float* ds, int64_t rows, int32_t cols, uint32_t* amax_ds, dp_stream_t st) {
   DP_REQUIRE(p && dp && ds, DP_ERR_NULL); DP_REQUIRE(rows > 0 && cols > 0, DP_ERR_SHAPE);
   long long nb = (rows + NT / 32 - 1) / (NT / 32);
   DP_REQUIRE(nb < (1ll << 31), DP_ERR_SHAPE);
-  softmax_bwd_kernel<<<(unsigned)nb, NT, 0, (cudaStream_t)st>>>(p, dp, ds, rows, cols);
+  softmax_bwd_kernel<<<(unsigned)nb, NT, 0, (cudaStream_t)st>>>(p, dp, ds, rows, cols, amax_ds);
   return dp_check_launch();
 }
 extern "C" int dp_ddim_step(const float* x, const float* eps, const float* noise, float* out, int64_t n, float sqrt_beta_t,

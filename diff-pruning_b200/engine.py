@@ -88,7 +88,8 @@ class BItem:
 
     def __init__(self):
         self.steps: List[Step] = []
-        self.writes: List[Tuple[View, Callable[[bool], None]]] = []
+        # (gradient target view, setter(first_write: bool), amax_setter(slot) or None when the writing kernel cannot report max|value|)
+        self.writes: List[Tuple[View, Callable[[bool], None], Optional[Callable[[int], None]]]] = []
 
 
 def _copy_args(a):
@@ -98,6 +99,8 @@ def _copy_args(a):
 
 
 AMAX_SLOTS = 8192  # capacity of a plan's amax-slot arrays (one uint32 per tensor-core operand use)
+AUDIT_SLOTS = False  # tests: plans built while this is set check every amax slot against torch.amax of its operand right before the
+                     # consuming launch (eager runs only: the check synchronises)
 SPLITK = True      # small-M fprop / dgrad launches split their K loop over idle SMs (dp_conv_splitk_workspace_floats)
 ARENA_ALIGN = 64   # floats: every parameter's slice of a flat arena starts on a 256-byte boundary
 
@@ -153,6 +156,18 @@ class Plan:
         self._wslots = torch.zeros(AMAX_SLOTS, device=self.dev, dtype=torch.int32)
         self._n_slots = self._n_wslots = 0
         self._amax_fwd: Dict[Tuple[int, int, int, int], int] = {}
+        # producer-filled slots, keyed by the activation tensor's base address: forward = every kernel writing into the tensor adds
+        # max|written| (an upper bound for any sub-view a consumer reads); backward = the same for the tensor's gradient buffer, bound
+        # at _finalize_build once all writers are known (a writer without amax support keeps the consumer's dp_amax launch)
+        self._slot_tags: List[str] = []
+        self._fslot: Dict[int, int] = {}
+        self._fslot_bad: set = set()
+        self._bslot: Dict[int, dict] = {}
+        one = torch.tensor([1.0], dtype=torch.float32).view(torch.int32).to(self.dev)
+        self._wslots[AMAX_SLOTS - 1:] = one            # constant slot: bound 1.0 (softmax probabilities)
+        self._one_slot = self._wslots.data_ptr() + 4 * (AMAX_SLOTS - 1)
+        self.audit_log: list = []
+        self.audit = AUDIT_SLOTS
         self.params = [p for p in model.parameters()]
         self.dropout_seed_dev = torch.zeros(1, device=self.dev, dtype=torch.int64)
         self._n_dropout = 0
@@ -289,7 +304,7 @@ class Plan:
             na, nb = RS * K * lib.dp_tc_weight_row(Cin), RS * Cin * lib.dp_tc_weight_row(K)   # rows padded for aligned TMA box rows
             wslot = self._wslots.data_ptr() + 4 * self._n_wslots
             self._n_wslots += 1
-            assert self._n_wslots <= AMAX_SLOTS
+            assert self._n_wslots < AMAX_SLOTS
             # fp16 kc_hi kc_lo ck_hi ck_lo + the weight's amax slot (one power-of-two scale per tensor)
             tc = tuple(torch.empty(n, device=self.dev, dtype=torch.float16) for n in (na, na, nb, nb)) + (wslot,)
             self._rec(self.pack, lambda s, w=w, K=K, Cin=Cin, R=R, S=S, t=tc:
@@ -298,8 +313,9 @@ class Plan:
         self._packs[id(w)] = (wck, wkc, tc)
         return wck, wkc, tc
 
-    def _new_slot(self) -> int:
+    def _new_slot(self, tag: str = "") -> int:
         """Device address of a fresh per-pass amax slot (zeroed by the first launch of every forward)."""
+        self._slot_tags.append(tag)
         slot = self._slots.data_ptr() + 4 * self._n_slots
         self._n_slots += 1
         assert self._n_slots <= AMAX_SLOTS, "raise engine.AMAX_SLOTS"
@@ -310,12 +326,74 @@ class Plan:
         written once per pass, so consumers of the same view share one slot (fwd_key)."""
         if fwd_key is not None and fwd_key in self._amax_fwd:
             return self._amax_fwd[fwd_key]
-        slot = self._new_slot()
+        slot = self._new_slot(f"amax {rows}x{cols}")
         lib = self.lib
         self._rec(lst, lambda s, g=ptr_get: lib.dp_amax(g(), ld, rows, cols, slot, s), what="amax")
         if fwd_key is not None:
             self._amax_fwd[fwd_key] = slot
         return slot
+
+    def _out_slot(self, out: View) -> Optional[int]:
+        """Producer side (forward): the slot of the tensor `out` lives in; the producing kernel adds max|values written|."""
+        if not self.tc:
+            return None
+        k = out.t.data_ptr()
+        if k not in self._fslot:
+            self._fslot[k] = self._new_slot(f"out {out.N}x{out.H}x{out.W}x{out.t.shape[-1]}")
+        return self._fslot[k]
+
+    def _alias_slot(self, out: View, src: View):
+        """`out` holds copies of src's values only (nearest-neighbour upsampling): src's bound is out's bound."""
+        k = src.t.data_ptr()
+        if self.tc and k in self._fslot and k not in self._fslot_bad:
+            self._fslot[out.t.data_ptr()] = self._fslot[k]
+
+    def _unslotted(self, out: View):
+        """A kernel without amax support writes into this tensor: consumers must measure their operand themselves."""
+        self._fslot_bad.add(out.t.data_ptr())
+
+    def _x_slot(self, x: View) -> int:
+        """Consumer side (forward): the producer-filled slot of x's tensor, else a dp_amax launch over the view."""
+        k = x.t.data_ptr()
+        if k in self._fslot and k not in self._fslot_bad:
+            slot = self._fslot[k]
+        else:
+            slot = self._amax(self.fwd, lambda p=x.ptr: p, x.ld, x.rows, x.C, fwd_key=(x.ptr, x.ld, x.rows, x.C))
+        self._audit(self.fwd, slot, lambda x=x: x.torch())
+        return slot
+
+    def _dy_slot(self, steps: List[Step], v: View) -> int:
+        """Consumer side (backward): slot of max|v.grad|.  The writers of v.grad are built later; _finalize_build hands them the slot and
+        drops the dp_amax launch recorded here when every one of them can report its own maximum."""
+        g = self.gradof(v)
+        rec = self._bslot.get(v.t.data_ptr())
+        if rec is None:
+            rec = self._bslot[v.t.data_ptr()] = {"slot": self._new_slot(f"grad {v.N}x{v.H}x{v.W}x{v.t.shape[-1]}"), "flags": []}
+        slot, flag, lib = rec["slot"], [True], self.lib
+        rec["flags"].append(flag)
+
+        def run(s, flag=flag, g=g):
+            if flag[0]:
+                L.check(lib.dp_amax(g.ptr, g.ld, g.rows, g.C, slot, s), "amax")
+        run.what, run.info = "amax", ""
+        steps.append(run)
+        self._audit(steps, slot, lambda g=g: g.torch())
+        return slot
+
+    def _audit(self, lst: List[Step], slot: int, get):
+        if not self.audit:
+            return
+
+        def run(s, slot=slot, get=get):
+            torch.cuda.current_stream().synchronize()
+            arr = self._slots if self._slots.data_ptr() <= slot < self._slots.data_ptr() + 4 * AMAX_SLOTS else self._wslots
+            bound = float(arr.view(torch.float32)[(slot - arr.data_ptr()) // 4])
+            true = float(get().abs().max())
+            if not (bound >= true):
+                raise AssertionError(f"amax slot {bound} below the operand's maximum {true}")
+            self.audit_log.append((bound, true))
+        run.what, run.info = "audit", ""
+        lst.append(run)
 
     # ------------------------------------------------------------------ bf16 tier plumbing
     def _bf_geom(self, x: View, out: View, w: nn.Parameter, stride: int, pad: int) -> "L.ConvBf16Args":
@@ -396,11 +474,10 @@ class Plan:
     def conv(self, x: View, w: nn.Parameter, b: Optional[nn.Parameter], out: View, stride=1, pad=1,
              rowadd: Optional[View] = None, residual: Optional[View] = None, accumulate_out=False, need_dx=True,
              dx_scratch: Optional[str] = None, seg_out: Optional[str] = None, dy_dense: Optional[str] = None,
-             dx_into: Optional[View] = None, dy_slot: Optional[int] = None):
+             dx_into: Optional[View] = None):
         """Records fprop (fwd) and bias-grad / wgrad / dgrad (bwd).
         dgrad target: `dx_scratch` (shared dense scratch [rows][C]) or the gradient view of `dx_into` / `x`.
-        dy source: out.grad, or the dense scratch `dy_dense` ([rows][K]) when the consumer provides it.
-        dy_slot: amax slot of dy that the (single) producer of out.grad fills itself (gn_bwd(amax_dx=)); else a dp_amax launch is recorded."""
+        dy source: out.grad, or the dense scratch `dy_dense` ([rows][K]) when the consumer provides it."""
         lib = self.lib
         K, Cin = w.shape[0], w.shape[1]
         R = w.shape[2] if w.dim() == 4 else 1
@@ -413,13 +490,14 @@ class Plan:
         a = L.ConvArgs()
         if wtc is not None:
             a.w_tc_hi, a.w_tc_lo, a.amax_w = wtc[0].data_ptr(), wtc[1].data_ptr(), wtc[4]
-            a.amax_x = self._amax(self.fwd, lambda p=x.ptr: p, x.ld, x.rows, x.C, fwd_key=(x.ptr, x.ld, x.rows, x.C))
+            a.amax_x = self._x_slot(x)
         a.N, a.H, a.W, a.C = x.N, x.H, x.W, x.C
         a.P, a.Q, a.K = out.H, out.W, K
         a.R, a.S, a.stride, a.pad_t, a.pad_l = R, S, stride, pad, pad
         a.flags = 1 if accumulate_out else 0
         a.splits = 1
         a.x, a.ldx, a.y, a.ldy = x.ptr, x.ld, out.ptr, out.ld
+        a.amax_out = self._out_slot(out)
         a.w = wck.data_ptr()
         a.bias = b.data_ptr() if b is not None else None
         if rowadd is not None:
@@ -463,9 +541,11 @@ class Plan:
         chunks = max(1, out.rows // 64)              # tensor-core wgrad walks 64-pixel chunks
         splits = _wgrad_splits(tiles, chunks)
         self.scratch("wgrad_ws", splits * K * TC)
-        amax_dy = (dy_slot or self._amax(steps, dy_get, dy_ld, out.rows, K)) if wtc is not None else None
+        amax_dy = None
+        if wtc is not None:
+            amax_dy = self._amax(steps, dy_get, dy_ld, out.rows, K) if dy_dense is not None else self._dy_slot(steps, out)
         wa = _copy_args(a)
-        wa.amax_y = amax_dy
+        wa.amax_y, wa.amax_out = amax_dy, None
         wa.flags, wa.splits = 0, splits
         wa.ldy = dy_ld
         wa.rowadd, wa.residual, wa.bias = None, None, None
@@ -487,6 +567,7 @@ class Plan:
             if wtc is not None:
                 da.w_tc_hi, da.w_tc_lo, da.amax_y = wtc[2].data_ptr(), wtc[3].data_ptr(), amax_dy
             da.flags = 0
+            da.amax_out = None
             da.rowadd, da.residual, da.bias = None, None, None
             self._late.append(lambda da=da, g=dy_get: setattr(da, "y", g()))
             if dx_scratch is not None:
@@ -497,7 +578,8 @@ class Plan:
                 tgt = dx_into if dx_into is not None else x
                 gx = self.gradof(tgt)
                 da.x, da.ldx = gx.ptr, gx.ld
-                it.writes.append((tgt, lambda init, da=da: setattr(da, "flags", 1 if init else 0)))
+                it.writes.append((tgt, lambda init, da=da: setattr(da, "flags", 1 if init else 0),
+                                  lambda slot, da=da: setattr(da, "amax_out", slot)))
             da.workspace = None
             self._splitk(da, 1)
             self._rec(steps, lib.dp_conv2d_dgrad, da, "conv dgrad", info)
@@ -518,6 +600,7 @@ class Plan:
         kc, ck = self._packed_bf16(w)
         xb, ldxb = self._bf16_of(x)
         self.n_bf16_convs += 1
+        self._unslotted(out)        # the bf16 kernels do not report max|out|
         a = self._bf_geom(x, out, w, stride, pad)
         a.flags = 1 if accumulate_out else 0
         a.x_bf16, a.ldx = xb.data_ptr(), ldxb
@@ -581,7 +664,7 @@ class Plan:
                 tgt = dx_into if dx_into is not None else x
                 gx = self.gradof(tgt)
                 da.out, da.ld_out = gx.ptr, gx.ld
-                it.writes.append((tgt, lambda init, da=da: setattr(da, "flags", 1 if init else 0)))
+                it.writes.append((tgt, lambda init, da=da: setattr(da, "flags", 1 if init else 0), None))
             self._rec(steps, lib.dp_conv2d_dgrad_bf16, da, "conv dgrad", info)
 
     GN_MAX_C = 1024      # channels one dp_groupnorm launch handles (256 threads x 4 channel slots); wider tensors are split by groups
@@ -607,10 +690,7 @@ class Plan:
             self._bf_cache[(out.t.data_ptr(), out.off, out.C)] = (yb, ldyb)
         cp, gp = x.C // parts, G // parts
         args = []
-        yslot = None
-        if self.tc and not bf16_only:   # the tensor-core convolutions that read `out` find its amax slot already filled
-            yslot = self._new_slot()
-            self._amax_fwd[(out.ptr, out.ld, out.rows, out.C)] = yslot
+        yslot = self._out_slot(out) if not bf16_only else None   # the tensor-core convolutions that read `out` find its slot filled
         for i in range(parts):
             c0 = i * cp
             a = L.GnArgs()
@@ -635,16 +715,15 @@ class Plan:
         return args
 
     def gn_bwd(self, a_fwd, x: View, norm: nn.Module, dy_get: Callable[[], int], lddy: int,
-               add2: Optional[View] = None, amax_dx: Optional[int] = None):
-        """x.grad (=|+=) GN(+SiLU)(+dropout) backward (+ add2); dgamma/dbeta += .  a_fwd: what gn() returned.
-        amax_dx: amax slot the kernel fills with max|x.grad| — only when this call is the ONLY writer of x.grad (see conv(dy_slot=))."""
+               add2: Optional[View] = None):
+        """x.grad (=|+=) GN(+SiLU)(+dropout) backward (+ add2); dgamma/dbeta += .  a_fwd: what gn() returned."""
         lib = self.lib
         gx = self.gradof(x)
         it = self._bitem()
         parts = []
         for a_part, c0 in a_fwd:
             b = _copy_args(a_part)
-            b.amax_y, b.amax_dx = None, amax_dx
+            b.amax_y, b.amax_dx = None, None
             b.dx, b.lddx, b.lddy = gx.ptr + 4 * c0, gx.ld, lddy
             if add2 is not None:
                 b.dx_add2, b.ldadd2 = add2.ptr + 4 * c0, add2.ld
@@ -657,7 +736,7 @@ class Plan:
             if init:
                 for b, c0 in parts:
                     b.dx_add, b.ldadd = gx.ptr + 4 * c0, gx.ld
-        it.writes.append((x, resolve))
+        it.writes.append((x, resolve, lambda slot, parts=parts: [setattr(b, "amax_dx", slot) for b, _ in parts]))
 
     # ------------------------------------------------------------------ blocks
     def resnet(self, m: ResnetBlock2D, x: View, out: View):
@@ -677,12 +756,10 @@ class Plan:
         # time_emb_proj(silu(temb)) -> per-image row added in conv1's epilogue; its dY are conv1's per-image sums
         self.conv(self.silu_temb, m.time_emb_proj.weight, m.time_emb_proj.bias, tp, pad=0, dy_dense="seg",
                   dx_into=self.silu_temb)
-        # h1 feeds norm2 only, so norm2's backward writes all of h1.grad = conv1's dy and leaves its amax on the way
-        s_h1 = self._new_slot() if (self.tc and self.need_grad) else None
-        self.conv(a1, m.conv1.weight, m.conv1.bias, h1, rowadd=tp, seg_out="seg", dx_scratch="da", dy_slot=s_h1)
+        self.conv(a1, m.conv1.weight, m.conv1.bias, h1, rowadd=tp, seg_out="seg", dx_scratch="da")
         g2 = self.gn(h1, m.norm2, a2, silu=True, dropout_p=p_drop, bf16_only=self.conv_bf16_ok(a2, out, m.conv2.weight))
         if self.need_grad:
-            self.gn_bwd(g2, h1, m.norm2, da, Cout, amax_dx=s_h1)
+            self.gn_bwd(g2, h1, m.norm2, da, Cout)
         if has_sc:
             self.conv(a2, m.conv2.weight, m.conv2.bias, out, dx_scratch="da")
             self.conv(x, m.conv_shortcut.weight, m.conv_shortcut.bias, out, pad=0, accumulate_out=True)
@@ -746,7 +823,7 @@ class Plan:
                                                     dv.ptr, dv.ld, T * dv.ld, 1.0), "attn dV")
             self._rec(st, lib.dp_gemm_batched, gemm(T, T, inner, do.ptr, do.ld, 1, T * do.ld, v.ptr, 1, v.ld, T * v.ld,
                                                     dPp, T, T * T, 1.0), "attn dP")
-            self._rec(st, lambda s: lib.dp_softmax_bwd(Pp, dPp, dPp, N * T, T, s), what="softmax bwd")
+            self._rec(st, lambda s: lib.dp_softmax_bwd(Pp, dPp, dPp, N * T, T, None, s), what="softmax bwd")
             self._rec(st, lib.dp_gemm_batched, gemm(T, inner, T, dPp, T, 1, T * T, k.ptr, k.ld, 1, T * k.ld,
                                                     dq.ptr, dq.ld, T * dq.ld, sc), "attn dQ")
             self._rec(st, lib.dp_gemm_batched, gemm(T, inner, T, dPp, 1, T, T * T, q.ptr, q.ld, 1, T * q.ld,
@@ -754,58 +831,63 @@ class Plan:
 
     def _attention_core_tc(self, N, H, W, T, inner, q, k, v, o, P, sc):
         """softmax(scale q k^T) v and its backward on the tensor-core NT GEMM (dp_gemm_nt_tc): every product is written as
-        C = A B^T with a K-contiguous activation A (TMA box of the token grid) and a pre-split hi/lo B built by
+        C = A B^T with a K-contiguous activation A (TMA box of the token grid) and a pre-split fp16 hi/lo' B built by
         dp_split_h3 (optionally transposing); P^T / dS^T come from dp_transpose_batched.
           fwd : S = q k^T          B = split(k)            O  = P v         B = split^T(v)
           bwd : dV = P^T dO        A = P^T, B = split^T(dO)   dP = dO v^T    B = split(v)
-                dQ = dS k          B = split^T(k)            dK = dS^T q    A = dS^T, B = split^T(q)"""
+                dQ = dS k          B = split^T(k)            dK = dS^T q    A = dS^T, B = split^T(q)
+        Operand amax slots: q, k, v, dO come from the kernels that wrote those tensors, P / P^T are bounded by 1, dS by softmax_bwd."""
         lib = self.lib
         i8, t8 = (inner + 7) // 8 * 8, (T + 7) // 8 * 8
         nsplit = N * max(T * i8, inner * t8)          # fp16 elements; the scratch is counted in floats
         self.scratch("att_hi", (nsplit + 1) // 2); self.scratch("att_lo", (nsplit + 1) // 2); self.scratch("att_t", N * T * T)
         Pp = P.data_ptr()
-        bslot = [None]
 
-        def split(lst, src: View, transpose: int):   # src is an [N][T][inner] activation view
-            slot = self._amax(lst, lambda p=src.ptr: p, src.ld, N * T, inner)
-            bslot[0] = slot
+        def split(lst, src: View, slot: int, transpose: int):   # src is an [N][T][inner] activation view
             self._rec(lst, lambda s, p=src.ptr, ld=src.ld, tr=transpose: lib.dp_split_h3(
                 p, ld, T * ld, N, T, inner, tr, slot, self.sptr("att_hi"), self.sptr("att_lo"), s), what="attn split")
 
-        def gemm(lst, A_get, ld_a, Kg, Nn, C_ptr, ldc, alpha, what):
+        def gemm(lst, A_get, ld_a, Kg, Nn, C_ptr, ldc, alpha, what, slot_a, slot_b, slot_out=None):
             ga = L.GemmNtArgs()
             ga.batch, ga.H, ga.W, ga.Kg, ga.N = N, H, W, Kg, Nn
             ga.ld_a, ga.C, ga.ldc, ga.alpha = ld_a, C_ptr, ldc, alpha
-            ga.amax_a, ga.amax_b = self._amax(lst, A_get, ld_a, N * T, Kg), bslot[0]
+            ga.amax_a, ga.amax_b, ga.amax_out = slot_a, slot_b, slot_out
             self._late.append(lambda ga=ga, g=A_get: (setattr(ga, "A", g()), setattr(ga, "b_hi", self.sptr("att_hi")),
                                                       setattr(ga, "b_lo", self.sptr("att_lo"))))
             self._rec(lst, lib.dp_gemm_nt_tc, ga, what)
+            return ga
 
         f = self.fwd
-        split(f, k, 0)
-        gemm(f, lambda: q.ptr, q.ld, inner, T, Pp, T, sc, "attn qk (tc)")
+        sq, sk, sv, one = self._x_slot(q), self._x_slot(k), self._x_slot(v), self._one_slot
+        split(f, k, sk, 0)
+        gemm(f, lambda: q.ptr, q.ld, inner, T, Pp, T, sc, "attn qk (tc)", sq, sk)
         self._rec(f, lambda s: lib.dp_softmax_fwd(Pp, Pp, N * T, T, s), what="softmax")
-        split(f, v, 1)
-        gemm(f, lambda: Pp, T, T, inner, o.ptr, o.ld, 1.0, "attn pv (tc)")
+        split(f, v, sv, 1)
+        gemm(f, lambda: Pp, T, T, inner, o.ptr, o.ld, 1.0, "attn pv (tc)", one, sv, self._out_slot(o))
         if not self.need_grad:
             return
         dq, dk, dv, do = (self.gradof(t) for t in (q, k, v, o))
         dP = torch.empty_like(P)
         self._keep.append(dP)
         dPp = dP.data_ptr()
-        st = self._bitem().steps
+        it = self._bitem()
+        st = it.steps
         tptr = lambda: self.sptr("att_t")
+        sdo, sds = self._dy_slot(st, o), self._new_slot("dS")
         self._rec(st, lambda s: lib.dp_transpose_batched(Pp, tptr(), N, T, T, s), what="attn transpose")
-        split(st, do, 1)
-        gemm(st, tptr, T, T, inner, dv.ptr, dv.ld, 1.0, "attn dV (tc)")
-        split(st, v, 0)
-        gemm(st, lambda: do.ptr, do.ld, inner, T, dPp, T, 1.0, "attn dP (tc)")
-        self._rec(st, lambda s: lib.dp_softmax_bwd(Pp, dPp, dPp, N * T, T, s), what="softmax bwd")
-        split(st, k, 1)
-        gemm(st, lambda: dPp, T, T, inner, dq.ptr, dq.ld, sc, "attn dQ (tc)")
+        split(st, do, sdo, 1)
+        g_dv = gemm(st, tptr, T, T, inner, dv.ptr, dv.ld, 1.0, "attn dV (tc)", one, sdo)
+        split(st, v, sv, 0)
+        gemm(st, lambda: do.ptr, do.ld, inner, T, dPp, T, 1.0, "attn dP (tc)", sdo, sv)
+        self._rec(st, lambda s: lib.dp_softmax_bwd(Pp, dPp, dPp, N * T, T, sds, s), what="softmax bwd")
+        split(st, k, sk, 1)
+        g_dq = gemm(st, lambda: dPp, T, T, inner, dq.ptr, dq.ld, sc, "attn dQ (tc)", sds, sk)
         self._rec(st, lambda s: lib.dp_transpose_batched(dPp, tptr(), N, T, T, s), what="attn transpose")
-        split(st, q, 1)
-        gemm(st, tptr, T, T, inner, dk.ptr, dk.ld, sc, "attn dK (tc)")
+        split(st, q, sq, 1)
+        g_dk = gemm(st, tptr, T, T, inner, dk.ptr, dk.ld, sc, "attn dK (tc)", sds, sq)
+        # dq / dk / dv are written (=) exactly once, by these GEMMs, which report their maxima to the 1x1 convolutions' dy slots
+        for t_, g_ in ((q, g_dq), (k, g_dk), (v, g_dv)):
+            it.writes.append((t_, lambda init: None, lambda slot, g_=g_: setattr(g_, "amax_out", slot)))
 
     # ------------------------------------------------------------------ whole network
     def _build(self):
@@ -940,10 +1022,11 @@ class Plan:
                 xx = x
                 self._rec(self.fwd, lambda s, xx=xx, up=up: lib.dp_upsample2x_fwd(xx.ptr, xx.ld, up.ptr, up.ld, xx.N, xx.H, xx.W, xx.C, s),
                           what="upsample")
+                self._alias_slot(up, xx)
                 if self.need_grad:
                     it = self._bitem()
                     accf = [0]
-                    it.writes.append((xx, lambda init, accf=accf: accf.__setitem__(0, 1 if init else 0)))
+                    it.writes.append((xx, lambda init, accf=accf: accf.__setitem__(0, 1 if init else 0), None))
                     self._rec(it.steps, lambda s, xx=xx, up=up, accf=accf: lib.dp_upsample2x_bwd(
                         self.gradof(up).ptr, up.ld, self.gradof(xx).ptr, self.gradof(xx).ld, xx.N, xx.H, xx.W, xx.C, accf[0], s),
                         what="upsample bwd")
@@ -973,9 +1056,21 @@ class Plan:
             self.g_mark(self.silu_temb)   # zeroed at backward start; every resnet accumulates into it
             self.g_mark(self.y_out)       # loaded from the loss gradient
             for it in reversed(self.bwd):
-                for view, setter in it.writes:
+                for view, setter, _ in it.writes:
                     setter(self.g_is_init(view))
                     self.g_mark(view)
+            # gradient amax slots: when every writer of a tensor's gradient reports its own maximum, the consumers' dp_amax launches go
+            writers: Dict[int, list] = {}
+            for it in self.bwd:
+                for view, _, amax_setter in it.writes:
+                    writers.setdefault(view.t.data_ptr(), []).append(amax_setter)
+            for key, rec in self._bslot.items():
+                ws = writers.get(key, [])
+                if ws and all(w is not None for w in ws):
+                    for w in ws:
+                        w(rec["slot"])
+                    for flag in rec["flags"]:
+                        flag[0] = False
         self._packed_version = None
         if self._n_slots:       # every activation / gradient amax slot starts the pass at zero
             zero: List[Step] = []
@@ -1037,7 +1132,7 @@ class Plan:
         self._rec(self.fwd, lambda s: lib.dp_geglu_fwd(u.ptr, u.ld, gg.ptr, gg.ld, rows, I, s), what="geglu")
         if self.need_grad:
             it = self._bitem()
-            it.writes.append((u, lambda init: None))        # du is written (=) exactly once, by this op
+            it.writes.append((u, lambda init: None, None))        # du is written (=) exactly once, by this op
             self._rec(it.steps, lambda s: lib.dp_geglu_bwd(u.ptr, u.ld, self.gradof(gg).ptr, gg.ld, self.gradof(u).ptr, u.ld, rows, I, s),
                       what="geglu bwd")
         self.conv(gg, lin2.weight, lin2.bias, x3, pad=0, residual=x2)
@@ -1149,10 +1244,11 @@ class Plan:
                     xx = x
                     self._rec(self.fwd, lambda s, xx=xx, up=up: lib.dp_upsample2x_fwd(xx.ptr, xx.ld, up.ptr, up.ld, xx.N, xx.H, xx.W, xx.C, s),
                               what="upsample")
+                    self._alias_slot(up, xx)
                     if self.need_grad:
                         it = self._bitem()
                         accf = [0]
-                        it.writes.append((xx, lambda init, accf=accf: accf.__setitem__(0, 1 if init else 0)))
+                        it.writes.append((xx, lambda init, accf=accf: accf.__setitem__(0, 1 if init else 0), None))
                         self._rec(it.steps, lambda s, xx=xx, up=up, accf=accf: lib.dp_upsample2x_bwd(
                             self.gradof(up).ptr, up.ld, self.gradof(xx).ptr, self.gradof(xx).ld, xx.N, xx.H, xx.W, xx.C, accf[0], s),
                             what="upsample bwd")

@@ -78,6 +78,8 @@ typedef struct dp_conv_args {
    * max|v| over the operand — amax_x for x, amax_y for y / dy (both accumulated by dp_amax), amax_w for the packed weight
    * (written by dp_pack_conv_weight_tc).  A NULL slot sends the launch to the exact-fp32 SIMT kernel. */
   const uint32_t* amax_x; const uint32_t* amax_y; const uint32_t* amax_w;
+  uint32_t* amax_out;  /* optional: fprop accumulates max|y| of what it wrote, dgrad max|dx| (dp_amax semantics), on every kernel
+                          path — the consumer of that tensor then needs no dp_amax pass */
 } dp_conv_args;
 
 int dp_conv2d_fprop(const dp_conv_args* a, dp_stream_t stream);
@@ -183,6 +185,7 @@ typedef struct dp_gemm_nt_args {
   float* C; int64_t ldc;
   float alpha;
   const uint32_t* amax_a; const uint32_t* amax_b;
+  uint32_t* amax_out;  /* optional: accumulates max|C| */
 } dp_gemm_nt_args;
 int dp_gemm_nt_tc(const dp_gemm_nt_args* a, dp_stream_t stream);
 /* fp16 hi / lo' split (see dp_pack_conv_weight_tc) of a batched [rows][cols] fp32 matrix (row stride ld, batch stride bs) with the scale of
@@ -196,7 +199,7 @@ int dp_transpose_batched(const float* in, float* out, int32_t batch, int32_t row
 /* row softmax over [rows][cols] fp32 (attention_processor.py:352, upcast_softmax) and its backward
  * dS = P * (dP - sum_j dP*P); in-place allowed (out == in). */
 int dp_softmax_fwd(const float* s, float* p, int64_t rows, int32_t cols, dp_stream_t stream);
-int dp_softmax_bwd(const float* p, const float* dp, float* ds, int64_t rows, int32_t cols, dp_stream_t stream);
+int dp_softmax_bwd(const float* p, const float* dp, float* ds, int64_t rows, int32_t cols, uint32_t* amax_ds, dp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * GroupNorm (+ fused SiLU).  Replaces aten::native_group_norm(+backward) and aten::silu(+backward) at

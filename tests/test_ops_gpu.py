@@ -179,7 +179,7 @@ def test_softmax_fwd_bwd(lib, rows, cols):
     assert lib.dp_softmax_fwd(sd.data_ptr(), sd.data_ptr(), rows, cols, S()) == 0
     assert rel_err(sd.cpu(), p) < 1e-6
     gd = gp.cuda()
-    assert lib.dp_softmax_bwd(sd.data_ptr(), gd.data_ptr(), gd.data_ptr(), rows, cols, S()) == 0
+    assert lib.dp_softmax_bwd(sd.data_ptr(), gd.data_ptr(), gd.data_ptr(), rows, cols, None, S()) == 0
     assert rel_err(gd.cpu(), s.grad) < 5e-6
 
 

@@ -580,3 +580,40 @@ def test_ldm_unet_two_accumulated_passes_vs_reference():
         loss.backward()
     assert loss.item() == pytest.approx(G["losses"][1], rel=5e-6)
     assert worst_grad_err(((k, p.grad) for k, p in m.named_parameters()), G["grads"]) < 1e-4
+
+
+@pytest.mark.parametrize("family", ["unet2d_c1", "unet2d_lsun_block", "ldm_tiny"])
+def test_amax_slots_bound_their_operands(family):
+    """Every tensor-core launch scales its operands by the power of two taken from an amax slot.  Most slots are filled by the kernel
+    that WROTE the tensor (convolution / GEMM epilogues, GroupNorm, softmax backward) instead of a separate dp_amax pass: with
+    engine.AUDIT_SLOTS the plan compares each slot with torch's max|operand| right before the consuming launch (eager pass)."""
+    from diff_pruning_b200 import engine
+    engine.AUDIT_SLOTS = True
+    try:
+        if family == "ldm_tiny":
+            from test_oracle_golden import ldm_tiny_model
+            from diff_pruning_b200 import ldm
+            G = load_golden("ldm_tiny.pt")
+            m = ldm_tiny_model(G).cuda()
+            clean, noise = inputs(2, 16)
+            sc = TaylorScorer(m, clean.cuda(), noise.cuda(), alphas_cumprod=ldm.ldm_alphas_cumprod(), use_graph=False, context=G["context"].cuda())
+        elif family == "unet2d_c1":
+            m = build(dp.CIFAR10_DDPM_CONFIG)
+            clean, noise = inputs(8, 32)
+            sc = TaylorScorer(m, clean.cuda(), noise.cuda(), use_graph=False)
+        else:       # six levels, up / down sampling at every resolution from 64x64 to 2x2, attention at level 4
+            cfg = dict(dp.LSUN256_DDPM_CONFIG, block_out_channels=(32, 32, 64, 64, 128, 128), sample_size=64)
+            m = build(cfg, seed=3)
+            clean, noise = inputs(2, 64)
+            sc = TaylorScorer(m, clean.cuda(), noise.cuda(), use_graph=False)
+        for t in (3, 600):
+            sc.step(t)
+        log = sc.plan.audit_log
+        assert len(log) > 50, len(log)
+        # the bounds are tight where the producer wrote the whole tensor, and never more than the tensor they live in allows
+        assert all(b >= v for b, v in log)
+        standalone = sum(1 for f in sc.plan.fwd + sc.plan.bwd_steps if getattr(f, "what", "") == "amax")
+        convs = sum(1 for f in sc.plan.fwd + sc.plan.bwd_steps if getattr(f, "what", "").startswith("conv fprop"))
+        assert standalone < 2 * convs, (standalone, convs)
+    finally:
+        engine.AUDIT_SLOTS = False

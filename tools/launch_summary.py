@@ -23,8 +23,8 @@ for row in csv.DictReader(lines):
         name = "conv_tc_kernel<BN=%s> (tcgen05 3xTF32 fprop/dgrad)" % m.group(1)
     m = re.search(r"wgrad_tc_kernel", row["Kernel Name"])
     if m:
-        name = "wgrad_tc_kernel (tcgen05 3xTF32 wgrad)"
-    for kn, label in (("conv_tc_ps_kernel", "conv_tc_ps_kernel (tcgen05 3xTF32 fprop/dgrad, persistent)"),
+        name = "wgrad_tc_kernel (tcgen05 kind::f16, 3-product fp16 split: wgrad)"
+    for kn, label in (("conv_tc_ps_kernel", "conv_tc_ps_kernel (tcgen05 kind::f16, 3-product fp16 split: fprop/dgrad/NT GEMM, persistent)"),
                       ("conv_tc_ts_kernel", "conv_tc_ts_kernel<64> (tcgen05 3xTF32 fprop/dgrad, <= 64 channels)"),
                       ("conv_bf16_kernel", "conv_bf16_kernel (tcgen05 kind::f16 fprop/dgrad, persistent)"),
                       ("wgrad_bf16_kernel", "wgrad_bf16_kernel (tcgen05 kind::f16 wgrad)")):
