@@ -109,6 +109,14 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// A operand from TENSOR memory (packed fp16 pairs, 8 columns per 16-element K step)
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
 // amax slot -> power-of-two scale.  E = biased exponent of the bound (|v| < 2^(E-126)), clamped so that both factors are normal floats;
 // up = 2^(140-E) brings the operand below 2^14 (fp16 overflows at 65504), dn = 2^(E-140) undoes it in the epilogue.
 __device__ __forceinline__ int amax_exponent(const uint32_t* slot) {
@@ -163,14 +171,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {  
 
 // ------------------------------------------------------------------------------------------------ persistent variant
 // One CTA per SM loops over (tile, K split) work items (static stride), 10 warps: TMA producer | MMA issuer | 4 splitter warps |
-// 4 epilogue warps.  Stage = [A box k 0..31 -> a_hi | A box k 32..63 -> a_lo' | b_hi | b_lo'] x 16 KB: splitter thread r owns pixel row r
-// of both raw boxes (2 x 128 B, TMA 128B-swizzled), reads its 64 floats and overwrites the same two rows with the row's 64 fp16 hi
-// values and 64 fp16 lo' values in the K-major SWIZZLE_128B layout the MMA descriptors expect — no second buffer, no cross-thread hazard.  Two accumulator sets in TMEM (2 x [main 128 | correction 128] = 512 columns) let the epilogue of tile
-// i (TMEM -> registers -> global, ~20-50 % of a short-K tile) overlap the main loop of tile i+1; barrier init, TMEM
-// allocation and descriptor prefetch are paid once per SM instead of once per tile.  A operand hi/lo in shared memory
-// (SS mode; the TS variant needs the TMEM columns the second accumulator set occupies).
+// 4 epilogue warps.  Stage in shared memory = [A box k 0..31 | A box k 32..63 | b_hi | b_lo'] x 16 KB.  Splitter thread <-> pixel row
+// reads its 64 raw floats (2 x 128 B, TMA 128B-swizzled: conflict-free for a quarter warp), scales and splits them.  Two operand paths:
+//   TS = false  the row's 64 fp16 hi / 64 lo' values overwrite the same two 128-byte rows IN PLACE (K-major SWIZZLE_128B tiles, no
+//               second buffer, no cross-thread hazard); SS-mode MMA.  TMEM = two accumulator sets (2 x [main 128 | correction 128]),
+//               so the epilogue of tile i overlaps the main loop of tile i+1.  Shared-memory traffic per stage: 64 KB TMA writes + 64 KB
+//               splitter + 80 KB MMA operand reads (measured: L1/TEX 72 % busy — the limiter, profiles/r02_experiments.md).
+//   TS = true   hi / lo' go to TENSOR memory with tcgen05.st (thread = TMEM lane) and the MMA takes A from TMEM: 64 + 32 + 48 KB per
+//               stage.  The A stages take the TMEM columns of the second accumulator set ([0,256) accumulators | 256 + 64 s: a_hi 32
+//               a_lo' 32), so the epilogue drains the single set into registers first and hands it back before touching global memory.
+// launch_tc picks TS for long K loops (>= 9 stages per work item: the 3x3 convolutions, + 7-15 % on the big layers) and the
+// double-buffered SS form for short ones (1x1 convolutions / linears: 4-stage tiles lose more to the accumulator hand-over than they gain).
 constexpr int PS_THREADS = 320, PS_STAGES = 3;
+constexpr int PS_TS_MIN_STAGES = 9;     // K-loop length (stages per work item) from which the TS operand path wins
 
+template <bool TS>
 __global__ void __launch_bounds__(PS_THREADS, 1)
 conv_tc_ps_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBh,
                   const __grid_constant__ CUtensorMap mapBl, const TcParams p, const int tiles_m, const int total_tiles) {
@@ -254,64 +269,124 @@ conv_tc_ps_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         // kind::f16 instruction descriptor: D = fp32 (bit 4), A / B format 0 = fp16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
         const uint32_t idesc = (1u << 4) | ((n_instr >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
         const uint32_t idesc256 = (1u << 4) | ((256u >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-        const uint32_t b = tl & 1u, use = tl >> 1;
-        mbar_wait(tempty_bar(b), (use & 1u) ^ 1u);          // epilogue has drained this accumulator set
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t acc = tmem_base + b * 256u;
-        for (int it = it0; it < it1; ++it, ++g) {
-          const int s = g % PS_STAGES;
-          const uint32_t ph = (g / PS_STAGES) & 1u;
-          mbar_wait(conv_bar(s), ph);
+        if constexpr (TS) {
+          mbar_wait(tempty_bar(0), (tl & 1u) ^ 1u);           // epilogue has drained the accumulators of the previous tile
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t st = sbase + s * STAGE_BYTES;
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {      // one instruction = 16 fp16 along K = 32 bytes of every 128-byte row
-            const uint64_t a_hi = umma_desc(st + k * 32), a_lo = umma_desc(st + A_BYTES + k * 32);
-            const uint64_t b_hi = umma_desc(st + 2 * A_BYTES + k * 32);
-            const uint32_t first = (it > it0 || k > 0) ? 1u : 0u;
-            // a_hi x [b_hi | b_lo'] -> [main | correction] as ONE N=256 instruction (the two B tiles are adjacent in shared memory):
-            // 8 instead of 12 instructions per stage and 5/6 of the operand reads
-            umma_f16(acc, a_hi, b_hi, idesc256, first);
-            umma_f16(acc + 128, a_lo, b_hi, idesc, 1u);
+          const uint32_t acc = tmem_base;
+          for (int it = it0; it < it1; ++it, ++g) {
+            const int s = g % PS_STAGES;
+            const uint32_t ph = (g / PS_STAGES) & 1u;
+            mbar_wait(conv_bar(s), ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t st = sbase + s * STAGE_BYTES;
+  #pragma unroll
+            const uint32_t a_t = tmem_base + 256u + 64u * (uint32_t)s;
+  #pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {      // one instruction = 16 fp16 along K = 8 packed TMEM columns of A, 32 bytes of every B row
+              const uint64_t b_hi = umma_desc(st + 2 * A_BYTES + k * 32);
+              const uint32_t first = (it > it0 || k > 0) ? 1u : 0u;
+              // a_hi x [b_hi | b_lo'] -> [main | correction] as ONE N=256 instruction (the two B tiles are adjacent in shared memory)
+              umma_f16_ts(acc, a_t + k * 8, b_hi, idesc256, first);
+              umma_f16_ts(acc + 128, a_t + 32 + k * 8, b_hi, idesc, 1u);
+            }
+            umma_commit(empty_bar(s));
           }
-          umma_commit(empty_bar(s));
+          umma_commit(tfull_bar(0));
+        } else {
+          const uint32_t b = tl & 1u, use = tl >> 1;
+          mbar_wait(tempty_bar(b), (use & 1u) ^ 1u);          // epilogue has drained this accumulator set
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t acc = tmem_base + b * 256u;
+          for (int it = it0; it < it1; ++it, ++g) {
+            const int s = g % PS_STAGES;
+            const uint32_t ph = (g / PS_STAGES) & 1u;
+            mbar_wait(conv_bar(s), ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t st = sbase + s * STAGE_BYTES;
+  #pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {      // one instruction = 16 fp16 along K = 32 bytes of every 128-byte row
+              const uint64_t a_hi = umma_desc(st + k * 32), a_lo = umma_desc(st + A_BYTES + k * 32);
+              const uint64_t b_hi = umma_desc(st + 2 * A_BYTES + k * 32);
+              const uint32_t first = (it > it0 || k > 0) ? 1u : 0u;
+              // a_hi x [b_hi | b_lo'] -> [main | correction] as ONE N=256 instruction (the two B tiles are adjacent in shared memory):
+              // 8 instead of 12 instructions per stage and 5/6 of the operand reads
+              umma_f16(acc, a_hi, b_hi, idesc256, first);
+              umma_f16(acc + 128, a_lo, b_hi, idesc, 1u);
+            }
+            umma_commit(empty_bar(s));
+          }
+          umma_commit(tfull_bar(b));
         }
-        umma_commit(tfull_bar(b));
       }
     }
   } else if (warp < 6) {
-    // ---- splitter warps 2..5
-    const int r = threadIdx.x - 64;                  // pixel row of the tile
-    const uint32_t sw = (uint32_t)(r & 7);           // 128B swizzle: 16-byte chunk c of row r sits at chunk position c ^ (r & 7)
-    const float sa = scale_up(amax_exponent(p.amax_a));
-    uint32_t g = 0;
-    for (int wi = blockIdx.x; wi < total_work; wi += gridDim.x) {
-      const int it0 = (wi / total_tiles) * p.it_per_split, it1 = min(iters_per_tile, it0 + p.it_per_split);
-      for (int it = it0; it < it1; ++it, ++g) {
-        const int s = g % PS_STAGES;
-        const uint32_t ph = (g / PS_STAGES) & 1u;
-        mbar_wait(full_bar(s), ph);
-        uint8_t* a0 = smem + s * STAGE_BYTES + r * 128;      // row r of the k 0..31 box  -> row r of a_hi
-        uint8_t* a1 = a0 + A_BYTES;                          // row r of the k 32..63 box -> row r of a_lo'
-        float4 v[16];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {       // a quarter warp (8 consecutive rows) touches 8 distinct chunk positions: conflict-free
-          v[c] = *reinterpret_cast<const float4*>(a0 + ((c ^ sw) << 4));
-          v[8 + c] = *reinterpret_cast<const float4*>(a1 + ((c ^ sw) << 4));
+    if constexpr (TS) {
+      // ---- splitter warps 2..5 (TMEM lane quarter = warp & 3)
+      const int r = (warp & 3) * 32 + lane;            // pixel row of the tile = TMEM lane
+      const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+      const uint32_t sw = (uint32_t)(r & 7);           // 128B swizzle: 16-byte chunk c of row r sits at chunk position c ^ (r & 7)
+      const float sa = scale_up(amax_exponent(p.amax_a));
+      uint32_t g = 0;
+      for (int wi = blockIdx.x; wi < total_work; wi += gridDim.x) {
+        const int it0 = (wi / total_tiles) * p.it_per_split, it1 = min(iters_per_tile, it0 + p.it_per_split);
+        for (int it = it0; it < it1; ++it, ++g) {
+          const int s = g % PS_STAGES;
+          const uint32_t ph = (g / PS_STAGES) & 1u;
+          mbar_wait(full_bar(s), ph);
+          const uint8_t* a0 = smem + s * STAGE_BYTES + r * 128;      // row r of the k 0..31 box
+          const uint8_t* a1 = a0 + A_BYTES;                          // row r of the k 32..63 box
+          uint32_t hi[32], lo[32];                                   // column j = K elements (2j, 2j+1)
+  #pragma unroll
+          for (int c = 0; c < 8; ++c) {       // a quarter warp (8 consecutive rows) touches 8 distinct chunk positions: conflict-free
+            const float4 x0 = *reinterpret_cast<const float4*>(a0 + ((c ^ sw) << 4));
+            const float4 x1 = *reinterpret_cast<const float4*>(a1 + ((c ^ sw) << 4));
+            split2(x0.x * sa, x0.y * sa, hi[2 * c], lo[2 * c]);
+            split2(x0.z * sa, x0.w * sa, hi[2 * c + 1], lo[2 * c + 1]);
+            split2(x1.x * sa, x1.y * sa, hi[16 + 2 * c], lo[16 + 2 * c]);
+            split2(x1.z * sa, x1.w * sa, hi[16 + 2 * c + 1], lo[16 + 2 * c + 1]);
+          }
+          const uint32_t a_t = tmem_base + lane_addr + 256u + 64u * (uint32_t)s;
+          tmem_st32(a_t, hi);
+          tmem_st32(a_t + 32, lo);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          mbar_arrive(conv_bar(s));
         }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {       // output chunk c = k 8c .. 8c+7
-          const float4 x0 = v[2 * c], x1 = v[2 * c + 1];
-          uint4 h, l;
-          split2(x0.x * sa, x0.y * sa, h.x, l.x);
-          split2(x0.z * sa, x0.w * sa, h.y, l.y);
-          split2(x1.x * sa, x1.y * sa, h.z, l.z);
-          split2(x1.z * sa, x1.w * sa, h.w, l.w);
-          *reinterpret_cast<uint4*>(a0 + ((c ^ sw) << 4)) = h;
-          *reinterpret_cast<uint4*>(a1 + ((c ^ sw) << 4)) = l;
+      }
+    } else {
+      // ---- splitter warps 2..5
+      const int r = threadIdx.x - 64;                  // pixel row of the tile
+      const uint32_t sw = (uint32_t)(r & 7);           // 128B swizzle: 16-byte chunk c of row r sits at chunk position c ^ (r & 7)
+      const float sa = scale_up(amax_exponent(p.amax_a));
+      uint32_t g = 0;
+      for (int wi = blockIdx.x; wi < total_work; wi += gridDim.x) {
+        const int it0 = (wi / total_tiles) * p.it_per_split, it1 = min(iters_per_tile, it0 + p.it_per_split);
+        for (int it = it0; it < it1; ++it, ++g) {
+          const int s = g % PS_STAGES;
+          const uint32_t ph = (g / PS_STAGES) & 1u;
+          mbar_wait(full_bar(s), ph);
+          uint8_t* a0 = smem + s * STAGE_BYTES + r * 128;      // row r of the k 0..31 box  -> row r of a_hi
+          uint8_t* a1 = a0 + A_BYTES;                          // row r of the k 32..63 box -> row r of a_lo'
+          float4 v[16];
+  #pragma unroll
+          for (int c = 0; c < 8; ++c) {       // a quarter warp (8 consecutive rows) touches 8 distinct chunk positions: conflict-free
+            v[c] = *reinterpret_cast<const float4*>(a0 + ((c ^ sw) << 4));
+            v[8 + c] = *reinterpret_cast<const float4*>(a1 + ((c ^ sw) << 4));
+          }
+  #pragma unroll
+          for (int c = 0; c < 8; ++c) {       // output chunk c = k 8c .. 8c+7
+            const float4 x0 = v[2 * c], x1 = v[2 * c + 1];
+            uint4 h, l;
+            split2(x0.x * sa, x0.y * sa, h.x, l.x);
+            split2(x0.z * sa, x0.w * sa, h.y, l.y);
+            split2(x1.x * sa, x1.y * sa, h.z, l.z);
+            split2(x1.z * sa, x1.w * sa, h.w, l.w);
+            *reinterpret_cast<uint4*>(a0 + ((c ^ sw) << 4)) = h;
+            *reinterpret_cast<uint4*>(a1 + ((c ^ sw) << 4)) = l;
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive(conv_bar(s));
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(conv_bar(s));
       }
     }
   } else {
@@ -329,73 +404,136 @@ conv_tc_ps_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       const int tile = wi % total_tiles;
       int q0, p0, n0, nblk;
       tile_coords(tile, q0, p0, n0, nblk);
-      const uint32_t b = tl & 1u, use = tl >> 1;
-      mbar_wait(tfull_bar(b), use & 1u);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int img = n0 + n_l;
-      const bool row_ok = img < p.Nimg;
-      const long long m = ((long long)img * p.Ho + ((p0 + h_l) * p.os + p.oa)) * p.Wo + ((q0 + w_l) * p.os + p.ob);
-      float* yrow = p.y + m * p.ldy;
-      const float* rrow = p.residual ? p.residual + m * p.ld_res : nullptr;
-      const float* arow2 = p.rowadd ? p.rowadd + (long long)img * p.ld_rowadd : nullptr;
-#pragma unroll 1
-      for (int j = 0; j < BN / 32; ++j) {
-        uint32_t v[32], u[32];
-        const uint32_t taddr = tmem_base + lane_addr + b * 256u + (uint32_t)(j * 32);
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-            : "r"(taddr));
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
-              "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
-              "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
-              "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
-            : "r"(taddr + 128u));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (j == BN / 32 - 1) {   // accumulators are in registers: hand the TMEM set back to the MMA warp
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          mbar_arrive(tempty_bar(b));
+      if constexpr (TS) {
+        mbar_wait(tfull_bar(0), tl & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int img = n0 + n_l;
+        const bool row_ok = img < p.Nimg;
+        const long long m = ((long long)img * p.Ho + ((p0 + h_l) * p.os + p.oa)) * p.Wo + ((q0 + w_l) * p.os + p.ob);
+        float* yrow = p.y + m * p.ldy;
+        const float* rrow = p.residual ? p.residual + m * p.ld_res : nullptr;
+        const float* arow2 = p.rowadd ? p.rowadd + (long long)img * p.ld_rowadd : nullptr;
+        float out[BN];          // this thread's row of the tile: drained before anything else so the MMA warp can start the next tile
+  #pragma unroll
+        for (int j = 0; j < BN / 32; ++j) {
+          uint32_t v[32], u[32];
+          const uint32_t taddr = tmem_base + lane_addr + (uint32_t)(j * 32);
+          tmem_ld32(taddr, v);
+          tmem_ld32(taddr + 128u, u);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  #pragma unroll
+          for (int i = 0; i < 32; ++i) out[j * 32 + i] = fin(v[i], u[i]);
         }
-        if (p.ksplit > 1) {   // split-K: raw partial sums into this split's slab of the (padded) workspace; splitk_epilogue_kernel finishes
-          float* wrow = p.ws + (long long)(wi / total_tiles) * p.ws_split_stride + ((long long)(tile - nblk * tiles_m) * BM + row) * p.ws_ld + nblk * BN + j * 32;
-#pragma unroll
-          for (int i = 0; i < 32; i += 4)
-            *reinterpret_cast<float4*>(wrow + i) = make_float4(fin(v[i], u[i]), fin(v[i + 1], u[i + 1]), fin(v[i + 2], u[i + 2]), fin(v[i + 3], u[i + 3]));
-        } else if (row_ok) {
-          const int c0 = nblk * BN + j * 32;
-          if (p.vec4 && c0 + 32 <= p.Nout) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              float4 o = make_float4(fin(v[i], u[i]), fin(v[i + 1], u[i + 1]), fin(v[i + 2], u[i + 2]), fin(v[i + 3], u[i + 3]));
-              if (p.bias) { float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + i)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
-              if (arow2) { float4 t = __ldg(reinterpret_cast<const float4*>(arow2 + c0 + i)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
-              if (rrow) { float4 t = __ldg(reinterpret_cast<const float4*>(rrow + c0 + i)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
-              float4* dst = reinterpret_cast<float4*>(yrow + c0 + i);
-              if (p.accumulate) { float4 t = *dst; o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
-              *dst = o;
-              amax = fmaxf(fmaxf(amax, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(tempty_bar(0));
+  #pragma unroll
+        for (int j = 0; j < BN / 32; ++j) {
+          const float* oj = out + j * 32;
+          if (p.ksplit > 1) {   // split-K: partial sums into this split's slab of the (padded) workspace; splitk_epilogue_kernel finishes
+            float* wrow = p.ws + (long long)(wi / total_tiles) * p.ws_split_stride + ((long long)(tile - nblk * tiles_m) * BM + row) * p.ws_ld + nblk * BN + j * 32;
+  #pragma unroll
+            for (int i = 0; i < 32; i += 4)
+              *reinterpret_cast<float4*>(wrow + i) = make_float4(oj[i], oj[i + 1], oj[i + 2], oj[i + 3]);
+          } else if (row_ok) {
+            const int c0 = nblk * BN + j * 32;
+            if (p.vec4 && c0 + 32 <= p.Nout) {
+  #pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                float4 o = make_float4(oj[i], oj[i + 1], oj[i + 2], oj[i + 3]);
+                if (p.bias) { float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + i)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+                if (arow2) { float4 t = __ldg(reinterpret_cast<const float4*>(arow2 + c0 + i)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+                if (rrow) { float4 t = __ldg(reinterpret_cast<const float4*>(rrow + c0 + i)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+                float4* dst = reinterpret_cast<float4*>(yrow + c0 + i);
+                if (p.accumulate) { float4 t = *dst; o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+                *dst = o;
+                amax = fmaxf(fmaxf(amax, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
+              }
+            } else {
+  #pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const int c = c0 + i;
+                if (c < p.Nout) {
+                  float o = oj[i];
+                  if (p.bias) o += __ldg(p.bias + c);
+                  if (arow2) o += __ldg(arow2 + c);
+                  if (rrow) o += __ldg(rrow + c);
+                  if (p.accumulate) o += yrow[c];
+                  yrow[c] = o;
+                  amax = fmaxf(amax, fabsf(o));
+                }
+              }
             }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int c = c0 + i;
-              if (c < p.Nout) {
-                float o = fin(v[i], u[i]);
-                if (p.bias) o += __ldg(p.bias + c);
-                if (arow2) o += __ldg(arow2 + c);
-                if (rrow) o += __ldg(rrow + c);
-                if (p.accumulate) o += yrow[c];
-                yrow[c] = o;
-                amax = fmaxf(amax, fabsf(o));
+          }
+        }
+      } else {
+        const uint32_t b = tl & 1u, use = tl >> 1;
+        mbar_wait(tfull_bar(b), use & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int img = n0 + n_l;
+        const bool row_ok = img < p.Nimg;
+        const long long m = ((long long)img * p.Ho + ((p0 + h_l) * p.os + p.oa)) * p.Wo + ((q0 + w_l) * p.os + p.ob);
+        float* yrow = p.y + m * p.ldy;
+        const float* rrow = p.residual ? p.residual + m * p.ld_res : nullptr;
+        const float* arow2 = p.rowadd ? p.rowadd + (long long)img * p.ld_rowadd : nullptr;
+  #pragma unroll 1
+        for (int j = 0; j < BN / 32; ++j) {
+          uint32_t v[32], u[32];
+          const uint32_t taddr = tmem_base + lane_addr + b * 256u + (uint32_t)(j * 32);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+              : "r"(taddr));
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+              : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+                "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
+                "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
+                "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+              : "r"(taddr + 128u));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (j == BN / 32 - 1) {   // accumulators are in registers: hand the TMEM set back to the MMA warp
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(tempty_bar(b));
+          }
+          if (p.ksplit > 1) {   // split-K: raw partial sums into this split's slab of the (padded) workspace; splitk_epilogue_kernel finishes
+            float* wrow = p.ws + (long long)(wi / total_tiles) * p.ws_split_stride + ((long long)(tile - nblk * tiles_m) * BM + row) * p.ws_ld + nblk * BN + j * 32;
+  #pragma unroll
+            for (int i = 0; i < 32; i += 4)
+              *reinterpret_cast<float4*>(wrow + i) = make_float4(fin(v[i], u[i]), fin(v[i + 1], u[i + 1]), fin(v[i + 2], u[i + 2]), fin(v[i + 3], u[i + 3]));
+          } else if (row_ok) {
+            const int c0 = nblk * BN + j * 32;
+            if (p.vec4 && c0 + 32 <= p.Nout) {
+  #pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                float4 o = make_float4(fin(v[i], u[i]), fin(v[i + 1], u[i + 1]), fin(v[i + 2], u[i + 2]), fin(v[i + 3], u[i + 3]));
+                if (p.bias) { float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + i)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+                if (arow2) { float4 t = __ldg(reinterpret_cast<const float4*>(arow2 + c0 + i)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+                if (rrow) { float4 t = __ldg(reinterpret_cast<const float4*>(rrow + c0 + i)); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+                float4* dst = reinterpret_cast<float4*>(yrow + c0 + i);
+                if (p.accumulate) { float4 t = *dst; o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+                *dst = o;
+                amax = fmaxf(fmaxf(amax, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
+              }
+            } else {
+  #pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const int c = c0 + i;
+                if (c < p.Nout) {
+                  float o = fin(v[i], u[i]);
+                  if (p.bias) o += __ldg(p.bias + c);
+                  if (arow2) o += __ldg(arow2 + c);
+                  if (rrow) o += __ldg(rrow + c);
+                  if (p.accumulate) o += yrow[c];
+                  yrow[c] = o;
+                  amax = fmaxf(amax, fabsf(o));
+                }
               }
             }
           }
@@ -483,13 +621,6 @@ constexpr int WG_STAGES = 3, WG_STAGE_BYTES = 8 * WG_BLK;
 // blocks, SBO = 1 KB between 8-pixel K groups
 __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(WG_BLK >> 4) << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
 }
 
 // warps: 0 TMA | 1, 6 MMA issuers (alternate stages) | 2-5 splitters + epilogue.  (A second splitter group on alternate stages was
@@ -715,7 +846,8 @@ int tc_init() {
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
       qres != cudaDriverEntryPointSuccess) { (void)cudaGetLastError(); return 0; }
   g_encode = (EncodeTiledFn)fn;
-  bool ok = cudaFuncSetAttribute(conv_tc_ps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PS_SMEM) == cudaSuccess;
+  bool ok = cudaFuncSetAttribute(conv_tc_ps_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PS_SMEM) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(conv_tc_ps_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PS_SMEM) == cudaSuccess;
   ok = ok && cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM) == cudaSuccess;
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   if (!ok) { (void)cudaGetLastError(); return 0; }
@@ -836,7 +968,8 @@ int launch_tc(const float* act, long long ld_act, const uint32_t* amax_a, int Ni
     }
     const int work = total * p.ksplit;
     const int ctas = work < g_num_sms ? work : g_num_sms;
-    conv_tc_ps_kernel<<<ctas, PS_THREADS, PS_SMEM, st>>>(mA, mBh, mBl, p, tiles_m, total);
+    if (p.it_per_split >= PS_TS_MIN_STAGES) conv_tc_ps_kernel<true><<<ctas, PS_THREADS, PS_SMEM, st>>>(mA, mBh, mBl, p, tiles_m, total);
+    else conv_tc_ps_kernel<false><<<ctas, PS_THREADS, PS_SMEM, st>>>(mA, mBh, mBl, p, tiles_m, total);
     if (p.ksplit > 1) {
       int rc = dp_check_launch();
       if (rc) return rc;
