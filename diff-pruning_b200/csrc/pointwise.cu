@@ -230,22 +230,33 @@ __global__ void softmax_fwd_kernel(const float* __restrict__ s, float* __restric
 }
 __global__ void softmax_bwd_kernel(const float* __restrict__ p, const float* __restrict__ dp, float* __restrict__ ds, long long rows, int cols,
                                    uint32_t* __restrict__ amax_ds) {
-  long long row = blockIdx.x * (long long)(NT / 32) + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  int lane = threadIdx.x & 31;
-  const float* pr = p + row * cols;
-  const float* dr = dp + row * cols;
-  float* o = ds + row * cols;
-  float dot = 0.f;
-  for (int j = lane; j < cols; j += 32) dot += pr[j] * dr[j];
-  dot = warp_sum(dot);
+  __shared__ float wmax[NT / 32];
+  const long long row = blockIdx.x * (long long)(NT / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   float amax = 0.f;
-  for (int j = lane; j < cols; j += 32) {
-    const float v = pr[j] * (dr[j] - dot);
-    o[j] = v;
-    amax = fmaxf(amax, fabsf(v));
+  if (row < rows) {
+    const float* pr = p + row * cols;
+    const float* dr = dp + row * cols;
+    float* o = ds + row * cols;
+    float dot = 0.f;
+    for (int j = lane; j < cols; j += 32) dot += pr[j] * dr[j];
+    dot = warp_sum(dot);
+    for (int j = lane; j < cols; j += 32) {
+      const float v = pr[j] * (dr[j] - dot);
+      o[j] = v;
+      amax = fmaxf(amax, fabsf(v));
+    }
   }
-  if (amax_ds) amax_commit(amax_ds, amax);
+  if (amax_ds) {      // one atomic per block (a row per warp would serialise tens of thousands of them on one address)
+    amax = warp_max(amax);
+    if (lane == 0) wmax[threadIdx.x >> 5] = amax;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float m = 0.f;
+      for (int i = 0; i < NT / 32; ++i) m = fmaxf(m, wmax[i]);
+      if (m > 0.f) atomicMax(amax_ds, __float_as_uint(m));
+    }
+  }
 }
 __global__ void ddim_step_kernel(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ nz,
                                  float* __restrict__ out, long long n, float sb, float sa, float clip, float sap, float dir, float sigma) {
