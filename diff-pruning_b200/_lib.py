@@ -15,12 +15,12 @@ class ConvArgs(C.Structure):
     _fields_ = [(n, i32) for n in ("N", "H", "W", "C", "P", "Q", "K", "R", "S", "stride", "pad_t", "pad_l", "flags",
                                    "splits")] + [
         ("x", vp), ("ldx", i64), ("y", vp), ("ldy", i64), ("w", vp), ("w_tc_hi", vp), ("w_tc_lo", vp), ("bias", vp), ("rowadd", vp),
-        ("ld_rowadd", i64), ("residual", vp), ("ld_res", i64), ("workspace", vp), ("amax_x", vp), ("amax_y", vp), ("amax_w", vp), ("amax_out", vp)]
+        ("ld_rowadd", i64), ("residual", vp), ("ld_res", i64), ("workspace", vp), ("amax_x", vp), ("amax_y", vp), ("amax_w", vp), ("amax_out", vp), ("bias_ws", vp)]
 
 
 class WgradReduceArgs(C.Structure):
     _fields_ = [(n, i32) for n in ("K", "C", "R", "S", "splits")] + [
-        ("workspace", vp), ("dw", vp), ("w", vp), ("score_out", vp), ("score_in", vp)]
+        ("workspace", vp), ("dw", vp), ("w", vp), ("score_out", vp), ("score_in", vp), ("bias_ws", vp), ("db", vp)]
 
 
 class GemmArgs(C.Structure):

@@ -612,6 +612,7 @@ struct WgParams {
   float* ws;
   int in_stride;             // x pixel = in_stride * dy pixel + tap offset
   const uint32_t* amax_x; const uint32_t* amax_y;
+  float* bias_ws;            // optional [splits][K]: column sums of dy over this split's pixels (written by the tap 0 / c-tile 0 CTAs)
 };
 constexpr int WG_KPIX = 64;                  // pixels per stage
 constexpr int WG_BLK = WG_KPIX * 128;        // 8 KB: one raw fp32 box [64 px][32 ch] = one fp16 block [64 px][64 ch]
@@ -739,6 +740,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant
     const float sy = scale_up(Ey), sxs = scale_up(Ex);
     const int xj = tid >> 6, xp = tid & 63;   // x task of this thread: 64-channel block, pixel row
     const uint32_t xsw = (uint32_t)(xp & 7);
+    float bsum = 0.f;                         // sum of this thread's out-channel of dy over the split's pixels (bias gradient)
     for (int it = 0; it < num_iters; ++it) {
       const int s = it % WSTAGES;
       const uint32_t ph = (uint32_t)(it / WSTAGES) & 1u;
@@ -747,12 +749,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant
       {
         const uint8_t* blk = smem + s * STAGE_BYTES + q * WG_BLK + (lane & 3) * 4;
         uint32_t hi[32], lo[32];
+        float ssum = 0.f;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float v0 = *reinterpret_cast<const float*>(blk + (2 * j) * 128 + ((((lane >> 2) ^ (2 * j)) & 7) << 4));
           const float v1 = *reinterpret_cast<const float*>(blk + (2 * j + 1) * 128 + ((((lane >> 2) ^ (2 * j + 1)) & 7) << 4));
           split2(v0 * sy, v1 * sy, hi[j], lo[j]);      // TMEM column j = pixels (2j, 2j+1), low half first
+          ssum += v0 + v1;
         }
+        bsum += ssum;
         const uint32_t a_t = tmem_base + lane_addr + 256u + 64u * s;
         tmem_st32(a_t, hi);
         tmem_st32(a_t + 32, lo);
@@ -791,6 +796,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant
     const int kout = kt * 128 + row;
     const long long TC_ = (long long)T * p.C;
     float* wrow = p.ws + ((long long)blockIdx.y * p.K + kout) * TC_ + (long long)tap * p.C;
+    if (p.bias_ws && tap == 0 && ct == 0 && kout < p.K) p.bias_ws[(long long)blockIdx.y * p.K + kout] = bsum;   // 0 for an empty split
     if (num_iters == 0) {                     // nothing was accumulated (TMEM holds garbage): this split contributes zeros
       if (kout < p.K)
         for (int c = ct * 128; c < min(p.C, ct * 128 + 128); ++c) wrow[c] = 0.f;
@@ -1218,7 +1224,7 @@ int dp_conv2d_wgrad_tc(const dp_conv_args* a, dp_stream_t stream) {
   p.Nimg = a->N; p.H = a->P; p.W = a->Q; p.C = a->C; p.K = a->K; p.R = a->R; p.S = a->S; p.pad = a->pad_t; p.in_stride = a->stride;
   p.bw = bw; p.bh = bh; p.bn = bn; p.tiles_w = a->Q / bw; p.tiles_h = a->P / bh;
   p.total_chunks = p.tiles_w * p.tiles_h * img_boxes;
-  p.amax_x = a->amax_x; p.amax_y = a->amax_y;
+  p.amax_x = a->amax_x; p.amax_y = a->amax_y; p.bias_ws = a->bias_ws;
   p.chunks_per_split = (p.total_chunks + a->splits - 1) / a->splits;
   p.c_tiles = (a->C + 127) / 128;
   p.ws = a->workspace;

@@ -343,7 +343,15 @@ int dp_conv2d_wgrad_simt(const dp_conv_args* a, dp_stream_t stream) {
   g.P = a->P; g.Q = a->Q; g.PQ = a->P * a->Q; g.S = a->S;
   g.sm = a->stride; g.sr = 1; g.off_h = -a->pad_t; g.off_w = -a->pad_l; g.sds = 0;
   g.logQ = ilog2_exact(g.Q); g.logPQ = ilog2_exact(g.PQ);
-  return launch_gemm<A_MC, B_GATHER>(p, a->splits, (cudaStream_t)stream);
+  rc = launch_gemm<A_MC, B_GATHER>(p, a->splits, (cudaStream_t)stream);
+  if (rc || !a->bias_ws) return rc;
+  // the column sums of dy the tensor-core kernel produces on the way: one column-sum segment per K split (the same pixel ranges)
+  const int64_t rows = (int64_t)a->N * a->P * a->Q;
+  const int64_t nseg = (rows + kper - 1) / kper;
+  if (nseg < a->splits &&
+      cudaMemsetAsync(a->bias_ws + nseg * a->K, 0, (size_t)(a->splits - nseg) * a->K * sizeof(float), (cudaStream_t)stream) != cudaSuccess)
+    return dp_check_launch();
+  return dp_colsum((const float*)a->y, a->ldy, rows, a->K, kper, a->bias_ws, a->K, 0, stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -388,6 +396,11 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const dp_wgrad_reduce
     const int tap = i / a.C, c = i - tap * a.C;
     const long long gi = ((long long)k * a.C + c) * RS + tap;
     a.dw[gi] += s;
+    if (a.bias_ws && i == 0) {        // bias gradient: the per-split column sums of dy, summed in split order
+      float b = 0.f;
+      for (int z2 = 0; z2 < a.splits; ++z2) b += a.bias_ws[(long long)z2 * a.K + k];
+      a.db[k] += b;
+    }
     // signed first-order Taylor term of this pass, parked in the (already consumed) split-0 slot for the score kernels
     if (a.w && (a.score_out || a.score_in)) const_cast<float*>(a.workspace)[(long long)k * TC + i] = a.w[gi] * s;
   }
@@ -444,6 +457,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int K, int C, in
 
 extern "C" int dp_conv2d_wgrad_reduce(const dp_wgrad_reduce_args* a, dp_stream_t stream) {
   DP_REQUIRE(a && a->workspace && a->dw, DP_ERR_NULL);
+  DP_REQUIRE((a->bias_ws == nullptr) == (a->db == nullptr), DP_ERR_NULL);
   DP_REQUIRE(a->K > 0 && a->C > 0 && a->R > 0 && a->S > 0 && a->splits >= 1, DP_ERR_SHAPE);
   cudaStream_t st = (cudaStream_t)stream;
   const int TC = a->R * a->S * a->C;

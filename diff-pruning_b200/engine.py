@@ -521,8 +521,10 @@ class Plan:
         else:
             dout = self.gradof(out)
             dy_get, dy_ld = (lambda p=dout.ptr: p), dout.ld
-        # 1. bias gradient (and per-image sums for the caller when seg_out is set)
-        if b is not None or seg_out is not None:
+        # 1. bias gradient (and per-image sums for the caller when seg_out is set).  Without seg_out the bias gradient falls out of the
+        #    wgrad kernel's pass over dy (bias_ws -> dp_conv2d_wgrad_reduce): no column-sum launches at all
+        bias_in_wgrad = b is not None and seg_out is None and dy_dense is None
+        if (b is not None or seg_out is not None) and not bias_in_wgrad:
             if dy_dense is not None and out.H * out.W == 1:
                 seg = dy_dense  # already dense per-image rows
             else:
@@ -550,6 +552,9 @@ class Plan:
         wa.ldy = dy_ld
         wa.rowadd, wa.residual, wa.bias = None, None, None
         self._late.append(lambda wa=wa, g=dy_get: (setattr(wa, "y", g()), setattr(wa, "workspace", self.sptr("wgrad_ws"))))
+        if bias_in_wgrad:
+            self.scratch("bias_ws", splits * K)
+            self._late.append(lambda wa=wa: setattr(wa, "bias_ws", self.sptr("bias_ws")))
         self._rec(steps, lib.dp_conv2d_wgrad, wa, "conv wgrad", info)
         ra = L.WgradReduceArgs()
         ra.K, ra.C, ra.R, ra.S, ra.splits = K, Cin, R, S, splits
@@ -558,6 +563,9 @@ class Plan:
             so, si = self._score_views(w, K, Cin)
             ra.w, ra.score_out, ra.score_in = w.data_ptr(), so.data_ptr(), si.data_ptr()
         self._late.append(lambda ra=ra: setattr(ra, "workspace", self.sptr("wgrad_ws")))
+        if bias_in_wgrad:
+            ra.db = self.pgrad(b)
+            self._late.append(lambda ra=ra: setattr(ra, "bias_ws", self.sptr("bias_ws")))
         self._rec(steps, lib.dp_conv2d_wgrad_reduce, ra, "conv wgrad reduce")
         # 3. dgrad
         if need_dx:

@@ -80,6 +80,8 @@ typedef struct dp_conv_args {
   const uint32_t* amax_x; const uint32_t* amax_y; const uint32_t* amax_w;
   uint32_t* amax_out;  /* optional: fprop accumulates max|y| of what it wrote, dgrad max|dx| (dp_amax semantics), on every kernel
                           path — the consumer of that tensor then needs no dp_amax pass */
+  float* bias_ws;      /* optional, wgrad: also writes the per-split column sums of dy, [splits][K] — the bias gradient falls out of the
+                          pass over dy the weight gradient makes anyway (dp_conv2d_wgrad_reduce adds them to db in fixed order) */
 } dp_conv_args;
 
 int dp_conv2d_fprop(const dp_conv_args* a, dp_stream_t stream);
@@ -103,6 +105,8 @@ typedef struct dp_wgrad_reduce_args {
   const float* w;         /* [K][C][R][S] or NULL */
   float* score_out;       /* [K] or NULL */
   float* score_in;        /* [C] or NULL */
+  const float* bias_ws;   /* [splits][K] column sums of dy written by dp_conv2d_wgrad (dp_conv_args.bias_ws), or NULL */
+  float* db;              /* [K] bias gradient, accumulated into (+= sum over splits, fixed order) */
 } dp_wgrad_reduce_args;
 int dp_conv2d_wgrad_reduce(const dp_wgrad_reduce_args* a, dp_stream_t stream);
 

@@ -198,17 +198,21 @@ def test_conv_tc_fprop_dgrad(lib, N, Cin, H, W, K, R, ldx, ldy):
         wg = L.ConvArgs()
         C.memmove(C.byref(wg), C.byref(a), C.sizeof(a))
         wg.flags, wg.splits, wg.y, wg.ldy, wg.workspace, wg.amax_y = 0, splits, gyd.data_ptr(), K, ws.data_ptr(), sdy.data_ptr()
+        bws = torch.full((splits * K,), float("nan"), device="cuda")      # the bias gradient falls out of the same pass over dy
+        wg.bias_ws = bws.data_ptr()
         assert lib.dp_conv2d_wgrad(C.byref(wg), S()) == 0
-        dw = torch.ones(K, Cin, R, R, device="cuda")
+        dw, db = torch.ones(K, Cin, R, R, device="cuda"), torch.ones(K, device="cuda")
         r = L.WgradReduceArgs()
         r.K, r.C, r.R, r.S, r.splits = K, Cin, R, R, splits
-        r.workspace, r.dw = ws.data_ptr(), dw.data_ptr()
+        r.workspace, r.dw, r.bias_ws, r.db = ws.data_ptr(), dw.data_ptr(), bws.data_ptr(), db.data_ptr()
         assert lib.dp_conv2d_wgrad_reduce(C.byref(r), S()) == 0
+        assert rel_err(db.cpu() - 1, gy.sum((0, 2, 3))) < 1e-5, splits
         assert rel_err(dw.cpu() - 1, wr.grad) < (1.5e-5 if N * H * W // splits <= 2048 else 4e-5), splits   # longer per-CTA chains drift (see above)
         # and the SIMT path on the same problem agrees
-        ws2 = torch.empty_like(ws)
-        wg.flags, wg.workspace = 2, ws2.data_ptr()
+        ws2, bws2 = torch.empty_like(ws), torch.full_like(bws, float("nan"))
+        wg.flags, wg.workspace, wg.bias_ws = 2, ws2.data_ptr(), bws2.data_ptr()
         assert lib.dp_conv2d_wgrad(C.byref(wg), S()) == 0
+        assert rel_err(bws2.view(splits, K).sum(0).cpu(), gy.sum((0, 2, 3))) < 1e-5
         assert rel_err(ws.view(splits, -1).sum(0), ws2.view(splits, -1).sum(0)) < (1.5e-5 if N * H * W // splits <= 2048 else 4e-5)
 
 

@@ -34,9 +34,9 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     from diff_pruning_b200 import _lib as L
-    assert ctypes.sizeof(L.ConvArgs) == 56 + 17 * 8
+    assert ctypes.sizeof(L.ConvArgs) == 56 + 18 * 8
     assert ctypes.sizeof(L.GemmArgs) == 16 + 11 * 8 + 8
-    assert ctypes.sizeof(L.WgradReduceArgs) == 24 + 5 * 8
+    assert ctypes.sizeof(L.WgradReduceArgs) == 24 + 7 * 8
     assert ctypes.sizeof(L.TaylorArgs) == 16 + 8 * 8
     assert ctypes.sizeof(L.GnArgs) == 24 + 19 * 8 + 8 + 8 + 8 + 16 + 16
     assert ctypes.sizeof(L.ConvBf16Args) == 56 + 13 * 8
