@@ -157,6 +157,14 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
         "r"(v[30]), "r"(v[31])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {   // caller issues tcgen05.wait::ld
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -624,10 +632,11 @@ __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(WG_BLK >> 4) << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
-// warps: 0 TMA | 1, 6 MMA issuers (alternate stages) | 2-5 splitters + epilogue.  (A second splitter group on alternate stages was
-// measured: no gain — the kernel is not instruction-bound — and with an odd stage count a group that visits a barrier only every
-// second phase can be lapped, so it is gone.)
-constexpr int WG_THREADS = 224;
+// warps: 0 TMA | 1, 6 MMA issuers (alternate stages) | 2-5 and 7-10: two half-groups of splitters that work on the SAME stage (pixels
+// 0..31 / 32..63 of dy, first / second raw box of every x row) + epilogue.  The ring is latency bound — period ~ (TMA latency + split +
+// MMA) / stages, r02_experiments.md section 13 — so halving the ~850-instruction split of a stage shortens every stage's chain; groups on
+// ALTERNATE stages did not (same chain) and, visiting each barrier only every second phase of a 3-stage ring, could be lapped.
+constexpr int WG_THREADS = 352;
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant__ CUtensorMap mapX, const WgParams p) {
   constexpr int WSTAGES = WG_STAGES;
@@ -647,7 +656,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * WSTAGES + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < WSTAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(conv_bar(s), 128); mbar_init(empty_bar(s), 1); mbar_init(iss_bar(s), 1); }
+    for (int s = 0; s < WSTAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(conv_bar(s), 256); mbar_init(empty_bar(s), 1); mbar_init(iss_bar(s), 1); }
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -732,56 +741,59 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant
       }
       __syncwarp();
     }
-  } else if (warp < 6) {
-    const int tid = threadIdx.x - 64;
-    const int q = warp & 3;                   // TMEM lane quarter == 32-channel box of dy
+  } else {
+    const int half = warp > 6 ? 1 : 0;        // splitter half-group
+    const int tid = threadIdx.x - (half ? 224 : 64);
+    const int q = warp & 3;                   // TMEM lane quarter == 32-channel box of dy (each half-group covers the four quarters)
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const int Ey = amax_exponent(p.amax_y), Ex = amax_exponent(p.amax_x);
     const float sy = scale_up(Ey), sxs = scale_up(Ex);
-    const int xj = tid >> 6, xp = tid & 63;   // x task of this thread: 64-channel block, pixel row
+    const int xj = tid >> 6, xp = tid & 63;   // x task of this thread: 64-channel block, pixel row; `half` picks the raw box of the row
     const uint32_t xsw = (uint32_t)(xp & 7);
-    float bsum = 0.f;                         // sum of this thread's out-channel of dy over the split's pixels (bias gradient)
+    float bsum = 0.f;                         // sum of this thread's out-channel of dy over its pixels of the split (bias gradient)
+    float* bsh = reinterpret_cast<float*>(tmem_slot + 2);      // 128 floats behind the barriers: the halves' bias sums meet here
     for (int it = 0; it < num_iters; ++it) {
       const int s = it % WSTAGES;
       const uint32_t ph = (uint32_t)(it / WSTAGES) & 1u;
       mbar_wait(full_bar(s), ph);
-      // (1) dy^T -> TMEM: channel `lane` of box q, pixel rows 0..63; 16-byte chunk j of row `pix` sits at chunk position j ^ (pix & 7)
+      // (1) dy^T -> TMEM: channel `lane` of box q, pixel rows 32 half .. 32 half + 31; 16-byte chunk j of row `pix` sits at position j ^ (pix & 7)
       {
-        const uint8_t* blk = smem + s * STAGE_BYTES + q * WG_BLK + (lane & 3) * 4;
-        uint32_t hi[32], lo[32];
+        const uint8_t* blk = smem + s * STAGE_BYTES + q * WG_BLK + half * 32 * 128 + (lane & 3) * 4;
+        uint32_t hi[16], lo[16];
         float ssum = 0.f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
+        for (int j = 0; j < 16; ++j) {
           const float v0 = *reinterpret_cast<const float*>(blk + (2 * j) * 128 + ((((lane >> 2) ^ (2 * j)) & 7) << 4));
           const float v1 = *reinterpret_cast<const float*>(blk + (2 * j + 1) * 128 + ((((lane >> 2) ^ (2 * j + 1)) & 7) << 4));
-          split2(v0 * sy, v1 * sy, hi[j], lo[j]);      // TMEM column j = pixels (2j, 2j+1), low half first
+          split2(v0 * sy, v1 * sy, hi[j], lo[j]);      // TMEM column 16 half + j = pixels (2j, 2j+1) of this half, low half first
           ssum += v0 + v1;
         }
         bsum += ssum;
-        const uint32_t a_t = tmem_base + lane_addr + 256u + 64u * s;
-        tmem_st32(a_t, hi);
-        tmem_st32(a_t + 32, lo);
+        const uint32_t a_t = tmem_base + lane_addr + 256u + 64u * s + 16u * half;
+        tmem_st16(a_t, hi);
+        tmem_st16(a_t + 32, lo);
       }
-      // (2) x: rows xp of the two raw boxes of block xj -> row xp of x_hi[xj] and of x_lo'[xj], in place
+      // (2) x: row xp of block xj.  This thread reads the row's raw box `half` (channels 32 half .. 32 half + 31 of the block); once BOTH
+      //     halves have read, it writes chunks 4 half .. 4 half + 3 of the fp16 x_hi row (over box 0) and of the x_lo' row (over box 1)
       {
         uint8_t* a0 = smem + s * STAGE_BYTES + (4 + xj) * WG_BLK + xp * 128;
         uint8_t* a1 = a0 + 2 * WG_BLK;
-        float4 v[16];
+        const uint8_t* src = half ? a1 : a0;
+        float4 v[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          v[c] = *reinterpret_cast<const float4*>(a0 + ((c ^ xsw) << 4));
-          v[8 + c] = *reinterpret_cast<const float4*>(a1 + ((c ^ xsw) << 4));
-        }
+        for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const float4*>(src + ((c ^ xsw) << 4));
+        asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
+        for (int c = 0; c < 4; ++c) {
           const float4 x0 = v[2 * c], x1 = v[2 * c + 1];
           uint4 h, l;
           split2(x0.x * sxs, x0.y * sxs, h.x, l.x);
           split2(x0.z * sxs, x0.w * sxs, h.y, l.y);
           split2(x1.x * sxs, x1.y * sxs, h.z, l.z);
           split2(x1.z * sxs, x1.w * sxs, h.w, l.w);
-          *reinterpret_cast<uint4*>(a0 + ((c ^ xsw) << 4)) = h;
-          *reinterpret_cast<uint4*>(a1 + ((c ^ xsw) << 4)) = l;
+          const uint32_t pos = (uint32_t)(((4 * half + c) ^ xsw) << 4);
+          *reinterpret_cast<uint4*>(a0 + pos) = h;
+          *reinterpret_cast<uint4*>(a1 + pos) = l;
         }
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -789,6 +801,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(conv_bar(s));
     }
+    if (half) bsh[q * 32 + lane] = bsum;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (!half) bsum += bsh[q * 32 + lane];
     mbar_wait(tmem_full_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const float f1 = scale_dn(Ey), f2 = scale_dn(Ex);
@@ -796,13 +811,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant
     const int kout = kt * 128 + row;
     const long long TC_ = (long long)T * p.C;
     float* wrow = p.ws + ((long long)blockIdx.y * p.K + kout) * TC_ + (long long)tap * p.C;
-    if (p.bias_ws && tap == 0 && ct == 0 && kout < p.K) p.bias_ws[(long long)blockIdx.y * p.K + kout] = bsum;   // 0 for an empty split
+    if (p.bias_ws && !half && tap == 0 && ct == 0 && kout < p.K) p.bias_ws[(long long)blockIdx.y * p.K + kout] = bsum;   // 0 for an empty split
+    // epilogue: half-group 0 drains accumulator columns [0, 64), half-group 1 [64, 128)
     if (num_iters == 0) {                     // nothing was accumulated (TMEM holds garbage): this split contributes zeros
       if (kout < p.K)
-        for (int c = ct * 128; c < min(p.C, ct * 128 + 128); ++c) wrow[c] = 0.f;
+        for (int c = ct * 128 + half * 64; c < min(p.C, ct * 128 + half * 64 + 64); ++c) wrow[c] = 0.f;
     } else
 #pragma unroll 1
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 2 * half; j < 2 * half + 2; ++j) {
       uint32_t v[32], u[32];
       const uint32_t taddr = tmem_base + lane_addr + (uint32_t)(j * 32);
       tmem_ld32(taddr, v);
