@@ -304,7 +304,7 @@ def timed_conv_launches(plan, prologue=None, midlogue=None):
     reduce): (summed seconds, launch count, ms by tag, ms by (tag, layer shape))."""
     s_int = torch.cuda.current_stream().cuda_stream
     s = torch.cuda.current_stream()
-    pairs = []
+    pairs, others = [], []
 
     def run_list(steps):
         for i, f in enumerate(steps):
@@ -312,12 +312,9 @@ def timed_conv_launches(plan, prologue=None, midlogue=None):
                 # keep the GPU busy with a spin kernel (~3 ms) while the host enqueues the next launches: a CUDA-event pair around a
                 # short kernel otherwise measures the host's launch latency (ctypes call + tensor-map encodes, ~20 us), not the kernel
                 torch.cuda._sleep(6_000_000)
-            if getattr(f, "what", "").startswith("conv"):
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(s); f(s_int); e1.record(s)
-                pairs.append((e0, e1, f.what, getattr(f, "info", "")))
-            else:
-                f(s_int)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(s); f(s_int); e1.record(s)
+            (pairs if getattr(f, "what", "").startswith("conv") else others).append((e0, e1, getattr(f, "what", "") or "untagged", getattr(f, "info", "")))
     if prologue:
         prologue(s_int)
     run_list(plan.fwd)
@@ -337,6 +334,10 @@ def timed_conv_launches(plan, prologue=None, midlogue=None):
             cnt, tot = by_layer.get(key, (0, 0.0))
             by_layer[key] = (cnt + 1, tot + ms)
     total = sum(a.elapsed_time(b) for a, b, _, _ in pairs) * 1e-3
+    other = {}
+    for a, b, tag, _ in others:         # everything that is not a convolution launch, by tag (same eager, L2-warm conditions)
+        other[tag] = other.get(tag, 0.0) + a.elapsed_time(b)
+    timed_conv_launches.last_other_ms = {k: round(v, 3) for k, v in sorted(other.items(), key=lambda kv: -kv[1])}
     ranked = sorted(by_layer.items(), key=lambda kv: -kv[1][1])
     dump = os.environ.get("DPB200_LAYERS_OUT")           # developer knob: append the full per-layer table of every timed plan to a file
     if dump:
@@ -579,6 +580,7 @@ def run_ours(args, rank, world, local_rank):
             L.check(lib.dp_mse_loss_grad(p.y_out.ptr, sc.noise_nhwc.data_ptr(), gy.ptr, sc.n, sc.loss_scale, sc.grad_scale,
                                          sc.partial.data_ptr(), sc.loss.data_ptr(), s_int))
         conv_s, n_conv, conv_by_tag, conv_by_layer = timed_conv_launches(p, pro, mid)
+        other_ms = timed_conv_launches.last_other_ms
     else:
         conv_s, n_conv, conv_by_tag, conv_by_layer = 1.0, 0, {}, {}
     sampling = None
@@ -639,7 +641,7 @@ def run_ours(args, rank, world, local_rank):
     tier_ceiling = tf_sus / 3.0      # 3 kind::f16 tensor instructions per product (fp16 runs at the bf16 rate MEASURED_PEAKS.json holds)
     roofline = {"bound": "tensor", "achieved": achieved, "peak": tf_sus, "unit": "TFLOP/s", "frac": achieved / tf_sus,
                 "traffic": traffic, "breakdown_ms": conv_by_tag, "top_layers_ms": conv_by_layer,
-                "tf32_peak_measured": tf32, "tier_ceiling_tflops": tier_ceiling, "frac_of_tier_ceiling": achieved / tier_ceiling,
+                "other_launches_ms": other_ms, "tf32_peak_measured": tf32, "tier_ceiling_tflops": tier_ceiling, "frac_of_tier_ceiling": achieved / tier_ceiling,
                 "plan_conv_gflop_per_image": 6.0 * plan_macs / plan_B / 1e9, "plan_linear_gflop_per_image": 6.0 * plan_lin_macs / plan_B / 1e9,
                 "kernel": "conv implicit GEMM (fprop+dgrad+wgrad launches of one pass: %d)" % n_conv,
                 "note": (f"algorithmic conv FLOPs/pass = {B} x {c['conv_flop'] / 1e9:.2f} GFLOP (SURVEY.md §8d) / summed conv-launch device time "

@@ -678,6 +678,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant
   const int chunk0 = blockIdx.y * p.chunks_per_split;
   const int chunk1 = min(p.total_chunks, chunk0 + p.chunks_per_split);
   const int num_iters = max(0, chunk1 - chunk0);   // 0 for a trailing empty split: its workspace tile is zero-filled
+  // 32-channel boxes that hold valid channels (pruned widths: 96 / 179 / 358 ...): boxes past the last channel are neither loaded nor
+  // split — their accumulator rows / columns are never stored, so whatever the stage buffers still hold there is harmless
+  const int dy_boxes = min(4, (p.K - kt * 128 + 31) >> 5), x_boxes = min(4, (p.C - ct * 128 + 31) >> 5);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -687,7 +690,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant
         const int s = it % WSTAGES;
         const uint32_t ph = (uint32_t)(it / WSTAGES) & 1u;
         mbar_wait(empty_bar(s), ph ^ 1u);
-        mbar_expect_tx(full_bar(s), 8 * WG_BLK);
+        mbar_expect_tx(full_bar(s), (uint32_t)((dy_boxes + x_boxes) * WG_BLK));
         const int chunk = chunk0 + it;
         const int tw = chunk % p.tiles_w;
         const int th = (chunk / p.tiles_w) % p.tiles_h;
@@ -696,12 +699,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant
         const uint32_t st = sbase + s * STAGE_BYTES;
         const int xw = q0 * p.in_stride + sx - p.pad, xh = p0 * p.in_stride + r - p.pad;
 #pragma unroll
-        for (int b = 0; b < 4; ++b)     // dy: 4 boxes of 32 out-channels
-          tma_load_4d(st + b * WG_BLK, &mapDy, full_bar(s), kt * 128 + b * 32, q0, p0, n0);
+        for (int b = 0; b < 4; ++b)     // dy: up to 4 boxes of 32 out-channels
+          if (b < dy_boxes) tma_load_4d(st + b * WG_BLK, &mapDy, full_bar(s), kt * 128 + b * 32, q0, p0, n0);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {   // x: channels [64j, 64j+32) -> future x_hi[j], [64j+32, 64j+64) -> future x_lo'[j]
-          tma_load_4d(st + (4 + j) * WG_BLK, &mapX, full_bar(s), ct * 128 + 64 * j, xw, xh, n0);
-          tma_load_4d(st + (6 + j) * WG_BLK, &mapX, full_bar(s), ct * 128 + 64 * j + 32, xw, xh, n0);
+          if (2 * j < x_boxes) tma_load_4d(st + (4 + j) * WG_BLK, &mapX, full_bar(s), ct * 128 + 64 * j, xw, xh, n0);
+          if (2 * j + 1 < x_boxes) tma_load_4d(st + (6 + j) * WG_BLK, &mapX, full_bar(s), ct * 128 + 64 * j + 32, xw, xh, n0);
         }
       }
     }
@@ -757,7 +760,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant
       const uint32_t ph = (uint32_t)(it / WSTAGES) & 1u;
       mbar_wait(full_bar(s), ph);
       // (1) dy^T -> TMEM: channel `lane` of box q, pixel rows 32 half .. 32 half + 31; 16-byte chunk j of row `pix` sits at position j ^ (pix & 7)
-      {
+      if (q < dy_boxes) {
         const uint8_t* blk = smem + s * STAGE_BYTES + q * WG_BLK + half * 32 * 128 + (lane & 3) * 4;
         uint32_t hi[16], lo[16];
         float ssum = 0.f;
@@ -779,10 +782,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDy, const __grid_constant
         uint8_t* a0 = smem + s * STAGE_BYTES + (4 + xj) * WG_BLK + xp * 128;
         uint8_t* a1 = a0 + 2 * WG_BLK;
         const uint8_t* src = half ? a1 : a0;
+        const bool x_valid = 2 * xj + half < x_boxes;
         float4 v[8];
+        if (x_valid) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const float4*>(src + ((c ^ xsw) << 4));
+          for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const float4*>(src + ((c ^ xsw) << 4));
+        }
         asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (x_valid)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const float4 x0 = v[2 * c], x1 = v[2 * c + 1];
@@ -1027,35 +1034,57 @@ __global__ void pack_tc_kernel(const float* __restrict__ w, int K, int C, int RS
     }
   }
 }
-__global__ void split_h3_kernel(const float* __restrict__ x, long long ld, long long bs, int rows, int cols, int transpose,
-                                __half* __restrict__ hi, __half* __restrict__ lo, const uint32_t* __restrict__ amax) {
-  // 32x32 tile through shared memory so both the read (along cols) and the transposed write (along rows) are coalesced
-  __shared__ float t[32][33];
+// fp16 hi / lo' split of a batched [rows][cols] fp32 matrix, dense output rows of `pitch` = round8(cols) elements: 8 columns per thread
+// (two float4 loads, one 16-byte store per output)
+__global__ void split_h3_rows_kernel(const float* __restrict__ x, long long ld, long long bs, int rows, int cols, int pitch, int vec,
+                                     __half* __restrict__ hi, __half* __restrict__ lo, const uint32_t* __restrict__ amax) {
   const float sx = scale_up(amax_exponent(amax));
-  const int b = blockIdx.z, r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int groups = pitch >> 3;
+  const long long total = (long long)rows * groups;
+  const float* xb = x + (long long)blockIdx.y * bs;
+  __half* hb = hi + (long long)blockIdx.y * rows * pitch;
+  __half* lb = lo + (long long)blockIdx.y * rows * pitch;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const long long r = i / groups;
+    const int c0 = (int)(i - r * groups) << 3;
+    const float* src = xb + r * ld + c0;
+    float v[8];
+    if (vec && c0 + 8 <= cols) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src + 4));
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (c0 + j < cols) ? __ldg(src + j) : 0.f;
+    }
+    uint4 h, l;
+    split2(v[0] * sx, v[1] * sx, h.x, l.x); split2(v[2] * sx, v[3] * sx, h.y, l.y);
+    split2(v[4] * sx, v[5] * sx, h.z, l.z); split2(v[6] * sx, v[7] * sx, h.w, l.w);
+    *reinterpret_cast<uint4*>(hb + r * pitch + c0) = h;
+    *reinterpret_cast<uint4*>(lb + r * pitch + c0) = l;
+  }
+}
+// transposed form: out[b][c][r] (rows of round8(rows) elements).  A 32 (c) x 64 (r) tile through shared memory: coalesced float reads
+// along c, half2 writes along r (128 bytes per warp store)
+__global__ void split_h3_t_kernel(const float* __restrict__ x, long long ld, long long bs, int rows, int cols,
+                                  __half* __restrict__ hi, __half* __restrict__ lo, const uint32_t* __restrict__ amax) {
+  __shared__ float t[64][33];
+  const float sx = scale_up(amax_exponent(amax));
+  const int b = blockIdx.z, r0 = blockIdx.y * 64, c0 = blockIdx.x * 32;
   const float* xb = x + (long long)b * bs;
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    int r = r0 + i, c = c0 + threadIdx.x;
+  for (int i = threadIdx.y; i < 64; i += 8) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
     t[i][threadIdx.x] = (r < rows && c < cols) ? xb[(long long)r * ld + c] * sx : 0.f;
   }
   __syncthreads();
-  if (!transpose) {
-    const int cols8 = (cols + 7) & ~7;
-    for (int i = threadIdx.y; i < 32; i += 8) {
-      int r = r0 + i, c = c0 + threadIdx.x;
-      if (r < rows && c < cols8) {
-        long long o = ((long long)b * rows + r) * cols8 + c;
-        split1(t[i][threadIdx.x], hi[o], lo[o]);
-      }
-    }
-  } else {
-    const int rows8 = (rows + 7) & ~7;
-    for (int i = threadIdx.y; i < 32; i += 8) {
-      int c = c0 + i, r = r0 + threadIdx.x;
-      if (c < cols && r < rows8) {
-        long long o = ((long long)b * cols + c) * rows8 + r;
-        split1(t[threadIdx.x][i], hi[o], lo[o]);
-      }
+  const int rows8 = (rows + 7) & ~7;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + 2 * threadIdx.x;
+    if (c < cols && r < rows8) {        // rows8 is even: the pair (r, r+1) is inside the padded row or outside together
+      uint32_t h, l;
+      split2(t[2 * threadIdx.x][i], t[2 * threadIdx.x + 1][i], h, l);
+      const long long o = ((long long)b * cols + c) * rows8 + r;
+      *reinterpret_cast<uint32_t*>(hi + o) = h;
+      *reinterpret_cast<uint32_t*>(lo + o) = l;
     }
   }
 }
@@ -1080,10 +1109,18 @@ extern "C" int dp_split_h3(const float* x, int64_t ld, int64_t bs, int32_t batch
                            const uint32_t* amax, void* hi, void* lo, dp_stream_t stream) {
   DP_REQUIRE(x && hi && lo && amax, DP_ERR_NULL);
   DP_REQUIRE(batch > 0 && rows > 0 && cols > 0 && ld >= cols && batch <= 65535, DP_ERR_SHAPE);
-  // the padded tail of a row (cols8 / rows8) must be covered by the grid: round the covered extent up
-  const int ccov = transpose ? cols : ((cols + 7) & ~7), rcov = transpose ? ((rows + 7) & ~7) : rows;
-  dim3 grid((ccov + 31) / 32, (rcov + 31) / 32, batch);
-  split_h3_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(x, ld, bs, rows, cols, transpose, (__half*)hi, (__half*)lo, amax);
+  if (!transpose) {
+    const int pitch = (cols + 7) & ~7;
+    const int vec = ((((uintptr_t)x) & 15) == 0 && ld % 4 == 0 && bs % 4 == 0) ? 1 : 0;
+    long long blocks = ((long long)rows * (pitch >> 3) + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    split_h3_rows_kernel<<<dim3((unsigned)blocks, (unsigned)batch), 256, 0, (cudaStream_t)stream>>>(x, ld, bs, rows, cols, pitch, vec, (__half*)hi,
+                                                                                                (__half*)lo, amax);
+  } else {
+    // the padded tail of a row (rows8) must be covered by the grid: round the covered extent up
+    dim3 grid((cols + 31) / 32, (((rows + 7) & ~7) + 63) / 64, batch);
+    split_h3_t_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(x, ld, bs, rows, cols, (__half*)hi, (__half*)lo, amax);
+  }
   return dp_check_launch();
 }
 extern "C" int dp_transpose_batched(const float* in, float* out, int32_t batch, int32_t rows, int32_t cols, dp_stream_t stream) {

@@ -539,7 +539,7 @@ class Plan:
                           what="bias grad")
         # 2. wgrad -> split-K workspace -> fixed-order reduce into Parameter.grad
         TC = R * S * Cin
-        tiles = ((K + 127) // 128) * ((TC + 127) // 128)
+        tiles = ((K + 127) // 128) * ((Cin + 127) // 128) * R * S   # the kernel's grid: out-channel tiles x in-channel tiles x taps
         chunks = max(1, out.rows // 64)              # tensor-core wgrad walks 64-pixel chunks
         splits = _wgrad_splits(tiles, chunks)
         self.scratch("wgrad_ws", splits * K * TC)
