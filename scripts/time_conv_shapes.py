@@ -10,7 +10,7 @@ from diff_pruning_b200 import _lib as L  # noqa: E402
 
 lib = L.load()
 S = lambda: torch.cuda.current_stream().cuda_stream
-R = 3
+R = int(os.environ.get('CONV_R', '3'))
 SHAPES = [(128, 128, 32, 128)] if os.environ.get('ONE_SHAPE') else None
 for Cin, K, H, N in SHAPES or [(128, 128, 32, 128), (96, 96, 32, 128), (92, 92, 32, 128), (90, 90, 32, 128), (90, 128, 32, 128), (128, 90, 32, 128),
                      (256, 256, 16, 128), (192, 192, 16, 128), (180, 180, 16, 128), (179, 179, 16, 128), (358, 179, 16, 128)]:
@@ -27,7 +27,7 @@ for Cin, K, H, N in SHAPES or [(128, 128, 32, 128), (96, 96, 32, 128), (92, 92, 
     a = L.ConvArgs()
     a.N, a.H, a.W, a.C, a.P, a.Q, a.K = N, H, H, Cin, H, H, K
     a.R = a.S = R
-    a.stride, a.pad_t, a.pad_l, a.splits = 1, 1, 1, 1
+    a.stride, a.pad_t, a.pad_l, a.splits = 1, R // 2, R // 2, 1
     a.x, a.ldx, a.y, a.ldy = x.data_ptr(), ldx, y.data_ptr(), ldy
     a.w, a.w_tc_hi, a.w_tc_lo = w.data_ptr(), packs[0].data_ptr(), packs[1].data_ptr()
     a.amax_w, a.amax_x = slots.data_ptr(), slots.data_ptr() + 4
@@ -41,6 +41,6 @@ for Cin, K, H, N in SHAPES or [(128, 128, 32, 128), (96, 96, 32, 128), (92, 92, 
     e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 100
-    gf = 2.0 * N * H * H * K * Cin * 9 / 1e9
-    stages = ((Cin + 63) // 64) * 9
+    gf = 2.0 * N * H * H * K * Cin * R * R / 1e9
+    stages = ((Cin + 63) // 64) * R * R
     print(f"Cin {Cin:4d} K {K:4d} @{H}x{H}: {us:7.1f} us  {gf / us * 1e3:6.1f} TF algorithmic  ({stages} stages/tile, {(K + 127) // 128} N tile(s), ld {ldx}/{ldy}) -> {us / stages / ((K + 127) // 128):.2f} us per stage-column")
