@@ -377,22 +377,27 @@ extern "C" int dp_gemm_batched(const dp_gemm_args* a, dp_stream_t stream) {
 // ---------------------------------------------------------------------------------------------
 // split-K reduce + scatter into the OIHW gradient (+ optional signed Taylor accumulation)
 namespace {
+// sum of the splits of one workspace element, in the fixed order every variant of this kernel has used: 4 interleaved accumulators,
+// (s0 + s1) + (s2 + s3)
+__device__ __forceinline__ float split_sum(const float* __restrict__ ws, long long split_stride, int splits) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int z = 0;
+  for (; z + 4 <= splits; z += 4) {
+    s0 += ws[(z + 0) * split_stride]; s1 += ws[(z + 1) * split_stride];
+    s2 += ws[(z + 2) * split_stride]; s3 += ws[(z + 3) * split_stride];
+  }
+  for (; z < splits; ++z) s0 += ws[z * split_stride];
+  return (s0 + s1) + (s2 + s3);
+}
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const dp_wgrad_reduce_args a) {
-  // block (x = chunk of 256 (tap,c) entries, y = output channel k): coalesced reads of every split, 4 splits in flight
+  // block (x = chunk of 256 (tap,c) entries, y = output channel k): coalesced reads of every split, 4 splits in flight.  (One thread per
+  // (k, c) writing the R*S contiguous gradient values was measured: better stores, but 9x fewer threads — slower on C1 / C3 weights.)
   const int k = blockIdx.y;
   const int RS = a.R * a.S, TC = RS * a.C;
   const long long split_stride = (long long)a.K * TC;
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i < TC) {
-    const float* ws = a.workspace + (long long)k * TC + i;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int z = 0;
-    for (; z + 4 <= a.splits; z += 4) {
-      s0 += ws[(z + 0) * split_stride]; s1 += ws[(z + 1) * split_stride];
-      s2 += ws[(z + 2) * split_stride]; s3 += ws[(z + 3) * split_stride];
-    }
-    for (; z < a.splits; ++z) s0 += ws[z * split_stride];
-    const float s = (s0 + s1) + (s2 + s3);
+    const float s = split_sum(a.workspace + (long long)k * TC + i, split_stride, a.splits);
     const int tap = i / a.C, c = i - tap * a.C;
     const long long gi = ((long long)k * a.C + c) * RS + tap;
     a.dw[gi] += s;
@@ -404,6 +409,37 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const dp_wgrad_reduce
     // signed first-order Taylor term of this pass, parked in the (already consumed) split-0 slot for the score kernels
     if (a.w && (a.score_out || a.score_in)) const_cast<float*>(a.workspace)[(long long)k * TC + i] = a.w[gi] * s;
   }
+}
+// R = S = 1 with 16-byte aligned rows (every nn.Linear, 1x1 convolution): the tensor is flat, 4 elements per thread
+__global__ void __launch_bounds__(256) wgrad_reduce_flat4_kernel(const dp_wgrad_reduce_args a) {
+  const long long n4 = (long long)a.K * a.C / 4, split_stride4 = n4;
+  const bool scores = a.w && (a.score_out || a.score_in);
+  const float4* ws = reinterpret_cast<const float4*>(a.workspace);
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    float4 s0 = make_float4(0, 0, 0, 0), s1 = s0, s2 = s0, s3 = s0;
+    auto add = [](float4& acc, const float4 v) { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; };
+    int z = 0;
+    for (; z + 4 <= a.splits; z += 4) {
+      add(s0, ws[(z + 0) * split_stride4 + i]); add(s1, ws[(z + 1) * split_stride4 + i]);
+      add(s2, ws[(z + 2) * split_stride4 + i]); add(s3, ws[(z + 3) * split_stride4 + i]);
+    }
+    for (; z < a.splits; ++z) add(s0, ws[z * split_stride4 + i]);
+    const float4 s = make_float4((s0.x + s1.x) + (s2.x + s3.x), (s0.y + s1.y) + (s2.y + s3.y), (s0.z + s1.z) + (s2.z + s3.z), (s0.w + s1.w) + (s2.w + s3.w));
+    float4* dst = reinterpret_cast<float4*>(a.dw) + i;
+    float4 d = *dst;
+    d.x += s.x; d.y += s.y; d.z += s.z; d.w += s.w;
+    *dst = d;
+    if (scores) {
+      const float4 w = reinterpret_cast<const float4*>(a.w)[i];
+      const_cast<float4*>(ws)[i] = make_float4(w.x * s.x, w.y * s.y, w.z * s.z, w.w * s.w);
+    }
+  }
+  if (a.bias_ws)
+    for (long long k = blockIdx.x * 256ll + threadIdx.x; k < a.K; k += (long long)gridDim.x * 256) {
+      float b = 0.f;
+      for (int z2 = 0; z2 < a.splits; ++z2) b += a.bias_ws[(long long)z2 * a.K + k];
+      a.db[k] += b;
+    }
 }
 __global__ void wgrad_score_out_kernel(const dp_wgrad_reduce_args a) {
   // one block per output channel k: fixed-order sum over (tap, c) of W*dW_t
@@ -460,10 +496,17 @@ extern "C" int dp_conv2d_wgrad_reduce(const dp_wgrad_reduce_args* a, dp_stream_t
   DP_REQUIRE((a->bias_ws == nullptr) == (a->db == nullptr), DP_ERR_NULL);
   DP_REQUIRE(a->K > 0 && a->C > 0 && a->R > 0 && a->S > 0 && a->splits >= 1, DP_ERR_SHAPE);
   cudaStream_t st = (cudaStream_t)stream;
-  const int TC = a->R * a->S * a->C;
-  const int nblk = (TC + 255) / 256;
-  DP_REQUIRE(a->K <= 65535, DP_ERR_SHAPE);
-  wgrad_reduce_kernel<<<dim3(nblk, a->K), 256, 0, st>>>(*a);
+  const int RS = a->R * a->S, TC = RS * a->C;
+  const long long kc = (long long)a->K * a->C;
+  if (RS == 1 && a->C % 4 == 0 && ((((uintptr_t)a->workspace) | ((uintptr_t)a->dw) | ((uintptr_t)a->w)) & 15) == 0) {
+    // flat tensor (every nn.Linear / 1x1 convolution: most of the 400 M LDM parameters): 4 elements per thread, grid-stride
+    long long blocks = (kc / 4 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    wgrad_reduce_flat4_kernel<<<(unsigned)(blocks < 1 ? 1 : blocks), 256, 0, st>>>(*a);
+  } else {
+    DP_REQUIRE(a->K <= 65535, DP_ERR_SHAPE);
+    wgrad_reduce_kernel<<<dim3((TC + 255) / 256, a->K), 256, 0, st>>>(*a);
+  }
   int rc = dp_check_launch();
   if (rc) return rc;
   if (a->w && a->score_out) {
