@@ -381,3 +381,50 @@ def test_attention_nt_gemm_tc(lib, N, H, W, Kg, Nn):
     Y = torch.empty(N, 45, 70, device="cuda")
     assert lib.dp_transpose_batched(X.data_ptr(), Y.data_ptr(), N, 70, 45, S()) == 0
     assert torch.equal(Y, X.transpose(1, 2))
+
+
+def test_fp16_split_dynamic_range_within_one_tensor(lib):
+    """The 3-product fp16 split scales every operand by ONE power of two per tensor.  Elements far below the tensor's maximum keep their
+    relative precision as long as the scaled value stays a normal fp16 number (2^28 of range below the 2^14 the maximum is scaled to);
+    beyond that the ABSOLUTE error stays at 2^-50 of the maximum.  dgrad of a 1x1 convolution whose dy has output channels scaled by
+    2^0 / 2^-12 / 2^-24 / 2^-36: each group of input-gradient contributions is checked against fp64 on its own scale."""
+    from diff_pruning_b200 import _lib as L
+    g = torch.Generator().manual_seed(5)
+    N, H, Cin, K = 4, 16, 128, 128
+    w = torch.randn(K, Cin, 1, 1, generator=g) / math.sqrt(Cin)
+    gy = torch.randn(N, K, H, H, generator=g)
+    scales = (0, -12, -24, -36)
+    wd = w.contiguous().cuda()
+    packs = pack_tc(lib, wd, K, Cin, 1)
+    kc = torch.empty(w.numel(), device="cuda")
+    ck = torch.empty(w.numel(), device="cuda")
+    assert lib.dp_pack_conv_weight(wd.data_ptr(), K, Cin, 1, 1, ck.data_ptr(), kc.data_ptr(), S()) == 0
+    worst = {}
+    for e in scales:
+        # only the first 32 output channels carry gradient, at scale 2^e; the rest of the tensor holds O(1) values in OTHER pixels' rows,
+        # so the tensor's maximum (and with it the scale) stays O(1): zero them where the probe lives to read the probe's contribution alone
+        gyp = torch.zeros_like(gy)
+        gyp[:, :32] = gy[:, :32] * 2.0 ** e
+        big = torch.zeros_like(gy)
+        big[0, 64:, 0, 0] = 8.0                                   # one pixel keeps max|dy| = 8 whatever e is
+        dyd = nhwc(gyp + big)
+        ref = F.conv_transpose2d((gyp + big).double(), w.double())   # dx = dy * W for a 1x1 convolution
+        ref_probe = F.conv_transpose2d(gyp.double(), w.double())
+        gx = torch.full((N, H, H, Cin), float("nan"), device="cuda")
+        d = L.ConvArgs()
+        d.N, d.H, d.W, d.C, d.P, d.Q, d.K = N, H, H, Cin, H, H, K
+        d.R = d.S = 1
+        d.stride, d.pad_t, d.pad_l, d.splits = 1, 0, 0, 1
+        d.x, d.ldx, d.y, d.ldy = gx.data_ptr(), Cin, dyd.data_ptr(), K
+        sdy = amax_slot(lib, dyd)
+        d.w, d.w_tc_hi, d.w_tc_lo, d.amax_w, d.amax_y = kc.data_ptr(), packs[2].data_ptr(), packs[3].data_ptr(), packs[4].data_ptr(), sdy.data_ptr()
+        n0 = lib.dp_launch_count()
+        assert lib.dp_conv2d_dgrad(C.byref(d), S()) == 0 and lib.dp_launch_count() - n0 == 1
+        got = nchw(gx).double()
+        assert rel_err(got, ref) < 1.5e-5
+        keep = torch.ones(N, 1, H, H, dtype=torch.bool)
+        keep[0, 0, 0, 0] = False                                  # the big pixel's own outputs are O(1): fp32 output rounding hides the probe there
+        worst[e] = float(((got - ref_probe) * keep).norm() / (ref_probe * keep).norm())
+    print("relative error of the 2^e-scaled part on its own scale:", worst)
+    assert worst[0] < 1e-6 and worst[-12] < 1e-6 and worst[-24] < 1e-5     # still normal fp16 numbers after scaling: full precision (measured 1e-7, 1e-7, 2e-7)
+    assert worst[-36] < 1e-2                                                  # below fp16's range: absolute error ~2^-50 of the maximum (measured 6e-4)
