@@ -52,4 +52,6 @@ __device__ __forceinline__ void amax_commit(uint32_t* slot, float m) {
   const uint32_t r = __reduce_max_sync(mask, __float_as_uint(m));
   if ((threadIdx.x & 31) == (unsigned)(__ffs(mask) - 1) && r) atomicMax(slot, r);
 }
-__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+// 1 / (1 + exp(-x)): __frcp_rn is the correctly rounded reciprocal, i.e. the same bits as the IEEE division 1.0f / y, without the
+// division's slow-path check
+__device__ __forceinline__ float sigmoidf_acc(float x) { return __frcp_rn(1.0f + expf(-x)); }

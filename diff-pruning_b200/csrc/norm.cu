@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(NT) gn_bwd_partial4_kernel(const dp_gn_args a,
   if (act) {
     const float* xb = a.x + (long long)n * a.HW * a.ldx + c0;
     const float* db = a.dy + (long long)n * a.HW * a.lddy + c0;
-#pragma unroll 2
+#pragma unroll 4
     for (int pix = p0 + pl; pix < p1; pix += mp.PL) {
       float4 xv = ld4(xb + (long long)pix * a.ldx), dv = ld4(db + (long long)pix * a.lddy);
       float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ds[4] = {dv.x, dv.y, dv.z, dv.w};
@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(NT) gn_bwd_apply4_kernel(const dp_gn_args a, c
   const float* ab = a.dx_add ? a.dx_add + (long long)n * a.HW * a.ldadd + c0 : nullptr;
   const float* ab2 = a.dx_add2 ? a.dx_add2 + (long long)n * a.HW * a.ldadd2 + c0 : nullptr;
   float amax = 0.f;
-#pragma unroll 2
+#pragma unroll 4
   for (int pix = p0 + pl; pix < p1; pix += mp.PL) {
     float4 xv = ld4(xb + (long long)pix * a.ldx), dv = ld4(db + (long long)pix * a.lddy);
     float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ds[4] = {dv.x, dv.y, dv.z, dv.w}, d[4];
