@@ -101,6 +101,8 @@ def _copy_args(a):
 AMAX_SLOTS = 8192  # capacity of a plan's amax-slot arrays (one uint32 per tensor-core operand use)
 AUDIT_SLOTS = False  # tests: plans built while this is set check every amax slot against torch.amax of its operand right before the
                      # consuming launch (eager runs only: the check synchronises)
+SIDE_WGRAD = True  # backward: weight-gradient launches (wgrad + split-K reduce) run on a second stream.  They only feed Parameter.grad, so the
+                   # dgrad -> GroupNorm chain does not wait for them, and the small latency-bound kernels of that chain share SMs with wgrad CTAs
 SPLITK = True      # small-M fprop / dgrad launches split their K loop over idle SMs (dp_conv_splitk_workspace_floats)
 ARENA_ALIGN = 64   # floats: every parameter's slice of a flat arena starts on a 256-byte boundary
 
@@ -542,7 +544,11 @@ class Plan:
         tiles = ((K + 127) // 128) * ((Cin + 127) // 128) * R * S   # the kernel's grid: out-channel tiles x in-channel tiles x taps
         chunks = max(1, out.rows // 64)              # tensor-core wgrad walks 64-pixel chunks
         splits = _wgrad_splits(tiles, chunks)
-        self.scratch("wgrad_ws", splits * K * TC)
+        # dy in a per-tensor gradient buffer stays valid for the rest of the backward: its weight gradient may run on the side stream
+        # (own scratch: the main stream's wgrads — the temb projections, whose dy lives in a reused scratch — must not share it)
+        side = SIDE_WGRAD and dy_dense is None
+        ws_name, bws_name = ("wgrad_ws_side", "bias_ws_side") if side else ("wgrad_ws", "bias_ws")
+        self.scratch(ws_name, splits * K * TC)
         amax_dy = None
         if wtc is not None:
             amax_dy = self._amax(steps, dy_get, dy_ld, out.rows, K) if dy_dense is not None else self._dy_slot(steps, out)
@@ -551,22 +557,24 @@ class Plan:
         wa.flags, wa.splits = 0, splits
         wa.ldy = dy_ld
         wa.rowadd, wa.residual, wa.bias = None, None, None
-        self._late.append(lambda wa=wa, g=dy_get: (setattr(wa, "y", g()), setattr(wa, "workspace", self.sptr("wgrad_ws"))))
+        self._late.append(lambda wa=wa, g=dy_get, n=ws_name: (setattr(wa, "y", g()), setattr(wa, "workspace", self.sptr(n))))
         if bias_in_wgrad:
-            self.scratch("bias_ws", splits * K)
-            self._late.append(lambda wa=wa: setattr(wa, "bias_ws", self.sptr("bias_ws")))
+            self.scratch(bws_name, splits * K)
+            self._late.append(lambda wa=wa, n=bws_name: setattr(wa, "bias_ws", self.sptr(n)))
         self._rec(steps, lib.dp_conv2d_wgrad, wa, "conv wgrad", info)
+        steps[-1].side = 2 if side else 0          # 2: first launch of a side group (waits for the main stream's progress so far)
         ra = L.WgradReduceArgs()
         ra.K, ra.C, ra.R, ra.S, ra.splits = K, Cin, R, S, splits
         ra.dw = self.pgrad(w)
         if self.fused_scores:   # signed first-order Taylor terms sum_k W*dW_t fall out of the split-K reduce (ddpm_prune.py:60)
             so, si = self._score_views(w, K, Cin)
             ra.w, ra.score_out, ra.score_in = w.data_ptr(), so.data_ptr(), si.data_ptr()
-        self._late.append(lambda ra=ra: setattr(ra, "workspace", self.sptr("wgrad_ws")))
+        self._late.append(lambda ra=ra, n=ws_name: setattr(ra, "workspace", self.sptr(n)))
         if bias_in_wgrad:
             ra.db = self.pgrad(b)
-            self._late.append(lambda ra=ra: setattr(ra, "bias_ws", self.sptr("bias_ws")))
+            self._late.append(lambda ra=ra, n=bws_name: setattr(ra, "bias_ws", self.sptr(n)))
         self._rec(steps, lib.dp_conv2d_wgrad_reduce, ra, "conv wgrad reduce")
+        steps[-1].side = 1 if side else 0
         # 3. dgrad
         if need_dx:
             da = _copy_args(a)
@@ -1086,6 +1094,8 @@ class Plan:
             self._rec(zero, lambda s: lib.dp_zero_u32(ptr, n, s), what="amax zero")
             self.fwd.insert(0, zero[0])
         self.bwd_steps: List[Step] = [f for it in reversed(self.bwd) for f in it.steps]
+        self._has_side = any(getattr(f, "side", 0) for f in self.bwd_steps)
+        self._side_stream = None
 
     # ------------------------------------------------------------------ latent-diffusion UNetModel (ldm.py; BASELINE configs[4])
     def _tokens(self, v: View) -> View:
@@ -1330,8 +1340,24 @@ class Plan:
     def run_backward(self, s: Optional[int] = None):
         s = _stream() if s is None else s
         self.gradof(self.silu_temb).t.zero_()
+        main = torch.cuda.current_stream(self.dev)
+        if not self._has_side or main.cuda_stream != s:
+            for f in self.bwd_steps:
+                f(s)
+            return
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=self.dev)
+        side = self._side_stream
+        s2 = side.cuda_stream
         for f in self.bwd_steps:
-            f(s)
+            k = getattr(f, "side", 0)
+            if k == 2:                  # dy (and its amax slot) are final at this point of the main stream
+                side.wait_stream(main)
+            if k:
+                f(s2)
+            else:
+                f(s)
+        main.wait_stream(side)          # Parameter.grad is complete when the pass ends (also closes a CUDA-graph capture's fork)
 
     def load_input_nchw(self, sample: torch.Tensor, timesteps: torch.Tensor):
         sample = sample.contiguous()
