@@ -453,7 +453,7 @@ class Plan:
         return got
 
     def _colsum_tree(self, steps: List[Step], src_ptr: int, ld: int, rows: int, per_img: int, cols: int,
-                     seg_name: Optional[str]) -> str:
+                     seg_name: Optional[str], tmp: Tuple[str, str] = ("cs_a", "cs_b")) -> str:
         """Deterministic hierarchical column sums of a [rows][cols] view down to per-image sums (dense [N][cols]);
         returns the scratch name holding them."""
         lib = self.lib
@@ -463,7 +463,7 @@ class Plan:
             s_rows = 256 if (cur_per > 256 and cur_per % 256 == 0) else cur_per
             nseg = cur_rows // s_rows
             last = cur_per == s_rows
-            out_name = seg_name if (last and seg_name) else ("cs_a", "cs_b")[level & 1]
+            out_name = seg_name if (last and seg_name) else tmp[level & 1]
             self.scratch(out_name, nseg * cols)
             self._rec(steps, lambda s, g=get, ld_=cur_ld, r=cur_rows, sr=s_rows, o=out_name:
                       lib.dp_colsum(g(), ld_, r, cols, sr, self.sptr(o), cols, 0, s), what="colsum")
@@ -517,6 +517,10 @@ class Plan:
             return
         it = self._bitem()
         steps = it.steps
+        # The time-embedding branch of a resnet (per-image sums of conv1's dy -> bias / time_emb_proj gradients -> d silu(temb)) only meets
+        # the main chain again at the very end of the backward: all of it runs on the side stream (fp32-grade plans; scratch of its own)
+        temb_side = SIDE_WGRAD and not self.bf16 and (dy_dense is not None or seg_out is not None)
+        n_steps0 = len(steps)
         if dy_dense is not None:
             self.scratch(dy_dense, out.rows * K)
             dy_get, dy_ld = (lambda n=dy_dense: self.sptr(n)), K
@@ -535,10 +539,15 @@ class Plan:
                 # src pointer may be late-bound (dense scratch) -> wrap
                 if dy_dense is not None:
                     raise NotImplementedError("dense dy with spatial extent")
-                seg = self._colsum_tree(steps, dout.ptr, dout.ld, out.rows, out.H * out.W, K, seg_out)
+                seg = self._colsum_tree(steps, dout.ptr, dout.ld, out.rows, out.H * out.W, K, seg_out,
+                                        ("cs_a_side", "cs_b_side") if temb_side else ("cs_a", "cs_b"))
             if b is not None:
                 self._rec(steps, lambda s, seg=seg, b=b, n=x.N: lib.dp_colsum(self.sptr(seg), K, n, K, n, self.pgrad(b), K, 1, s),
                           what="bias grad")
+            if temb_side:
+                for f in steps[n_steps0:]:
+                    f.side = 1
+                steps[n_steps0].side = 2
         # 2. wgrad -> split-K workspace -> fixed-order reduce into Parameter.grad
         TC = R * S * Cin
         tiles = ((K + 127) // 128) * ((Cin + 127) // 128) * R * S   # the kernel's grid: out-channel tiles x in-channel tiles x taps
@@ -546,8 +555,9 @@ class Plan:
         splits = _wgrad_splits(tiles, chunks)
         # dy in a per-tensor gradient buffer stays valid for the rest of the backward: its weight gradient may run on the side stream
         # (own scratch: the main stream's wgrads — the temb projections, whose dy lives in a reused scratch — must not share it)
-        side = SIDE_WGRAD and dy_dense is None
+        side = SIDE_WGRAD and (dy_dense is None or temb_side)
         ws_name, bws_name = ("wgrad_ws_side", "bias_ws_side") if side else ("wgrad_ws", "bias_ws")
+        n_steps1 = len(steps)
         self.scratch(ws_name, splits * K * TC)
         amax_dy = None
         if wtc is not None:
@@ -597,15 +607,19 @@ class Plan:
                 it.writes.append((tgt, lambda init, da=da: setattr(da, "flags", 1 if init else 0),
                                   lambda slot, da=da: setattr(da, "amax_out", slot)))
             da.workspace = None
-            self._splitk(da, 1)
+            self._splitk(da, 1, "splitk_ws_side" if (temb_side and dy_dense is not None) else "splitk_ws")
             self._rec(steps, lib.dp_conv2d_dgrad, da, "conv dgrad", info)
+        if temb_side and dy_dense is not None:      # the time_emb_proj convolution: amax(dy), wgrad, reduce, dgrad all on the side stream
+            for f in steps[n_steps1:]:
+                f.side = 1
+            steps[n_steps1].side = 2
 
-    def _splitk(self, a, op: int):
+    def _splitk(self, a, op: int, name: str = "splitk_ws"):
         """Small-M launches (4x4 .. 16x16 levels) split their K loop over the idle SMs: one shared scratch, bound late."""
         need = int(self.lib.dp_conv_splitk_workspace_floats(C.byref(a), op)) if SPLITK else 0
         if need > 0:
-            self.scratch("splitk_ws", need)
-            self._late.append(lambda a=a: setattr(a, "workspace", self.sptr("splitk_ws")))
+            self.scratch(name, need)
+            self._late.append(lambda a=a, n=name: setattr(a, "workspace", self.sptr(n)))
 
     def _conv_bf16(self, x, w, b, out, stride, pad, rowadd, residual, accumulate_out, need_dx, dx_scratch, seg_out, dx_into):
         """conv() on the bf16 tensor tier: same launch structure and fp32 outputs, operands as bf16 copies."""
@@ -943,6 +957,7 @@ class Plan:
             self._rec(self._bitem().steps,
                       lambda s: lib.dp_silu_bwd(emb.ptr, self.gradof(self.silu_temb).ptr, self.gradof(emb).ptr, n2, 0, s),
                       what="silu bwd")
+            self.bwd[-1].steps[-1].join = True     # d silu(temb) is complete only when the side stream's time-embedding branches are
 
         # ---- skip/concat geometry: every skip lives in the upper channel range of its consumer's concat buffer
         skip_shapes = []
@@ -1205,6 +1220,7 @@ class Plan:
         if self.need_grad:
             self._rec(self._bitem().steps,
                       lambda s: lib.dp_silu_bwd(emb.ptr, self.gradof(self.silu_temb).ptr, self.gradof(emb).ptr, n2, 0, s), what="silu bwd")
+            self.bwd[-1].steps[-1].join = True     # d silu(temb) is complete only when the side stream's time-embedding branches are
 
         def as_resnet(rb):     # ResBlock (openaimodel.py:163-275) in the attribute vocabulary of Plan.resnet()
             sk = rb.skip_connection
@@ -1341,7 +1357,7 @@ class Plan:
         s = _stream() if s is None else s
         self.gradof(self.silu_temb).t.zero_()
         main = torch.cuda.current_stream(self.dev)
-        if not self._has_side or main.cuda_stream != s:
+        if not self._has_side or main.cuda_stream != s or self.audit:
             for f in self.bwd_steps:
                 f(s)
             return
@@ -1356,6 +1372,8 @@ class Plan:
             if k:
                 f(s2)
             else:
+                if getattr(f, "join", False):
+                    main.wait_stream(side)
                 f(s)
         main.wait_stream(side)          # Parameter.grad is complete when the pass ends (also closes a CUDA-graph capture's fork)
 
