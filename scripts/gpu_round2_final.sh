@@ -6,8 +6,8 @@ mkdir -p gpurun_out
 timeout 2400 python -m pytest tests -q -m gpu --timeout=900 > gpurun_out/pytest_main.log 2>&1
 echo "== full suite rc=$?"; grep -n "^E  .*Error\|^E   *assert\|^FAILED\|passed\|failed" gpurun_out/pytest_main.log | head -30
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-/usr/bin/time -v -o gpurun_out/bench_time.txt timeout 900 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
-echo "== default bench rc=$? wall: $(grep Elapsed gpurun_out/bench_time.txt)"; python - <<'PY'
+S0=$(date +%s); timeout 900 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
+echo "== default bench rc=$? wall: $(( $(date +%s) - S0 )) s"; python - <<'PY'
 import json
 d=json.loads(open('gpurun_out/bench_default.json').read().strip().split('\n')[-1])
 print('c1', d['value'], d['ms_per_step'], 'e2e', d['e2e'], 'launches', d['gpu_launches'], 'clocks', d['clocks'])
