@@ -452,6 +452,139 @@ __global__ void __launch_bounds__(NT) gn_bwd_apply4_kernel(const dp_gn_args a, c
 
 static inline bool al16(const void* p, long long ld) { return p == nullptr || ((((uintptr_t)p) & 15) == 0 && (ld % 4) == 0); }
 
+// ------------------------------------------------------------------------------------------------------------
+// LayerNorm = GroupNorm with ONE group over the channels of a ONE-pixel "image" (the LDM transformer blocks call it on every token:
+// N = tokens).  The chunked kernels above would spend a whole 256-thread block on one token; here a warp owns a row: float4 loads,
+// two passes over registers (mean, then centred sum of squares), warp-shuffle reductions.  Rows of up to 4 * 32 * LN_V = 1280 channels.
+constexpr int LN_V = 10;
+__device__ __forceinline__ float warp_sum_all(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const dp_gn_args a) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= a.N) return;
+  const int nv = a.C >> 2;
+  const float* xr = a.x + row * a.ldx;
+  float4 v[LN_V];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < LN_V; ++j) {
+    const int i = lane + 32 * j;
+    v[j] = i < nv ? ld4(xr + 4 * i) : make_float4(0, 0, 0, 0);
+    s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+  }
+  const float mean = warp_sum_all(s) / (float)a.C;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < LN_V; ++j)
+    if (lane + 32 * j < nv) {
+      const float dx = v[j].x - mean, dy = v[j].y - mean, dz = v[j].z - mean, dw = v[j].w - mean;
+      q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    }
+  const float rstd = 1.0f / sqrtf(warp_sum_all(q) / (float)a.C + a.eps);
+  if (lane == 0) { a.mean[row] = mean; a.rstd[row] = rstd; }
+  float* yr = a.y + row * a.ldy;
+  float amax = 0.f;
+#pragma unroll
+  for (int j = 0; j < LN_V; ++j) {
+    const int i = lane + 32 * j;
+    if (i < nv) {
+      const float4 g = ld4(a.gamma + 4 * i), b = ld4(a.beta + 4 * i);
+      float4 y;
+      y.x = fmaf((v[j].x - mean) * rstd, g.x, b.x); y.y = fmaf((v[j].y - mean) * rstd, g.y, b.y);
+      y.z = fmaf((v[j].z - mean) * rstd, g.z, b.z); y.w = fmaf((v[j].w - mean) * rstd, g.w, b.w);
+      *reinterpret_cast<float4*>(yr + 4 * i) = y;
+      amax = fmaxf(fmaxf(amax, fmaxf(fabsf(y.x), fabsf(y.y))), fmaxf(fabsf(y.z), fabsf(y.w)));
+    }
+  }
+  if (a.amax_y) amax_commit(a.amax_y, amax);
+}
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)) (+ addends), g = dy * gamma
+__global__ void __launch_bounds__(256) ln_bwd_dx_kernel(const dp_gn_args a) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= a.N) return;
+  const int nv = a.C >> 2;
+  const float mean = a.mean[row], rstd = a.rstd[row];
+  const float* xr = a.x + row * a.ldx;
+  const float* dr = a.dy + row * a.lddy;
+  float4 xh[LN_V], g[LN_V];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < LN_V; ++j) {
+    const int i = lane + 32 * j;
+    if (i < nv) {
+      const float4 x = ld4(xr + 4 * i), d = ld4(dr + 4 * i), ga = ld4(a.gamma + 4 * i);
+      xh[j] = make_float4((x.x - mean) * rstd, (x.y - mean) * rstd, (x.z - mean) * rstd, (x.w - mean) * rstd);
+      g[j] = make_float4(d.x * ga.x, d.y * ga.y, d.z * ga.z, d.w * ga.w);
+      s1 += (g[j].x + g[j].y) + (g[j].z + g[j].w);
+      s2 += (g[j].x * xh[j].x + g[j].y * xh[j].y) + (g[j].z * xh[j].z + g[j].w * xh[j].w);
+    } else { xh[j] = make_float4(0, 0, 0, 0); g[j] = xh[j]; }
+  }
+  const float m1 = warp_sum_all(s1) / (float)a.C, m2 = warp_sum_all(s2) / (float)a.C;
+  float* out = a.dx + row * a.lddx;
+  const float* ab = a.dx_add ? a.dx_add + row * a.ldadd : nullptr;
+  const float* ab2 = a.dx_add2 ? a.dx_add2 + row * a.ldadd2 : nullptr;
+  float amax = 0.f;
+#pragma unroll
+  for (int j = 0; j < LN_V; ++j) {
+    const int i = lane + 32 * j;
+    if (i < nv) {
+      float4 d = make_float4(rstd * (g[j].x - m1 - xh[j].x * m2), rstd * (g[j].y - m1 - xh[j].y * m2),
+                             rstd * (g[j].z - m1 - xh[j].z * m2), rstd * (g[j].w - m1 - xh[j].w * m2));
+      if (ab) { const float4 t = *reinterpret_cast<const float4*>(ab + 4 * i); d.x += t.x; d.y += t.y; d.z += t.z; d.w += t.w; }
+      if (ab2) { const float4 t = ld4(ab2 + 4 * i); d.x += t.x; d.y += t.y; d.z += t.z; d.w += t.w; }
+      *reinterpret_cast<float4*>(out + 4 * i) = d;
+      amax = fmaxf(fmaxf(amax, fmaxf(fabsf(d.x), fabsf(d.y))), fmaxf(fabsf(d.z), fabsf(d.w)));
+    }
+  }
+  if (a.amax_dx) amax_commit(a.amax_dx, amax);
+}
+// dgamma / dbeta partials: block = 32 float4 column groups x 8 row lanes over a chunk of LN_ROWS rows; part[chunk][2][C]
+constexpr int LN_ROWS = 256;
+__global__ void __launch_bounds__(256) ln_bwd_param_partial_kernel(const dp_gn_args a, float* __restrict__ part) {
+  __shared__ float4 sg[8][33], sb[8][33];
+  const int cx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + cx;                 // float4 column group
+  const int nv = a.C >> 2;
+  const long long r0 = (long long)blockIdx.y * LN_ROWS, r1 = min((long long)a.N, r0 + LN_ROWS);
+  float4 tg = make_float4(0, 0, 0, 0), tb = tg;
+  if (i < nv)
+    for (long long r = r0 + ly; r < r1; r += 8) {
+      const float mean = a.mean[r], rstd = a.rstd[r];
+      const float4 x = ld4(a.x + r * a.ldx + 4 * i), d = ld4(a.dy + r * a.lddy + 4 * i);
+      tg.x += d.x * ((x.x - mean) * rstd); tg.y += d.y * ((x.y - mean) * rstd);
+      tg.z += d.z * ((x.z - mean) * rstd); tg.w += d.w * ((x.w - mean) * rstd);
+      tb.x += d.x; tb.y += d.y; tb.z += d.z; tb.w += d.w;
+    }
+  sg[ly][cx] = tg; sb[ly][cx] = tb;
+  __syncthreads();
+  if (ly == 0 && i < nv) {
+    for (int l = 1; l < 8; ++l) {
+      tg.x += sg[l][cx].x; tg.y += sg[l][cx].y; tg.z += sg[l][cx].z; tg.w += sg[l][cx].w;
+      tb.x += sb[l][cx].x; tb.y += sb[l][cx].y; tb.z += sb[l][cx].z; tb.w += sb[l][cx].w;
+    }
+    float* o = part + (long long)blockIdx.y * 2 * a.C;
+    *reinterpret_cast<float4*>(o + 4 * i) = tg;
+    *reinterpret_cast<float4*>(o + a.C + 4 * i) = tb;
+  }
+}
+__global__ void ln_bwd_param_final_kernel(const dp_gn_args a, const float* __restrict__ part, int chunks) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.C) return;
+  double tg = 0, tb = 0;
+  for (int ch = 0; ch < chunks; ++ch) { tg += part[(long long)ch * 2 * a.C + c]; tb += part[(long long)ch * 2 * a.C + a.C + c]; }
+  if (a.dgamma) a.dgamma[c] += (float)tg;
+  if (a.dbeta) a.dbeta[c] += (float)tb;
+}
+static inline bool ln_fast(const dp_gn_args* a) {     // the row kernels take what the LDM transformer blocks ask for
+  return a->HW == 1 && a->G == 1 && a->C % 4 == 0 && a->C <= 4 * 32 * LN_V && !a->silu && a->dropout_p == 0.f && !a->y_bf16;
+}
+
+
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 }  // namespace
@@ -469,7 +602,7 @@ extern "C" size_t dp_groupnorm_workspace_bytes(int32_t N, int32_t HW, int32_t C,
 static int gn_validate(const dp_gn_args* a) {
   DP_REQUIRE(a && a->x && a->gamma && a->beta && a->mean && a->rstd && a->workspace, DP_ERR_NULL);
   DP_REQUIRE(a->N > 0 && a->HW > 0 && a->C > 0 && a->G > 0 && a->C % a->G == 0, DP_ERR_SHAPE);
-  DP_REQUIRE(a->C <= NT * MAXCPT && a->G <= 1024, DP_ERR_UNSUPPORTED);
+  DP_REQUIRE((a->C <= NT * MAXCPT || ln_fast(a)) && a->G <= 1024, DP_ERR_UNSUPPORTED);
   DP_REQUIRE(a->N <= 65535, DP_ERR_SHAPE);
   DP_REQUIRE(a->ldx >= a->C, DP_ERR_SHAPE);
   DP_REQUIRE(a->dropout_p >= 0.f && a->dropout_p < 1.f, DP_ERR_SHAPE);
@@ -484,6 +617,10 @@ extern "C" int dp_groupnorm_fwd(const dp_gn_args* a, dp_stream_t stream) {
   DP_REQUIRE(!a->y_bf16 || (a->ldyb >= a->C && a->ldyb % 8 == 0 && (((uintptr_t)a->y_bf16) & 15) == 0), DP_ERR_ALIGN);
   cudaStream_t st = (cudaStream_t)stream;
   const bool v4 = (a->C % 4 == 0) && al16(a->x, a->ldx) && al16(a->y, a->ldy);
+  if (v4 && a->y && ln_fast(a) && al16(a->gamma, 0) && al16(a->beta, 0)) {     // LayerNorm over tokens: one warp per row
+    ln_fwd_kernel<<<(unsigned)((a->N + 7) / 8), 256, 0, st>>>(*a);
+    return dp_check_launch();
+  }
   Map mp = v4 ? make_map4(a->HW, a->C) : make_map(a->HW, a->C);
   dim3 grid(mp.nchunks, a->N);
   if (v4) {
@@ -508,6 +645,18 @@ extern "C" int dp_groupnorm_bwd(const dp_gn_args* a, dp_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const bool v4 = (a->C % 4 == 0) && al16(a->x, a->ldx) && al16(a->dy, a->lddy) && al16(a->dx, a->lddx) &&
                   al16(a->dx_add, a->ldadd) && al16(a->dx_add2, a->ldadd2);
+  if (v4 && ln_fast(a) && al16(a->gamma, 0)) {      // LayerNorm over tokens: row kernel for dx, chunked column sums for dgamma / dbeta
+    ln_bwd_dx_kernel<<<(unsigned)((a->N + 7) / 8), 256, 0, st>>>(*a);
+    if ((rc = dp_check_launch())) return rc;
+    if (a->dgamma || a->dbeta) {
+      const int chunks = (a->N + LN_ROWS - 1) / LN_ROWS;       // partials [chunks][2][C] fit the GroupNorm workspace (N * 2 * C floats and more)
+      ln_bwd_param_partial_kernel<<<dim3((a->C / 4 + 31) / 32, chunks), 256, 0, st>>>(*a, (float*)a->workspace);
+      if ((rc = dp_check_launch())) return rc;
+      ln_bwd_param_final_kernel<<<(a->C + 127) / 128, 128, 0, st>>>(*a, (const float*)a->workspace, chunks);
+      rc = dp_check_launch();
+    }
+    return rc;
+  }
   Map mp = v4 ? make_map4(a->HW, a->C) : make_map(a->HW, a->C);
   char* ws = (char*)a->workspace;
   float* part = (float*)ws;

@@ -227,6 +227,51 @@ def test_groupnorm_fwd_bwd(lib, N, H, W, Cc, G, silu, ldx):
     assert rel_err(dg.cpu() - 1, gamma.grad) < 2e-5 and rel_err(db.cpu() - 1, beta.grad) < 2e-5
 
 
+@pytest.mark.parametrize("rows,Cc", [(203, 320), (64, 640), (37, 1280), (130, 96), (9, 1002)])
+def test_layernorm_rows_fwd_bwd(lib, rows, Cc):
+    """nn.LayerNorm over the channels of every token (ldm attention.py:204-206) = dp_groupnorm with one group over one-pixel images.
+    Up to 1280 channels (a multiple of 4) a warp-per-row kernel takes it (1002: the chunked GroupNorm kernels); vs torch fp64, incl. both gradient addends
+    and the accumulating dgamma / dbeta."""
+    L = L_()
+    g = torch.Generator().manual_seed(rows + Cc)
+    x = (torch.randn(rows, Cc, generator=g, dtype=torch.float64) * 1.7 + 0.4).requires_grad_(True)
+    gamma = (torch.randn(Cc, generator=g, dtype=torch.float64) * 0.5 + 1).requires_grad_(True)
+    beta = torch.randn(Cc, generator=g, dtype=torch.float64).requires_grad_(True)
+    y = F.layer_norm(x, (Cc,), gamma, beta, 1e-5)
+    gy = torch.randn(rows, Cc, generator=g, dtype=torch.float64)
+    y.backward(gy)
+    ld = Cc + 4
+    xb = torch.randn(rows, ld, generator=g).cuda()
+    xb[:, 4:] = x.detach().float().cuda()
+    yd = torch.empty(rows, Cc, device="cuda")
+    stats = torch.empty(2 * rows, device="cuda")
+    ws = torch.empty(lib.dp_groupnorm_workspace_bytes(rows, 1, Cc, 1) // 4 + 64, device="cuda")
+    gm, bt = gamma.detach().float().cuda(), beta.detach().float().cuda()
+    slots = torch.zeros(2, dtype=torch.int32, device="cuda")
+    a = L.GnArgs()
+    a.N, a.HW, a.C, a.G, a.eps, a.silu = rows, 1, Cc, 1, 1e-5, 0
+    a.x, a.ldx, a.y, a.ldy = xb.data_ptr() + 16, ld, yd.data_ptr(), Cc
+    a.gamma, a.beta, a.mean, a.rstd, a.workspace = gm.data_ptr(), bt.data_ptr(), stats.data_ptr(), stats.data_ptr() + 4 * rows, ws.data_ptr()
+    a.amax_y = slots.data_ptr()
+    n0 = lib.dp_launch_count()
+    assert lib.dp_groupnorm_fwd(C.byref(a), S()) == 0
+    assert lib.dp_launch_count() - n0 == (1 if Cc % 4 == 0 else 3)
+    assert rel_err(yd.cpu().double(), y.detach()) < 2e-6
+    assert slots.view(torch.float32)[0].item() == float(yd.abs().max())
+    gyd, add2 = gy.float().cuda(), torch.randn(rows, Cc, generator=g).cuda()
+    add = torch.randn(rows, Cc, generator=g).cuda()
+    dx = add.clone()
+    dg, db = torch.ones(Cc, device="cuda"), torch.ones(Cc, device="cuda")
+    a.amax_y, a.amax_dx = None, slots.data_ptr() + 4
+    a.dy, a.lddy, a.dx, a.lddx = gyd.data_ptr(), Cc, dx.data_ptr(), Cc
+    a.dx_add, a.ldadd, a.dx_add2, a.ldadd2 = dx.data_ptr(), Cc, add2.data_ptr(), Cc
+    a.dgamma, a.dbeta = dg.data_ptr(), db.data_ptr()
+    assert lib.dp_groupnorm_bwd(C.byref(a), S()) == 0
+    assert rel_err((dx - add - add2).cpu().double(), x.grad) < 2e-5
+    assert rel_err(dg.cpu().double() - 1, gamma.grad) < 2e-5 and rel_err(db.cpu().double() - 1, beta.grad) < 2e-5
+    assert slots.view(torch.float32)[1].item() == float(dx.abs().max())
+
+
 def test_groupnorm_dropout_mask_consistent(lib):
     """Dropout folded behind SiLU: backward regenerates the forward mask; keep-rate ~ 1-p; mean preserved."""
     L = L_()
