@@ -41,7 +41,7 @@ class GnArgs(C.Structure):
                 ("rstd", vp), ("dy", vp), ("lddy", i64), ("dx", vp), ("lddx", i64), ("dx_add", vp), ("ldadd", i64),
                 ("dx_add2", vp), ("ldadd2", i64), ("dgamma", vp), ("dbeta", vp), ("workspace", vp),
                 ("dropout_p", f32), ("dropout_seed", u64), ("dropout_seed_dev", vp), ("y_bf16", vp), ("ldyb", i64),
-                ("amax_y", vp), ("amax_dx", vp)]
+                ("amax_y", vp), ("amax_dx", vp), ("fin", vp)]
 
 
 class ConvBf16Args(C.Structure):
@@ -96,6 +96,7 @@ _SIGS = {
     "dp_groupnorm_workspace_bytes": (C.c_size_t, [i32, i32, i32, i32]),
     "dp_groupnorm_fwd": (C.c_int, [C.POINTER(GnArgs), vp]),
     "dp_groupnorm_bwd": (C.c_int, [C.POINTER(GnArgs), vp]),
+    "dp_groupnorm_bwd_param": (C.c_int, [C.POINTER(GnArgs), vp]),
     "dp_silu_fwd": (C.c_int, [vp, vp, i64, vp]),
     "dp_silu_bwd": (C.c_int, [vp, vp, vp, i64, i32, vp]),
     "dp_geglu_fwd": (C.c_int, [vp, i64, vp, i64, i64, i32, vp]),
@@ -110,6 +111,7 @@ _SIGS = {
     "dp_upsample2x_bwd": (C.c_int, [vp, i64, vp, i64, i32, i32, i32, i32, i32, vp]),
     "dp_colsum": (C.c_int, [vp, i64, i64, i32, i64, vp, i64, i32, vp]),
     "dp_add_views": (C.c_int, [vp, i64, vp, i64, vp, i64, i64, i32, vp]),
+    "dp_copy_rows": (C.c_int, [vp, i64, vp, i64, i64, i32, vp]),
     "dp_taylor_reduce": (C.c_int, [C.POINTER(TaylorArgs), vp]),
     "dp_sumsq_partials": (i64, [i64]),
     "dp_sumsq": (C.c_int, [vp, i64, vp, vp, vp]),

@@ -64,11 +64,11 @@ __global__ void __launch_bounds__(NT) gn_stats_kernel(const dp_gn_args a, const 
   }
 }
 
-__global__ void gn_finalize_kernel(const dp_gn_args a, const Map mp, const double* __restrict__ ws) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;  // (n, g)
-  if (i >= a.N * a.G) return;
-  int n = i / a.G, g = i - n * a.G;
+// mean / rstd of (n, g) from the stats partials: fixed-order fp64 sums over the chunks
+__device__ __forceinline__ void gn_finalize_one(const dp_gn_args& a, const Map& mp, const double* __restrict__ ws, int n, int g,
+                                                float& mean_f, float& rstd_f) {
   double ts = 0, tq = 0;
+#pragma unroll 4
   for (int ch = 0; ch < mp.nchunks; ++ch) {
     const double* o = ws + (((long long)n * mp.nchunks + ch) * a.G + g) * 2;
     ts += o[0]; tq += o[1];
@@ -76,22 +76,49 @@ __global__ void gn_finalize_kernel(const dp_gn_args a, const Map mp, const doubl
   double m = (double)a.HW * (a.C / a.G);
   double mean = ts / m, var = tq / m - mean * mean;
   if (var < 0) var = 0;
-  a.mean[i] = (float)mean;
-  a.rstd[i] = (float)(1.0 / sqrt(var + (double)a.eps));
+  mean_f = (float)mean;
+  rstd_f = (float)(1.0 / sqrt(var + (double)a.eps));
 }
 
-__global__ void __launch_bounds__(NT) gn_apply_kernel(const dp_gn_args a, const Map mp) {
+__global__ void gn_finalize_kernel(const dp_gn_args a, const Map mp, const double* __restrict__ ws) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;  // (n, g)
+  if (i >= a.N * a.G) return;
+  int n = i / a.G, g = i - n * a.G;
+  gn_finalize_one(a, mp, ws, n, g, a.mean[i], a.rstd[i]);
+}
+
+// Folded finalize (images of at most GN_FOLD_FWD chunks): there is no finalize launch; every block of the apply pass re-derives the
+// statistics of its image from the partials (G x nchunks fp64 pairs out of L2: the same sums in the same order, so every block gets
+// the same bits) into shared memory, and the chunk-0 block stores them for the backward.  One tiny dependent launch less per layer on
+// a chain that is launch-latency bound (51 GroupNorms per C1 pass).
+constexpr int GN_FOLD_FWD = 32;
+__device__ __forceinline__ void gn_fold_stats(const dp_gn_args& a, const Map& mp, const double* __restrict__ ws, int n, bool store,
+                                              float* smean, float* srstd) {
+  for (int g = threadIdx.x; g < a.G; g += NT) {
+    float mu, rs;
+    gn_finalize_one(a, mp, ws, n, g, mu, rs);
+    smean[g] = mu; srstd[g] = rs;
+    if (store) { a.mean[n * a.G + g] = mu; a.rstd[n * a.G + g] = rs; }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(NT) gn_apply_kernel(const dp_gn_args a, const Map mp, const double* __restrict__ fold_ws) {
+  extern __shared__ float shst[];   // folded finalize: [2][G]
   const int n = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
   const int ct = tid % mp.CT, pl = tid / mp.CT;
   const int p0 = chunk * mp.PPC, p1 = min(a.HW, p0 + mp.PPC);
   const int cpg = a.C / a.G;
+  const float* gmean = a.mean + n * a.G;
+  const float* grstd = a.rstd + n * a.G;
+  if (fold_ws) { gn_fold_stats(a, mp, fold_ws, n, chunk == 0, shst, shst + a.G); gmean = shst; grstd = shst + a.G; }
   float sc[MAXCPT], shf[MAXCPT];
 #pragma unroll
   for (int u = 0; u < MAXCPT; ++u) {
     int c = ct + u * NT;
     if (c < a.C) {
       int g = c / cpg;
-      float mu = a.mean[n * a.G + g], rs = a.rstd[n * a.G + g];
+      float mu = gmean[g], rs = grstd[g];
       float ga = __ldg(a.gamma + c), be = __ldg(a.beta + c);
       sc[u] = rs * ga; shf[u] = be - mu * rs * ga;
     } else { sc[u] = 0.f; shf[u] = 0.f; }
@@ -169,18 +196,22 @@ __global__ void __launch_bounds__(NT) gn_bwd_partial_kernel(const dp_gn_args a, 
   }
 }
 
-__global__ void __launch_bounds__(NT) gn_bwd_finalize_kernel(const dp_gn_args a, const Map mp, const float* __restrict__ part,
-                                                             float* __restrict__ fin, float* __restrict__ coef) {
-  extern __shared__ float shc[];  // [2][C] gamma-weighted sums
-  const int n = blockIdx.x, tid = threadIdx.x;
+// Per image: channel sums over the chunks (fixed order, fp64) -> fin[n][2][C] for the dgamma / dbeta kernel (written when `store`),
+// then the two gamma-weighted group means -> coef[g][2].  shc: [2][C] floats of shared memory; coef may be shared or global.
+__device__ __forceinline__ void gn_bwd_coef(const dp_gn_args& a, const Map& mp, const float* __restrict__ part, float* __restrict__ fin,
+                                            int n, bool store, float* shc, float* coef) {
+  const int tid = threadIdx.x;
   for (int c = tid; c < a.C; c += NT) {
     double t1 = 0, t2 = 0;
+#pragma unroll 4
     for (int ch = 0; ch < mp.nchunks; ++ch) {
       const float* o = part + ((long long)n * mp.nchunks + ch) * 2 * a.C;
       t1 += o[c]; t2 += o[a.C + c];
     }
-    fin[((long long)n * 2) * a.C + c] = (float)t1;
-    fin[((long long)n * 2 + 1) * a.C + c] = (float)t2;
+    if (store) {
+      fin[((long long)n * 2) * a.C + c] = (float)t1;
+      fin[((long long)n * 2 + 1) * a.C + c] = (float)t2;
+    }
     float ga = __ldg(a.gamma + c);
     shc[c] = (float)t1 * ga; shc[a.C + c] = (float)t2 * ga;
   }
@@ -190,10 +221,19 @@ __global__ void __launch_bounds__(NT) gn_bwd_finalize_kernel(const dp_gn_args a,
   for (int g = tid; g < a.G; g += NT) {
     double u1 = 0, u2 = 0;
     for (int c = g * cpg; c < (g + 1) * cpg; ++c) { u1 += shc[c]; u2 += shc[a.C + c]; }
-    coef[((long long)n * a.G + g) * 2] = (float)(u1 * inv_m);
-    coef[((long long)n * a.G + g) * 2 + 1] = (float)(u2 * inv_m);
+    coef[g * 2] = (float)(u1 * inv_m);
+    coef[g * 2 + 1] = (float)(u2 * inv_m);
   }
 }
+
+__global__ void __launch_bounds__(NT) gn_bwd_finalize_kernel(const dp_gn_args a, const Map mp, const float* __restrict__ part,
+                                                             float* __restrict__ fin, float* __restrict__ coef) {
+  extern __shared__ float shc[];  // [2][C] gamma-weighted sums
+  gn_bwd_coef(a, mp, part, fin, blockIdx.x, true, shc, coef + (long long)blockIdx.x * a.G * 2);
+}
+// Folded form (images of at most GN_FOLD_BWD chunks): no finalize launch; every block of the apply pass derives the coefficients of
+// its image itself (2 C nchunks floats out of L2, the same sums in the same order), the chunk-0 block also stores fin.
+constexpr int GN_FOLD_BWD = 8;
 
 __global__ void __launch_bounds__(1024) gn_bwd_param_kernel(const dp_gn_args a, const float* __restrict__ fin) {
   // block = 32 channels x 32 image lanes; fixed-order tree over the lanes (deterministic), coalesced 128-byte rows.  The grid is
@@ -213,18 +253,26 @@ __global__ void __launch_bounds__(1024) gn_bwd_param_kernel(const dp_gn_args a, 
   }
 }
 
-__global__ void __launch_bounds__(NT) gn_bwd_apply_kernel(const dp_gn_args a, const Map mp, const float* __restrict__ coef) {
+__global__ void __launch_bounds__(NT) gn_bwd_apply_kernel(const dp_gn_args a, const Map mp, const float* __restrict__ coef_g,
+                                                          const float* __restrict__ fold_part, float* __restrict__ fin) {
+  extern __shared__ float shfold[];   // folded finalize: [2][C] weighted sums + [G][2] coefficients
   const int n = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
   const int ct = tid % mp.CT, pl = tid / mp.CT;
   const int p0 = chunk * mp.PPC, p1 = min(a.HW, p0 + mp.PPC);
   const int cpg = a.C / a.G;
+  const float* coef = coef_g + (long long)n * a.G * 2;
+  if (fold_part) {
+    gn_bwd_coef(a, mp, fold_part, fin, n, chunk == 0, shfold, shfold + 2 * a.C);
+    __syncthreads();
+    coef = shfold + 2 * a.C;
+  }
   float mu[MAXCPT], rs[MAXCPT], ga[MAXCPT], be[MAXCPT], c1[MAXCPT], c2[MAXCPT];
 #pragma unroll
   for (int u = 0; u < MAXCPT; ++u) {
     int c = ct + u * NT;
     if (c < a.C) {
       int g = c / cpg; mu[u] = a.mean[n * a.G + g]; rs[u] = a.rstd[n * a.G + g]; ga[u] = __ldg(a.gamma + c); be[u] = __ldg(a.beta + c);
-      c1[u] = coef[((long long)n * a.G + g) * 2]; c2[u] = coef[((long long)n * a.G + g) * 2 + 1];
+      c1[u] = coef[g * 2]; c2[u] = coef[g * 2 + 1];
     } else { mu[u] = rs[u] = ga[u] = be[u] = c1[u] = c2[u] = 0.f; }
   }
   const float* xb = a.x + (long long)n * a.HW * a.ldx;
@@ -317,9 +365,13 @@ __global__ void __launch_bounds__(NT) gn_stats4_kernel(const dp_gn_args a, const
   }
 }
 
-__global__ void __launch_bounds__(NT) gn_apply4_kernel(const dp_gn_args a, const Map mp) {
+__global__ void __launch_bounds__(NT) gn_apply4_kernel(const dp_gn_args a, const Map mp, const double* __restrict__ fold_ws) {
+  extern __shared__ float shst[];   // folded finalize: [2][G]
   const int n = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
   const int ct = tid % mp.CT, pl = tid / mp.CT, c0 = ct * 4;
+  const float* gmean = a.mean + n * a.G;
+  const float* grstd = a.rstd + n * a.G;
+  if (fold_ws) { gn_fold_stats(a, mp, fold_ws, n, chunk == 0, shst, shst + a.G); gmean = shst; grstd = shst + a.G; }
   if (c0 >= a.C) return;
   const int p0 = chunk * mp.PPC, p1 = min(a.HW, p0 + mp.PPC);
   const int cpg = a.C / a.G;
@@ -327,7 +379,7 @@ __global__ void __launch_bounds__(NT) gn_apply4_kernel(const dp_gn_args a, const
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     int c = c0 + e, g = c / cpg;
-    float mu = a.mean[n * a.G + g], rs = a.rstd[n * a.G + g], ga = __ldg(a.gamma + c), be = __ldg(a.beta + c);
+    float mu = gmean[g], rs = grstd[g], ga = __ldg(a.gamma + c), be = __ldg(a.beta + c);
     sc[e] = rs * ga; shf[e] = be - mu * rs * ga;
   }
   const float* xb = a.x + (long long)n * a.HW * a.ldx + c0;
@@ -412,9 +464,17 @@ __global__ void __launch_bounds__(NT) gn_bwd_partial4_kernel(const dp_gn_args a,
   }
 }
 
-__global__ void __launch_bounds__(NT) gn_bwd_apply4_kernel(const dp_gn_args a, const Map mp, const float* __restrict__ coef) {
+__global__ void __launch_bounds__(NT) gn_bwd_apply4_kernel(const dp_gn_args a, const Map mp, const float* __restrict__ coef_g,
+                                                           const float* __restrict__ fold_part, float* __restrict__ fin) {
+  extern __shared__ float shfold[];   // folded finalize: [2][C] weighted sums + [G][2] coefficients
   const int n = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
   const int ct = tid % mp.CT, pl = tid / mp.CT, c0 = ct * 4;
+  const float* coef = coef_g + (long long)n * a.G * 2;
+  if (fold_part) {
+    gn_bwd_coef(a, mp, fold_part, fin, n, chunk == 0, shfold, shfold + 2 * a.C);
+    __syncthreads();
+    coef = shfold + 2 * a.C;
+  }
   if (c0 >= a.C) return;
   const int p0 = chunk * mp.PPC, p1 = min(a.HW, p0 + mp.PPC);
   const int cpg = a.C / a.G;
@@ -423,7 +483,7 @@ __global__ void __launch_bounds__(NT) gn_bwd_apply4_kernel(const dp_gn_args a, c
   for (int e = 0; e < 4; ++e) {
     int c = c0 + e, g = c / cpg;
     mu[e] = a.mean[n * a.G + g]; rs[e] = a.rstd[n * a.G + g]; ga[e] = __ldg(a.gamma + c); be[e] = __ldg(a.beta + c);
-    k1[e] = coef[((long long)n * a.G + g) * 2]; k2[e] = coef[((long long)n * a.G + g) * 2 + 1];
+    k1[e] = coef[g * 2]; k2[e] = coef[g * 2 + 1];
   }
   const float* xb = a.x + (long long)n * a.HW * a.ldx + c0;
   const float* db = a.dy + (long long)n * a.HW * a.lddy + c0;
@@ -630,10 +690,15 @@ extern "C" int dp_groupnorm_fwd(const dp_gn_args* a, dp_stream_t stream) {
     gn_stats_kernel<<<grid, NT, 2 * slots * sizeof(double), st>>>(*a, mp, (double*)a->workspace);
   }
   if ((rc = dp_check_launch())) return rc;
-  gn_finalize_kernel<<<(a->N * a->G + 127) / 128, 128, 0, st>>>(*a, mp, (const double*)a->workspace);
-  if ((rc = dp_check_launch())) return rc;
-  if (v4) gn_apply4_kernel<<<grid, NT, 0, st>>>(*a, mp);
-  else gn_apply_kernel<<<grid, NT, 0, st>>>(*a, mp);
+  const bool fold = mp.nchunks <= GN_FOLD_FWD;
+  if (!fold) {
+    gn_finalize_kernel<<<(a->N * a->G + 127) / 128, 128, 0, st>>>(*a, mp, (const double*)a->workspace);
+    if ((rc = dp_check_launch())) return rc;
+  }
+  const double* fws = fold ? (const double*)a->workspace : nullptr;
+  const size_t fsm = fold ? 2 * (size_t)a->G * sizeof(float) : 0;
+  if (v4) gn_apply4_kernel<<<grid, NT, fsm, st>>>(*a, mp, fws);
+  else gn_apply_kernel<<<grid, NT, fsm, st>>>(*a, mp, fws);
   return dp_check_launch();
 }
 
@@ -645,6 +710,7 @@ extern "C" int dp_groupnorm_bwd(const dp_gn_args* a, dp_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const bool v4 = (a->C % 4 == 0) && al16(a->x, a->ldx) && al16(a->dy, a->lddy) && al16(a->dx, a->lddx) &&
                   al16(a->dx_add, a->ldadd) && al16(a->dx_add2, a->ldadd2);
+  DP_REQUIRE(!(a->fin && ln_fast(a)), DP_ERR_UNSUPPORTED);     // the row kernels take dgamma / dbeta from x and dy, not from fin
   if (v4 && ln_fast(a) && al16(a->gamma, 0)) {      // LayerNorm over tokens: row kernel for dx, chunked column sums for dgamma / dbeta
     ln_bwd_dx_kernel<<<(unsigned)((a->N + 7) / 8), 256, 0, st>>>(*a);
     if ((rc = dp_check_launch())) return rc;
@@ -662,17 +728,33 @@ extern "C" int dp_groupnorm_bwd(const dp_gn_args* a, dp_stream_t stream) {
   float* part = (float*)ws;
   float* fin = (float*)(ws + align256((size_t)a->N * mp.nchunks * 2 * a->C * sizeof(float)));
   float* coef = (float*)((char*)fin + align256((size_t)a->N * 2 * a->C * sizeof(float)));
+  if (a->fin) fin = a->fin;      // caller-owned: outlives the shared workspace, dgamma / dbeta are taken later (dp_groupnorm_bwd_param)
   dim3 grid(mp.nchunks, a->N);
   if (v4) gn_bwd_partial4_kernel<<<grid, NT, 2 * mp.PL * mp.CT * 4 * sizeof(float), st>>>(*a, mp, part);
   else gn_bwd_partial_kernel<<<grid, NT, 2 * mp.PL * mp.CT * sizeof(float), st>>>(*a, mp, part);
   if ((rc = dp_check_launch())) return rc;
-  gn_bwd_finalize_kernel<<<a->N, NT, 2 * a->C * sizeof(float), st>>>(*a, mp, part, fin, coef);
-  if ((rc = dp_check_launch())) return rc;
-  if (a->dgamma || a->dbeta) {
-    gn_bwd_param_kernel<<<(a->C + 31) / 32, 1024, 0, st>>>(*a, fin);
+  const bool fold = mp.nchunks <= GN_FOLD_BWD;
+  if (!fold) {
+    gn_bwd_finalize_kernel<<<a->N, NT, 2 * a->C * sizeof(float), st>>>(*a, mp, part, fin, coef);
     if ((rc = dp_check_launch())) return rc;
   }
-  if (v4) gn_bwd_apply4_kernel<<<grid, NT, 0, st>>>(*a, mp, coef);
-  else gn_bwd_apply_kernel<<<grid, NT, 0, st>>>(*a, mp, coef);
+  const float* fpart = fold ? part : nullptr;
+  const size_t fsm = fold ? (2 * (size_t)a->C + 2 * (size_t)a->G) * sizeof(float) : 0;
+  if (v4) gn_bwd_apply4_kernel<<<grid, NT, fsm, st>>>(*a, mp, coef, fpart, fin);
+  else gn_bwd_apply_kernel<<<grid, NT, fsm, st>>>(*a, mp, coef, fpart, fin);
+  if ((rc = dp_check_launch())) return rc;
+  if (!a->fin && (a->dgamma || a->dbeta)) {      // after the apply pass: its chunk-0 blocks write fin in the folded form
+    gn_bwd_param_kernel<<<(a->C + 31) / 32, 1024, 0, st>>>(*a, fin);
+    rc = dp_check_launch();
+  }
+  return rc;
+}
+
+extern "C" int dp_groupnorm_bwd_param(const dp_gn_args* a, dp_stream_t stream) {
+  DP_REQUIRE(a && a->fin, DP_ERR_NULL);
+  DP_REQUIRE(a->N > 0 && a->C > 0, DP_ERR_SHAPE);
+  DP_REQUIRE(!ln_fast(a), DP_ERR_UNSUPPORTED);
+  if (!a->dgamma && !a->dbeta) return DP_OK;
+  gn_bwd_param_kernel<<<(a->C + 31) / 32, 1024, 0, (cudaStream_t)stream>>>(*a, a->fin);
   return dp_check_launch();
 }

@@ -213,6 +213,14 @@ __global__ void add_views_kernel(const float* __restrict__ a, long long lda, con
     y[r * ldy + c] = a[r * lda + c] + b[r * ldb + c];
   }
 }
+__global__ void copy_rows_kernel(const float* __restrict__ a, long long lda, float* __restrict__ y, long long ldy, long long rows, int cols) {
+  long long total = rows * cols;
+  for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < total; i += (long long)gridDim.x * NT) {
+    int c = (int)(i % cols);
+    long long r = i / cols;
+    y[r * ldy + c] = a[r * lda + c];
+  }
+}
 __global__ void softmax_fwd_kernel(const float* __restrict__ s, float* __restrict__ p, long long rows, int cols) {
   long long row = blockIdx.x * (long long)(NT / 32) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -367,6 +375,11 @@ extern "C" int dp_colsum(const float* x, int64_t ld, int64_t rows, int32_t cols,
 extern "C" int dp_add_views(const float* a, int64_t lda, const float* b, int64_t ldb, float* y, int64_t ldy, int64_t rows, int32_t cols, dp_stream_t st) {
   DP_REQUIRE(a && b && y, DP_ERR_NULL); DP_REQUIRE(rows > 0 && cols > 0, DP_ERR_SHAPE);
   add_views_kernel<<<nblocks(rows * cols, NT), NT, 0, (cudaStream_t)st>>>(a, lda, b, ldb, y, ldy, rows, cols);
+  return dp_check_launch();
+}
+extern "C" int dp_copy_rows(const float* a, int64_t lda, float* y, int64_t ldy, int64_t rows, int32_t cols, dp_stream_t st) {
+  DP_REQUIRE(a && y, DP_ERR_NULL); DP_REQUIRE(rows > 0 && cols > 0 && lda >= cols && ldy >= cols, DP_ERR_SHAPE);
+  copy_rows_kernel<<<nblocks(rows * cols, NT), NT, 0, (cudaStream_t)st>>>(a, lda, y, ldy, rows, cols);
   return dp_check_launch();
 }
 extern "C" int dp_softmax_fwd(const float* s, float* p, int64_t rows, int32_t cols, dp_stream_t st) {

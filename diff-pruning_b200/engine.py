@@ -614,6 +614,117 @@ class Plan:
                 f.side = 1
             steps[n_steps1].side = 2
 
+    FUSE_QKV = os.environ.get("DPB200_FUSE_QKV", "1") != "0"      # to_q / to_k / to_v of an attention block as one projection (conv_qkv); 0: A/B runs
+
+    def qkv_fusable(self, x: View, lins) -> bool:
+        ws = [l.weight for l in lins]
+        inner, Cin = ws[0].shape[0], ws[0].shape[1]
+        return bool(self.FUSE_QKV and self.tc and not self.bf16 and all(tuple(w.shape) == (inner, Cin) for w in ws)
+                    and inner % 4 == 0 and Cin % 4 == 0 and inner * Cin >= 256 and x.rows >= 128
+                    and len({l.bias is None for l in lins}) == 1)
+
+    def conv_qkv(self, x: View, lins) -> Tuple[View, View, View]:
+        """q, k, v = to_q(x), to_k(x), to_v(x) (attention_processor.py:432-441; ldm attention.py:172-176) as ONE 1x1 convolution over the
+        concatenated out-channels, q / k / v being channel ranges of one [N][H][W][3 inner] buffer: x is read once instead of three
+        times, and the backward needs one dgrad over K = 3 inner instead of three launches of which two read-modify-write dx.  The
+        weight gradients stay three launches (one per Parameter: their .grad slices are not adjacent in the arena), each over its
+        channel range of the shared dy buffer, on the side stream like every other wgrad.  The fused fp32 operand [3 inner][C] is
+        gathered from the three Parameters by the pack list (re-run whenever the weights change) and packed like any other weight;
+        one amax slot covers q, k and v (an upper bound is all a slot has to be)."""
+        lib = self.lib
+        ws = [l.weight for l in lins]
+        bs = [l.bias for l in lins]
+        inner, Cin = ws[0].shape[0], ws[0].shape[1]
+        K = 3 * inner
+        assert x.C == Cin
+        qkv = self.new(x.N, x.H, x.W, K)
+        parts = tuple(View(qkv.t, i * inner, inner) for i in range(3))
+        wf = torch.zeros((K, Cin), device=self.dev, dtype=torch.float32)
+        self._keep.append(wf)
+        for i, w in enumerate(ws):
+            self._rec(self.pack, lambda s, w=w, d=wf.data_ptr() + 4 * i * inner * Cin:
+                      lib.dp_copy_rows(w.data_ptr(), Cin, d, Cin, inner, Cin, s), what="pack qkv")
+        has_bias = bs[0] is not None
+        bf = None
+        if has_bias:
+            bf = torch.zeros(K, device=self.dev, dtype=torch.float32)
+            self._keep.append(bf)
+            for i, b in enumerate(bs):
+                self._rec(self.pack, lambda s, b=b, d=bf.data_ptr() + 4 * i * inner:
+                          lib.dp_copy_rows(b.data_ptr(), inner, d, inner, 1, inner, s), what="pack qkv")
+        wck, wkc, wtc = self._packed(wf)
+        assert wtc is not None
+        a = L.ConvArgs()
+        a.w_tc_hi, a.w_tc_lo, a.amax_w = wtc[0].data_ptr(), wtc[1].data_ptr(), wtc[4]
+        a.amax_x = self._x_slot(x)
+        a.N, a.H, a.W, a.C = x.N, x.H, x.W, Cin
+        a.P, a.Q, a.K = x.H, x.W, K
+        a.R, a.S, a.stride, a.pad_t, a.pad_l = 1, 1, 1, 0, 0
+        a.flags, a.splits = 0, 1
+        a.x, a.ldx, a.y, a.ldy = x.ptr, x.ld, qkv.ptr, qkv.ld
+        a.amax_out = self._out_slot(qkv)
+        a.w = wck.data_ptr()
+        a.bias = bf.data_ptr() if has_bias else None
+        info = f"{Cin}->{K} 1x1 @{x.H}x{x.W}"
+        self.lin_macs += qkv.rows * K * Cin
+        self._splitk(a, 0)
+        self._rec(self.fwd, lib.dp_conv2d_fprop, a, "conv fprop", info)
+        if not self.need_grad:
+            return parts
+        it = self._bitem()
+        steps = it.steps
+        dout = self.gradof(qkv)
+        amax_dy = self._dy_slot(steps, qkv)
+        # weight (and bias) gradients: one launch per Parameter over its channel range of dy, side stream
+        pinfo = f"{Cin}->{inner} 1x1 @{x.H}x{x.W}"
+        tiles = ((inner + 127) // 128) * ((Cin + 127) // 128)
+        splits = _wgrad_splits(tiles, max(1, qkv.rows // 64))
+        side = SIDE_WGRAD
+        ws_name, bws_name = ("wgrad_ws_side", "bias_ws_side") if side else ("wgrad_ws", "bias_ws")
+        self.scratch(ws_name, splits * inner * Cin)
+        if has_bias:
+            self.scratch(bws_name, splits * inner)
+        for i, (w, b) in enumerate(zip(ws, bs)):
+            wa = _copy_args(a)
+            wa.K = inner
+            wa.y, wa.ldy = dout.ptr + 4 * i * inner, dout.ld
+            wa.amax_y, wa.amax_out = amax_dy, None
+            wa.flags, wa.splits = 0, splits
+            wa.rowadd, wa.residual, wa.bias, wa.workspace = None, None, None, None
+            self._late.append(lambda wa=wa, n=ws_name: setattr(wa, "workspace", self.sptr(n)))
+            if has_bias:
+                self._late.append(lambda wa=wa, n=bws_name: setattr(wa, "bias_ws", self.sptr(n)))
+            self._rec(steps, lib.dp_conv2d_wgrad, wa, "conv wgrad", pinfo)
+            steps[-1].side = 2 if side else 0
+            ra = L.WgradReduceArgs()
+            ra.K, ra.C, ra.R, ra.S, ra.splits = inner, Cin, 1, 1, splits
+            ra.dw = self.pgrad(w)
+            if self.fused_scores:
+                so, si = self._score_views(w, inner, Cin)
+                ra.w, ra.score_out, ra.score_in = w.data_ptr(), so.data_ptr(), si.data_ptr()
+            self._late.append(lambda ra=ra, n=ws_name: setattr(ra, "workspace", self.sptr(n)))
+            if has_bias:
+                ra.db = self.pgrad(b)
+                self._late.append(lambda ra=ra, n=bws_name: setattr(ra, "bias_ws", self.sptr(n)))
+            self._rec(steps, lib.dp_conv2d_wgrad_reduce, ra, "conv wgrad reduce")
+            steps[-1].side = 1 if side else 0
+        # one dgrad over all 3 inner channels of dy
+        da = _copy_args(a)
+        da.y, da.ldy = dout.ptr, dout.ld
+        da.w = wkc.data_ptr()
+        da.w_tc_hi, da.w_tc_lo, da.amax_y = wtc[2].data_ptr(), wtc[3].data_ptr(), amax_dy
+        da.flags = 0
+        da.amax_out = None
+        da.rowadd, da.residual, da.bias = None, None, None
+        gx = self.gradof(x)
+        da.x, da.ldx = gx.ptr, gx.ld
+        it.writes.append((x, lambda init, da=da: setattr(da, "flags", 1 if init else 0),
+                          lambda slot, da=da: setattr(da, "amax_out", slot)))
+        da.workspace = None
+        self._splitk(da, 1)
+        self._rec(steps, lib.dp_conv2d_dgrad, da, "conv dgrad", info)
+        return parts
+
     def _splitk(self, a, op: int, name: str = "splitk_ws"):
         """Small-M launches (4x4 .. 16x16 levels) split their K loop over the idle SMs: one shared scratch, bound late."""
         need = int(self.lib.dp_conv_splitk_workspace_floats(C.byref(a), op)) if SPLITK else 0
@@ -760,7 +871,15 @@ class Plan:
             b.dgamma, b.dbeta = self.pgrad(norm.weight) + 4 * c0, self.pgrad(norm.bias) + 4 * c0
             self._late.append(lambda b=b, c0=c0: (setattr(b, "dy", dy_get() + 4 * c0), setattr(b, "workspace", self.sptr("gn_ws"))))
             parts.append((b, c0))
+            side_param = b.HW > 1       # not the one-pixel LayerNorm shapes: their row kernels take dgamma / dbeta from x and dy
+            if side_param:              # per-image channel sums in a buffer of this layer's own: dgamma / dbeta leave the dx chain
+                fin = torch.empty(2 * b.N * b.C, device=self.dev, dtype=torch.float32)
+                self._keep.append(fin)
+                b.fin = fin.data_ptr()
             self._rec(it.steps, lib.dp_groupnorm_bwd, b, "gn bwd")
+            if side_param:
+                self._rec(it.steps, lib.dp_groupnorm_bwd_param, b, "gn bwd param")
+                it.steps[-1].side = 2 if SIDE_WGRAD else 0     # only feeds Parameter.grad, like the weight gradients
 
         def resolve(init, parts=parts, gx=gx):
             if init:
@@ -804,15 +923,22 @@ class Plan:
         N, H, W = x.N, x.H, x.W
         inner = m.to_q.out_features
         xn = self.new(N, H, W, x.C)
-        q, k, v, o = (self.new(N, H, W, inner) for _ in range(4))
+        lins = (m.to_q, m.to_k, m.to_v)
+        fuse = self.qkv_fusable(xn, lins)
+        o = self.new(N, H, W, inner)
+        if not fuse:
+            q, k, v = (self.new(N, H, W, inner) for _ in range(3))
         g = self.gn(x, m.group_norm, xn, silu=False,
-                    bf16_only=all(self.conv_bf16_ok(xn, q, l.weight, 1, 0) for l in (m.to_q, m.to_k, m.to_v)))
+                    bf16_only=(not fuse) and all(self.conv_bf16_ok(xn, q, l.weight, 1, 0) for l in lins))
         if self.need_grad:
             self.gn_bwd(g, x, m.group_norm, lambda xn=xn: self.gradof(xn).ptr, x.C,
                         add2=self.gradof(out) if m.residual_connection else None)
-        self.conv(xn, m.to_q.weight, m.to_q.bias, q, pad=0)
-        self.conv(xn, m.to_k.weight, m.to_k.bias, k, pad=0)
-        self.conv(xn, m.to_v.weight, m.to_v.bias, v, pad=0)
+        if fuse:
+            q, k, v = self.conv_qkv(xn, lins)
+        else:
+            self.conv(xn, m.to_q.weight, m.to_q.bias, q, pad=0)
+            self.conv(xn, m.to_k.weight, m.to_k.bias, k, pad=0)
+            self.conv(xn, m.to_v.weight, m.to_v.bias, v, pad=0)
         self._attn_core(q, k, v, o, float(m.scale))
         self.conv(o, m.to_out[0].weight, m.to_out[0].bias, out, pad=0, residual=x if m.residual_connection else None)
 
@@ -1147,10 +1273,15 @@ class Plan:
         x2 = self.new(N, H, W, d)
         h1 = self.new(N, H, W, d)
         self.layernorm(x, blk.norm1, h1, add2=self.gradof(x2))
-        q, k, v, o = (self.new(N, H, W, inner) for _ in range(4))
-        self.conv(h1, a1.to_q.weight, None, q, pad=0)
-        self.conv(h1, a1.to_k.weight, None, k, pad=0)
-        self.conv(h1, a1.to_v.weight, None, v, pad=0)
+        o = self.new(N, H, W, inner)
+        lins = (a1.to_q, a1.to_k, a1.to_v)
+        if all(l.bias is None for l in lins) and self.qkv_fusable(h1, lins):
+            q, k, v = self.conv_qkv(h1, lins)
+        else:
+            q, k, v = (self.new(N, H, W, inner) for _ in range(3))
+            self.conv(h1, a1.to_q.weight, None, q, pad=0)
+            self.conv(h1, a1.to_k.weight, None, k, pad=0)
+            self.conv(h1, a1.to_v.weight, None, v, pad=0)
         self._attn_core(q, k, v, o, float(a1.scale))
         self.conv(o, a1.to_out[0].weight, a1.to_out[0].bias, x2, pad=0, residual=x, rowadd=octx, seg_out="seg_ctx")
         # GEGLU feed-forward

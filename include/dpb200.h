@@ -235,10 +235,18 @@ typedef struct dp_gn_args {
   /* optional amax slots (dp_amax semantics) of the tensors this call writes: forward y, backward dx — the tensor-core convolution
    * that consumes them then needs no separate dp_amax pass */
   uint32_t* amax_y; uint32_t* amax_dx;
+  /* optional, backward: caller-owned [N][2][C] floats that outlive the shared workspace.  When set, dp_groupnorm_bwd leaves the
+   * per-image channel sums there and does NOT touch dgamma / dbeta; dp_groupnorm_bwd_param adds them later, on any stream ordered
+   * after the dp_groupnorm_bwd call (parameter gradients feed nothing inside the pass: they need not sit on the dx chain).
+   * Not for the one-pixel LayerNorm shapes (DP_ERR_UNSUPPORTED). */
+  float* fin;
 } dp_gn_args;
 size_t dp_groupnorm_workspace_bytes(int32_t N, int32_t HW, int32_t C, int32_t G);
 int dp_groupnorm_fwd(const dp_gn_args* a, dp_stream_t stream);
 int dp_groupnorm_bwd(const dp_gn_args* a, dp_stream_t stream);
+/* dgamma[c] += sum_n fin[n][1][c], dbeta[c] += sum_n fin[n][0][c] (fixed order) — the tail of native_group_norm_backward for a
+ * dp_groupnorm_bwd call that was given `fin` */
+int dp_groupnorm_bwd_param(const dp_gn_args* a, dp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Small fused pointwise / reduction ops of the path
@@ -289,6 +297,9 @@ int dp_colsum(const float* x, int64_t ld, int64_t rows, int32_t cols, int64_t se
 /* y = a + b over an NHWC view (used where an add cannot be folded into a GEMM epilogue) */
 int dp_add_views(const float* a, int64_t lda, const float* b, int64_t ldb, float* y, int64_t ldy, int64_t rows,
                  int32_t cols, dp_stream_t stream);
+/* y = a over a [rows][cols] view (device to device, on the stream): gathers the to_q / to_k / to_v weights of an attention block
+ * (attention_processor.py:432-441) into the one [3 inner][C] operand their fused projection reads, whenever the weights change */
+int dp_copy_rows(const float* a, int64_t lda, float* y, int64_t ldy, int64_t rows, int32_t cols, dp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Taylor importance reductions — torch_pruning TaylorImportance.__call__

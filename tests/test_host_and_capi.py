@@ -38,7 +38,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(L.GemmArgs) == 16 + 11 * 8 + 8
     assert ctypes.sizeof(L.WgradReduceArgs) == 24 + 7 * 8
     assert ctypes.sizeof(L.TaylorArgs) == 16 + 8 * 8
-    assert ctypes.sizeof(L.GnArgs) == 24 + 19 * 8 + 8 + 8 + 8 + 16 + 16
+    assert ctypes.sizeof(L.GnArgs) == 24 + 19 * 8 + 8 + 8 + 8 + 16 + 16 + 8
     assert ctypes.sizeof(L.ConvBf16Args) == 56 + 13 * 8
     assert ctypes.sizeof(L.AdamArgs) == 8 + 6 * 8 + 6 * 8 + 4 + 4 + 8
 

@@ -186,7 +186,9 @@ def test_softmax_fwd_bwd(lib, rows, cols):
 GN_CASES = [(2, 8, 8, 32, 8, 1, 0), (3, 4, 4, 96, 32, 1, 16), (2, 16, 16, 128, 32, 0, 0), (2, 4, 4, 512, 32, 1, 0),
             (2, 2, 2, 768, 32, 1, 0), (1, 32, 32, 192, 32, 1, 64), (4, 3, 5, 24, 3, 0, 0),
             (2, 8, 8, 30, 3, 1, 0), (2, 8, 8, 64, 8, 1, 2), (2, 4, 4, 358, 2, 1, 0),   # scalar path: C%4!=0 / misaligned view
-            (1, 64, 64, 128, 32, 1, 0), (3, 32, 32, 96, 32, 1, 0), (2, 16, 16, 384, 32, 1, 8)]   # chunked float4 path (HW too large for a slab) / slab path: pruned 96, concat 384
+            (1, 64, 64, 128, 32, 1, 0), (3, 32, 32, 96, 32, 1, 0), (2, 16, 16, 384, 32, 1, 8),   # chunked float4 path: 32 / 7 / 7 chunks per image
+            (1, 128, 64, 128, 32, 1, 0),                                   # 64 chunks: separate finalize launches in both directions
+            (2, 32, 32, 90, 30, 1, 0), (2, 16, 16, 179, 1, 1, 0)]          # scalar path at pruned widths: 12 chunks (forward folded only) / 6 (both folded)
 
 
 @pytest.mark.parametrize("N,H,W,Cc,G,silu,ldx", GN_CASES)
@@ -225,6 +227,17 @@ def test_groupnorm_fwd_bwd(lib, N, H, W, Cc, G, silu, ldx):
     assert lib.dp_groupnorm_bwd(C.byref(a), S()) == 0
     assert rel_err(nchw(dx - add - add2), x.grad) < 2e-5
     assert rel_err(dg.cpu() - 1, gamma.grad) < 2e-5 and rel_err(db.cpu() - 1, beta.grad) < 2e-5
+    # the same call with a caller-owned `fin`: dx identical, dgamma / dbeta untouched until dp_groupnorm_bwd_param (the engine runs that
+    # on its side stream), then bit-identical to the one-call form
+    dx2 = add.clone()
+    dg2, db2 = torch.ones(Cc, device="cuda"), torch.ones(Cc, device="cuda")
+    fin = torch.full((2 * N * Cc,), float("nan"), device="cuda")
+    a.dx, a.dx_add, a.dgamma, a.dbeta, a.fin = dx2.data_ptr(), dx2.data_ptr(), dg2.data_ptr(), db2.data_ptr(), fin.data_ptr()
+    assert lib.dp_groupnorm_bwd(C.byref(a), S()) == 0
+    assert torch.equal(dx2, dx) and bool((dg2 == 1).all()) and bool((db2 == 1).all())
+    ws.fill_(float("nan"))          # the shared workspace may be reused before the parameter gradients are taken
+    assert lib.dp_groupnorm_bwd_param(C.byref(a), S()) == 0
+    assert torch.equal(dg2, dg) and torch.equal(db2, db)
 
 
 @pytest.mark.parametrize("rows,Cc", [(203, 320), (64, 640), (37, 1280), (130, 96), (9, 1002)])
