@@ -620,8 +620,7 @@ class Plan:
         ws = [l.weight for l in lins]
         inner, Cin = ws[0].shape[0], ws[0].shape[1]
         return bool(self.FUSE_QKV and self.tc and not self.bf16 and all(tuple(w.shape) == (inner, Cin) for w in ws)
-                    and inner % 4 == 0 and Cin % 4 == 0 and inner * Cin >= 256 and x.rows >= 128
-                    and len({l.bias is None for l in lins}) == 1)
+                    and inner * Cin >= 256 and x.rows >= 128 and len({l.bias is None for l in lins}) == 1)
 
     def conv_qkv(self, x: View, lins) -> Tuple[View, View, View]:
         """q, k, v = to_q(x), to_k(x), to_v(x) (attention_processor.py:432-441; ldm attention.py:172-176) as ONE 1x1 convolution over the
@@ -630,19 +629,22 @@ class Plan:
         weight gradients stay three launches (one per Parameter: their .grad slices are not adjacent in the arena), each over its
         channel range of the shared dy buffer, on the side stream like every other wgrad.  The fused fp32 operand [3 inner][C] is
         gathered from the three Parameters by the pack list (re-run whenever the weights change) and packed like any other weight;
-        one amax slot covers q, k and v (an upper bound is all a slot has to be)."""
+        one amax slot covers q, k and v (an upper bound is all a slot has to be).  Pruned widths (inner = 179 ...): every part starts on a
+        multiple of 4 channels (16-byte aligned views for TMA); the pad channels have zero weight rows and zero bias, so the forward
+        writes zeros there, and their gradient columns are zeroed once here and never written again."""
         lib = self.lib
         ws = [l.weight for l in lins]
         bs = [l.bias for l in lins]
         inner, Cin = ws[0].shape[0], ws[0].shape[1]
-        K = 3 * inner
+        ip = (inner + 3) // 4 * 4          # channel pitch of a part inside the fused buffer
+        K = 3 * ip
         assert x.C == Cin
         qkv = self.new(x.N, x.H, x.W, K)
-        parts = tuple(View(qkv.t, i * inner, inner) for i in range(3))
+        parts = tuple(View(qkv.t, i * ip, inner) for i in range(3))
         wf = torch.zeros((K, Cin), device=self.dev, dtype=torch.float32)
         self._keep.append(wf)
         for i, w in enumerate(ws):
-            self._rec(self.pack, lambda s, w=w, d=wf.data_ptr() + 4 * i * inner * Cin:
+            self._rec(self.pack, lambda s, w=w, d=wf.data_ptr() + 4 * i * ip * Cin:
                       lib.dp_copy_rows(w.data_ptr(), Cin, d, Cin, inner, Cin, s), what="pack qkv")
         has_bias = bs[0] is not None
         bf = None
@@ -650,7 +652,7 @@ class Plan:
             bf = torch.zeros(K, device=self.dev, dtype=torch.float32)
             self._keep.append(bf)
             for i, b in enumerate(bs):
-                self._rec(self.pack, lambda s, b=b, d=bf.data_ptr() + 4 * i * inner:
+                self._rec(self.pack, lambda s, b=b, d=bf.data_ptr() + 4 * i * ip:
                           lib.dp_copy_rows(b.data_ptr(), inner, d, inner, 1, inner, s), what="pack qkv")
         wck, wkc, wtc = self._packed(wf)
         assert wtc is not None
@@ -674,6 +676,8 @@ class Plan:
         it = self._bitem()
         steps = it.steps
         dout = self.gradof(qkv)
+        if ip != inner:
+            dout.t.zero_()                 # pad columns of dy: read by the fused dgrad (against zero weights), written by nobody
         amax_dy = self._dy_slot(steps, qkv)
         # weight (and bias) gradients: one launch per Parameter over its channel range of dy, side stream
         pinfo = f"{Cin}->{inner} 1x1 @{x.H}x{x.W}"
@@ -687,7 +691,7 @@ class Plan:
         for i, (w, b) in enumerate(zip(ws, bs)):
             wa = _copy_args(a)
             wa.K = inner
-            wa.y, wa.ldy = dout.ptr + 4 * i * inner, dout.ld
+            wa.y, wa.ldy = dout.ptr + 4 * i * ip, dout.ld
             wa.amax_y, wa.amax_out = amax_dy, None
             wa.flags, wa.splits = 0, splits
             wa.rowadd, wa.residual, wa.bias, wa.workspace = None, None, None, None

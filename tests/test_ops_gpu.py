@@ -268,7 +268,7 @@ def test_layernorm_rows_fwd_bwd(lib, rows, Cc):
     a.amax_y = slots.data_ptr()
     n0 = lib.dp_launch_count()
     assert lib.dp_groupnorm_fwd(C.byref(a), S()) == 0
-    assert lib.dp_launch_count() - n0 == (1 if Cc % 4 == 0 else 3)
+    assert lib.dp_launch_count() - n0 == (1 if Cc % 4 == 0 else 2)     # row kernel | chunked stats + apply (finalize folded in)
     assert rel_err(yd.cpu().double(), y.detach()) < 2e-6
     assert slots.view(torch.float32)[0].item() == float(yd.abs().max())
     gyd, add2 = gy.float().cuda(), torch.randn(rows, Cc, generator=g).cuda()
