@@ -64,6 +64,14 @@ __global__ void __launch_bounds__(NT) gn_stats_kernel(const dp_gn_args a, const 
   }
 }
 
+// mean / rstd of a group from its fp64 sum / sum of squares
+__device__ __forceinline__ void gn_stats_final(const dp_gn_args& a, double ts, double tq, float& mean_f, float& rstd_f) {
+  double m = (double)a.HW * (a.C / a.G);
+  double mean = ts / m, var = tq / m - mean * mean;
+  if (var < 0) var = 0;
+  mean_f = (float)mean;
+  rstd_f = (float)(1.0 / sqrt(var + (double)a.eps));
+}
 // mean / rstd of (n, g) from the stats partials: fixed-order fp64 sums over the chunks
 __device__ __forceinline__ void gn_finalize_one(const dp_gn_args& a, const Map& mp, const double* __restrict__ ws, int n, int g,
                                                 float& mean_f, float& rstd_f) {
@@ -73,18 +81,23 @@ __device__ __forceinline__ void gn_finalize_one(const dp_gn_args& a, const Map& 
     const double* o = ws + (((long long)n * mp.nchunks + ch) * a.G + g) * 2;
     ts += o[0]; tq += o[1];
   }
-  double m = (double)a.HW * (a.C / a.G);
-  double mean = ts / m, var = tq / m - mean * mean;
-  if (var < 0) var = 0;
-  mean_f = (float)mean;
-  rstd_f = (float)(1.0 / sqrt(var + (double)a.eps));
+  gn_stats_final(a, ts, tq, mean_f, rstd_f);
 }
 
-__global__ void gn_finalize_kernel(const dp_gn_args a, const Map mp, const double* __restrict__ ws) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;  // (n, g)
+// Images of many chunks (LSUN 256x256: 512-1024 per image): one WARP per (n, g) — lane l sums chunks l, l + 32, ... in order, then a fixed
+// butterfly.  (One thread per (n, g) walked all chunks serially: N * G = 128 threads in one block, ~100 us per 256x256 layer, more than
+// the stats and apply passes over the 134 MB tensor take together.)
+__global__ void __launch_bounds__(256) gn_finalize_kernel(const dp_gn_args a, const Map mp, const double* __restrict__ ws) {
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;  // (n, g), whole warps
   if (i >= a.N * a.G) return;
-  int n = i / a.G, g = i - n * a.G;
-  gn_finalize_one(a, mp, ws, n, g, a.mean[i], a.rstd[i]);
+  const int n = i / a.G, g = i - n * a.G;
+  double ts = 0, tq = 0;
+  for (int ch = lane; ch < mp.nchunks; ch += 32) {
+    const double* o = ws + (((long long)n * mp.nchunks + ch) * a.G + g) * 2;
+    ts += o[0]; tq += o[1];
+  }
+  ts = warp_sum_d(ts); tq = warp_sum_d(tq);
+  if (lane == 0) gn_stats_final(a, ts, tq, a.mean[i], a.rstd[i]);
 }
 
 // Folded finalize (images of at most GN_FOLD_FWD chunks): there is no finalize launch; every block of the apply pass re-derives the
@@ -196,16 +209,16 @@ __global__ void __launch_bounds__(NT) gn_bwd_partial_kernel(const dp_gn_args a, 
   }
 }
 
-// Per image: channel sums over the chunks (fixed order, fp64) -> fin[n][2][C] for the dgamma / dbeta kernel (written when `store`),
-// then the two gamma-weighted group means -> coef[g][2].  shc: [2][C] floats of shared memory; coef may be shared or global.
-__device__ __forceinline__ void gn_bwd_coef(const dp_gn_args& a, const Map& mp, const float* __restrict__ part, float* __restrict__ fin,
+// Per image: channel sums over the `nrows` partial rows (fixed order, fp64) -> fin[n][2][C] for the dgamma / dbeta kernel (written when
+// `store`), then the two gamma-weighted group means -> coef[g][2].  shc: [2][C] floats of shared memory; coef: shared memory.
+__device__ __forceinline__ void gn_bwd_coef(const dp_gn_args& a, int nrows, const float* part, float* fin,   // part == fin when nrows == 1
                                             int n, bool store, float* shc, float* coef) {
   const int tid = threadIdx.x;
   for (int c = tid; c < a.C; c += NT) {
     double t1 = 0, t2 = 0;
 #pragma unroll 4
-    for (int ch = 0; ch < mp.nchunks; ++ch) {
-      const float* o = part + ((long long)n * mp.nchunks + ch) * 2 * a.C;
+    for (int ch = 0; ch < nrows; ++ch) {
+      const float* o = part + ((long long)n * nrows + ch) * 2 * a.C;
       t1 += o[c]; t2 += o[a.C + c];
     }
     if (store) {
@@ -224,16 +237,33 @@ __device__ __forceinline__ void gn_bwd_coef(const dp_gn_args& a, const Map& mp, 
     coef[g * 2] = (float)(u1 * inv_m);
     coef[g * 2 + 1] = (float)(u2 * inv_m);
   }
+  __syncthreads();
 }
-
-__global__ void __launch_bounds__(NT) gn_bwd_finalize_kernel(const dp_gn_args a, const Map mp, const float* __restrict__ part,
-                                                             float* __restrict__ fin, float* __restrict__ coef) {
-  extern __shared__ float shc[];  // [2][C] gamma-weighted sums
-  gn_bwd_coef(a, mp, part, fin, blockIdx.x, true, shc, coef + (long long)blockIdx.x * a.G * 2);
-}
-// Folded form (images of at most GN_FOLD_BWD chunks): no finalize launch; every block of the apply pass derives the coefficients of
-// its image itself (2 C nchunks floats out of L2, the same sums in the same order), the chunk-0 block also stores fin.
+// There is no finalize launch in the backward: every block of the apply pass derives the coefficients of its image itself, from the
+// chunk partials when an image has at most GN_FOLD_BWD of them (2 C nchunks floats out of L2; the chunk-0 block also stores fin), else
+// from fin, which gn_bwd_reduce_kernel fills first: block = 32 channels x 32 chunk lanes, lane l sums chunks l, l + 32, ... in order, then
+// a fixed-order sum over the lanes (deterministic).  (The former per-image finalize block walked all chunks serially per channel: N = 4
+// blocks and ~100 us per 256x256 LSUN layer.)
 constexpr int GN_FOLD_BWD = 8;
+__global__ void __launch_bounds__(1024) gn_bwd_reduce_kernel(const dp_gn_args a, const Map mp, const float* __restrict__ part,
+                                                             float* __restrict__ fin) {
+  __shared__ double s1[32][33], s2[32][33];
+  const int cx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx, n = blockIdx.y;
+  double t1 = 0, t2 = 0;
+  if (c < a.C)
+    for (int ch = ly; ch < mp.nchunks; ch += 32) {
+      const float* o = part + ((long long)n * mp.nchunks + ch) * 2 * a.C;
+      t1 += o[c]; t2 += o[a.C + c];
+    }
+  s1[ly][cx] = t1; s2[ly][cx] = t2;
+  __syncthreads();
+  if (ly == 0 && c < a.C) {
+    for (int l = 1; l < 32; ++l) { t1 += s1[l][cx]; t2 += s2[l][cx]; }
+    fin[((long long)n * 2) * a.C + c] = (float)t1;
+    fin[((long long)n * 2 + 1) * a.C + c] = (float)t2;
+  }
+}
 
 __global__ void __launch_bounds__(1024) gn_bwd_param_kernel(const dp_gn_args a, const float* __restrict__ fin) {
   // block = 32 channels x 32 image lanes; fixed-order tree over the lanes (deterministic), coalesced 128-byte rows.  The grid is
@@ -253,19 +283,14 @@ __global__ void __launch_bounds__(1024) gn_bwd_param_kernel(const dp_gn_args a, 
   }
 }
 
-__global__ void __launch_bounds__(NT) gn_bwd_apply_kernel(const dp_gn_args a, const Map mp, const float* __restrict__ coef_g,
-                                                          const float* __restrict__ fold_part, float* __restrict__ fin) {
+__global__ void __launch_bounds__(NT) gn_bwd_apply_kernel(const dp_gn_args a, const Map mp, const float* part, int nrows, float* fin) {
   extern __shared__ float shfold[];   // folded finalize: [2][C] weighted sums + [G][2] coefficients
   const int n = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
   const int ct = tid % mp.CT, pl = tid / mp.CT;
   const int p0 = chunk * mp.PPC, p1 = min(a.HW, p0 + mp.PPC);
   const int cpg = a.C / a.G;
-  const float* coef = coef_g + (long long)n * a.G * 2;
-  if (fold_part) {
-    gn_bwd_coef(a, mp, fold_part, fin, n, chunk == 0, shfold, shfold + 2 * a.C);
-    __syncthreads();
-    coef = shfold + 2 * a.C;
-  }
+  const float* coef = shfold + 2 * a.C;
+  gn_bwd_coef(a, nrows, part, fin, n, chunk == 0 && part != fin, shfold, shfold + 2 * a.C);
   float mu[MAXCPT], rs[MAXCPT], ga[MAXCPT], be[MAXCPT], c1[MAXCPT], c2[MAXCPT];
 #pragma unroll
   for (int u = 0; u < MAXCPT; ++u) {
@@ -464,17 +489,12 @@ __global__ void __launch_bounds__(NT) gn_bwd_partial4_kernel(const dp_gn_args a,
   }
 }
 
-__global__ void __launch_bounds__(NT) gn_bwd_apply4_kernel(const dp_gn_args a, const Map mp, const float* __restrict__ coef_g,
-                                                           const float* __restrict__ fold_part, float* __restrict__ fin) {
+__global__ void __launch_bounds__(NT) gn_bwd_apply4_kernel(const dp_gn_args a, const Map mp, const float* part, int nrows, float* fin) {
   extern __shared__ float shfold[];   // folded finalize: [2][C] weighted sums + [G][2] coefficients
   const int n = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
   const int ct = tid % mp.CT, pl = tid / mp.CT, c0 = ct * 4;
-  const float* coef = coef_g + (long long)n * a.G * 2;
-  if (fold_part) {
-    gn_bwd_coef(a, mp, fold_part, fin, n, chunk == 0, shfold, shfold + 2 * a.C);
-    __syncthreads();
-    coef = shfold + 2 * a.C;
-  }
+  const float* coef = shfold + 2 * a.C;
+  gn_bwd_coef(a, nrows, part, fin, n, chunk == 0 && part != fin, shfold, shfold + 2 * a.C);
   if (c0 >= a.C) return;
   const int p0 = chunk * mp.PPC, p1 = min(a.HW, p0 + mp.PPC);
   const int cpg = a.C / a.G;
@@ -692,7 +712,7 @@ extern "C" int dp_groupnorm_fwd(const dp_gn_args* a, dp_stream_t stream) {
   if ((rc = dp_check_launch())) return rc;
   const bool fold = mp.nchunks <= GN_FOLD_FWD;
   if (!fold) {
-    gn_finalize_kernel<<<(a->N * a->G + 127) / 128, 128, 0, st>>>(*a, mp, (const double*)a->workspace);
+    gn_finalize_kernel<<<(a->N * a->G + 7) / 8, 256, 0, st>>>(*a, mp, (const double*)a->workspace);
     if ((rc = dp_check_launch())) return rc;
   }
   const double* fws = fold ? (const double*)a->workspace : nullptr;
@@ -727,7 +747,6 @@ extern "C" int dp_groupnorm_bwd(const dp_gn_args* a, dp_stream_t stream) {
   char* ws = (char*)a->workspace;
   float* part = (float*)ws;
   float* fin = (float*)(ws + align256((size_t)a->N * mp.nchunks * 2 * a->C * sizeof(float)));
-  float* coef = (float*)((char*)fin + align256((size_t)a->N * 2 * a->C * sizeof(float)));
   if (a->fin) fin = a->fin;      // caller-owned: outlives the shared workspace, dgamma / dbeta are taken later (dp_groupnorm_bwd_param)
   dim3 grid(mp.nchunks, a->N);
   if (v4) gn_bwd_partial4_kernel<<<grid, NT, 2 * mp.PL * mp.CT * 4 * sizeof(float), st>>>(*a, mp, part);
@@ -735,13 +754,14 @@ extern "C" int dp_groupnorm_bwd(const dp_gn_args* a, dp_stream_t stream) {
   if ((rc = dp_check_launch())) return rc;
   const bool fold = mp.nchunks <= GN_FOLD_BWD;
   if (!fold) {
-    gn_bwd_finalize_kernel<<<a->N, NT, 2 * a->C * sizeof(float), st>>>(*a, mp, part, fin, coef);
+    gn_bwd_reduce_kernel<<<dim3((a->C + 31) / 32, a->N), 1024, 0, st>>>(*a, mp, part, fin);
     if ((rc = dp_check_launch())) return rc;
   }
-  const float* fpart = fold ? part : nullptr;
-  const size_t fsm = fold ? (2 * (size_t)a->C + 2 * (size_t)a->G) * sizeof(float) : 0;
-  if (v4) gn_bwd_apply4_kernel<<<grid, NT, fsm, st>>>(*a, mp, coef, fpart, fin);
-  else gn_bwd_apply_kernel<<<grid, NT, fsm, st>>>(*a, mp, coef, fpart, fin);
+  const float* src = fold ? part : fin;
+  const int nrows = fold ? mp.nchunks : 1;
+  const size_t fsm = (2 * (size_t)a->C + 2 * (size_t)a->G) * sizeof(float);
+  if (v4) gn_bwd_apply4_kernel<<<grid, NT, fsm, st>>>(*a, mp, src, nrows, fin);
+  else gn_bwd_apply_kernel<<<grid, NT, fsm, st>>>(*a, mp, src, nrows, fin);
   if ((rc = dp_check_launch())) return rc;
   if (!a->fin && (a->dgamma || a->dbeta)) {      // after the apply pass: its chunk-0 blocks write fin in the folded form
     gn_bwd_param_kernel<<<(a->C + 31) / 32, 1024, 0, st>>>(*a, fin);

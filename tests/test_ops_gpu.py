@@ -187,7 +187,7 @@ GN_CASES = [(2, 8, 8, 32, 8, 1, 0), (3, 4, 4, 96, 32, 1, 16), (2, 16, 16, 128, 3
             (2, 2, 2, 768, 32, 1, 0), (1, 32, 32, 192, 32, 1, 64), (4, 3, 5, 24, 3, 0, 0),
             (2, 8, 8, 30, 3, 1, 0), (2, 8, 8, 64, 8, 1, 2), (2, 4, 4, 358, 2, 1, 0),   # scalar path: C%4!=0 / misaligned view
             (1, 64, 64, 128, 32, 1, 0), (3, 32, 32, 96, 32, 1, 0), (2, 16, 16, 384, 32, 1, 8),   # chunked float4 path: 32 / 7 / 7 chunks per image
-            (1, 128, 64, 128, 32, 1, 0),                                   # 64 chunks: separate finalize launches in both directions
+            (1, 128, 64, 128, 32, 1, 0), (2, 64, 64, 90, 30, 1, 0),        # 64 / 46 chunks (float4 / scalar): warp-per-group finalize, chunk-reduction launch
             (2, 32, 32, 90, 30, 1, 0), (2, 16, 16, 179, 1, 1, 0)]          # scalar path at pruned widths: 12 chunks (forward folded only) / 6 (both folded)
 
 
