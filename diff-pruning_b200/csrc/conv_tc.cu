@@ -1063,44 +1063,88 @@ __global__ void split_h3_rows_kernel(const float* __restrict__ x, long long ld, 
     *reinterpret_cast<uint4*>(lb + r * pitch + c0) = l;
   }
 }
-// transposed form: out[b][c][r] (rows of round8(rows) elements).  A 32 (c) x 64 (r) tile through shared memory: coalesced float reads
-// along c, half2 writes along r (128 bytes per warp store)
-__global__ void split_h3_t_kernel(const float* __restrict__ x, long long ld, long long bs, int rows, int cols,
-                                  __half* __restrict__ hi, __half* __restrict__ lo, const uint32_t* __restrict__ amax) {
-  __shared__ float t[64][33];
+// transposed form: out[b][c][r] (rows of round8(rows) elements).  A 64 (r) x 64 (c) tile through shared memory: float4 reads along c
+// (256 bytes per 16 threads), then every thread owns one output row segment of 16 consecutive r: two 16-byte stores per array
+__global__ void __launch_bounds__(256) split_h3_t_kernel(const float* __restrict__ x, long long ld, long long bs, int rows, int cols, int vec,
+                                                         __half* __restrict__ hi, __half* __restrict__ lo, const uint32_t* __restrict__ amax) {
+  __shared__ float t[64][65];
   const float sx = scale_up(amax_exponent(amax));
-  const int b = blockIdx.z, r0 = blockIdx.y * 64, c0 = blockIdx.x * 32;
+  const int b = blockIdx.z, r0 = blockIdx.y * 64, c0 = blockIdx.x * 64, tid = threadIdx.x;
   const float* xb = x + (long long)b * bs;
-  for (int i = threadIdx.y; i < 64; i += 8) {
-    const int r = r0 + i, c = c0 + threadIdx.x;
-    t[i][threadIdx.x] = (r < rows && c < cols) ? xb[(long long)r * ld + c] * sx : 0.f;
+  {
+    const int cc = (tid & 15) * 4, c = c0 + cc;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int rr = (tid >> 4) + 16 * i, r = r0 + rr;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < rows) {
+        const float* src = xb + (long long)r * ld + c;
+        if (vec && c + 4 <= cols) v = __ldg(reinterpret_cast<const float4*>(src));
+        else {
+          if (c < cols) v.x = __ldg(src);
+          if (c + 1 < cols) v.y = __ldg(src + 1);
+          if (c + 2 < cols) v.z = __ldg(src + 2);
+          if (c + 3 < cols) v.w = __ldg(src + 3);
+        }
+      }
+      t[rr][cc] = v.x * sx; t[rr][cc + 1] = v.y * sx; t[rr][cc + 2] = v.z * sx; t[rr][cc + 3] = v.w * sx;
+    }
   }
   __syncthreads();
   const int rows8 = (rows + 7) & ~7;
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    const int c = c0 + i, r = r0 + 2 * threadIdx.x;
-    if (c < cols && r < rows8) {        // rows8 is even: the pair (r, r+1) is inside the padded row or outside together
-      uint32_t h, l;
-      split2(t[2 * threadIdx.x][i], t[2 * threadIdx.x + 1][i], h, l);
-      const long long o = ((long long)b * cols + c) * rows8 + r;
-      *reinterpret_cast<uint32_t*>(hi + o) = h;
-      *reinterpret_cast<uint32_t*>(lo + o) = l;
+  const int c = c0 + (tid >> 2), rs = (tid & 3) * 16;
+  if (c < cols) {
+    const long long o = ((long long)b * cols + c) * rows8 + r0 + rs;
+#pragma unroll
+    for (int h8 = 0; h8 < 2; ++h8) {
+      if (r0 + rs + 8 * h8 + 8 <= rows8) {         // rows8 and the segments are multiples of 8: a segment is inside or outside as a whole
+        uint4 h, l;
+        const int rb = rs + 8 * h8, cl = tid >> 2;
+        split2(t[rb][cl], t[rb + 1][cl], h.x, l.x); split2(t[rb + 2][cl], t[rb + 3][cl], h.y, l.y);
+        split2(t[rb + 4][cl], t[rb + 5][cl], h.z, l.z); split2(t[rb + 6][cl], t[rb + 7][cl], h.w, l.w);
+        *reinterpret_cast<uint4*>(hi + o + 8 * h8) = h;
+        *reinterpret_cast<uint4*>(lo + o + 8 * h8) = l;
+      }
     }
   }
 }
-__global__ void transpose_batched_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
-  __shared__ float t[32][33];
-  const int b = blockIdx.z, r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+// out[b][c][r] = in[b][r][c]: 64 x 64 tiles, float4 on both sides when the extents allow it
+__global__ void __launch_bounds__(256) transpose_batched_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols, int vec) {
+  __shared__ float t[64][65];
+  const int b = blockIdx.z, r0 = blockIdx.y * 64, c0 = blockIdx.x * 64, tid = threadIdx.x;
   const float* ib = in + (long long)b * rows * cols;
   float* ob = out + (long long)b * rows * cols;
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    int r = r0 + i, c = c0 + threadIdx.x;
-    if (r < rows && c < cols) t[i][threadIdx.x] = ib[(long long)r * cols + c];
+  const int q4 = (tid & 15) * 4, l16 = tid >> 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int rr = l16 + 16 * i, r = r0 + rr, c = c0 + q4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < rows) {
+      const float* src = ib + (long long)r * cols + c;
+      if (vec && c + 4 <= cols) v = __ldg(reinterpret_cast<const float4*>(src));
+      else {
+        if (c < cols) v.x = __ldg(src);
+        if (c + 1 < cols) v.y = __ldg(src + 1);
+        if (c + 2 < cols) v.z = __ldg(src + 2);
+        if (c + 3 < cols) v.w = __ldg(src + 3);
+      }
+    }
+    t[rr][q4] = v.x; t[rr][q4 + 1] = v.y; t[rr][q4 + 2] = v.z; t[rr][q4 + 3] = v.w;
   }
   __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    int c = c0 + i, r = r0 + threadIdx.x;
-    if (c < cols && r < rows) ob[(long long)c * rows + r] = t[threadIdx.x][i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int cc = l16 + 16 * i, c = c0 + cc, r = r0 + q4;
+    if (c < cols) {
+      float* dst = ob + (long long)c * rows + r;
+      if (vec && r + 4 <= rows) *reinterpret_cast<float4*>(dst) = make_float4(t[q4][cc], t[q4 + 1][cc], t[q4 + 2][cc], t[q4 + 3][cc]);
+      else {
+        if (r < rows) dst[0] = t[q4][cc];
+        if (r + 1 < rows) dst[1] = t[q4 + 1][cc];
+        if (r + 2 < rows) dst[2] = t[q4 + 2][cc];
+        if (r + 3 < rows) dst[3] = t[q4 + 3][cc];
+      }
+    }
   }
 }
 }  // namespace
@@ -1118,16 +1162,19 @@ extern "C" int dp_split_h3(const float* x, int64_t ld, int64_t bs, int32_t batch
                                                                                                 (__half*)lo, amax);
   } else {
     // the padded tail of a row (rows8) must be covered by the grid: round the covered extent up
-    dim3 grid((cols + 31) / 32, (((rows + 7) & ~7) + 63) / 64, batch);
-    split_h3_t_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(x, ld, bs, rows, cols, (__half*)hi, (__half*)lo, amax);
+    const int vec = ((((uintptr_t)x) & 15) == 0 && ld % 4 == 0 && bs % 4 == 0) ? 1 : 0;
+    DP_REQUIRE((((uintptr_t)hi) & 15) == 0 && (((uintptr_t)lo) & 15) == 0, DP_ERR_ALIGN);
+    dim3 grid((cols + 63) / 64, (((rows + 7) & ~7) + 63) / 64, batch);
+    split_h3_t_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ld, bs, rows, cols, vec, (__half*)hi, (__half*)lo, amax);
   }
   return dp_check_launch();
 }
 extern "C" int dp_transpose_batched(const float* in, float* out, int32_t batch, int32_t rows, int32_t cols, dp_stream_t stream) {
   DP_REQUIRE(in && out, DP_ERR_NULL);
   DP_REQUIRE(batch > 0 && rows > 0 && cols > 0 && batch <= 65535, DP_ERR_SHAPE);
-  dim3 grid((cols + 31) / 32, (rows + 31) / 32, batch);
-  transpose_batched_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(in, out, rows, cols);
+  const int vec = ((((uintptr_t)in) & 15) == 0 && (((uintptr_t)out) & 15) == 0 && rows % 4 == 0 && cols % 4 == 0) ? 1 : 0;
+  dim3 grid((cols + 63) / 64, (rows + 63) / 64, batch);
+  transpose_batched_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, rows, cols, vec);
   return dp_check_launch();
 }
 extern "C" int dp_gemm_nt_tc(const dp_gemm_nt_args* a, dp_stream_t stream) {

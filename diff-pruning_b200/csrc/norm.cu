@@ -20,14 +20,43 @@ static inline Map make_map(int HW, int C) {
   return m;
 }
 
-__device__ __forceinline__ float keep_scale(uint64_t seed, uint64_t idx, float p) {
-  // counter-based hash (splitmix64) -> uniform in [0,1); keep if u >= p, scaled by 1/(1-p)
-  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1);
+// Dropout keep-mask: a counter-based hash (splitmix64) of (seed, element index / 4) yields 64 bits = one 16-bit uniform for each of
+// 4 consecutive elements (the float4 kernels hash once per load); keep if u16 >= thr = round(p * 65536), survivors scaled by
+// 65536 / (65536 - thr) (the exact inverse keep rate).  Forward and backward regenerate the same mask from the element index alone.
+struct Drop {
+  uint64_t seed; uint32_t thr; float inv; bool on;
+};
+__device__ __forceinline__ Drop make_drop(const dp_gn_args& a) {
+  Drop d;
+  d.on = a.dropout_p > 0.f;
+  d.seed = a.dropout_seed + ((d.on && a.dropout_seed_dev) ? *a.dropout_seed_dev : 0ull);
+  d.thr = d.on ? __float2uint_rn(a.dropout_p * 65536.f) : 0u;
+  d.inv = 65536.f / (float)(65536u - d.thr);
+  return d;
+}
+__device__ __forceinline__ uint64_t drop_bits(uint64_t seed, uint64_t group) {
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (group + 1);
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  float u = (float)(z >> 40) * (1.0f / 16777216.0f);
-  return u >= p ? 1.0f / (1.0f - p) : 0.0f;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ float keep_scale(const Drop& d, uint64_t idx) {
+  const uint32_t u = (uint32_t)(drop_bits(d.seed, idx >> 2) >> (16 * (int)(idx & 3))) & 0xFFFFu;
+  return u >= d.thr ? d.inv : 0.f;
+}
+__device__ __forceinline__ void keep_scale4(const Drop& d, uint64_t idx0 /* % 4 == 0 */, float (&k)[4]) {
+  const uint64_t z = drop_bits(d.seed, idx0 >> 2);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) k[e] = ((uint32_t)(z >> (16 * e)) & 0xFFFFu) >= d.thr ? d.inv : 0.f;
+}
+// SiLU through the special-function unit: ex2.approx + rcp.approx (~3e-7 relative on the sigmoid, an order below the 22-bit operand
+// split of the convolutions that consume it).  The accurate expf + correctly rounded reciprocal cost ~16 instructions per element and made
+// every GroupNorm kernel with a SiLU issue-bound at ~40 % of the HBM rate (profiles/r02_experiments.md, section 17).
+__device__ __forceinline__ float sigmoidf_fast(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
 }
 
 __global__ void __launch_bounds__(NT) gn_stats_kernel(const dp_gn_args a, const Map mp, double* __restrict__ ws) {
@@ -138,6 +167,7 @@ __global__ void __launch_bounds__(NT) gn_apply_kernel(const dp_gn_args a, const 
   }
   const float* xb = a.x + (long long)n * a.HW * a.ldx;
   float* yb = a.y + (long long)n * a.HW * a.ldy;
+  const Drop drop = make_drop(a);
   float amax = 0.f;
   for (int pix = p0 + pl; pix < p1; pix += mp.PL) {
     const float* row = xb + (long long)pix * a.ldx;
@@ -147,8 +177,8 @@ __global__ void __launch_bounds__(NT) gn_apply_kernel(const dp_gn_args a, const 
       int c = ct + u * NT;
       if (c < a.C) {
         float y = fmaf(__ldg(row + c), sc[u], shf[u]);
-        if (a.silu) y = y * sigmoidf_acc(y);
-        if (a.dropout_p > 0.f) y *= keep_scale(a.dropout_seed + (a.dropout_seed_dev ? *a.dropout_seed_dev : 0ull), ((uint64_t)n * a.HW + pix) * a.C + c, a.dropout_p);
+        if (a.silu) y = y * sigmoidf_fast(y);
+        if (drop.on) y *= keep_scale(drop, ((uint64_t)n * a.HW + pix) * a.C + c);
         if (a.y) orow[c] = y;
         if (a.y_bf16) reinterpret_cast<__nv_bfloat16*>(a.y_bf16)[((long long)n * a.HW + pix) * a.ldyb + c] = __float2bfloat16_rn(y);
         amax = fmaxf(amax, fabsf(y));
@@ -159,10 +189,8 @@ __global__ void __launch_bounds__(NT) gn_apply_kernel(const dp_gn_args a, const 
 }
 
 // ---- backward ----
-__device__ __forceinline__ float gn_dy(const dp_gn_args& a, float dA, float y, uint64_t eidx) {
-  float g = dA;
-  if (a.dropout_p > 0.f) g *= keep_scale(a.dropout_seed + (a.dropout_seed_dev ? *a.dropout_seed_dev : 0ull), eidx, a.dropout_p);
-  if (a.silu) { float s = sigmoidf_acc(y); g *= s * (1.f + y * (1.f - s)); }
+__device__ __forceinline__ float gn_dy(const dp_gn_args& a, float g, float y) {   // g: dy with the dropout keep-scale already applied
+  if (a.silu) { float s = sigmoidf_fast(y); g *= s * (1.f + y * (1.f - s)); }
   return g;
 }
 
@@ -181,6 +209,7 @@ __global__ void __launch_bounds__(NT) gn_bwd_partial_kernel(const dp_gn_args a, 
   }
   const float* xb = a.x + (long long)n * a.HW * a.ldx;
   const float* db = a.dy + (long long)n * a.HW * a.lddy;
+  const Drop drop = make_drop(a);
   for (int pix = p0 + pl; pix < p1; pix += mp.PL) {
 #pragma unroll
     for (int u = 0; u < MAXCPT; ++u) {
@@ -188,7 +217,9 @@ __global__ void __launch_bounds__(NT) gn_bwd_partial_kernel(const dp_gn_args a, 
       if (c < a.C) {
         float xh = (__ldg(xb + (long long)pix * a.ldx + c) - mu[u]) * rs[u];
         float y = fmaf(xh, ga[u], be[u]);
-        float g = gn_dy(a, __ldg(db + (long long)pix * a.lddy + c), y, ((uint64_t)n * a.HW + pix) * a.C + c);
+        float g = __ldg(db + (long long)pix * a.lddy + c);
+        if (drop.on) g *= keep_scale(drop, ((uint64_t)n * a.HW + pix) * a.C + c);
+        g = gn_dy(a, g, y);
         s1[u] += g; s2[u] += g * xh;
       }
     }
@@ -302,6 +333,7 @@ __global__ void __launch_bounds__(NT) gn_bwd_apply_kernel(const dp_gn_args a, co
   }
   const float* xb = a.x + (long long)n * a.HW * a.ldx;
   const float* db = a.dy + (long long)n * a.HW * a.lddy;
+  const Drop drop = make_drop(a);
   float* ob = a.dx + (long long)n * a.HW * a.lddx;
   const float* ab = a.dx_add ? a.dx_add + (long long)n * a.HW * a.ldadd : nullptr;
   const float* ab2 = a.dx_add2 ? a.dx_add2 + (long long)n * a.HW * a.ldadd2 : nullptr;
@@ -313,7 +345,9 @@ __global__ void __launch_bounds__(NT) gn_bwd_apply_kernel(const dp_gn_args a, co
       if (c < a.C) {
         float xh = (__ldg(xb + (long long)pix * a.ldx + c) - mu[u]) * rs[u];
         float y = fmaf(xh, ga[u], be[u]);
-        float g = gn_dy(a, __ldg(db + (long long)pix * a.lddy + c), y, ((uint64_t)n * a.HW + pix) * a.C + c);
+        float g = __ldg(db + (long long)pix * a.lddy + c);
+        if (drop.on) g *= keep_scale(drop, ((uint64_t)n * a.HW + pix) * a.C + c);
+        g = gn_dy(a, g, y);
         float d = rs[u] * (ga[u] * g - c1[u] - xh * c2[u]);
         if (ab) d += ab[(long long)pix * a.ldadd + c];
         if (ab2) d += ab2[(long long)pix * a.ldadd2 + c];
@@ -409,7 +443,7 @@ __global__ void __launch_bounds__(NT) gn_apply4_kernel(const dp_gn_args a, const
   }
   const float* xb = a.x + (long long)n * a.HW * a.ldx + c0;
   float* yb = a.y + (long long)n * a.HW * a.ldy + c0;
-  const uint64_t seed = a.dropout_seed + (a.dropout_seed_dev ? *a.dropout_seed_dev : 0ull);
+  const Drop drop = make_drop(a);
   float amax = 0.f;
   float4 cur[GU], nxt[GU];       // software pipeline: see gn_stats4_kernel
   const int gstep = GU * mp.PL;
@@ -429,8 +463,13 @@ __global__ void __launch_bounds__(NT) gn_apply4_kernel(const dp_gn_args a, const
     float y[4] = {fmaf(v.x, sc[0], shf[0]), fmaf(v.y, sc[1], shf[1]), fmaf(v.z, sc[2], shf[2]), fmaf(v.w, sc[3], shf[3])};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      if (a.silu) y[e] = y[e] * sigmoidf_acc(y[e]);
-      if (a.dropout_p > 0.f) y[e] *= keep_scale(seed, ((uint64_t)n * a.HW + pix) * a.C + c0 + e, a.dropout_p);
+      if (a.silu) y[e] = y[e] * sigmoidf_fast(y[e]);
+    }
+    if (drop.on) {
+      float k[4];
+      keep_scale4(drop, ((uint64_t)n * a.HW + pix) * a.C + c0, k);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) y[e] *= k[e];
     }
     if (a.y) *reinterpret_cast<float4*>(yb + (long long)pix * a.ldy) = make_float4(y[0], y[1], y[2], y[3]);
     if (a.y_bf16) {   // the next convolution's bf16 operand (c0 % 4 == 0 and ldyb % 8 == 0: 8-byte aligned)
@@ -464,14 +503,21 @@ __global__ void __launch_bounds__(NT) gn_bwd_partial4_kernel(const dp_gn_args a,
   if (act) {
     const float* xb = a.x + (long long)n * a.HW * a.ldx + c0;
     const float* db = a.dy + (long long)n * a.HW * a.lddy + c0;
+    const Drop drop = make_drop(a);
 #pragma unroll 4
     for (int pix = p0 + pl; pix < p1; pix += mp.PL) {
       float4 xv = ld4(xb + (long long)pix * a.ldx), dv = ld4(db + (long long)pix * a.lddy);
       float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ds[4] = {dv.x, dv.y, dv.z, dv.w};
+      if (drop.on) {
+        float k[4];
+        keep_scale4(drop, ((uint64_t)n * a.HW + pix) * a.C + c0, k);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) ds[e] *= k[e];
+      }
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         float xh = (xs[e] - mu[e]) * rs[e];
-        float g = gn_dy(a, ds[e], fmaf(xh, ga[e], be[e]), ((uint64_t)n * a.HW + pix) * a.C + c0 + e);
+        float g = gn_dy(a, ds[e], fmaf(xh, ga[e], be[e]));
         s1[e] += g; s2[e] += g * xh;
       }
     }
@@ -507,6 +553,7 @@ __global__ void __launch_bounds__(NT) gn_bwd_apply4_kernel(const dp_gn_args a, c
   }
   const float* xb = a.x + (long long)n * a.HW * a.ldx + c0;
   const float* db = a.dy + (long long)n * a.HW * a.lddy + c0;
+  const Drop drop = make_drop(a);
   float* ob = a.dx + (long long)n * a.HW * a.lddx + c0;
   const float* ab = a.dx_add ? a.dx_add + (long long)n * a.HW * a.ldadd + c0 : nullptr;
   const float* ab2 = a.dx_add2 ? a.dx_add2 + (long long)n * a.HW * a.ldadd2 + c0 : nullptr;
@@ -515,10 +562,16 @@ __global__ void __launch_bounds__(NT) gn_bwd_apply4_kernel(const dp_gn_args a, c
   for (int pix = p0 + pl; pix < p1; pix += mp.PL) {
     float4 xv = ld4(xb + (long long)pix * a.ldx), dv = ld4(db + (long long)pix * a.lddy);
     float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ds[4] = {dv.x, dv.y, dv.z, dv.w}, d[4];
+    if (drop.on) {
+      float k[4];
+      keep_scale4(drop, ((uint64_t)n * a.HW + pix) * a.C + c0, k);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) ds[e] *= k[e];
+    }
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       float xh = (xs[e] - mu[e]) * rs[e];
-      float g = gn_dy(a, ds[e], fmaf(xh, ga[e], be[e]), ((uint64_t)n * a.HW + pix) * a.C + c0 + e);
+      float g = gn_dy(a, ds[e], fmaf(xh, ga[e], be[e]));
       d[e] = rs[e] * (ga[e] * g - k1[e] - xh * k2[e]);
     }
     if (ab) { float4 t = *reinterpret_cast<const float4*>(ab + (long long)pix * a.ldadd); d[0] += t.x; d[1] += t.y; d[2] += t.z; d[3] += t.w; }
