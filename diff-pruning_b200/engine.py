@@ -614,7 +614,7 @@ class Plan:
                 f.side = 1
             steps[n_steps1].side = 2
 
-    FUSE_QKV = os.environ.get("DPB200_FUSE_QKV", "1") != "0"      # to_q / to_k / to_v of an attention block as one projection (conv_qkv); 0: A/B runs
+    FUSE_QKV = True      # to_q / to_k / to_v of an attention block as one projection (conv_qkv); tests / A-B runs may clear it before planning
 
     def qkv_fusable(self, x: View, lins) -> bool:
         ws = [l.weight for l in lins]

@@ -14,6 +14,7 @@ print({k: v for k, v in d['roofline']['other_launches_ms'].items() if v > 0.05})
 for k in ('finetune','finetune_bf16','config3'):
     if k in d: print(k, d[k]['value'], d[k]['ms_per_step'], d[k].get('roofline',{}).get('breakdown_ms'), d[k].get('roofline',{}).get('frac'))
 PY
+# (the A/B switch DPB200_FUSE_QKV existed only at the commit this call ran on)
 DPB200_FUSE_QKV=0 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu --no-finetune --no-c3 > gpurun_out/bench_c1_noqkv.json 2> gpurun_out/bench_c1_noqkv.err
 echo "== bench c1 (q/k/v unfused) rc=$?"; python - <<'PY'
 import json

@@ -183,6 +183,17 @@ def test_softmax_fwd_bwd(lib, rows, cols):
     assert rel_err(gd.cpu(), s.grad) < 5e-6
 
 
+def test_copy_rows(lib):
+    """dp_copy_rows: strided [rows][cols] device copy (the pack list gathers to_q / to_k / to_v into the fused projection's operand)."""
+    g = torch.Generator().manual_seed(5)
+    src = torch.randn(37, 200, generator=g).cuda()
+    dst = torch.full((40, 190), -7.0, device="cuda")
+    assert lib.dp_copy_rows(src.data_ptr() + 4 * 3, 200, dst.data_ptr() + 4 * (2 * 190 + 5), 190, 37, 179, S()) == 0
+    assert torch.equal(dst[2:39, 5:184], src[:, 3:182])
+    assert bool((dst[:2] == -7).all()) and bool((dst[39:] == -7).all()) and bool((dst[2:39, :5] == -7).all()) and bool((dst[2:39, 184:] == -7).all())
+    assert lib.dp_copy_rows(src.data_ptr(), 100, dst.data_ptr(), 190, 2, 179, S()) == -1     # lda < cols: DP_ERR_SHAPE
+
+
 GN_CASES = [(2, 8, 8, 32, 8, 1, 0), (3, 4, 4, 96, 32, 1, 16), (2, 16, 16, 128, 32, 0, 0), (2, 4, 4, 512, 32, 1, 0),
             (2, 2, 2, 768, 32, 1, 0), (1, 32, 32, 192, 32, 1, 64), (4, 3, 5, 24, 3, 0, 0),
             (2, 8, 8, 30, 3, 1, 0), (2, 8, 8, 64, 8, 1, 2), (2, 4, 4, 358, 2, 1, 0),   # scalar path: C%4!=0 / misaligned view
