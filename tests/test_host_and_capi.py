@@ -131,3 +131,41 @@ def test_tc_weight_row_padding_rule():
                     (512, 512)]:
         assert lib.dp_tc_weight_row(c) == want, (c, lib.dp_tc_weight_row(c), want)
     assert lib.dp_tc_weight_row(0) == 0
+
+
+def test_planner_fuses_qkv_and_moves_groupnorm_param_grads_off_the_chain():
+    """Host-side planning only (no launch): with the tensor path forced on, a CPU-built plan of the tiny UNet shows the launch structure
+    the GPU runs — to_q / to_k / to_v as one fprop and one dgrad with three weight gradients (engine.conv_qkv), and every GroupNorm's
+    dgamma / dbeta launch flagged for the side stream right behind its dx launch."""
+    from collections import Counter
+    from diff_pruning_b200 import engine
+
+    class P(engine.Plan):
+        def _build(self):
+            self.tc = True          # what dp_tc_available() answers on an sm_100a device
+            return super()._build()
+
+    torch.manual_seed(0)
+    m = dp.UNet2DModel(**dp.TINY_TEST_CONFIG)
+    n_attn = sum(1 for mod in m.modules() if type(mod).__name__ == "Attention")
+    n_gn = sum(1 for mod in m.modules() if isinstance(mod, torch.nn.GroupNorm))
+    assert n_attn > 0
+
+    def counts(fuse):
+        P.FUSE_QKV = fuse
+        try:
+            p = P(m, 2, 16, 16, "cpu", need_grad=True)
+        finally:
+            P.FUSE_QKV = True
+        return p, Counter(f.what for f in p.fwd), Counter(f.what for f in p.bwd_steps), Counter(f.what for f in p.pack)
+
+    p1, f1, b1, k1 = counts(True)
+    p0, f0, b0, k0 = counts(False)
+    assert f0["conv fprop"] - f1["conv fprop"] == 2 * n_attn and b0["conv dgrad"] - b1["conv dgrad"] == 2 * n_attn
+    assert b0["conv wgrad"] == b1["conv wgrad"] and b0["conv wgrad reduce"] == b1["conv wgrad reduce"]
+    assert k1["pack qkv"] == 6 * n_attn and k0["pack qkv"] == 0          # three weights + three biases gathered per block
+    assert f1["gn fwd"] == n_gn and b1["gn bwd"] == n_gn and b1["gn bwd param"] == n_gn
+    steps = p1.bwd_steps
+    for i, f in enumerate(steps):
+        if f.what == "gn bwd":
+            assert steps[i + 1].what == "gn bwd param" and getattr(steps[i + 1], "side", 0) == 2 and not getattr(f, "side", 0)
