@@ -32,6 +32,7 @@ for N, HW, Cc, G in SHAPES:
     a.workspace, a.amax_y, a.amax_dx = ws.data_ptr(), slots.data_ptr(), slots.data_ptr() + 4
     a.dy, a.lddy, a.dx, a.lddx = dy.data_ptr(), Cc, dx.data_ptr(), Cc
     a.dx_add2, a.ldadd2 = add2.data_ptr(), Cc
+    a.dx_add, a.ldadd = dx.data_ptr(), Cc          # accumulate into the existing gradient (aliases dx), as most layers of a pass do
     a.dgamma, a.dbeta, a.fin = dg.data_ptr(), db.data_ptr(), fin.data_ptr()
     runs.append((a, (x, y, dy, dx, add2, gm, bt, dg, db, stats, ws, fin, slots)))
 # attention operand split / transpose (C1: 128 images x 256 tokens x 256 channels)
