@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(NT) gn_stats4_kernel(const dp_gn_args a, const
   }
 }
 
-__global__ void __launch_bounds__(NT) gn_apply4_kernel(const dp_gn_args a, const Map mp, const double* __restrict__ fold_ws) {
+__global__ void __launch_bounds__(NT, 4) gn_apply4_kernel(const dp_gn_args a, const Map mp, const double* __restrict__ fold_ws) {
   extern __shared__ float shst[];   // folded finalize: [2][G]
   const int n = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
   const int ct = tid % mp.CT, pl = tid / mp.CT, c0 = ct * 4;
@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(NT) gn_apply4_kernel(const dp_gn_args a, const
   if (a.amax_y) amax_commit(a.amax_y, amax);
 }
 
-__global__ void __launch_bounds__(NT) gn_bwd_partial4_kernel(const dp_gn_args a, const Map mp, float* __restrict__ part) {
+__global__ void __launch_bounds__(NT, 4) gn_bwd_partial4_kernel(const dp_gn_args a, const Map mp, float* __restrict__ part) {
   extern __shared__ float shf32[];  // [2][PL][CT*4]
   const int n = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
   const int ct = tid % mp.CT, pl = tid / mp.CT, c0 = ct * 4;
@@ -504,21 +504,37 @@ __global__ void __launch_bounds__(NT) gn_bwd_partial4_kernel(const dp_gn_args a,
     const float* xb = a.x + (long long)n * a.HW * a.ldx + c0;
     const float* db = a.dy + (long long)n * a.HW * a.lddy + c0;
     const Drop drop = make_drop(a);
-#pragma unroll 4
-    for (int pix = p0 + pl; pix < p1; pix += mp.PL) {
-      float4 xv = ld4(xb + (long long)pix * a.ldx), dv = ld4(db + (long long)pix * a.lddy);
-      float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ds[4] = {dv.x, dv.y, dv.z, dv.w};
-      if (drop.on) {
-        float k[4];
-        keep_scale4(drop, ((uint64_t)n * a.HW + pix) * a.C + c0, k);
+    // groups of PU pixels with ALL their loads issued before the first use: the SiLU / dropout branches inside the body are basic-block
+    // boundaries the compiler does not move loads across, so a plain (even unrolled) loop keeps one pixel = two 16-byte loads in flight
+    // per thread — 24 KB per SM, a quarter of what HBM needs (profiles/r02_experiments.md, section 18).  Same summation order.
+    constexpr int PU = 2;
+    const int gstep = PU * mp.PL;
+    for (int base = p0 + pl; base < p1; base += gstep) {
+      float4 xg[PU], dg[PU];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) ds[e] *= k[e];
+      for (int u = 0; u < PU; ++u) {
+        const int px = base + u * mp.PL;
+        xg[u] = dg[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (px < p1) { xg[u] = ld4(xb + (long long)px * a.ldx); dg[u] = ld4(db + (long long)px * a.lddy); }
       }
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float xh = (xs[e] - mu[e]) * rs[e];
-        float g = gn_dy(a, ds[e], fmaf(xh, ga[e], be[e]));
-        s1[e] += g; s2[e] += g * xh;
+      for (int u = 0; u < PU; ++u) {
+        const int pix = base + u * mp.PL;
+        if (pix < p1) {
+          float xs[4] = {xg[u].x, xg[u].y, xg[u].z, xg[u].w}, ds[4] = {dg[u].x, dg[u].y, dg[u].z, dg[u].w};
+          if (drop.on) {
+            float k[4];
+            keep_scale4(drop, ((uint64_t)n * a.HW + pix) * a.C + c0, k);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) ds[e] *= k[e];
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float xh = (xs[e] - mu[e]) * rs[e];
+            float g = gn_dy(a, ds[e], fmaf(xh, ga[e], be[e]));
+            s1[e] += g; s2[e] += g * xh;
+          }
+        }
       }
     }
   }
@@ -535,7 +551,7 @@ __global__ void __launch_bounds__(NT) gn_bwd_partial4_kernel(const dp_gn_args a,
   }
 }
 
-__global__ void __launch_bounds__(NT) gn_bwd_apply4_kernel(const dp_gn_args a, const Map mp, const float* part, int nrows, float* fin) {
+__global__ void __launch_bounds__(NT, 4) gn_bwd_apply4_kernel(const dp_gn_args a, const Map mp, const float* part, int nrows, float* fin) {
   extern __shared__ float shfold[];   // folded finalize: [2][C] weighted sums + [G][2] coefficients
   const int n = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
   const int ct = tid % mp.CT, pl = tid / mp.CT, c0 = ct * 4;
@@ -558,26 +574,45 @@ __global__ void __launch_bounds__(NT) gn_bwd_apply4_kernel(const dp_gn_args a, c
   const float* ab = a.dx_add ? a.dx_add + (long long)n * a.HW * a.ldadd + c0 : nullptr;
   const float* ab2 = a.dx_add2 ? a.dx_add2 + (long long)n * a.HW * a.ldadd2 + c0 : nullptr;
   float amax = 0.f;
-#pragma unroll 4
-  for (int pix = p0 + pl; pix < p1; pix += mp.PL) {
-    float4 xv = ld4(xb + (long long)pix * a.ldx), dv = ld4(db + (long long)pix * a.lddy);
-    float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ds[4] = {dv.x, dv.y, dv.z, dv.w}, d[4];
-    if (drop.on) {
-      float k[4];
-      keep_scale4(drop, ((uint64_t)n * a.HW + pix) * a.C + c0, k);
+  // pairs of pixels with all eight loads (x, dy and the two optional addends) issued before the first use — see gn_bwd_partial4_kernel.
+  // dx_add may alias dx: every element is read by the thread that later writes it, and a pair's reads precede the pair's stores
+  constexpr int BU = 2;
+  const int gstep = BU * mp.PL;
+  for (int base = p0 + pl; base < p1; base += gstep) {
+    float4 xg[BU], dg[BU], ag[BU], bg[BU];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) ds[e] *= k[e];
+    for (int u = 0; u < BU; ++u) {
+      const int px = base + u * mp.PL;
+      xg[u] = dg[u] = ag[u] = bg[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (px < p1) {
+        xg[u] = ld4(xb + (long long)px * a.ldx); dg[u] = ld4(db + (long long)px * a.lddy);
+        if (ab) ag[u] = *reinterpret_cast<const float4*>(ab + (long long)px * a.ldadd);
+        if (ab2) bg[u] = ld4(ab2 + (long long)px * a.ldadd2);
+      }
     }
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float xh = (xs[e] - mu[e]) * rs[e];
-      float g = gn_dy(a, ds[e], fmaf(xh, ga[e], be[e]));
-      d[e] = rs[e] * (ga[e] * g - k1[e] - xh * k2[e]);
+    for (int u = 0; u < BU; ++u) {
+      const int pix = base + u * mp.PL;
+      if (pix < p1) {
+        float xs[4] = {xg[u].x, xg[u].y, xg[u].z, xg[u].w}, ds[4] = {dg[u].x, dg[u].y, dg[u].z, dg[u].w}, d[4];
+        if (drop.on) {
+          float k[4];
+          keep_scale4(drop, ((uint64_t)n * a.HW + pix) * a.C + c0, k);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) ds[e] *= k[e];
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float xh = (xs[e] - mu[e]) * rs[e];
+          float g = gn_dy(a, ds[e], fmaf(xh, ga[e], be[e]));
+          d[e] = rs[e] * (ga[e] * g - k1[e] - xh * k2[e]);
+        }
+        if (ab) { d[0] += ag[u].x; d[1] += ag[u].y; d[2] += ag[u].z; d[3] += ag[u].w; }
+        if (ab2) { d[0] += bg[u].x; d[1] += bg[u].y; d[2] += bg[u].z; d[3] += bg[u].w; }
+        *reinterpret_cast<float4*>(ob + (long long)pix * a.lddx) = make_float4(d[0], d[1], d[2], d[3]);
+        amax = fmaxf(fmaxf(amax, fmaxf(fabsf(d[0]), fabsf(d[1]))), fmaxf(fabsf(d[2]), fabsf(d[3])));
+      }
     }
-    if (ab) { float4 t = *reinterpret_cast<const float4*>(ab + (long long)pix * a.ldadd); d[0] += t.x; d[1] += t.y; d[2] += t.z; d[3] += t.w; }
-    if (ab2) { float4 t = ld4(ab2 + (long long)pix * a.ldadd2); d[0] += t.x; d[1] += t.y; d[2] += t.z; d[3] += t.w; }
-    *reinterpret_cast<float4*>(ob + (long long)pix * a.lddx) = make_float4(d[0], d[1], d[2], d[3]);
-    amax = fmaxf(fmaxf(amax, fmaxf(fabsf(d[0]), fabsf(d[1]))), fmaxf(fabsf(d[2]), fabsf(d[3])));
   }
   if (a.amax_dx) amax_commit(a.amax_dx, amax);
 }
