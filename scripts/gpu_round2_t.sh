@@ -1,6 +1,6 @@
 #!/bin/bash
 # GPU call T: final evidence of round 2 (second session): full GPU suite, smoke(), the default bench line exactly as the driver runs it,
-# the reference arm, the c3 / c5 lines, the ncu launch list of one C1 pass and an `ncu --set full` capture of the GroupNorm kernels
+# the reference arm, the c3 / c5 lines, the ncu launch list of one C1 pass (the `ncu --set full` GroupNorm capture of profiles/r02_ncu_groupnorm.md was the last step of its first run)
 set -u
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -q -m gpu --timeout=600 > gpurun_out/pytest_main.log 2>&1
@@ -33,6 +33,3 @@ PY
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
     --log-file gpurun_out/launches_c1_pass.csv python bench.py --profile-pass --batch 128 > gpurun_out/ncu_launch.log 2>&1
 echo "launch list rc=$?"; python tools/launch_summary.py gpurun_out/launches_c1_pass.csv > gpurun_out/launches_c1_pass.md; head -24 gpurun_out/launches_c1_pass.md
-GN_TIME=0 timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -f -o gpurun_out/r02_gn \
-    python scripts/gpu_prof_gn.py 4 > gpurun_out/ncu_gn.log 2>&1
-echo "gn capture rc=$?"; ls -la gpurun_out/r02_gn.ncu-rep
