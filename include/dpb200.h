@@ -213,7 +213,7 @@ int dp_softmax_bwd(const float* p, const float* dp, float* ds, int64_t rows, int
 typedef struct dp_gn_args {
   int32_t N, HW, C, G;
   float eps;
-  int32_t silu;          /* 1: y = silu(gn(x)) */
+  int32_t silu;          /* 1: y = silu(gn(x)); the sigmoid runs on the special-function unit (ex2.approx + rcp.approx, ~3e-7 relative) */
   const float* x; int64_t ldx;
   float* y; int64_t ldy; /* fwd: output | bwd: unused */
   const float* gamma; const float* beta;
@@ -225,7 +225,9 @@ typedef struct dp_gn_args {
   const float* dx_add2; int64_t ldadd2; /* optional second addend (e.g. the residual branch's dY while dx_add == dx) */
   float* dgamma; float* dbeta;    /* [C], accumulated into (+=) */
   void* workspace;                /* dp_groupnorm_workspace_bytes() */
-  /* dropout folded behind the SiLU (resnet.py:631): keep-mask = hash(seed, element) ; p = 0 disables */
+  /* dropout folded behind the SiLU (resnet.py:631): keep-mask from a counter-based hash of (seed, element index / 4), one 16-bit uniform
+   * per element: keep iff u16 >= round(p * 65536), survivors scaled by 65536 / (65536 - round(p * 65536)); the backward regenerates
+   * the same mask from the element index ; p = 0 disables */
   float dropout_p; uint64_t dropout_seed;
   const uint64_t* dropout_seed_dev; /* optional DEVICE scalar added to dropout_seed (lets a captured CUDA graph
                                        draw a fresh mask every replay) */
