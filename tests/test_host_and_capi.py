@@ -169,3 +169,22 @@ def test_planner_fuses_qkv_and_moves_groupnorm_param_grads_off_the_chain():
     for i, f in enumerate(steps):
         if f.what == "gn bwd":
             assert steps[i + 1].what == "gn bwd param" and getattr(steps[i + 1], "side", 0) == 2 and not getattr(f, "side", 0)
+
+
+def test_groupnorm_param_split_argument_checks():
+    """dp_groupnorm_bwd_param / the `fin` field: validation happens before any launch (no GPU needed; the pointers are never dereferenced
+    on the host).  The one-pixel LayerNorm shapes take dgamma / dbeta from x and dy, so `fin` is refused there."""
+    from diff_pruning_b200 import _lib as L
+    lib = L.load()
+    a = L.GnArgs()
+    fake = 0x10000
+    a.N, a.HW, a.C, a.G, a.eps, a.silu = 64, 1, 320, 1, 1e-5, 0
+    a.x, a.ldx, a.gamma, a.beta, a.mean, a.rstd, a.workspace = fake, 320, fake, fake, fake, fake, fake
+    a.dy, a.lddy, a.dx, a.lddx = fake, 320, fake, 320
+    assert lib.dp_groupnorm_bwd_param(ctypes.byref(a), None) == -5          # no fin
+    a.fin = fake
+    assert lib.dp_groupnorm_bwd(ctypes.byref(a), None) == -3                # LayerNorm rows + fin
+    assert lib.dp_groupnorm_bwd_param(ctypes.byref(a), None) == -3
+    assert lib.dp_groupnorm_bwd_param(None, None) == -5
+    assert lib.dp_copy_rows(None, 4, None, 4, 1, 4, None) == -5
+    assert lib.dp_copy_rows(fake, 2, fake, 4, 1, 4, None) == -1             # row pitch shorter than the row
